@@ -1,0 +1,311 @@
+"""Host-side message model + batch packer.
+
+Mirrors the shapes the reference hot path consumes (go-tdlib `client.Message` /
+`client.FormattedText` / `client.TextEntity`; `youtubemodel.YouTubeVideo`,
+model/youtube/types.go:23-36) and lowers them to the packed columnar batch of include/tgingest.h.
+This is what the Go shim's packer does; here it exists so that tests can be
+written like the reference's own tests (telegramhelper/channel_links_test.go).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import abi
+
+
+def _b(s) -> bytes:
+    if s is None:
+        return b""
+    return s if isinstance(s, (bytes, bytearray)) else str(s).encode("utf-8")
+
+
+@dataclass
+class TextEntity:  # client.TextEntity
+    offset: int
+    length: int
+    type: str = "other"  # "mention" | "url" | "text_url" | anything else
+    url: str | bytes = ""
+
+
+@dataclass
+class FormattedText:  # client.FormattedText
+    text: str | bytes = ""
+    entities: list[TextEntity] = field(default_factory=list)
+
+
+@dataclass
+class Comment:  # model.Comment as GetMessageComments builds it (telegramutils.go:589-635)
+    text: str | bytes = ""
+    reactions: list[tuple[str | bytes, int]] | None = None
+    view_count: int = 0
+    reply_count: int = 0
+    handle: str | bytes = "unknown"
+
+
+@dataclass
+class Message:  # client.Message + pre-resolved RPC results
+    content_type: str = "messageText"  # MessageContentType(); "none" = nil content
+    text: FormattedText | None = None  # Text / Caption
+    alt: str | bytes = ""              # emoji / poll question / prize type / file name / type name
+    media: str | bytes = ""            # remote id that becomes media_url
+    id: int = 1 << 20
+    chat_id: int = -1001234567890
+    date: int = 1_700_000_000
+    media_album_id: int = 0
+    view_count: int = 0
+    share_count: int = 0
+    reactions: list[tuple[str | bytes, int]] = field(default_factory=list)
+    comments: list[Comment] | None = field(default_factory=list)  # None = nil slice
+    handle: str | bytes = "unknown"
+    channel: int = 0
+    panics: bool = False
+
+
+@dataclass
+class Channel:
+    title: str | bytes = "Test Channel"
+    name: str | bytes = "testchannel"       # channelName argument (page URL)
+    username: str | bytes = "testchannel"   # ActiveUsernames[0]; "" = private
+    member_count: int = 0
+    post_count: int = 0
+    view_count: int = 0
+
+
+class TgBatch:
+    """Owns the numpy arrays of one packed Telegram batch and builds the C descriptor."""
+
+    FIELDS = ("recs", "strs", "ent_off", "ents", "react_off", "reacts", "comment_off", "comments",
+              "aux", "chans", "chan_strs")
+
+    def __init__(self, **arrays):
+        for k in self.FIELDS:
+            setattr(self, k, arrays[k])
+        self.n = len(self.recs)
+
+    def descriptor(self) -> abi.TgBatchC:
+        d = abi.TgBatchC()
+        d.n = self.n
+        d.recs = abi.ptr(self.recs)
+        d.strs = abi.ptr(self.strs)
+        d.strs_len = self.strs.size
+        d.ent_off = abi.ptr(self.ent_off)
+        d.ents = abi.ptr(self.ents)
+        d.react_off = abi.ptr(self.react_off)
+        d.reacts = abi.ptr(self.reacts)
+        d.n_reacts = len(self.reacts)
+        d.comment_off = abi.ptr(self.comment_off)
+        d.comments = abi.ptr(self.comments)
+        d.n_comments = len(self.comments)
+        d.aux = abi.ptr(self.aux)
+        d.aux_len = self.aux.size
+        d.n_chans = len(self.chans)
+        d.chans = abi.ptr(self.chans)
+        d.chan_strs = abi.ptr(self.chan_strs)
+        d.chan_strs_len = self.chan_strs.size
+        return d
+
+    def input_bytes(self) -> int:
+        """algorithmic input bytes: every input array read once."""
+        return sum(getattr(self, k).nbytes for k in self.FIELDS)
+
+    def slice(self, a: int, b: int) -> "TgBatch":
+        """records [a,b) as a self-contained batch sharing the channel table and aux blob."""
+        recs = self.recs[a:b].copy()
+        s0 = int(self.recs["str_off"][a]) if a < self.n else self.strs.size
+        s1 = int(self.recs["str_off"][b]) if b < self.n else self.strs.size
+        recs["str_off"] -= s0
+        e0, e1 = int(self.ent_off[a]), int(self.ent_off[b])
+        r0, r1 = int(self.react_off[a]), int(self.react_off[b])
+        c0, c1 = int(self.comment_off[a]), int(self.comment_off[b])
+        # comment reactions live behind the message reactions; keep the whole array for simplicity
+        return TgBatch(recs=recs, strs=self.strs[s0:s1].copy(),
+                       ent_off=(self.ent_off[a:b + 1] - e0).astype(np.uint32),
+                       ents=self.ents[e0:e1].copy(),
+                       react_off=self.react_off[a:b + 1].copy(), reacts=self.reacts,
+                       comment_off=(self.comment_off[a:b + 1] - c0).astype(np.uint32),
+                       comments=self.comments[c0:c1].copy(), aux=self.aux, chans=self.chans,
+                       chan_strs=self.chan_strs)
+
+
+_ENT_TYPES = {"text_url": abi.ENT_TEXT_URL, "mention": abi.ENT_MENTION, "url": abi.ENT_URL}
+
+
+def pack_telegram(messages: list[Message], channels: list[Channel] | None = None) -> TgBatch:
+    channels = channels or [Channel()]
+    n = len(messages)
+    recs = np.zeros(n, abi.TG_REC)
+    strs = bytearray()
+    aux = bytearray()
+    ents, reacts, comments = [], [], []
+    ent_off = np.zeros(n + 1, np.uint32)
+    react_off = np.zeros(n + 1, np.uint32)
+    comment_off = np.zeros(n + 1, np.uint32)
+    comment_reacts: list[tuple[int, list]] = []  # (comment index, reactions)
+    for i, m in enumerate(messages):
+        r = recs[i]
+        ct = abi.CT.get(m.content_type, abi.CT["other"])
+        alt = _b(m.alt)
+        if ct == abi.CT["other"] and not alt:
+            alt = _b(m.content_type)
+        text = _b(m.text.text) if m.text is not None else b""
+        media, handle = _b(m.media), _b(m.handle)
+        flags = 0
+        if m.text is not None:
+            flags |= abi.RF_HAS_TEXT
+        if m.comments is None:
+            flags |= abi.RF_COMMENTS_NIL
+        if m.panics:
+            flags |= abi.RF_PANIC
+        r["id"], r["chat_id"], r["media_album_id"] = m.id, m.chat_id, m.media_album_id
+        r["str_off"] = len(strs)
+        r["date"], r["view_count"], r["share_count"] = m.date, m.view_count, m.share_count
+        r["chan_idx"] = m.channel
+        r["text_len"], r["alt_len"] = len(text), len(alt)
+        r["media_len"], r["handle_len"] = len(media), len(handle)
+        r["content_type"], r["flags"] = ct, flags
+        strs += text + alt + media + handle
+        if m.text is not None:
+            for e in m.text.entities:
+                url = _b(e.url)
+                ents.append((e.offset, e.length, len(aux), len(url), _ENT_TYPES.get(e.type, 0), 0))
+                aux += url
+        ent_off[i + 1] = len(ents)
+        for emoji, cnt in m.reactions:
+            eb = _b(emoji)
+            reacts.append((len(aux), len(eb), 0, cnt))
+            aux += eb
+        react_off[i + 1] = len(reacts)
+        for c in (m.comments or []):
+            tb, hb = _b(c.text), _b(c.handle)
+            comments.append([len(aux), len(tb), len(aux) + len(tb), len(hb),
+                             1 if c.reactions is not None else 0, 0, c.view_count, c.reply_count,
+                             0, 0])
+            aux += tb + hb
+            comment_reacts.append((len(comments) - 1, c.reactions or []))
+        comment_off[i + 1] = len(comments)
+    for ci, rl in comment_reacts:  # comment reactions go after all message reactions
+        comments[ci][8] = len(reacts)
+        comments[ci][9] = len(rl)
+        for emoji, cnt in rl:
+            eb = _b(emoji)
+            reacts.append((len(aux), len(eb), 0, cnt))
+            aux += eb
+    chans = np.zeros(len(channels), abi.TG_CHAN)
+    cstrs = bytearray()
+    for i, ch in enumerate(channels):
+        t, nm, u = _b(ch.title), _b(ch.name), _b(ch.username)
+        chans[i] = (len(cstrs), len(t), len(nm), len(u), 0, 0, ch.member_count, ch.post_count,
+                    ch.view_count)
+        cstrs += t + nm + u
+
+    def arr(lst, dt):
+        a = np.zeros(len(lst), dt)
+        for k, row in enumerate(lst):
+            a[k] = tuple(row)
+        return a
+
+    return TgBatch(recs=recs, strs=_blob(strs), ent_off=ent_off, ents=arr(ents, abi.ENTITY),
+                   react_off=react_off, reacts=arr(reacts, abi.REACTION), comment_off=comment_off,
+                   comments=arr(comments, abi.COMMENT), aux=_blob(aux), chans=chans,
+                   chan_strs=_blob(cstrs))
+
+
+def _blob(b: bytearray | bytes) -> np.ndarray:
+    """uint8 array view with 16 readable pad bytes behind it (kernels may over-read <= 15 bytes)."""
+    full = np.frombuffer(bytes(b) + b"\0" * 16, np.uint8).copy()
+    return full[: len(b)]
+
+
+# ---- YouTube ----------------------------------------------------------------------------------
+@dataclass
+class YouTubeChannel:  # youtubemodel.YouTubeChannel; cached=False -> GetChannelInfo failed
+    id: str | bytes = "UCxxxxxxxxxxxxxxxxxxxxxx"
+    title: str | bytes = ""
+    description: str | bytes = ""
+    thumb_default: str | bytes = ""
+    country: str | bytes = ""
+    subscriber_count: int = 0
+    view_count: int = 0
+    video_count: int = 0
+    published_sec: int = 0
+    published_nsec: int = 0
+    cached: bool = True
+
+
+@dataclass
+class YouTubeVideo:  # youtubemodel.YouTubeVideo
+    id: str | bytes = "dQw4w9WgXcQ"
+    title: str | bytes = ""
+    description: str | bytes = ""
+    published_sec: int = 1_600_000_000
+    published_nsec: int = 0
+    view_count: int = 0
+    like_count: int = 0
+    comment_count: int = 0
+    duration: str | bytes = ""
+    thumbnails: dict[str, str | bytes] = field(default_factory=dict)
+    language: str | bytes = ""
+    channel: int = 0
+
+
+class YtBatch:
+    FIELDS = ("recs", "strs", "chans", "chan_strs")
+
+    def __init__(self, **arrays):
+        for k in self.FIELDS:
+            setattr(self, k, arrays[k])
+        self.n = len(self.recs)
+
+    def descriptor(self) -> abi.YtBatchC:
+        d = abi.YtBatchC()
+        d.n = self.n
+        d.recs = abi.ptr(self.recs)
+        d.strs = abi.ptr(self.strs)
+        d.strs_len = self.strs.size
+        d.n_chans = len(self.chans)
+        d.chans = abi.ptr(self.chans)
+        d.chan_strs = abi.ptr(self.chan_strs)
+        d.chan_strs_len = self.chan_strs.size
+        return d
+
+    def input_bytes(self) -> int:
+        return sum(getattr(self, k).nbytes for k in self.FIELDS)
+
+
+def pack_youtube(videos: list[YouTubeVideo], channels: list[YouTubeChannel] | None = None) -> YtBatch:
+    channels = channels or [YouTubeChannel()]
+    recs = np.zeros(len(videos), abi.YT_REC)
+    strs = bytearray()
+    for i, v in enumerate(videos):
+        r = recs[i]
+        parts = [_b(v.id), _b(v.title), _b(v.description), _b(v.duration), _b(v.language)]
+        r["str_off"] = len(strs)
+        r["published_sec"], r["published_nsec"] = v.published_sec, v.published_nsec
+        r["view_count"], r["like_count"], r["comment_count"] = v.view_count, v.like_count, v.comment_count
+        r["id_len"], r["title_len"], r["desc_len"] = len(parts[0]), len(parts[1]), len(parts[2])
+        r["duration_len"], r["lang_len"] = len(parts[3]), len(parts[4])
+        r["chan_idx"] = v.channel
+        for k, key in enumerate(abi.YT_THUMB_KEYS):
+            if key in v.thumbnails:
+                tb = _b(v.thumbnails[key])
+                r["thumb_len"][k] = len(tb)
+                parts.append(tb)
+            else:
+                r["thumb_len"][k] = abi.YT_THUMB_ABSENT
+        strs += b"".join(parts)
+    chans = np.zeros(len(channels), abi.YT_CHAN)
+    cstrs = bytearray()
+    for i, ch in enumerate(channels):
+        parts = [_b(ch.id), _b(ch.title), _b(ch.description), _b(ch.thumb_default), _b(ch.country)]
+        c = chans[i]
+        c["str_off"] = len(cstrs)
+        c["id_len"], c["title_len"], c["desc_len"] = len(parts[0]), len(parts[1]), len(parts[2])
+        c["thumb_len"], c["country_len"] = len(parts[3]), len(parts[4])
+        c["subscriber_count"], c["view_count"], c["video_count"] = (
+            ch.subscriber_count, ch.view_count, ch.video_count)
+        c["published_sec"], c["published_nsec"], c["cached"] = (
+            ch.published_sec, ch.published_nsec, 1 if ch.cached else 0)
+        cstrs += b"".join(parts)
+    return YtBatch(recs=recs, strs=_blob(strs), chans=chans, chan_strs=_blob(cstrs))
