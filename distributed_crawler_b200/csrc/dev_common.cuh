@@ -1,0 +1,519 @@
+// dev_common.cuh — warp-level building blocks shared by the ingest kernels (sm_100a).
+//
+// Everything here is integer/byte work on HBM-resident packed batches (include/tgingest.h).
+// Convention: functions named warp_* are warp-collective (all 32 lanes call them with
+// warp-uniform arguments unless stated otherwise).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tgingest.h"
+
+#define FULL 0xffffffffu
+#define DEVI __device__ __forceinline__
+
+namespace tgi {
+
+DEVI int lane_id() { return (int)(threadIdx.x & 31); }
+
+// ---- global byte / word loads (read-only path) ---------------------------------------------------
+DEVI uint32_t ldb(const uint8_t* p) { return (uint32_t)__ldg(p); }
+
+// 4 bytes at arbitrary alignment, little-endian; may touch up to 3 bytes past p+3 rounded to a
+// word boundary (device blobs are padded by 32 zero bytes).
+DEVI uint32_t ld_u32_unaligned(const uint8_t* p) {
+  uintptr_t a = (uintptr_t)p;
+  const uint32_t* q = (const uint32_t*)(a & ~(uintptr_t)3);
+  uint32_t sh = (uint32_t)(a & 3) * 8;
+  uint32_t lo = __ldg(q);
+  if (sh == 0) return lo;
+  uint32_t hi = __ldg(q + 1);
+  return __funnelshift_r(lo, hi, sh);
+}
+
+// ---- character classes ---------------------------------------------------------------------------
+DEVI bool is_letter(uint32_t c) { return ((c | 32u) - 'a') < 26u; }
+DEVI bool is_word(uint32_t c) { return is_letter(c) || (c - '0') < 10u || c == '_'; }
+DEVI uint32_t ascii_lower(uint32_t c) { return (c - 'A') < 26u ? c + 32u : c; }
+
+// Go encoding/json (escapeHTML=true, go>=1.22) output length of one ASCII byte: 1, 2 or 6.
+DEVI uint32_t ascii_esc_len(uint32_t b) {
+  if (b >= 0x20) {
+    if (b == '"' || b == '\\') return 2;
+    if (b == '<' || b == '>' || b == '&') return 6;
+    return 1;
+  }
+  const uint32_t two = (1u << 8) | (1u << 9) | (1u << 10) | (1u << 12) | (1u << 13);
+  return ((two >> b) & 1u) ? 2u : 6u;
+}
+
+// ---- exact UTF-8 decoding rules of Go's unicode/utf8 (DecodeRuneInString) -----------------------
+// returns the sequence length (2..4) if a VALID sequence starts at s[i], else 0.  s[i] >= 0x80.
+DEVI int utf8_valid_lead(const uint8_t* s, int64_t i, int64_t n) {
+  uint32_t b0 = ldb(s + i);
+  if (b0 < 0xC2 || b0 > 0xF4) return 0;
+  int need = b0 < 0xE0 ? 2 : (b0 < 0xF0 ? 3 : 4);
+  if (i + need > n) return 0;
+  uint32_t b1 = ldb(s + i + 1);
+  uint32_t lo = 0x80, hi = 0xBF;
+  if (b0 == 0xE0) lo = 0xA0;
+  if (b0 == 0xED) hi = 0x9F;
+  if (b0 == 0xF0) lo = 0x90;
+  if (b0 == 0xF4) hi = 0x8F;
+  if (b1 < lo || b1 > hi) return 0;
+  if (need >= 3 && (ldb(s + i + 2) & 0xC0) != 0x80) return 0;
+  if (need == 4 && (ldb(s + i + 3) & 0xC0) != 0x80) return 0;
+  return need;
+}
+
+// Exact classification of byte i of string s[0..n):
+//   esc : bytes this input byte contributes to the JSON-escaped output (0,1,2,6)
+//   u16 : UTF-16 code units it contributes in utf16OffsetToBytes (tdutils.go:55-78) (0,1,2)
+//   start: 1 if a rune starts here (Go's loop visits this index)
+struct ByteInfo {
+  uint32_t esc, u16, start;
+};
+DEVI ByteInfo byte_info_exact(const uint8_t* s, int64_t i, int64_t n) {
+  ByteInfo r;
+  uint32_t b = ldb(s + i);
+  if (b < 0x80) {
+    r.esc = ascii_esc_len(b);
+    r.u16 = 1;
+    r.start = 1;
+    return r;
+  }
+  if ((b & 0xC0) == 0x80) {  // continuation byte: consumed iff a valid lead precedes it closely enough
+    for (int d = 1; d <= 3; d++) {
+      if (i - d < 0) break;
+      uint32_t p = ldb(s + i - d);
+      if ((p & 0xC0) == 0x80) continue;  // another continuation: keep looking back
+      if (p >= 0xC2) {
+        int need = utf8_valid_lead(s, i - d, n);
+        if (need > d) {  // covered
+          bool ls = (need == 3 && p == 0xE2 && ldb(s + i - d + 1) == 0x80 &&
+                     (ldb(s + i - d + 2) | 1u) == 0xA9);  // U+2028 / U+2029
+          r.esc = ls ? 0 : 1;
+          r.u16 = 0;
+          r.start = 0;
+          return r;
+        }
+      }
+      break;  // nearest non-continuation byte decides
+    }
+    r.esc = 6;
+    r.u16 = 1;
+    r.start = 1;
+    return r;
+  }
+  int need = utf8_valid_lead(s, i, n);
+  if (need == 0) {
+    r.esc = 6;  // �
+    r.u16 = 1;
+    r.start = 1;
+    return r;
+  }
+  bool ls = (need == 3 && b == 0xE2 && ldb(s + i + 1) == 0x80 && (ldb(s + i + 2) | 1u) == 0xA9);
+  r.esc = ls ? 6 : 1;
+  r.u16 = need == 4 ? 2 : 1;
+  r.start = 1;
+  return r;
+}
+
+// ---- warp scans / reductions ---------------------------------------------------------------------
+DEVI uint32_t warp_incl_scan(uint32_t v) {
+  int l = lane_id();
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(FULL, v, d);
+    if (l >= d) v += t;
+  }
+  return v;
+}
+DEVI uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(FULL, v); }
+
+// ---- a strip = 128 consecutive bytes of a string, 4 per lane ------------------------------------
+// Lane l owns bytes [base+4l, base+4l+4).  `w` holds them little-endian with bytes at index >= n
+// forced to 0.  The fast path handles ASCII and every structurally valid UTF-8 sequence whose
+// validity can be decided with SWAR tests (2/3/4-byte leads incl. the E0/ED/F0 second-byte ranges).
+// What is left for the exact per-byte path (byte_info_exact): bytes >= 0xF4, C0/C1, E2 80 xx
+// (U+2028/9 candidates) and any structural mismatch.  `exact` is warp-uniform.
+struct Strip {
+  uint32_t w;       // own 4 bytes
+  uint32_t nvalid;  // how many of them are < n (0..4)
+  bool exact;       // warp-uniform
+  uint32_t cont;    // fast path: continuation-byte mask (bit 7 of each byte)
+  uint32_t l4;      // fast path: 4-byte-lead mask (bit 7 of each byte)
+};
+
+DEVI uint32_t swar_has_byte(uint32_t w, uint32_t c) {  // bit7 of each byte equal to c
+  uint32_t x = w ^ (c * 0x01010101u);
+  return (x - 0x01010101u) & ~x & 0x80808080u;
+}
+
+// carry: structure flags of the previous strip's lane 31 (bit 0: previous strip was exact with a
+// pending sequence, which forces this strip to be exact as well); 0 at string start
+DEVI Strip warp_load_strip(const uint8_t* s, int64_t base, int64_t n, uint32_t& carry) {
+  Strip st;
+  int l = lane_id();
+  int64_t p0 = base + 4 * l;
+  int64_t rem = n - p0;
+  st.nvalid = rem <= 0 ? 0u : (rem >= 4 ? 4u : (uint32_t)rem);
+  uint32_t w = 0;
+  if (st.nvalid) {
+    w = ld_u32_unaligned(s + p0);
+    if (st.nvalid < 4) w &= (1u << (8 * st.nvalid)) - 1u;
+  }
+  st.w = w;
+  uint32_t hi = w & 0x80808080u;
+  st.cont = 0;
+  st.l4 = 0;
+  if (__ballot_sync(FULL, hi != 0) == 0 && carry == 0) {
+    st.exact = false;
+    return st;
+  }
+  const uint32_t M = 0x80808080u;
+  uint32_t c = w & ((~w) << 1) & M;   // 10xxxxxx
+  uint32_t ld = w & (w << 1) & M;     // 11xxxxxx
+  uint32_t l3 = ld & (w << 2);        // 111xxxxx
+  uint32_t l4 = l3 & (w << 3);        // 1111xxxx
+  uint32_t isF0 = swar_has_byte(w, 0xF0), isE2 = swar_has_byte(w, 0xE2), isE0 = swar_has_byte(w, 0xE0),
+           isED = swar_has_byte(w, 0xED);
+  uint32_t P = ld | (l3 >> 1) | (l4 >> 2) | (isF0 >> 3) | (isE2 >> 4) | (isE0 >> 5) | (isED >> 6);
+  uint32_t Pp = __shfl_up_sync(FULL, P, 1);
+  if (l == 0) Pp = carry & ~1u;
+  uint32_t Q = __funnelshift_l(Pp, P, 8);  // byte i of Q = flags of byte i-1
+  uint32_t e1 = Q & M;
+  uint32_t e2 = (__funnelshift_l(Pp, P, 16) << 1) & M;
+  uint32_t e3 = (__funnelshift_l(Pp, P, 24) << 2) & M;
+  uint32_t expect = e1 | e2 | e3;
+  uint32_t pF0 = (Q << 3) & M, pE2 = (Q << 4) & M, pE0 = (Q << 5) & M, pED = (Q << 6) & M;
+  uint32_t b20 = (w << 2) & M;                                  // (b & 0x20) != 0
+  uint32_t nz30 = ((w & 0x30303030u) + 0x70707070u) & M;        // (b & 0x30) != 0
+  uint32_t geF4 = l4 & (((w & 0x0C0C0C0Cu) + 0x7C7C7C7Cu) & M);  // byte >= 0xF4
+  // evaluate one virtual byte past the end too (a lead as the last byte must be flagged)
+  uint32_t chk = st.nvalid >= 4 ? M : (((1u << (8 * (st.nvalid + 1))) - 1u) & M);
+  if (rem < 0) chk = 0;
+  uint32_t bad = ((c ^ expect) & chk) | geF4 | swar_has_byte(w & 0xFEFEFEFEu, 0xC0) | (pF0 & ~nz30) |
+                 (pE0 & ~b20) | (pED & b20) | (pE2 & swar_has_byte(w, 0x80));
+  if (l == 31 && (P & 0x80402000u)) {
+    if (base + 128 >= n) {
+      bad |= 1;  // string ends at the strip end: the open sequence is truncated
+    } else {
+      // a sequence starts in the last bytes of this strip and ends in the next one: its validity
+      // (and the U+2028/9 special case) depends on bytes this strip does not hold -> check it now
+      int64_t pos = p0 + ((P & 0x80000000u) ? 3 : ((P & 0x00400000u) ? 2 : 1));
+      int v = utf8_valid_lead(s, pos, n);
+      bool ls = v == 3 && ldb(s + pos) == 0xE2 && ldb(s + pos + 1) == 0x80 && (ldb(s + pos + 2) | 1u) == 0xA9;
+      if (v == 0 || ls) bad |= 1;
+    }
+  }
+  bool exact = __ballot_sync(FULL, bad != 0) != 0 || (carry & 1u);
+  st.exact = exact;
+  st.cont = c;
+  st.l4 = l4;
+  uint32_t tail = __shfl_sync(FULL, P, 31);
+  // pending = the last bytes open a sequence that continues into the next strip
+  carry = (tail & 0x80402000u) ? ((tail & ~1u) | (exact ? 1u : 0u)) : 0u;
+  return st;
+}
+
+// per-lane totals for the strip: escaped bytes and UTF-16 units of the lane's valid bytes
+DEVI void strip_lane_totals(const Strip& st, const uint8_t* s, int64_t base, int64_t n,
+                            uint32_t& esc, uint32_t& u16) {
+  esc = 0;
+  u16 = 0;
+  if (!st.nvalid) return;
+  if (st.exact) {
+    int64_t p0 = base + 4 * lane_id();
+    for (uint32_t k = 0; k < st.nvalid; k++) {
+      ByteInfo bi = byte_info_exact(s, p0 + k, n);
+      esc += bi.esc;
+      u16 += bi.u16;
+    }
+    return;
+  }
+#pragma unroll
+  for (uint32_t k = 0; k < 4; k++) {
+    if (k < st.nvalid) {
+      uint32_t b = (st.w >> (8 * k)) & 0xFF;
+      esc += b < 0x80 ? ascii_esc_len(b) : 1u;
+    }
+  }
+  u16 = st.nvalid - __popc(st.cont) + __popc(st.l4);
+}
+
+// JSON-escaped length of s[0..n) (without the quotes)
+__device__ __noinline__ uint32_t warp_esc_len(const uint8_t* s, int64_t n) {
+  uint32_t tot = 0, carry = 0;
+  for (int64_t base = 0; base < n; base += 128) {
+    Strip st = warp_load_strip(s, base, n, carry);
+    uint32_t e, u;
+    strip_lane_totals(st, s, base, n, e, u);
+    tot += e;
+  }
+  return warp_sum(tot);
+}
+
+// ---- single-thread number / time rendering (different lanes render different fields) ------------
+__device__ __noinline__ int render_u64(uint8_t* dst, uint64_t v) {
+  uint8_t tmp[20];
+  int n = 0;
+  // peel 9-digit chunks with 32-bit arithmetic
+  while (v >= 1000000000ull) {
+    uint64_t q = v / 1000000000ull;
+    uint32_t r = (uint32_t)(v - q * 1000000000ull);
+    for (int k = 0; k < 9; k++) {
+      tmp[n++] = (uint8_t)('0' + r % 10);
+      r /= 10;
+    }
+    v = q;
+  }
+  uint32_t r = (uint32_t)v;
+  do {
+    tmp[n++] = (uint8_t)('0' + r % 10);
+    r /= 10;
+  } while (r);
+  for (int k = 0; k < n; k++) dst[k] = tmp[n - 1 - k];
+  return n;
+}
+DEVI int render_i64(uint8_t* dst, int64_t v) {
+  if (v < 0) {
+    dst[0] = '-';
+    return 1 + render_u64(dst + 1, (uint64_t)0 - (uint64_t)v);
+  }
+  return render_u64(dst, (uint64_t)v);
+}
+DEVI void put2(uint8_t* d, uint32_t v) {
+  d[0] = (uint8_t)('0' + v / 10);
+  d[1] = (uint8_t)('0' + v % 10);
+}
+// time.Time.MarshalJSON (RFC3339Nano, quoted) for a fixed-offset zone; returns 0 if the year is
+// outside [0,9999] (Marshal error).  dst needs 40 bytes.
+__device__ __noinline__ int render_time(uint8_t* dst, int64_t sec, int32_t nsec, int32_t tz) {
+  int64_t t = sec + tz;
+  int64_t days = t / 86400;
+  int32_t rem = (int32_t)(t - days * 86400);
+  if (rem < 0) {
+    rem += 86400;
+    days -= 1;
+  }
+  int64_t z = days + 719468;
+  int64_t era = (z >= 0 ? z : z - 146096) / 146097;
+  uint32_t doe = (uint32_t)(z - era * 146097);
+  uint32_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+  int64_t y = (int64_t)yoe + era * 400;
+  uint32_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+  uint32_t mp = (5 * doy + 2) / 153;
+  uint32_t d = doy - (153 * mp + 2) / 5 + 1;
+  uint32_t m = mp < 10 ? mp + 3 : mp - 9;
+  if (m <= 2) y += 1;
+  if (y < 0 || y > 9999) return 0;
+  int o = 0;
+  dst[o++] = '"';
+  put2(dst + o, (uint32_t)y / 100);
+  put2(dst + o + 2, (uint32_t)y % 100);
+  o += 4;
+  dst[o++] = '-';
+  put2(dst + o, m);
+  o += 2;
+  dst[o++] = '-';
+  put2(dst + o, d);
+  o += 2;
+  dst[o++] = 'T';
+  put2(dst + o, (uint32_t)rem / 3600);
+  o += 2;
+  dst[o++] = ':';
+  put2(dst + o, (uint32_t)rem % 3600 / 60);
+  o += 2;
+  dst[o++] = ':';
+  put2(dst + o, (uint32_t)rem % 60);
+  o += 2;
+  if (nsec != 0) {
+    uint8_t f[9];
+    uint32_t v = (uint32_t)nsec;
+    for (int k = 8; k >= 0; k--) {
+      f[k] = (uint8_t)('0' + v % 10);
+      v /= 10;
+    }
+    int k = 9;
+    while (k > 0 && f[k - 1] == '0') k--;
+    dst[o++] = '.';
+    for (int j = 0; j < k; j++) dst[o++] = f[j];
+  }
+  if (tz == 0) {
+    dst[o++] = 'Z';
+  } else {
+    uint32_t a = (uint32_t)(tz < 0 ? -tz : tz);
+    dst[o++] = tz < 0 ? '-' : '+';
+    put2(dst + o, a / 3600);
+    o += 2;
+    dst[o++] = ':';
+    put2(dst + o, a % 3600 / 60);
+    o += 2;
+  }
+  dst[o++] = '"';
+  return o;
+}
+
+// ---- output writers ------------------------------------------------------------------------------
+// The record "walkers" (tg_walk.cuh / yt_walk.cuh) are written once against this interface and
+// instantiated with Sizer (pass 1: byte count) and Emitter (pass 2: bytes).  Using the same code
+// for both passes is what guarantees that the scanned offsets and the emitted bytes agree.
+
+struct Sizer {
+  uint64_t total = 0;
+  template <int N>
+  DEVI void lit(const char (&)[N], const uint8_t* /*dev_copy*/) { total += N - 1; }
+  DEVI void raw_smem(const uint8_t*, uint32_t n) { total += n; }
+  DEVI void raw(const uint8_t*, uint32_t n) { total += n; }
+  DEVI void esc(const uint8_t* s, uint32_t n) { total += warp_esc_len(s, n); }
+  DEVI void esc_known(const uint8_t*, uint32_t, uint32_t esc_len) { total += esc_len; }
+  DEVI void ch(uint8_t) { total += 1; }
+};
+
+constexpr int EMIT_CAP = 4096;       // per-warp staging bytes
+constexpr int EMIT_FLUSH_AT = 3072;  // flush when fill exceeds this before a piece (piece <= 1 KiB)
+
+// Per-warp staging buffer in shared memory mapped onto the output stream: buf[i] <-> gout[gbase+i],
+// gbase 16-byte aligned (as an address).  The first `skip` bytes of the buffer belong to the
+// previous warp's range and are never written from here.
+struct Emitter {
+  uint8_t* buf;    // smem, 16-byte aligned, EMIT_CAP bytes
+  uint8_t* gout;   // global output blob
+  uint64_t gbase;  // global byte offset of buf[0]
+  uint32_t fill;   // bytes currently in buf (including the skip region)
+  uint32_t skip;   // leading bytes not owned (only before the first flush)
+
+  DEVI void begin(uint8_t* smem, uint8_t* out, uint64_t start_off) {
+    buf = smem;
+    gout = out;
+    uint64_t addr = (uint64_t)(uintptr_t)out + start_off;
+    skip = (uint32_t)(addr & 15);
+    gbase = start_off - skip;
+    fill = skip;
+  }
+  // write all complete 16-byte chunks; keep the tail
+  __device__ __noinline__ void flush() {
+    __syncwarp();
+    uint32_t nch = fill >> 4;
+    int l = lane_id();
+    for (uint32_t c = l; c < nch; c += 32) {
+      if (c == 0 && skip) {
+        for (uint32_t k = skip; k < 16; k++) gout[gbase + k] = buf[k];
+      } else {
+        uint4 v = *(const uint4*)(buf + 16 * c);
+        *(uint4*)(gout + gbase + 16ull * c) = v;
+      }
+    }
+    __syncwarp();
+    uint32_t tail = fill & 15;
+    uint8_t t = 0;
+    if (nch && (uint32_t)l < tail) t = buf[16 * nch + l];
+    __syncwarp();
+    if (nch) {
+      if ((uint32_t)l < tail) buf[l] = t;
+      gbase += 16ull * nch;
+      fill = tail;
+      skip = 0;
+    }
+    __syncwarp();
+  }
+  DEVI void finish() {  // end of this warp's range: write everything, byte-wise for the tail
+    flush();
+    int l = lane_id();
+    if ((uint32_t)l >= skip && (uint32_t)l < fill) gout[gbase + l] = buf[l];
+    __syncwarp();
+    fill = 0;
+    skip = 0;
+  }
+  DEVI void room() {
+    if (fill > EMIT_FLUSH_AT) flush();
+  }
+  template <int N>
+  DEVI void lit(const char (&)[N], const uint8_t* dev_copy) { raw(dev_copy, N - 1); }
+  DEVI void raw_smem(const uint8_t* s, uint32_t n) {  // n <= 1024, s in shared memory
+    room();
+    for (uint32_t i = lane_id(); i < n; i += 32) buf[fill + i] = s[i];
+    fill += n;
+  }
+  DEVI void raw(const uint8_t* s, uint32_t n) {  // global source, any length
+    for (uint32_t o = 0; o < n; o += 1024) {
+      room();
+      uint32_t m = n - o < 1024 ? n - o : 1024;
+      for (uint32_t i = lane_id(); i < m; i += 32) buf[fill + i] = ldb(s + o + i);
+      fill += m;
+    }
+  }
+  DEVI void ch(uint8_t c) {
+    room();
+    if (lane_id() == 0) buf[fill] = c;
+    fill += 1;
+  }
+  DEVI static void put_escaped(uint8_t* d, uint32_t b, uint32_t len) {
+    const char* hex = "0123456789abcdef";
+    if (len == 1) {
+      d[0] = (uint8_t)b;
+    } else if (len == 2) {
+      d[0] = '\\';
+      uint8_t c = (uint8_t)b;
+      if (b == '\b') c = 'b';
+      else if (b == '\f') c = 'f';
+      else if (b == '\n') c = 'n';
+      else if (b == '\r') c = 'r';
+      else if (b == '\t') c = 't';
+      d[1] = c;
+    } else {
+      d[0] = '\\'; d[1] = 'u'; d[2] = '0'; d[3] = '0';
+      d[4] = (uint8_t)hex[b >> 4];
+      d[5] = (uint8_t)hex[b & 15];
+    }
+  }
+  // JSON-escape s[0..n) into the stream (no quotes)
+  __device__ __noinline__ void esc(const uint8_t* s, uint32_t n) {
+    uint32_t carry = 0;
+    for (int64_t base = 0; base < (int64_t)n; base += 128) {
+      room();  // one strip expands to at most 768 bytes
+      Strip st = warp_load_strip(s, base, n, carry);
+      uint32_t e, u;
+      strip_lane_totals(st, s, base, n, e, u);
+      uint32_t incl = warp_incl_scan(e);
+      uint32_t tot = __shfl_sync(FULL, incl, 31);
+      uint8_t* d = buf + fill + (incl - e);
+      if (st.nvalid) {
+        if (!st.exact) {
+#pragma unroll
+          for (uint32_t k = 0; k < 4; k++) {
+            if (k < st.nvalid) {
+              uint32_t b = (st.w >> (8 * k)) & 0xFF;
+              uint32_t len = b < 0x80 ? ascii_esc_len(b) : 1u;
+              put_escaped(d, b, len);
+              d += len;
+            }
+          }
+        } else {
+          int64_t p0 = base + 4 * lane_id();
+          for (uint32_t k = 0; k < st.nvalid; k++) {
+            ByteInfo bi = byte_info_exact(s, p0 + k, n);
+            uint32_t b = (st.w >> (8 * k)) & 0xFF;
+            if (bi.esc == 6 && b >= 0x80) {
+              if (b == 0xE2 && bi.start && utf8_valid_lead(s, p0 + k, n) == 3) {  // U+2028/9
+                uint32_t last = ldb(s + p0 + k + 2);
+                d[0] = '\\'; d[1] = 'u'; d[2] = '2'; d[3] = '0'; d[4] = '2';
+                d[5] = (uint8_t)(last == 0xA8 ? '8' : '9');
+              } else {  // invalid byte -> �
+                d[0] = '\\'; d[1] = 'u'; d[2] = 'f'; d[3] = 'f'; d[4] = 'f'; d[5] = 'd';
+              }
+            } else if (bi.esc) {
+              put_escaped(d, b, bi.esc);
+            }
+            d += bi.esc;
+          }
+        }
+      }
+      fill += tot;
+    }
+  }
+  DEVI void esc_known(const uint8_t* s, uint32_t n, uint32_t) { esc(s, n); }
+};
+
+}  // namespace tgi

@@ -1,0 +1,503 @@
+// kernels.cuh — __global__ kernels of the ingest engine (sm_100a).  See DESIGN.md for the data
+// layout and the per-kernel roofline model.  All kernels are HBM-bound integer/byte work:
+//   tg_chan_size / tg_chan_emit   per-channel constant strings (once per batch, tiny)
+//   tg_parse      link extraction (K2-K4) + JSONL line length (K6 size), one warp per record
+//   scan_*        exclusive scan u32 -> u64 offsets (K6)
+//   tg_emit       gather-style JSONL emit through per-warp shared-memory staging (K7)
+//   frontier_*    exact open-addressed hash set over 32-byte keys (K5)
+#pragma once
+#include "tg_walk.cuh"
+
+namespace tgi {
+
+constexpr int WARPS_PER_CTA = 8;
+constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+constexpr int EMIT_RECS_PER_WARP = 8;  // contiguous records per warp task in the emit kernel
+
+#define ERR_ARENA_OVERFLOW 1
+#define ERR_TOO_MANY_REACTIONS 2
+#define ERR_FRONTIER_FULL 4
+#define ERR_TOO_MANY_LINKS 8
+
+// ---- channel job -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA_THREADS) tg_chan_size_kernel(TgBatchDev b, ChanDerived* cd, uint32_t* len) {
+  __shared__ WarpScratch ws[WARPS_PER_CTA];
+  int wid = threadIdx.x >> 5;
+  uint32_t c = blockIdx.x * WARPS_PER_CTA + wid;
+  if (c >= b.n_chans) return;
+  uint32_t seg[4];
+  for (int s = 0; s < 4; s++) {
+    Sizer z;
+    walk_tg_chan(z, &ws[wid], b, c, s);
+    seg[s] = (uint32_t)z.total;
+  }
+  if (lane_id() == 0) {
+    ChanDerived d;
+    d.off = 0;
+    d.user_len = seg[0];
+    d.name_len = seg[1];
+    d.title_len = seg[2];
+    d.cdata_len = seg[3];
+    cd[c] = d;
+    len[c] = seg[0] + seg[1] + seg[2] + seg[3];
+  }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) tg_chan_emit_kernel(TgBatchDev b, ChanDerived* cd, const uint64_t* off, uint8_t* blob) {
+  __shared__ WarpScratch ws[WARPS_PER_CTA];
+  __shared__ __align__(16) uint8_t stage[WARPS_PER_CTA][EMIT_CAP];
+  int wid = threadIdx.x >> 5;
+  uint32_t task = blockIdx.x * WARPS_PER_CTA + wid;
+  uint32_t c0 = task * EMIT_RECS_PER_WARP;
+  if (c0 >= b.n_chans) return;
+  uint32_t c1 = min(c0 + (uint32_t)EMIT_RECS_PER_WARP, b.n_chans);
+  Emitter em;
+  em.begin(stage[wid], blob, off[c0]);
+  for (uint32_t c = c0; c < c1; c++) {
+    if (lane_id() == 0) cd[c].off = off[c];
+    for (int s = 0; s < 4; s++) walk_tg_chan(em, &ws[wid], b, c, s);
+  }
+  em.finish();
+}
+
+// ---- parse: status + links + line length ---------------------------------------------------------
+struct ParseOut {
+  uint8_t* status;       // [n]
+  uint32_t* linelen;     // [n]
+  uint32_t* link_start;  // [n] arena index of the record's first link
+  uint32_t* link_count;  // [n]
+  tgi_link* arena;
+  uint32_t arena_cap;
+  uint32_t* cursor;      // arena allocation cursor (keeps counting past arena_cap)
+  int* err;
+};
+
+DEVI TgRecView load_rec_view(const TgBatchDev& b, uint64_t r) {
+  TgRecView v;
+  const tgi_tg_rec* rec = &b.recs[r];
+  v.rec = rec;
+  v.text = b.strs + rec->str_off;
+  v.text_len = rec->text_len;
+  v.alt = v.text + v.text_len;
+  v.alt_len = rec->alt_len;
+  v.media = v.alt + v.alt_len;
+  v.media_len = rec->media_len;
+  v.handle = v.media + v.media_len;
+  v.handle_len = rec->handle_len;
+  v.ct = rec->content_type;
+  v.flags = rec->flags;
+  v.e0 = b.ent_off[r];
+  v.e1 = b.ent_off[r + 1];
+  return v;
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) tg_parse_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) {
+  __shared__ WarpScratch ws[WARPS_PER_CTA];
+  int wid = threadIdx.x >> 5, l = lane_id();
+  uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
+    TgRecView v = load_rec_view(b, r);
+    uint32_t status = TGI_ST_EMITTED, nlinks = 0, lstart = 0, llen = 0;
+    if ((cfg.flags & TGI_CFG_HAS_MIN_POST_DATE) && (int64_t)v.rec->date < cfg.min_post_date) {
+      status = TGI_ST_SKIPPED;  // tdutils.go:419-421
+    } else if (v.flags & TGI_RF_PANIC) {
+      status = TGI_ST_FAILED;
+    } else {
+      if (b.react_off[r + 1] - b.react_off[r] > 32) {
+        if (l == 0) atomicOr(o.err, ERR_TOO_MANY_REACTIONS);
+      }
+      uint32_t ub = warp_link_upper_bound(v, b.ents);
+      if (ub > 4096) {  // seq packing of the frontier needs ordinal < 4096
+        if (l == 0) atomicOr(o.err, ERR_TOO_MANY_LINKS);
+        ub = 0;
+      }
+      bool ok = true;
+      if (ub) {
+        if (l == 0) lstart = atomicAdd(o.cursor, ub);
+        lstart = __shfl_sync(FULL, lstart, 0);
+        if (lstart + ub > o.arena_cap || lstart + ub < lstart) {
+          if (l == 0) atomicOr(o.err, ERR_ARENA_OVERFLOW);
+        } else {
+          const tgi_tg_chan* ch = &b.chans[v.rec->chan_idx];
+          LinkSink ls;
+          ls.out = o.arena + lstart;
+          ls.cap = ub;
+          ls.count = 0;
+          ls.self = b.chan_strs + ch->str_off + ch->title_len;
+          ls.self_len = ch->name_len;
+          ok = warp_extract_links(v, b.ents, b.aux, ls);
+          nlinks = ls.count;
+        }
+      }
+      if (!ok) {
+        status = TGI_ST_FAILED;
+        nlinks = 0;
+      } else if (run_flags & TGI_RUN_JSONL) {
+        TgWalkArgs a;
+        a.b = &b;
+        a.cfg = &cfg;
+        a.r = r;
+        a.v = v;
+        a.links = o.arena + lstart;
+        a.n_links = nlinks;
+        Sizer z;
+        if (walk_tg_record(z, &ws[wid], a)) llen = (uint32_t)z.total;
+        else status = TGI_ST_NOLINE;
+      }
+    }
+    if (l == 0) {
+      o.status[r] = (uint8_t)status;
+      o.linelen[r] = llen;
+      o.link_start[r] = lstart;
+      o.link_count[r] = nlinks;
+    }
+  }
+}
+
+// ---- emit ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA_THREADS) tg_emit_kernel(TgBatchDev b, CfgDev cfg, const uint8_t* status, const uint64_t* line_off,
+                               const uint32_t* link_start, const uint32_t* link_count,
+                               const tgi_link* arena, uint8_t* out) {
+  __shared__ WarpScratch ws[WARPS_PER_CTA];
+  __shared__ __align__(16) uint8_t stage[WARPS_PER_CTA][EMIT_CAP];
+  int wid = threadIdx.x >> 5;
+  uint64_t ntasks = (b.n + EMIT_RECS_PER_WARP - 1) / EMIT_RECS_PER_WARP;
+  uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t task = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; task < ntasks; task += nwarps) {
+    uint64_t r0 = task * EMIT_RECS_PER_WARP;
+    uint64_t r1 = r0 + EMIT_RECS_PER_WARP < b.n ? r0 + EMIT_RECS_PER_WARP : b.n;
+    Emitter em;
+    em.begin(stage[wid], out, line_off[r0]);
+    for (uint64_t r = r0; r < r1; r++) {
+      if (status[r] != TGI_ST_EMITTED) continue;
+      TgWalkArgs a;
+      a.b = &b;
+      a.cfg = &cfg;
+      a.r = r;
+      a.v = load_rec_view(b, r);
+      a.links = arena + link_start[r];
+      a.n_links = link_count[r];
+      walk_tg_record(em, &ws[wid], a);
+    }
+    em.finish();
+  }
+}
+
+// ---- exclusive scan u32 -> u64 (out has n+1 entries) ----------------------------------------------
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint64_t block_reduce_u64(uint64_t v, uint64_t* sm) {
+  for (int d = 16; d; d >>= 1) v += __shfl_down_sync(FULL, v, d);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  uint64_t t = 0;
+  if (threadIdx.x < 32) {
+    t = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0;
+    for (int d = 16; d; d >>= 1) t += __shfl_down_sync(FULL, t, d);
+  }
+  return t;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums_kernel(const uint32_t* in, uint64_t n, uint64_t* tile_sums) {
+  __shared__ uint64_t sm[32];
+  uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+  uint64_t s = 0;
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    uint64_t i = base + (uint64_t)k * SCAN_THREADS + threadIdx.x;
+    if (i < n) s += in[i];
+  }
+  uint64_t t = block_reduce_u64(s, sm);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = t;
+}
+
+// single block: exclusive scan of tile sums in place; total -> out_total
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(uint64_t* tile_sums, uint64_t ntiles, uint64_t* out_total) {
+  __shared__ uint64_t sm[32];
+  __shared__ uint64_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint64_t base = 0; base < ntiles; base += 1024) {
+    uint64_t i = base + threadIdx.x;
+    uint64_t v = i < ntiles ? tile_sums[i] : 0;
+    uint64_t x = v;
+    int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int d = 1; d < 32; d <<= 1) {
+      uint64_t t = __shfl_up_sync(FULL, x, d);
+      if (l >= d) x += t;
+    }
+    if (l == 31) sm[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      uint64_t y = sm[l];
+      for (int d = 1; d < 32; d <<= 1) {
+        uint64_t t = __shfl_up_sync(FULL, y, d);
+        if (l >= d) y += t;
+      }
+      sm[l] = y;
+    }
+    __syncthreads();
+    uint64_t carry = carry_s;
+    uint64_t incl = x + (w ? sm[w - 1] : 0);
+    if (i < ntiles) tile_sums[i] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out_total = carry_s;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const uint32_t* in, uint64_t n, const uint64_t* tile_base,
+                                                               const uint64_t* total, uint64_t* out) {
+  __shared__ uint64_t sm[32];
+  // blocked arrangement: thread t owns items [t*ITEMS, (t+1)*ITEMS) of the tile
+  uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  uint64_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    v[k] = base + k < n ? in[base + k] : 0;
+    s += v[k];
+  }
+  uint64_t x = s;
+  int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int d = 1; d < 32; d <<= 1) {
+    uint64_t t = __shfl_up_sync(FULL, x, d);
+    if (l >= d) x += t;
+  }
+  if (l == 31) sm[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    uint64_t y = l < (SCAN_THREADS >> 5) ? sm[l] : 0;
+    for (int d = 1; d < 32; d <<= 1) {
+      uint64_t t = __shfl_up_sync(FULL, y, d);
+      if (l >= d) y += t;
+    }
+    sm[l] = y;
+  }
+  __syncthreads();
+  uint64_t excl = tile_base[blockIdx.x] + (w ? sm[w - 1] : 0) + x - s;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < n) out[base + k] = excl;
+    excl += v[k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *total;
+}
+
+// ---- frontier: exact hash set of 32-byte keys ------------------------------------------------------
+struct FrontierDev {
+  uint8_t* pool;     // [cap][32] distinct keys in first-occurrence order
+  uint64_t cap;
+  uint64_t* table;   // persistent table: 0 = empty, else (pool_idx+1) | fp << 40
+  uint64_t tmask;
+  uint64_t* count;   // device scalar: number of keys in the pool
+};
+struct FrontierBatch {
+  uint64_t* btable;  // per-batch table: 0 = empty, else ((rec << 12) | ordinal) + 1 (atomicMin'd)
+  uint64_t bmask;
+  uint32_t* lstate;  // per arena slot: LS_* or batch-table slot index
+  uint32_t* rec_new; // [n] new keys first seen in this record
+};
+#define LS_INELIGIBLE 0xFFFFFFFFu
+#define LS_KNOWN 0xFFFFFFFEu
+
+struct Key32 {
+  uint32_t w[8];
+};
+DEVI Key32 load_key(const uint8_t* p) {  // 4-byte aligned
+  Key32 k;
+  const uint32_t* q = (const uint32_t*)p;
+#pragma unroll
+  for (int i = 0; i < 8; i++) k.w[i] = q[i];
+  return k;
+}
+DEVI bool key_eq(const Key32& a, const Key32& b) {
+  uint32_t d = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) d |= a.w[i] ^ b.w[i];
+  return d == 0;
+}
+DEVI uint64_t key_hash(const Key32& k) {
+  uint64_t h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    uint64_t x = (uint64_t)k.w[i] | ((uint64_t)k.w[i + 1] << 32);
+    h = (h ^ x) * 0xFF51AFD7ED558CCDull;
+    h ^= h >> 32;
+  }
+  h *= 0xC4CEB9FE1A85EC53ull;
+  return h ^ (h >> 29);
+}
+
+DEVI bool link_eligible(const tgi_link& lk, uint32_t run_flags) {
+  if ((run_flags & TGI_RUN_SKIP_SELF) && (lk.flags & TGI_LF_SELF)) return false;    // runner.go:1231
+  if ((run_flags & TGI_RUN_FILTER) && !(lk.flags & TGI_LF_FILTER_OK)) return false; // runner.go:1261
+  return true;
+}
+
+// phase 1: probe the persistent set; unseen keys race into the batch table, min sequence wins
+__global__ void frontier_probe_kernel(uint64_t n, const uint32_t* link_start, const uint32_t* link_count,
+                                      const tgi_link* arena, uint32_t run_flags, FrontierDev f, FrontierBatch fb) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  uint32_t cnt = link_count[r];
+  if (!cnt) return;
+  uint32_t ls = link_start ? link_start[r] : (uint32_t)r;
+  for (uint32_t k = 0; k < cnt; k++) {
+    uint32_t idx = ls + k;
+    const tgi_link& lk = arena[idx];
+    if (!link_eligible(lk, run_flags)) {
+      fb.lstate[idx] = LS_INELIGIBLE;
+      continue;
+    }
+    Key32 key = load_key(lk.name);
+    uint64_t h = key_hash(key);
+    uint64_t fp = (h >> 40) | 1ull;  // 24-bit fingerprint, never 0
+    bool known = false;
+    for (uint64_t s = h & f.tmask;; s = (s + 1) & f.tmask) {
+      uint64_t e = f.table[s];
+      if (e == 0) break;
+      if ((e >> 40) == fp) {
+        uint64_t pi = (e & 0xFFFFFFFFFFull) - 1;
+        if (key_eq(key, load_key(f.pool + 32 * pi))) {
+          known = true;
+          break;
+        }
+      }
+    }
+    if (known) {
+      fb.lstate[idx] = LS_KNOWN;
+      continue;
+    }
+    uint64_t v = (((uint64_t)r << 12) | k) + 1;
+    for (uint64_t s = (h >> 7) & fb.bmask;; s = (s + 1) & fb.bmask) {
+      uint64_t cur = fb.btable[s];
+      if (cur == 0) {
+        cur = atomicCAS((unsigned long long*)&fb.btable[s], 0ull, (unsigned long long)v);
+        if (cur == 0) {
+          fb.lstate[idx] = (uint32_t)s;
+          break;
+        }
+      }
+      uint64_t r2 = (cur - 1) >> 12, k2 = (cur - 1) & 4095;
+      uint32_t ls2 = link_start ? link_start[r2] : (uint32_t)r2;
+      if (key_eq(key, load_key(arena[ls2 + k2].name))) {
+        atomicMin((unsigned long long*)&fb.btable[s], (unsigned long long)v);
+        fb.lstate[idx] = (uint32_t)s;
+        break;
+      }
+    }
+  }
+}
+
+// phase 2: per record, how many of its links are the global first occurrence of a new key
+__global__ void frontier_count_kernel(uint64_t n, const uint32_t* link_start, const uint32_t* link_count,
+                                      FrontierBatch fb) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  uint32_t cnt = link_count[r], c = 0;
+  uint32_t ls = link_start ? link_start[r] : (uint32_t)r;
+  for (uint32_t k = 0; k < cnt; k++) {
+    uint32_t st = fb.lstate[ls + k];
+    if (st >= LS_KNOWN) continue;
+    if (fb.btable[st] == (((uint64_t)r << 12) | k) + 1) c++;
+  }
+  fb.rec_new[r] = c;
+}
+
+// phase 3: append the new keys to the pool in (record, ordinal) order and publish them
+__global__ void frontier_append_kernel(uint64_t n, const uint32_t* link_start, const uint32_t* link_count,
+                                       tgi_link* arena, FrontierDev f, FrontierBatch fb,
+                                       const uint64_t* new_off, int* err) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  if (!fb.rec_new[r]) return;
+  uint64_t base = *f.count, total = new_off[n];
+  if (base + total > f.cap) {
+    if (r == 0 || true) atomicOr(err, ERR_FRONTIER_FULL);
+    return;
+  }
+  uint32_t cnt = link_count[r];
+  uint32_t ls = link_start ? link_start[r] : (uint32_t)r;
+  uint64_t pi = base + new_off[r];
+  for (uint32_t k = 0; k < cnt; k++) {
+    uint32_t st = fb.lstate[ls + k];
+    if (st >= LS_KNOWN) continue;
+    if (fb.btable[st] != (((uint64_t)r << 12) | k) + 1) continue;
+    tgi_link& lk = arena[ls + k];
+    Key32 key = load_key(lk.name);
+    uint32_t* dst = (uint32_t*)(f.pool + 32 * pi);
+#pragma unroll
+    for (int i = 0; i < 8; i++) dst[i] = key.w[i];
+    uint64_t h = key_hash(key);
+    uint64_t e = (pi + 1) | (((h >> 40) | 1ull) << 40);
+    for (uint64_t s = h & f.tmask;; s = (s + 1) & f.tmask) {
+      if (f.table[s] == 0 && atomicCAS((unsigned long long*)&f.table[s], 0ull, (unsigned long long)e) == 0) break;
+    }
+    lk.flags |= TGI_LF_NEW;
+    pi++;
+  }
+}
+__global__ void frontier_commit_kernel(FrontierDev f, const uint64_t* new_off, uint64_t n, uint64_t* out_new, int* err) {
+  uint64_t total = new_off[n];
+  if (*f.count + total <= f.cap) {
+    *f.count += total;
+    *out_new = total;
+  } else {
+    *out_new = 0;
+    atomicOr(err, ERR_FRONTIER_FULL);
+  }
+  out_new[1] = *f.count;
+}
+
+// keys32 -> pseudo arena (one link per "record") for tgi_frontier_insert
+__global__ void keys_to_links_kernel(const uint8_t* keys, uint64_t n, tgi_link* arena, uint32_t* link_count) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  tgi_link lk;
+  int len = 0;
+  for (int k = 0; k < 32; k++) {
+    lk.name[k] = keys[32 * i + k];
+    if (lk.name[k]) len = k + 1;
+  }
+  lk.len = (uint8_t)len;
+  lk.src = 0;
+  lk.flags = 0;
+  lk.filter_reason = 0;
+  arena[i] = lk;
+  link_count[i] = 1;
+}
+__global__ void links_new_flags_kernel(const tgi_link* arena, uint64_t n, uint8_t* is_new) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) is_new[i] = (arena[i].flags & TGI_LF_NEW) ? 1 : 0;
+}
+
+// ---- compaction of the per-record links for the host result -----------------------------------------
+__global__ void links_compact_kernel(uint64_t n, const uint32_t* link_start, const uint32_t* link_count,
+                                     const uint64_t* link_off, const tgi_link* arena, tgi_link* out,
+                                     uint32_t* link_off32) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n) return;
+  link_off32[r] = (uint32_t)link_off[r];
+  if (r == n) return;
+  uint32_t cnt = link_count[r];
+  const uint32_t* src = (const uint32_t*)(arena + link_start[r]);
+  uint32_t* dst = (uint32_t*)(out + link_off[r]);
+  for (uint32_t k = 0; k < cnt * 9; k++) dst[k] = src[k];
+}
+
+// FilterUsername over a list of names (tgi_filter_usernames): one warp per name
+__global__ void filter_usernames_kernel(const uint8_t* names, const uint32_t* off, uint64_t n, uint8_t* reason) {
+  uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n) return;
+  int l = lane_id();
+  uint32_t a = off[i], len = off[i + 1] - a;
+  uint32_t c = ((uint32_t)l < len) ? ldb(names + a + l) : 0u;
+  uint32_t res = warp_filter_username(c, len);
+  if (res == TGI_FU_INVALID_CHAR || res == TGI_FU_VALID || res == TGI_FU_BOT_SUFFIX) {
+    // names longer than a warp cannot reach here (len > 32 -> too_long)
+  }
+  if (l == 0) reason[i] = (uint8_t)res;
+}
+
+}  // namespace tgi

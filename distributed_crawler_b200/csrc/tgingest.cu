@@ -1,0 +1,947 @@
+// tgingest.cu — host side of libtgingest: the C ABI of include/tgingest.h on top of the sm_100a
+// kernels in kernels.cuh.  One context = one GPU.  Three staging slots, each with its own stream
+// and worker thread, so H2D of one batch, kernels of another and D2H of a third overlap.
+// There is no CPU fallback: without a CUDA device tgi_create fails with TGI_E_NODEVICE.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace tgi;
+
+namespace {
+
+constexpr size_t PAD = 64;  // zero bytes behind every device blob (kernels over-read <= 16 bytes)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    bytes += PAD;
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    cap = e == cudaSuccess ? want : 0;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return (T*)p; }
+};
+struct HostBuf {  // pinned
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap && p) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    size_t want = bytes + bytes / 8 + 64;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    cap = e == cudaSuccess ? want : 0;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return (T*)p; }
+};
+
+enum JobKind { JOB_NONE = 0, JOB_TG, JOB_TG_RESIDENT, JOB_TG_UPLOAD, JOB_YT, JOB_YT_RESIDENT, JOB_YT_UPLOAD, JOB_QUIT };
+
+struct Slot {
+  int idx = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_mid = nullptr, ev_p0 = nullptr, ev_p1 = nullptr, ev_e0 = nullptr, ev_e1 = nullptr;
+  // device inputs
+  DevBuf d_recs, d_strs, d_ent_off, d_ents, d_react_off, d_reacts, d_comment_off, d_comments, d_aux,
+      d_chans, d_chan_strs;
+  // device intermediates / outputs
+  DevBuf d_chan_derived, d_chan_len, d_chan_off, d_chan_blob, d_status, d_linelen, d_line_off,
+      d_link_start, d_link_count, d_arena, d_lstate, d_rec_new, d_new_off, d_link_off, d_links_out,
+      d_link_off32, d_btable, d_tiles, d_scalars, d_jsonl;
+  // pinned host outputs
+  HostBuf h_status, h_line_off, h_jsonl, h_link_off, h_links, h_scalars;
+  // resident batch descriptor
+  TgBatchDev tg{};
+  uint64_t n_ents = 0, n_reacts = 0, n_comments = 0, in_bytes = 0;
+  bool resident = false;
+  uint64_t dev_jsonl_len = 0;
+  // job hand-off
+  std::mutex mu;
+  std::condition_variable cv;
+  JobKind job = JOB_NONE;
+  bool busy = false, done = false, claimed = false;
+  const tgi_tg_batch* in_tg = nullptr;
+  uint32_t run_flags = 0;
+  int rc = 0;
+  tgi_result res{};
+  std::thread worker;
+};
+
+}  // namespace
+
+struct tgi_ctx {
+  tgi_config cfg{};
+  std::string label;
+  int device = 0;
+  int sms = 148;
+  std::string err;
+  std::mutex err_mu;
+  Slot slots[TGI_SLOTS];
+  // config blob on device
+  DevBuf d_cfg;
+  CfgDev cfgdev{};
+  std::mutex cfg_mu;
+  // frontier
+  DevBuf d_pool, d_table, d_fcount, d_err;
+  FrontierDev fr{};
+  std::mutex fr_mu;
+  cudaEvent_t fr_event = nullptr;
+  bool fr_event_valid = false;
+  // stats
+  std::mutex st_mu;
+  tgi_stats stats{};
+  // slot allocation for the blocking entry points
+  std::mutex alloc_mu;
+  std::condition_variable alloc_cv;
+};
+
+namespace {
+
+std::string g_create_err;
+
+void set_err(tgi_ctx* c, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) {
+    std::lock_guard<std::mutex> g(c->err_mu);
+    c->err = buf;
+  } else {
+    g_create_err = buf;
+  }
+}
+
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t _e = (call);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      set_err(c, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return _e == cudaErrorMemoryAllocation ? TGI_E_NOMEM : TGI_E_CUDA;                \
+    }                                                                                   \
+  } while (0)
+
+// ---- host-side rendering of the injected clock (same rules as render_time on the device) --------
+int host_render_time(char* dst, int64_t sec, int32_t nsec, int32_t tz) {
+  int64_t t = sec + tz;
+  int64_t days = t / 86400, rem = t % 86400;
+  if (rem < 0) { rem += 86400; days -= 1; }
+  int64_t z = days + 719468;
+  int64_t era = (z >= 0 ? z : z - 146096) / 146097;
+  int64_t doe = z - era * 146097;
+  int64_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+  int64_t y = yoe + era * 400;
+  int64_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+  int64_t mp = (5 * doy + 2) / 153;
+  int64_t d = doy - (153 * mp + 2) / 5 + 1;
+  int64_t m = mp < 10 ? mp + 3 : mp - 9;
+  if (m <= 2) y += 1;
+  if (y < 0 || y > 9999) return 0;
+  int o = snprintf(dst, 40, "\"%04d-%02d-%02dT%02d:%02d:%02d", (int)y, (int)m, (int)d, (int)(rem / 3600),
+                   (int)(rem % 3600 / 60), (int)(rem % 60));
+  if (nsec) {
+    char f[16];
+    snprintf(f, sizeof f, "%09d", nsec);
+    int k = 9;
+    while (k > 0 && f[k - 1] == '0') k--;
+    dst[o++] = '.';
+    memcpy(dst + o, f, k);
+    o += k;
+  }
+  if (tz == 0) dst[o++] = 'Z';
+  else {
+    int a = tz < 0 ? -tz : tz;
+    o += snprintf(dst + o, 8, "%c%02d:%02d", tz < 0 ? '-' : '+', a / 3600, a % 3600 / 60);
+  }
+  dst[o++] = '"';
+  return o;
+}
+
+// Builds the per-context constant blob (escaped label + clock strings) and uploads it.  The label
+// is JSON-escaped ON THE DEVICE by the same Emitter code that escapes everything else.
+__global__ void cfg_label_size_kernel(const uint8_t* s, uint32_t n, uint32_t* out) {
+  uint32_t e = warp_esc_len(s, n);
+  if (lane_id() == 0) *out = e;
+}
+__global__ void cfg_label_emit_kernel(const uint8_t* s, uint32_t n, uint8_t* out) {
+  __shared__ __align__(16) uint8_t stage[EMIT_CAP];
+  Emitter em;
+  em.begin(stage, out, 0);
+  em.esc(s, n);
+  em.finish();
+}
+
+int build_cfg_blob(tgi_ctx* c) {
+  const tgi_config& cfg = c->cfg;
+  char t_tg[48], t_yt[48], t_cap[48];
+  int n_tg = host_render_time(t_tg, cfg.created_at_sec, 0, 0);
+  int n_yt = host_render_time(t_yt, cfg.created_at_sec, cfg.created_at_nsec, cfg.tz_offset_sec);
+  int n_cap = host_render_time(t_cap, cfg.capture_sec, cfg.capture_nsec, cfg.tz_offset_sec);
+  cudaStream_t s = c->slots[0].stream;
+  uint32_t n = (uint32_t)c->label.size();
+  DevBuf raw, len;
+  CK(raw.ensure(n));
+  CK(len.ensure(4));
+  CK(cudaMemsetAsync(raw.p, 0, n + PAD, s));
+  if (n) CK(cudaMemcpyAsync(raw.p, c->label.data(), n, cudaMemcpyHostToDevice, s));
+  cfg_label_size_kernel<<<1, 32, 0, s>>>(raw.as<uint8_t>(), n, len.as<uint32_t>());
+  uint32_t esc = 0;
+  CK(cudaMemcpyAsync(&esc, len.p, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  size_t total = (size_t)esc + n_tg + n_yt + n_cap;
+  CK(c->d_cfg.ensure(total + 16));
+  CK(cudaMemsetAsync(c->d_cfg.p, 0, total + 16 + PAD, s));
+  cfg_label_emit_kernel<<<1, 32, 0, s>>>(raw.as<uint8_t>(), n, c->d_cfg.as<uint8_t>());
+  uint8_t* b = c->d_cfg.as<uint8_t>();
+  CK(cudaMemcpyAsync(b + esc, t_tg, n_tg, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(b + esc + n_tg, t_yt, n_yt, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(b + esc + n_tg + n_yt, t_cap, n_cap, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));
+  raw.release();
+  len.release();
+  CfgDev d{};
+  d.blob = b;
+  d.label_len = esc;
+  d.created_tg_len = (uint32_t)n_tg;
+  d.created_yt_len = (uint32_t)n_yt;
+  d.capture_len = (uint32_t)n_cap;
+  d.flags = cfg.flags | ((n_tg == 0 || n_cap == 0) ? CFGDEV_CLOCK_INVALID : 0);
+  d.tz = cfg.tz_offset_sec;
+  d.min_post_date = cfg.min_post_date;
+  c->cfgdev = d;
+  return TGI_OK;
+}
+
+uint64_t next_pow2(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// exclusive scan u32[n] -> u64[n+1]; total also lands in *d_total
+int launch_scan(tgi_ctx* c, Slot& s, const uint32_t* in, uint64_t n, uint64_t* out, uint64_t* d_total, uint32_t& launches) {
+  uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (ntiles == 0) ntiles = 1;
+  CK(s.d_tiles.ensure(ntiles * 8));
+  scan_tile_sums_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, s.stream>>>(in, n, s.d_tiles.as<uint64_t>());
+  scan_tiles_kernel<<<1, 1024, 0, s.stream>>>(s.d_tiles.as<uint64_t>(), ntiles, d_total);
+  scan_apply_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, s.stream>>>(in, n, s.d_tiles.as<uint64_t>(), d_total, out);
+  launches += 3;
+  CK(cudaGetLastError());
+  return TGI_OK;
+}
+
+template <class T>
+int h2d(tgi_ctx* c, Slot& s, DevBuf& d, const T* src, size_t count) {
+  size_t bytes = count * sizeof(T);
+  CK(d.ensure(bytes));
+  if (bytes) CK(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, s.stream));
+  CK(cudaMemsetAsync((uint8_t*)d.p + bytes, 0, PAD, s.stream));
+  s.in_bytes += bytes;
+  return TGI_OK;
+}
+
+int validate_tg(tgi_ctx* c, const tgi_tg_batch* in) {
+  if (!in) { set_err(c, "null batch"); return TGI_E_ARG; }
+  if (in->n && (!in->recs || !in->ent_off || !in->react_off || !in->comment_off || !in->chans)) {
+    set_err(c, "telegram batch: recs/ent_off/react_off/comment_off/chans must be non-null");
+    return TGI_E_ARG;
+  }
+  if (in->n >= (1ull << 40)) { set_err(c, "telegram batch: too many records"); return TGI_E_ARG; }
+  if (!(c->cfg.flags & TGI_CFG_SKIP_MEDIA)) {
+    set_err(c, "TGI_CFG_SKIP_MEDIA is required: media download is an RPC outside this path");
+    return TGI_E_ARG;
+  }
+  return TGI_OK;
+}
+
+int upload_tg(tgi_ctx* c, Slot& s, const tgi_tg_batch* in) {
+  int rc = validate_tg(c, in);
+  if (rc) return rc;
+  uint64_t n = in->n;
+  s.in_bytes = 0;
+  uint64_t n_ents = n ? in->ent_off[n] : 0;
+#define UP(buf, ptr, cnt)                      \
+  rc = h2d(c, s, s.buf, ptr, (size_t)(cnt));   \
+  if (rc) return rc;
+  UP(d_recs, in->recs, n);
+  UP(d_strs, in->strs, in->strs_len);
+  UP(d_ent_off, in->ent_off, n + 1);
+  UP(d_ents, in->ents, n_ents);
+  UP(d_react_off, in->react_off, n + 1);
+  UP(d_reacts, in->reacts, in->n_reacts);
+  UP(d_comment_off, in->comment_off, n + 1);
+  UP(d_comments, in->comments, in->n_comments);
+  UP(d_aux, in->aux, in->aux_len);
+  UP(d_chans, in->chans, in->n_chans);
+  UP(d_chan_strs, in->chan_strs, in->chan_strs_len);
+#undef UP
+  TgBatchDev& b = s.tg;
+  b.n = n;
+  b.recs = s.d_recs.as<tgi_tg_rec>();
+  b.strs = s.d_strs.as<uint8_t>();
+  b.ent_off = s.d_ent_off.as<uint32_t>();
+  b.ents = s.d_ents.as<tgi_entity>();
+  b.react_off = s.d_react_off.as<uint32_t>();
+  b.reacts = s.d_reacts.as<tgi_reaction>();
+  b.comment_off = s.d_comment_off.as<uint32_t>();
+  b.comments = s.d_comments.as<tgi_comment>();
+  b.aux = s.d_aux.as<uint8_t>();
+  b.n_chans = in->n_chans;
+  b.chans = s.d_chans.as<tgi_tg_chan>();
+  b.chan_strs = s.d_chan_strs.as<uint8_t>();
+  s.n_ents = n_ents;
+  s.n_reacts = in->n_reacts;
+  s.n_comments = in->n_comments;
+  s.resident = true;
+  return TGI_OK;
+}
+
+// scalars block (device + pinned mirror): [0] chan total, [1] line total, [2] cursor(u32)+err(int),
+// [3] n_new, [4] frontier size, [5] link total
+enum { SC_CHAN_TOTAL = 0, SC_LINE_TOTAL = 1, SC_CURSOR = 2, SC_NEW = 3, SC_FSIZE = 4, SC_LINK_TOTAL = 5, SC_COUNT = 8 };
+
+int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
+  TgBatchDev& b = s.tg;
+  uint64_t n = b.n;
+  cudaStream_t st = s.stream;
+  uint32_t launches = 0;
+  const bool want_json = flags & TGI_RUN_JSONL, want_links = flags & TGI_RUN_LINKS, want_fr = flags & TGI_RUN_FRONTIER;
+  CfgDev cfg;
+  {
+    std::lock_guard<std::mutex> g(c->cfg_mu);
+    cfg = c->cfgdev;
+  }
+  CK(s.d_scalars.ensure(SC_COUNT * 8));
+  CK(s.h_scalars.ensure(SC_COUNT * 8));
+  uint64_t* dsc = s.d_scalars.as<uint64_t>();
+  uint64_t* hsc = s.h_scalars.as<uint64_t>();
+  CK(s.d_status.ensure(n));
+  CK(s.d_linelen.ensure(n * 4));
+  CK(s.d_line_off.ensure((n + 1) * 8));
+  CK(s.d_link_start.ensure(n * 4));
+  CK(s.d_link_count.ensure(n * 4));
+  uint64_t arena_cap = s.n_ents + n / 2 + 1024;
+  if (s.d_arena.cap / sizeof(tgi_link) > arena_cap + 8) arena_cap = (s.d_arena.cap - PAD) / sizeof(tgi_link);
+
+  CK(cudaEventRecord(s.ev_k0, st));
+  int dev_err = 0;
+  for (int attempt = 0; attempt < 3; attempt++) {
+    CK(s.d_arena.ensure(arena_cap * sizeof(tgi_link)));
+    CK(cudaMemsetAsync(dsc, 0, SC_COUNT * 8, st));
+    if (want_json) {
+      CK(s.d_chan_derived.ensure((size_t)b.n_chans * sizeof(ChanDerived)));
+      CK(s.d_chan_len.ensure((size_t)b.n_chans * 4));
+      CK(s.d_chan_off.ensure(((size_t)b.n_chans + 1) * 8));
+      b.chan_derived = s.d_chan_derived.as<ChanDerived>();
+      unsigned g = (b.n_chans + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+      if (g) {
+        tg_chan_size_kernel<<<g, CTA_THREADS, 0, st>>>(b, s.d_chan_derived.as<ChanDerived>(), s.d_chan_len.as<uint32_t>());
+        launches++;
+      }
+      int rc = launch_scan(c, s, s.d_chan_len.as<uint32_t>(), b.n_chans, s.d_chan_off.as<uint64_t>(), dsc + SC_CHAN_TOTAL, launches);
+      if (rc) return rc;
+    }
+    ParseOut po;
+    po.status = s.d_status.as<uint8_t>();
+    po.linelen = s.d_linelen.as<uint32_t>();
+    po.link_start = s.d_link_start.as<uint32_t>();
+    po.link_count = s.d_link_count.as<uint32_t>();
+    po.arena = s.d_arena.as<tgi_link>();
+    po.arena_cap = (uint32_t)arena_cap;
+    po.cursor = (uint32_t*)(dsc + SC_CURSOR);
+    po.err = (int*)(dsc + SC_CURSOR) + 1;
+    if (n) {
+      uint64_t want = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+      unsigned g = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms * 8);
+      CK(cudaEventRecord(s.ev_p0, st));
+      tg_parse_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
+      CK(cudaEventRecord(s.ev_p1, st));
+      launches++;
+    }
+    if (want_json) {
+      int rc = launch_scan(c, s, s.d_linelen.as<uint32_t>(), n, s.d_line_off.as<uint64_t>(), dsc + SC_LINE_TOTAL, launches);
+      if (rc) return rc;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hsc, dsc, SC_COUNT * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    dev_err = ((int*)(hsc + SC_CURSOR))[1];
+    uint32_t cursor = ((uint32_t*)(hsc + SC_CURSOR))[0];
+    if (dev_err & ERR_ARENA_OVERFLOW) {
+      arena_cap = (uint64_t)cursor + 1024;  // exact demand is known now: rerun the parse
+      continue;
+    }
+    break;
+  }
+  if (dev_err & ERR_ARENA_OVERFLOW) { set_err(c, "link arena overflow persisted"); return TGI_E_CAPACITY; }
+  if (dev_err & ERR_TOO_MANY_REACTIONS) { set_err(c, "a reactions map has more than 32 entries (format limit)"); return TGI_E_ARG; }
+  if (dev_err & ERR_TOO_MANY_LINKS) { set_err(c, "a record has more than 4096 link candidates (format limit)"); return TGI_E_ARG; }
+  uint64_t chan_total = hsc[SC_CHAN_TOTAL], line_total = hsc[SC_LINE_TOTAL];
+  uint32_t arena_used = ((uint32_t*)(hsc + SC_CURSOR))[0];
+
+  if (want_json) {
+    if (c->cfg.max_out_bytes && line_total > c->cfg.max_out_bytes) {
+      set_err(c, "JSONL output %llu bytes exceeds max_out_bytes", (unsigned long long)line_total);
+      return TGI_E_CAPACITY;
+    }
+    CK(s.d_chan_blob.ensure(chan_total));
+    CK(s.d_jsonl.ensure(line_total));
+    b.chan_blob = s.d_chan_blob.as<uint8_t>();
+    unsigned tasks = (b.n_chans + EMIT_RECS_PER_WARP - 1) / EMIT_RECS_PER_WARP;
+    unsigned g = (tasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    if (g) {
+      tg_chan_emit_kernel<<<g, CTA_THREADS, 0, st>>>(b, s.d_chan_derived.as<ChanDerived>(), s.d_chan_off.as<uint64_t>(), s.d_chan_blob.as<uint8_t>());
+      launches++;
+    }
+    if (n) {
+      uint64_t ntasks = (n + EMIT_RECS_PER_WARP - 1) / EMIT_RECS_PER_WARP;
+      uint64_t want = (ntasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+      unsigned ge = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms * 5);
+      CK(cudaEventRecord(s.ev_e0, st));
+      tg_emit_kernel<<<ge, CTA_THREADS, 0, st>>>(b, cfg, s.d_status.as<uint8_t>(), s.d_line_off.as<uint64_t>(),
+                                                s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(),
+                                                s.d_arena.as<tgi_link>(), s.d_jsonl.as<uint8_t>());
+      CK(cudaEventRecord(s.ev_e1, st));
+      launches++;
+    }
+    CK(cudaGetLastError());
+  }
+  s.dev_jsonl_len = want_json ? line_total : 0;
+
+  if (want_fr && n) {
+    // frontier phases of different slots are serialised in submission order
+    std::unique_lock<std::mutex> fg(c->fr_mu);
+    if (c->fr_event_valid) CK(cudaStreamWaitEvent(st, c->fr_event, 0));
+    uint64_t bslots = next_pow2(std::max<uint64_t>(2ull * arena_used, 1024));
+    CK(s.d_btable.ensure(bslots * 8));
+    CK(s.d_lstate.ensure((size_t)arena_cap * 4));
+    CK(s.d_rec_new.ensure(n * 4));
+    CK(s.d_new_off.ensure((n + 1) * 8));
+    CK(cudaMemsetAsync(s.d_btable.p, 0, bslots * 8, st));
+    FrontierBatch fb;
+    fb.btable = s.d_btable.as<uint64_t>();
+    fb.bmask = bslots - 1;
+    fb.lstate = s.d_lstate.as<uint32_t>();
+    fb.rec_new = s.d_rec_new.as<uint32_t>();
+    unsigned g = (unsigned)((n + 255) / 256);
+    frontier_probe_kernel<<<g, 256, 0, st>>>(n, s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(),
+                                             s.d_arena.as<tgi_link>(), flags, c->fr, fb);
+    frontier_count_kernel<<<g, 256, 0, st>>>(n, s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(), fb);
+    launches += 2;
+    int rc = launch_scan(c, s, fb.rec_new, n, s.d_new_off.as<uint64_t>(), dsc + SC_NEW, launches);
+    if (rc) return rc;
+    int* derr = (int*)(dsc + SC_CURSOR) + 1;
+    frontier_append_kernel<<<g, 256, 0, st>>>(n, s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(),
+                                              s.d_arena.as<tgi_link>(), c->fr, fb, s.d_new_off.as<uint64_t>(), derr);
+    frontier_commit_kernel<<<1, 1, 0, st>>>(c->fr, s.d_new_off.as<uint64_t>(), n, dsc + SC_NEW, derr);
+    launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->fr_event, st));
+    c->fr_event_valid = true;
+  }
+  if (want_links) {
+    CK(s.d_link_off.ensure((n + 1) * 8));
+    CK(s.d_link_off32.ensure((n + 1) * 4));
+    int rc = launch_scan(c, s, s.d_link_count.as<uint32_t>(), n, s.d_link_off.as<uint64_t>(), dsc + SC_LINK_TOTAL, launches);
+    if (rc) return rc;
+    CK(s.d_links_out.ensure((size_t)arena_used * sizeof(tgi_link) + 64));
+    unsigned g = (unsigned)((n + 1 + 255) / 256);
+    links_compact_kernel<<<g, 256, 0, st>>>(n, s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(),
+                                            s.d_link_off.as<uint64_t>(), s.d_arena.as<tgi_link>(),
+                                            s.d_links_out.as<tgi_link>(), s.d_link_off32.as<uint32_t>());
+    launches++;
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(s.ev_k1, st));
+  CK(cudaMemcpyAsync(hsc, dsc, SC_COUNT * 8, cudaMemcpyDeviceToHost, st));
+
+  memset(out, 0, sizeof *out);
+  out->n = n;
+  const bool d2h = !(flags & TGI_RUN_NO_D2H);
+  uint64_t n_links_total = 0;
+  if (d2h) {
+    CK(s.h_status.ensure(n + 1));
+    CK(cudaMemcpyAsync(s.h_status.p, s.d_status.p, n, cudaMemcpyDeviceToHost, st));
+    if (want_json) {
+      CK(s.h_line_off.ensure((n + 1) * 8));
+      CK(s.h_jsonl.ensure(line_total + 1));
+      CK(cudaMemcpyAsync(s.h_line_off.p, s.d_line_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+      if (line_total) CK(cudaMemcpyAsync(s.h_jsonl.p, s.d_jsonl.p, line_total, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  CK(cudaStreamSynchronize(st));
+  dev_err = ((int*)(hsc + SC_CURSOR))[1];
+  if (dev_err & ERR_FRONTIER_FULL) { set_err(c, "frontier capacity %llu exceeded", (unsigned long long)c->fr.cap); return TGI_E_CAPACITY; }
+  n_links_total = want_links ? hsc[SC_LINK_TOTAL] : 0;
+  if (d2h && want_links) {
+    CK(s.h_link_off.ensure((n + 1) * 4));
+    CK(s.h_links.ensure(n_links_total * sizeof(tgi_link) + 64));
+    CK(cudaMemcpyAsync(s.h_link_off.p, s.d_link_off32.p, (n + 1) * 4, cudaMemcpyDeviceToHost, st));
+    if (n_links_total) CK(cudaMemcpyAsync(s.h_links.p, s.d_links_out.p, n_links_total * sizeof(tgi_link), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1);
+  out->kernel_ms = ms;
+  out->gpu_launches = launches;
+  out->slot = s.idx;
+  if (n) cudaEventElapsedTime(&out->parse_ms, s.ev_p0, s.ev_p1);
+  if (n && want_json) cudaEventElapsedTime(&out->emit_ms, s.ev_e0, s.ev_e1);
+  out->jsonl_len = want_json ? line_total : 0;
+  out->n_links = n_links_total;
+  out->n_new = want_fr ? hsc[SC_NEW] : 0;
+  out->frontier_size = want_fr ? hsc[SC_FSIZE] : 0;
+  if (d2h) {
+    out->status = s.h_status.as<uint8_t>();
+    if (want_json) {
+      out->jsonl = s.h_jsonl.as<uint8_t>();
+      out->line_off = s.h_line_off.as<uint64_t>();
+    }
+    if (want_links) {
+      out->link_off = s.h_link_off.as<uint32_t>();
+      out->links = s.h_links.as<tgi_link>();
+    }
+  }
+  {
+    std::lock_guard<std::mutex> g(c->st_mu);
+    c->stats.records += n;
+    c->stats.bytes_in += s.in_bytes;
+    c->stats.bytes_out += out->jsonl_len;
+    c->stats.links += n_links_total;
+    c->stats.launches += launches;
+    c->stats.kernel_ms_total += ms;
+    if (want_fr) c->stats.frontier_size = out->frontier_size;
+  }
+  return TGI_OK;
+}
+
+void worker_main(tgi_ctx* c, Slot* s) {
+  cudaSetDevice(c->device);
+  for (;;) {
+    JobKind job;
+    {
+      std::unique_lock<std::mutex> lk(s->mu);
+      s->cv.wait(lk, [&] { return s->job != JOB_NONE; });
+      job = s->job;
+    }
+    if (job == JOB_QUIT) return;
+    int rc = TGI_OK;
+    if (job == JOB_TG || job == JOB_TG_UPLOAD) rc = upload_tg(c, *s, s->in_tg);
+    if (rc == TGI_OK && job == JOB_TG_UPLOAD) {
+      cudaError_t e = cudaStreamSynchronize(s->stream);
+      if (e != cudaSuccess) { set_err(c, "upload sync: %s", cudaGetErrorString(e)); rc = TGI_E_CUDA; }
+    }
+    if (rc == TGI_OK && (job == JOB_TG || job == JOB_TG_RESIDENT)) rc = run_tg(c, *s, s->run_flags, &s->res);
+    if (rc == TGI_OK && (job == JOB_YT || job == JOB_YT_RESIDENT || job == JOB_YT_UPLOAD)) {
+      set_err(c, "youtube path is not built yet in this round");
+      rc = TGI_E_STATE;
+    }
+    {
+      std::lock_guard<std::mutex> lk(s->mu);
+      s->rc = rc;
+      s->job = JOB_NONE;
+      s->done = true;
+    }
+    s->cv.notify_all();
+  }
+}
+
+int post_job(tgi_ctx* c, int slot, JobKind kind, const tgi_tg_batch* in, uint32_t flags) {
+  if (!c) return TGI_E_ARG;
+  if (slot < 0 || slot >= TGI_SLOTS) { set_err(c, "bad slot %d", slot); return TGI_E_ARG; }
+  Slot& s = c->slots[slot];
+  std::lock_guard<std::mutex> lk(s.mu);
+  if (s.busy) { set_err(c, "slot %d is busy (wait/release it first)", slot); return TGI_E_STATE; }
+  if ((kind == JOB_TG_RESIDENT) && !s.resident) { set_err(c, "slot %d holds no resident batch", slot); return TGI_E_STATE; }
+  s.busy = true;
+  s.done = false;
+  s.in_tg = in;
+  s.run_flags = flags;
+  s.job = kind;
+  s.cv.notify_all();
+  return TGI_OK;
+}
+
+int wait_job(tgi_ctx* c, int slot, tgi_result* out) {
+  if (!c || slot < 0 || slot >= TGI_SLOTS) return TGI_E_ARG;
+  Slot& s = c->slots[slot];
+  std::unique_lock<std::mutex> lk(s.mu);
+  if (!s.busy) { set_err(c, "slot %d has no submitted job", slot); return TGI_E_STATE; }
+  s.cv.wait(lk, [&] { return s.done; });
+  if (out) *out = s.res;
+  int rc = s.rc;
+  if (rc != TGI_OK) s.busy = false;  // nothing to release after a failed job
+  return rc;
+}
+
+int claim_slot(tgi_ctx* c) {
+  std::unique_lock<std::mutex> lk(c->alloc_mu);
+  for (;;) {
+    for (int i = 0; i < TGI_SLOTS; i++) {
+      Slot& s = c->slots[i];
+      std::lock_guard<std::mutex> g(s.mu);
+      if (!s.busy && !s.claimed) { s.claimed = true; return i; }
+    }
+    c->alloc_cv.wait(lk);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int tgi_create(const tgi_config* cfg, tgi_ctx** out) {
+  tgi_ctx* c = nullptr;
+  if (!cfg || !out) { set_err(nullptr, "null argument"); return TGI_E_ARG; }
+  if (cfg->abi_version != TGI_ABI_VERSION) { set_err(nullptr, "ABI version mismatch: library %d, caller %u", TGI_ABI_VERSION, cfg->abi_version); return TGI_E_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_err(nullptr, "no CUDA device visible: libtgingest has no CPU fallback");
+    return TGI_E_NODEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { set_err(nullptr, "device %d out of range (%d visible)", cfg->device, ndev); return TGI_E_ARG; }
+  tgi_ctx* ctx = new tgi_ctx();
+  ctx->cfg = *cfg;
+  ctx->label.assign(cfg->crawl_label ? cfg->crawl_label : "", cfg->crawl_label ? cfg->crawl_label_len : 0);
+  ctx->cfg.crawl_label = nullptr;
+  ctx->device = cfg->device;
+  c = ctx;
+  auto fail = [&](int rc) {
+    g_create_err = ctx->err;
+    tgi_destroy(ctx);
+    return rc;
+  };
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { set_err(c, "cudaSetDevice failed"); return fail(TGI_E_CUDA); }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) ctx->sms = prop.multiProcessorCount;
+  for (int i = 0; i < TGI_SLOTS; i++) {
+    Slot& s = ctx->slots[i];
+    s.idx = i;
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&s.ev_k0) != cudaSuccess || cudaEventCreate(&s.ev_k1) != cudaSuccess ||
+        cudaEventCreate(&s.ev_p0) != cudaSuccess || cudaEventCreate(&s.ev_p1) != cudaSuccess ||
+        cudaEventCreate(&s.ev_e0) != cudaSuccess || cudaEventCreate(&s.ev_e1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.ev_mid, cudaEventDisableTiming) != cudaSuccess) {
+      set_err(c, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return fail(TGI_E_CUDA);
+    }
+  }
+  if (cudaEventCreateWithFlags(&ctx->fr_event, cudaEventDisableTiming) != cudaSuccess) { set_err(c, "event creation failed"); return fail(TGI_E_CUDA); }
+  // frontier
+  uint64_t fcap = cfg->frontier_capacity ? cfg->frontier_capacity : (1ull << 22);
+  uint64_t tslots = next_pow2(2 * fcap);
+  if (ctx->d_pool.ensure(fcap * 32) != cudaSuccess || ctx->d_table.ensure(tslots * 8) != cudaSuccess ||
+      ctx->d_fcount.ensure(16) != cudaSuccess) {
+    set_err(c, "frontier allocation failed (%llu keys)", (unsigned long long)fcap);
+    return fail(TGI_E_NOMEM);
+  }
+  cudaMemset(ctx->d_table.p, 0, tslots * 8);
+  cudaMemset(ctx->d_fcount.p, 0, 16);
+  ctx->fr.pool = ctx->d_pool.as<uint8_t>();
+  ctx->fr.cap = fcap;
+  ctx->fr.table = ctx->d_table.as<uint64_t>();
+  ctx->fr.tmask = tslots - 1;
+  ctx->fr.count = ctx->d_fcount.as<uint64_t>();
+  int rc = build_cfg_blob(ctx);
+  if (rc) return fail(rc);
+  for (int i = 0; i < TGI_SLOTS; i++) ctx->slots[i].worker = std::thread(worker_main, ctx, &ctx->slots[i]);
+  *out = ctx;
+  return TGI_OK;
+}
+
+void tgi_destroy(tgi_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  for (int i = 0; i < TGI_SLOTS; i++) {
+    Slot& s = c->slots[i];
+    if (s.worker.joinable()) {
+      {
+        std::unique_lock<std::mutex> lk(s.mu);
+        s.cv.wait(lk, [&] { return s.job == JOB_NONE; });
+        s.job = JOB_QUIT;
+      }
+      s.cv.notify_all();
+      s.worker.join();
+    }
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    DevBuf* db[] = {&s.d_recs, &s.d_strs, &s.d_ent_off, &s.d_ents, &s.d_react_off, &s.d_reacts, &s.d_comment_off,
+                    &s.d_comments, &s.d_aux, &s.d_chans, &s.d_chan_strs, &s.d_chan_derived, &s.d_chan_len,
+                    &s.d_chan_off, &s.d_chan_blob, &s.d_status, &s.d_linelen, &s.d_line_off, &s.d_link_start,
+                    &s.d_link_count, &s.d_arena, &s.d_lstate, &s.d_rec_new, &s.d_new_off, &s.d_link_off,
+                    &s.d_links_out, &s.d_link_off32, &s.d_btable, &s.d_tiles, &s.d_scalars, &s.d_jsonl};
+    for (DevBuf* d : db) d->release();
+    HostBuf* hb[] = {&s.h_status, &s.h_line_off, &s.h_jsonl, &s.h_link_off, &s.h_links, &s.h_scalars};
+    for (HostBuf* h : hb) h->release();
+    if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+    if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+    if (s.ev_mid) cudaEventDestroy(s.ev_mid);
+    for (cudaEvent_t e : {s.ev_p0, s.ev_p1, s.ev_e0, s.ev_e1}) if (e) cudaEventDestroy(e);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  c->d_cfg.release();
+  c->d_pool.release();
+  c->d_table.release();
+  c->d_fcount.release();
+  c->d_err.release();
+  if (c->fr_event) cudaEventDestroy(c->fr_event);
+  delete c;
+}
+
+const char* tgi_last_error(tgi_ctx* c) {
+  if (!c) return g_create_err.c_str();
+  std::lock_guard<std::mutex> g(c->err_mu);
+  return c->err.c_str();
+}
+
+void tgi_get_stats(tgi_ctx* c, tgi_stats* out) {
+  if (!c || !out) return;
+  std::lock_guard<std::mutex> g(c->st_mu);
+  *out = c->stats;
+}
+
+int tgi_set_clock(tgi_ctx* c, int64_t created_at_sec, int32_t created_at_nsec, int64_t capture_sec, int32_t capture_nsec) {
+  if (!c) return TGI_E_ARG;
+  cudaSetDevice(c->device);
+  for (int i = 0; i < TGI_SLOTS; i++) {
+    std::lock_guard<std::mutex> lk(c->slots[i].mu);
+    if (c->slots[i].busy && !c->slots[i].done) { set_err(c, "tgi_set_clock while slot %d is in flight", i); return TGI_E_STATE; }
+  }
+  std::lock_guard<std::mutex> g(c->cfg_mu);
+  c->cfg.created_at_sec = created_at_sec;
+  c->cfg.created_at_nsec = created_at_nsec;
+  c->cfg.capture_sec = capture_sec;
+  c->cfg.capture_nsec = capture_nsec;
+  return build_cfg_blob(c);
+}
+
+int tgi_telegram_submit(tgi_ctx* c, int slot, const tgi_tg_batch* in, uint32_t run_flags) {
+  return post_job(c, slot, JOB_TG, in, run_flags);
+}
+int tgi_telegram_wait(tgi_ctx* c, int slot, tgi_result* out) { return wait_job(c, slot, out); }
+
+void tgi_result_release(tgi_ctx* c, int slot) {
+  if (!c || slot < 0 || slot >= TGI_SLOTS) return;
+  Slot& s = c->slots[slot];
+  {
+    std::lock_guard<std::mutex> lk(s.mu);
+    s.busy = false;
+    s.claimed = false;
+  }
+  c->alloc_cv.notify_all();
+}
+
+int tgi_telegram_batch(tgi_ctx* c, const tgi_tg_batch* in, uint32_t run_flags, tgi_result* out) {
+  if (!c) return TGI_E_ARG;
+  int slot = claim_slot(c);
+  int rc = post_job(c, slot, JOB_TG, in, run_flags);
+  if (rc == TGI_OK) rc = wait_job(c, slot, out);
+  if (rc != TGI_OK) {
+    tgi_result_release(c, slot);
+    return rc;
+  }
+  return TGI_OK;  // result stays valid until tgi_result_release(ctx, out->slot)
+}
+
+int tgi_telegram_upload(tgi_ctx* c, int slot, const tgi_tg_batch* in) {
+  int rc = post_job(c, slot, JOB_TG_UPLOAD, in, 0);
+  if (rc) return rc;
+  rc = wait_job(c, slot, nullptr);
+  tgi_result_release(c, slot);
+  return rc;
+}
+int tgi_telegram_run_resident(tgi_ctx* c, int slot, uint32_t run_flags, tgi_result* out) {
+  int rc = post_job(c, slot, JOB_TG_RESIDENT, nullptr, run_flags);
+  if (rc) return rc;
+  rc = wait_job(c, slot, out);
+  if (rc != TGI_OK) tgi_result_release(c, slot);
+  return rc;
+}
+
+int tgi_result_read_jsonl(tgi_ctx* c, int slot, uint64_t off, uint64_t len, uint8_t* dst) {
+  if (!c || slot < 0 || slot >= TGI_SLOTS || !dst) return TGI_E_ARG;
+  cudaSetDevice(c->device);
+  Slot& s = c->slots[slot];
+  if (off + len > s.dev_jsonl_len) { set_err(c, "read_jsonl out of range"); return TGI_E_ARG; }
+  CK(cudaMemcpy(dst, s.d_jsonl.as<uint8_t>() + off, len, cudaMemcpyDeviceToHost));
+  return TGI_OK;
+}
+
+int tgi_youtube_submit(tgi_ctx* c, int, const tgi_yt_batch*, uint32_t) { set_err(c, "youtube path not built yet"); return TGI_E_STATE; }
+int tgi_youtube_wait(tgi_ctx* c, int, tgi_result*) { set_err(c, "youtube path not built yet"); return TGI_E_STATE; }
+int tgi_youtube_batch(tgi_ctx* c, const tgi_yt_batch*, uint32_t, tgi_result*) { set_err(c, "youtube path not built yet"); return TGI_E_STATE; }
+int tgi_youtube_upload(tgi_ctx* c, int, const tgi_yt_batch*) { set_err(c, "youtube path not built yet"); return TGI_E_STATE; }
+int tgi_youtube_run_resident(tgi_ctx* c, int, uint32_t, tgi_result*) { set_err(c, "youtube path not built yet"); return TGI_E_STATE; }
+
+// ---- frontier host API ------------------------------------------------------------------------------
+static int frontier_insert_impl(tgi_ctx* c, const void* d_keys, uint64_t n, void* d_is_new) {
+  // runs on slot 0's stream under the frontier lock; uses private scratch buffers
+  Slot& s = c->slots[0];
+  cudaStream_t st = s.stream;
+  static thread_local DevBuf arena, cnt, lstate, recnew, newoff, btable, tiles, sc;
+  uint32_t launches = 0;
+  std::unique_lock<std::mutex> fg(c->fr_mu);
+  if (c->fr_event_valid) CK(cudaStreamWaitEvent(st, c->fr_event, 0));
+  CK(arena.ensure(n * sizeof(tgi_link)));
+  CK(cnt.ensure(n * 4));
+  CK(lstate.ensure(n * 4));
+  CK(recnew.ensure(n * 4));
+  CK(newoff.ensure((n + 1) * 8));
+  CK(sc.ensure(64));
+  uint64_t bslots = next_pow2(std::max<uint64_t>(2 * n, 1024));
+  CK(btable.ensure(bslots * 8));
+  CK(cudaMemsetAsync(btable.p, 0, bslots * 8, st));
+  CK(cudaMemsetAsync(sc.p, 0, 64, st));
+  unsigned g = (unsigned)((n + 255) / 256);
+  if (!g) g = 1;
+  keys_to_links_kernel<<<g, 256, 0, st>>>((const uint8_t*)d_keys, n, arena.as<tgi_link>(), cnt.as<uint32_t>());
+  FrontierBatch fb;
+  fb.btable = btable.as<uint64_t>();
+  fb.bmask = bslots - 1;
+  fb.lstate = lstate.as<uint32_t>();
+  fb.rec_new = recnew.as<uint32_t>();
+  frontier_probe_kernel<<<g, 256, 0, st>>>(n, nullptr, cnt.as<uint32_t>(), arena.as<tgi_link>(), 0, c->fr, fb);
+  frontier_count_kernel<<<g, 256, 0, st>>>(n, nullptr, cnt.as<uint32_t>(), fb);
+  // scan with private tile buffer
+  {
+    uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (!ntiles) ntiles = 1;
+    CK(tiles.ensure(ntiles * 8));
+    scan_tile_sums_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(fb.rec_new, n, tiles.as<uint64_t>());
+    scan_tiles_kernel<<<1, 1024, 0, st>>>(tiles.as<uint64_t>(), ntiles, sc.as<uint64_t>());
+    scan_apply_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(fb.rec_new, n, tiles.as<uint64_t>(), sc.as<uint64_t>(), newoff.as<uint64_t>());
+  }
+  int* derr = (int*)(sc.as<uint64_t>() + 4);
+  frontier_append_kernel<<<g, 256, 0, st>>>(n, nullptr, cnt.as<uint32_t>(), arena.as<tgi_link>(), c->fr, fb, newoff.as<uint64_t>(), derr);
+  frontier_commit_kernel<<<1, 1, 0, st>>>(c->fr, newoff.as<uint64_t>(), n, sc.as<uint64_t>() + 1, derr);
+  if (d_is_new) links_new_flags_kernel<<<g, 256, 0, st>>>(arena.as<tgi_link>(), n, (uint8_t*)d_is_new);
+  (void)launches;
+  CK(cudaGetLastError());
+  int herr = 0;
+  CK(cudaMemcpyAsync(&herr, derr, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(c->fr_event, st));
+  c->fr_event_valid = true;
+  CK(cudaStreamSynchronize(st));
+  if (herr & ERR_FRONTIER_FULL) { set_err(c, "frontier capacity %llu exceeded", (unsigned long long)c->fr.cap); return TGI_E_CAPACITY; }
+  return TGI_OK;
+}
+
+int tgi_frontier_insert(tgi_ctx* c, const uint8_t* keys32, uint64_t n, uint8_t* is_new) {
+  if (!c || (n && !keys32)) return TGI_E_ARG;
+  if (n >= (1ull << 32)) { set_err(c, "too many keys in one call"); return TGI_E_ARG; }
+  cudaSetDevice(c->device);
+  if (!n) return TGI_OK;
+  DevBuf dk, dn;
+  CK(dk.ensure(n * 32));
+  CK(dn.ensure(n));
+  CK(cudaMemcpy(dk.p, keys32, n * 32, cudaMemcpyHostToDevice));
+  int rc = frontier_insert_impl(c, dk.p, n, dn.p);
+  if (rc == TGI_OK && is_new) CK(cudaMemcpy(is_new, dn.p, n, cudaMemcpyDeviceToHost));
+  dk.release();
+  dn.release();
+  return rc;
+}
+int tgi_frontier_insert_dev(tgi_ctx* c, const void* d_keys32, uint64_t n, void* d_is_new) {
+  if (!c || (n && !d_keys32)) return TGI_E_ARG;
+  cudaSetDevice(c->device);
+  if (!n) return TGI_OK;
+  return frontier_insert_impl(c, d_keys32, n, d_is_new);
+}
+int tgi_frontier_sync(tgi_ctx* c) {
+  if (!c) return TGI_E_ARG;
+  cudaSetDevice(c->device);
+  std::lock_guard<std::mutex> g(c->fr_mu);
+  if (c->fr_event_valid) CK(cudaEventSynchronize(c->fr_event));
+  return TGI_OK;
+}
+int tgi_frontier_size(tgi_ctx* c, uint64_t* n) {
+  if (!c || !n) return TGI_E_ARG;
+  int rc = tgi_frontier_sync(c);
+  if (rc) return rc;
+  CK(cudaMemcpy(n, c->fr.count, 8, cudaMemcpyDeviceToHost));
+  return TGI_OK;
+}
+int tgi_frontier_export(tgi_ctx* c, uint8_t* keys32, uint64_t cap, uint64_t* n) {
+  if (!c || !n) return TGI_E_ARG;
+  uint64_t sz = 0;
+  int rc = tgi_frontier_size(c, &sz);
+  if (rc) return rc;
+  uint64_t m = sz < cap ? sz : cap;
+  if (m && keys32) CK(cudaMemcpy(keys32, c->fr.pool, m * 32, cudaMemcpyDeviceToHost));
+  *n = sz;
+  return TGI_OK;
+}
+int tgi_frontier_export_dev(tgi_ctx* c, void* d_keys32, uint64_t cap, uint64_t first, uint64_t* n) {
+  if (!c || !n) return TGI_E_ARG;
+  uint64_t sz = 0;
+  int rc = tgi_frontier_size(c, &sz);
+  if (rc) return rc;
+  uint64_t avail = first < sz ? sz - first : 0;
+  uint64_t m = avail < cap ? avail : cap;
+  if (m && d_keys32) CK(cudaMemcpy(d_keys32, c->fr.pool + 32 * first, m * 32, cudaMemcpyDeviceToDevice));
+  *n = m;
+  return TGI_OK;
+}
+int tgi_frontier_clear(tgi_ctx* c) {
+  if (!c) return TGI_E_ARG;
+  int rc = tgi_frontier_sync(c);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> g(c->fr_mu);
+  CK(cudaMemset(c->fr.table, 0, (c->fr.tmask + 1) * 8));
+  CK(cudaMemset(c->fr.count, 0, 8));
+  return TGI_OK;
+}
+
+int tgi_filter_usernames(tgi_ctx* c, const uint8_t* names, const uint32_t* off, uint64_t n, uint8_t* reason) {
+  if (!c || !off || !reason) return TGI_E_ARG;
+  cudaSetDevice(c->device);
+  if (!n) return TGI_OK;
+  DevBuf dn, doff, dr;
+  uint32_t total = off[n];
+  CK(dn.ensure(total));
+  CK(doff.ensure((n + 1) * 4));
+  CK(dr.ensure(n));
+  CK(cudaMemset(dn.p, 0, total + PAD));
+  if (total) CK(cudaMemcpy(dn.p, names, total, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(doff.p, off, (n + 1) * 4, cudaMemcpyHostToDevice));
+  unsigned g = (unsigned)((n * 32 + 255) / 256);
+  filter_usernames_kernel<<<g, 256>>>(dn.as<uint8_t>(), doff.as<uint32_t>(), n, dr.as<uint8_t>());
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(reason, dr.p, n, cudaMemcpyDeviceToHost));
+  dn.release();
+  doff.release();
+  dr.release();
+  return TGI_OK;
+}
+
+}  // extern "C"

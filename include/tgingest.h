@@ -286,6 +286,10 @@ typedef struct tgi_result {
   uint64_t frontier_size;   /* distinct names after this call                                     */
   float kernel_ms;          /* device time of the kernels of this call (CUDA events)              */
   uint32_t gpu_launches;    /* kernels launched by this call                                      */
+  float parse_ms;           /* device time of the parse (link extraction + size) kernel           */
+  float emit_ms;            /* device time of the JSONL emit kernel                               */
+  int32_t slot;             /* staging slot that owns the buffers: pass to tgi_result_release     */
+  uint32_t reserved;
 } tgi_result;
 
 typedef struct tgi_stats {
@@ -301,6 +305,7 @@ void tgi_destroy(tgi_ctx* ctx);
 const char* tgi_last_error(tgi_ctx* ctx); /* ctx may be NULL: last create error                   */
 void tgi_get_stats(tgi_ctx* ctx, tgi_stats* out);
 /* injected clock can change per channel batch (tdutils.go:611,715 call time.Now per message).    */
+/* must not be called while a job is in flight on any slot (returns TGI_E_STATE)                  */
 int tgi_set_clock(tgi_ctx* ctx, int64_t created_at_sec, int32_t created_at_nsec, int64_t capture_sec,
                   int32_t capture_nsec);
 
@@ -309,7 +314,8 @@ int tgi_set_clock(tgi_ctx* ctx, int64_t created_at_sec, int32_t created_at_nsec,
  * json.Marshal+'\n' (state/storageproviders.go:276-282, state/daprstate.go:1118-1120) for a whole
  * slice of messages in one call.  `slot` selects one of TGI_SLOTS independent staging slots so
  * calls from different goroutines / pipelined calls overlap (H2D, kernels and D2H on the slot's
- * stream).  tgi_telegram_batch = submit + wait.                                                  */
+ * stream).  Inputs must stay valid until the matching wait returns.  tgi_telegram_batch = claim a
+ * free slot + submit + wait; its result is released with tgi_result_release(ctx, out->slot).     */
 #define TGI_SLOTS 3
 int tgi_telegram_submit(tgi_ctx* ctx, int slot, const tgi_tg_batch* in, uint32_t run_flags);
 int tgi_telegram_wait(tgi_ctx* ctx, int slot, tgi_result* out);

@@ -464,10 +464,30 @@ static int fset_insert(fset_t* f, const uint8_t* k) {
   return 1;
 }
 
+/* per-thread scratch + result arrays are owned by the context and only grow: after one warm-up call
+ * a batch of the same size touches no fresh pages (first-touch page faults would otherwise dominate
+ * the timed CPU baseline). */
+typedef struct work work_t;
+struct work {
+  const orc_ctx* c;
+  const tgi_tg_batch* tg;
+  const tgi_yt_batch* yt;
+  uint64_t r0, r1;
+  uint32_t run_flags;
+  buf_t json;        /* lines of this range */
+  buf_t links;       /* tgi_link[] */
+  buf_t b_linelen, b_status, b_nlinks, b_tmp, scratch;
+  uint64_t* linelen; /* [r1-r0] */
+  uint8_t* status;   /* [r1-r0] */
+  uint32_t* nlinks;  /* [r1-r0] */
+};
 struct orc_ctx {
   tgi_config cfg;
   char* label;
   fset_t fs;
+  work_t* w;
+  int nw;
+  buf_t r_status, r_jsonl, r_line_off, r_link_off, r_links;
 };
 
 orc_ctx* orc_create(const tgi_config* cfg) {
@@ -480,6 +500,13 @@ orc_ctx* orc_create(const tgi_config* cfg) {
 }
 void orc_destroy(orc_ctx* c) {
   if (!c) return;
+  for (int t = 0; t < c->nw; t++) {
+    work_t* w = &c->w[t];
+    free(w->json.p); free(w->links.p); free(w->b_linelen.p); free(w->b_status.p); free(w->b_nlinks.p);
+    free(w->b_tmp.p); free(w->scratch.p);
+  }
+  free(c->w);
+  free(c->r_status.p); free(c->r_jsonl.p); free(c->r_line_off.p); free(c->r_link_off.p); free(c->r_links.p);
   free(c->label);
   free(c->fs.keys);
   free(c->fs.slots);
@@ -986,33 +1013,23 @@ static int yt_record(const orc_ctx* c, const tgi_yt_batch* b, uint64_t r, buf_t*
 
 /* ------------------------------------------------------------------------------------------- */
 /* batch drivers                                                                                 */
-typedef struct {
-  const orc_ctx* c;
-  const tgi_tg_batch* tg;
-  const tgi_yt_batch* yt;
-  uint64_t r0, r1;
-  uint32_t run_flags;
-  buf_t json;        /* lines of this range */
-  uint64_t* linelen; /* [r1-r0] */
-  uint8_t* status;   /* [r1-r0] */
-  buf_t links;       /* tgi_link[] */
-  uint32_t* nlinks;  /* [r1-r0] */
-} work_t;
 
 #define ORC_MAX_LINKS 4096
 
 static void* worker(void* arg) {
   work_t* w = (work_t*)arg;
   uint64_t m = w->r1 - w->r0;
-  w->linelen = (uint64_t*)calloc(m ? m : 1, sizeof(uint64_t));
-  w->status = (uint8_t*)calloc(m ? m : 1, 1);
-  w->nlinks = (uint32_t*)calloc(m ? m : 1, sizeof(uint32_t));
-  tgi_link* tmp = (tgi_link*)malloc(sizeof(tgi_link) * ORC_MAX_LINKS);
-  buf_t scratch = {0};
+  w->json.len = w->links.len = w->b_linelen.len = w->b_status.len = w->b_nlinks.len = w->b_tmp.len = 0;
+  buf_reserve(&w->b_linelen, (m + 1) * 8); w->linelen = (uint64_t*)w->b_linelen.p;
+  buf_reserve(&w->b_status, m + 1); w->status = w->b_status.p;
+  buf_reserve(&w->b_nlinks, (m + 1) * 4); w->nlinks = (uint32_t*)w->b_nlinks.p;
+  buf_reserve(&w->b_tmp, sizeof(tgi_link) * ORC_MAX_LINKS);
+  tgi_link* tmp = (tgi_link*)w->b_tmp.p;
   for (uint64_t r = w->r0; r < w->r1; r++) {
     linkset_t ls = {tmp, 0, ORC_MAX_LINKS, 0};
-    buf_t* o = (w->run_flags & TGI_RUN_JSONL) ? &w->json : &scratch;
-    scratch.len = 0;
+    buf_t* o = (w->run_flags & TGI_RUN_JSONL) ? &w->json : &w->scratch;
+    w->scratch.len = 0;
+    w->nlinks[r - w->r0] = 0;
     size_t before = o->len;
     int st = w->tg ? tg_record(w->c, w->tg, r, o, &ls) : yt_record(w->c, w->yt, r, o, &ls);
     w->status[r - w->r0] = (uint8_t)st;
@@ -1035,8 +1052,6 @@ static void* worker(void* arg) {
       w->nlinks[r - w->r0] = (uint32_t)ls.n;
     }
   }
-  free(tmp);
-  free(scratch.p);
   return NULL;
 }
 
@@ -1045,7 +1060,12 @@ static int run_batch(orc_ctx* c, const tgi_tg_batch* tg, const tgi_yt_batch* yt,
   uint64_t n = tg ? tg->n : yt->n;
   if (nthreads < 1) nthreads = 1;
   if ((uint64_t)nthreads > n) nthreads = n ? (int)n : 1;
-  work_t* w = (work_t*)calloc((size_t)nthreads, sizeof(work_t));
+  if (c->nw < nthreads) {
+    c->w = (work_t*)realloc(c->w, sizeof(work_t) * (size_t)nthreads);
+    memset(c->w + c->nw, 0, sizeof(work_t) * (size_t)(nthreads - c->nw));
+    c->nw = nthreads;
+  }
+  work_t* w = c->w;
   pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
   for (int t = 0; t < nthreads; t++) {
     w[t].c = c; w[t].tg = tg; w[t].yt = yt; w[t].run_flags = run_flags;
@@ -1058,13 +1078,14 @@ static int run_batch(orc_ctx* c, const tgi_tg_batch* tg, const tgi_yt_batch* yt,
     for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
   memset(out, 0, sizeof *out);
   out->n = n;
-  out->status = (uint8_t*)malloc(n ? n : 1);
-  out->line_off = (uint64_t*)malloc(sizeof(uint64_t) * (n + 1));
-  out->link_off = (uint32_t*)malloc(sizeof(uint32_t) * (n + 1));
   uint64_t jl = 0, nl = 0;
   for (int t = 0; t < nthreads; t++) { jl += w[t].json.len; nl += w[t].links.len / sizeof(tgi_link); }
-  out->jsonl = (uint8_t*)malloc(jl ? jl : 1);
-  out->links = (tgi_link*)malloc(sizeof(tgi_link) * (nl ? nl : 1));
+  c->r_status.len = c->r_jsonl.len = c->r_line_off.len = c->r_link_off.len = c->r_links.len = 0;
+  buf_reserve(&c->r_status, n + 1); out->status = c->r_status.p;
+  buf_reserve(&c->r_line_off, 8 * (n + 1)); out->line_off = (uint64_t*)c->r_line_off.p;
+  buf_reserve(&c->r_link_off, 4 * (n + 1)); out->link_off = (uint32_t*)c->r_link_off.p;
+  buf_reserve(&c->r_jsonl, jl + 1); out->jsonl = c->r_jsonl.p;
+  buf_reserve(&c->r_links, sizeof(tgi_link) * (nl + 1)); out->links = (tgi_link*)c->r_links.p;
   uint64_t jo = 0, lo = 0;
   for (int t = 0; t < nthreads; t++) {
     memcpy(out->jsonl + jo, w[t].json.p, w[t].json.len);
@@ -1079,7 +1100,6 @@ static int run_batch(orc_ctx* c, const tgi_tg_batch* tg, const tgi_yt_batch* yt,
     }
     jo += w[t].json.len;
     lo += w[t].links.len / sizeof(tgi_link);
-    free(w[t].json.p); free(w[t].links.p); free(w[t].linelen); free(w[t].status); free(w[t].nlinks);
   }
   out->line_off[n] = jo;
   out->link_off[n] = (uint32_t)lo;
@@ -1095,7 +1115,6 @@ static int run_batch(orc_ctx* c, const tgi_tg_batch* tg, const tgi_yt_batch* yt,
     }
   }
   out->frontier_size = c->fs.n;
-  free(w);
   free(th);
   return 0;
 }
@@ -1108,7 +1127,6 @@ int orc_youtube_batch(orc_ctx* c, const tgi_yt_batch* in, uint32_t run_flags, in
                       orc_result* out) {
   return run_batch(c, NULL, in, run_flags, nthreads, out);
 }
-void orc_result_free(orc_result* r) {
-  free(r->status); free(r->jsonl); free(r->line_off); free(r->link_off); free(r->links);
+void orc_result_free(orc_result* r) { /* arrays are context-owned; valid until the next batch call */
   memset(r, 0, sizeof *r);
 }

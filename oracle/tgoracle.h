@@ -27,7 +27,7 @@ extern "C" {
 
 typedef struct orc_ctx orc_ctx; /* holds config + the frontier set */
 
-typedef struct orc_result { /* all arrays malloc'd; free with orc_result_free */
+typedef struct orc_result { /* arrays are owned by the orc_ctx, valid until its next batch call */
   uint64_t n;
   uint8_t* status;
   uint8_t* jsonl;
