@@ -1,0 +1,341 @@
+#!/usr/bin/env python3
+"""bench.py — messages/sec through the hot path (parse -> link-extract -> filter/dedup -> JSONL).
+
+Contract (see the task statement):  python bench.py --gpus N --steps K --warmup W [--impl reference]
+  * N = 1 workload: BASELINE.json configs[1] — 10 M synthetic Telegram mixed text/photo/video-metadata
+    messages, parse + JSONL on 1 x B200.  N > 1: weak scaling, every rank takes its own 10 M-message
+    shard of the same generator (record-index sharding, no data-path collective) and the ranks merge
+    their dedup sets with one NCCL all-gather per step.
+  * value  = whole-job messages/s with the packed batch already resident in HBM (kernels only).
+  * e2e    = the same metric through the public C ABI call with HOST buffers: pinned-host -> device
+    copy of every input array and device -> pinned-host copy of the JSONL blob, line offsets and
+    status inside the timed region, pipelined over the library's three staging slots.
+  * roofline: the dominant kernel (tg_emit_kernel) — algorithmic bytes per launch / its CUDA-event
+    duration measured live on the launching stream, against MEASURED_PEAKS.json.
+  * cpu_baseline / --impl reference: the CPU oracle (C restatement of the reference's Go path — the
+    reference itself cannot be built here, there is no Go toolchain) on the box's host cores.
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_MESSAGES = int(os.environ.get("TGI_BENCH_N", 10_000_000))   # configs[1]
+E2E_CHUNK = int(os.environ.get("TGI_BENCH_CHUNK", 500_000))   # records per C-ABI call in the e2e leg
+CPU_SAMPLE = int(os.environ.get("TGI_BENCH_CPU_SAMPLE", 2_000_000))
+SEED = 0x5EED0002
+METRIC = "messages/sec parsed+link-extracted+JSONL"
+UNIT = "messages/s"
+
+
+def ensure_built():
+    import __graft_entry__ as g
+    need = [os.path.join(ROOT, "distributed_crawler_b200", "libtgingest.so"),
+            os.path.join(ROOT, "corpus", "libtgcorpus.so"), os.path.join(ROOT, "oracle", "libtgoracle.so")]
+    if not all(os.path.exists(p) for p in need):
+        g.build()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.p = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic():
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+def pin(batch):
+    """page-lock the corpus arrays so the e2e leg's H2D copies come from pinned host memory"""
+    import torch
+    rt = torch.cuda.cudart()
+    pinned = 0
+    for k in batch.FIELDS:
+        a = getattr(batch, k)
+        if a.nbytes:
+            rc = rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+            if int(rc) == 0:
+                pinned += a.nbytes
+    return pinned
+
+
+def cpu_baseline(batch, nthreads: int, sample: int, flags: int):
+    from oracle.pyoracle import Oracle
+    sub = batch.slice(0, min(sample, batch.n))
+    o = Oracle()
+    o.telegram(sub, flags, nthreads=nthreads, copy=False)  # warm-up: page in the context-owned buffers
+    from oracle import pyoracle
+    pyoracle.lib().orc_frontier_clear(o.h)
+    t0 = time.perf_counter()
+    o.telegram(sub, flags, nthreads=nthreads, copy=False)
+    dt = time.perf_counter() - t0
+    o.close()
+    return sub.n / dt, sub.n, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference path's CPU implementation (oracle port) on the host cores."""
+    if rank != 0:
+        return
+    from distributed_crawler_b200 import abi
+    from distributed_crawler_b200.corpus import Corpus
+    from oracle.pyoracle import Oracle
+    from oracle import pyoracle
+    cores = os.cpu_count() or 1
+    sample = min(CPU_SAMPLE, N_MESSAGES)
+    c = Corpus(sample, seed=SEED, profile=2, nthreads=min(cores, 64))
+    flags = abi.RUN_JSONL | abi.RUN_LINKS | abi.RUN_FRONTIER | abi.RUN_SKIP_SELF
+    o = Oracle()
+    for _ in range(max(args.warmup, 1)):
+        pyoracle.lib().orc_frontier_clear(o.h)
+        o.telegram(c.batch, flags, nthreads=cores, copy=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pyoracle.lib().orc_frontier_clear(o.h)
+        o.telegram(c.batch, flags, nthreads=cores, copy=False)
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "configs[1]: 10M synthetic Telegram mixed text/photo/video-metadata messages, parse+JSONL",
+                       "sample": f"first {sample} messages of the same seeded corpus per step"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} messages x {args.steps} steps, C restatement of the Go path, {cores} threads"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    ensure_built() if rank == 0 or world == 1 else time.sleep(0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from distributed_crawler_b200 import abi
+    from distributed_crawler_b200.corpus import Corpus
+    from distributed_crawler_b200.engine import Engine
+    from distributed_crawler_b200.frontier_merge import EngineFrontier, merge_frontier
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+
+    cores = os.cpu_count() or 1
+    n = N_MESSAGES
+    t_gen = time.perf_counter()
+    corpus = Corpus(n, seed=SEED, first=rank * n, profile=2, nthreads=max(1, min(cores // max(world, 1), 64)))
+    batch = corpus.batch
+    t_gen = time.perf_counter() - t_gen
+    in_bytes = batch.input_bytes()
+    pinned = pin(batch)
+
+    eng = Engine(device=local, frontier_capacity=1 << 23)
+    fset = EngineFrontier(eng, dev)
+    RUN = abi.RUN_JSONL | abi.RUN_FRONTIER | abi.RUN_SKIP_SELF
+    eng.telegram_upload(0, batch)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: kernels only, batch resident in HBM ------------------------------------------------
+    def step_resident():
+        eng.frontier_clear()
+        r = eng.telegram_run_resident(0, RUN | abi.RUN_NO_D2H)
+        gsize = r.frontier_size
+        if world > 1:
+            gsize, _ = merge_frontier(fset, 0)
+        return r, gsize
+
+    for _ in range(max(args.warmup, 3)):
+        r, gsize = step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches = 0
+    emit_ms, parse_ms, kern_ms = [], [], []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, gsize = step_resident()
+        launches += r.gpu_launches
+        emit_ms.append(r.emit_ms); parse_ms.append(r.parse_ms); kern_ms.append(r.kernel_ms)
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    jsonl_len = r.jsonl_len
+    dt_t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+    dt_max = float(dt_t.item())
+    value = n * world * args.steps / dt_max
+
+    # ---- e2e: host buffers through the C ABI, 3 slots pipelined ----------------------------------
+    chunks = [(a, min(a + E2E_CHUNK, n)) for a in range(0, n, E2E_CHUNK)]
+    subs = [batch.slice(a, b) for a, b in chunks]  # views copied once, outside the timed region
+    for s in subs:
+        pin(s)
+
+    def step_e2e():
+        eng.frontier_clear()
+        d2h = 0
+        inflight = []
+        for i, sub in enumerate(subs):
+            slot = i % abi.SLOTS
+            if len(inflight) == abi.SLOTS:
+                s0 = inflight.pop(0)
+                rr = eng.telegram_wait(s0)
+                d2h += rr.jsonl_len + rr.n * 9 + 8
+                eng.release(s0)
+            eng.telegram_submit(slot, sub, RUN)
+            inflight.append(slot)
+        for s0 in inflight:
+            rr = eng.telegram_wait(s0)
+            d2h += rr.jsonl_len + rr.n * 9 + 8
+            eng.release(s0)
+        if world > 1:
+            merge_frontier(fset, 0)
+        return d2h
+
+    for _ in range(2):
+        d2h_bytes = step_e2e()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        d2h_bytes = step_e2e()
+    barrier()
+    dte = time.perf_counter() - t0
+    dte_t = torch.tensor([dte], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dte_t, op=dist.ReduceOp.MAX)
+    e2e_value = n * world * e2e_steps / float(dte_t.item())
+    h2d_bytes = sum(s.input_bytes() for s in subs)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        alg_bytes = in_bytes + jsonl_len + 8 * (n + 1)  # every input byte read once, every output byte written once
+        em = sum(emit_ms) / len(emit_ms)
+        achieved = alg_bytes / (em * 1e-3) / 1e9
+        step_ms = dt_max / args.steps * 1e3
+        traffic = load_traffic()
+        roofline = {"bound": "hbm", "kernel": "tg_emit_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "peak_source": peak_src,
+                    "traffic": (traffic or {}).get("tg_emit_kernel_bytes_per_launch"),
+                    "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": em,
+                    "kernel_share_of_step": em / step_ms,
+                    "step": {"achieved": alg_bytes / (step_ms * 1e-3) / 1e9, "frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak,
+                             "parse_ms": sum(parse_ms) / len(parse_ms), "kernels_ms": sum(kern_ms) / len(kern_ms)}}
+        cpu_v = cpu_n = cpu_dt = None
+        if world == 1 or True:
+            cpu_v, cpu_n, cpu_dt = cpu_baseline(batch, cores, CPU_SAMPLE, abi.RUN_JSONL | abi.RUN_LINKS | abi.RUN_FRONTIER | abi.RUN_SKIP_SELF)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: 10M synthetic Telegram mixed text/photo/video-metadata messages, parse+link-extract+dedup+JSONL",
+                       "messages_per_gpu": n, "seed": hex(SEED), "input_bytes_per_gpu": in_bytes, "jsonl_bytes_per_gpu": jsonl_len,
+                       "l2": "inputs (%.1f GB) and outputs (%.1f GB) per step are far larger than the 126 MB L2" % (in_bytes / 1e9, jsonl_len / 1e9),
+                       "parallelism": f"record-index sharding x{world}" + ("; NCCL all-gather set merge per step" if world > 1 else ""),
+                       "frontier_unique": int(gsize), "corpus_gen_s": round(t_gen, 2)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "steps": e2e_steps, "chunk_records": E2E_CHUNK, "slots": abi.SLOTS, "pinned_input_bytes": pinned},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"first {cpu_n} messages of the same corpus, {cpu_dt:.1f} s, C restatement of the Go path (oracle), {cores} threads, warm"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -119,13 +119,6 @@ class StatsC(C.Structure):
                 ("kernel_ms_total", C.c_double)]
 
 
-class OrcResultC(C.Structure):  # oracle/tgoracle.h orc_result (test infrastructure)
-    _fields_ = [
-        ("n", C.c_uint64), ("status", C.c_void_p), ("jsonl", C.c_void_p), ("jsonl_len", C.c_uint64),
-        ("line_off", C.c_void_p), ("link_off", C.c_void_p), ("links", C.c_void_p),
-        ("n_links", C.c_uint64), ("n_new", C.c_uint64), ("frontier_size", C.c_uint64)]
-
-
 def ptr(a: np.ndarray | None) -> int | None:
     """address of a C-contiguous numpy array (None -> NULL)."""
     if a is None:

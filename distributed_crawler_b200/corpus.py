@@ -69,6 +69,7 @@ class Corpus:
             aux=_view(b.aux, b.aux_len, np.uint8), chans=_view(b.chans, b.n_chans * 40, abi.TG_CHAN),
             chan_strs=_view(b.chan_strs, b.chan_strs_len, np.uint8))
         self.total_bytes = int(_lib().tgc_total_bytes(self._h))
+        self.batch._owner = self  # the views borrow the generator's memory: keep it alive with them
 
     def close(self):
         if getattr(self, "_h", None):

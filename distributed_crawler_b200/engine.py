@@ -84,7 +84,7 @@ def _copy(p, n, dt):
 
 
 class Result:
-    """Host copy of a tgi_result (same accessors as the oracle's Result)."""
+    """Host copy of a tgi_result."""
 
     def __init__(self, r: abi.ResultC, copy: bool = True):
         n = int(r.n)

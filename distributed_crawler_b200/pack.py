@@ -111,7 +111,8 @@ class TgBatch:
         return sum(getattr(self, k).nbytes for k in self.FIELDS)
 
     def slice(self, a: int, b: int) -> "TgBatch":
-        """records [a,b) as a self-contained batch sharing the channel table and aux blob."""
+        """records [a,b) as a self-contained batch (every offset rebased; only referenced rows of the
+        side arrays are kept) — what a caller packing that range on its own would have produced."""
         recs = self.recs[a:b].copy()
         s0 = int(self.recs["str_off"][a]) if a < self.n else self.strs.size
         s1 = int(self.recs["str_off"][b]) if b < self.n else self.strs.size
@@ -119,14 +120,61 @@ class TgBatch:
         e0, e1 = int(self.ent_off[a]), int(self.ent_off[b])
         r0, r1 = int(self.react_off[a]), int(self.react_off[b])
         c0, c1 = int(self.comment_off[a]), int(self.comment_off[b])
-        # comment reactions live behind the message reactions; keep the whole array for simplicity
-        return TgBatch(recs=recs, strs=self.strs[s0:s1].copy(),
-                       ent_off=(self.ent_off[a:b + 1] - e0).astype(np.uint32),
-                       ents=self.ents[e0:e1].copy(),
-                       react_off=self.react_off[a:b + 1].copy(), reacts=self.reacts,
+        ents = self.ents[e0:e1].copy()
+        comments = self.comments[c0:c1].copy()
+        # comment reactions sit behind the message reactions: gather the referenced range
+        has = (comments["flags"] & 1).astype(bool) & (comments["react_count"] > 0)
+        if has.any():
+            cr0 = int(comments["react_start"][has].min())
+            cr1 = int((comments["react_start"][has] + comments["react_count"][has]).max())
+        else:
+            cr0 = cr1 = 0
+        reacts = np.concatenate([self.reacts[r0:r1], self.reacts[cr0:cr1]]) if (r1 > r0 or cr1 > cr0) else self.reacts[:0].copy()
+        comments["react_start"] = np.where(has, comments["react_start"] - cr0 + (r1 - r0), 0)
+        # aux: smallest window covering everything referenced
+        los, his = [], []
+        tu = ents["type"] == abi.ENT_TEXT_URL
+        if tu.any():
+            los.append(int(ents["url_off"][tu].min())); his.append(int((ents["url_off"][tu] + ents["url_len"][tu]).max()))
+        if len(reacts):
+            los.append(int(reacts["emoji_off"].min())); his.append(int((reacts["emoji_off"] + reacts["emoji_len"]).max()))
+        if len(comments):
+            los.append(int(min(comments["text_off"].min(), comments["handle_off"].min())))
+            his.append(int(max((comments["text_off"] + comments["text_len"]).max(),
+                               (comments["handle_off"] + comments["handle_len"]).max())))
+        alo, ahi = (min(los), max(his)) if los else (0, 0)
+        ents["url_off"] = np.where(tu, ents["url_off"] - alo, 0)
+        reacts = reacts.copy()
+        reacts["emoji_off"] -= alo
+        comments["text_off"] -= alo
+        comments["handle_off"] -= alo
+        # channel rows actually referenced
+        if len(recs):
+            cmin, cmax = int(recs["chan_idx"].min()), int(recs["chan_idx"].max())
+        else:
+            cmin, cmax = 0, -1
+        chans = self.chans[cmin:cmax + 1].copy()
+        recs["chan_idx"] -= cmin
+        if len(chans):
+            clo = int(chans["str_off"].min())
+            ln = chans["title_len"].astype(np.int64) + chans["name_len"] + chans["user_len"]
+            chi = int((chans["str_off"] + ln).max())
+            chans["str_off"] -= clo
+        else:
+            clo = chi = 0
+        return TgBatch(recs=recs, strs=_pad(self.strs[s0:s1]),
+                       ent_off=(self.ent_off[a:b + 1] - e0).astype(np.uint32), ents=ents,
+                       react_off=(self.react_off[a:b + 1] - r0).astype(np.uint32), reacts=reacts,
                        comment_off=(self.comment_off[a:b + 1] - c0).astype(np.uint32),
-                       comments=self.comments[c0:c1].copy(), aux=self.aux, chans=self.chans,
-                       chan_strs=self.chan_strs)
+                       comments=comments, aux=_pad(self.aux[alo:ahi]), chans=chans,
+                       chan_strs=_pad(self.chan_strs[clo:chi]))
+
+
+def _pad(a: np.ndarray) -> np.ndarray:
+    """copy of a uint8 array with 16 readable pad bytes behind it"""
+    full = np.zeros(a.size + 16, np.uint8)
+    full[: a.size] = a
+    return full[: a.size]
 
 
 _ENT_TYPES = {"text_url": abi.ENT_TEXT_URL, "mention": abi.ENT_MENTION, "url": abi.ENT_URL}

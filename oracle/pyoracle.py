@@ -14,6 +14,16 @@ import numpy as np
 from distributed_crawler_b200 import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class OrcResultC(C.Structure):  # oracle/tgoracle.h orc_result 
+    _fields_ = [
+        ("n", C.c_uint64), ("status", C.c_void_p), ("jsonl", C.c_void_p), ("jsonl_len", C.c_uint64),
+        ("line_off", C.c_void_p), ("link_off", C.c_void_p), ("links", C.c_void_p),
+        ("n_links", C.c_uint64), ("n_new", C.c_uint64), ("frontier_size", C.c_uint64)]
+
+
+
 _LIB = None
 
 
@@ -34,10 +44,10 @@ def lib() -> C.CDLL:
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_set_clock.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32]
         L.orc_telegram_batch.argtypes = [C.c_void_p, C.POINTER(abi.TgBatchC), C.c_uint32, C.c_int,
-                                         C.POINTER(abi.OrcResultC)]
+                                         C.POINTER(OrcResultC)]
         L.orc_youtube_batch.argtypes = [C.c_void_p, C.POINTER(abi.YtBatchC), C.c_uint32, C.c_int,
-                                        C.POINTER(abi.OrcResultC)]
-        L.orc_result_free.argtypes = [C.POINTER(abi.OrcResultC)]
+                                        C.POINTER(OrcResultC)]
+        L.orc_result_free.argtypes = [C.POINTER(OrcResultC)]
         L.orc_frontier_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.orc_frontier_size.restype = C.c_uint64
         L.orc_frontier_size.argtypes = [C.c_void_p]
@@ -101,7 +111,7 @@ class Oracle:
 
     def telegram(self, batch, run_flags=abi.RUN_JSONL | abi.RUN_LINKS, nthreads=1, copy=True):
         d = batch.descriptor()
-        r = abi.OrcResultC()
+        r = OrcResultC()
         rc = lib().orc_telegram_batch(self.h, C.byref(d), run_flags, nthreads, C.byref(r))
         assert rc == 0
         out = result_from_c(r) if copy else (int(r.n), int(r.jsonl_len), int(r.n_links))
@@ -110,7 +120,7 @@ class Oracle:
 
     def youtube(self, batch, run_flags=abi.RUN_JSONL | abi.RUN_LINKS, nthreads=1, copy=True):
         d = batch.descriptor()
-        r = abi.OrcResultC()
+        r = OrcResultC()
         rc = lib().orc_youtube_batch(self.h, C.byref(d), run_flags, nthreads, C.byref(r))
         assert rc == 0
         out = result_from_c(r) if copy else (int(r.n), int(r.jsonl_len), int(r.n_links))

@@ -1,0 +1,203 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical packed
+batches.  Bit-exact: every comparison is byte equality."""
+import random
+
+import numpy as np
+import pytest
+
+from distributed_crawler_b200 import abi
+from distributed_crawler_b200.corpus import Corpus
+from distributed_crawler_b200.engine import Engine, names_to_keys32
+from distributed_crawler_b200.pack import Channel, Comment, pack_telegram
+from helpers import ALL, TANDEM, assert_results_equal, msg, names, vector_message
+from oracle.pyoracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def both(batch, flags=ALL, **cfg):
+    o, e = Oracle(**cfg), Engine(**cfg)
+    ro, rg = o.telegram(batch, flags), e.telegram(batch, flags)
+    assert_results_equal(ro, rg, flags)
+    if flags & abi.RUN_FRONTIER:
+        assert np.array_equal(o.frontier_export(), e.frontier_export())
+    assert rg.gpu_launches > 0
+    e.close()
+    return ro, rg
+
+
+def test_reference_link_vectors_on_gpu(vectors, engine):
+    msgs = [vector_message(v) for v in vectors["channel_links"]]
+    r = engine.telegram(pack_telegram(msgs), abi.RUN_LINKS)
+    for i, v in enumerate(vectors["channel_links"]):
+        assert names(r, i) == sorted(v["expected"]), f'{v["name"]} ({v["go_file"]}:{v["go_line"]})'
+
+
+def test_reference_filter_vectors_on_gpu(vectors, engine):
+    got = engine.filter_usernames([v["username"].encode() for v in vectors["filter_username"]])
+    for v, reason in zip(vectors["filter_username"], got):
+        assert (reason == "") == v["valid"], v["name"]
+        if not v["valid"]:
+            assert reason == v["reason"], v["name"]
+
+
+def test_tandem_vector_on_gpu(vectors, engine):
+    t = vectors["tandem"]["with_edges"]
+    m = msg("messageText", t["text"], [tuple(e) for e in t["entities"]])
+    r = engine.telegram(pack_telegram([m], [Channel(name=t["owner_url"], username=t["owner_url"])]), TANDEM)
+    edges = [l["name"][: l["len"]].tobytes().decode() for l in r.links if l["flags"] & abi.LF_NEW]
+    assert edges == t["expected_edges"]
+
+
+@pytest.mark.parametrize("n,profile", [(1, 2), (7, 1), (3000, 2), (60000, 2), (60000, 3), (20000, 1)])
+def test_corpus_parity(n, profile):
+    c = Corpus(n, profile=profile, first=12345)
+    both(c.batch, ALL)
+
+
+def test_corpus_parity_configs():
+    c = Corpus(30000, profile=2)
+    both(c.batch, ALL, tz_offset_sec=19800, crawl_label=b'lab"<el>\xff', min_post_date=1_720_000_000,
+         capture_nsec=0, created_at_sec=1_760_000_000)
+    both(c.batch, TANDEM, tz_offset_sec=-18000)
+    both(c.batch, abi.RUN_JSONL)
+
+
+def test_empty_and_ragged():
+    both(pack_telegram([]))
+    ms = [msg("messageText", ""), msg("messageText", None), msg("none"), msg("messagePhoto", "", media="x"),
+          msg("messageText", "a"), msg("messageVideo", None, media="VID"), msg("messageText", "t.me/", handle=""),
+          msg("messageText", "t.me/abcd"), msg("messageText", "t.me/abcde"), msg("messageText", "xt.me/abcdefghijklmnopqrstuvwxyz0123456789x")]
+    both(pack_telegram(ms, [Channel("", "", "")]))
+
+
+def test_status_edge_cases():
+    ms = [msg(date=1_600_000_000, text="t.me/skipped1"), msg(date=1_800_000_000, text="t.me/kept12"),
+          msg(text="x", panics=True, date=1_800_000_000),
+          msg("messageText", "😀 @testchan", [(1, 5, "mention", "")], date=1_800_000_000),
+          msg("messageText", "abc @testchan", [(4, -3, "mention", "")], date=1_800_000_000),
+          msg("messageText", "abc @testchan", [(2 ** 31 - 1, 2, "url", "")], date=1_800_000_000)]
+    ro, rg = both(pack_telegram(ms), ALL, min_post_date=1_700_000_000)
+    assert list(rg.status[:4]) == [abi.ST_SKIPPED, abi.ST_EMITTED, abi.ST_FAILED, abi.ST_FAILED]
+
+
+def test_regex_adversarial():
+    chain = "t.me/abcdt.me/efght.me/ijklmt.me/nopqr xt.me/chain_end " * 40
+    longname = "t.me/" + "a" * 31 + "t.me/bcdefg " + "t.me/" + "b" * 32 + "t.me/cdefgh " + "t.me/" + "c" * 40
+    many = " ".join(f"t.me/name{i:05d}" for i in range(1500))
+    dup = " ".join("t.me/SameName https://t.me/samename/1" for _ in range(300))
+    reserved = "t.me/joinchat/x t.me/JoinChat t.me/sharefoo t.me/share t.me/proxy?x t.me/addstickers t.me/setlanguagex"
+    ents = [(0, 4, "url", ""), (5, 600, "url", ""), (3, 9, "mention", ""), (0, 5000, "mention", ""), (7, 1, "text_url", "http://t.me/share"),
+            (7, 1, "text_url", "https://t.me/share/url?url=https://t.me/realchan"), (9, 2, "text_url", "t.me/ok_chan_1"), (0, 0, "bold", "")]
+    ms = [msg("messageText", chain), msg("messageText", longname), msg("messageText", many), msg("messageText", dup),
+          msg("messageText", reserved), msg("messagePhoto", many[:9000], ents), msg("messageText", "@ab @abcd @abcde_ @1abcde", [(0, 25, "mention", "")]),
+          msg("messageText", "é" * 70 + "t.me/after_two_byte " + "😀" * 33 + "t.me/after_emoji", [(70, 20, "url", ""), (70 + 20 + 66, 16, "url", "")])]
+    both(pack_telegram(ms))
+
+
+def test_utf8_escape_fuzz_around_strip_boundaries():
+    rng = random.Random(99)
+    frag = [b"a", b" ", b"\"", b"\\", b"<", b"&", b"\n", b"\x01", b"\x7f", "é".encode(), "Я".encode(), "中".encode(),
+            "😀".encode(), " ".encode(), " ".encode(), "‧".encode(), b"\xe2\x80", b"\xe2", b"\x80", b"\xbf",
+            b"\xff", b"\xc0\x80", b"\xc1", b"\xed\xa0\x80", b"\xed\x9f\xbf", b"\xf0\x9f", b"\xf0\x9f\x98", b"\xf4\x90\x80\x80",
+            b"\xf4\x8f\xbf\xbf", b"\xe0\x9f\x80", b"\xe0\xa0\x80", b"\xf0\x8f\x80\x80", b"\xf0\x90\x80\x80", b"\xf5\x80\x80\x80"]
+    ms = []
+    for t in range(1500):
+        n = rng.choice([120, 124, 126, 127, 128, 129, 130, 132, 250, 256, 260, 384, 5, 0, 1, 3])
+        body = bytearray()
+        while len(body) < n:
+            body += rng.choice(frag) if rng.random() < 0.5 else b"xyz "[: rng.randrange(1, 5)]
+        body = bytes(body[: n + rng.randrange(0, 4)])
+        ents = [(rng.randrange(0, 140), rng.randrange(0, 12), rng.choice(["mention", "url"]), "")] if t % 3 == 0 else []
+        ms.append(msg("messageText", body, ents, handle=body[:40], reactions=[(body[:7], 3), (body[3:9], 1)] if t % 5 == 0 else []))
+    ro, rg = both(pack_telegram(ms))
+    assert (ro.status == abi.ST_FAILED).sum() > 0  # the fuzz does hit the surrogate-offset panic path
+
+
+def test_reactions_and_comments():
+    rs = [("👍", 3), ("❤", 2), ("👍", 9), ("❤️", 1), ("", 5), ("zz", -4), ("a\"b", 2 ** 31 - 1)]
+    cm = [Comment("c1 <x>", [("🔥", 1), ("🔥", 2), ("a", 0)], 5, 0, "bob"), Comment("", None, 0, 1, ""), Comment("t.me/notalink", [], -1, -2, "h\n")]
+    ms = [msg("messageText", "x", reactions=rs, comments=cm), msg("messageText", "y", reactions=rs[:1], comments=None),
+          msg("messageText", "z", reactions=[(f"k{i:02d}", i) for i in range(31, -1, -1)])]
+    both(pack_telegram(ms))
+
+
+def test_too_many_reactions_is_a_batch_error(engine):
+    ms = [msg("messageText", "z", reactions=[(f"k{i:02d}", i) for i in range(33)])]
+    from distributed_crawler_b200.engine import EngineError
+    with pytest.raises(EngineError) as ei:
+        engine.telegram(pack_telegram(ms))
+    assert ei.value.code == abi.E_ARG
+
+
+def test_frontier_across_batches_and_slots():
+    c = Corpus(90000, profile=3)
+    o, e = Oracle(), Engine()
+    parts = [c.batch.slice(a, a + 30000) for a in (0, 30000, 60000)]
+    for p in parts:
+        ro = o.telegram(p, TANDEM)
+        rg = e.telegram(p, TANDEM)
+        assert_results_equal(ro, rg, TANDEM)
+    assert np.array_equal(o.frontier_export(), e.frontier_export())
+    # pipelined submission over the three slots gives the same set (membership; order is per batch)
+    e2 = Engine()
+    for s, p in enumerate(parts):
+        e2.telegram_submit(s, p, TANDEM)
+    tot = 0
+    for s in range(3):
+        tot += e2.telegram_wait(s).n_new
+        e2.release(s)
+    assert tot == e.frontier_size()
+    a = {bytes(x) for x in e2.frontier_export()}
+    assert a == {bytes(x) for x in e.frontier_export()}
+
+
+def test_frontier_insert_api(engine):
+    o = Oracle()
+    rng = random.Random(5)
+    names_ = [b"name%05d" % rng.randrange(3000) for _ in range(20000)]
+    k = names_to_keys32(names_)
+    assert np.array_equal(o.frontier_insert(k), engine.frontier_insert(k))
+    assert np.array_equal(o.frontier_export(), engine.frontier_export())
+    k2 = names_to_keys32([b"name%05d" % i for i in range(2990, 3010)])
+    assert np.array_equal(o.frontier_insert(k2), engine.frontier_insert(k2))
+    engine.frontier_clear()
+    assert engine.frontier_size() == 0
+
+
+def test_resident_run_matches_batch_call(engine):
+    c = Corpus(20000, profile=2)
+    r1 = engine.telegram(c.batch, abi.RUN_JSONL | abi.RUN_LINKS)
+    engine.telegram_upload(1, c.batch)
+    r2 = engine.telegram_run_resident(1, abi.RUN_JSONL | abi.RUN_LINKS, copy=True)
+    assert np.array_equal(r1.jsonl, r2.jsonl) and np.array_equal(r1.links, r2.links)
+    r3 = engine.telegram_run_resident(1, abi.RUN_JSONL | abi.RUN_NO_D2H)
+    assert r3.jsonl_len == r1.jsonl_len
+    assert engine.read_jsonl(1, 0, 4096) == r1.jsonl[:4096].tobytes()
+
+
+def test_full_size_config2_properties():
+    """BASELINE config 2 at full size (10 M messages): too big for a full oracle pass in a test, so
+    check size-independent properties + byte parity on random windows."""
+    n = 10_000_000
+    c = Corpus(n, profile=2)
+    e = Engine()
+    e.telegram_upload(0, c.batch)
+    r = e.telegram_run_resident(0, abi.RUN_JSONL | abi.RUN_LINKS | abi.RUN_NO_D2H)
+    assert r.n == n and r.jsonl_len > 2000 * n * 0.9
+    o = Oracle()
+    rng = random.Random(3)
+    total_lines = 0
+    for _ in range(12):
+        a = rng.randrange(0, n - 4000)
+        sub = c.batch.slice(a, a + 4000)
+        ro = o.telegram(sub, abi.RUN_JSONL)
+        rg = e.telegram(sub, abi.RUN_JSONL)
+        assert np.array_equal(ro.jsonl, rg.jsonl)
+        total_lines += int((ro.status == 0).sum())
+    # the big run's first and last windows are byte-identical to the windowed runs
+    head = o.telegram(c.batch.slice(0, 3000), abi.RUN_JSONL)
+    assert e.read_jsonl(0, 0, len(head.jsonl)) == head.jsonl.tobytes()
+    tail = o.telegram(c.batch.slice(n - 3000, n), abi.RUN_JSONL)
+    assert e.read_jsonl(0, r.jsonl_len - len(tail.jsonl), len(tail.jsonl)) == tail.jsonl.tobytes()
+    assert e.read_jsonl(0, r.jsonl_len - 1, 1) == b"\n"

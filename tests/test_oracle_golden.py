@@ -1,0 +1,203 @@
+"""CPU tests (no GPU): pin the oracle against the reference's own known-answer vectors and against an
+independent restatement of the Go rules (tests/go_rules.py)."""
+import random
+
+import numpy as np
+import pytest
+
+import go_rules
+from distributed_crawler_b200 import abi
+from distributed_crawler_b200.corpus import Corpus
+from distributed_crawler_b200.pack import Channel, Comment, pack_telegram
+from helpers import ALL, TANDEM, msg, names, vector_message
+from oracle import pyoracle
+
+
+def test_channel_link_vectors(vectors, oracle):
+    """telegramhelper/channel_links_test.go (24 tests), compared as sets like sortedEqual (:20-32)."""
+    msgs = [vector_message(v) for v in vectors["channel_links"]]
+    r = oracle.telegram(pack_telegram(msgs), abi.RUN_LINKS)
+    for i, v in enumerate(vectors["channel_links"]):
+        assert names(r, i) == sorted(v["expected"]), f'{v["name"]} ({v["go_file"]}:{v["go_line"]})'
+
+
+def test_dedup_vector_is_exactly_one(vectors, oracle):
+    v = next(x for x in vectors["channel_links"] if x["name"] == "Deduplication")
+    r = oracle.telegram(pack_telegram([vector_message(v)]), abi.RUN_LINKS)
+    assert r.record_links(0) == [(b"samechan", "text_url")]  # first (most structured) source wins
+
+
+def test_filter_username_vectors(vectors):
+    for v in vectors["filter_username"]:
+        reason = pyoracle.filter_username(v["username"].encode())
+        assert (reason == "") == v["valid"], v["name"]
+        if not v["valid"]:
+            assert reason == v["reason"], v["name"]
+
+
+def test_tandem_vector(vectors, oracle):
+    """crawl/runner_tandem_test.go:15-93: two mention edges pass FilterUsername + seenInBatch."""
+    t = vectors["tandem"]["with_edges"]
+    m = msg("messageText", t["text"], [tuple(e) for e in t["entities"]])
+    b = pack_telegram([m], [Channel(name=t["owner_url"], username=t["owner_url"])])
+    r = oracle.telegram(b, TANDEM)
+    edges = [l["name"][: l["len"]].tobytes().decode() for l in r.links if l["flags"] & abi.LF_NEW]
+    assert edges == t["expected_edges"]
+    assert all(l["flags"] & abi.LF_FILTER_OK for l in r.links)
+
+
+def test_self_reference_and_filter_flags(oracle):
+    m = msg("messageText", "t.me/mychannel t.me/some_bot t.me/goodchan t.me/goodchan")
+    b = pack_telegram([m], [Channel(name="mychannel")])
+    r = oracle.telegram(b, TANDEM)
+    got = {l["name"][: l["len"]].tobytes(): int(l["flags"]) for l in r.links}
+    assert got[b"mychannel"] & abi.LF_SELF and not got[b"mychannel"] & abi.LF_NEW
+    assert not got[b"some_bot"] & abi.LF_FILTER_OK and not got[b"some_bot"] & abi.LF_NEW
+    assert got[b"goodchan"] == abi.LF_FILTER_OK | abi.LF_NEW
+    assert r.n_new == 1
+
+
+@pytest.mark.parametrize("text,off,ln", [
+    ("Hello @testchan!", 6, 9), ("Привет @testchan", 7, 9), ("😀 @testchan", 3, 9), ("😀 @testchan", 1, 5),
+    ("abc", 5, 2), ("abc", 1, 10), ("abc", 1, 0), ("abc", 2, -1), ("", 0, 0), ("😀😀", 2, 2), ("😀😀", 3, 1),
+    ("a\xffb", 1, 1)])
+def test_utf16_offsets_vs_independent(text, off, ln):
+    b = text.encode("utf-8", "surrogateescape") if "\xff" not in text else b"a\xffb"
+    assert pyoracle.utf16_offset_to_bytes(b, off, ln) == go_rules.utf16_offset_to_bytes(b, off, ln)
+
+
+def _random_bytes(rng, n):
+    alphabet = [b"a", b"Z", b" ", b"\"", b"\\", b"<", b">", b"&", b"\n", b"\t", b"\x01", b"\x08", b"\x0c", b"\x1f",
+                b"\x7f", "é".encode(), "Я".encode(), "中".encode(), "😀".encode(), " ".encode(),
+                " ".encode(), b"\xe2\x80", b"\xe2", b"\x80", b"\xff", b"\xc0\x80", b"\xed\xa0\x80",
+                b"\xf0\x9f", b"\xf4\x90\x80\x80", b"\xe0\x9f\x80", b"\xe0\xa0\x80", b"\xf0\x8f\x80\x80"]
+    return b"".join(rng.choice(alphabet) for _ in range(n))
+
+
+def test_json_string_vs_independent():
+    rng = random.Random(1234)
+    for _ in range(600):
+        b = _random_bytes(rng, rng.randrange(0, 60))
+        assert pyoracle.json_string(b) == go_rules.go_json_string(b), b
+
+
+def test_json_time_vs_independent():
+    rng = random.Random(7)
+    for _ in range(400):
+        sec = rng.randrange(-2_000_000_000, 4_000_000_000)
+        nsec = rng.choice([0, 1, 120_000_000, 999_999_999, 500, 123_456_789])
+        tz = rng.choice([0, 3600, -18000, 19800, 12600])
+        assert pyoracle.json_time(sec, nsec, tz) == go_rules.go_time_json(sec, nsec, tz)
+    assert pyoracle.json_time(-62135596800) == b'"0001-01-01T00:00:00Z"'  # Go zero time
+    assert pyoracle.json_time(253402300800) == b""                         # year 10000 -> Marshal error
+
+
+def test_iso8601_duration():
+    cases = [b"PT1H2M3S", b"P1DT2H", b"PT", b"P", b"P0D", b"PT15M", b"", b"PT1H2M3", b"P1D2H", b"PT1M1H",
+             b"PT99999999999999999999S", b"XPT1S", b"PT1S "]
+    for c in cases:
+        assert pyoracle.parse_iso8601_duration(c) == go_rules.parse_iso8601_duration(c), c
+
+
+def test_float_of_int64():
+    for v, want in [(0, b"0"), (10000, b"10000"), (123456789, b"123456789"), (2 ** 53, b"9007199254740992"),
+                    (2 ** 53 + 1, b"9007199254740992"), (12345678901234567890 // 2, b"6172839450617283000"),
+                    (-42, b"-42"), (9223372036854775807, b"9223372036854775807")]:
+        got = pyoracle.json_float_of_int64(v)
+        assert float(got) == float(v)
+        # shortest round-trip: repr(float) has the same significant digits
+        assert got.rstrip(b"0") .lstrip(b"-") == repr(float(v)).replace(".", "").split("e")[0].rstrip("0").lstrip("-").encode() \
+            or got == want
+
+
+def test_links_vs_independent_on_corpus(oracle):
+    c = Corpus(3000, profile=3, nthreads=2)
+    b = c.batch
+    r = oracle.telegram(b, abi.RUN_LINKS)
+    src_names = {"text_url": "text_url", "mention": "mention", "url": "url"}
+    strs, aux = b.strs.tobytes(), b.aux.tobytes()
+    for i in range(b.n):
+        rec = b.recs[i]
+        so = int(rec["str_off"])
+        text = strs[so:so + int(rec["text_len"])] if rec["flags"] & abi.RF_HAS_TEXT else None
+        ents = []
+        for e in b.ents[int(b.ent_off[i]):int(b.ent_off[i + 1])]:
+            typ = {1: "text_url", 2: "mention", 3: "url"}.get(int(e["type"]), "other")
+            ents.append((int(e["offset"]), int(e["length"]), typ, aux[int(e["url_off"]):int(e["url_off"]) + int(e["url_len"])]))
+        want = go_rules.extract_links(text, ents)
+        if rec["flags"] & abi.RF_PANIC:
+            continue
+        if want is None:
+            assert r.status[i] == abi.ST_FAILED, i
+        else:
+            assert r.record_links(i) == want, i
+
+
+def test_post_line_is_json_and_roundtrips(oracle):
+    import json
+    m = [msg("messageText", "hello <b> & \"q\" \\   t.me/abcdef", reactions=[("👍", 3), ("❤", 2), ("👍", 9)],
+             comments=[Comment("c1", [("🔥", 1)], 5, 0, "bob"), Comment("c2", None, 0, 1, "al")], id=77 << 20,
+             view_count=12, share_count=3, handle="Chan"),
+         msg("messageVideo", "cap", media="REMOTEID", media_album_id=5),
+         msg("messageDocument", "t.me/docchan", alt="file.pdf", media="DOCID"),
+         msg("messageLocation"), msg("none"), msg("messagePoll", alt="why?"), msg("messageText", None, comments=None)]
+    r = oracle.telegram(pack_telegram(m, [Channel("T<itle>", "nm", "usr", 10, 20, 30)]))
+    d = [json.loads(r.line(i)) for i in range(len(m))]
+    assert list(d[0].keys())[:5] == ["post_link", "channel_id", "post_uid", "url", "published_at"]
+    assert len(d[0]) == 65
+    assert d[0]["post_link"] == "https://t.me/usr/77" and d[0]["post_uid"] == "77-nm"
+    assert d[0]["reactions"] == {"❤": 2, "👍": 9} and list(d[0]["reactions"]) == ["❤", "👍"]
+    assert d[0]["comments"][1]["reactions"] is None and d[0]["comment_count"] == 2
+    assert d[0]["outlinks"] == ["abcdef"] and d[0]["channel_name"] == "T<itle>"
+    assert d[0]["channel_data"]["channel_url"] == "https://t.me/c/nm"
+    assert d[1]["post_link"].endswith("?single") and d[1]["media_url"] == "REMOTEID" and d[1]["description"] == "cap"
+    assert d[2]["description"] == "file.pdf" and d[2]["outlinks"] == ["docchan"] and d[2]["post_type"] == ["messageDocument"]
+    assert d[3]["post_type"] == ["messageLocation"] and d[4]["post_type"] == ["unknown"]
+    assert d[5]["description"] == "why?" and d[5]["outlinks"] == []
+    assert d[6]["comments"] is None and d[6]["description"] == ""
+    assert b"\\u003cb\\u003e \\u0026" in r.line(0) and b"\\u2028" in r.line(0)
+
+
+def test_status_semantics():
+    o = pyoracle.Oracle(min_post_date=1_700_000_000)
+    m = [msg(date=1_600_000_000, text="t.me/skipped1"), msg(date=1_800_000_000, text="t.me/kept12"),
+         msg(text="x", panics=True, date=1_800_000_000),
+         msg("messageText", "😀 @testchan", [(1, 5, "mention", "")], date=1_800_000_000)]
+    r = o.telegram(pack_telegram(m))
+    assert list(r.status) == [abi.ST_SKIPPED, abi.ST_EMITTED, abi.ST_FAILED, abi.ST_FAILED]
+    assert [len(r.line(i)) > 0 for i in range(4)] == [False, True, False, False]
+    assert r.record_links(0) == [] and r.record_links(1) == [(b"kept12", "plaintext")]
+
+
+def test_corpus_deterministic_and_shardable():
+    a = Corpus(5000, nthreads=1).batch
+    b = Corpus(5000, nthreads=4).batch
+    for k in a.FIELDS:
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    sh = Corpus(700, first=1300, nthreads=2).batch
+    sl = a.slice(1300, 2000)
+    assert np.array_equal(sh.strs, sl.strs)
+    for f in sh.recs.dtype.names:
+        if f != "chan_idx":  # slice() rebases the channel table, a shard keeps the global one
+            assert np.array_equal(sh.recs[f], sl.recs[f]), f
+    for f in ("offset", "length", "type", "url_len"):
+        assert np.array_equal(sh.ents[f], sl.ents[f]), f
+    # same shard -> same oracle output (aux offsets differ, contents do not)
+    r1, r2 = pyoracle.Oracle().telegram(sh, ALL), pyoracle.Oracle().telegram(sl, ALL)
+    assert np.array_equal(r1.jsonl, r2.jsonl) and np.array_equal(r1.links, r2.links)
+
+
+def test_oracle_threads_agree():
+    c = Corpus(20000, nthreads=2)
+    r1 = pyoracle.Oracle().telegram(c.batch, ALL, nthreads=1)
+    r4 = pyoracle.Oracle().telegram(c.batch, ALL, nthreads=4)
+    assert np.array_equal(r1.jsonl, r4.jsonl) and np.array_equal(r1.links, r4.links) and r1.n_new == r4.n_new
+
+
+def test_frontier_first_occurrence_order():
+    o = pyoracle.Oracle()
+    from distributed_crawler_b200.engine import names_to_keys32
+    k = names_to_keys32([b"bbbbb", b"aaaaa", b"bbbbb", b"ccccc", b"aaaaa"])
+    assert list(o.frontier_insert(k)) == [1, 1, 0, 1, 0]
+    assert [bytes(x).rstrip(b"\0") for x in o.frontier_export()] == [b"bbbbb", b"aaaaa", b"ccccc"]
+    assert list(o.frontier_insert(names_to_keys32([b"ccccc", b"ddddd"]))) == [0, 1]
