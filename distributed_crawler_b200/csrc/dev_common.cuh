@@ -191,7 +191,7 @@ DEVI Strip warp_load_strip(const uint8_t* s, int64_t base, int64_t n, uint32_t& 
   uint32_t nz30 = ((w & 0x30303030u) + 0x70707070u) & M;        // (b & 0x30) != 0
   uint32_t geF4 = l4 & (((w & 0x0C0C0C0Cu) + 0x7C7C7C7Cu) & M);  // byte >= 0xF4
   // evaluate one virtual byte past the end too (a lead as the last byte must be flagged)
-  uint32_t chk = st.nvalid >= 4 ? M : (((1u << (8 * (st.nvalid + 1))) - 1u) & M);
+  uint32_t chk = st.nvalid >= 3 ? M : (((1u << (8 * (st.nvalid + 1))) - 1u) & M);
   if (rem < 0) chk = 0;
   uint32_t bad = ((c ^ expect) & chk) | geF4 | swar_has_byte(w & 0xFEFEFEFEu, 0xC0) | (pF0 & ~nz30) |
                  (pE0 & ~b20) | (pED & b20) | (pE2 & swar_has_byte(w, 0x80));
@@ -255,25 +255,36 @@ __device__ __noinline__ uint32_t warp_esc_len(const uint8_t* s, int64_t n) {
 }
 
 // ---- single-thread number / time rendering (different lanes render different fields) ------------
+DEVI uint32_t ndigits_u32(uint32_t v) {
+  return 1u + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) + (v >= 1000000u) +
+         (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
+}
+DEVI uint32_t ndigits_u64(uint64_t v) {
+  if ((v >> 32) == 0) return ndigits_u32((uint32_t)v);
+  uint32_t d = 10;
+  uint64_t p = 10000000000ull;
+  while (d < 20 && v >= p) {
+    d++;
+    p *= 10;
+  }
+  return d;
+}
+DEVI uint32_t ndigits_i64(int64_t v) { return v < 0 ? 1u + ndigits_u64((uint64_t)0 - (uint64_t)v) : ndigits_u64((uint64_t)v); }
+
 __device__ __noinline__ int render_u64(uint8_t* dst, uint64_t v) {
-  uint8_t tmp[20];
-  int n = 0;
-  // peel 9-digit chunks with 32-bit arithmetic
-  while (v >= 1000000000ull) {
-    uint64_t q = v / 1000000000ull;
-    uint32_t r = (uint32_t)(v - q * 1000000000ull);
-    for (int k = 0; k < 9; k++) {
-      tmp[n++] = (uint8_t)('0' + r % 10);
-      r /= 10;
-    }
+  int n = (int)ndigits_u64(v);
+  int k = n;
+  while (v >> 32) {
+    uint64_t q = v / 10;
+    dst[--k] = (uint8_t)('0' + (uint32_t)(v - q * 10));
     v = q;
   }
   uint32_t r = (uint32_t)v;
   do {
-    tmp[n++] = (uint8_t)('0' + r % 10);
-    r /= 10;
-  } while (r);
-  for (int k = 0; k < n; k++) dst[k] = tmp[n - 1 - k];
+    uint32_t q = r / 10;
+    dst[--k] = (uint8_t)('0' + (r - q * 10));
+    r = q;
+  } while (k > 0);
   return n;
 }
 DEVI int render_i64(uint8_t* dst, int64_t v) {
@@ -355,165 +366,248 @@ __device__ __noinline__ int render_time(uint8_t* dst, int64_t sec, int32_t nsec,
   return o;
 }
 
-// ---- output writers ------------------------------------------------------------------------------
-// The record "walkers" (tg_walk.cuh / yt_walk.cuh) are written once against this interface and
-// instantiated with Sizer (pass 1: byte count) and Emitter (pass 2: bytes).  Using the same code
-// for both passes is what guarantees that the scanned offsets and the emitted bytes agree.
+// ---- shared-memory access by 32-bit shared-space address ------------------------------------------
+DEVI uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DEVI void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v)); }
+DEVI uint32_t lds8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+DEVI uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+DEVI uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
 
-struct Sizer {
-  uint64_t total = 0;
-  template <int N>
-  DEVI void lit(const char (&)[N], const uint8_t* /*dev_copy*/) { total += N - 1; }
-  DEVI void raw_smem(const uint8_t*, uint32_t n) { total += n; }
-  DEVI void raw(const uint8_t*, uint32_t n) { total += n; }
-  DEVI void esc(const uint8_t* s, uint32_t n) { total += warp_esc_len(s, n); }
-  DEVI void esc_known(const uint8_t*, uint32_t, uint32_t esc_len) { total += esc_len; }
-  DEVI void ch(uint8_t) { total += 1; }
+// ---- single-thread JSON escaping (Go's sequential algorithm, for short strings such as map keys) --
+DEVI uint32_t thread_esc_len(const uint8_t* s, uint32_t n) {
+  uint32_t o = 0;
+  for (uint32_t i = 0; i < n;) {
+    uint32_t b = ldb(s + i);
+    if (b < 0x80) {
+      o += ascii_esc_len(b);
+      i++;
+      continue;
+    }
+    int need = utf8_valid_lead(s, i, n);
+    if (need == 0) {
+      o += 6;
+      i++;
+    } else {
+      bool ls = need == 3 && b == 0xE2 && ldb(s + i + 1) == 0x80 && (ldb(s + i + 2) | 1u) == 0xA9;
+      o += ls ? 6u : (uint32_t)need;
+      i += (uint32_t)need;
+    }
+  }
+  return o;
+}
+DEVI void put_escaped_s(uint32_t d, uint32_t b, uint32_t len) {  // d: shared address
+  if (len == 1) {
+    sts8(d, b);
+  } else if (len == 2) {
+    sts8(d, '\\');
+    uint32_t c = b;
+    if (b == '\b') c = 'b';
+    else if (b == '\f') c = 'f';
+    else if (b == '\n') c = 'n';
+    else if (b == '\r') c = 'r';
+    else if (b == '\t') c = 't';
+    sts8(d + 1, c);
+  } else {
+    uint32_t h = b >> 4, l = b & 15;
+    sts8(d, '\\'); sts8(d + 1, 'u'); sts8(d + 2, '0'); sts8(d + 3, '0');
+    sts8(d + 4, h < 10 ? '0' + h : 'a' + h - 10);
+    sts8(d + 5, l < 10 ? '0' + l : 'a' + l - 10);
+  }
+}
+DEVI void put_u_s(uint32_t d, uint32_t a, uint32_t b, uint32_t c, uint32_t e) {  // ꯎ
+  sts8(d, '\\'); sts8(d + 1, 'u'); sts8(d + 2, a); sts8(d + 3, b); sts8(d + 4, c); sts8(d + 5, e);
+}
+// escapes s[0..n) into shared memory at d (capacity cap); returns the length or ~0u if it does not fit
+DEVI uint32_t thread_esc(const uint8_t* s, uint32_t n, uint32_t d, uint32_t cap) {
+  uint32_t o = 0;
+  for (uint32_t i = 0; i < n;) {
+    uint32_t b = ldb(s + i);
+    if (o + 6 > cap) return ~0u;
+    if (b < 0x80) {
+      uint32_t len = ascii_esc_len(b);
+      put_escaped_s(d + o, b, len);
+      o += len;
+      i++;
+      continue;
+    }
+    int need = utf8_valid_lead(s, i, n);
+    if (need == 0) {
+      put_u_s(d + o, 'f', 'f', 'f', 'd');
+      o += 6;
+      i++;
+    } else if (need == 3 && b == 0xE2 && ldb(s + i + 1) == 0x80 && (ldb(s + i + 2) | 1u) == 0xA9) {
+      put_u_s(d + o, '2', '0', '2', ldb(s + i + 2) == 0xA8 ? '8' : '9');
+      o += 6;
+      i += 3;
+    } else {
+      for (int k = 0; k < need; k++) sts8(d + o + k, ldb(s + i + k));
+      o += (uint32_t)need;
+      i += (uint32_t)need;
+    }
+  }
+  return o;
+}
+
+// ---- the emitter ------------------------------------------------------------------------------------
+// Per-warp staging buffer in shared memory mapped onto the output stream: stage byte i <-> output
+// byte gbase+i, with (gout+gbase) 16-byte aligned, so complete 16-byte chunks leave as aligned
+// 128-bit stores.  The first `skip` bytes belong to the previous warp's range and are never written
+// from here.  The struct is kept in registers: heavy operations are free functions that take and
+// return it by value.
+constexpr int EMIT_CAP = 4096;       // per-warp staging bytes
+constexpr int EMIT_FLUSH_AT = 3072;  // flush before a piece when fill exceeds this (piece <= 1 KiB)
+
+struct Em {
+  uint32_t sbuf;   // shared-space address of the staging buffer (16-byte aligned)
+  uint32_t fill;   // bytes staged (including the skip region)
+  uint32_t skip;   // leading bytes not owned (only before the first flush)
+  uint8_t* gout;   // output blob
+  uint64_t gbase;  // output offset of stage byte 0
 };
 
-constexpr int EMIT_CAP = 4096;       // per-warp staging bytes
-constexpr int EMIT_FLUSH_AT = 3072;  // flush when fill exceeds this before a piece (piece <= 1 KiB)
-
-// Per-warp staging buffer in shared memory mapped onto the output stream: buf[i] <-> gout[gbase+i],
-// gbase 16-byte aligned (as an address).  The first `skip` bytes of the buffer belong to the
-// previous warp's range and are never written from here.
-struct Emitter {
-  uint8_t* buf;    // smem, 16-byte aligned, EMIT_CAP bytes
-  uint8_t* gout;   // global output blob
-  uint64_t gbase;  // global byte offset of buf[0]
-  uint32_t fill;   // bytes currently in buf (including the skip region)
-  uint32_t skip;   // leading bytes not owned (only before the first flush)
-
-  DEVI void begin(uint8_t* smem, uint8_t* out, uint64_t start_off) {
-    buf = smem;
-    gout = out;
-    uint64_t addr = (uint64_t)(uintptr_t)out + start_off;
-    skip = (uint32_t)(addr & 15);
-    gbase = start_off - skip;
-    fill = skip;
-  }
-  // write all complete 16-byte chunks; keep the tail
-  __device__ __noinline__ void flush() {
-    __syncwarp();
-    uint32_t nch = fill >> 4;
-    int l = lane_id();
-    for (uint32_t c = l; c < nch; c += 32) {
-      if (c == 0 && skip) {
-        for (uint32_t k = skip; k < 16; k++) gout[gbase + k] = buf[k];
-      } else {
-        uint4 v = *(const uint4*)(buf + 16 * c);
-        *(uint4*)(gout + gbase + 16ull * c) = v;
-      }
-    }
-    __syncwarp();
-    uint32_t tail = fill & 15;
-    uint8_t t = 0;
-    if (nch && (uint32_t)l < tail) t = buf[16 * nch + l];
-    __syncwarp();
-    if (nch) {
-      if ((uint32_t)l < tail) buf[l] = t;
-      gbase += 16ull * nch;
-      fill = tail;
-      skip = 0;
-    }
-    __syncwarp();
-  }
-  DEVI void finish() {  // end of this warp's range: write everything, byte-wise for the tail
-    flush();
-    int l = lane_id();
-    if ((uint32_t)l >= skip && (uint32_t)l < fill) gout[gbase + l] = buf[l];
-    __syncwarp();
-    fill = 0;
-    skip = 0;
-  }
-  DEVI void room() {
-    if (fill > EMIT_FLUSH_AT) flush();
-  }
-  template <int N>
-  DEVI void lit(const char (&)[N], const uint8_t* dev_copy) { raw(dev_copy, N - 1); }
-  DEVI void raw_smem(const uint8_t* s, uint32_t n) {  // n <= 1024, s in shared memory
-    room();
-    for (uint32_t i = lane_id(); i < n; i += 32) buf[fill + i] = s[i];
-    fill += n;
-  }
-  DEVI void raw(const uint8_t* s, uint32_t n) {  // global source, any length
-    for (uint32_t o = 0; o < n; o += 1024) {
-      room();
-      uint32_t m = n - o < 1024 ? n - o : 1024;
-      for (uint32_t i = lane_id(); i < m; i += 32) buf[fill + i] = ldb(s + o + i);
-      fill += m;
-    }
-  }
-  DEVI void ch(uint8_t c) {
-    room();
-    if (lane_id() == 0) buf[fill] = c;
-    fill += 1;
-  }
-  DEVI static void put_escaped(uint8_t* d, uint32_t b, uint32_t len) {
-    const char* hex = "0123456789abcdef";
-    if (len == 1) {
-      d[0] = (uint8_t)b;
-    } else if (len == 2) {
-      d[0] = '\\';
-      uint8_t c = (uint8_t)b;
-      if (b == '\b') c = 'b';
-      else if (b == '\f') c = 'f';
-      else if (b == '\n') c = 'n';
-      else if (b == '\r') c = 'r';
-      else if (b == '\t') c = 't';
-      d[1] = c;
+DEVI Em em_begin(uint32_t sbuf, uint8_t* out, uint64_t start_off) {
+  Em e;
+  e.sbuf = sbuf;
+  e.gout = out;
+  uint64_t addr = (uint64_t)(uintptr_t)out + start_off;
+  e.skip = (uint32_t)(addr & 15);
+  e.gbase = start_off - e.skip;
+  e.fill = e.skip;
+  return e;
+}
+// write all complete 16-byte chunks; keep the tail
+__device__ __noinline__ Em em_flush(Em e) {
+  __syncwarp();
+  uint32_t nch = e.fill >> 4;
+  int l = lane_id();
+  uint8_t* g = e.gout + e.gbase;
+  for (uint32_t c = l; c < nch; c += 32) {
+    if (c == 0 && e.skip) {
+      for (uint32_t k = e.skip; k < 16; k++) g[k] = (uint8_t)lds8(e.sbuf + k);
     } else {
-      d[0] = '\\'; d[1] = 'u'; d[2] = '0'; d[3] = '0';
-      d[4] = (uint8_t)hex[b >> 4];
-      d[5] = (uint8_t)hex[b & 15];
+      *(uint4*)(g + 16ull * c) = lds128(e.sbuf + 16 * c);
     }
   }
-  // JSON-escape s[0..n) into the stream (no quotes)
-  __device__ __noinline__ void esc(const uint8_t* s, uint32_t n) {
-    uint32_t carry = 0;
-    for (int64_t base = 0; base < (int64_t)n; base += 128) {
-      room();  // one strip expands to at most 768 bytes
-      Strip st = warp_load_strip(s, base, n, carry);
-      uint32_t e, u;
-      strip_lane_totals(st, s, base, n, e, u);
-      uint32_t incl = warp_incl_scan(e);
-      uint32_t tot = __shfl_sync(FULL, incl, 31);
-      uint8_t* d = buf + fill + (incl - e);
-      if (st.nvalid) {
-        if (!st.exact) {
+  __syncwarp();
+  uint32_t tail = e.fill & 15;
+  uint32_t t = 0;
+  if (nch && (uint32_t)l < tail) t = lds8(e.sbuf + 16 * nch + l);
+  __syncwarp();
+  if (nch) {
+    if ((uint32_t)l < tail) sts8(e.sbuf + l, t);
+    e.gbase += 16ull * nch;
+    e.fill = tail;
+    e.skip = 0;
+  }
+  __syncwarp();
+  return e;
+}
+__device__ __noinline__ void em_finish(Em e) {  // end of the warp's range: tail goes out byte-wise
+  e = em_flush(e);
+  int l = lane_id();
+  if ((uint32_t)l >= e.skip && (uint32_t)l < e.fill) e.gout[e.gbase + l] = (uint8_t)lds8(e.sbuf + l);
+  __syncwarp();
+}
+DEVI void em_room(Em& e) {
+  if (e.fill > EMIT_FLUSH_AT) e = em_flush(e);
+}
+// n <= 1024, global source
+DEVI void em_copy_g(Em& e, const uint8_t* src, uint32_t n) {
+  em_room(e);
+  uint32_t l = lane_id();
+  uint32_t d = e.sbuf + e.fill + l;
+  const uint8_t* s = src + l;
+  uint32_t i = 0;
+  for (; i + 128 <= n; i += 128) {
+    uint32_t b0 = ldb(s + i), b1 = ldb(s + i + 32), b2 = ldb(s + i + 64), b3 = ldb(s + i + 96);
+    sts8(d + i, b0); sts8(d + i + 32, b1); sts8(d + i + 64, b2); sts8(d + i + 96, b3);
+  }
+  for (; i + l < n; i += 32) sts8(d + i, ldb(s + i));
+  e.fill += n;
+}
+DEVI void em_copy_g_long(Em& e, const uint8_t* src, uint32_t n) {
+  for (uint32_t o = 0; o < n; o += 1024) em_copy_g(e, src + o, n - o < 1024 ? n - o : 1024);
+}
+// n <= 1024, shared source (shared-space address)
+DEVI void em_copy_s(Em& e, uint32_t src, uint32_t n) {
+  em_room(e);
+  uint32_t l = lane_id();
+  for (uint32_t i = l; i < n; i += 32) sts8(e.sbuf + e.fill + i, lds8(src + i));
+  e.fill += n;
+}
+DEVI void em_ch(Em& e, uint32_t c) {
+  em_room(e);
+  if (lane_id() == 0) sts8(e.sbuf + e.fill, c);
+  e.fill += 1;
+}
+DEVI void em_ch2(Em& e, uint32_t c0, uint32_t c1) {
+  em_room(e);
+  if (lane_id() == 0) {
+    sts8(e.sbuf + e.fill, c0);
+    sts8(e.sbuf + e.fill + 1, c1);
+  }
+  e.fill += 2;
+}
+// JSON-escape s[0..n) into the stream (no quotes), 128-byte strips, 4 bytes per lane
+__device__ __noinline__ Em em_esc(Em e, const uint8_t* s, uint32_t n) {
+  uint32_t carry = 0;
+  for (int64_t base = 0; base < (int64_t)n; base += 128) {
+    em_room(e);  // one strip expands to at most 768 bytes
+    Strip st = warp_load_strip(s, base, n, carry);
+    uint32_t el, u;
+    strip_lane_totals(st, s, base, n, el, u);
+    uint32_t incl = warp_incl_scan(el);
+    uint32_t tot = __shfl_sync(FULL, incl, 31);
+    uint32_t d = e.sbuf + e.fill + (incl - el);
+    if (st.nvalid) {
+      if (!st.exact) {
+        if (el == st.nvalid) {  // nothing to escape in this lane's bytes
+#pragma unroll
+          for (uint32_t k = 0; k < 4; k++)
+            if (k < st.nvalid) sts8(d + k, (st.w >> (8 * k)) & 0xFF);
+        } else {
 #pragma unroll
           for (uint32_t k = 0; k < 4; k++) {
             if (k < st.nvalid) {
               uint32_t b = (st.w >> (8 * k)) & 0xFF;
               uint32_t len = b < 0x80 ? ascii_esc_len(b) : 1u;
-              put_escaped(d, b, len);
+              put_escaped_s(d, b, len);
               d += len;
             }
           }
-        } else {
-          int64_t p0 = base + 4 * lane_id();
-          for (uint32_t k = 0; k < st.nvalid; k++) {
-            ByteInfo bi = byte_info_exact(s, p0 + k, n);
-            uint32_t b = (st.w >> (8 * k)) & 0xFF;
-            if (bi.esc == 6 && b >= 0x80) {
-              if (b == 0xE2 && bi.start && utf8_valid_lead(s, p0 + k, n) == 3) {  // U+2028/9
-                uint32_t last = ldb(s + p0 + k + 2);
-                d[0] = '\\'; d[1] = 'u'; d[2] = '2'; d[3] = '0'; d[4] = '2';
-                d[5] = (uint8_t)(last == 0xA8 ? '8' : '9');
-              } else {  // invalid byte -> �
-                d[0] = '\\'; d[1] = 'u'; d[2] = 'f'; d[3] = 'f'; d[4] = 'f'; d[5] = 'd';
-              }
-            } else if (bi.esc) {
-              put_escaped(d, b, bi.esc);
-            }
-            d += bi.esc;
+        }
+      } else {
+        int64_t p0 = base + 4 * lane_id();
+        for (uint32_t k = 0; k < st.nvalid; k++) {
+          ByteInfo bi = byte_info_exact(s, p0 + k, n);
+          uint32_t b = (st.w >> (8 * k)) & 0xFF;
+          if (bi.esc == 6 && b >= 0x80) {
+            if (b == 0xE2 && bi.start && utf8_valid_lead(s, p0 + k, n) == 3)  // U+2028/9
+              put_u_s(d, '2', '0', '2', ldb(s + p0 + k + 2) == 0xA8 ? '8' : '9');
+            else  // invalid byte -> U+FFFD
+              put_u_s(d, 'f', 'f', 'f', 'd');
+          } else if (bi.esc) {
+            put_escaped_s(d, b, bi.esc);
           }
+          d += bi.esc;
         }
       }
-      fill += tot;
     }
+    e.fill += tot;
   }
-  DEVI void esc_known(const uint8_t* s, uint32_t n, uint32_t) { esc(s, n); }
-};
+  return e;
+}
 
 }  // namespace tgi

@@ -19,45 +19,39 @@ constexpr int EMIT_RECS_PER_WARP = 8;  // contiguous records per warp task in th
 #define ERR_FRONTIER_FULL 4
 #define ERR_TOO_MANY_LINKS 8
 
+// dynamic shared memory of the emitting kernels: per-warp staging buffers, then per-warp scratch
+constexpr size_t EMIT_SMEM_BYTES = (size_t)WARPS_PER_CTA * (EMIT_CAP + sizeof(WarpScratch));
+DEVI uint32_t emit_stage_addr(uint8_t* dyn, int wid) { return smem_addr(dyn + (size_t)wid * EMIT_CAP); }
+DEVI WarpScratch* emit_scratch(uint8_t* dyn, int wid) {
+  return (WarpScratch*)(dyn + (size_t)WARPS_PER_CTA * EMIT_CAP) + wid;
+}
+
 // ---- channel job -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CTA_THREADS) tg_chan_size_kernel(TgBatchDev b, ChanDerived* cd, uint32_t* len) {
-  __shared__ WarpScratch ws[WARPS_PER_CTA];
   int wid = threadIdx.x >> 5;
   uint32_t c = blockIdx.x * WARPS_PER_CTA + wid;
   if (c >= b.n_chans) return;
-  uint32_t seg[4];
-  for (int s = 0; s < 4; s++) {
-    Sizer z;
-    walk_tg_chan(z, &ws[wid], b, c, s);
-    seg[s] = (uint32_t)z.total;
-  }
+  ChanDerived d = size_tg_chan(b, c);
   if (lane_id() == 0) {
-    ChanDerived d;
-    d.off = 0;
-    d.user_len = seg[0];
-    d.name_len = seg[1];
-    d.title_len = seg[2];
-    d.cdata_len = seg[3];
     cd[c] = d;
-    len[c] = seg[0] + seg[1] + seg[2] + seg[3];
+    len[c] = d.user_len + d.name_len + d.title_len + d.cdata_len;
   }
 }
 
 __global__ void __launch_bounds__(CTA_THREADS) tg_chan_emit_kernel(TgBatchDev b, ChanDerived* cd, const uint64_t* off, uint8_t* blob) {
-  __shared__ WarpScratch ws[WARPS_PER_CTA];
-  __shared__ __align__(16) uint8_t stage[WARPS_PER_CTA][EMIT_CAP];
+  extern __shared__ __align__(16) uint8_t dyn[];
   int wid = threadIdx.x >> 5;
   uint32_t task = blockIdx.x * WARPS_PER_CTA + wid;
   uint32_t c0 = task * EMIT_RECS_PER_WARP;
   if (c0 >= b.n_chans) return;
   uint32_t c1 = min(c0 + (uint32_t)EMIT_RECS_PER_WARP, b.n_chans);
-  Emitter em;
-  em.begin(stage[wid], blob, off[c0]);
+  WarpScratch* ws = emit_scratch(dyn, wid);
+  Em e = em_begin(emit_stage_addr(dyn, wid), blob, off[c0]);
   for (uint32_t c = c0; c < c1; c++) {
     if (lane_id() == 0) cd[c].off = off[c];
-    for (int s = 0; s < 4; s++) walk_tg_chan(em, &ws[wid], b, c, s);
+    e = emit_tg_chan(e, ws, b, c);
   }
-  em.finish();
+  em_finish(e);
 }
 
 // ---- parse: status + links + line length ---------------------------------------------------------
@@ -92,7 +86,6 @@ DEVI TgRecView load_rec_view(const TgBatchDev& b, uint64_t r) {
 }
 
 __global__ void __launch_bounds__(CTA_THREADS) tg_parse_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) {
-  __shared__ WarpScratch ws[WARPS_PER_CTA];
   int wid = threadIdx.x >> 5, l = lane_id();
   uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
@@ -140,9 +133,8 @@ __global__ void __launch_bounds__(CTA_THREADS) tg_parse_kernel(TgBatchDev b, Cfg
         a.v = v;
         a.links = o.arena + lstart;
         a.n_links = nlinks;
-        Sizer z;
-        if (walk_tg_record(z, &ws[wid], a)) llen = (uint32_t)z.total;
-        else status = TGI_ST_NOLINE;
+        llen = size_tg_record(a);
+        if (llen == 0) status = TGI_ST_NOLINE;
       }
     }
     if (l == 0) {
@@ -158,16 +150,16 @@ __global__ void __launch_bounds__(CTA_THREADS) tg_parse_kernel(TgBatchDev b, Cfg
 __global__ void __launch_bounds__(CTA_THREADS) tg_emit_kernel(TgBatchDev b, CfgDev cfg, const uint8_t* status, const uint64_t* line_off,
                                const uint32_t* link_start, const uint32_t* link_count,
                                const tgi_link* arena, uint8_t* out) {
-  __shared__ WarpScratch ws[WARPS_PER_CTA];
-  __shared__ __align__(16) uint8_t stage[WARPS_PER_CTA][EMIT_CAP];
+  extern __shared__ __align__(16) uint8_t dyn[];
   int wid = threadIdx.x >> 5;
+  WarpScratch* ws = emit_scratch(dyn, wid);
+  const uint32_t stage = emit_stage_addr(dyn, wid);
   uint64_t ntasks = (b.n + EMIT_RECS_PER_WARP - 1) / EMIT_RECS_PER_WARP;
   uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   for (uint64_t task = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; task < ntasks; task += nwarps) {
     uint64_t r0 = task * EMIT_RECS_PER_WARP;
     uint64_t r1 = r0 + EMIT_RECS_PER_WARP < b.n ? r0 + EMIT_RECS_PER_WARP : b.n;
-    Emitter em;
-    em.begin(stage[wid], out, line_off[r0]);
+    Em e = em_begin(stage, out, line_off[r0]);
     for (uint64_t r = r0; r < r1; r++) {
       if (status[r] != TGI_ST_EMITTED) continue;
       TgWalkArgs a;
@@ -177,9 +169,9 @@ __global__ void __launch_bounds__(CTA_THREADS) tg_emit_kernel(TgBatchDev b, CfgD
       a.v = load_rec_view(b, r);
       a.links = arena + link_start[r];
       a.n_links = link_count[r];
-      walk_tg_record(em, &ws[wid], a);
+      e = emit_tg_record(e, ws, a);
     }
-    em.finish();
+    em_finish(e);
   }
 }
 

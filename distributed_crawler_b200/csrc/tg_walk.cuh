@@ -1,24 +1,19 @@
-// tg_walk.cuh — the Telegram Post as a piece walk: one templated function that visits every byte
-// range of the JSONL line in order.  Instantiated with tgi::Sizer in the parse kernel (line length)
-// and with tgi::Emitter in the emit kernel (bytes).
+// tg_walk.cuh — the Telegram Post line: closed-form length (parse kernel) and table-driven emission
+// (emit kernel), both derived from the same generated piece table (tools/gen_pieces.py).
 //
 // Replaces telegramhelper/tdutils.go:380-732 ParseMessage (field map :633-717) followed by
 // json.Marshal(post)+'\n' (state/storageproviders.go:276-282, state/daprstate.go:1118-1120) for
 // model.Post (model/data.go:9-75).  Key order = struct declaration order; see SURVEY Appendix A.6
 // for the encoding/json rules restated in dev_common.cuh.
 #pragma once
+#include <cstddef>
+
 #include "dev_common.cuh"
 #include "tg_links.cuh"
 
 namespace tgi {
 
-#define LIT(w, str)                                   \
-  do {                                                \
-    static __device__ const char _lit[] = str;        \
-    (w).lit(_lit, (const uint8_t*)_lit);              \
-  } while (0)
-
-// per-channel strings pre-rendered once per batch by the channel job (see ChanWalk below)
+// per-channel strings pre-rendered once per batch by the channel job
 struct ChanDerived {
   uint64_t off;        // into chan_blob: esc_user | esc_name | "esc_title" | cdata
   uint32_t user_len;   // JSON-escaped ActiveUsernames[0] (0 = no public link)
@@ -45,9 +40,9 @@ struct TgBatchDev {
   const uint8_t* chan_blob;
 };
 
-struct CfgDev {           // per-context constants in a small device blob
-  const uint8_t* blob;    // label_esc | created_tg | created_yt | capture
-  uint32_t label_len;     // JSON-escaped crawl_label (no quotes)
+struct CfgDev {             // per-context constants in a small device blob
+  const uint8_t* blob;      // label_esc | created_tg | created_yt | capture
+  uint32_t label_len;       // JSON-escaped crawl_label (no quotes)
   uint32_t created_tg_len;  // quoted RFC3339 of created_at.UTC().Truncate(s)
   uint32_t created_yt_len;  // quoted RFC3339Nano of created_at in the local zone
   uint32_t capture_len;     // quoted RFC3339Nano of capture_time
@@ -65,18 +60,15 @@ __device__ const char kPostType[TGI_CT__COUNT][28] = {
     ""};
 __device__ const uint8_t kPostTypeLen[TGI_CT__COUNT] = {7, 11, 12, 12, 16, 20, 11, 15, 16, 14, 22, 24, 16, 15, 12, 16, 0};
 
-// per-warp shared scratch used by the walkers
+// per-warp shared scratch of the emit kernel
 struct WarpScratch {
-  uint8_t field[8][40];   // rendered numeric / time fields
-  uint32_t flen[8];       // their lengths
-  uint8_t rslot[32][12];  // per-lane rendered reaction counts
+  uint8_t field[8][40];    // rendered numeric / time fields
+  uint32_t flen[8];        // their lengths
+  uint64_t src_ptr[8];     // global sources: chan segments 0..3, cfg segments 4..7
+  uint32_t src_len[8];
+  uint8_t rslot[32][64];   // per-lane rendered map entries  "key":count
 };
 
-// the line as data: see tools/gen_pieces.py
-struct Piece {
-  uint8_t kind, arg, cond, pad;
-  uint16_t off, len;
-};
 enum { K_LIT, K_FIELD, K_CHAN, K_CFG, K_ESC, K_POSTTYPE, K_COMMENTS, K_REACTIONS, K_OUTLINKS };
 enum { C_NONE, C_USER, C_ALBUM, C_CT_OTHER, C_NOT_CT_OTHER, C_HAS_MEDIA };
 enum { F_MSGNO, F_CHAT, F_VIEW, F_SHARE, F_NCOMM, F_TIME };
@@ -84,7 +76,7 @@ enum { F_MSGNO, F_CHAT, F_VIEW, F_SHARE, F_NCOMM, F_TIME };
 
 // ---- map[string]int (reactions) ------------------------------------------------------------------
 // encoding/json sorts map keys bytewise; later duplicates of a key overwrite earlier ones (Go map
-// assignment, tdutils.go:598).  Up to 32 entries per map (checked by the caller).
+// assignment, tdutils.go:598).  Up to 32 entries per map (checked in the parse kernel).
 DEVI int key_cmp(const uint8_t* a, uint32_t la, const uint8_t* b, uint32_t lb) {
   uint32_t m = la < lb ? la : lb;
   for (uint32_t i = 0; i < m; i++) {
@@ -94,64 +86,173 @@ DEVI int key_cmp(const uint8_t* a, uint32_t la, const uint8_t* b, uint32_t lb) {
   return la < lb ? -1 : (la > lb ? 1 : 0);
 }
 
-template <class W>
-__device__ __noinline__ void walk_reaction_map(W& w, WarpScratch* ws, const tgi_reaction* reacts, uint32_t r0,
-                                               uint32_t r1, const uint8_t* aux) {
+struct MapLane {  // one map entry per lane
+  const uint8_t* kp;
+  uint32_t kl;
+  int32_t cnt;
+  bool live;       // last occurrence of its key
+  uint32_t rank;   // position among the live keys in bytewise order
+  uint32_t nlive;
+};
+DEVI MapLane warp_map_prepare(const tgi_reaction* reacts, uint32_t r0, uint32_t r1, const uint8_t* aux, bool want_rank) {
   int l = lane_id();
   uint32_t n = r1 - r0;
-  if (n == 0) {
-    w.ch('{');
-    w.ch('}');
-    return;
-  }
   if (n > 32) n = 32;
-  const uint8_t* kp = nullptr;
-  uint32_t kl = 0;
-  int32_t cnt = 0;
+  MapLane m;
+  m.kp = nullptr;
+  m.kl = 0;
+  m.cnt = 0;
   if ((uint32_t)l < n) {
     tgi_reaction rc = reacts[r0 + l];
-    kp = aux + rc.emoji_off;
-    kl = rc.emoji_len;
-    cnt = rc.count;
+    m.kp = aux + rc.emoji_off;
+    m.kl = rc.emoji_len;
+    m.cnt = rc.count;
   }
-  // last occurrence of each key wins
-  bool live = (uint32_t)l < n;
+  m.live = (uint32_t)l < n;
   for (uint32_t j = 1; j < n; j++) {
-    const uint8_t* pj = (const uint8_t*)__shfl_sync(FULL, (unsigned long long)kp, j);
-    uint32_t lj = __shfl_sync(FULL, kl, j);
-    if ((uint32_t)l < j && live && key_cmp(kp, kl, pj, lj) == 0) live = false;
+    const uint8_t* pj = (const uint8_t*)__shfl_sync(FULL, (unsigned long long)m.kp, j);
+    uint32_t lj = __shfl_sync(FULL, m.kl, j);
+    if ((uint32_t)l < j && m.live && key_cmp(m.kp, m.kl, pj, lj) == 0) m.live = false;
   }
-  uint32_t livemask = __ballot_sync(FULL, live);
-  uint32_t rank = 0;
-  for (uint32_t j = 0; j < n; j++) {
-    if (!((livemask >> j) & 1u)) continue;
-    const uint8_t* pj = (const uint8_t*)__shfl_sync(FULL, (unsigned long long)kp, j);
-    uint32_t lj = __shfl_sync(FULL, kl, j);
-    if (live && (uint32_t)l != j && key_cmp(pj, lj, kp, kl) < 0) rank++;
+  uint32_t livemask = __ballot_sync(FULL, m.live);
+  m.nlive = __popc(livemask);
+  m.rank = 0;
+  if (want_rank) {
+    for (uint32_t j = 0; j < n; j++) {
+      if (!((livemask >> j) & 1u)) continue;
+      const uint8_t* pj = (const uint8_t*)__shfl_sync(FULL, (unsigned long long)m.kp, j);
+      uint32_t lj = __shfl_sync(FULL, m.kl, j);
+      if (m.live && (uint32_t)l != j && key_cmp(pj, lj, m.kp, m.kl) < 0) m.rank++;
+    }
   }
-  uint32_t dl = 0;
-  __syncwarp();
-  if (live) dl = (uint32_t)render_i64(ws->rslot[l], cnt);
-  __syncwarp();
-  w.ch('{');
-  uint32_t m = __popc(livemask);
-  for (uint32_t r = 0; r < m; r++) {
-    uint32_t who = __ballot_sync(FULL, live && rank == r);
-    int src = __ffs(who) - 1;
-    const uint8_t* pj = (const uint8_t*)__shfl_sync(FULL, (unsigned long long)kp, src);
-    uint32_t lj = __shfl_sync(FULL, kl, src);
-    uint32_t dj = __shfl_sync(FULL, dl, src);
-    if (r) w.ch(',');
-    w.ch('"');
-    w.esc(pj, lj);
-    w.ch('"');
-    w.ch(':');
-    w.raw_smem(ws->rslot[src], dj);
-  }
-  w.ch('}');
+  return m;
 }
 
-// ---- record walk ----------------------------------------------------------------------------------
+__device__ __noinline__ uint32_t size_reaction_map(const tgi_reaction* reacts, uint32_t r0, uint32_t r1, const uint8_t* aux) {
+  if (r1 == r0) return 2;
+  MapLane m = warp_map_prepare(reacts, r0, r1, aux, false);
+  uint32_t mine = m.live ? 3u + thread_esc_len(m.kp, m.kl) + ndigits_i64(m.cnt) : 0u;  // "key":n
+  return 2u + warp_sum(mine) + (m.nlive - 1);
+}
+
+__device__ __noinline__ Em emit_reaction_map(Em e, WarpScratch* ws, const tgi_reaction* reacts, uint32_t r0, uint32_t r1,
+                                             const uint8_t* aux) {
+  if (r1 == r0) {
+    em_ch2(e, '{', '}');
+    return e;
+  }
+  int l = lane_id();
+  MapLane m = warp_map_prepare(reacts, r0, r1, aux, true);
+  // every live lane renders its own  "key":count  into its slot; long keys fall back to the warp path
+  uint32_t slot = smem_addr(ws->rslot[l]);
+  uint32_t sl = 0;
+  __syncwarp();
+  if (m.live) {
+    sts8(slot, '"');
+    uint32_t k = thread_esc(m.kp, m.kl, slot + 1, 64 - 1 - 2 - 11);
+    if (k != ~0u) {
+      sts8(slot + 1 + k, '"');
+      sts8(slot + 2 + k, ':');
+      sl = 3 + k + (uint32_t)render_i64(ws->rslot[l] + 3 + k, m.cnt);
+    } else {
+      sl = ~0u;
+    }
+  }
+  __syncwarp();
+  em_ch(e, '{');
+  for (uint32_t r = 0; r < m.nlive; r++) {
+    uint32_t who = __ballot_sync(FULL, m.live && m.rank == r);
+    int src = __ffs(who) - 1;
+    uint32_t len = __shfl_sync(FULL, sl, src);
+    if (r) em_ch(e, ',');
+    if (len != ~0u) {
+      em_copy_s(e, smem_addr(ws->rslot[src]), len);
+    } else {  // key too long for a slot: escape it cooperatively
+      const uint8_t* pj = (const uint8_t*)__shfl_sync(FULL, (unsigned long long)m.kp, src);
+      uint32_t lj = __shfl_sync(FULL, m.kl, src);
+      int32_t cj = __shfl_sync(FULL, m.cnt, src);
+      em_ch(e, '"');
+      e = em_esc(e, pj, lj);
+      em_ch2(e, '"', ':');
+      uint32_t dl = 0;
+      __syncwarp();
+      if (l == 0) dl = (uint32_t)render_i64(ws->field[7], cj);
+      __syncwarp();
+      dl = __shfl_sync(FULL, dl, 0);
+      em_copy_s(e, smem_addr(ws->field[7]), dl);
+      __syncwarp();
+    }
+  }
+  em_ch(e, '}');
+  return e;
+}
+
+// ---- []model.Comment --------------------------------------------------------------------------------
+__device__ const char kCm0[] = "{\"text\":\"";
+__device__ const char kCm1[] = "\",\"reactions\":";
+__device__ const char kCm2[] = ",\"view_count\":";
+__device__ const char kCm3[] = ",\"reply_count\":";
+__device__ const char kCm4[] = ",\"handle\":\"";
+__device__ const char kCm5[] = "\"}";
+__device__ const char kNullLit[] = "null";
+constexpr uint32_t kCmFixed = sizeof(kCm0) + sizeof(kCm1) + sizeof(kCm2) + sizeof(kCm3) + sizeof(kCm4) + sizeof(kCm5) - 6;
+
+__device__ __noinline__ uint32_t size_tg_comments(const TgBatchDev& b, uint32_t c0, uint32_t c1) {
+  uint32_t tot = 2 + (c1 > c0 ? c1 - c0 - 1 : 0);  // [ ] and commas
+  for (uint32_t k = c0; k < c1; k++) {
+    tgi_comment cm = b.comments[k];
+    tot += kCmFixed + warp_esc_len(b.aux + cm.text_off, cm.text_len) + warp_esc_len(b.aux + cm.handle_off, cm.handle_len) +
+           ndigits_i64(cm.view_count) + ndigits_i64(cm.reply_count) +
+           ((cm.flags & 1) ? size_reaction_map(b.reacts, cm.react_start, cm.react_start + cm.react_count, b.aux) : 4u);
+  }
+  return tot;
+}
+
+__device__ __noinline__ Em emit_tg_comments(Em e, WarpScratch* ws, const TgBatchDev& b, uint32_t c0, uint32_t c1) {
+  int l = lane_id();
+  em_ch(e, '[');
+  for (uint32_t k = c0; k < c1; k++) {
+    tgi_comment cm = b.comments[k];
+    uint32_t dl = 0;
+    __syncwarp();
+    if (l < 2) dl = (uint32_t)render_i64(ws->field[6 + l], l == 0 ? cm.view_count : cm.reply_count);
+    __syncwarp();
+    uint32_t d0 = __shfl_sync(FULL, dl, 0), d1 = __shfl_sync(FULL, dl, 1);
+    if (k > c0) em_ch(e, ',');
+    em_copy_g(e, (const uint8_t*)kCm0, sizeof(kCm0) - 1);
+    e = em_esc(e, b.aux + cm.text_off, cm.text_len);
+    em_copy_g(e, (const uint8_t*)kCm1, sizeof(kCm1) - 1);
+    if (cm.flags & 1) e = emit_reaction_map(e, ws, b.reacts, cm.react_start, cm.react_start + cm.react_count, b.aux);
+    else em_copy_g(e, (const uint8_t*)kNullLit, 4);
+    em_copy_g(e, (const uint8_t*)kCm2, sizeof(kCm2) - 1);
+    em_copy_s(e, smem_addr(ws->field[6]), d0);
+    em_copy_g(e, (const uint8_t*)kCm3, sizeof(kCm3) - 1);
+    em_copy_s(e, smem_addr(ws->field[7]), d1);
+    em_copy_g(e, (const uint8_t*)kCm4, sizeof(kCm4) - 1);
+    e = em_esc(e, b.aux + cm.handle_off, cm.handle_len);
+    em_copy_g(e, (const uint8_t*)kCm5, sizeof(kCm5) - 1);
+    __syncwarp();
+  }
+  em_ch(e, ']');
+  return e;
+}
+
+__device__ __noinline__ Em emit_tg_outlinks(Em e, const tgi_link* links, uint32_t n) {
+  for (uint32_t k = 0; k < n; k++) {
+    if (k) em_ch2(e, ',', '"'); else em_ch(e, '"');
+    em_copy_g(e, links[k].name, links[k].len);  // [a-z0-9_] only: no escaping needed
+    em_ch(e, '"');
+  }
+  return e;
+}
+DEVI uint32_t size_tg_outlinks(const tgi_link* links, uint32_t n) {
+  if (!n) return 0;
+  uint32_t s = 0;
+  for (uint32_t k = lane_id(); k < n; k += 32) s += links[k].len + 2u;
+  return warp_sum(s) + (n - 1);
+}
+
+// ---- record ---------------------------------------------------------------------------------------
 struct TgWalkArgs {
   const TgBatchDev* b;
   const CfgDev* cfg;
@@ -161,186 +262,182 @@ struct TgWalkArgs {
   uint32_t n_links;
 };
 
-template <class W>
-__device__ __noinline__ void walk_tg_comments(W& w, WarpScratch* ws, const TgBatchDev& b, uint32_t c0, uint32_t c1) {
-  static __device__ const char k0[] = "{\"text\":\"";
-  static __device__ const char k1[] = "\",\"reactions\":";
-  static __device__ const char k2[] = ",\"view_count\":";
-  static __device__ const char k3[] = ",\"reply_count\":";
-  static __device__ const char k4[] = ",\"handle\":\"";
-  static __device__ const char k5[] = "\"}";
-  static __device__ const char kNull[] = "null";
-  int l = lane_id();
-  w.ch('[');
-  for (uint32_t k = c0; k < c1; k++) {
-    tgi_comment cm = b.comments[k];
-    uint32_t dl = 0;
-    __syncwarp();
-    if (l < 2) dl = (uint32_t)render_i64(ws->field[6 + l], l == 0 ? cm.view_count : cm.reply_count);
-    __syncwarp();
-    uint32_t d0 = __shfl_sync(FULL, dl, 0), d1 = __shfl_sync(FULL, dl, 1);
-    if (k > c0) w.ch(',');
-    w.raw((const uint8_t*)k0, sizeof(k0) - 1);
-    w.esc(b.aux + cm.text_off, cm.text_len);
-    w.raw((const uint8_t*)k1, sizeof(k1) - 1);
-    if (cm.flags & 1) walk_reaction_map(w, ws, b.reacts, cm.react_start, cm.react_start + cm.react_count, b.aux);
-    else w.raw((const uint8_t*)kNull, 4);
-    w.raw((const uint8_t*)k2, sizeof(k2) - 1);
-    w.raw_smem(ws->field[6], d0);
-    w.raw((const uint8_t*)k3, sizeof(k3) - 1);
-    w.raw_smem(ws->field[7], d1);
-    w.raw((const uint8_t*)k4, sizeof(k4) - 1);
-    w.esc(b.aux + cm.handle_off, cm.handle_len);
-    w.raw((const uint8_t*)k5, sizeof(k5) - 1);
+struct TgDerived {  // what both passes need to know about a record
+  const uint8_t* desc;
+  uint32_t desc_len;
+  bool has_media, has_user, album, comments_nil;
+  uint32_t c0, c1;
+  int64_t ncomments;
+};
+DEVI TgDerived tg_derive(const TgWalkArgs& a, const ChanDerived& cd) {
+  TgDerived d;
+  const TgBatchDev& b = *a.b;
+  d.c0 = b.comment_off[a.r];
+  d.c1 = b.comment_off[a.r + 1];
+  d.comments_nil = (a.v.flags & TGI_RF_COMMENTS_NIL) != 0;
+  d.ncomments = d.comments_nil ? 0 : (int64_t)(d.c1 - d.c0);
+  // description / media by content type (tdutils.go:443-587)
+  d.desc = nullptr;
+  d.desc_len = 0;
+  uint32_t ct = a.v.ct;
+  if (ct == TGI_CT_TEXT || ct == TGI_CT_VIDEO || ct == TGI_CT_PHOTO || ct == TGI_CT_ANIMATION) {
+    if (a.v.flags & TGI_RF_HAS_TEXT) { d.desc = a.v.text; d.desc_len = a.v.text_len; }
+  } else if (ct == TGI_CT_ANIMATED_EMOJI || ct == TGI_CT_POLL || ct == TGI_CT_GIVEAWAY ||
+             ct == TGI_CT_PAID_MEDIA || ct == TGI_CT_DOCUMENT) {
+    d.desc = a.v.alt; d.desc_len = a.v.alt_len;
   }
-  w.ch(']');
+  d.has_media = ct == TGI_CT_VIDEO || ct == TGI_CT_VIDEO_NOTE || ct == TGI_CT_DOCUMENT;
+  d.has_user = cd.user_len != 0;
+  d.album = d.has_user && a.v.rec->media_album_id != 0;
+  return d;
 }
 
-template <class W>
-__device__ __noinline__ void walk_tg_outlinks(W& w, const tgi_link* links, uint32_t n) {
-  for (uint32_t k = 0; k < n; k++) {
-    if (k) w.ch(',');
-    w.ch('"');
-    w.raw(links[k].name, links[k].len);  // [a-z0-9_] only: no escaping needed
-    w.ch('"');
-  }
+// line length in bytes; 0 if a time field is not representable (Marshal error -> TGI_ST_NOLINE).
+// The formula's coefficients come from the generated piece table, so it cannot drift from emit.
+DEVI uint32_t size_tg_record(const TgWalkArgs& a) {
+  const TgBatchDev& b = *a.b;
+  const CfgDev& cfg = *a.cfg;
+  const tgi_tg_rec* rec = a.v.rec;
+  const ChanDerived cd = b.chan_derived[rec->chan_idx];
+  TgDerived d = tg_derive(a, cd);
+  if (cfg.flags & CFGDEV_CLOCK_INVALID) return 0;
+  // int32 dates are always inside year [0,9999]: RFC3339 with quotes, 'Z' or a +hh:mm offset
+  uint32_t L[8] = {ndigits_i64(rec->id / 1048576), ndigits_i64(rec->chat_id), ndigits_i64(rec->view_count),
+                   ndigits_i64(rec->share_count), ndigits_i64(d.ncomments), cfg.tz == 0 ? 22u : 27u, 0, 0};
+  uint32_t chan[4] = {cd.user_len, cd.name_len, cd.title_len, cd.cdata_len};
+  uint32_t cf[4] = {cfg.label_len, cfg.created_tg_len, cfg.created_yt_len, cfg.capture_len};
+  uint32_t tot = tg_size_fixed(L, chan, cf, d.has_user, d.album);
+  tot += warp_esc_len(d.desc, d.desc_len);
+  tot += a.v.ct == TGI_CT_OTHER ? warp_esc_len(a.v.alt, a.v.alt_len) : (uint32_t)kPostTypeLen[a.v.ct];
+  if (d.has_media) tot += warp_esc_len(a.v.media, a.v.media_len);
+  tot += warp_esc_len(a.v.handle, a.v.handle_len);
+  tot += d.comments_nil ? 4u : size_tg_comments(b, d.c0, d.c1);
+  tot += size_reaction_map(b.reacts, b.react_off[a.r], b.react_off[a.r + 1], b.aux);
+  tot += size_tg_outlinks(a.links, a.n_links);
+  return tot;
 }
 
-// returns false if a time field is not representable (Marshal error -> TGI_ST_NOLINE)
-template <class W>
-DEVI bool walk_tg_record(W& w, WarpScratch* ws, const TgWalkArgs& a) {
+DEVI Em emit_tg_record(Em e, WarpScratch* ws, const TgWalkArgs& a) {
   const TgBatchDev& b = *a.b;
   const CfgDev& cfg = *a.cfg;
   const tgi_tg_rec* rec = a.v.rec;
   int l = lane_id();
   const ChanDerived cd = b.chan_derived[rec->chan_idx];
-  const uint8_t* cb = b.chan_blob + cd.off;
-  uint32_t c0 = b.comment_off[a.r], c1 = b.comment_off[a.r + 1];
-  bool comments_nil = (a.v.flags & TGI_RF_COMMENTS_NIL) != 0;
-  int64_t ncomments = comments_nil ? 0 : (int64_t)(c1 - c0);
+  TgDerived d = tg_derive(a, cd);
+  const uint32_t ws_s = smem_addr(ws);
 
-  // prologue: lanes 0..5 render the numeric / time fields of this record into shared scratch
+  // prologue: lanes 0..5 render the numeric / time fields, lanes 8..15 fill the source table
   __syncwarp();
   if (l < 5) {
     int64_t v = l == 0 ? rec->id / 1048576                                     // tdutils.go:1008
                        : l == 1 ? rec->chat_id
                                 : l == 2 ? (int64_t)rec->view_count
-                                         : l == 3 ? (int64_t)rec->share_count : ncomments;
+                                         : l == 3 ? (int64_t)rec->share_count : d.ncomments;
     ws->flen[l] = (uint32_t)render_i64(ws->field[l], v);
   } else if (l == 5) {
     ws->flen[5] = (uint32_t)render_time(ws->field[5], rec->date, 0, cfg.tz);  // :417
+  } else if (l >= 8 && l < 12) {
+    int k = l - 8;
+    uint32_t o = k == 0 ? 0u : k == 1 ? cd.user_len : k == 2 ? cd.user_len + cd.name_len : cd.user_len + cd.name_len + cd.title_len;
+    ws->src_ptr[k] = (uint64_t)(uintptr_t)(b.chan_blob + cd.off + o);
+    ws->src_len[k] = k == 0 ? cd.user_len : k == 1 ? cd.name_len : k == 2 ? cd.title_len : cd.cdata_len;
+  } else if (l >= 12 && l < 16) {
+    int k = l - 12;
+    uint32_t o = k == 0 ? 0u : k == 1 ? cfg.label_len : k == 2 ? cfg.label_len + cfg.created_tg_len
+                                                               : cfg.label_len + cfg.created_tg_len + cfg.created_yt_len;
+    ws->src_ptr[4 + k] = (uint64_t)(uintptr_t)(cfg.blob + o);
+    ws->src_len[4 + k] = k == 0 ? cfg.label_len : k == 1 ? cfg.created_tg_len : k == 2 ? cfg.created_yt_len : cfg.capture_len;
   }
   __syncwarp();
-  if (ws->flen[F_TIME] == 0 || (cfg.flags & CFGDEV_CLOCK_INVALID)) return false;
 
-  // description / media by content type (tdutils.go:443-587)
-  const uint8_t* desc = nullptr;
-  uint32_t desc_len = 0;
-  uint32_t ct = a.v.ct;
-  if (ct == TGI_CT_TEXT || ct == TGI_CT_VIDEO || ct == TGI_CT_PHOTO || ct == TGI_CT_ANIMATION) {
-    if (a.v.flags & TGI_RF_HAS_TEXT) { desc = a.v.text; desc_len = a.v.text_len; }
-  } else if (ct == TGI_CT_ANIMATED_EMOJI || ct == TGI_CT_POLL || ct == TGI_CT_GIVEAWAY ||
-             ct == TGI_CT_PAID_MEDIA || ct == TGI_CT_DOCUMENT) {
-    desc = a.v.alt; desc_len = a.v.alt_len;
-  }
-  const bool has_media = ct == TGI_CT_VIDEO || ct == TGI_CT_VIDEO_NOTE || ct == TGI_CT_DOCUMENT;
-  const bool has_user = cd.user_len != 0, album = has_user && rec->media_album_id != 0;
-  static __device__ const char kNullLit[] = "null";
-
+  const uint32_t ct = a.v.ct;
+  const uint32_t condmask = 1u | (d.has_user ? 1u << C_USER : 0) | (d.album ? 1u << C_ALBUM : 0) |
+                            (ct == TGI_CT_OTHER ? 1u << C_CT_OTHER : 1u << C_NOT_CT_OTHER) |
+                            (d.has_media ? 1u << C_HAS_MEDIA : 0);
   for (int pi = 0; pi < kTgNPieces; pi++) {
-    const Piece pc = kTgPieces[pi];
-    switch (pc.cond) {
-      case C_USER: if (!has_user) continue; break;
-      case C_ALBUM: if (!album) continue; break;
-      case C_CT_OTHER: if (ct != TGI_CT_OTHER) continue; break;
-      case C_NOT_CT_OTHER: if (ct == TGI_CT_OTHER) continue; break;
-      case C_HAS_MEDIA: if (!has_media) continue; break;
-      default: break;
-    }
-    const uint8_t* src = nullptr;
-    uint32_t len = 0;
-    int mode = 0;  // 0 copy from global, 1 copy from shared, 2 escape, 3 composite
-    switch (pc.kind) {
-      case K_LIT: src = (const uint8_t*)kTgTemplate + pc.off; len = pc.len; break;
-      case K_FIELD: src = ws->field[pc.arg]; len = ws->flen[pc.arg]; mode = 1; break;
-      case K_CHAN: {
-        uint32_t o = pc.arg == 0 ? 0u : pc.arg == 1 ? cd.user_len : pc.arg == 2 ? cd.user_len + cd.name_len
-                                                                                : cd.user_len + cd.name_len + cd.title_len;
-        len = pc.arg == 0 ? cd.user_len : pc.arg == 1 ? cd.name_len : pc.arg == 2 ? cd.title_len : cd.cdata_len;
-        src = cb + o;
-        break;
-      }
-      case K_CFG: {
-        uint32_t o = pc.arg == 0 ? 0u : pc.arg == 1 ? cfg.label_len : pc.arg == 2 ? cfg.label_len + cfg.created_tg_len
-                                                                                  : cfg.label_len + cfg.created_tg_len + cfg.created_yt_len;
-        len = pc.arg == 0 ? cfg.label_len : pc.arg == 1 ? cfg.created_tg_len : pc.arg == 2 ? cfg.created_yt_len : cfg.capture_len;
-        src = cfg.blob + o;
-        break;
-      }
-      case K_ESC:
-        mode = 2;
-        if (pc.arg == 0) { src = desc; len = desc_len; }
-        else if (pc.arg == 1) { src = a.v.media; len = a.v.media_len; }
-        else if (pc.arg == 2) { src = a.v.handle; len = a.v.handle_len; }
-        else { src = a.v.alt; len = a.v.alt_len; }
-        break;
-      case K_POSTTYPE: src = (const uint8_t*)kPostType[ct]; len = kPostTypeLen[ct]; break;
-      default: mode = 3; break;
-    }
-    if (mode == 0) w.raw(src, len);
-    else if (mode == 1) w.raw_smem(src, len);
-    else if (mode == 2) w.esc(src, len);
-    else if (pc.kind == K_COMMENTS) {
-      if (comments_nil) w.raw((const uint8_t*)kNullLit, 4);
-      else walk_tg_comments(w, ws, b, c0, c1);
-    } else if (pc.kind == K_REACTIONS) {
-      walk_reaction_map(w, ws, b.reacts, b.react_off[a.r], b.react_off[a.r + 1], b.aux);
+    const uint32_t pc = kTgPieces[pi];
+    const uint32_t kind = pc & 15u, arg = (pc >> 4) & 15u;
+    if (!((condmask >> ((pc >> 8) & 15u)) & 1u)) continue;
+    if (kind == K_LIT) {
+      em_copy_g(e, (const uint8_t*)kTgTemplate + ((pc >> 12) & 0x7FFu), pc >> 23);
+    } else if (kind == K_FIELD) {
+      em_copy_s(e, ws_s + (uint32_t)offsetof(WarpScratch, field) + 40u * arg,
+                lds32(ws_s + (uint32_t)offsetof(WarpScratch, flen) + 4u * arg));
+    } else if (kind == K_CHAN || kind == K_CFG) {
+      uint32_t idx = (kind == K_CFG ? 4u : 0u) + arg;
+      em_copy_g_long(e, (const uint8_t*)(uintptr_t)ws->src_ptr[idx], ws->src_len[idx]);
+    } else if (kind == K_ESC) {
+      const uint8_t* p = arg == 0 ? d.desc : arg == 1 ? a.v.media : arg == 2 ? a.v.handle : a.v.alt;
+      uint32_t n = arg == 0 ? d.desc_len : arg == 1 ? a.v.media_len : arg == 2 ? a.v.handle_len : a.v.alt_len;
+      e = em_esc(e, p, n);
+    } else if (kind == K_POSTTYPE) {
+      em_copy_g(e, (const uint8_t*)kPostType[ct], kPostTypeLen[ct]);
+    } else if (kind == K_COMMENTS) {
+      if (d.comments_nil) em_copy_g(e, (const uint8_t*)kNullLit, 4);
+      else e = emit_tg_comments(e, ws, b, d.c0, d.c1);
+    } else if (kind == K_REACTIONS) {
+      e = emit_reaction_map(e, ws, b.reacts, b.react_off[a.r], b.react_off[a.r + 1], b.aux);
     } else {
-      walk_tg_outlinks(w, a.links, a.n_links);
+      e = emit_tg_outlinks(e, a.links, a.n_links);
     }
   }
-  return true;
+  return e;
 }
 
-// ---- channel walk: the per-channel constant strings, rendered once per batch -------------------
-// segment 0: esc(username)  1: esc(channelName)  2: "esc(title)"  3: channel_data tail
-template <class W>
-DEVI void walk_tg_chan(W& w, WarpScratch* ws, const TgBatchDev& b, uint32_t c, int seg) {
+// ---- channel job: the per-channel constant strings, rendered once per batch ----------------------
+// blob layout per channel: esc(username) | esc(channelName) | "esc(title)" | channel_data tail
+__device__ const char kCd0[] = ",\"channel_name\":\"";
+__device__ const char kCd1[] = "\",\"channel_description\":\"\",\"channel_profile_image\":\"\",\"channel_engagement_data\":{\"follower_count\":";
+__device__ const char kCd2[] = ",\"following_count\":0,\"like_count\":0,\"post_count\":";
+__device__ const char kCd3[] = ",\"views_count\":";
+__device__ const char kCd4[] = ",\"comment_count\":0,\"share_count\":0},\"channel_url_external\":\"https://t.me/c/";
+__device__ const char kCd5[] = "\",\"channel_url\":\"https://t.me/c/";
+__device__ const char kCd6[] = "\",\"country_code\":\"\",\"published_at\":\"0001-01-01T00:00:00Z\"}";
+constexpr uint32_t kCdFixed = sizeof(kCd0) + sizeof(kCd1) + sizeof(kCd2) + sizeof(kCd3) + sizeof(kCd4) + sizeof(kCd5) + sizeof(kCd6) - 7;
+
+DEVI ChanDerived size_tg_chan(const TgBatchDev& b, uint32_t c) {
+  const tgi_tg_chan ch = b.chans[c];
+  const uint8_t* cs = b.chan_strs + ch.str_off;
+  uint32_t et = warp_esc_len(cs, ch.title_len), en = warp_esc_len(cs + ch.title_len, ch.name_len),
+           eu = warp_esc_len(cs + ch.title_len + ch.name_len, ch.user_len);
+  ChanDerived d;
+  d.off = 0;
+  d.user_len = eu;
+  d.name_len = en;
+  d.title_len = et + 2;
+  d.cdata_len = kCdFixed + et + 2 * en + ndigits_i64(ch.member_count) + ndigits_i64(ch.post_count) + ndigits_i64(ch.view_count);
+  return d;
+}
+
+DEVI Em emit_tg_chan(Em e, WarpScratch* ws, const TgBatchDev& b, uint32_t c) {
   const tgi_tg_chan ch = b.chans[c];
   const uint8_t* cs = b.chan_strs + ch.str_off;
   const uint8_t *title = cs, *name = cs + ch.title_len, *user = name + ch.name_len;
   int l = lane_id();
-  if (seg == 0) {
-    w.esc(user, ch.user_len);
-  } else if (seg == 1) {
-    w.esc(name, ch.name_len);
-  } else if (seg == 2) {
-    w.ch('"');
-    w.esc(title, ch.title_len);
-    w.ch('"');
-  } else {
-    uint32_t flen = 0;
-    __syncwarp();
-    if (l == 0) flen = (uint32_t)render_i64(ws->field[0], ch.member_count);
-    else if (l == 1) flen = (uint32_t)render_i64(ws->field[1], ch.post_count);
-    else if (l == 2) flen = (uint32_t)render_i64(ws->field[2], ch.view_count);
-    __syncwarp();
-    uint32_t L0 = __shfl_sync(FULL, flen, 0), L1 = __shfl_sync(FULL, flen, 1), L2 = __shfl_sync(FULL, flen, 2);
-    LIT(w, ",\"channel_name\":\"");
-    w.esc(title, ch.title_len);
-    LIT(w, "\",\"channel_description\":\"\",\"channel_profile_image\":\"\",\"channel_engagement_data\":{"
-           "\"follower_count\":");
-    w.raw_smem(ws->field[0], L0);
-    LIT(w, ",\"following_count\":0,\"like_count\":0,\"post_count\":");
-    w.raw_smem(ws->field[1], L1);
-    LIT(w, ",\"views_count\":");
-    w.raw_smem(ws->field[2], L2);
-    LIT(w, ",\"comment_count\":0,\"share_count\":0},\"channel_url_external\":\"https://t.me/c/");
-    w.esc(name, ch.name_len);
-    LIT(w, "\",\"channel_url\":\"https://t.me/c/");
-    w.esc(name, ch.name_len);
-    LIT(w, "\",\"country_code\":\"\",\"published_at\":\"0001-01-01T00:00:00Z\"}");
-  }
+  __syncwarp();
+  if (l < 3) ws->flen[l] = (uint32_t)render_i64(ws->field[l], l == 0 ? ch.member_count : l == 1 ? ch.post_count : ch.view_count);
+  __syncwarp();
+  uint32_t L0 = ws->flen[0], L1 = ws->flen[1], L2 = ws->flen[2];
+  e = em_esc(e, user, ch.user_len);
+  e = em_esc(e, name, ch.name_len);
+  em_ch(e, '"');
+  e = em_esc(e, title, ch.title_len);
+  em_ch(e, '"');
+  em_copy_g(e, (const uint8_t*)kCd0, sizeof(kCd0) - 1);
+  e = em_esc(e, title, ch.title_len);
+  em_copy_g(e, (const uint8_t*)kCd1, sizeof(kCd1) - 1);
+  em_copy_s(e, smem_addr(ws->field[0]), L0);
+  em_copy_g(e, (const uint8_t*)kCd2, sizeof(kCd2) - 1);
+  em_copy_s(e, smem_addr(ws->field[1]), L1);
+  em_copy_g(e, (const uint8_t*)kCd3, sizeof(kCd3) - 1);
+  em_copy_s(e, smem_addr(ws->field[2]), L2);
+  em_copy_g(e, (const uint8_t*)kCd4, sizeof(kCd4) - 1);
+  e = em_esc(e, name, ch.name_len);
+  em_copy_g(e, (const uint8_t*)kCd5, sizeof(kCd5) - 1);
+  e = em_esc(e, name, ch.name_len);
+  em_copy_g(e, (const uint8_t*)kCd6, sizeof(kCd6) - 1);
+  __syncwarp();
+  return e;
 }
 
 }  // namespace tgi

@@ -195,10 +195,9 @@ __global__ void cfg_label_size_kernel(const uint8_t* s, uint32_t n, uint32_t* ou
 }
 __global__ void cfg_label_emit_kernel(const uint8_t* s, uint32_t n, uint8_t* out) {
   __shared__ __align__(16) uint8_t stage[EMIT_CAP];
-  Emitter em;
-  em.begin(stage, out, 0);
-  em.esc(s, n);
-  em.finish();
+  Em e = em_begin(smem_addr(stage), out, 0);
+  e = em_esc(e, s, n);
+  em_finish(e);
 }
 
 int build_cfg_blob(tgi_ctx* c) {
@@ -421,7 +420,7 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     unsigned tasks = (b.n_chans + EMIT_RECS_PER_WARP - 1) / EMIT_RECS_PER_WARP;
     unsigned g = (tasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (g) {
-      tg_chan_emit_kernel<<<g, CTA_THREADS, 0, st>>>(b, s.d_chan_derived.as<ChanDerived>(), s.d_chan_off.as<uint64_t>(), s.d_chan_blob.as<uint8_t>());
+      tg_chan_emit_kernel<<<g, CTA_THREADS, EMIT_SMEM_BYTES, st>>>(b, s.d_chan_derived.as<ChanDerived>(), s.d_chan_off.as<uint64_t>(), s.d_chan_blob.as<uint8_t>());
       launches++;
     }
     if (n) {
@@ -429,7 +428,7 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       uint64_t want = (ntasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
       unsigned ge = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms * 5);
       CK(cudaEventRecord(s.ev_e0, st));
-      tg_emit_kernel<<<ge, CTA_THREADS, 0, st>>>(b, cfg, s.d_status.as<uint8_t>(), s.d_line_off.as<uint64_t>(),
+      tg_emit_kernel<<<ge, CTA_THREADS, EMIT_SMEM_BYTES, st>>>(b, cfg, s.d_status.as<uint8_t>(), s.d_line_off.as<uint64_t>(),
                                                 s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(),
                                                 s.d_arena.as<tgi_link>(), s.d_jsonl.as<uint8_t>());
       CK(cudaEventRecord(s.ev_e1, st));
@@ -673,6 +672,11 @@ int tgi_create(const tgi_config* cfg, tgi_ctx** out) {
   ctx->fr.table = ctx->d_table.as<uint64_t>();
   ctx->fr.tmask = tslots - 1;
   ctx->fr.count = ctx->d_fcount.as<uint64_t>();
+  if (cudaFuncSetAttribute(tg_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMIT_SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(tg_chan_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMIT_SMEM_BYTES) != cudaSuccess) {
+    set_err(c, "cudaFuncSetAttribute(max dynamic smem %zu) failed", (size_t)EMIT_SMEM_BYTES);
+    return fail(TGI_E_CUDA);
+  }
   int rc = build_cfg_blob(ctx);
   if (rc) return fail(rc);
   for (int i = 0; i < TGI_SLOTS; i++) ctx->slots[i].worker = std::thread(worker_main, ctx, &ctx->slots[i]);

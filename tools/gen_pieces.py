@@ -67,8 +67,15 @@ def c_string(b: bytes) -> str:
 
 
 def emit_table(name, prog):
+    """packed table: bits 0-3 kind, 4-7 arg, 8-11 cond, 12-22 template offset, 23-31 length;
+    plus the constants of the closed-form line-length formula, derived from the same program."""
     blob = bytearray()
     rows = []
+    const_len = user_lit = album_lit = 0
+    nfield = [[0] * 8, [0] * 8]      # [cond NONE, cond USER][field]
+    nchan = [[0] * 4, [0] * 4]
+    ncfg = [0] * 4
+    nesc = {}
     for kind, arg, cond, text in prog:
         off = ln = 0
         if kind == K_LIT:
@@ -78,17 +85,44 @@ def emit_table(name, prog):
                 off = len(blob)
                 blob += tb
             ln = len(tb)
-        rows.append((kind, arg, cond, off, ln))
+            assert off < 2048 and ln < 512
+            if cond == C_NONE: const_len += ln
+            elif cond == C_USER: user_lit += ln
+            elif cond == C_ALBUM: album_lit += ln
+            else: raise ValueError("literal under unsupported condition")
+        elif kind == K_FIELD:
+            assert cond in (C_NONE, C_USER)
+            nfield[cond == C_USER][arg] += 1
+        elif kind == K_CHAN:
+            assert cond in (C_NONE, C_USER)
+            nchan[cond == C_USER][arg] += 1
+        elif kind == K_CFG:
+            assert cond == C_NONE
+            ncfg[arg] += 1
+        elif kind == K_ESC:
+            nesc[arg] = nesc.get(arg, 0) + 1
+            assert nesc[arg] == 1 and cond == {E_DESC: C_NONE, E_MEDIA: C_HAS_MEDIA, E_HANDLE: C_NONE, E_ALT: C_CT_OTHER}[arg]
+        rows.append(kind | (arg << 4) | (cond << 8) | (off << 12) | (ln << 23))
     lines = [f"// generated by tools/gen_pieces.py — do not edit",
              f"constexpr int k{name}NPieces = {len(rows)};",
+             f"// closed-form length of the fixed part of the line: L = field lengths, chan / cf = segment lengths",
+             f"DEVI uint32_t {name.lower()}_size_fixed(const uint32_t* L, const uint32_t* chan, const uint32_t* cf, bool has_user, bool album) {{",
+             f"  uint32_t t = {const_len}u" + "".join(f" + {c}u * L[{j}]" for j, c in enumerate(nfield[0]) if c)
+             + "".join(f" + {c}u * chan[{j}]" for j, c in enumerate(nchan[0]) if c)
+             + "".join(f" + {c}u * cf[{j}]" for j, c in enumerate(ncfg) if c) + ";",
+             f"  if (has_user) t += {user_lit}u" + "".join(f" + {c}u * L[{j}]" for j, c in enumerate(nfield[1]) if c)
+             + "".join(f" + {c}u * chan[{j}]" for j, c in enumerate(nchan[1]) if c) + ";",
+             f"  if (album) t += {album_lit}u;",
+             f"  return t;",
+             f"}}",
              f"__device__ const char k{name}Template[] ="]
     bb = bytes(blob)
     for i in range(0, len(bb), 72):
         lines.append("    " + c_string(bb[i:i + 72]))
     lines[-1] += ";"
-    lines.append(f"__constant__ Piece k{name}Pieces[k{name}NPieces] = {{")
-    for r in rows:
-        lines.append("    {%d, %d, %d, 0, %d, %d}," % r)
+    lines.append(f"__constant__ uint32_t k{name}Pieces[k{name}NPieces] = {{")
+    for i in range(0, len(rows), 6):
+        lines.append("    " + ", ".join("0x%08xu" % r for r in rows[i:i + 6]) + ",")
     lines.append("};")
     return "\n".join(lines) + "\n"
 
