@@ -274,17 +274,23 @@ DEVI uint32_t ndigits_i64(int64_t v) { return v < 0 ? 1u + ndigits_u64((uint64_t
 __device__ __noinline__ int render_u64(uint8_t* dst, uint64_t v) {
   int n = (int)ndigits_u64(v);
   int k = n;
-  while (v >> 32) {
-    uint64_t q = v / 10;
-    dst[--k] = (uint8_t)('0' + (uint32_t)(v - q * 10));
+  while (v >> 32) {  // peel 9 digits at a time with one 64-bit division
+    uint64_t q = v / 1000000000ull;
+    uint32_t r = (uint32_t)(v - q * 1000000000ull);
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      uint32_t t = r / 10;
+      dst[--k] = (uint8_t)('0' + (r - t * 10));
+      r = t;
+    }
     v = q;
   }
   uint32_t r = (uint32_t)v;
-  do {
-    uint32_t q = r / 10;
-    dst[--k] = (uint8_t)('0' + (r - q * 10));
-    r = q;
-  } while (k > 0);
+  while (k > 0) {
+    uint32_t t = r / 10;
+    dst[--k] = (uint8_t)('0' + (r - t * 10));
+    r = t;
+  }
   return n;
 }
 DEVI int render_i64(uint8_t* dst, int64_t v) {
@@ -466,8 +472,8 @@ DEVI uint32_t thread_esc(const uint8_t* s, uint32_t n, uint32_t d, uint32_t cap)
 // 128-bit stores.  The first `skip` bytes belong to the previous warp's range and are never written
 // from here.  The struct is kept in registers: heavy operations are free functions that take and
 // return it by value.
-constexpr int EMIT_CAP = 4096;       // per-warp staging bytes
-constexpr int EMIT_FLUSH_AT = 3072;  // flush before a piece when fill exceeds this (piece <= 1 KiB)
+constexpr int EMIT_CAP = 6144;       // per-warp staging bytes
+constexpr int EMIT_FLUSH_AT = 5120;  // flush before a piece when fill exceeds this (piece <= 1 KiB)
 
 struct Em {
   uint32_t sbuf;   // shared-space address of the staging buffer (16-byte aligned)
@@ -560,17 +566,18 @@ DEVI void em_ch2(Em& e, uint32_t c0, uint32_t c1) {
   }
   e.fill += 2;
 }
-// JSON-escape s[0..n) into the stream (no quotes), 128-byte strips, 4 bytes per lane
-__device__ __noinline__ Em em_esc(Em e, const uint8_t* s, uint32_t n) {
-  uint32_t carry = 0;
-  for (int64_t base = 0; base < (int64_t)n; base += 128) {
-    em_room(e);  // one strip expands to at most 768 bytes
+// JSON-escape the strips [b0, b1) of s[0..n) to shared memory at dst (no quotes); returns the bytes
+// written.  128-byte strips, 4 bytes per lane.  `carry` threads the UTF-8 context between calls.
+__device__ __noinline__ uint32_t esc_range(uint32_t dst, const uint8_t* s, uint32_t n, uint32_t b0, uint32_t b1,
+                                           uint32_t& carry_io) {
+  uint32_t carry = carry_io, out = 0;
+  for (int64_t base = b0; base < (int64_t)b1; base += 128) {
     Strip st = warp_load_strip(s, base, n, carry);
     uint32_t el, u;
     strip_lane_totals(st, s, base, n, el, u);
     uint32_t incl = warp_incl_scan(el);
     uint32_t tot = __shfl_sync(FULL, incl, 31);
-    uint32_t d = e.sbuf + e.fill + (incl - el);
+    uint32_t d = dst + out + (incl - el);
     if (st.nvalid) {
       if (!st.exact) {
         if (el == st.nvalid) {  // nothing to escape in this lane's bytes
@@ -605,9 +612,35 @@ __device__ __noinline__ Em em_esc(Em e, const uint8_t* s, uint32_t n) {
         }
       }
     }
-    e.fill += tot;
+    out += tot;
   }
-  return e;
+  carry_io = carry;
+  return out;
+}
+// streaming form: at most 512 input bytes (<= 3 KiB of output) between capacity checks
+DEVI void em_esc_stream(Em& e, const uint8_t* s, uint32_t n) {
+  uint32_t carry = 0;
+  for (uint32_t b0 = 0; b0 < n; b0 += 128) {
+    em_room(e);  // one strip expands to at most 768 bytes
+    e.fill += esc_range(e.sbuf + e.fill, s, n, b0, b0 + 128 < n ? b0 + 128 : n, carry);
+  }
+}
+// whole string in one go: the caller guarantees the room (lane-parallel path)
+DEVI void em_esc_fit(Em& e, const uint8_t* s, uint32_t n) {
+  uint32_t carry = 0;
+  if (n) e.fill += esc_range(e.sbuf + e.fill, s, n, 0, n, carry);
+}
+// global -> shared copy at a fixed position, any length, 4 independent loads in flight per lane
+DEVI void copy_g_to(uint32_t dst, const uint8_t* src, uint32_t n) {
+  uint32_t l = lane_id();
+  uint32_t d = dst + l;
+  const uint8_t* s = src + l;
+  uint32_t i = 0;
+  for (; i + 128 <= n; i += 128) {
+    uint32_t b0 = ldb(s + i), b1 = ldb(s + i + 32), b2 = ldb(s + i + 64), b3 = ldb(s + i + 96);
+    sts8(d + i, b0); sts8(d + i + 32, b1); sts8(d + i + 64, b2); sts8(d + i + 96, b3);
+  }
+  for (; i + l < n; i += 32) sts8(d + i, ldb(s + i));
 }
 
 }  // namespace tgi

@@ -20,7 +20,8 @@ constexpr int EMIT_RECS_PER_WARP = 8;  // contiguous records per warp task in th
 #define ERR_TOO_MANY_LINKS 8
 
 // dynamic shared memory of the emitting kernels: per-warp staging buffers, then per-warp scratch
-constexpr size_t EMIT_SMEM_BYTES = (size_t)WARPS_PER_CTA * (EMIT_CAP + sizeof(WarpScratch));
+constexpr size_t EMIT_SMEM_BYTES = (size_t)WARPS_PER_CTA * (EMIT_CAP + sizeof(WarpScratch)) + sizeof(CtaShared);
+DEVI CtaShared* emit_cta_shared(uint8_t* dyn) { return (CtaShared*)(dyn + (size_t)WARPS_PER_CTA * (EMIT_CAP + sizeof(WarpScratch))); }
 DEVI uint32_t emit_stage_addr(uint8_t* dyn, int wid) { return smem_addr(dyn + (size_t)wid * EMIT_CAP); }
 DEVI WarpScratch* emit_scratch(uint8_t* dyn, int wid) {
   return (WarpScratch*)(dyn + (size_t)WARPS_PER_CTA * EMIT_CAP) + wid;
@@ -60,6 +61,9 @@ struct ParseOut {
   uint32_t* linelen;     // [n]
   uint32_t* link_start;  // [n] arena index of the record's first link
   uint32_t* link_count;  // [n]
+  uint32_t* xlen;        // [n][8] emitted lengths of the variable pieces (XL_*)
+  uint32_t* long_list;   // records whose line does not fit the staging buffer (sequential kernel)
+  uint32_t* long_count;
   tgi_link* arena;
   uint32_t arena_cap;
   uint32_t* cursor;      // arena allocation cursor (keeps counting past arena_cap)
@@ -85,7 +89,7 @@ DEVI TgRecView load_rec_view(const TgBatchDev& b, uint64_t r) {
   return v;
 }
 
-__global__ void __launch_bounds__(CTA_THREADS) tg_parse_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) {
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) {
   int wid = threadIdx.x >> 5, l = lane_id();
   uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
@@ -133,8 +137,15 @@ __global__ void __launch_bounds__(CTA_THREADS) tg_parse_kernel(TgBatchDev b, Cfg
         a.v = v;
         a.links = o.arena + lstart;
         a.n_links = nlinks;
-        llen = size_tg_record(a);
+        uint32_t xl[XL_COUNT];
+        llen = size_tg_record(a, xl);
         if (llen == 0) status = TGI_ST_NOLINE;
+        uint32_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < XL_COUNT; j++)
+          if (l == j) mine = xl[j];
+        if (l < 8) o.xlen[r * 8 + l] = mine;
+        if (l == 0 && llen + 16 > (uint32_t)EMIT_FLUSH_AT) o.long_list[atomicAdd(o.long_count, 1u)] = (uint32_t)r;
       }
     }
     if (l == 0) {
@@ -147,12 +158,16 @@ __global__ void __launch_bounds__(CTA_THREADS) tg_parse_kernel(TgBatchDev b, Cfg
 }
 
 // ---- emit ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CTA_THREADS) tg_emit_kernel(TgBatchDev b, CfgDev cfg, const uint8_t* status, const uint64_t* line_off,
-                               const uint32_t* link_start, const uint32_t* link_count,
-                               const tgi_link* arena, uint8_t* out) {
+__global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_kernel(TgBatchDev b, CfgDev cfg, const uint8_t* status, const uint64_t* line_off,
+                               const uint32_t* link_start, const uint32_t* link_count, const uint32_t* xlen,
+                               const tgi_link* arena, uint8_t* out, int* err) {
   extern __shared__ __align__(16) uint8_t dyn[];
   int wid = threadIdx.x >> 5;
   WarpScratch* ws = emit_scratch(dyn, wid);
+  CtaShared* cs = emit_cta_shared(dyn);
+  for (int i = threadIdx.x; i < kTgNEnt; i += blockDim.x) cs->ents[i] = kTgEnts[i];
+  for (int i = threadIdx.x; i < kTgTemplateLen; i += blockDim.x) cs->tmpl[i] = (uint8_t)kTgTemplate[i];
+  __syncthreads();
   const uint32_t stage = emit_stage_addr(dyn, wid);
   uint64_t ntasks = (b.n + EMIT_RECS_PER_WARP - 1) / EMIT_RECS_PER_WARP;
   uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
@@ -169,10 +184,39 @@ __global__ void __launch_bounds__(CTA_THREADS) tg_emit_kernel(TgBatchDev b, CfgD
       a.v = load_rec_view(b, r);
       a.links = arena + link_start[r];
       a.n_links = link_count[r];
-      e = emit_tg_record(e, ws, a);
+      uint32_t total = (uint32_t)(line_off[r + 1] - line_off[r]);
+      if (total + 16 <= (uint32_t)EMIT_FLUSH_AT) {
+        if (e.fill + total > (uint32_t)EMIT_FLUSH_AT) e = em_flush(e);
+        e = emit_tg_record_fast(e, ws, cs, a, total, xlen + r * 8, err);
+      } else {  // long line: written by tg_emit_long_kernel; restart the stream behind it
+        em_finish(e);
+        e = em_begin(stage, out, line_off[r + 1]);
+      }
     }
     em_finish(e);
   }
+}
+
+// long lines (> staging capacity): one warp per record, sequential piece walk, streaming flushes
+__global__ void __launch_bounds__(CTA_THREADS) tg_emit_long_kernel(TgBatchDev b, CfgDev cfg, const uint32_t* long_list, uint32_t n_long,
+                                                               const uint64_t* line_off, const uint32_t* link_start,
+                                                               const uint32_t* link_count, const tgi_link* arena, uint8_t* out) {
+  extern __shared__ __align__(16) uint8_t dyn[];
+  int wid = threadIdx.x >> 5;
+  uint32_t i = blockIdx.x * WARPS_PER_CTA + wid;
+  if (i >= n_long) return;
+  uint64_t r = long_list[i];
+  WarpScratch* ws = emit_scratch(dyn, wid);
+  Em e = em_begin(emit_stage_addr(dyn, wid), out, line_off[r]);
+  TgWalkArgs a;
+  a.b = &b;
+  a.cfg = &cfg;
+  a.r = r;
+  a.v = load_rec_view(b, r);
+  a.links = arena + link_start[r];
+  a.n_links = link_count[r];
+  e = emit_tg_record_seq(e, ws, a);
+  em_finish(e);
 }
 
 // ---- exclusive scan u32 -> u64 (out has n+1 entries) ----------------------------------------------

@@ -66,13 +66,22 @@ struct WarpScratch {
   uint32_t flen[8];        // their lengths
   uint64_t src_ptr[8];     // global sources: chan segments 0..3, cfg segments 4..7
   uint32_t src_len[8];
+  uint32_t xlen[8];        // emitted lengths of the variable pieces (XL_*), computed by the parse kernel
   uint8_t rslot[32][64];   // per-lane rendered map entries  "key":count
 };
 
 enum { K_LIT, K_FIELD, K_CHAN, K_CFG, K_ESC, K_POSTTYPE, K_COMMENTS, K_REACTIONS, K_OUTLINKS };
 enum { C_NONE, C_USER, C_ALBUM, C_CT_OTHER, C_NOT_CT_OTHER, C_HAS_MEDIA };
-enum { F_MSGNO, F_CHAT, F_VIEW, F_SHARE, F_NCOMM, F_TIME };
+enum { F_MSGNO, F_CHAT, F_VIEW, F_SHARE, F_NCOMM, F_TIME, F_POSTTYPE };
+enum { XL_DESC, XL_MEDIA, XL_HANDLE, XL_ALT, XL_COMMENTS, XL_REACTIONS, XL_OUTLINKS, XL_COUNT };
+constexpr uint32_t K_NOP = 15;
 #include "tg_pieces.inc"
+
+// block-shared copies of the template and the lane-parallel entry table (filled once per CTA)
+struct CtaShared {
+  uint32_t ents[kTgNEnt];
+  __align__(16) uint8_t tmpl[(kTgTemplateLen + 15) / 16 * 16];
+};
 
 // ---- map[string]int (reactions) ------------------------------------------------------------------
 // encoding/json sorts map keys bytewise; later duplicates of a key overwrite earlier ones (Go map
@@ -135,6 +144,7 @@ __device__ __noinline__ uint32_t size_reaction_map(const tgi_reaction* reacts, u
   return 2u + warp_sum(mine) + (m.nlive - 1);
 }
 
+template <bool STREAM>
 __device__ __noinline__ Em emit_reaction_map(Em e, WarpScratch* ws, const tgi_reaction* reacts, uint32_t r0, uint32_t r1,
                                              const uint8_t* aux) {
   if (r1 == r0) {
@@ -172,7 +182,7 @@ __device__ __noinline__ Em emit_reaction_map(Em e, WarpScratch* ws, const tgi_re
       uint32_t lj = __shfl_sync(FULL, m.kl, src);
       int32_t cj = __shfl_sync(FULL, m.cnt, src);
       em_ch(e, '"');
-      e = em_esc(e, pj, lj);
+      if (STREAM) em_esc_stream(e, pj, lj); else em_esc_fit(e, pj, lj);
       em_ch2(e, '"', ':');
       uint32_t dl = 0;
       __syncwarp();
@@ -208,6 +218,7 @@ __device__ __noinline__ uint32_t size_tg_comments(const TgBatchDev& b, uint32_t 
   return tot;
 }
 
+template <bool STREAM>
 __device__ __noinline__ Em emit_tg_comments(Em e, WarpScratch* ws, const TgBatchDev& b, uint32_t c0, uint32_t c1) {
   int l = lane_id();
   em_ch(e, '[');
@@ -220,16 +231,16 @@ __device__ __noinline__ Em emit_tg_comments(Em e, WarpScratch* ws, const TgBatch
     uint32_t d0 = __shfl_sync(FULL, dl, 0), d1 = __shfl_sync(FULL, dl, 1);
     if (k > c0) em_ch(e, ',');
     em_copy_g(e, (const uint8_t*)kCm0, sizeof(kCm0) - 1);
-    e = em_esc(e, b.aux + cm.text_off, cm.text_len);
+    if (STREAM) em_esc_stream(e, b.aux + cm.text_off, cm.text_len); else em_esc_fit(e, b.aux + cm.text_off, cm.text_len);
     em_copy_g(e, (const uint8_t*)kCm1, sizeof(kCm1) - 1);
-    if (cm.flags & 1) e = emit_reaction_map(e, ws, b.reacts, cm.react_start, cm.react_start + cm.react_count, b.aux);
+    if (cm.flags & 1) e = emit_reaction_map<STREAM>(e, ws, b.reacts, cm.react_start, cm.react_start + cm.react_count, b.aux);
     else em_copy_g(e, (const uint8_t*)kNullLit, 4);
     em_copy_g(e, (const uint8_t*)kCm2, sizeof(kCm2) - 1);
     em_copy_s(e, smem_addr(ws->field[6]), d0);
     em_copy_g(e, (const uint8_t*)kCm3, sizeof(kCm3) - 1);
     em_copy_s(e, smem_addr(ws->field[7]), d1);
     em_copy_g(e, (const uint8_t*)kCm4, sizeof(kCm4) - 1);
-    e = em_esc(e, b.aux + cm.handle_off, cm.handle_len);
+    if (STREAM) em_esc_stream(e, b.aux + cm.handle_off, cm.handle_len); else em_esc_fit(e, b.aux + cm.handle_off, cm.handle_len);
     em_copy_g(e, (const uint8_t*)kCm5, sizeof(kCm5) - 1);
     __syncwarp();
   }
@@ -294,7 +305,7 @@ DEVI TgDerived tg_derive(const TgWalkArgs& a, const ChanDerived& cd) {
 
 // line length in bytes; 0 if a time field is not representable (Marshal error -> TGI_ST_NOLINE).
 // The formula's coefficients come from the generated piece table, so it cannot drift from emit.
-DEVI uint32_t size_tg_record(const TgWalkArgs& a) {
+DEVI uint32_t size_tg_record(const TgWalkArgs& a, uint32_t* xl) {
   const TgBatchDev& b = *a.b;
   const CfgDev& cfg = *a.cfg;
   const tgi_tg_rec* rec = a.v.rec;
@@ -307,26 +318,25 @@ DEVI uint32_t size_tg_record(const TgWalkArgs& a) {
   uint32_t chan[4] = {cd.user_len, cd.name_len, cd.title_len, cd.cdata_len};
   uint32_t cf[4] = {cfg.label_len, cfg.created_tg_len, cfg.created_yt_len, cfg.capture_len};
   uint32_t tot = tg_size_fixed(L, chan, cf, d.has_user, d.album);
-  tot += warp_esc_len(d.desc, d.desc_len);
-  tot += a.v.ct == TGI_CT_OTHER ? warp_esc_len(a.v.alt, a.v.alt_len) : (uint32_t)kPostTypeLen[a.v.ct];
-  if (d.has_media) tot += warp_esc_len(a.v.media, a.v.media_len);
-  tot += warp_esc_len(a.v.handle, a.v.handle_len);
-  tot += d.comments_nil ? 4u : size_tg_comments(b, d.c0, d.c1);
-  tot += size_reaction_map(b.reacts, b.react_off[a.r], b.react_off[a.r + 1], b.aux);
-  tot += size_tg_outlinks(a.links, a.n_links);
+  xl[XL_DESC] = warp_esc_len(d.desc, d.desc_len);
+  xl[XL_ALT] = a.v.ct == TGI_CT_OTHER ? warp_esc_len(a.v.alt, a.v.alt_len) : 0u;
+  xl[XL_MEDIA] = d.has_media ? warp_esc_len(a.v.media, a.v.media_len) : 0u;
+  xl[XL_HANDLE] = warp_esc_len(a.v.handle, a.v.handle_len);
+  xl[XL_COMMENTS] = d.comments_nil ? 4u : size_tg_comments(b, d.c0, d.c1);
+  xl[XL_REACTIONS] = size_reaction_map(b.reacts, b.react_off[a.r], b.react_off[a.r + 1], b.aux);
+  xl[XL_OUTLINKS] = size_tg_outlinks(a.links, a.n_links);
+  tot += a.v.ct == TGI_CT_OTHER ? 0u : (uint32_t)kPostTypeLen[a.v.ct];
+  for (int j = 0; j < XL_COUNT; j++) tot += xl[j];
   return tot;
 }
 
-DEVI Em emit_tg_record(Em e, WarpScratch* ws, const TgWalkArgs& a) {
+// prologue of both emit paths: lanes render the numeric / time fields and fill the source tables
+DEVI void emit_tg_prologue(WarpScratch* ws, const TgWalkArgs& a, const ChanDerived& cd, const TgDerived& d,
+                           const uint32_t* xlen_g) {
   const TgBatchDev& b = *a.b;
   const CfgDev& cfg = *a.cfg;
   const tgi_tg_rec* rec = a.v.rec;
   int l = lane_id();
-  const ChanDerived cd = b.chan_derived[rec->chan_idx];
-  TgDerived d = tg_derive(a, cd);
-  const uint32_t ws_s = smem_addr(ws);
-
-  // prologue: lanes 0..5 render the numeric / time fields, lanes 8..15 fill the source table
   __syncwarp();
   if (l < 5) {
     int64_t v = l == 0 ? rec->id / 1048576                                     // tdutils.go:1008
@@ -336,6 +346,12 @@ DEVI Em emit_tg_record(Em e, WarpScratch* ws, const TgWalkArgs& a) {
     ws->flen[l] = (uint32_t)render_i64(ws->field[l], v);
   } else if (l == 5) {
     ws->flen[5] = (uint32_t)render_time(ws->field[5], rec->date, 0, cfg.tz);  // :417
+  } else if (l == 6) {  // MessageContentType() string (28-byte rows, 4-byte aligned)
+    const uint32_t* src = (const uint32_t*)kPostType[a.v.ct];
+    uint32_t* dst = (uint32_t*)ws->field[F_POSTTYPE];
+#pragma unroll
+    for (int w = 0; w < 7; w++) dst[w] = src[w];
+    ws->flen[F_POSTTYPE] = kPostTypeLen[a.v.ct];
   } else if (l >= 8 && l < 12) {
     int k = l - 8;
     uint32_t o = k == 0 ? 0u : k == 1 ? cd.user_len : k == 2 ? cd.user_len + cd.name_len : cd.user_len + cd.name_len + cd.title_len;
@@ -347,13 +363,26 @@ DEVI Em emit_tg_record(Em e, WarpScratch* ws, const TgWalkArgs& a) {
                                                                : cfg.label_len + cfg.created_tg_len + cfg.created_yt_len;
     ws->src_ptr[4 + k] = (uint64_t)(uintptr_t)(cfg.blob + o);
     ws->src_len[4 + k] = k == 0 ? cfg.label_len : k == 1 ? cfg.created_tg_len : k == 2 ? cfg.created_yt_len : cfg.capture_len;
+  } else if (l >= 16 && l < 16 + XL_COUNT && xlen_g) {
+    ws->xlen[l - 16] = xlen_g[l - 16];
   }
   __syncwarp();
+}
 
+DEVI uint32_t tg_condmask(const TgWalkArgs& a, const TgDerived& d) {
+  return 1u | (d.has_user ? 1u << C_USER : 0) | (d.album ? 1u << C_ALBUM : 0) |
+         (a.v.ct == TGI_CT_OTHER ? 1u << C_CT_OTHER : 1u << C_NOT_CT_OTHER) | (d.has_media ? 1u << C_HAS_MEDIA : 0);
+}
+
+// sequential path (any line length): walk the piece table, streaming through the staging buffer
+__device__ __noinline__ Em emit_tg_record_seq(Em e, WarpScratch* ws, const TgWalkArgs& a) {
+  const TgBatchDev& b = *a.b;
+  const ChanDerived cd = b.chan_derived[a.v.rec->chan_idx];
+  TgDerived d = tg_derive(a, cd);
+  const uint32_t ws_s = smem_addr(ws);
+  emit_tg_prologue(ws, a, cd, d, nullptr);
   const uint32_t ct = a.v.ct;
-  const uint32_t condmask = 1u | (d.has_user ? 1u << C_USER : 0) | (d.album ? 1u << C_ALBUM : 0) |
-                            (ct == TGI_CT_OTHER ? 1u << C_CT_OTHER : 1u << C_NOT_CT_OTHER) |
-                            (d.has_media ? 1u << C_HAS_MEDIA : 0);
+  const uint32_t condmask = tg_condmask(a, d);
   for (int pi = 0; pi < kTgNPieces; pi++) {
     const uint32_t pc = kTgPieces[pi];
     const uint32_t kind = pc & 15u, arg = (pc >> 4) & 15u;
@@ -369,18 +398,123 @@ DEVI Em emit_tg_record(Em e, WarpScratch* ws, const TgWalkArgs& a) {
     } else if (kind == K_ESC) {
       const uint8_t* p = arg == 0 ? d.desc : arg == 1 ? a.v.media : arg == 2 ? a.v.handle : a.v.alt;
       uint32_t n = arg == 0 ? d.desc_len : arg == 1 ? a.v.media_len : arg == 2 ? a.v.handle_len : a.v.alt_len;
-      e = em_esc(e, p, n);
+      em_esc_stream(e, p, n);
     } else if (kind == K_POSTTYPE) {
       em_copy_g(e, (const uint8_t*)kPostType[ct], kPostTypeLen[ct]);
     } else if (kind == K_COMMENTS) {
       if (d.comments_nil) em_copy_g(e, (const uint8_t*)kNullLit, 4);
-      else e = emit_tg_comments(e, ws, b, d.c0, d.c1);
+      else e = emit_tg_comments<true>(e, ws, b, d.c0, d.c1);
     } else if (kind == K_REACTIONS) {
-      e = emit_reaction_map(e, ws, b.reacts, b.react_off[a.r], b.react_off[a.r + 1], b.aux);
+      e = emit_reaction_map<true>(e, ws, b.reacts, b.react_off[a.r], b.react_off[a.r + 1], b.aux);
     } else {
       e = emit_tg_outlinks(e, a.links, a.n_links);
     }
   }
+  return e;
+}
+
+// lane-parallel path: the whole line (total bytes, <= EMIT_FLUSH_AT - fill) is assembled out of order.
+// Every lane owns kTgEPL consecutive entries of the entry table; an exclusive scan over the lanes'
+// length sums gives each entry its offset.  Small pieces (literal chunks, rendered fields) are
+// copied by their owning lane, 4 source bytes per step; the few variable pieces are then written
+// cooperatively at their scanned offsets.
+DEVI Em emit_tg_record_fast(Em e, WarpScratch* ws, const CtaShared* cs, const TgWalkArgs& a, uint32_t total,
+                            const uint32_t* xlen_g, int* err) {
+  const TgBatchDev& b = *a.b;
+  const ChanDerived cd = b.chan_derived[a.v.rec->chan_idx];
+  TgDerived d = tg_derive(a, cd);
+  const uint32_t ws_s = smem_addr(ws), ents_s = smem_addr(cs->ents), tmpl_s = smem_addr(cs->tmpl);
+  emit_tg_prologue(ws, a, cd, d, xlen_g);
+  const uint32_t condmask = tg_condmask(a, d);
+  const int l = lane_id();
+  uint32_t ent[kTgEPL], len[kTgEPL], off[kTgEPL];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < kTgEPL; k++) {
+    uint32_t en = lds32(ents_s + 4u * (uint32_t)(kTgEPL * l + k));
+    uint32_t kind = en & 15u, arg = (en >> 4) & 15u;
+    uint32_t ln = 0;
+    if ((condmask >> ((en >> 8) & 15u)) & 1u) {
+      if (kind == K_LIT) ln = en >> 23;
+      else if (kind == K_FIELD) ln = lds32(ws_s + (uint32_t)offsetof(WarpScratch, flen) + 4u * arg);
+      else if (kind == K_POSTTYPE) ln = lds32(ws_s + (uint32_t)offsetof(WarpScratch, flen) + 4u * F_POSTTYPE);
+      else if (kind == K_CHAN) ln = lds32(ws_s + (uint32_t)offsetof(WarpScratch, src_len) + 4u * arg);
+      else if (kind == K_CFG) ln = lds32(ws_s + (uint32_t)offsetof(WarpScratch, src_len) + 4u * (4u + arg));
+      else if (kind == K_ESC) ln = lds32(ws_s + (uint32_t)offsetof(WarpScratch, xlen) + 4u * arg);
+      else if (kind == K_COMMENTS) ln = lds32(ws_s + (uint32_t)offsetof(WarpScratch, xlen) + 4u * XL_COMMENTS);
+      else if (kind == K_REACTIONS) ln = lds32(ws_s + (uint32_t)offsetof(WarpScratch, xlen) + 4u * XL_REACTIONS);
+      else if (kind == K_OUTLINKS) ln = lds32(ws_s + (uint32_t)offsetof(WarpScratch, xlen) + 4u * XL_OUTLINKS);
+    }
+    ent[k] = en;
+    len[k] = ln;
+    sum += ln;
+  }
+  uint32_t incl = warp_incl_scan(sum);
+  uint32_t run = incl - sum;
+#pragma unroll
+  for (int k = 0; k < kTgEPL; k++) {
+    off[k] = run;
+    run += len[k];
+  }
+  if (__shfl_sync(FULL, incl, 31) != total) {  // sizing and emission disagree: never expected
+    if (l == 0) atomicOr(err, 16);
+    e.fill += total;  // keep the stream aligned; the host reports the error
+    return e;
+  }
+  const uint32_t base = e.sbuf + e.fill;
+  // lane-owned pieces
+#pragma unroll
+  for (int k = 0; k < kTgEPL; k++) {
+    uint32_t kind = ent[k] & 15u;
+    if (len[k] && (kind == K_LIT || kind == K_FIELD || kind == K_POSTTYPE)) {
+      uint32_t src = kind == K_LIT ? tmpl_s + ((ent[k] >> 12) & 0x7FFu)
+                                   : ws_s + (uint32_t)offsetof(WarpScratch, field) + 40u * (kind == K_FIELD ? (ent[k] >> 4) & 15u : F_POSTTYPE);
+      uint32_t dst = base + off[k], n = len[k];
+      for (uint32_t w = 0; w < n; w += 4) {
+        uint32_t v = lds32(src + w);
+        sts8(dst + w, v);
+        if (w + 1 < n) sts8(dst + w + 1, v >> 8);
+        if (w + 2 < n) sts8(dst + w + 2, v >> 16);
+        if (w + 3 < n) sts8(dst + w + 3, v >> 24);
+      }
+    }
+  }
+  // cooperative pieces, in line order
+  for (int bi = 0; bi < kTgNBig; bi++) {
+    const uint32_t idx = kTgBig[bi];
+    const uint32_t owner = idx / kTgEPL, kk = idx % kTgEPL;
+    uint32_t o_sel = off[0], l_sel = len[0];
+#pragma unroll
+    for (int k = 1; k < kTgEPL; k++)
+      if (kk == (uint32_t)k) { o_sel = off[k]; l_sel = len[k]; }
+    const uint32_t ln = __shfl_sync(FULL, l_sel, owner);
+    if (ln == 0) continue;
+    const uint32_t o = __shfl_sync(FULL, o_sel, owner);
+    const uint32_t en = kTgEnts[idx];
+    const uint32_t kind = en & 15u, arg = (en >> 4) & 15u;
+    if (kind == K_CHAN || kind == K_CFG) {
+      uint32_t si = (kind == K_CFG ? 4u : 0u) + arg;
+      copy_g_to(base + o, (const uint8_t*)(uintptr_t)ws->src_ptr[si], ln);
+    } else if (kind == K_ESC) {
+      const uint8_t* p = arg == 0 ? d.desc : arg == 1 ? a.v.media : arg == 2 ? a.v.handle : a.v.alt;
+      uint32_t n = arg == 0 ? d.desc_len : arg == 1 ? a.v.media_len : arg == 2 ? a.v.handle_len : a.v.alt_len;
+      uint32_t carry = 0;
+      esc_range(base + o, p, n, 0, n, carry);
+    } else {
+      Em t = e;
+      t.fill = e.fill + o;  // never reaches EMIT_FLUSH_AT: the caller checked fill + total
+      if (kind == K_COMMENTS) {
+        if (d.comments_nil) em_copy_g(t, (const uint8_t*)kNullLit, 4);
+        else t = emit_tg_comments<false>(t, ws, b, d.c0, d.c1);
+      } else if (kind == K_REACTIONS) {
+        t = emit_reaction_map<false>(t, ws, b.reacts, b.react_off[a.r], b.react_off[a.r + 1], b.aux);
+      } else {
+        t = emit_tg_outlinks(t, a.links, a.n_links);
+      }
+    }
+  }
+  __syncwarp();
+  e.fill += total;
   return e;
 }
 
@@ -418,13 +552,13 @@ DEVI Em emit_tg_chan(Em e, WarpScratch* ws, const TgBatchDev& b, uint32_t c) {
   if (l < 3) ws->flen[l] = (uint32_t)render_i64(ws->field[l], l == 0 ? ch.member_count : l == 1 ? ch.post_count : ch.view_count);
   __syncwarp();
   uint32_t L0 = ws->flen[0], L1 = ws->flen[1], L2 = ws->flen[2];
-  e = em_esc(e, user, ch.user_len);
-  e = em_esc(e, name, ch.name_len);
+  em_esc_stream(e, user, ch.user_len);
+  em_esc_stream(e, name, ch.name_len);
   em_ch(e, '"');
-  e = em_esc(e, title, ch.title_len);
+  em_esc_stream(e, title, ch.title_len);
   em_ch(e, '"');
   em_copy_g(e, (const uint8_t*)kCd0, sizeof(kCd0) - 1);
-  e = em_esc(e, title, ch.title_len);
+  em_esc_stream(e, title, ch.title_len);
   em_copy_g(e, (const uint8_t*)kCd1, sizeof(kCd1) - 1);
   em_copy_s(e, smem_addr(ws->field[0]), L0);
   em_copy_g(e, (const uint8_t*)kCd2, sizeof(kCd2) - 1);
@@ -432,9 +566,9 @@ DEVI Em emit_tg_chan(Em e, WarpScratch* ws, const TgBatchDev& b, uint32_t c) {
   em_copy_g(e, (const uint8_t*)kCd3, sizeof(kCd3) - 1);
   em_copy_s(e, smem_addr(ws->field[2]), L2);
   em_copy_g(e, (const uint8_t*)kCd4, sizeof(kCd4) - 1);
-  e = em_esc(e, name, ch.name_len);
+  em_esc_stream(e, name, ch.name_len);
   em_copy_g(e, (const uint8_t*)kCd5, sizeof(kCd5) - 1);
-  e = em_esc(e, name, ch.name_len);
+  em_esc_stream(e, name, ch.name_len);
   em_copy_g(e, (const uint8_t*)kCd6, sizeof(kCd6) - 1);
   __syncwarp();
   return e;

@@ -75,7 +75,7 @@ struct Slot {
       d_chans, d_chan_strs;
   // device intermediates / outputs
   DevBuf d_chan_derived, d_chan_len, d_chan_off, d_chan_blob, d_status, d_linelen, d_line_off,
-      d_link_start, d_link_count, d_arena, d_lstate, d_rec_new, d_new_off, d_link_off, d_links_out,
+      d_link_start, d_link_count, d_xlen, d_long, d_arena, d_lstate, d_rec_new, d_new_off, d_link_off, d_links_out,
       d_link_off32, d_btable, d_tiles, d_scalars, d_jsonl;
   // pinned host outputs
   HostBuf h_status, h_line_off, h_jsonl, h_link_off, h_links, h_scalars;
@@ -196,7 +196,7 @@ __global__ void cfg_label_size_kernel(const uint8_t* s, uint32_t n, uint32_t* ou
 __global__ void cfg_label_emit_kernel(const uint8_t* s, uint32_t n, uint8_t* out) {
   __shared__ __align__(16) uint8_t stage[EMIT_CAP];
   Em e = em_begin(smem_addr(stage), out, 0);
-  e = em_esc(e, s, n);
+  em_esc_stream(e, s, n);
   em_finish(e);
 }
 
@@ -328,7 +328,7 @@ int upload_tg(tgi_ctx* c, Slot& s, const tgi_tg_batch* in) {
 
 // scalars block (device + pinned mirror): [0] chan total, [1] line total, [2] cursor(u32)+err(int),
 // [3] n_new, [4] frontier size, [5] link total
-enum { SC_CHAN_TOTAL = 0, SC_LINE_TOTAL = 1, SC_CURSOR = 2, SC_NEW = 3, SC_FSIZE = 4, SC_LINK_TOTAL = 5, SC_COUNT = 8 };
+enum { SC_CHAN_TOTAL = 0, SC_LINE_TOTAL = 1, SC_CURSOR = 2, SC_NEW = 3, SC_FSIZE = 4, SC_LINK_TOTAL = 5, SC_LONG = 6, SC_COUNT = 8 };
 
 int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   TgBatchDev& b = s.tg;
@@ -350,6 +350,8 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   CK(s.d_line_off.ensure((n + 1) * 8));
   CK(s.d_link_start.ensure(n * 4));
   CK(s.d_link_count.ensure(n * 4));
+  CK(s.d_xlen.ensure(n * 32));
+  CK(s.d_long.ensure(n * 4));
   uint64_t arena_cap = s.n_ents + n / 2 + 1024;
   if (s.d_arena.cap / sizeof(tgi_link) > arena_cap + 8) arena_cap = (s.d_arena.cap - PAD) / sizeof(tgi_link);
 
@@ -376,6 +378,9 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     po.linelen = s.d_linelen.as<uint32_t>();
     po.link_start = s.d_link_start.as<uint32_t>();
     po.link_count = s.d_link_count.as<uint32_t>();
+    po.xlen = s.d_xlen.as<uint32_t>();
+    po.long_list = s.d_long.as<uint32_t>();
+    po.long_count = (uint32_t*)(dsc + SC_LONG);
     po.arena = s.d_arena.as<tgi_link>();
     po.arena_cap = (uint32_t)arena_cap;
     po.cursor = (uint32_t*)(dsc + SC_CURSOR);
@@ -426,13 +431,20 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     if (n) {
       uint64_t ntasks = (n + EMIT_RECS_PER_WARP - 1) / EMIT_RECS_PER_WARP;
       uint64_t want = (ntasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-      unsigned ge = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms * 5);
+      unsigned ge = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms * 3);
       CK(cudaEventRecord(s.ev_e0, st));
       tg_emit_kernel<<<ge, CTA_THREADS, EMIT_SMEM_BYTES, st>>>(b, cfg, s.d_status.as<uint8_t>(), s.d_line_off.as<uint64_t>(),
-                                                s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(),
-                                                s.d_arena.as<tgi_link>(), s.d_jsonl.as<uint8_t>());
-      CK(cudaEventRecord(s.ev_e1, st));
+                                                s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(), s.d_xlen.as<uint32_t>(),
+                                                s.d_arena.as<tgi_link>(), s.d_jsonl.as<uint8_t>(), (int*)(dsc + SC_CURSOR) + 1);
       launches++;
+      uint32_t n_long = ((uint32_t*)(hsc + SC_LONG))[0];
+      if (n_long) {
+        tg_emit_long_kernel<<<(n_long + WARPS_PER_CTA - 1) / WARPS_PER_CTA, CTA_THREADS, EMIT_SMEM_BYTES, st>>>(
+            b, cfg, s.d_long.as<uint32_t>(), n_long, s.d_line_off.as<uint64_t>(), s.d_link_start.as<uint32_t>(),
+            s.d_link_count.as<uint32_t>(), s.d_arena.as<tgi_link>(), s.d_jsonl.as<uint8_t>());
+        launches++;
+      }
+      CK(cudaEventRecord(s.ev_e1, st));
     }
     CK(cudaGetLastError());
   }
@@ -502,6 +514,7 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   CK(cudaStreamSynchronize(st));
   dev_err = ((int*)(hsc + SC_CURSOR))[1];
   if (dev_err & ERR_FRONTIER_FULL) { set_err(c, "frontier capacity %llu exceeded", (unsigned long long)c->fr.cap); return TGI_E_CAPACITY; }
+  if (dev_err & 16) { set_err(c, "internal: sized and emitted line lengths disagree"); return TGI_E_STATE; }
   n_links_total = want_links ? hsc[SC_LINK_TOTAL] : 0;
   if (d2h && want_links) {
     CK(s.h_link_off.ensure((n + 1) * 4));
@@ -673,6 +686,7 @@ int tgi_create(const tgi_config* cfg, tgi_ctx** out) {
   ctx->fr.tmask = tslots - 1;
   ctx->fr.count = ctx->d_fcount.as<uint64_t>();
   if (cudaFuncSetAttribute(tg_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMIT_SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(tg_emit_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMIT_SMEM_BYTES) != cudaSuccess ||
       cudaFuncSetAttribute(tg_chan_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMIT_SMEM_BYTES) != cudaSuccess) {
     set_err(c, "cudaFuncSetAttribute(max dynamic smem %zu) failed", (size_t)EMIT_SMEM_BYTES);
     return fail(TGI_E_CUDA);
@@ -702,7 +716,7 @@ void tgi_destroy(tgi_ctx* c) {
     DevBuf* db[] = {&s.d_recs, &s.d_strs, &s.d_ent_off, &s.d_ents, &s.d_react_off, &s.d_reacts, &s.d_comment_off,
                     &s.d_comments, &s.d_aux, &s.d_chans, &s.d_chan_strs, &s.d_chan_derived, &s.d_chan_len,
                     &s.d_chan_off, &s.d_chan_blob, &s.d_status, &s.d_linelen, &s.d_line_off, &s.d_link_start,
-                    &s.d_link_count, &s.d_arena, &s.d_lstate, &s.d_rec_new, &s.d_new_off, &s.d_link_off,
+                    &s.d_link_count, &s.d_xlen, &s.d_long, &s.d_arena, &s.d_lstate, &s.d_rec_new, &s.d_new_off, &s.d_link_off,
                     &s.d_links_out, &s.d_link_off32, &s.d_btable, &s.d_tiles, &s.d_scalars, &s.d_jsonl};
     for (DevBuf* d : db) d->release();
     HostBuf* hb[] = {&s.h_status, &s.h_line_off, &s.h_jsonl, &s.h_link_off, &s.h_links, &s.h_scalars};

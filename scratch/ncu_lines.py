@@ -32,3 +32,13 @@ def srcline(f, n):
     return srcs[f][n - 1].strip()[:100] if 0 < n <= len(srcs[f]) else ""
 for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:int(sys.argv[4]) if len(sys.argv) > 4 else 40]:
     print(f"{a[0]/ti*100:5.1f}% inst {a[1]/ts*100:5.1f}% smp thr {a[2]/max(a[0],1):4.1f}  {loc[0]}:{loc[1]}  {srcline(*loc)}")
+
+# bucket view: instructions per (file, 25-line bucket)
+print("---- buckets (>=1.5% of instructions)")
+bk = collections.defaultdict(lambda: [0, 0])
+for loc, a in agg.items():
+    k = (loc[0], loc[1] // 25 * 25)
+    bk[k][0] += a[0]; bk[k][1] += a[1]
+for k, a in sorted(bk.items(), key=lambda kv: -kv[1][0]):
+    if a[0] / ti > 0.015:
+        print(f"{a[0]/ti*100:5.1f}% inst {a[1]/ts*100:5.1f}% smp  {k[0]}:{k[1]}-{k[1]+24}  {srcline(k[0], k[1]+1)[:60]}")

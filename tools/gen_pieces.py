@@ -66,31 +66,43 @@ def c_string(b: bytes) -> str:
     return '"' + ''.join(out) + '"'
 
 
+CHUNK = 32  # lane-pieces are at most this long (one lane copies one piece)
+K_NOP = 15
+LANE_KINDS = (K_LIT, K_FIELD, K_POSTTYPE)
+
+
 def emit_table(name, prog):
-    """packed table: bits 0-3 kind, 4-7 arg, 8-11 cond, 12-22 template offset, 23-31 length;
-    plus the constants of the closed-form line-length formula, derived from the same program."""
+    """Two views of the same program:
+    (1) the sequential piece table (fallback path for lines longer than the staging buffer);
+    (2) the lane-parallel entry table: literals cut into <= 32-byte chunks whose template copies
+        start 4-byte aligned; entry e belongs to lane e // EPL, so an exclusive scan over the
+        per-lane length sums yields every piece's offset.
+    Both use the packing  kind | arg << 4 | cond << 8 | off << 12 | len << 23.
+    Also generates the closed-form size function from the same program."""
     blob = bytearray()
-    rows = []
+    rows, ents = [], []
     const_len = user_lit = album_lit = 0
     nfield = [[0] * 8, [0] * 8]      # [cond NONE, cond USER][field]
     nchan = [[0] * 4, [0] * 4]
     ncfg = [0] * 4
     nesc = {}
     for kind, arg, cond, text in prog:
-        off = ln = 0
         if kind == K_LIT:
             tb = text.encode()
-            off = blob.find(tb)  # share identical literals
-            if off < 0:
-                off = len(blob)
-                blob += tb
-            ln = len(tb)
-            assert off < 2048 and ln < 512
-            if cond == C_NONE: const_len += ln
-            elif cond == C_USER: user_lit += ln
-            elif cond == C_ALBUM: album_lit += ln
+            if cond == C_NONE: const_len += len(tb)
+            elif cond == C_USER: user_lit += len(tb)
+            elif cond == C_ALBUM: album_lit += len(tb)
             else: raise ValueError("literal under unsupported condition")
-        elif kind == K_FIELD:
+            while len(blob) % 4: blob.append(0)
+            base = len(blob)
+            blob += tb
+            assert len(tb) < 512 and base + len(tb) < 4096
+            rows.append(kind | (arg << 4) | (cond << 8) | (base << 12) | (len(tb) << 23))
+            for o in range(0, len(tb), CHUNK):  # chunk starts stay 4-aligned because CHUNK % 4 == 0
+                ln = min(CHUNK, len(tb) - o)
+                ents.append(kind | (cond << 8) | ((base + o) << 12) | (ln << 23))
+            continue
+        if kind == K_FIELD:
             assert cond in (C_NONE, C_USER)
             nfield[cond == C_USER][arg] += 1
         elif kind == K_CHAN:
@@ -102,9 +114,17 @@ def emit_table(name, prog):
         elif kind == K_ESC:
             nesc[arg] = nesc.get(arg, 0) + 1
             assert nesc[arg] == 1 and cond == {E_DESC: C_NONE, E_MEDIA: C_HAS_MEDIA, E_HANDLE: C_NONE, E_ALT: C_CT_OTHER}[arg]
-        rows.append(kind | (arg << 4) | (cond << 8) | (off << 12) | (ln << 23))
+        rows.append(kind | (arg << 4) | (cond << 8))
+        ents.append(kind | (arg << 4) | (cond << 8))
+    epl = (len(ents) + 31) // 32
+    big = [i for i, e in enumerate(ents) if (e & 15) not in LANE_KINDS]
+    ents += [K_NOP] * (32 * epl - len(ents))
     lines = [f"// generated by tools/gen_pieces.py — do not edit",
              f"constexpr int k{name}NPieces = {len(rows)};",
+             f"constexpr int k{name}EPL = {epl};            // lane-parallel entries per lane",
+             f"constexpr int k{name}NEnt = {32 * epl};",
+             f"constexpr int k{name}NBig = {len(big)};          // entries handled cooperatively, in line order",
+             f"constexpr int k{name}TemplateLen = {len(blob)};",
              f"// closed-form length of the fixed part of the line: L = field lengths, chan / cf = segment lengths",
              f"DEVI uint32_t {name.lower()}_size_fixed(const uint32_t* L, const uint32_t* chan, const uint32_t* cf, bool has_user, bool album) {{",
              f"  uint32_t t = {const_len}u" + "".join(f" + {c}u * L[{j}]" for j, c in enumerate(nfield[0]) if c)
@@ -115,15 +135,17 @@ def emit_table(name, prog):
              f"  if (album) t += {album_lit}u;",
              f"  return t;",
              f"}}",
-             f"__device__ const char k{name}Template[] ="]
+             f"__device__ __align__(16) const char k{name}Template[] ="]
     bb = bytes(blob)
-    for i in range(0, len(bb), 72):
-        lines.append("    " + c_string(bb[i:i + 72]))
+    for i in range(0, len(bb), 64):
+        lines.append("    " + c_string(bb[i:i + 64]))
     lines[-1] += ";"
-    lines.append(f"__constant__ uint32_t k{name}Pieces[k{name}NPieces] = {{")
-    for i in range(0, len(rows), 6):
-        lines.append("    " + ", ".join("0x%08xu" % r for r in rows[i:i + 6]) + ",")
-    lines.append("};")
+    for nm, arr in (("Pieces", rows), ("Ents", ents)):
+        lines.append(f"__device__ const uint32_t k{name}{nm}[{len(arr)}] = {{")
+        for i in range(0, len(arr), 6):
+            lines.append("    " + ", ".join("0x%08xu" % r for r in arr[i:i + 6]) + ",")
+        lines.append("};")
+    lines.append(f"__device__ const uint8_t k{name}Big[{len(big)}] = {{" + ", ".join(map(str, big)) + "};")
     return "\n".join(lines) + "\n"
 
 
