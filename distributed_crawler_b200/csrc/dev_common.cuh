@@ -49,7 +49,7 @@ DEVI uint32_t ascii_esc_len(uint32_t b) {
 
 // ---- exact UTF-8 decoding rules of Go's unicode/utf8 (DecodeRuneInString) -----------------------
 // returns the sequence length (2..4) if a VALID sequence starts at s[i], else 0.  s[i] >= 0x80.
-DEVI int utf8_valid_lead(const uint8_t* s, int64_t i, int64_t n) {
+__device__ __noinline__ int utf8_valid_lead(const uint8_t* s, int64_t i, int64_t n) {
   uint32_t b0 = ldb(s + i);
   if (b0 < 0xC2 || b0 > 0xF4) return 0;
   int need = b0 < 0xE0 ? 2 : (b0 < 0xF0 ? 3 : 4);
@@ -73,7 +73,7 @@ DEVI int utf8_valid_lead(const uint8_t* s, int64_t i, int64_t n) {
 struct ByteInfo {
   uint32_t esc, u16, start;
 };
-DEVI ByteInfo byte_info_exact(const uint8_t* s, int64_t i, int64_t n) {
+__device__ __noinline__ ByteInfo byte_info_exact(const uint8_t* s, int64_t i, int64_t n) {
   ByteInfo r;
   uint32_t b = ldb(s + i);
   if (b < 0x80) {
@@ -385,6 +385,12 @@ DEVI uint32_t lds32(uint32_t a) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
+DEVI uint32_t lds16(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+DEVI void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
 DEVI uint4 lds128(uint32_t a) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));

@@ -19,6 +19,8 @@ constexpr int EMIT_RECS_PER_WARP = 8;  // contiguous records per warp task in th
 #define ERR_FRONTIER_FULL 4
 #define ERR_TOO_MANY_LINKS 8
 
+DEVI bool tg_is_slow_record(uint32_t line_len, uint32_t n_comments) { return line_len + 16 > (uint32_t)EMIT_FLUSH_AT || n_comments != 0; }
+
 // dynamic shared memory of the emitting kernels: per-warp staging buffers, then per-warp scratch
 constexpr size_t EMIT_SMEM_BYTES = (size_t)WARPS_PER_CTA * (EMIT_CAP + sizeof(WarpScratch)) + sizeof(CtaShared);
 DEVI CtaShared* emit_cta_shared(uint8_t* dyn) { return (CtaShared*)(dyn + (size_t)WARPS_PER_CTA * (EMIT_CAP + sizeof(WarpScratch))); }
@@ -145,7 +147,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_kernel(TgBatchDev b, 
         for (int j = 0; j < XL_COUNT; j++)
           if (l == j) mine = xl[j];
         if (l < 8) o.xlen[r * 8 + l] = mine;
-        if (l == 0 && llen + 16 > (uint32_t)EMIT_FLUSH_AT) o.long_list[atomicAdd(o.long_count, 1u)] = (uint32_t)r;
+        // lines that do not fit the staging buffer, and the rare records with comments, take the
+        // sequential kernel (keeps the hot kernel's instruction footprint small)
+        if (l == 0 && tg_is_slow_record(llen, b.comment_off[r + 1] - b.comment_off[r])) o.long_list[atomicAdd(o.long_count, 1u)] = (uint32_t)r;
       }
     }
     if (l == 0) {
@@ -165,8 +169,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_kernel(TgBatchDev b, C
   int wid = threadIdx.x >> 5;
   WarpScratch* ws = emit_scratch(dyn, wid);
   CtaShared* cs = emit_cta_shared(dyn);
-  for (int i = threadIdx.x; i < kTgNEnt; i += blockDim.x) cs->ents[i] = kTgEnts[i];
-  for (int i = threadIdx.x; i < kTgTemplateLen; i += blockDim.x) cs->tmpl[i] = (uint8_t)kTgTemplate[i];
+  for (int i = threadIdx.x; i < kTgNEnt; i += blockDim.x) cs->ents[i] = kTgPieces[i];
+  for (int i = threadIdx.x; i < kTgNWords; i += blockDim.x) {
+    cs->tmpl[i] = ((const uint32_t*)kTgTemplate)[i];
+    cs->wmeta[i] = kTgWordMeta[i];
+  }
   __syncthreads();
   const uint32_t stage = emit_stage_addr(dyn, wid);
   uint64_t ntasks = (b.n + EMIT_RECS_PER_WARP - 1) / EMIT_RECS_PER_WARP;
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_kernel(TgBatchDev b, C
       a.links = arena + link_start[r];
       a.n_links = link_count[r];
       uint32_t total = (uint32_t)(line_off[r + 1] - line_off[r]);
-      if (total + 16 <= (uint32_t)EMIT_FLUSH_AT) {
+      if (!tg_is_slow_record(total, b.comment_off[r + 1] - b.comment_off[r])) {
         if (e.fill + total > (uint32_t)EMIT_FLUSH_AT) e = em_flush(e);
         e = emit_tg_record_fast(e, ws, cs, a, total, xlen + r * 8, err);
       } else {  // long line: written by tg_emit_long_kernel; restart the stream behind it

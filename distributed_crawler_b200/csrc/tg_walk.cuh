@@ -67,6 +67,7 @@ struct WarpScratch {
   uint64_t src_ptr[8];     // global sources: chan segments 0..3, cfg segments 4..7
   uint32_t src_len[8];
   uint32_t xlen[8];        // emitted lengths of the variable pieces (XL_*), computed by the parse kernel
+  uint32_t vshift[64];     // per piece: output offset - template offset (literal pieces), or VSHIFT_SKIP
   uint8_t rslot[32][64];   // per-lane rendered map entries  "key":count
 };
 
@@ -78,9 +79,11 @@ constexpr uint32_t K_NOP = 15;
 #include "tg_pieces.inc"
 
 // block-shared copies of the template and the lane-parallel entry table (filled once per CTA)
+#define VSHIFT_SKIP 0x80000000u
 struct CtaShared {
   uint32_t ents[kTgNEnt];
-  __align__(16) uint8_t tmpl[(kTgTemplateLen + 15) / 16 * 16];
+  uint32_t tmpl[kTgNWords];
+  uint16_t wmeta[kTgNWords];
 };
 
 // ---- map[string]int (reactions) ------------------------------------------------------------------
@@ -413,17 +416,18 @@ __device__ __noinline__ Em emit_tg_record_seq(Em e, WarpScratch* ws, const TgWal
   return e;
 }
 
-// lane-parallel path: the whole line (total bytes, <= EMIT_FLUSH_AT - fill) is assembled out of order.
-// Every lane owns kTgEPL consecutive entries of the entry table; an exclusive scan over the lanes'
-// length sums gives each entry its offset.  Small pieces (literal chunks, rendered fields) are
-// copied by their owning lane, 4 source bytes per step; the few variable pieces are then written
-// cooperatively at their scanned offsets.
+// lane-parallel path: the whole line (total bytes, fill + total <= EMIT_FLUSH_AT) is assembled out of
+// order.  Lane i owns pieces kTgEPL*i ..; an exclusive scan over the lanes' length sums gives each
+// piece its output offset.  Literal pieces only publish their shift (output offset - template offset);
+// the template is then copied word by word (340 words = 11 steps) with the shift of the owning piece.
+// Rendered fields are copied by their owning lane; the few variable pieces cooperatively.
 DEVI Em emit_tg_record_fast(Em e, WarpScratch* ws, const CtaShared* cs, const TgWalkArgs& a, uint32_t total,
                             const uint32_t* xlen_g, int* err) {
   const TgBatchDev& b = *a.b;
   const ChanDerived cd = b.chan_derived[a.v.rec->chan_idx];
   TgDerived d = tg_derive(a, cd);
   const uint32_t ws_s = smem_addr(ws), ents_s = smem_addr(cs->ents), tmpl_s = smem_addr(cs->tmpl);
+  const uint32_t vs_s = ws_s + (uint32_t)offsetof(WarpScratch, vshift);
   emit_tg_prologue(ws, a, cd, d, xlen_g);
   const uint32_t condmask = tg_condmask(a, d);
   const int l = lane_id();
@@ -462,13 +466,14 @@ DEVI Em emit_tg_record_fast(Em e, WarpScratch* ws, const CtaShared* cs, const Tg
     return e;
   }
   const uint32_t base = e.sbuf + e.fill;
-  // lane-owned pieces
+  // literal pieces publish their shift; field pieces are copied by their owning lane
 #pragma unroll
   for (int k = 0; k < kTgEPL; k++) {
     uint32_t kind = ent[k] & 15u;
-    if (len[k] && (kind == K_LIT || kind == K_FIELD || kind == K_POSTTYPE)) {
-      uint32_t src = kind == K_LIT ? tmpl_s + ((ent[k] >> 12) & 0x7FFu)
-                                   : ws_s + (uint32_t)offsetof(WarpScratch, field) + 40u * (kind == K_FIELD ? (ent[k] >> 4) & 15u : F_POSTTYPE);
+    if (kind == K_LIT) {
+      sts32(vs_s + 4u * (uint32_t)(kTgEPL * l + k), len[k] ? off[k] - ((ent[k] >> 12) & 0x7FFu) : VSHIFT_SKIP);
+    } else if (len[k] && (kind == K_FIELD || kind == K_POSTTYPE)) {
+      uint32_t src = ws_s + (uint32_t)offsetof(WarpScratch, field) + 40u * (kind == K_FIELD ? (ent[k] >> 4) & 15u : F_POSTTYPE);
       uint32_t dst = base + off[k], n = len[k];
       for (uint32_t w = 0; w < n; w += 4) {
         uint32_t v = lds32(src + w);
@@ -476,6 +481,24 @@ DEVI Em emit_tg_record_fast(Em e, WarpScratch* ws, const CtaShared* cs, const Tg
         if (w + 1 < n) sts8(dst + w + 1, v >> 8);
         if (w + 2 < n) sts8(dst + w + 2, v >> 16);
         if (w + 3 < n) sts8(dst + w + 3, v >> 24);
+      }
+    }
+  }
+  __syncwarp();
+  // the template, word by word
+  {
+    const uint32_t wm_s = smem_addr(cs->wmeta);
+#pragma unroll 2
+    for (uint32_t j = l; j < (uint32_t)kTgNWords; j += 32) {
+      uint32_t m = lds16(wm_s + 2u * j);
+      uint32_t sh = lds32(vs_s + 4u * (m >> 3));
+      if (sh != VSHIFT_SKIP) {
+        uint32_t v = lds32(tmpl_s + 4u * j);
+        uint32_t dst = base + 4u * j + sh, nv = m & 7u;
+        sts8(dst, v);
+        if (nv > 1) sts8(dst + 1, v >> 8);
+        if (nv > 2) sts8(dst + 2, v >> 16);
+        if (nv > 3) sts8(dst + 3, v >> 24);
       }
     }
   }
@@ -490,7 +513,7 @@ DEVI Em emit_tg_record_fast(Em e, WarpScratch* ws, const CtaShared* cs, const Tg
     const uint32_t ln = __shfl_sync(FULL, l_sel, owner);
     if (ln == 0) continue;
     const uint32_t o = __shfl_sync(FULL, o_sel, owner);
-    const uint32_t en = kTgEnts[idx];
+    const uint32_t en = kTgPieces[idx];
     const uint32_t kind = en & 15u, arg = (en >> 4) & 15u;
     if (kind == K_CHAN || kind == K_CFG) {
       uint32_t si = (kind == K_CFG ? 4u : 0u) + arg;
@@ -503,9 +526,9 @@ DEVI Em emit_tg_record_fast(Em e, WarpScratch* ws, const CtaShared* cs, const Tg
     } else {
       Em t = e;
       t.fill = e.fill + o;  // never reaches EMIT_FLUSH_AT: the caller checked fill + total
-      if (kind == K_COMMENTS) {
+      if (kind == K_COMMENTS) {  // records with comments never reach this kernel: "null" or "[]"
         if (d.comments_nil) em_copy_g(t, (const uint8_t*)kNullLit, 4);
-        else t = emit_tg_comments<false>(t, ws, b, d.c0, d.c1);
+        else em_ch2(t, '[', ']');
       } else if (kind == K_REACTIONS) {
         t = emit_reaction_map<false>(t, ws, b.reacts, b.react_off[a.r], b.react_off[a.r + 1], b.aux);
       } else {

@@ -35,6 +35,7 @@ class EngineFrontier:
         out = torch.empty((n, 32), dtype=torch.uint8, device=self.device)
         if n:
             got = C.c_uint64()
+            torch.cuda.synchronize(self.device)  # `out` was allocated on torch's stream
             self.e._check(self._lib.tgi_frontier_export_dev(self.e.h, out.data_ptr(), n, first, C.byref(got)))
             assert got.value == n
         return out
@@ -43,6 +44,9 @@ class EngineFrontier:
         n = int(keys.shape[0])
         if n:
             keys = keys.contiguous()
+            # the library launches on its own stream: the collective that produced `keys` (torch /
+            # NCCL streams) must have finished before its kernels read them
+            torch.cuda.synchronize(self.device)
             self.e._check(self._lib.tgi_frontier_insert_dev(self.e.h, keys.data_ptr(), n, None))
         return self.size()
 

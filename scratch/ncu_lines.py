@@ -30,7 +30,7 @@ def srcline(f, n):
         g = glob.glob(f"/root/repo/distributed_crawler_b200/csrc/{f}")
         srcs[f] = open(g[0]).read().splitlines() if g else []
     return srcs[f][n - 1].strip()[:100] if 0 < n <= len(srcs[f]) else ""
-for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:int(sys.argv[4]) if len(sys.argv) > 4 else 40]:
+for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(sys.argv[4]) if len(sys.argv) > 4 else 40]:
     print(f"{a[0]/ti*100:5.1f}% inst {a[1]/ts*100:5.1f}% smp thr {a[2]/max(a[0],1):4.1f}  {loc[0]}:{loc[1]}  {srcline(*loc)}")
 
 # bucket view: instructions per (file, 25-line bucket)

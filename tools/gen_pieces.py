@@ -66,26 +66,28 @@ def c_string(b: bytes) -> str:
     return '"' + ''.join(out) + '"'
 
 
-CHUNK = 32  # lane-pieces are at most this long (one lane copies one piece)
 K_NOP = 15
 LANE_KINDS = (K_LIT, K_FIELD, K_POSTTYPE)
 
 
 def emit_table(name, prog):
-    """Two views of the same program:
-    (1) the sequential piece table (fallback path for lines longer than the staging buffer);
-    (2) the lane-parallel entry table: literals cut into <= 32-byte chunks whose template copies
-        start 4-byte aligned; entry e belongs to lane e // EPL, so an exclusive scan over the
-        per-lane length sums yields every piece's offset.
-    Both use the packing  kind | arg << 4 | cond << 8 | off << 12 | len << 23.
-    Also generates the closed-form size function from the same program."""
+    """Generated from ONE program (the Post line in declaration order):
+    (1) the piece table  kind | arg << 4 | cond << 8 | off << 12 | len << 23; literal pieces start
+        4-byte aligned in the template blob and carry their ordinal (`arg`), so the emit kernel can
+        copy the whole template word by word with a per-piece shift (output offset - template offset);
+        entry e belongs to lane e // EPL: an exclusive warp scan over the per-lane length sums gives
+        every piece its output offset;
+    (2) per template word: owning piece index << 3 | valid bytes;
+    (3) the list of pieces that are written cooperatively (variable length);
+    (4) the closed-form length of the fixed part of the line."""
     blob = bytearray()
-    rows, ents = [], []
+    rows, wmeta = [], []
     const_len = user_lit = album_lit = 0
     nfield = [[0] * 8, [0] * 8]      # [cond NONE, cond USER][field]
     nchan = [[0] * 4, [0] * 4]
     ncfg = [0] * 4
     nesc = {}
+    nlit = 0
     for kind, arg, cond, text in prog:
         if kind == K_LIT:
             tb = text.encode()
@@ -96,11 +98,11 @@ def emit_table(name, prog):
             while len(blob) % 4: blob.append(0)
             base = len(blob)
             blob += tb
-            assert len(tb) < 512 and base + len(tb) < 4096
-            rows.append(kind | (arg << 4) | (cond << 8) | (base << 12) | (len(tb) << 23))
-            for o in range(0, len(tb), CHUNK):  # chunk starts stay 4-aligned because CHUNK % 4 == 0
-                ln = min(CHUNK, len(tb) - o)
-                ents.append(kind | (cond << 8) | ((base + o) << 12) | (ln << 23))
+            assert len(tb) < 512 and base + len(tb) < 2048
+            for o in range(0, len(tb), 4):
+                wmeta.append((len(rows) << 3) | min(4, len(tb) - o))  # piece index << 3 | valid bytes
+            rows.append(kind | (cond << 8) | (base << 12) | (len(tb) << 23))
+            nlit += 1
             continue
         if kind == K_FIELD:
             assert cond in (C_NONE, C_USER)
@@ -115,16 +117,20 @@ def emit_table(name, prog):
             nesc[arg] = nesc.get(arg, 0) + 1
             assert nesc[arg] == 1 and cond == {E_DESC: C_NONE, E_MEDIA: C_HAS_MEDIA, E_HANDLE: C_NONE, E_ALT: C_CT_OTHER}[arg]
         rows.append(kind | (arg << 4) | (cond << 8))
-        ents.append(kind | (arg << 4) | (cond << 8))
-    epl = (len(ents) + 31) // 32
-    big = [i for i, e in enumerate(ents) if (e & 15) not in LANE_KINDS]
-    ents += [K_NOP] * (32 * epl - len(ents))
+    while len(blob) % 4: blob.append(0)
+    assert len(wmeta) == len(blob) // 4
+    npieces = len(rows)
+    epl = (npieces + 31) // 32
+    big = [i for i, e in enumerate(rows) if (e & 15) not in LANE_KINDS]
+    ents = rows + [K_NOP] * (32 * epl - npieces)
     lines = [f"// generated by tools/gen_pieces.py — do not edit",
-             f"constexpr int k{name}NPieces = {len(rows)};",
-             f"constexpr int k{name}EPL = {epl};            // lane-parallel entries per lane",
+             f"constexpr int k{name}NPieces = {npieces};",
+             f"constexpr int k{name}EPL = {epl};            // entries per lane in the lane-parallel path",
              f"constexpr int k{name}NEnt = {32 * epl};",
-             f"constexpr int k{name}NBig = {len(big)};          // entries handled cooperatively, in line order",
-             f"constexpr int k{name}TemplateLen = {len(blob)};",
+             f"constexpr int k{name}NBig = {len(big)};          // pieces written cooperatively, in line order",
+             f"constexpr int k{name}NLit = {nlit};",
+             f"constexpr int k{name}TemplateLen = {len(blob)};   // multiple of 4",
+             f"constexpr int k{name}NWords = {len(blob) // 4};",
              f"// closed-form length of the fixed part of the line: L = field lengths, chan / cf = segment lengths",
              f"DEVI uint32_t {name.lower()}_size_fixed(const uint32_t* L, const uint32_t* chan, const uint32_t* cf, bool has_user, bool album) {{",
              f"  uint32_t t = {const_len}u" + "".join(f" + {c}u * L[{j}]" for j, c in enumerate(nfield[0]) if c)
@@ -140,11 +146,14 @@ def emit_table(name, prog):
     for i in range(0, len(bb), 64):
         lines.append("    " + c_string(bb[i:i + 64]))
     lines[-1] += ";"
-    for nm, arr in (("Pieces", rows), ("Ents", ents)):
-        lines.append(f"__device__ const uint32_t k{name}{nm}[{len(arr)}] = {{")
-        for i in range(0, len(arr), 6):
-            lines.append("    " + ", ".join("0x%08xu" % r for r in arr[i:i + 6]) + ",")
-        lines.append("};")
+    lines.append(f"__device__ const uint32_t k{name}Pieces[{len(ents)}] = {{")
+    for i in range(0, len(ents), 6):
+        lines.append("    " + ", ".join("0x%08xu" % r for r in ents[i:i + 6]) + ",")
+    lines.append("};")
+    lines.append(f"__device__ const uint16_t k{name}WordMeta[{len(wmeta)}] = {{")
+    for i in range(0, len(wmeta), 24):
+        lines.append("    " + ", ".join(map(str, wmeta[i:i + 24])) + ",")
+    lines.append("};")
     lines.append(f"__device__ const uint8_t k{name}Big[{len(big)}] = {{" + ", ".join(map(str, big)) + "};")
     return "\n".join(lines) + "\n"
 
