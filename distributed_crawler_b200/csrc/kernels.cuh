@@ -162,45 +162,73 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_kernel(TgBatchDev b, 
 }
 
 // ---- emit ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_kernel(TgBatchDev b, CfgDev cfg, const uint8_t* status, const uint64_t* line_off,
+// One persistent CTA of EMIT_WARPS warps per SM; every warp owns 8 consecutive records per task and
+// all warps walk through the record phases in lockstep (see tg_walk.cuh "in phases").
+constexpr int EMIT_WARPS = 24;
+constexpr size_t EMITP_SMEM_BYTES = (size_t)EMIT_WARPS * (EMIT_CAP + sizeof(WarpScratch)) + sizeof(CtaShared);
+
+__global__ void __launch_bounds__(EMIT_WARPS * 32, 1) tg_emit_kernel(TgBatchDev b, CfgDev cfg, const uint8_t* status, const uint64_t* line_off,
                                const uint32_t* link_start, const uint32_t* link_count, const uint32_t* xlen,
                                const tgi_link* arena, uint8_t* out, int* err) {
   extern __shared__ __align__(16) uint8_t dyn[];
-  int wid = threadIdx.x >> 5;
-  WarpScratch* ws = emit_scratch(dyn, wid);
-  CtaShared* cs = emit_cta_shared(dyn);
+  const int wid = threadIdx.x >> 5;
+  WarpScratch* ws = (WarpScratch*)(dyn + (size_t)EMIT_WARPS * EMIT_CAP) + wid;
+  CtaShared* cs = (CtaShared*)(dyn + (size_t)EMIT_WARPS * (EMIT_CAP + sizeof(WarpScratch)));
+  const uint32_t stage = smem_addr(dyn + (size_t)wid * EMIT_CAP);
   for (int i = threadIdx.x; i < kTgNEnt; i += blockDim.x) cs->ents[i] = kTgPieces[i];
   for (int i = threadIdx.x; i < kTgNWords; i += blockDim.x) {
     cs->tmpl[i] = ((const uint32_t*)kTgTemplate)[i];
     cs->wmeta[i] = kTgWordMeta[i];
   }
   __syncthreads();
-  const uint32_t stage = emit_stage_addr(dyn, wid);
-  uint64_t ntasks = (b.n + EMIT_RECS_PER_WARP - 1) / EMIT_RECS_PER_WARP;
-  uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
-  for (uint64_t task = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; task < ntasks; task += nwarps) {
-    uint64_t r0 = task * EMIT_RECS_PER_WARP;
-    uint64_t r1 = r0 + EMIT_RECS_PER_WARP < b.n ? r0 + EMIT_RECS_PER_WARP : b.n;
-    Em e = em_begin(stage, out, line_off[r0]);
-    for (uint64_t r = r0; r < r1; r++) {
-      if (status[r] != TGI_ST_EMITTED) continue;
+  const uint64_t ntasks = (b.n + EMIT_RECS_PER_WARP - 1) / EMIT_RECS_PER_WARP;
+  const uint64_t nwarps = (uint64_t)gridDim.x * EMIT_WARPS;
+  const uint64_t iters = (ntasks + nwarps - 1) / nwarps;
+  for (uint64_t it = 0; it < iters; it++) {  // uniform trip counts: every warp reaches every barrier
+    const uint64_t task = it * nwarps + (uint64_t)blockIdx.x * EMIT_WARPS + wid;
+    const bool valid = task < ntasks;
+    const uint64_t r0 = task * EMIT_RECS_PER_WARP;
+    const uint64_t r1 = valid ? (r0 + EMIT_RECS_PER_WARP < b.n ? r0 + EMIT_RECS_PER_WARP : b.n) : 0;
+    Em e = em_begin(stage, out, valid ? line_off[r0] : 0);
+    for (int j = 0; j < EMIT_RECS_PER_WARP; j++) {
+      const uint64_t r = r0 + j;
+      bool act = valid && r < r1 && status[r] == TGI_ST_EMITTED;
+      uint32_t total = 0;
       TgWalkArgs a;
-      a.b = &b;
-      a.cfg = &cfg;
-      a.r = r;
-      a.v = load_rec_view(b, r);
-      a.links = arena + link_start[r];
-      a.n_links = link_count[r];
-      uint32_t total = (uint32_t)(line_off[r + 1] - line_off[r]);
-      if (!tg_is_slow_record(total, b.comment_off[r + 1] - b.comment_off[r])) {
+      FastRec f;
+      f.ok = false;
+      if (act) {
+        total = (uint32_t)(line_off[r + 1] - line_off[r]);
+        if (tg_is_slow_record(total, b.comment_off[r + 1] - b.comment_off[r])) {
+          // long line / comments: written by tg_emit_long_kernel; restart the stream behind it
+          em_finish(e);
+          e = em_begin(stage, out, line_off[r + 1]);
+          act = false;
+        }
+      }
+      if (act) {
+        a.b = &b;
+        a.cfg = &cfg;
+        a.r = r;
+        a.v = load_rec_view(b, r);
+        a.links = arena + link_start[r];
+        a.n_links = link_count[r];
         if (e.fill + total > (uint32_t)EMIT_FLUSH_AT) e = em_flush(e);
-        e = emit_tg_record_fast(e, ws, cs, a, total, xlen + r * 8, err);
-      } else {  // long line: written by tg_emit_long_kernel; restart the stream behind it
-        em_finish(e);
-        e = em_begin(stage, out, line_off[r + 1]);
+        fast_phase_prologue(f, ws, a, xlen + r * 8);
+      }
+      __syncthreads();
+      if (act) fast_phase_fixed(f, e, ws, cs, a, total, err);
+      __syncthreads();
+      if (act) fast_phase_esc(f, a);
+      __syncthreads();
+      if (act) {
+        fast_phase_maps(f, e, ws, a);
+        __syncwarp();
+        e.fill += total;
       }
     }
-    em_finish(e);
+    if (valid) em_finish(e);
+    __syncthreads();
   }
 }
 

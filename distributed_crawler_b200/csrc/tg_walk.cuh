@@ -416,22 +416,38 @@ __device__ __noinline__ Em emit_tg_record_seq(Em e, WarpScratch* ws, const TgWal
   return e;
 }
 
-// lane-parallel path: the whole line (total bytes, fill + total <= EMIT_FLUSH_AT) is assembled out of
-// order.  Lane i owns pieces kTgEPL*i ..; an exclusive scan over the lanes' length sums gives each
-// piece its output offset.  Literal pieces only publish their shift (output offset - template offset);
-// the template is then copied word by word (340 words = 11 steps) with the shift of the owning piece.
-// Rendered fields are copied by their owning lane; the few variable pieces cooperatively.
-DEVI Em emit_tg_record_fast(Em e, WarpScratch* ws, const CtaShared* cs, const TgWalkArgs& a, uint32_t total,
-                            const uint32_t* xlen_g, int* err) {
-  const TgBatchDev& b = *a.b;
-  const ChanDerived cd = b.chan_derived[a.v.rec->chan_idx];
-  TgDerived d = tg_derive(a, cd);
+// ---- lane-parallel path, in phases ------------------------------------------------------------------
+// The whole line (total bytes, fill + total <= EMIT_FLUSH_AT) is assembled out of order in the staging
+// buffer.  Lane i owns pieces kTgEPL*i ..; an exclusive scan over the lanes' length sums gives each
+// piece its output offset.  Literal pieces only publish their shift (output offset - template
+// offset); the template is then copied word by word (340 words = 11 steps) with the shift of the
+// owning piece.  Rendered fields are copied by their owning lane, the variable pieces cooperatively.
+//
+// The work is cut into phases that the emit kernel separates with __syncthreads(): all 24 warps of
+// the (single) CTA of an SM execute the same few KB of code at any time.  The B200 instruction caches
+// are small (L0 ~6 KB per sub-partition, L1.5 32 KB per SM); without this, 24 warps at 24 different
+// places of a 70 KB kernel stall mostly on instruction fetch (ncu: stall_no_instruction).
+struct FastRec {
+  TgDerived d;
+  uint32_t off[kTgEPL], len[kTgEPL];
+  uint32_t base;   // shared address of the line's first byte
+  bool ok;
+};
+
+DEVI void fast_phase_prologue(FastRec& f, WarpScratch* ws, const TgWalkArgs& a, const uint32_t* xlen_g) {
+  const ChanDerived cd = a.b->chan_derived[a.v.rec->chan_idx];
+  f.d = tg_derive(a, cd);
+  emit_tg_prologue(ws, a, cd, f.d, xlen_g);
+}
+
+// entries + scan + shifts + lane-owned field copies + template + CHAN/CFG copies
+DEVI void fast_phase_fixed(FastRec& f, const Em& e, WarpScratch* ws, const CtaShared* cs, const TgWalkArgs& a,
+                           uint32_t total, int* err) {
   const uint32_t ws_s = smem_addr(ws), ents_s = smem_addr(cs->ents), tmpl_s = smem_addr(cs->tmpl);
   const uint32_t vs_s = ws_s + (uint32_t)offsetof(WarpScratch, vshift);
-  emit_tg_prologue(ws, a, cd, d, xlen_g);
-  const uint32_t condmask = tg_condmask(a, d);
+  const uint32_t condmask = tg_condmask(a, f.d);
   const int l = lane_id();
-  uint32_t ent[kTgEPL], len[kTgEPL], off[kTgEPL];
+  uint32_t ent[kTgEPL];
   uint32_t sum = 0;
 #pragma unroll
   for (int k = 0; k < kTgEPL; k++) {
@@ -450,31 +466,31 @@ DEVI Em emit_tg_record_fast(Em e, WarpScratch* ws, const CtaShared* cs, const Tg
       else if (kind == K_OUTLINKS) ln = lds32(ws_s + (uint32_t)offsetof(WarpScratch, xlen) + 4u * XL_OUTLINKS);
     }
     ent[k] = en;
-    len[k] = ln;
+    f.len[k] = ln;
     sum += ln;
   }
   uint32_t incl = warp_incl_scan(sum);
   uint32_t run = incl - sum;
 #pragma unroll
   for (int k = 0; k < kTgEPL; k++) {
-    off[k] = run;
-    run += len[k];
+    f.off[k] = run;
+    run += f.len[k];
   }
-  if (__shfl_sync(FULL, incl, 31) != total) {  // sizing and emission disagree: never expected
+  f.base = e.sbuf + e.fill;
+  f.ok = __shfl_sync(FULL, incl, 31) == total;
+  if (!f.ok) {  // sizing and emission disagree: never expected; the host reports it
     if (l == 0) atomicOr(err, 16);
-    e.fill += total;  // keep the stream aligned; the host reports the error
-    return e;
+    return;
   }
-  const uint32_t base = e.sbuf + e.fill;
-  // literal pieces publish their shift; field pieces are copied by their owning lane
+  const uint32_t base = f.base;
 #pragma unroll
   for (int k = 0; k < kTgEPL; k++) {
     uint32_t kind = ent[k] & 15u;
     if (kind == K_LIT) {
-      sts32(vs_s + 4u * (uint32_t)(kTgEPL * l + k), len[k] ? off[k] - ((ent[k] >> 12) & 0x7FFu) : VSHIFT_SKIP);
-    } else if (len[k] && (kind == K_FIELD || kind == K_POSTTYPE)) {
+      sts32(vs_s + 4u * (uint32_t)(kTgEPL * l + k), f.len[k] ? f.off[k] - ((ent[k] >> 12) & 0x7FFu) : VSHIFT_SKIP);
+    } else if (f.len[k] && (kind == K_FIELD || kind == K_POSTTYPE)) {
       uint32_t src = ws_s + (uint32_t)offsetof(WarpScratch, field) + 40u * (kind == K_FIELD ? (ent[k] >> 4) & 15u : F_POSTTYPE);
-      uint32_t dst = base + off[k], n = len[k];
+      uint32_t dst = base + f.off[k], n = f.len[k];
       for (uint32_t w = 0; w < n; w += 4) {
         uint32_t v = lds32(src + w);
         sts8(dst + w, v);
@@ -485,8 +501,7 @@ DEVI Em emit_tg_record_fast(Em e, WarpScratch* ws, const CtaShared* cs, const Tg
     }
   }
   __syncwarp();
-  // the template, word by word
-  {
+  {  // the template, word by word
     const uint32_t wm_s = smem_addr(cs->wmeta);
 #pragma unroll 2
     for (uint32_t j = l; j < (uint32_t)kTgNWords; j += 32) {
@@ -502,43 +517,67 @@ DEVI Em emit_tg_record_fast(Em e, WarpScratch* ws, const CtaShared* cs, const Tg
       }
     }
   }
-  // cooperative pieces, in line order
-  for (int bi = 0; bi < kTgNBig; bi++) {
-    const uint32_t idx = kTgBig[bi];
+  for (int bi = 0; bi < kTgNCopy; bi++) {  // per-channel / per-context strings
+    const uint32_t idx = kTgCopy[bi];
     const uint32_t owner = idx / kTgEPL, kk = idx % kTgEPL;
-    uint32_t o_sel = off[0], l_sel = len[0];
+    uint32_t o_sel = f.off[0], l_sel = f.len[0];
 #pragma unroll
     for (int k = 1; k < kTgEPL; k++)
-      if (kk == (uint32_t)k) { o_sel = off[k]; l_sel = len[k]; }
+      if (kk == (uint32_t)k) { o_sel = f.off[k]; l_sel = f.len[k]; }
     const uint32_t ln = __shfl_sync(FULL, l_sel, owner);
     if (ln == 0) continue;
     const uint32_t o = __shfl_sync(FULL, o_sel, owner);
     const uint32_t en = kTgPieces[idx];
-    const uint32_t kind = en & 15u, arg = (en >> 4) & 15u;
-    if (kind == K_CHAN || kind == K_CFG) {
-      uint32_t si = (kind == K_CFG ? 4u : 0u) + arg;
-      copy_g_to(base + o, (const uint8_t*)(uintptr_t)ws->src_ptr[si], ln);
-    } else if (kind == K_ESC) {
-      const uint8_t* p = arg == 0 ? d.desc : arg == 1 ? a.v.media : arg == 2 ? a.v.handle : a.v.alt;
-      uint32_t n = arg == 0 ? d.desc_len : arg == 1 ? a.v.media_len : arg == 2 ? a.v.handle_len : a.v.alt_len;
-      uint32_t carry = 0;
-      esc_range(base + o, p, n, 0, n, carry);
+    uint32_t si = ((en & 15u) == K_CFG ? 4u : 0u) + ((en >> 4) & 15u);
+    copy_g_to(base + o, (const uint8_t*)(uintptr_t)ws->src_ptr[si], ln);
+  }
+}
+
+DEVI void fast_piece_pos(const FastRec& f, uint32_t idx, uint32_t& o, uint32_t& ln) {
+  const uint32_t owner = idx / kTgEPL, kk = idx % kTgEPL;
+  uint32_t o_sel = f.off[0], l_sel = f.len[0];
+#pragma unroll
+  for (int k = 1; k < kTgEPL; k++)
+    if (kk == (uint32_t)k) { o_sel = f.off[k]; l_sel = f.len[k]; }
+  ln = __shfl_sync(FULL, l_sel, owner);
+  o = __shfl_sync(FULL, o_sel, owner);
+}
+
+DEVI void fast_phase_esc(const FastRec& f, const TgWalkArgs& a) {
+  if (!f.ok) return;
+  for (int bi = 0; bi < kTgNEsc; bi++) {
+    const uint32_t idx = kTgEsc[bi];
+    uint32_t o, ln;
+    fast_piece_pos(f, idx, o, ln);
+    if (ln == 0) continue;
+    const uint32_t arg = (kTgPieces[idx] >> 4) & 15u;
+    const uint8_t* p = arg == 0 ? f.d.desc : arg == 1 ? a.v.media : arg == 2 ? a.v.handle : a.v.alt;
+    uint32_t n = arg == 0 ? f.d.desc_len : arg == 1 ? a.v.media_len : arg == 2 ? a.v.handle_len : a.v.alt_len;
+    uint32_t carry = 0;
+    esc_range(f.base + o, p, n, 0, n, carry);
+  }
+}
+
+DEVI void fast_phase_maps(const FastRec& f, const Em& e, WarpScratch* ws, const TgWalkArgs& a) {
+  if (!f.ok) return;
+  const TgBatchDev& b = *a.b;
+  for (int bi = 0; bi < kTgNMap; bi++) {
+    const uint32_t idx = kTgMap[bi];
+    uint32_t o, ln;
+    fast_piece_pos(f, idx, o, ln);
+    if (ln == 0) continue;
+    const uint32_t kind = kTgPieces[idx] & 15u;
+    Em t = e;
+    t.fill = e.fill + o;  // never reaches EMIT_FLUSH_AT: the caller checked fill + total
+    if (kind == K_COMMENTS) {  // records with comments never reach this kernel: "null" or "[]"
+      if (f.d.comments_nil) em_copy_g(t, (const uint8_t*)kNullLit, 4);
+      else em_ch2(t, '[', ']');
+    } else if (kind == K_REACTIONS) {
+      t = emit_reaction_map<false>(t, ws, b.reacts, b.react_off[a.r], b.react_off[a.r + 1], b.aux);
     } else {
-      Em t = e;
-      t.fill = e.fill + o;  // never reaches EMIT_FLUSH_AT: the caller checked fill + total
-      if (kind == K_COMMENTS) {  // records with comments never reach this kernel: "null" or "[]"
-        if (d.comments_nil) em_copy_g(t, (const uint8_t*)kNullLit, 4);
-        else em_ch2(t, '[', ']');
-      } else if (kind == K_REACTIONS) {
-        t = emit_reaction_map<false>(t, ws, b.reacts, b.react_off[a.r], b.react_off[a.r + 1], b.aux);
-      } else {
-        t = emit_tg_outlinks(t, a.links, a.n_links);
-      }
+      t = emit_tg_outlinks(t, a.links, a.n_links);
     }
   }
-  __syncwarp();
-  e.fill += total;
-  return e;
 }
 
 // ---- channel job: the per-channel constant strings, rendered once per batch ----------------------

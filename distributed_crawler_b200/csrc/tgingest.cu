@@ -430,10 +430,10 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     }
     if (n) {
       uint64_t ntasks = (n + EMIT_RECS_PER_WARP - 1) / EMIT_RECS_PER_WARP;
-      uint64_t want = (ntasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-      unsigned ge = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms * 3);
+      uint64_t want = (ntasks + EMIT_WARPS - 1) / EMIT_WARPS;
+      unsigned ge = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms);  // one persistent CTA per SM
       CK(cudaEventRecord(s.ev_e0, st));
-      tg_emit_kernel<<<ge, CTA_THREADS, EMIT_SMEM_BYTES, st>>>(b, cfg, s.d_status.as<uint8_t>(), s.d_line_off.as<uint64_t>(),
+      tg_emit_kernel<<<ge, EMIT_WARPS * 32, EMITP_SMEM_BYTES, st>>>(b, cfg, s.d_status.as<uint8_t>(), s.d_line_off.as<uint64_t>(),
                                                 s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(), s.d_xlen.as<uint32_t>(),
                                                 s.d_arena.as<tgi_link>(), s.d_jsonl.as<uint8_t>(), (int*)(dsc + SC_CURSOR) + 1);
       launches++;
@@ -685,7 +685,7 @@ int tgi_create(const tgi_config* cfg, tgi_ctx** out) {
   ctx->fr.table = ctx->d_table.as<uint64_t>();
   ctx->fr.tmask = tslots - 1;
   ctx->fr.count = ctx->d_fcount.as<uint64_t>();
-  if (cudaFuncSetAttribute(tg_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMIT_SMEM_BYTES) != cudaSuccess ||
+  if (cudaFuncSetAttribute(tg_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMITP_SMEM_BYTES) != cudaSuccess ||
       cudaFuncSetAttribute(tg_emit_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMIT_SMEM_BYTES) != cudaSuccess ||
       cudaFuncSetAttribute(tg_chan_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMIT_SMEM_BYTES) != cudaSuccess) {
     set_err(c, "cudaFuncSetAttribute(max dynamic smem %zu) failed", (size_t)EMIT_SMEM_BYTES);

@@ -155,6 +155,11 @@ def emit_table(name, prog):
         lines.append("    " + ", ".join(map(str, wmeta[i:i + 24])) + ",")
     lines.append("};")
     lines.append(f"__device__ const uint8_t k{name}Big[{len(big)}] = {{" + ", ".join(map(str, big)) + "};")
+    groups = {"Copy": (K_CHAN, K_CFG), "Esc": (K_ESC,), "Map": (K_COMMENTS, K_REACTIONS, K_OUTLINKS)}
+    for gname, kinds in groups.items():  # the phased emit kernel visits the cooperative pieces by kind
+        sel = [i for i in big if (rows[i] & 15) in kinds]
+        lines.append(f"constexpr int k{name}N{gname} = {len(sel)};")
+        lines.append(f"__device__ const uint8_t k{name}{gname}[{len(sel)}] = {{" + ", ".join(map(str, sel)) + "};")
     return "\n".join(lines) + "\n"
 
 
