@@ -165,6 +165,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_kernel(TgBatchDev b, 
 // One persistent CTA of EMIT_WARPS warps per SM; every warp owns 8 consecutive records per task and
 // all warps walk through the record phases in lockstep (see tg_walk.cuh "in phases").
 constexpr int EMIT_WARPS = 24;
+#ifndef EMIT_SYNC_WARPS
+#define EMIT_SYNC_WARPS 8
+#endif
 constexpr size_t EMITP_SMEM_BYTES = (size_t)EMIT_WARPS * (EMIT_CAP + sizeof(WarpScratch)) + sizeof(CtaShared);
 
 __global__ void __launch_bounds__(EMIT_WARPS * 32, 1) tg_emit_kernel(TgBatchDev b, CfgDev cfg, const uint8_t* status, const uint64_t* line_off,
@@ -181,6 +184,10 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 1) tg_emit_kernel(TgBatchDev 
     cs->wmeta[i] = kTgWordMeta[i];
   }
   __syncthreads();
+  // warps synchronise in groups of EMIT_SYNC_WARPS (named barriers): small enough to limit the wait
+  // for the slowest record of a phase, large enough to keep the SM's instruction working set small
+  const uint32_t bar_id = 1u + (uint32_t)wid / EMIT_SYNC_WARPS;
+#define PHASE_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(EMIT_SYNC_WARPS * 32) : "memory")
   const uint64_t ntasks = (b.n + EMIT_RECS_PER_WARP - 1) / EMIT_RECS_PER_WARP;
   const uint64_t nwarps = (uint64_t)gridDim.x * EMIT_WARPS;
   const uint64_t iters = (ntasks + nwarps - 1) / nwarps;
@@ -216,11 +223,11 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 1) tg_emit_kernel(TgBatchDev 
         if (e.fill + total > (uint32_t)EMIT_FLUSH_AT) e = em_flush(e);
         fast_phase_prologue(f, ws, a, xlen + r * 8);
       }
-      __syncthreads();
+      PHASE_SYNC();
       if (act) fast_phase_fixed(f, e, ws, cs, a, total, err);
-      __syncthreads();
+      PHASE_SYNC();
       if (act) fast_phase_esc(f, a);
-      __syncthreads();
+      PHASE_SYNC();
       if (act) {
         fast_phase_maps(f, e, ws, a);
         __syncwarp();
@@ -228,9 +235,11 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32, 1) tg_emit_kernel(TgBatchDev 
       }
     }
     if (valid) em_finish(e);
-    __syncthreads();
+    PHASE_SYNC();
   }
 }
+
+#undef PHASE_SYNC
 
 // long lines (> staging capacity): one warp per record, sequential piece walk, streaming flushes
 __global__ void __launch_bounds__(CTA_THREADS) tg_emit_long_kernel(TgBatchDev b, CfgDev cfg, const uint32_t* long_list, uint32_t n_long,
