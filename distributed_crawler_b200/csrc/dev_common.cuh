@@ -419,184 +419,71 @@ DEVI uint32_t thread_esc_len(const uint8_t* s, uint32_t n) {
   }
   return o;
 }
-DEVI void put_escaped_s(uint32_t d, uint32_t b, uint32_t len) {  // d: shared address
+// ---- byte sinks ---------------------------------------------------------------------------------
+// All emission writes straight into the output blob in HBM (DstG) at offsets that were fixed by the
+// size + scan passes; the L2 merges the byte-granular stores of neighbouring lanes / instructions
+// into full sectors.  DstS (shared memory) is used for small per-lane staging only.
+struct DstG {
+  uint8_t* p;
+  DEVI void st(uint32_t off, uint32_t v) const { p[off] = (uint8_t)v; }
+  DEVI DstG at(uint32_t off) const { return DstG{p + off}; }
+};
+struct DstS {
+  uint32_t a;
+  DEVI void st(uint32_t off, uint32_t v) const { sts8(a + off, v); }
+  DEVI DstS at(uint32_t off) const { return DstS{a + off}; }
+};
+
+template <class D>
+DEVI void put_escaped(const D& d, uint32_t o, uint32_t b, uint32_t len) {
   if (len == 1) {
-    sts8(d, b);
+    d.st(o, b);
   } else if (len == 2) {
-    sts8(d, '\\');
+    d.st(o, '\\');
     uint32_t c = b;
     if (b == '\b') c = 'b';
     else if (b == '\f') c = 'f';
     else if (b == '\n') c = 'n';
     else if (b == '\r') c = 'r';
     else if (b == '\t') c = 't';
-    sts8(d + 1, c);
+    d.st(o + 1, c);
   } else {
     uint32_t h = b >> 4, l = b & 15;
-    sts8(d, '\\'); sts8(d + 1, 'u'); sts8(d + 2, '0'); sts8(d + 3, '0');
-    sts8(d + 4, h < 10 ? '0' + h : 'a' + h - 10);
-    sts8(d + 5, l < 10 ? '0' + l : 'a' + l - 10);
+    d.st(o, '\\'); d.st(o + 1, 'u'); d.st(o + 2, '0'); d.st(o + 3, '0');
+    d.st(o + 4, h < 10 ? '0' + h : 'a' + h - 10);
+    d.st(o + 5, l < 10 ? '0' + l : 'a' + l - 10);
   }
 }
-DEVI void put_u_s(uint32_t d, uint32_t a, uint32_t b, uint32_t c, uint32_t e) {  // ꯎ
-  sts8(d, '\\'); sts8(d + 1, 'u'); sts8(d + 2, a); sts8(d + 3, b); sts8(d + 4, c); sts8(d + 5, e);
-}
-// escapes s[0..n) into shared memory at d (capacity cap); returns the length or ~0u if it does not fit
-DEVI uint32_t thread_esc(const uint8_t* s, uint32_t n, uint32_t d, uint32_t cap) {
-  uint32_t o = 0;
-  for (uint32_t i = 0; i < n;) {
-    uint32_t b = ldb(s + i);
-    if (o + 6 > cap) return ~0u;
-    if (b < 0x80) {
-      uint32_t len = ascii_esc_len(b);
-      put_escaped_s(d + o, b, len);
-      o += len;
-      i++;
-      continue;
-    }
-    int need = utf8_valid_lead(s, i, n);
-    if (need == 0) {
-      put_u_s(d + o, 'f', 'f', 'f', 'd');
-      o += 6;
-      i++;
-    } else if (need == 3 && b == 0xE2 && ldb(s + i + 1) == 0x80 && (ldb(s + i + 2) | 1u) == 0xA9) {
-      put_u_s(d + o, '2', '0', '2', ldb(s + i + 2) == 0xA8 ? '8' : '9');
-      o += 6;
-      i += 3;
-    } else {
-      for (int k = 0; k < need; k++) sts8(d + o + k, ldb(s + i + k));
-      o += (uint32_t)need;
-      i += (uint32_t)need;
-    }
-  }
-  return o;
+template <class D>
+DEVI void put_u(const D& d, uint32_t o, uint32_t a, uint32_t b, uint32_t c, uint32_t e) {  // \uXXXX
+  d.st(o, '\\'); d.st(o + 1, 'u'); d.st(o + 2, a); d.st(o + 3, b); d.st(o + 4, c); d.st(o + 5, e);
 }
 
-// ---- the emitter ------------------------------------------------------------------------------------
-// Per-warp staging buffer in shared memory mapped onto the output stream: stage byte i <-> output
-// byte gbase+i, with (gout+gbase) 16-byte aligned, so complete 16-byte chunks leave as aligned
-// 128-bit stores.  The first `skip` bytes belong to the previous warp's range and are never written
-// from here.  The struct is kept in registers: heavy operations are free functions that take and
-// return it by value.
-constexpr int EMIT_CAP = 6144;       // per-warp staging bytes
-constexpr int EMIT_FLUSH_AT = 5120;  // flush before a piece when fill exceeds this (piece <= 1 KiB)
-
-struct Em {
-  uint32_t sbuf;   // shared-space address of the staging buffer (16-byte aligned)
-  uint32_t fill;   // bytes staged (including the skip region)
-  uint32_t skip;   // leading bytes not owned (only before the first flush)
-  uint8_t* gout;   // output blob
-  uint64_t gbase;  // output offset of stage byte 0
-};
-
-DEVI Em em_begin(uint32_t sbuf, uint8_t* out, uint64_t start_off) {
-  Em e;
-  e.sbuf = sbuf;
-  e.gout = out;
-  uint64_t addr = (uint64_t)(uintptr_t)out + start_off;
-  e.skip = (uint32_t)(addr & 15);
-  e.gbase = start_off - e.skip;
-  e.fill = e.skip;
-  return e;
-}
-// write all complete 16-byte chunks; keep the tail
-__device__ __noinline__ Em em_flush(Em e) {
-  __syncwarp();
-  uint32_t nch = e.fill >> 4;
-  int l = lane_id();
-  uint8_t* g = e.gout + e.gbase;
-  for (uint32_t c = l; c < nch; c += 32) {
-    if (c == 0 && e.skip) {
-      for (uint32_t k = e.skip; k < 16; k++) g[k] = (uint8_t)lds8(e.sbuf + k);
-    } else {
-      *(uint4*)(g + 16ull * c) = lds128(e.sbuf + 16 * c);
-    }
-  }
-  __syncwarp();
-  uint32_t tail = e.fill & 15;
-  uint32_t t = 0;
-  if (nch && (uint32_t)l < tail) t = lds8(e.sbuf + 16 * nch + l);
-  __syncwarp();
-  if (nch) {
-    if ((uint32_t)l < tail) sts8(e.sbuf + l, t);
-    e.gbase += 16ull * nch;
-    e.fill = tail;
-    e.skip = 0;
-  }
-  __syncwarp();
-  return e;
-}
-__device__ __noinline__ void em_finish(Em e) {  // end of the warp's range: tail goes out byte-wise
-  e = em_flush(e);
-  int l = lane_id();
-  if ((uint32_t)l >= e.skip && (uint32_t)l < e.fill) e.gout[e.gbase + l] = (uint8_t)lds8(e.sbuf + l);
-  __syncwarp();
-}
-DEVI void em_room(Em& e) {
-  if (e.fill > EMIT_FLUSH_AT) e = em_flush(e);
-}
-// n <= 1024, global source
-DEVI void em_copy_g(Em& e, const uint8_t* src, uint32_t n) {
-  em_room(e);
-  uint32_t l = lane_id();
-  uint32_t d = e.sbuf + e.fill + l;
-  const uint8_t* s = src + l;
-  uint32_t i = 0;
-  for (; i + 128 <= n; i += 128) {
-    uint32_t b0 = ldb(s + i), b1 = ldb(s + i + 32), b2 = ldb(s + i + 64), b3 = ldb(s + i + 96);
-    sts8(d + i, b0); sts8(d + i + 32, b1); sts8(d + i + 64, b2); sts8(d + i + 96, b3);
-  }
-  for (; i + l < n; i += 32) sts8(d + i, ldb(s + i));
-  e.fill += n;
-}
-DEVI void em_copy_g_long(Em& e, const uint8_t* src, uint32_t n) {
-  for (uint32_t o = 0; o < n; o += 1024) em_copy_g(e, src + o, n - o < 1024 ? n - o : 1024);
-}
-// n <= 1024, shared source (shared-space address)
-DEVI void em_copy_s(Em& e, uint32_t src, uint32_t n) {
-  em_room(e);
-  uint32_t l = lane_id();
-  for (uint32_t i = l; i < n; i += 32) sts8(e.sbuf + e.fill + i, lds8(src + i));
-  e.fill += n;
-}
-DEVI void em_ch(Em& e, uint32_t c) {
-  em_room(e);
-  if (lane_id() == 0) sts8(e.sbuf + e.fill, c);
-  e.fill += 1;
-}
-DEVI void em_ch2(Em& e, uint32_t c0, uint32_t c1) {
-  em_room(e);
-  if (lane_id() == 0) {
-    sts8(e.sbuf + e.fill, c0);
-    sts8(e.sbuf + e.fill + 1, c1);
-  }
-  e.fill += 2;
-}
-// JSON-escape the strips [b0, b1) of s[0..n) to shared memory at dst (no quotes); returns the bytes
-// written.  128-byte strips, 4 bytes per lane.  `carry` threads the UTF-8 context between calls.
-__device__ __noinline__ uint32_t esc_range(uint32_t dst, const uint8_t* s, uint32_t n, uint32_t b0, uint32_t b1,
-                                           uint32_t& carry_io) {
-  uint32_t carry = carry_io, out = 0;
-  for (int64_t base = b0; base < (int64_t)b1; base += 128) {
+// JSON-escape s[0..n) to dst (no quotes); returns the bytes written.  128-byte strips, 4 bytes per
+// lane; a warp scan over the per-lane output lengths places every lane's bytes.
+__device__ __noinline__ uint32_t esc_to_global(uint8_t* dstp, const uint8_t* s, uint32_t n) {
+  DstG dst{dstp};
+  uint32_t carry = 0, out = 0;
+  for (int64_t base = 0; base < (int64_t)n; base += 128) {
     Strip st = warp_load_strip(s, base, n, carry);
     uint32_t el, u;
     strip_lane_totals(st, s, base, n, el, u);
     uint32_t incl = warp_incl_scan(el);
     uint32_t tot = __shfl_sync(FULL, incl, 31);
-    uint32_t d = dst + out + (incl - el);
+    uint32_t d = out + (incl - el);
     if (st.nvalid) {
       if (!st.exact) {
         if (el == st.nvalid) {  // nothing to escape in this lane's bytes
 #pragma unroll
           for (uint32_t k = 0; k < 4; k++)
-            if (k < st.nvalid) sts8(d + k, (st.w >> (8 * k)) & 0xFF);
+            if (k < st.nvalid) dst.st(d + k, (st.w >> (8 * k)) & 0xFF);
         } else {
 #pragma unroll
           for (uint32_t k = 0; k < 4; k++) {
             if (k < st.nvalid) {
               uint32_t b = (st.w >> (8 * k)) & 0xFF;
               uint32_t len = b < 0x80 ? ascii_esc_len(b) : 1u;
-              put_escaped_s(d, b, len);
+              put_escaped(dst, d, b, len);
               d += len;
             }
           }
@@ -608,11 +495,11 @@ __device__ __noinline__ uint32_t esc_range(uint32_t dst, const uint8_t* s, uint3
           uint32_t b = (st.w >> (8 * k)) & 0xFF;
           if (bi.esc == 6 && b >= 0x80) {
             if (b == 0xE2 && bi.start && utf8_valid_lead(s, p0 + k, n) == 3)  // U+2028/9
-              put_u_s(d, '2', '0', '2', ldb(s + p0 + k + 2) == 0xA8 ? '8' : '9');
+              put_u(dst, d, '2', '0', '2', ldb(s + p0 + k + 2) == 0xA8 ? '8' : '9');
             else  // invalid byte -> U+FFFD
-              put_u_s(d, 'f', 'f', 'f', 'd');
+              put_u(dst, d, 'f', 'f', 'f', 'd');
           } else if (bi.esc) {
-            put_escaped_s(d, b, bi.esc);
+            put_escaped(dst, d, b, bi.esc);
           }
           d += bi.esc;
         }
@@ -620,33 +507,61 @@ __device__ __noinline__ uint32_t esc_range(uint32_t dst, const uint8_t* s, uint3
     }
     out += tot;
   }
-  carry_io = carry;
   return out;
 }
-// streaming form: at most 512 input bytes (<= 3 KiB of output) between capacity checks
-DEVI void em_esc_stream(Em& e, const uint8_t* s, uint32_t n) {
-  uint32_t carry = 0;
-  for (uint32_t b0 = 0; b0 < n; b0 += 128) {
-    em_room(e);  // one strip expands to at most 768 bytes
-    e.fill += esc_range(e.sbuf + e.fill, s, n, b0, b0 + 128 < n ? b0 + 128 : n, carry);
+
+// single-thread escape of a short string into shared memory (map keys); ~0u if it does not fit
+DEVI uint32_t thread_esc(const uint8_t* s, uint32_t n, uint32_t d, uint32_t cap) {
+  DstS dst{d};
+  uint32_t o = 0;
+  for (uint32_t i = 0; i < n;) {
+    uint32_t b = ldb(s + i);
+    if (o + 6 > cap) return ~0u;
+    if (b < 0x80) {
+      uint32_t len = ascii_esc_len(b);
+      put_escaped(dst, o, b, len);
+      o += len;
+      i++;
+      continue;
+    }
+    int need = utf8_valid_lead(s, i, n);
+    if (need == 0) {
+      put_u(dst, o, 'f', 'f', 'f', 'd');
+      o += 6;
+      i++;
+    } else if (need == 3 && b == 0xE2 && ldb(s + i + 1) == 0x80 && (ldb(s + i + 2) | 1u) == 0xA9) {
+      put_u(dst, o, '2', '0', '2', ldb(s + i + 2) == 0xA8 ? '8' : '9');
+      o += 6;
+      i += 3;
+    } else {
+      for (int k = 0; k < need; k++) dst.st(o + k, ldb(s + i + k));
+      o += (uint32_t)need;
+      i += (uint32_t)need;
+    }
   }
+  return o;
 }
-// whole string in one go: the caller guarantees the room (lane-parallel path)
-DEVI void em_esc_fit(Em& e, const uint8_t* s, uint32_t n) {
-  uint32_t carry = 0;
-  if (n) e.fill += esc_range(e.sbuf + e.fill, s, n, 0, n, carry);
-}
-// global -> shared copy at a fixed position, any length, 4 independent loads in flight per lane
-DEVI void copy_g_to(uint32_t dst, const uint8_t* src, uint32_t n) {
+
+// warp copies into the output blob (any length): global source / shared source / one or two bytes
+DEVI void gcopy_g(uint8_t* dst, const uint8_t* src, uint32_t n) {
   uint32_t l = lane_id();
-  uint32_t d = dst + l;
+  uint8_t* d = dst + l;
   const uint8_t* s = src + l;
   uint32_t i = 0;
   for (; i + 128 <= n; i += 128) {
     uint32_t b0 = ldb(s + i), b1 = ldb(s + i + 32), b2 = ldb(s + i + 64), b3 = ldb(s + i + 96);
-    sts8(d + i, b0); sts8(d + i + 32, b1); sts8(d + i + 64, b2); sts8(d + i + 96, b3);
+    d[i] = (uint8_t)b0; d[i + 32] = (uint8_t)b1; d[i + 64] = (uint8_t)b2; d[i + 96] = (uint8_t)b3;
   }
-  for (; i + l < n; i += 32) sts8(d + i, ldb(s + i));
+  for (; i + l < n; i += 32) d[i] = (uint8_t)ldb(s + i);
+}
+DEVI void gcopy_s(uint8_t* dst, uint32_t src, uint32_t n) {
+  for (uint32_t i = lane_id(); i < n; i += 32) dst[i] = (uint8_t)lds8(src + i);
+}
+DEVI void gput1(uint8_t* dst, uint32_t c) {
+  if (lane_id() == 0) dst[0] = (uint8_t)c;
+}
+DEVI void gput2(uint8_t* dst, uint32_t c0, uint32_t c1) {
+  if (lane_id() < 2) dst[lane_id()] = (uint8_t)(lane_id() ? c1 : c0);
 }
 
 }  // namespace tgi

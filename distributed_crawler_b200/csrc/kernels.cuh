@@ -19,16 +19,6 @@ constexpr int EMIT_RECS_PER_WARP = 8;  // contiguous records per warp task in th
 #define ERR_FRONTIER_FULL 4
 #define ERR_TOO_MANY_LINKS 8
 
-DEVI bool tg_is_slow_record(uint32_t line_len, uint32_t n_comments) { return line_len + 16 > (uint32_t)EMIT_FLUSH_AT || n_comments != 0; }
-
-// dynamic shared memory of the emitting kernels: per-warp staging buffers, then per-warp scratch
-constexpr size_t EMIT_SMEM_BYTES = (size_t)WARPS_PER_CTA * (EMIT_CAP + sizeof(WarpScratch)) + sizeof(CtaShared);
-DEVI CtaShared* emit_cta_shared(uint8_t* dyn) { return (CtaShared*)(dyn + (size_t)WARPS_PER_CTA * (EMIT_CAP + sizeof(WarpScratch))); }
-DEVI uint32_t emit_stage_addr(uint8_t* dyn, int wid) { return smem_addr(dyn + (size_t)wid * EMIT_CAP); }
-DEVI WarpScratch* emit_scratch(uint8_t* dyn, int wid) {
-  return (WarpScratch*)(dyn + (size_t)WARPS_PER_CTA * EMIT_CAP) + wid;
-}
-
 // ---- channel job -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CTA_THREADS) tg_chan_size_kernel(TgBatchDev b, ChanDerived* cd, uint32_t* len) {
   int wid = threadIdx.x >> 5;
@@ -42,19 +32,12 @@ __global__ void __launch_bounds__(CTA_THREADS) tg_chan_size_kernel(TgBatchDev b,
 }
 
 __global__ void __launch_bounds__(CTA_THREADS) tg_chan_emit_kernel(TgBatchDev b, ChanDerived* cd, const uint64_t* off, uint8_t* blob) {
-  extern __shared__ __align__(16) uint8_t dyn[];
+  __shared__ WarpScratch wss[WARPS_PER_CTA];
   int wid = threadIdx.x >> 5;
-  uint32_t task = blockIdx.x * WARPS_PER_CTA + wid;
-  uint32_t c0 = task * EMIT_RECS_PER_WARP;
-  if (c0 >= b.n_chans) return;
-  uint32_t c1 = min(c0 + (uint32_t)EMIT_RECS_PER_WARP, b.n_chans);
-  WarpScratch* ws = emit_scratch(dyn, wid);
-  Em e = em_begin(emit_stage_addr(dyn, wid), blob, off[c0]);
-  for (uint32_t c = c0; c < c1; c++) {
-    if (lane_id() == 0) cd[c].off = off[c];
-    e = emit_tg_chan(e, ws, b, c);
-  }
-  em_finish(e);
+  uint32_t c = blockIdx.x * WARPS_PER_CTA + wid;
+  if (c >= b.n_chans) return;
+  if (lane_id() == 0) cd[c].off = off[c];
+  emit_tg_chan(blob + off[c], &wss[wid], b, c);
 }
 
 // ---- parse: status + links + line length ---------------------------------------------------------
@@ -64,8 +47,6 @@ struct ParseOut {
   uint32_t* link_start;  // [n] arena index of the record's first link
   uint32_t* link_count;  // [n]
   uint32_t* xlen;        // [n][8] emitted lengths of the variable pieces (XL_*)
-  uint32_t* long_list;   // records whose line does not fit the staging buffer (sequential kernel)
-  uint32_t* long_count;
   tgi_link* arena;
   uint32_t arena_cap;
   uint32_t* cursor;      // arena allocation cursor (keeps counting past arena_cap)
@@ -91,12 +72,15 @@ DEVI TgRecView load_rec_view(const TgBatchDev& b, uint64_t r) {
   return v;
 }
 
+// The parse step is two kernels so that each one's instruction footprint stays small (the B200
+// instruction caches are 6 KB L0 / 32 KB L1.5): tg_parse_kernel = status + link extraction,
+// tg_size_kernel = line length.  The text is read twice; both kernels are far below the HBM roofline.
 __global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) {
   int wid = threadIdx.x >> 5, l = lane_id();
   uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
     TgRecView v = load_rec_view(b, r);
-    uint32_t status = TGI_ST_EMITTED, nlinks = 0, lstart = 0, llen = 0;
+    uint32_t status = TGI_ST_EMITTED, nlinks = 0, lstart = 0;
     if ((cfg.flags & TGI_CFG_HAS_MIN_POST_DATE) && (int64_t)v.rec->date < cfg.min_post_date) {
       status = TGI_ST_SKIPPED;  // tdutils.go:419-421
     } else if (v.flags & TGI_RF_PANIC) {
@@ -110,7 +94,6 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_kernel(TgBatchDev b, 
         if (l == 0) atomicOr(o.err, ERR_TOO_MANY_LINKS);
         ub = 0;
       }
-      bool ok = true;
       if (ub) {
         if (l == 0) lstart = atomicAdd(o.cursor, ub);
         lstart = __shfl_sync(FULL, lstart, 0);
@@ -124,143 +107,122 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_kernel(TgBatchDev b, 
           ls.count = 0;
           ls.self = b.chan_strs + ch->str_off + ch->title_len;
           ls.self_len = ch->name_len;
-          ok = warp_extract_links(v, b.ents, b.aux, ls);
+          bool ok = warp_extract_links(v, b.ents, b.aux, ls);
           nlinks = ls.count;
+          if (!ok) {
+            status = TGI_ST_FAILED;
+            nlinks = 0;
+          }
         }
-      }
-      if (!ok) {
-        status = TGI_ST_FAILED;
-        nlinks = 0;
-      } else if (run_flags & TGI_RUN_JSONL) {
-        TgWalkArgs a;
-        a.b = &b;
-        a.cfg = &cfg;
-        a.r = r;
-        a.v = v;
-        a.links = o.arena + lstart;
-        a.n_links = nlinks;
-        uint32_t xl[XL_COUNT];
-        llen = size_tg_record(a, xl);
-        if (llen == 0) status = TGI_ST_NOLINE;
-        uint32_t mine = 0;
-#pragma unroll
-        for (int j = 0; j < XL_COUNT; j++)
-          if (l == j) mine = xl[j];
-        if (l < 8) o.xlen[r * 8 + l] = mine;
-        // lines that do not fit the staging buffer, and the rare records with comments, take the
-        // sequential kernel (keeps the hot kernel's instruction footprint small)
-        if (l == 0 && tg_is_slow_record(llen, b.comment_off[r + 1] - b.comment_off[r])) o.long_list[atomicAdd(o.long_count, 1u)] = (uint32_t)r;
       }
     }
     if (l == 0) {
       o.status[r] = (uint8_t)status;
-      o.linelen[r] = llen;
+      o.linelen[r] = 0;
       o.link_start[r] = lstart;
       o.link_count[r] = nlinks;
     }
   }
 }
 
-// ---- emit ------------------------------------------------------------------------------------------
-// One persistent CTA of EMIT_WARPS warps per SM; every warp owns 8 consecutive records per task and
-// all warps walk through the record phases in lockstep (see tg_walk.cuh "in phases").
-constexpr int EMIT_WARPS = 24;
-#ifndef EMIT_SYNC_WARPS
-#define EMIT_SYNC_WARPS 8
-#endif
-constexpr size_t EMITP_SMEM_BYTES = (size_t)EMIT_WARPS * (EMIT_CAP + sizeof(WarpScratch)) + sizeof(CtaShared);
-
-__global__ void __launch_bounds__(EMIT_WARPS * 32, 1) tg_emit_kernel(TgBatchDev b, CfgDev cfg, const uint8_t* status, const uint64_t* line_off,
-                               const uint32_t* link_start, const uint32_t* link_count, const uint32_t* xlen,
-                               const tgi_link* arena, uint8_t* out, int* err) {
-  extern __shared__ __align__(16) uint8_t dyn[];
-  const int wid = threadIdx.x >> 5;
-  WarpScratch* ws = (WarpScratch*)(dyn + (size_t)EMIT_WARPS * EMIT_CAP) + wid;
-  CtaShared* cs = (CtaShared*)(dyn + (size_t)EMIT_WARPS * (EMIT_CAP + sizeof(WarpScratch)));
-  const uint32_t stage = smem_addr(dyn + (size_t)wid * EMIT_CAP);
-  for (int i = threadIdx.x; i < kTgNEnt; i += blockDim.x) cs->ents[i] = kTgPieces[i];
-  for (int i = threadIdx.x; i < kTgNWords; i += blockDim.x) {
-    cs->tmpl[i] = ((const uint32_t*)kTgTemplate)[i];
-    cs->wmeta[i] = kTgWordMeta[i];
-  }
-  __syncthreads();
-  // warps synchronise in groups of EMIT_SYNC_WARPS (named barriers): small enough to limit the wait
-  // for the slowest record of a phase, large enough to keep the SM's instruction working set small
-  const uint32_t bar_id = 1u + (uint32_t)wid / EMIT_SYNC_WARPS;
-#define PHASE_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(EMIT_SYNC_WARPS * 32) : "memory")
-  const uint64_t ntasks = (b.n + EMIT_RECS_PER_WARP - 1) / EMIT_RECS_PER_WARP;
-  const uint64_t nwarps = (uint64_t)gridDim.x * EMIT_WARPS;
-  const uint64_t iters = (ntasks + nwarps - 1) / nwarps;
-  for (uint64_t it = 0; it < iters; it++) {  // uniform trip counts: every warp reaches every barrier
-    const uint64_t task = it * nwarps + (uint64_t)blockIdx.x * EMIT_WARPS + wid;
-    const bool valid = task < ntasks;
-    const uint64_t r0 = task * EMIT_RECS_PER_WARP;
-    const uint64_t r1 = valid ? (r0 + EMIT_RECS_PER_WARP < b.n ? r0 + EMIT_RECS_PER_WARP : b.n) : 0;
-    Em e = em_begin(stage, out, valid ? line_off[r0] : 0);
-    for (int j = 0; j < EMIT_RECS_PER_WARP; j++) {
-      const uint64_t r = r0 + j;
-      bool act = valid && r < r1 && status[r] == TGI_ST_EMITTED;
-      uint32_t total = 0;
-      TgWalkArgs a;
-      FastRec f;
-      f.ok = false;
-      if (act) {
-        total = (uint32_t)(line_off[r + 1] - line_off[r]);
-        if (tg_is_slow_record(total, b.comment_off[r + 1] - b.comment_off[r])) {
-          // long line / comments: written by tg_emit_long_kernel; restart the stream behind it
-          em_finish(e);
-          e = em_begin(stage, out, line_off[r + 1]);
-          act = false;
-        }
-      }
-      if (act) {
-        a.b = &b;
-        a.cfg = &cfg;
-        a.r = r;
-        a.v = load_rec_view(b, r);
-        a.links = arena + link_start[r];
-        a.n_links = link_count[r];
-        if (e.fill + total > (uint32_t)EMIT_FLUSH_AT) e = em_flush(e);
-        fast_phase_prologue(f, ws, a, xlen + r * 8);
-      }
-      PHASE_SYNC();
-      if (act) fast_phase_fixed(f, e, ws, cs, a, total, err);
-      PHASE_SYNC();
-      if (act) fast_phase_esc(f, a);
-      PHASE_SYNC();
-      if (act) {
-        fast_phase_maps(f, e, ws, a);
-        __syncwarp();
-        e.fill += total;
-      }
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_kernel(TgBatchDev b, CfgDev cfg, ParseOut o) {
+  int wid = threadIdx.x >> 5, l = lane_id();
+  uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
+    if (o.status[r] != TGI_ST_EMITTED) continue;
+    TgWalkArgs a;
+    a.b = &b;
+    a.cfg = &cfg;
+    a.r = r;
+    a.v = load_rec_view(b, r);
+    a.links = o.arena + o.link_start[r];
+    a.n_links = o.link_count[r];
+    uint32_t xl[XL_COUNT];
+    uint32_t llen = size_tg_record(a, xl);
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < XL_COUNT; j++)
+      if (l == j) mine = xl[j];
+    if (l < 8) o.xlen[r * 8 + l] = mine;
+    if (l == 0) {
+      if (llen == 0) o.status[r] = TGI_ST_NOLINE;
+      o.linelen[r] = llen;
     }
-    if (valid) em_finish(e);
-    PHASE_SYNC();
   }
 }
 
-#undef PHASE_SYNC
+// ---- emit: three small kernels, one warp per record, direct stores into the output blob ----------
+// Small kernels on purpose: the B200 instruction caches are tiny (L0 ~6 KB per sub-partition, L1.5
+// 32 KB per SM).  A single fused emit kernel (70-100 KB of SASS) spent most of its cycles in
+// stall_no_instruction; split by piece class, every kernel's hot loop fits the L1.5.
+struct EmitIn {
+  const uint8_t* status;
+  const uint64_t* line_off;
+  const uint32_t* link_start;
+  const uint32_t* link_count;
+  const uint32_t* xlen;  // [n][8] lengths of the variable pieces
+  uint32_t* xpos;        // [n][8] their offsets inside the line (written by kernel 1)
+  const tgi_link* arena;
+  uint8_t* out;
+  int* err;
+};
 
-// long lines (> staging capacity): one warp per record, sequential piece walk, streaming flushes
-__global__ void __launch_bounds__(CTA_THREADS) tg_emit_long_kernel(TgBatchDev b, CfgDev cfg, const uint32_t* long_list, uint32_t n_long,
-                                                               const uint64_t* line_off, const uint32_t* link_start,
-                                                               const uint32_t* link_count, const tgi_link* arena, uint8_t* out) {
-  extern __shared__ __align__(16) uint8_t dyn[];
-  int wid = threadIdx.x >> 5;
-  uint32_t i = blockIdx.x * WARPS_PER_CTA + wid;
-  if (i >= n_long) return;
-  uint64_t r = long_list[i];
-  WarpScratch* ws = emit_scratch(dyn, wid);
-  Em e = em_begin(emit_stage_addr(dyn, wid), out, line_off[r]);
-  TgWalkArgs a;
-  a.b = &b;
-  a.cfg = &cfg;
-  a.r = r;
-  a.v = load_rec_view(b, r);
-  a.links = arena + link_start[r];
-  a.n_links = link_count[r];
-  e = emit_tg_record_seq(e, ws, a);
-  em_finish(e);
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_fixed_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
+  __shared__ WarpScratch wss[WARPS_PER_CTA];
+  __shared__ CtaShared cs;
+  const int wid = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < kTgNEnt; i += blockDim.x) cs.ents[i] = kTgPieces[i];
+  for (int i = threadIdx.x; i < kTgNWords; i += blockDim.x) {
+    cs.tmpl[i] = ((const uint32_t*)kTgTemplate)[i];
+    cs.wmeta[i] = kTgWordMeta[i];
+  }
+  __syncthreads();
+  const uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
+    if (in.status[r] != TGI_ST_EMITTED) continue;
+    TgWalkArgs a;
+    a.b = &b;
+    a.cfg = &cfg;
+    a.r = r;
+    a.v = load_rec_view(b, r);
+    a.links = nullptr;
+    a.n_links = 0;
+    const uint64_t lo = in.line_off[r];
+    emit_tg_fixed(in.out + lo, &wss[wid], &cs, a, (uint32_t)(in.line_off[r + 1] - lo), in.xlen + r * 8, in.xpos + r * 8, in.err);
+  }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_esc_kernel(TgBatchDev b, EmitIn in) {
+  const int wid = threadIdx.x >> 5;
+  const uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
+    if (in.status[r] != TGI_ST_EMITTED) continue;
+    TgWalkArgs a;
+    a.b = &b;
+    a.cfg = nullptr;
+    a.r = r;
+    a.v = load_rec_view(b, r);
+    emit_tg_escapes(in.out + in.line_off[r], a, in.xlen + r * 8, in.xpos + r * 8);
+  }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_maps_kernel(TgBatchDev b, EmitIn in) {
+  __shared__ MapScratch mss[WARPS_PER_CTA];
+  const int wid = threadIdx.x >> 5;
+  const uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
+    if (in.status[r] != TGI_ST_EMITTED) continue;
+    uint8_t* line = in.out + in.line_off[r];
+    const uint32_t* xp = in.xpos + r * 8;
+    const bool comments_nil = (b.recs[r].flags & TGI_RF_COMMENTS_NIL) != 0;
+    const uint32_t c0 = b.comment_off[r], c1 = b.comment_off[r + 1];
+    if (comments_nil) gcopy_g(line + xp[XL_COMMENTS], (const uint8_t*)kNullLit, 4);
+    else if (c1 == c0) gput2(line + xp[XL_COMMENTS], '[', ']');
+    else emit_tg_comments(line + xp[XL_COMMENTS], &mss[wid], b, c0, c1);
+    emit_reaction_map(line + xp[XL_REACTIONS], &mss[wid], b.reacts, b.react_off[r], b.react_off[r + 1], b.aux);
+    const uint32_t nl = in.link_count[r];
+    if (nl) emit_tg_outlinks(line + xp[XL_OUTLINKS], in.arena + in.link_start[r], nl);
+  }
 }
 
 // ---- exclusive scan u32 -> u64 (out has n+1 entries) ----------------------------------------------

@@ -75,7 +75,7 @@ struct Slot {
       d_chans, d_chan_strs;
   // device intermediates / outputs
   DevBuf d_chan_derived, d_chan_len, d_chan_off, d_chan_blob, d_status, d_linelen, d_line_off,
-      d_link_start, d_link_count, d_xlen, d_long, d_arena, d_lstate, d_rec_new, d_new_off, d_link_off, d_links_out,
+      d_link_start, d_link_count, d_xlen, d_xpos, d_arena, d_lstate, d_rec_new, d_new_off, d_link_off, d_links_out,
       d_link_off32, d_btable, d_tiles, d_scalars, d_jsonl;
   // pinned host outputs
   HostBuf h_status, h_line_off, h_jsonl, h_link_off, h_links, h_scalars;
@@ -193,12 +193,7 @@ __global__ void cfg_label_size_kernel(const uint8_t* s, uint32_t n, uint32_t* ou
   uint32_t e = warp_esc_len(s, n);
   if (lane_id() == 0) *out = e;
 }
-__global__ void cfg_label_emit_kernel(const uint8_t* s, uint32_t n, uint8_t* out) {
-  __shared__ __align__(16) uint8_t stage[EMIT_CAP];
-  Em e = em_begin(smem_addr(stage), out, 0);
-  em_esc_stream(e, s, n);
-  em_finish(e);
-}
+__global__ void cfg_label_emit_kernel(const uint8_t* s, uint32_t n, uint8_t* out) { esc_to_global(out, s, n); }
 
 int build_cfg_blob(tgi_ctx* c) {
   const tgi_config& cfg = c->cfg;
@@ -351,7 +346,7 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   CK(s.d_link_start.ensure(n * 4));
   CK(s.d_link_count.ensure(n * 4));
   CK(s.d_xlen.ensure(n * 32));
-  CK(s.d_long.ensure(n * 4));
+  CK(s.d_xpos.ensure(n * 32));
   uint64_t arena_cap = s.n_ents + n / 2 + 1024;
   if (s.d_arena.cap / sizeof(tgi_link) > arena_cap + 8) arena_cap = (s.d_arena.cap - PAD) / sizeof(tgi_link);
 
@@ -379,8 +374,6 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     po.link_start = s.d_link_start.as<uint32_t>();
     po.link_count = s.d_link_count.as<uint32_t>();
     po.xlen = s.d_xlen.as<uint32_t>();
-    po.long_list = s.d_long.as<uint32_t>();
-    po.long_count = (uint32_t*)(dsc + SC_LONG);
     po.arena = s.d_arena.as<tgi_link>();
     po.arena_cap = (uint32_t)arena_cap;
     po.cursor = (uint32_t*)(dsc + SC_CURSOR);
@@ -390,8 +383,12 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       unsigned g = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms * 8);
       CK(cudaEventRecord(s.ev_p0, st));
       tg_parse_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
-      CK(cudaEventRecord(s.ev_p1, st));
       launches++;
+      if (want_json) {
+        tg_size_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, po);
+        launches++;
+      }
+      CK(cudaEventRecord(s.ev_p1, st));
     }
     if (want_json) {
       int rc = launch_scan(c, s, s.d_linelen.as<uint32_t>(), n, s.d_line_off.as<uint64_t>(), dsc + SC_LINE_TOTAL, launches);
@@ -422,29 +419,30 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     CK(s.d_chan_blob.ensure(chan_total));
     CK(s.d_jsonl.ensure(line_total));
     b.chan_blob = s.d_chan_blob.as<uint8_t>();
-    unsigned tasks = (b.n_chans + EMIT_RECS_PER_WARP - 1) / EMIT_RECS_PER_WARP;
-    unsigned g = (tasks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    unsigned g = (b.n_chans + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (g) {
-      tg_chan_emit_kernel<<<g, CTA_THREADS, EMIT_SMEM_BYTES, st>>>(b, s.d_chan_derived.as<ChanDerived>(), s.d_chan_off.as<uint64_t>(), s.d_chan_blob.as<uint8_t>());
+      tg_chan_emit_kernel<<<g, CTA_THREADS, 0, st>>>(b, s.d_chan_derived.as<ChanDerived>(), s.d_chan_off.as<uint64_t>(), s.d_chan_blob.as<uint8_t>());
       launches++;
     }
     if (n) {
-      uint64_t ntasks = (n + EMIT_RECS_PER_WARP - 1) / EMIT_RECS_PER_WARP;
-      uint64_t want = (ntasks + EMIT_WARPS - 1) / EMIT_WARPS;
-      unsigned ge = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms);  // one persistent CTA per SM
+      EmitIn ei;
+      ei.status = s.d_status.as<uint8_t>();
+      ei.line_off = s.d_line_off.as<uint64_t>();
+      ei.link_start = s.d_link_start.as<uint32_t>();
+      ei.link_count = s.d_link_count.as<uint32_t>();
+      ei.xlen = s.d_xlen.as<uint32_t>();
+      ei.xpos = s.d_xpos.as<uint32_t>();
+      ei.arena = s.d_arena.as<tgi_link>();
+      ei.out = s.d_jsonl.as<uint8_t>();
+      ei.err = (int*)(dsc + SC_CURSOR) + 1;
+      uint64_t want = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+      unsigned ge = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms * 8);
       CK(cudaEventRecord(s.ev_e0, st));
-      tg_emit_kernel<<<ge, EMIT_WARPS * 32, EMITP_SMEM_BYTES, st>>>(b, cfg, s.d_status.as<uint8_t>(), s.d_line_off.as<uint64_t>(),
-                                                s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(), s.d_xlen.as<uint32_t>(),
-                                                s.d_arena.as<tgi_link>(), s.d_jsonl.as<uint8_t>(), (int*)(dsc + SC_CURSOR) + 1);
-      launches++;
-      uint32_t n_long = ((uint32_t*)(hsc + SC_LONG))[0];
-      if (n_long) {
-        tg_emit_long_kernel<<<(n_long + WARPS_PER_CTA - 1) / WARPS_PER_CTA, CTA_THREADS, EMIT_SMEM_BYTES, st>>>(
-            b, cfg, s.d_long.as<uint32_t>(), n_long, s.d_line_off.as<uint64_t>(), s.d_link_start.as<uint32_t>(),
-            s.d_link_count.as<uint32_t>(), s.d_arena.as<tgi_link>(), s.d_jsonl.as<uint8_t>());
-        launches++;
-      }
+      tg_emit_fixed_kernel<<<ge, CTA_THREADS, 0, st>>>(b, cfg, ei);
+      tg_emit_esc_kernel<<<ge, CTA_THREADS, 0, st>>>(b, ei);
+      tg_emit_maps_kernel<<<ge, CTA_THREADS, 0, st>>>(b, ei);
       CK(cudaEventRecord(s.ev_e1, st));
+      launches += 3;
     }
     CK(cudaGetLastError());
   }
@@ -685,12 +683,6 @@ int tgi_create(const tgi_config* cfg, tgi_ctx** out) {
   ctx->fr.table = ctx->d_table.as<uint64_t>();
   ctx->fr.tmask = tslots - 1;
   ctx->fr.count = ctx->d_fcount.as<uint64_t>();
-  if (cudaFuncSetAttribute(tg_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMITP_SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(tg_emit_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMIT_SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(tg_chan_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMIT_SMEM_BYTES) != cudaSuccess) {
-    set_err(c, "cudaFuncSetAttribute(max dynamic smem %zu) failed", (size_t)EMIT_SMEM_BYTES);
-    return fail(TGI_E_CUDA);
-  }
   int rc = build_cfg_blob(ctx);
   if (rc) return fail(rc);
   for (int i = 0; i < TGI_SLOTS; i++) ctx->slots[i].worker = std::thread(worker_main, ctx, &ctx->slots[i]);
@@ -716,7 +708,7 @@ void tgi_destroy(tgi_ctx* c) {
     DevBuf* db[] = {&s.d_recs, &s.d_strs, &s.d_ent_off, &s.d_ents, &s.d_react_off, &s.d_reacts, &s.d_comment_off,
                     &s.d_comments, &s.d_aux, &s.d_chans, &s.d_chan_strs, &s.d_chan_derived, &s.d_chan_len,
                     &s.d_chan_off, &s.d_chan_blob, &s.d_status, &s.d_linelen, &s.d_line_off, &s.d_link_start,
-                    &s.d_link_count, &s.d_xlen, &s.d_long, &s.d_arena, &s.d_lstate, &s.d_rec_new, &s.d_new_off, &s.d_link_off,
+                    &s.d_link_count, &s.d_xlen, &s.d_xpos, &s.d_arena, &s.d_lstate, &s.d_rec_new, &s.d_new_off, &s.d_link_off,
                     &s.d_links_out, &s.d_link_off32, &s.d_btable, &s.d_tiles, &s.d_scalars, &s.d_jsonl};
     for (DevBuf* d : db) d->release();
     HostBuf* hb[] = {&s.h_status, &s.h_line_off, &s.h_jsonl, &s.h_link_off, &s.h_links, &s.h_scalars};
