@@ -232,11 +232,19 @@ DEVI void strip_lane_totals(const Strip& st, const uint8_t* s, int64_t base, int
     }
     return;
   }
+  // SWAR: does any valid byte need escaping (< 0x20, '"', '\\', '<', '>', '&')?  Exact as an "any" test.
+  uint32_t wt = st.nvalid < 4 ? (st.w | (0x20202020u << (8 * st.nvalid))) : st.w;
+  uint32_t special = ((wt - 0x20202020u) & ~wt & 0x80808080u) | swar_has_byte(wt, 0x22) | swar_has_byte(wt, 0x5C) |
+                     swar_has_byte(wt, 0x3C) | swar_has_byte(wt, 0x3E) | swar_has_byte(wt, 0x26);
+  if (!special) {
+    esc = st.nvalid;
+  } else {
 #pragma unroll
-  for (uint32_t k = 0; k < 4; k++) {
-    if (k < st.nvalid) {
-      uint32_t b = (st.w >> (8 * k)) & 0xFF;
-      esc += b < 0x80 ? ascii_esc_len(b) : 1u;
+    for (uint32_t k = 0; k < 4; k++) {
+      if (k < st.nvalid) {
+        uint32_t b = (st.w >> (8 * k)) & 0xFF;
+        esc += b < 0x80 ? ascii_esc_len(b) : 1u;
+      }
     }
   }
   u16 = st.nvalid - __popc(st.cont) + __popc(st.l4);
