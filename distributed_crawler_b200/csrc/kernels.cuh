@@ -47,6 +47,7 @@ struct ParseOut {
   uint32_t* link_start;  // [n] arena index of the record's first link
   uint32_t* link_count;  // [n]
   uint32_t* xlen;        // [n][8] emitted lengths of the variable pieces (XL_*)
+  unsigned long long* var_total;  // sum of the variable pieces' lengths (statistics)
   tgi_link* arena;
   uint32_t arena_cap;
   uint32_t* cursor;      // arena allocation cursor (keeps counting past arena_cap)
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_kernel(TgBatchDev b, 
 __global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_kernel(TgBatchDev b, CfgDev cfg, ParseOut o) {
   int wid = threadIdx.x >> 5, l = lane_id();
   uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  uint64_t var_sum = 0;
   for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
     if (o.status[r] != TGI_ST_EMITTED) continue;
     TgWalkArgs a;
@@ -144,11 +146,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_kernel(TgBatchDev b, C
     for (int j = 0; j < XL_COUNT; j++)
       if (l == j) mine = xl[j];
     if (l < 8) o.xlen[r * 8 + l] = mine;
+    if (llen) var_sum += warp_sum(mine);
     if (l == 0) {
       if (llen == 0) o.status[r] = TGI_ST_NOLINE;
       o.linelen[r] = llen;
     }
   }
+  if (l == 0 && var_sum) atomicAdd(o.var_total, (unsigned long long)var_sum);
 }
 
 // ---- emit: three small kernels, one warp per record, direct stores into the output blob ----------

@@ -69,7 +69,7 @@ enum JobKind { JOB_NONE = 0, JOB_TG, JOB_TG_RESIDENT, JOB_TG_UPLOAD, JOB_YT, JOB
 struct Slot {
   int idx = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_mid = nullptr, ev_p0 = nullptr, ev_p1 = nullptr, ev_e0 = nullptr, ev_e1 = nullptr;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_mid = nullptr, ev_p0 = nullptr, ev_p1 = nullptr, ev_e0 = nullptr, ev_e1 = nullptr, ev_f1 = nullptr;
   // device inputs
   DevBuf d_recs, d_strs, d_ent_off, d_ents, d_react_off, d_reacts, d_comment_off, d_comments, d_aux,
       d_chans, d_chan_strs;
@@ -374,6 +374,7 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     po.link_start = s.d_link_start.as<uint32_t>();
     po.link_count = s.d_link_count.as<uint32_t>();
     po.xlen = s.d_xlen.as<uint32_t>();
+    po.var_total = (unsigned long long*)(dsc + SC_LONG);
     po.arena = s.d_arena.as<tgi_link>();
     po.arena_cap = (uint32_t)arena_cap;
     po.cursor = (uint32_t*)(dsc + SC_CURSOR);
@@ -410,6 +411,7 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   if (dev_err & ERR_TOO_MANY_LINKS) { set_err(c, "a record has more than 4096 link candidates (format limit)"); return TGI_E_ARG; }
   uint64_t chan_total = hsc[SC_CHAN_TOTAL], line_total = hsc[SC_LINE_TOTAL];
   uint32_t arena_used = ((uint32_t*)(hsc + SC_CURSOR))[0];
+  const uint64_t var_bytes = hsc[SC_LONG];
 
   if (want_json) {
     if (c->cfg.max_out_bytes && line_total > c->cfg.max_out_bytes) {
@@ -439,6 +441,7 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       unsigned ge = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms * 8);
       CK(cudaEventRecord(s.ev_e0, st));
       tg_emit_fixed_kernel<<<ge, CTA_THREADS, 0, st>>>(b, cfg, ei);
+      CK(cudaEventRecord(s.ev_f1, st));
       tg_emit_esc_kernel<<<ge, CTA_THREADS, 0, st>>>(b, ei);
       tg_emit_maps_kernel<<<ge, CTA_THREADS, 0, st>>>(b, ei);
       CK(cudaEventRecord(s.ev_e1, st));
@@ -527,7 +530,11 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   out->gpu_launches = launches;
   out->slot = s.idx;
   if (n) cudaEventElapsedTime(&out->parse_ms, s.ev_p0, s.ev_p1);
-  if (n && want_json) cudaEventElapsedTime(&out->emit_ms, s.ev_e0, s.ev_e1);
+  if (n && want_json) {
+    cudaEventElapsedTime(&out->emit_ms, s.ev_e0, s.ev_e1);
+    cudaEventElapsedTime(&out->emit_fixed_ms, s.ev_e0, s.ev_f1);
+    out->var_bytes = var_bytes;
+  }
   out->jsonl_len = want_json ? line_total : 0;
   out->n_links = n_links_total;
   out->n_new = want_fr ? hsc[SC_NEW] : 0;
@@ -661,7 +668,7 @@ int tgi_create(const tgi_config* cfg, tgi_ctx** out) {
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&s.ev_k0) != cudaSuccess || cudaEventCreate(&s.ev_k1) != cudaSuccess ||
         cudaEventCreate(&s.ev_p0) != cudaSuccess || cudaEventCreate(&s.ev_p1) != cudaSuccess ||
-        cudaEventCreate(&s.ev_e0) != cudaSuccess || cudaEventCreate(&s.ev_e1) != cudaSuccess ||
+        cudaEventCreate(&s.ev_e0) != cudaSuccess || cudaEventCreate(&s.ev_e1) != cudaSuccess || cudaEventCreate(&s.ev_f1) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.ev_mid, cudaEventDisableTiming) != cudaSuccess) {
       set_err(c, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
       return fail(TGI_E_CUDA);
@@ -716,7 +723,7 @@ void tgi_destroy(tgi_ctx* c) {
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_mid) cudaEventDestroy(s.ev_mid);
-    for (cudaEvent_t e : {s.ev_p0, s.ev_p1, s.ev_e0, s.ev_e1}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {s.ev_p0, s.ev_p1, s.ev_e0, s.ev_e1, s.ev_f1}) if (e) cudaEventDestroy(e);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   c->d_cfg.release();

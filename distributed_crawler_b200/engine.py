@@ -96,6 +96,8 @@ class Result:
         self.kernel_ms = float(r.kernel_ms)
         self.parse_ms = float(r.parse_ms)
         self.emit_ms = float(r.emit_ms)
+        self.emit_fixed_ms = float(r.emit_fixed_ms)
+        self.var_bytes = int(r.var_bytes)
         self.gpu_launches = int(r.gpu_launches)
         self.slot = int(r.slot)
         if copy:

@@ -286,10 +286,11 @@ typedef struct tgi_result {
   uint64_t frontier_size;   /* distinct names after this call                                     */
   float kernel_ms;          /* device time of the kernels of this call (CUDA events)              */
   uint32_t gpu_launches;    /* kernels launched by this call                                      */
-  float parse_ms;           /* device time of the parse (link extraction + size) kernel           */
-  float emit_ms;            /* device time of the JSONL emit kernel                               */
+  float parse_ms;           /* device time of the parse pass (link extraction + size kernels)     */
+  float emit_ms;            /* device time of the JSONL emit pass (three kernels)                 */
   int32_t slot;             /* staging slot that owns the buffers: pass to tgi_result_release     */
-  uint32_t reserved;
+  float emit_fixed_ms;      /* device time of tg_emit_fixed_kernel, the dominant kernel           */
+  uint64_t var_bytes;       /* JSONL bytes written by the escape + map kernels (rest: fixed part) */
 } tgi_result;
 
 typedef struct tgi_stats {
