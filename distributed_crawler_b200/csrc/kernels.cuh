@@ -7,6 +7,7 @@
 //   frontier_*    exact open-addressed hash set over 32-byte keys (K5)
 #pragma once
 #include "tg_walk.cuh"
+#include "yt_walk.cuh"
 
 namespace tgi {
 
@@ -226,6 +227,119 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_maps_kernel(TgBatchDev
     emit_reaction_map(line + xp[XL_REACTIONS], &mss[wid], b.reacts, b.react_off[r], b.react_off[r + 1], b.aux);
     const uint32_t nl = in.link_count[r];
     if (nl) emit_tg_outlinks(line + xp[XL_OUTLINKS], in.arena + in.link_start[r], nl);
+  }
+}
+
+// ---- YouTube (config 4) ------------------------------------------------------------------------------
+struct YtOut {
+  uint8_t* status;
+  uint32_t* linelen;
+  uint32_t* url_start;   // [n] first unique URL of the record in `urls`
+  uint32_t* url_count;
+  YtUrl* urls;
+  uint32_t urls_cap;
+  uint32_t* url_cursor;
+  uint32_t* link_start;  // [n] channel-id links (frontier candidates)
+  uint32_t* link_count;
+  tgi_link* arena;
+  uint32_t arena_cap;
+  uint32_t* cursor;
+  int* err;
+};
+
+// unique outlink URLs (extractURLs) and snowball channel ids (extractChannelIDsFromText)
+__global__ void __launch_bounds__(CTA_THREADS, 4) yt_parse_kernel(YtBatchDev b, CfgDev cfg, uint32_t run_flags, YtOut o) {
+  int wid = threadIdx.x >> 5, l = lane_id();
+  uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
+    const tgi_yt_rec v = b.recs[r];
+    const uint8_t* desc = b.strs + v.str_off + v.id_len + v.title_len;
+    uint32_t us = 0, uc = 0, ls = 0, lc = 0;
+    uint32_t ub = yt_count_http(desc, v.desc_len);
+    if (ub) {
+      if (l == 0) us = atomicAdd(o.url_cursor, ub);
+      us = __shfl_sync(FULL, us, 0);
+      if (us + ub > o.urls_cap || us + ub < us) {
+        if (l == 0) atomicOr(o.err, ERR_ARENA_OVERFLOW);
+      } else {
+        uc = yt_extract_urls(desc, v.desc_len, o.urls + us, ub);
+      }
+    }
+    if (run_flags & (TGI_RUN_LINKS | TGI_RUN_FRONTIER)) {
+      uint32_t lb = yt_count_ytcom(desc, v.desc_len);
+      if (lb > 4096) {
+        if (l == 0) atomicOr(o.err, ERR_TOO_MANY_LINKS);
+        lb = 0;
+      }
+      if (lb) {
+        if (l == 0) ls = atomicAdd(o.cursor, lb);
+        ls = __shfl_sync(FULL, ls, 0);
+        if (ls + lb > o.arena_cap || ls + lb < ls) {
+          if (l == 0) atomicOr(o.err, ERR_ARENA_OVERFLOW);
+        } else {
+          lc = yt_channel_ids(desc, v.desc_len, o.arena + ls, lb);
+        }
+      }
+    }
+    if (l == 0) {
+      // json.Marshal fails (no line, record still "fetched") when a time.Time is outside year
+      // [0,9999]; decided here so that the status does not depend on TGI_RUN_JSONL
+      uint8_t tmp[40];
+      bool ok = !(cfg.flags & CFGDEV_CLOCK_INVALID) && cfg.created_yt_len != 0 &&
+                render_time(tmp, v.published_sec, v.published_nsec, 0) != 0;
+      if (ok) {
+        const tgi_yt_chan& ch = b.chans[v.chan_idx];
+        if (ch.cached) ok = render_time(tmp, ch.published_sec, ch.published_nsec, 0) != 0;
+      }
+      o.status[r] = ok ? TGI_ST_EMITTED : TGI_ST_NOLINE;
+      o.linelen[r] = 0;
+      o.url_start[r] = us;
+      o.url_count[r] = uc;
+      o.link_start[r] = ls;
+      o.link_count[r] = lc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, 4) yt_size_kernel(YtBatchDev b, CfgDev cfg, YtOut o) {
+  __shared__ YtScratch scs[WARPS_PER_CTA];
+  int wid = threadIdx.x >> 5, l = lane_id();
+  uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
+    if (o.status[r] != TGI_ST_EMITTED) continue;  // linelen stays 0
+    YtArgs a;
+    a.b = &b;
+    a.cfg = &cfg;
+    a.r = r;
+    a.urls = o.urls + o.url_start[r];
+    a.n_urls = o.url_count[r];
+    YtSizer z;
+    z.sc = &scs[wid];
+    bool ok = walk_yt_record(z, a);
+    if (l == 0) {
+      o.linelen[r] = ok ? (uint32_t)z.total : 0u;
+      if (!ok) o.status[r] = TGI_ST_NOLINE;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_kernel(YtBatchDev b, CfgDev cfg, YtOut o, const uint64_t* line_off, uint8_t* out, int* err) {
+  __shared__ YtScratch scs[WARPS_PER_CTA];
+  int wid = threadIdx.x >> 5, l = lane_id();
+  uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
+    if (o.status[r] != TGI_ST_EMITTED) continue;
+    YtArgs a;
+    a.b = &b;
+    a.cfg = &cfg;
+    a.r = r;
+    a.urls = o.urls + o.url_start[r];
+    a.n_urls = o.url_count[r];
+    YtWriter w;
+    w.sc = &scs[wid];
+    w.p = out + line_off[r];
+    walk_yt_record(w, a);
+    if (l == 0 && (uint64_t)(w.p - out) != line_off[r + 1]) atomicOr(err, 16);
   }
 }
 

@@ -76,11 +76,13 @@ struct Slot {
   // device intermediates / outputs
   DevBuf d_chan_derived, d_chan_len, d_chan_off, d_chan_blob, d_status, d_linelen, d_line_off,
       d_link_start, d_link_count, d_xlen, d_xpos, d_arena, d_lstate, d_rec_new, d_new_off, d_link_off, d_links_out,
-      d_link_off32, d_btable, d_tiles, d_scalars, d_jsonl;
+      d_link_off32, d_btable, d_tiles, d_scalars, d_jsonl, d_url_start, d_url_count, d_urls;
   // pinned host outputs
   HostBuf h_status, h_line_off, h_jsonl, h_link_off, h_links, h_scalars;
   // resident batch descriptor
   TgBatchDev tg{};
+  YtBatchDev yt{};
+  uint64_t yt_desc_bytes = 0;
   uint64_t n_ents = 0, n_reacts = 0, n_comments = 0, in_bytes = 0;
   bool resident = false;
   uint64_t dev_jsonl_len = 0;
@@ -90,6 +92,7 @@ struct Slot {
   JobKind job = JOB_NONE;
   bool busy = false, done = false, claimed = false;
   const tgi_tg_batch* in_tg = nullptr;
+  const tgi_yt_batch* in_yt = nullptr;
   uint32_t run_flags = 0;
   int rc = 0;
   tgi_result res{};
@@ -323,7 +326,129 @@ int upload_tg(tgi_ctx* c, Slot& s, const tgi_tg_batch* in) {
 
 // scalars block (device + pinned mirror): [0] chan total, [1] line total, [2] cursor(u32)+err(int),
 // [3] n_new, [4] frontier size, [5] link total
-enum { SC_CHAN_TOTAL = 0, SC_LINE_TOTAL = 1, SC_CURSOR = 2, SC_NEW = 3, SC_FSIZE = 4, SC_LINK_TOTAL = 5, SC_LONG = 6, SC_COUNT = 8 };
+enum { SC_CHAN_TOTAL = 0, SC_LINE_TOTAL = 1, SC_CURSOR = 2, SC_NEW = 3, SC_FSIZE = 4, SC_LINK_TOTAL = 5, SC_LONG = 6, SC_URL_CURSOR = 7, SC_COUNT = 8 };
+
+// shared tail of the Telegram and YouTube pipelines: frontier phases, link compaction, D2H, result
+int finish_batch(tgi_ctx* c, Slot& s, uint64_t n, uint32_t flags, uint64_t line_total, uint32_t arena_used,
+                 uint64_t arena_cap, uint64_t var_bytes, uint32_t launches, tgi_result* out) {
+  cudaStream_t st = s.stream;
+  const bool want_json = flags & TGI_RUN_JSONL, want_links = flags & TGI_RUN_LINKS, want_fr = flags & TGI_RUN_FRONTIER;
+  uint64_t* dsc = s.d_scalars.as<uint64_t>();
+  uint64_t* hsc = s.h_scalars.as<uint64_t>();
+  int dev_err = 0;
+  s.dev_jsonl_len = want_json ? line_total : 0;
+
+  if (want_fr && n) {
+    // frontier phases of different slots are serialised in submission order
+    std::unique_lock<std::mutex> fg(c->fr_mu);
+    if (c->fr_event_valid) CK(cudaStreamWaitEvent(st, c->fr_event, 0));
+    uint64_t bslots = next_pow2(std::max<uint64_t>(2ull * arena_used, 1024));
+    CK(s.d_btable.ensure(bslots * 8));
+    CK(s.d_lstate.ensure((size_t)arena_cap * 4));
+    CK(s.d_rec_new.ensure(n * 4));
+    CK(s.d_new_off.ensure((n + 1) * 8));
+    CK(cudaMemsetAsync(s.d_btable.p, 0, bslots * 8, st));
+    FrontierBatch fb;
+    fb.btable = s.d_btable.as<uint64_t>();
+    fb.bmask = bslots - 1;
+    fb.lstate = s.d_lstate.as<uint32_t>();
+    fb.rec_new = s.d_rec_new.as<uint32_t>();
+    unsigned g = (unsigned)((n + 255) / 256);
+    frontier_probe_kernel<<<g, 256, 0, st>>>(n, s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(),
+                                             s.d_arena.as<tgi_link>(), flags, c->fr, fb);
+    frontier_count_kernel<<<g, 256, 0, st>>>(n, s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(), fb);
+    launches += 2;
+    int rc = launch_scan(c, s, fb.rec_new, n, s.d_new_off.as<uint64_t>(), dsc + SC_NEW, launches);
+    if (rc) return rc;
+    int* derr = (int*)(dsc + SC_CURSOR) + 1;
+    frontier_append_kernel<<<g, 256, 0, st>>>(n, s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(),
+                                              s.d_arena.as<tgi_link>(), c->fr, fb, s.d_new_off.as<uint64_t>(), derr);
+    frontier_commit_kernel<<<1, 1, 0, st>>>(c->fr, s.d_new_off.as<uint64_t>(), n, dsc + SC_NEW, derr);
+    launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->fr_event, st));
+    c->fr_event_valid = true;
+  }
+  if (want_links) {
+    CK(s.d_link_off.ensure((n + 1) * 8));
+    CK(s.d_link_off32.ensure((n + 1) * 4));
+    int rc = launch_scan(c, s, s.d_link_count.as<uint32_t>(), n, s.d_link_off.as<uint64_t>(), dsc + SC_LINK_TOTAL, launches);
+    if (rc) return rc;
+    CK(s.d_links_out.ensure((size_t)arena_used * sizeof(tgi_link) + 64));
+    unsigned g = (unsigned)((n + 1 + 255) / 256);
+    links_compact_kernel<<<g, 256, 0, st>>>(n, s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(),
+                                            s.d_link_off.as<uint64_t>(), s.d_arena.as<tgi_link>(),
+                                            s.d_links_out.as<tgi_link>(), s.d_link_off32.as<uint32_t>());
+    launches++;
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(s.ev_k1, st));
+  CK(cudaMemcpyAsync(hsc, dsc, SC_COUNT * 8, cudaMemcpyDeviceToHost, st));
+
+  memset(out, 0, sizeof *out);
+  out->n = n;
+  const bool d2h = !(flags & TGI_RUN_NO_D2H);
+  uint64_t n_links_total = 0;
+  if (d2h) {
+    CK(s.h_status.ensure(n + 1));
+    CK(cudaMemcpyAsync(s.h_status.p, s.d_status.p, n, cudaMemcpyDeviceToHost, st));
+    if (want_json) {
+      CK(s.h_line_off.ensure((n + 1) * 8));
+      CK(s.h_jsonl.ensure(line_total + 1));
+      CK(cudaMemcpyAsync(s.h_line_off.p, s.d_line_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+      if (line_total) CK(cudaMemcpyAsync(s.h_jsonl.p, s.d_jsonl.p, line_total, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  CK(cudaStreamSynchronize(st));
+  dev_err = ((int*)(hsc + SC_CURSOR))[1];
+  if (dev_err & ERR_FRONTIER_FULL) { set_err(c, "frontier capacity %llu exceeded", (unsigned long long)c->fr.cap); return TGI_E_CAPACITY; }
+  if (dev_err & 16) { set_err(c, "internal: sized and emitted line lengths disagree"); return TGI_E_STATE; }
+  n_links_total = want_links ? hsc[SC_LINK_TOTAL] : 0;
+  if (d2h && want_links) {
+    CK(s.h_link_off.ensure((n + 1) * 4));
+    CK(s.h_links.ensure(n_links_total * sizeof(tgi_link) + 64));
+    CK(cudaMemcpyAsync(s.h_link_off.p, s.d_link_off32.p, (n + 1) * 4, cudaMemcpyDeviceToHost, st));
+    if (n_links_total) CK(cudaMemcpyAsync(s.h_links.p, s.d_links_out.p, n_links_total * sizeof(tgi_link), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1);
+  out->kernel_ms = ms;
+  out->gpu_launches = launches;
+  out->slot = s.idx;
+  if (n) cudaEventElapsedTime(&out->parse_ms, s.ev_p0, s.ev_p1);
+  if (n && want_json) {
+    cudaEventElapsedTime(&out->emit_ms, s.ev_e0, s.ev_e1);
+    cudaEventElapsedTime(&out->emit_fixed_ms, s.ev_e0, s.ev_f1);
+    out->var_bytes = var_bytes;
+  }
+  out->jsonl_len = want_json ? line_total : 0;
+  out->n_links = n_links_total;
+  out->n_new = want_fr ? hsc[SC_NEW] : 0;
+  out->frontier_size = want_fr ? hsc[SC_FSIZE] : 0;
+  if (d2h) {
+    out->status = s.h_status.as<uint8_t>();
+    if (want_json) {
+      out->jsonl = s.h_jsonl.as<uint8_t>();
+      out->line_off = s.h_line_off.as<uint64_t>();
+    }
+    if (want_links) {
+      out->link_off = s.h_link_off.as<uint32_t>();
+      out->links = s.h_links.as<tgi_link>();
+    }
+  }
+  {
+    std::lock_guard<std::mutex> g(c->st_mu);
+    c->stats.records += n;
+    c->stats.bytes_in += s.in_bytes;
+    c->stats.bytes_out += out->jsonl_len;
+    c->stats.links += n_links_total;
+    c->stats.launches += launches;
+    c->stats.kernel_ms_total += ms;
+    if (want_fr) c->stats.frontier_size = out->frontier_size;
+  }
+  return TGI_OK;
+}
 
 int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   TgBatchDev& b = s.tg;
@@ -449,118 +574,117 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     }
     CK(cudaGetLastError());
   }
-  s.dev_jsonl_len = want_json ? line_total : 0;
+  return finish_batch(c, s, n, flags, line_total, arena_used, arena_cap, var_bytes, launches, out);
+}
 
-  if (want_fr && n) {
-    // frontier phases of different slots are serialised in submission order
-    std::unique_lock<std::mutex> fg(c->fr_mu);
-    if (c->fr_event_valid) CK(cudaStreamWaitEvent(st, c->fr_event, 0));
-    uint64_t bslots = next_pow2(std::max<uint64_t>(2ull * arena_used, 1024));
-    CK(s.d_btable.ensure(bslots * 8));
-    CK(s.d_lstate.ensure((size_t)arena_cap * 4));
-    CK(s.d_rec_new.ensure(n * 4));
-    CK(s.d_new_off.ensure((n + 1) * 8));
-    CK(cudaMemsetAsync(s.d_btable.p, 0, bslots * 8, st));
-    FrontierBatch fb;
-    fb.btable = s.d_btable.as<uint64_t>();
-    fb.bmask = bslots - 1;
-    fb.lstate = s.d_lstate.as<uint32_t>();
-    fb.rec_new = s.d_rec_new.as<uint32_t>();
-    unsigned g = (unsigned)((n + 255) / 256);
-    frontier_probe_kernel<<<g, 256, 0, st>>>(n, s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(),
-                                             s.d_arena.as<tgi_link>(), flags, c->fr, fb);
-    frontier_count_kernel<<<g, 256, 0, st>>>(n, s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(), fb);
-    launches += 2;
-    int rc = launch_scan(c, s, fb.rec_new, n, s.d_new_off.as<uint64_t>(), dsc + SC_NEW, launches);
-    if (rc) return rc;
-    int* derr = (int*)(dsc + SC_CURSOR) + 1;
-    frontier_append_kernel<<<g, 256, 0, st>>>(n, s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(),
-                                              s.d_arena.as<tgi_link>(), c->fr, fb, s.d_new_off.as<uint64_t>(), derr);
-    frontier_commit_kernel<<<1, 1, 0, st>>>(c->fr, s.d_new_off.as<uint64_t>(), n, dsc + SC_NEW, derr);
-    launches += 2;
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(c->fr_event, st));
-    c->fr_event_valid = true;
-  }
-  if (want_links) {
-    CK(s.d_link_off.ensure((n + 1) * 8));
-    CK(s.d_link_off32.ensure((n + 1) * 4));
-    int rc = launch_scan(c, s, s.d_link_count.as<uint32_t>(), n, s.d_link_off.as<uint64_t>(), dsc + SC_LINK_TOTAL, launches);
-    if (rc) return rc;
-    CK(s.d_links_out.ensure((size_t)arena_used * sizeof(tgi_link) + 64));
-    unsigned g = (unsigned)((n + 1 + 255) / 256);
-    links_compact_kernel<<<g, 256, 0, st>>>(n, s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(),
-                                            s.d_link_off.as<uint64_t>(), s.d_arena.as<tgi_link>(),
-                                            s.d_links_out.as<tgi_link>(), s.d_link_off32.as<uint32_t>());
-    launches++;
-    CK(cudaGetLastError());
-  }
-  CK(cudaEventRecord(s.ev_k1, st));
-  CK(cudaMemcpyAsync(hsc, dsc, SC_COUNT * 8, cudaMemcpyDeviceToHost, st));
-
-  memset(out, 0, sizeof *out);
-  out->n = n;
-  const bool d2h = !(flags & TGI_RUN_NO_D2H);
-  uint64_t n_links_total = 0;
-  if (d2h) {
-    CK(s.h_status.ensure(n + 1));
-    CK(cudaMemcpyAsync(s.h_status.p, s.d_status.p, n, cudaMemcpyDeviceToHost, st));
-    if (want_json) {
-      CK(s.h_line_off.ensure((n + 1) * 8));
-      CK(s.h_jsonl.ensure(line_total + 1));
-      CK(cudaMemcpyAsync(s.h_line_off.p, s.d_line_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
-      if (line_total) CK(cudaMemcpyAsync(s.h_jsonl.p, s.d_jsonl.p, line_total, cudaMemcpyDeviceToHost, st));
-    }
-  }
-  CK(cudaStreamSynchronize(st));
-  dev_err = ((int*)(hsc + SC_CURSOR))[1];
-  if (dev_err & ERR_FRONTIER_FULL) { set_err(c, "frontier capacity %llu exceeded", (unsigned long long)c->fr.cap); return TGI_E_CAPACITY; }
-  if (dev_err & 16) { set_err(c, "internal: sized and emitted line lengths disagree"); return TGI_E_STATE; }
-  n_links_total = want_links ? hsc[SC_LINK_TOTAL] : 0;
-  if (d2h && want_links) {
-    CK(s.h_link_off.ensure((n + 1) * 4));
-    CK(s.h_links.ensure(n_links_total * sizeof(tgi_link) + 64));
-    CK(cudaMemcpyAsync(s.h_link_off.p, s.d_link_off32.p, (n + 1) * 4, cudaMemcpyDeviceToHost, st));
-    if (n_links_total) CK(cudaMemcpyAsync(s.h_links.p, s.d_links_out.p, n_links_total * sizeof(tgi_link), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-  }
-  float ms = 0;
-  cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1);
-  out->kernel_ms = ms;
-  out->gpu_launches = launches;
-  out->slot = s.idx;
-  if (n) cudaEventElapsedTime(&out->parse_ms, s.ev_p0, s.ev_p1);
-  if (n && want_json) {
-    cudaEventElapsedTime(&out->emit_ms, s.ev_e0, s.ev_e1);
-    cudaEventElapsedTime(&out->emit_fixed_ms, s.ev_e0, s.ev_f1);
-    out->var_bytes = var_bytes;
-  }
-  out->jsonl_len = want_json ? line_total : 0;
-  out->n_links = n_links_total;
-  out->n_new = want_fr ? hsc[SC_NEW] : 0;
-  out->frontier_size = want_fr ? hsc[SC_FSIZE] : 0;
-  if (d2h) {
-    out->status = s.h_status.as<uint8_t>();
-    if (want_json) {
-      out->jsonl = s.h_jsonl.as<uint8_t>();
-      out->line_off = s.h_line_off.as<uint64_t>();
-    }
-    if (want_links) {
-      out->link_off = s.h_link_off.as<uint32_t>();
-      out->links = s.h_links.as<tgi_link>();
-    }
-  }
-  {
-    std::lock_guard<std::mutex> g(c->st_mu);
-    c->stats.records += n;
-    c->stats.bytes_in += s.in_bytes;
-    c->stats.bytes_out += out->jsonl_len;
-    c->stats.links += n_links_total;
-    c->stats.launches += launches;
-    c->stats.kernel_ms_total += ms;
-    if (want_fr) c->stats.frontier_size = out->frontier_size;
-  }
+int upload_yt(tgi_ctx* c, Slot& s, const tgi_yt_batch* in) {
+  if (!in) { set_err(c, "null batch"); return TGI_E_ARG; }
+  if (in->n && (!in->recs || !in->chans)) { set_err(c, "youtube batch: recs/chans must be non-null"); return TGI_E_ARG; }
+  if (in->n >= (1ull << 40)) { set_err(c, "youtube batch: too many records"); return TGI_E_ARG; }
+  s.in_bytes = 0;
+  int rc;
+#define UP(buf, ptr, cnt)                      \
+  rc = h2d(c, s, s.buf, ptr, (size_t)(cnt));   \
+  if (rc) return rc;
+  UP(d_recs, in->recs, in->n);
+  UP(d_strs, in->strs, in->strs_len);
+  UP(d_chans, in->chans, in->n_chans);
+  UP(d_chan_strs, in->chan_strs, in->chan_strs_len);
+#undef UP
+  YtBatchDev& b = s.yt;
+  b.n = in->n;
+  b.recs = s.d_recs.as<tgi_yt_rec>();
+  b.strs = s.d_strs.as<uint8_t>();
+  b.n_chans = in->n_chans;
+  b.chans = s.d_chans.as<tgi_yt_chan>();
+  b.chan_strs = s.d_chan_strs.as<uint8_t>();
+  s.yt_desc_bytes = in->strs_len;
+  s.resident = true;
+  s.tg.n = 0;
   return TGI_OK;
+}
+
+int run_yt(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
+  YtBatchDev& b = s.yt;
+  uint64_t n = b.n;
+  cudaStream_t st = s.stream;
+  uint32_t launches = 0;
+  const bool want_json = flags & TGI_RUN_JSONL;
+  CfgDev cfg;
+  {
+    std::lock_guard<std::mutex> g(c->cfg_mu);
+    cfg = c->cfgdev;
+  }
+  CK(s.d_scalars.ensure(SC_COUNT * 8));
+  CK(s.h_scalars.ensure(SC_COUNT * 8));
+  uint64_t* dsc = s.d_scalars.as<uint64_t>();
+  uint64_t* hsc = s.h_scalars.as<uint64_t>();
+  CK(s.d_status.ensure(n));
+  CK(s.d_linelen.ensure(n * 4));
+  CK(s.d_line_off.ensure((n + 1) * 8));
+  CK(s.d_link_start.ensure(n * 4));
+  CK(s.d_link_count.ensure(n * 4));
+  CK(s.d_url_start.ensure(n * 4));
+  CK(s.d_url_count.ensure(n * 4));
+  // every URL needs "http://x" (8 bytes), every channel link "youtube.com/" (12 bytes)
+  uint64_t urls_cap = s.yt_desc_bytes / 4 + 1024, arena_cap = s.yt_desc_bytes / 12 + 1024;
+  CK(s.d_urls.ensure(urls_cap * sizeof(YtUrl)));
+  CK(s.d_arena.ensure(arena_cap * sizeof(tgi_link)));
+  CK(cudaEventRecord(s.ev_k0, st));
+  CK(cudaMemsetAsync(dsc, 0, SC_COUNT * 8, st));
+  YtOut yo;
+  yo.status = s.d_status.as<uint8_t>();
+  yo.linelen = s.d_linelen.as<uint32_t>();
+  yo.url_start = s.d_url_start.as<uint32_t>();
+  yo.url_count = s.d_url_count.as<uint32_t>();
+  yo.urls = s.d_urls.as<YtUrl>();
+  yo.urls_cap = (uint32_t)std::min<uint64_t>(urls_cap, 0xFFFFFFFFu);
+  yo.url_cursor = (uint32_t*)(dsc + SC_URL_CURSOR);
+  yo.link_start = s.d_link_start.as<uint32_t>();
+  yo.link_count = s.d_link_count.as<uint32_t>();
+  yo.arena = s.d_arena.as<tgi_link>();
+  yo.arena_cap = (uint32_t)std::min<uint64_t>(arena_cap, 0xFFFFFFFFu);
+  yo.cursor = (uint32_t*)(dsc + SC_CURSOR);
+  yo.err = (int*)(dsc + SC_CURSOR) + 1;
+  unsigned g = (unsigned)std::min<uint64_t>((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
+  if (n) {
+    CK(cudaEventRecord(s.ev_p0, st));
+    yt_parse_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, flags, yo);
+    launches++;
+    if (want_json) {
+      yt_size_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, yo);
+      launches++;
+    }
+    CK(cudaEventRecord(s.ev_p1, st));
+  }
+  if (want_json) {
+    int rc = launch_scan(c, s, s.d_linelen.as<uint32_t>(), n, s.d_line_off.as<uint64_t>(), dsc + SC_LINE_TOTAL, launches);
+    if (rc) return rc;
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(hsc, dsc, SC_COUNT * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  int dev_err = ((int*)(hsc + SC_CURSOR))[1];
+  if (dev_err & ERR_ARENA_OVERFLOW) { set_err(c, "youtube url/link arena overflow (cannot happen: capacities are upper bounds)"); return TGI_E_CAPACITY; }
+  if (dev_err & ERR_TOO_MANY_LINKS) { set_err(c, "a record has more than 4096 channel-link candidates (format limit)"); return TGI_E_ARG; }
+  uint64_t line_total = hsc[SC_LINE_TOTAL];
+  uint32_t arena_used = ((uint32_t*)(hsc + SC_CURSOR))[0];
+  if (want_json) {
+    if (c->cfg.max_out_bytes && line_total > c->cfg.max_out_bytes) {
+      set_err(c, "JSONL output %llu bytes exceeds max_out_bytes", (unsigned long long)line_total);
+      return TGI_E_CAPACITY;
+    }
+    CK(s.d_jsonl.ensure(line_total));
+    if (n) {
+      CK(cudaEventRecord(s.ev_e0, st));
+      yt_emit_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, yo, s.d_line_off.as<uint64_t>(), s.d_jsonl.as<uint8_t>(), yo.err);
+      CK(cudaEventRecord(s.ev_f1, st));
+      CK(cudaEventRecord(s.ev_e1, st));
+      launches++;
+    }
+    CK(cudaGetLastError());
+  }
+  return finish_batch(c, s, n, flags, line_total, arena_used, arena_cap, 0, launches, out);
 }
 
 void worker_main(tgi_ctx* c, Slot* s) {
@@ -580,10 +704,12 @@ void worker_main(tgi_ctx* c, Slot* s) {
       if (e != cudaSuccess) { set_err(c, "upload sync: %s", cudaGetErrorString(e)); rc = TGI_E_CUDA; }
     }
     if (rc == TGI_OK && (job == JOB_TG || job == JOB_TG_RESIDENT)) rc = run_tg(c, *s, s->run_flags, &s->res);
-    if (rc == TGI_OK && (job == JOB_YT || job == JOB_YT_RESIDENT || job == JOB_YT_UPLOAD)) {
-      set_err(c, "youtube path is not built yet in this round");
-      rc = TGI_E_STATE;
+    if (job == JOB_YT || job == JOB_YT_UPLOAD) rc = upload_yt(c, *s, s->in_yt);
+    if (rc == TGI_OK && job == JOB_YT_UPLOAD) {
+      cudaError_t e = cudaStreamSynchronize(s->stream);
+      if (e != cudaSuccess) { set_err(c, "upload sync: %s", cudaGetErrorString(e)); rc = TGI_E_CUDA; }
     }
+    if (rc == TGI_OK && (job == JOB_YT || job == JOB_YT_RESIDENT)) rc = run_yt(c, *s, s->run_flags, &s->res);
     {
       std::lock_guard<std::mutex> lk(s->mu);
       s->rc = rc;
@@ -594,16 +720,17 @@ void worker_main(tgi_ctx* c, Slot* s) {
   }
 }
 
-int post_job(tgi_ctx* c, int slot, JobKind kind, const tgi_tg_batch* in, uint32_t flags) {
+int post_job(tgi_ctx* c, int slot, JobKind kind, const tgi_tg_batch* in, uint32_t flags, const tgi_yt_batch* in_yt = nullptr) {
   if (!c) return TGI_E_ARG;
   if (slot < 0 || slot >= TGI_SLOTS) { set_err(c, "bad slot %d", slot); return TGI_E_ARG; }
   Slot& s = c->slots[slot];
   std::lock_guard<std::mutex> lk(s.mu);
   if (s.busy) { set_err(c, "slot %d is busy (wait/release it first)", slot); return TGI_E_STATE; }
-  if ((kind == JOB_TG_RESIDENT) && !s.resident) { set_err(c, "slot %d holds no resident batch", slot); return TGI_E_STATE; }
+  if ((kind == JOB_TG_RESIDENT || kind == JOB_YT_RESIDENT) && !s.resident) { set_err(c, "slot %d holds no resident batch", slot); return TGI_E_STATE; }
   s.busy = true;
   s.done = false;
   s.in_tg = in;
+  s.in_yt = in_yt;
   s.run_flags = flags;
   s.job = kind;
   s.cv.notify_all();
@@ -716,7 +843,8 @@ void tgi_destroy(tgi_ctx* c) {
                     &s.d_comments, &s.d_aux, &s.d_chans, &s.d_chan_strs, &s.d_chan_derived, &s.d_chan_len,
                     &s.d_chan_off, &s.d_chan_blob, &s.d_status, &s.d_linelen, &s.d_line_off, &s.d_link_start,
                     &s.d_link_count, &s.d_xlen, &s.d_xpos, &s.d_arena, &s.d_lstate, &s.d_rec_new, &s.d_new_off, &s.d_link_off,
-                    &s.d_links_out, &s.d_link_off32, &s.d_btable, &s.d_tiles, &s.d_scalars, &s.d_jsonl};
+                    &s.d_links_out, &s.d_link_off32, &s.d_btable, &s.d_tiles, &s.d_scalars, &s.d_jsonl,
+                    &s.d_url_start, &s.d_url_count, &s.d_urls};
     for (DevBuf* d : db) d->release();
     HostBuf* hb[] = {&s.h_status, &s.h_line_off, &s.h_jsonl, &s.h_link_off, &s.h_links, &s.h_scalars};
     for (HostBuf* h : hb) h->release();
@@ -814,11 +942,32 @@ int tgi_result_read_jsonl(tgi_ctx* c, int slot, uint64_t off, uint64_t len, uint
   return TGI_OK;
 }
 
-int tgi_youtube_submit(tgi_ctx* c, int, const tgi_yt_batch*, uint32_t) { set_err(c, "youtube path not built yet"); return TGI_E_STATE; }
-int tgi_youtube_wait(tgi_ctx* c, int, tgi_result*) { set_err(c, "youtube path not built yet"); return TGI_E_STATE; }
-int tgi_youtube_batch(tgi_ctx* c, const tgi_yt_batch*, uint32_t, tgi_result*) { set_err(c, "youtube path not built yet"); return TGI_E_STATE; }
-int tgi_youtube_upload(tgi_ctx* c, int, const tgi_yt_batch*) { set_err(c, "youtube path not built yet"); return TGI_E_STATE; }
-int tgi_youtube_run_resident(tgi_ctx* c, int, uint32_t, tgi_result*) { set_err(c, "youtube path not built yet"); return TGI_E_STATE; }
+int tgi_youtube_submit(tgi_ctx* c, int slot, const tgi_yt_batch* in, uint32_t run_flags) {
+  return post_job(c, slot, JOB_YT, nullptr, run_flags, in);
+}
+int tgi_youtube_wait(tgi_ctx* c, int slot, tgi_result* out) { return wait_job(c, slot, out); }
+int tgi_youtube_batch(tgi_ctx* c, const tgi_yt_batch* in, uint32_t run_flags, tgi_result* out) {
+  if (!c) return TGI_E_ARG;
+  int slot = claim_slot(c);
+  int rc = post_job(c, slot, JOB_YT, nullptr, run_flags, in);
+  if (rc == TGI_OK) rc = wait_job(c, slot, out);
+  if (rc != TGI_OK) tgi_result_release(c, slot);
+  return rc;
+}
+int tgi_youtube_upload(tgi_ctx* c, int slot, const tgi_yt_batch* in) {
+  int rc = post_job(c, slot, JOB_YT_UPLOAD, nullptr, 0, in);
+  if (rc) return rc;
+  rc = wait_job(c, slot, nullptr);
+  tgi_result_release(c, slot);
+  return rc;
+}
+int tgi_youtube_run_resident(tgi_ctx* c, int slot, uint32_t run_flags, tgi_result* out) {
+  int rc = post_job(c, slot, JOB_YT_RESIDENT, nullptr, run_flags);
+  if (rc) return rc;
+  rc = wait_job(c, slot, out);
+  if (rc != TGI_OK) tgi_result_release(c, slot);
+  return rc;
+}
 
 // ---- frontier host API ------------------------------------------------------------------------------
 static int frontier_insert_impl(tgi_ctx* c, const void* d_keys, uint64_t n, void* d_is_new) {
