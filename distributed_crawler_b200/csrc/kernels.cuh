@@ -7,6 +7,7 @@
 //   frontier_*    exact open-addressed hash set over 32-byte keys (K5)
 #pragma once
 #include "tg_walk.cuh"
+#include "tg_lane.cuh"
 #include "yt_walk.cuh"
 
 namespace tgi {
@@ -28,7 +29,7 @@ __global__ void __launch_bounds__(CTA_THREADS) tg_chan_size_kernel(TgBatchDev b,
   ChanDerived d = size_tg_chan(b, c);
   if (lane_id() == 0) {
     cd[c] = d;
-    len[c] = d.user_len + d.name_len + d.title_len + d.cdata_len;
+    len[c] = pad16(d.user_len) + pad16(d.name_len) + pad16(d.title_len) + pad16(d.cdata_len);
   }
 }
 
@@ -195,6 +196,29 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_fixed_kernel(TgBatchDe
     const uint64_t lo = in.line_off[r];
     emit_tg_fixed(in.out + lo, &wss[wid], &cs, a, (uint32_t)(in.line_off[r + 1] - lo), in.xlen + r * 8, in.xpos + r * 8, in.err);
   }
+}
+
+// the same job, one LANE per record (tg_lane.cuh): 32 records per warp task
+__global__ void __launch_bounds__(CTA_THREADS, 2) tg_emit_lane_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
+  extern __shared__ __align__(128) uint8_t lane_smem[];
+  LaneShared& sh = *(LaneShared*)lane_smem;
+  static_assert(LANE_WARPS == WARPS_PER_CTA, "one field row block per warp");
+  lane_shared_fill(sh);
+  __syncthreads();
+  const int wid = threadIdx.x >> 5, l = lane_id();
+  const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  LaneStream s;
+  ls_init(s, smem_addr(sh.stage[wid][l]));
+  for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
+    uint64_t r = g * 32 + l;
+    bool active = r < b.n;
+    if (!active) r = b.n - 1;
+    active = active && in.status[r] == TGI_ST_EMITTED;
+    if (!__any_sync(FULL, active)) continue;
+    emit_tg_lane(sh, sh.rows[wid][l], s, b, cfg, r, active, in.out, in.line_off, in.xlen + r * 8,
+                 in.xpos + r * 8, in.err);
+  }
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging rows must outlive the bulk reads
 }
 
 __global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_esc_kernel(TgBatchDev b, EmitIn in) {

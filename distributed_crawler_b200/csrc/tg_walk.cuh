@@ -14,6 +14,9 @@
 namespace tgi {
 
 // per-channel strings pre-rendered once per batch by the channel job
+// the four segments start 16-byte aligned and are zero padded (the lane emitter fetches them in
+// 16-byte blocks): segment k starts at off + sum_{j<k} pad16(len_j)
+DEVI uint32_t pad16(uint32_t x) { return (x + 15u) & ~15u; }
 struct ChanDerived {
   uint64_t off;        // into chan_blob: esc_user | esc_name | "esc_title" | cdata
   uint32_t user_len;   // JSON-escaped ActiveUsernames[0] (0 = no public link)
@@ -41,7 +44,8 @@ struct TgBatchDev {
 };
 
 struct CfgDev {             // per-context constants in a small device blob
-  const uint8_t* blob;      // label_esc | created_tg | created_yt | capture
+  const uint8_t* blob;      // label_esc | created_tg | created_yt | capture: 16-byte aligned, zero padded
+  uint32_t off[4];          // segment offsets into blob
   uint32_t label_len;       // JSON-escaped crawl_label (no quotes)
   uint32_t created_tg_len;  // quoted RFC3339 of created_at.UTC().Truncate(s)
   uint32_t created_yt_len;  // quoted RFC3339Nano of created_at in the local zone
@@ -394,14 +398,13 @@ DEVI void emit_tg_prologue(WarpScratch* ws, const TgWalkArgs& a, const ChanDeriv
     ws->flen[F_POSTTYPE] = kPostTypeLen[a.v.ct];
   } else if (l >= 8 && l < 12) {
     int k = l - 8;
-    uint32_t o = k == 0 ? 0u : k == 1 ? cd.user_len : k == 2 ? cd.user_len + cd.name_len : cd.user_len + cd.name_len + cd.title_len;
+    uint32_t o = k == 0 ? 0u : k == 1 ? pad16(cd.user_len) : k == 2 ? pad16(cd.user_len) + pad16(cd.name_len)
+                                                            : pad16(cd.user_len) + pad16(cd.name_len) + pad16(cd.title_len);
     ws->src_ptr[k] = (uint64_t)(uintptr_t)(b.chan_blob + cd.off + o);
     ws->src_len[k] = k == 0 ? cd.user_len : k == 1 ? cd.name_len : k == 2 ? cd.title_len : cd.cdata_len;
   } else if (l >= 12 && l < 16) {
     int k = l - 12;
-    uint32_t o = k == 0 ? 0u : k == 1 ? cfg.label_len : k == 2 ? cfg.label_len + cfg.created_tg_len
-                                                               : cfg.label_len + cfg.created_tg_len + cfg.created_yt_len;
-    ws->src_ptr[4 + k] = (uint64_t)(uintptr_t)(cfg.blob + o);
+    ws->src_ptr[4 + k] = (uint64_t)(uintptr_t)(cfg.blob + cfg.off[k]);
     ws->src_len[4 + k] = k == 0 ? cfg.label_len : k == 1 ? cfg.created_tg_len : k == 2 ? cfg.created_yt_len : cfg.capture_len;
   } else if (l >= 16 && l < 16 + XL_COUNT) {
     ws->xlen[l - 16] = xlen_g[l - 16];
@@ -590,12 +593,15 @@ DEVI void emit_tg_chan(uint8_t* dst, WarpScratch* ws, const TgBatchDev& b, uint3
     o += sizeof(x) - 1;                              \
   } while (0)
   o += esc_to_global(dst + o, user, ch.user_len);
+  o = pad16(o);
   o += esc_to_global(dst + o, name, ch.name_len);
+  o = pad16(o);
   gput1(dst + o, '"');
   o++;
   o += esc_to_global(dst + o, title, ch.title_len);
   gput1(dst + o, '"');
   o++;
+  o = pad16(o);
   CH_LIT(kCd0);
   o += esc_to_global(dst + o, title, ch.title_len);
   CH_LIT(kCd1);

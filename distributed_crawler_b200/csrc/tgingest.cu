@@ -215,19 +215,25 @@ int build_cfg_blob(tgi_ctx* c) {
   uint32_t esc = 0;
   CK(cudaMemcpyAsync(&esc, len.p, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
-  size_t total = (size_t)esc + n_tg + n_yt + n_cap;
+  auto pad16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t o_tg = pad16(esc), o_yt = o_tg + pad16(n_tg), o_cap = o_yt + pad16(n_yt);
+  size_t total = o_cap + pad16(n_cap);
   CK(c->d_cfg.ensure(total + 16));
   CK(cudaMemsetAsync(c->d_cfg.p, 0, total + 16 + PAD, s));
   cfg_label_emit_kernel<<<1, 32, 0, s>>>(raw.as<uint8_t>(), n, c->d_cfg.as<uint8_t>());
   uint8_t* b = c->d_cfg.as<uint8_t>();
-  CK(cudaMemcpyAsync(b + esc, t_tg, n_tg, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(b + esc + n_tg, t_yt, n_yt, cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(b + esc + n_tg + n_yt, t_cap, n_cap, cudaMemcpyHostToDevice, s));
+  if (n_tg) CK(cudaMemcpyAsync(b + o_tg, t_tg, n_tg, cudaMemcpyHostToDevice, s));
+  if (n_yt) CK(cudaMemcpyAsync(b + o_yt, t_yt, n_yt, cudaMemcpyHostToDevice, s));
+  if (n_cap) CK(cudaMemcpyAsync(b + o_cap, t_cap, n_cap, cudaMemcpyHostToDevice, s));
   CK(cudaStreamSynchronize(s));
   raw.release();
   len.release();
   CfgDev d{};
   d.blob = b;
+  d.off[0] = 0;
+  d.off[1] = (uint32_t)o_tg;
+  d.off[2] = (uint32_t)o_yt;
+  d.off[3] = (uint32_t)o_cap;
   d.label_len = esc;
   d.created_tg_len = (uint32_t)n_tg;
   d.created_yt_len = (uint32_t)n_yt;
@@ -545,6 +551,7 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     }
     CK(s.d_chan_blob.ensure(chan_total));
     CK(s.d_jsonl.ensure(line_total));
+    if (chan_total) CK(cudaMemsetAsync(s.d_chan_blob.p, 0, chan_total, st));  // segment padding must read as zero
     b.chan_blob = s.d_chan_blob.as<uint8_t>();
     unsigned g = (b.n_chans + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (g) {
@@ -565,7 +572,18 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       uint64_t want = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
       unsigned ge = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms * 8);
       CK(cudaEventRecord(s.ev_e0, st));
-      tg_emit_fixed_kernel<<<ge, CTA_THREADS, 0, st>>>(b, cfg, ei);
+      static const bool warp_fixed = getenv("TGI_EMIT_FIXED_WARP") != nullptr;  // A/B switch: the warp-per-record walker
+      if (warp_fixed) {
+        tg_emit_fixed_kernel<<<ge, CTA_THREADS, 0, st>>>(b, cfg, ei);
+      } else {
+        const uint64_t groups = (n + 31) / 32;
+        unsigned gl = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 2);
+        static const bool attr_set = [] {
+          return cudaFuncSetAttribute(tg_emit_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LaneShared)) == cudaSuccess;
+        }();
+        if (!attr_set) { set_err(c, "cannot reserve %zu bytes of shared memory for the lane emitter", sizeof(LaneShared)); return TGI_E_CUDA; }
+        tg_emit_lane_kernel<<<gl, CTA_THREADS, sizeof(LaneShared), st>>>(b, cfg, ei);
+      }
       CK(cudaEventRecord(s.ev_f1, st));
       tg_emit_esc_kernel<<<ge, CTA_THREADS, 0, st>>>(b, ei);
       tg_emit_maps_kernel<<<ge, CTA_THREADS, 0, st>>>(b, ei);

@@ -376,8 +376,8 @@ DEVI bool walk_yt_record(W& w, const YtArgs& a) {
     vlen = __shfl_sync(FULL, vlen, 0);
   }
   const uint8_t* cblob = cfg.blob;
-  const uint8_t* created = cblob + cfg.label_len + cfg.created_tg_len;
-  const uint8_t* capture = created + cfg.created_yt_len;
+  const uint8_t* created = cblob + cfg.off[2];
+  const uint8_t* capture = cblob + cfg.off[3];
   const bool handle_url = ch.id_len > 0 && ldb(chid) == '@';
 
 #define VURL()                                      \

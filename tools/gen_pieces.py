@@ -163,11 +163,43 @@ def emit_table(name, prog):
     return "\n".join(lines) + "\n"
 
 
+def emit_lane_table(name, prog):
+    """The same program for the lane-per-record emitter (tg_lane.cuh): every lane streams its own
+    line, so literals are fetched as whole 16-byte blocks: they start 16-byte aligned in this blob
+    and are zero padded.  Entry = kind | arg << 4 | cond << 8 | (off / 16) << 12 | len << 23."""
+    blob = bytearray()
+    rows = []
+    for kind, arg, cond, text in prog:
+        if kind == K_LIT:
+            tb = text.encode()
+            while len(blob) % 16: blob.append(0)
+            base = len(blob)
+            blob += tb
+            assert len(tb) < 512 and base // 16 < 2048
+            rows.append(kind | (cond << 8) | ((base // 16) << 12) | (len(tb) << 23))
+        else:
+            rows.append(kind | (arg << 4) | (cond << 8))
+    while len(blob) % 16: blob.append(0)
+    lines = [f"constexpr int k{name}LaneNPieces = {len(rows)};",
+             f"constexpr int k{name}LaneTemplateLen = {len(blob)};   // multiple of 16",
+             f"__device__ __align__(16) const char k{name}LaneTemplate[] ="]
+    bb = bytes(blob)
+    for i in range(0, len(bb), 64):
+        lines.append("    " + c_string(bb[i:i + 64]))
+    lines[-1] += ";"
+    lines.append(f"__device__ const uint32_t k{name}LanePieces[{len(rows)}] = {{")
+    for i in range(0, len(rows), 6):
+        lines.append("    " + ", ".join("0x%08xu" % r for r in rows[i:i + 6]) + ",")
+    lines.append("};")
+    return "\n".join(lines) + "\n"
+
+
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
     out = os.path.join(here, "..", "distributed_crawler_b200", "csrc", "tg_pieces.inc")
     with open(out, "w") as f:
         f.write(emit_table("Tg", TG))
+        f.write(emit_lane_table("Tg", TG))
     print("wrote", os.path.normpath(out), "pieces:", len(TG))
 
 
