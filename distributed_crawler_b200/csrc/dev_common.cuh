@@ -562,6 +562,32 @@ DEVI void gcopy_g(uint8_t* dst, const uint8_t* src, uint32_t n) {
   }
   for (; i + l < n; i += 32) d[i] = (uint8_t)ldb(s + i);
 }
+// warp memcpy for long strings: 16-byte stores to the aligned part of dst, the source read as aligned
+// 16-byte blocks and funnel-shifted by its (warp-uniform) misalignment; <= 15 head and tail bytes
+// go out as single bytes.  Reads up to 31 bytes past src + n (device blobs carry that slack).
+__device__ __noinline__ void warp_copy_vec(uint8_t* dst, const uint8_t* src, uint32_t n) {
+  const uint32_t l = lane_id();
+  const uint32_t hh = min((16u - ((uint32_t)(uintptr_t)dst & 15u)) & 15u, n);
+  if (l < hh) dst[l] = (uint8_t)ldb(src + l);
+  dst += hh;
+  src += hh;
+  n -= hh;
+  const uint32_t sa = (uint32_t)(uintptr_t)src & 15u, sh = (sa & 3u) * 8u, q = sa >> 2;
+  const uint4* A = (const uint4*)(src - sa);
+  const uint32_t nb = n >> 4;
+  for (uint32_t i = l; i < nb; i += 32) {
+    const uint4 a = __ldg(A + i), b = __ldg(A + i + 1);
+    uint32_t w0, w1, w2, w3, w4;  // the five words that hold bytes [sa, sa + 16) of b:a
+    if (q == 0) { w0 = a.x; w1 = a.y; w2 = a.z; w3 = a.w; w4 = b.x; }
+    else if (q == 1) { w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; }
+    else if (q == 2) { w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; }
+    else { w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; }
+    *(uint4*)(dst + 16u * i) = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                                          __funnelshift_r(w3, w4, sh));
+  }
+  const uint32_t t0 = nb << 4;
+  if (t0 + l < n) dst[t0 + l] = (uint8_t)ldb(src + t0 + l);
+}
 DEVI void gcopy_s(uint8_t* dst, uint32_t src, uint32_t n) {
   for (uint32_t i = lane_id(); i < n; i += 32) dst[i] = (uint8_t)lds8(src + i);
 }

@@ -171,6 +171,7 @@ struct EmitIn {
   const tgi_link* arena;
   uint8_t* out;
   int* err;
+  uint32_t lane_text_max;  // see emit_tg_escapes
 };
 
 __global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_fixed_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_fixed_kernel(TgBatchDe
 }
 
 // the same job, one LANE per record (tg_lane.cuh): 32 records per warp task
-__global__ void __launch_bounds__(CTA_THREADS, 2) tg_emit_lane_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
+__global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_lane_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
   extern __shared__ __align__(128) uint8_t lane_smem[];
   LaneShared& sh = *(LaneShared*)lane_smem;
   static_assert(LANE_WARPS == WARPS_PER_CTA, "one field row block per warp");
@@ -218,7 +219,6 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tg_emit_lane_kernel(TgBatchDev
     emit_tg_lane(sh, sh.rows[wid][l], s, b, cfg, r, active, in.out, in.line_off, in.xlen + r * 8,
                  in.xpos + r * 8, in.err);
   }
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging rows must outlive the bulk reads
 }
 
 __global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_esc_kernel(TgBatchDev b, EmitIn in) {
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_esc_kernel(TgBatchDev 
     a.cfg = nullptr;
     a.r = r;
     a.v = load_rec_view(b, r);
-    emit_tg_escapes(in.out + in.line_off[r], a, in.xlen + r * 8, in.xpos + r * 8);
+    emit_tg_escapes(in.out + in.line_off[r], a, in.xlen + r * 8, in.xpos + r * 8, in.lane_text_max);
   }
 }
 

@@ -9,10 +9,8 @@
 //
 // A lane's output is a byte stream at an arbitrary address: LaneStream keeps the bytes of the
 // current 16-byte block in four registers.  Full blocks are staged in the lane's own shared-memory
-// row and drained to HBM by per-lane TMA bulk stores (cp.async.bulk global <- shared::cta): 32 lanes
-// writing 32 different lines with ST.128 cost the LSU 32 wavefronts per instruction and reached
-// 1.2 TB/s in a micro-benchmark, the same rows drained by bulk stores 4.8-6.1 TB/s
-// (scratch/tma_bench.cu, profiles/README.md).  Blocks shared with somebody else (the neighbouring
+// row; the warp drains all 32 rows together with coalesced 16-byte stores (ls_drain_warp).  Blocks
+// shared with somebody else (the neighbouring
 // line, or a variable piece written by the esc / maps kernels) are stored byte-exact (store_bytes),
 // so the kernels never overwrite each other's bytes.
 //
@@ -23,35 +21,50 @@
 
 namespace tgi {
 
-constexpr uint32_t LANE_STAGE_HALF = 128;                       // bytes per staging half (one bulk store)
-constexpr uint32_t LANE_STAGE_ROW = 2 * LANE_STAGE_HALF + 16;   // two halves; +16 spreads the rows over the banks
+constexpr uint32_t LANE_STAGE_BYTES = 128;                    // staged per lane between two drains
+constexpr uint32_t LANE_STAGE_ROW = LANE_STAGE_BYTES + 16;    // +16 spreads the lanes' rows over the banks
 
 struct LaneStream {
   uint64_t pos;             // absolute address of the next output byte
   uint32_t c0, c1, c2, c3;  // bytes [head, pos & 15) of the current block, zero elsewhere
   uint32_t head;            // first byte of the current block that belongs to this stream
-  uint64_t seg;             // global address of the first block staged in the active half
-  uint32_t row_s, half_s;   // shared-space address of the lane's staging row / of its active half
-  uint32_t fill;            // bytes staged in the active half
+  uint64_t seg;             // global address of the first block staged in the row
+  uint32_t row_s;           // shared-space address of the lane's staging row
+  uint32_t fill;            // bytes staged in the row (consecutive blocks starting at seg)
 };
 
-// hand the staged blocks to the TMA and switch halves; the half we switch to was read by the group
-// before the one committed here, so at most that one may still be pending
-DEVI void ls_drain(LaneStream& s) {
-  if (s.fill) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(s.seg), "r"(s.half_s), "r"(s.fill) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    s.half_s = s.half_s == s.row_s ? s.row_s + LANE_STAGE_HALF : s.row_s;
-    s.fill = 0;
-    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-  }
-}
 DEVI void ls_stage(LaneStream& s, uint64_t blk) {
   if (s.fill == 0) s.seg = blk;
-  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(s.half_s + s.fill), "r"(s.c0), "r"(s.c1), "r"(s.c2), "r"(s.c3) : "memory");
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(s.row_s + s.fill), "r"(s.c0), "r"(s.c1), "r"(s.c2), "r"(s.c3) : "memory");
   s.fill += 16;
-  if (s.fill == LANE_STAGE_HALF) ls_drain(s);
+}
+
+// Warp-collective: write every lane's staged blocks to HBM.  Eight lanes take one row (8 x 16 B), so
+// one LDS.128 / STG.128 pair moves four rows and the global stores are coalesced per row (the per-lane
+// alternatives, measured: ST.128 straight from the lanes = 32 lines per instruction, 1.2 TB/s in
+// scratch/tma_bench.cu; per-lane TMA bulk stores reach 4.8-6.1 TB/s there but cost ~10 issue slots
+// each, because UBLKCP is a uniform-datapath instruction and the compiler serialises the lanes).
+DEVI void ls_drain_warp(LaneStream& s) {
+  if (!__any_sync(FULL, s.fill != 0)) return;
+  __syncwarp();
+  const int l = lane_id(), sub = l >> 3, t16 = (l & 7) * 16;
+  const uint32_t warp_rows = s.row_s - (uint32_t)l * LANE_STAGE_ROW;
+#pragma unroll 2
+  for (int j = 0; j < 32; j += 4) {
+    const int rj = j + sub;
+    const uint32_t f = __shfl_sync(FULL, s.fill, rj);
+    const uint64_t sg = __shfl_sync(FULL, s.seg, rj);
+    if ((uint32_t)t16 < f) {
+      uint4 w;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(warp_rows + (uint32_t)rj * LANE_STAGE_ROW + (uint32_t)t16) : "memory");
+      *(uint4*)(uintptr_t)(sg + (uint32_t)t16) = w;
+    }
+  }
+  __syncwarp();
+  s.fill = 0;
+}
+DEVI void ls_maybe_drain(LaneStream& s) {
+  if (__any_sync(FULL, s.fill >= LANE_STAGE_BYTES)) ls_drain_warp(s);
 }
 
 // bytes [lo, hi) of the 16-byte block at blk (16-byte aligned)
@@ -71,10 +84,8 @@ __device__ __noinline__ void store_bytes(uint64_t blk, uint32_t c0, uint32_t c1,
   }
 }
 
-// once per kernel: the active half must survive from one record to the next, because the bulk store
-// of the previous record may still be reading the other one
-DEVI void ls_init(LaneStream& s, uint32_t row_s) {
-  s.row_s = s.half_s = row_s;
+DEVI void ls_init(LaneStream& s, uint32_t row_s) {  // once per kernel
+  s.row_s = row_s;
   s.fill = 0;
   s.seg = 0;
 }
@@ -114,17 +125,36 @@ DEVI void ls_append(LaneStream& s, uint4 w, uint32_t n) {
   s.pos += n;
 }
 
-// write out what the current block holds (before a gap / at the end of the line)
+// w >> (8 * sb) over 128 bits, sb in 0..15 (per lane)
+DEVI uint4 shr128_bytes(uint4 w, uint32_t sb) {
+  const uint32_t sh = (sb & 3u) * 8u;
+  const uint32_t v0 = __funnelshift_r(w.x, w.y, sh), v1 = __funnelshift_r(w.y, w.z, sh), v2 = __funnelshift_r(w.z, w.w, sh),
+                 v3 = w.w >> sh;
+  const bool b0 = (sb & 4u) != 0, b1 = (sb & 8u) != 0;
+  const uint32_t a0 = b0 ? v1 : v0, a1 = b0 ? v2 : v1, a2 = b0 ? v3 : v2, a3 = b0 ? 0u : v3;
+  return make_uint4(b1 ? a2 : a0, b1 ? a3 : a1, b1 ? 0u : a2, b1 ? 0u : a3);
+}
+// keep the low k bytes (k in 0..16)
+DEVI uint4 mask128(uint4 w, uint32_t k) {
+  auto m = [&](uint32_t lo) -> uint32_t {  // mask of word starting at byte lo
+    return k >= lo + 4u ? 0xffffffffu : (k <= lo ? 0u : (1u << ((k - lo) * 8u)) - 1u);
+  };
+  return make_uint4(w.x & m(0), w.y & m(4), w.z & m(8), w.w & m(12));
+}
+
+// write out what the current block holds (before a gap / at the end of the line); the staged blocks
+// stay in the row until the next warp-collective drain
 DEVI void ls_flush(LaneStream& s) {
-  ls_drain(s);
   const uint32_t ph = (uint32_t)s.pos & 15u;
   if (ph > s.head) store_bytes(s.pos & ~15ull, s.c0, s.c1, s.c2, s.c3, s.head, ph);
   s.c0 = s.c1 = s.c2 = s.c3 = 0;
   s.head = ph;
 }
 
-// leave g bytes to another writer
+// leave g bytes to another writer.  Warp-collective: the staged blocks of a lane must be consecutive,
+// so a gap in any lane drains the rows first.
 DEVI void ls_skip(LaneStream& s, uint32_t g) {
+  if (__any_sync(FULL, g != 0)) ls_drain_warp(s);
   if (g) {
     ls_flush(s);
     s.pos += g;
@@ -136,6 +166,7 @@ DEVI void ls_skip(LaneStream& s, uint32_t g) {
 constexpr int LANE_ROW_WORDS = 36;  // per lane: 8 blocks of rendered fields + 8 length bytes; 36 = 4 * odd
                                     // keeps the lanes' LDS.128 on distinct banks
 constexpr int LANE_WARPS = 8;
+constexpr uint32_t LANE_TEXT_MAX = 512;  // longer (or escaped) strings are left to the warp-per-record esc kernel
 struct LaneShared {
   uint4 tmpl[kTgLaneTemplateLen / 16];
   uint4 ptype[TGI_CT__COUNT * 2];  // MessageContentType() strings, 32 bytes each, zero padded
@@ -223,7 +254,10 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
       if (!on) n = 0;
       const uint32_t nmax = __reduce_max_sync(FULL, n);
       for (uint32_t i = 0; i < nmax; i += 16, src++)
+      {
         if (i < n) ls_append(s, *src, min(16u, n - i));
+        ls_maybe_drain(s);
+      }
     } else if (kind == K_CHAN || kind == K_CFG) {  // global sources, 16-byte aligned and zero padded
       const uint4* src;
       uint32_t n;
@@ -239,8 +273,44 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
       if (!on) n = 0;
       const uint32_t nmax = __reduce_max_sync(FULL, n);
       for (uint32_t i = 0; i < nmax; i += 16, src++)
+      {
         if (i < n) ls_append(s, __ldg(src), min(16u, n - i));
-    } else {  // pieces written by the esc / maps kernels: remember where they go
+        ls_maybe_drain(s);
+      }
+    } else if (kind == K_ESC) {  // a string of the record: copied here if it needs no escaping and is short
+      const uint8_t* p = arg == XL_DESC ? d.desc : arg == XL_MEDIA ? a.v.media : arg == XL_HANDLE ? a.v.handle : a.v.alt;
+      const uint32_t n = arg == XL_DESC ? d.desc_len : arg == XL_MEDIA ? a.v.media_len : arg == XL_HANDLE ? a.v.handle_len : a.v.alt_len;
+      uint32_t xl = 0;
+      if (active) {
+        xpos_g[arg] = (uint32_t)(s.pos - line_start);
+        if (on) xl = xlen_g[arg];
+      }
+      const bool mine = on && xl == n && n <= LANE_TEXT_MAX;  // same rule in emit_tg_escapes
+      ls_skip(s, mine ? 0u : xl);                             // else the esc kernel writes it
+      uint32_t rem = mine ? n : 0u;
+      if (__any_sync(FULL, rem != 0)) {
+        const uint32_t s0 = (uint32_t)(uintptr_t)p & 15u;
+        const uint4* A = (const uint4*)(p - s0);
+        if (rem) {  // bytes [s0, 16) of the first aligned block
+          const uint32_t k = min(rem, 16u - s0);
+          ls_append(s, mask128(shr128_bytes(__ldg(A), s0), k), k);
+          rem -= k;
+        }
+        A++;
+        ls_maybe_drain(s);
+        while (__any_sync(FULL, rem != 0)) {
+          if (rem) {
+            const uint32_t k = min(rem, 16u);
+            uint4 w = __ldg(A);
+            if (k < 16u) w = mask128(w, k);
+            ls_append(s, w, k);
+            rem -= k;
+          }
+          A++;
+          ls_maybe_drain(s);
+        }
+      }
+    } else {  // pieces written by the maps kernel: remember where they go
       const uint32_t xi = kind == K_ESC ? arg : kind == K_COMMENTS ? (uint32_t)XL_COMMENTS
                                                  : kind == K_REACTIONS ? (uint32_t)XL_REACTIONS : (uint32_t)XL_OUTLINKS;
       uint32_t g = 0;
@@ -252,6 +322,7 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
     }
   }
   ls_flush(s);
+  ls_drain_warp(s);
   if (active && (uint32_t)(s.pos - line_start) != total) atomicOr(err, 16);  // sizing and emission disagree: never expected
 }
 

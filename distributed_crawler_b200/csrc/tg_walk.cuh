@@ -525,7 +525,9 @@ DEVI void emit_tg_fixed(uint8_t* line, WarpScratch* ws, const CtaShared* cs, con
 }
 
 // ---- emit, kernel 2 of 3: the escaped strings --------------------------------------------------------
-DEVI void emit_tg_escapes(uint8_t* line, const TgWalkArgs& a, const uint32_t* xlen_g, const uint32_t* xpos_g) {
+// lane_text_max: strings that need no escaping and are at most this long were already copied by the
+// lane emitter (tg_lane.cuh, same rule); 0xffffffff = none were
+DEVI void emit_tg_escapes(uint8_t* line, const TgWalkArgs& a, const uint32_t* xlen_g, const uint32_t* xpos_g, uint32_t lane_text_max) {
   // description / media by content type (tdutils.go:443-587), as in tg_derive
   const uint32_t ct = a.v.ct;
   const uint8_t* desc = nullptr;
@@ -548,6 +550,13 @@ DEVI void emit_tg_escapes(uint8_t* line, const TgWalkArgs& a, const uint32_t* xl
     uint32_t o = __shfl_sync(FULL, myp, j);
     const uint8_t* p = j == 0 ? desc : j == 1 ? a.v.media : j == 2 ? a.v.handle : a.v.alt;
     uint32_t n = j == 0 ? desc_len : j == 1 ? a.v.media_len : j == 2 ? a.v.handle_len : a.v.alt_len;
+    if (ln == n) {  // nothing to escape
+      if (n <= lane_text_max && lane_text_max != 0xffffffffu) continue;
+      if (n >= 64) {
+        warp_copy_vec(line + o, p, n);
+        continue;
+      }
+    }
     esc_to_global(line + o, p, n);
   }
 }

@@ -573,11 +573,12 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       unsigned ge = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms * 8);
       CK(cudaEventRecord(s.ev_e0, st));
       static const bool warp_fixed = getenv("TGI_EMIT_FIXED_WARP") != nullptr;  // A/B switch: the warp-per-record walker
+      ei.lane_text_max = warp_fixed ? 0xffffffffu : LANE_TEXT_MAX;
       if (warp_fixed) {
         tg_emit_fixed_kernel<<<ge, CTA_THREADS, 0, st>>>(b, cfg, ei);
       } else {
         const uint64_t groups = (n + 31) / 32;
-        unsigned gl = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 2);
+        unsigned gl = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 3);
         static const bool attr_set = [] {
           return cudaFuncSetAttribute(tg_emit_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LaneShared)) == cudaSuccess;
         }();
