@@ -141,14 +141,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_kernel(TgBatchDev b, C
     a.v = load_rec_view(b, r);
     a.links = o.arena + o.link_start[r];
     a.n_links = o.link_count[r];
-    uint32_t xl[XL_COUNT];
+    uint32_t xl[8];
     uint32_t llen = size_tg_record(a, xl);
     uint32_t mine = 0;
 #pragma unroll
-    for (int j = 0; j < XL_COUNT; j++)
+    for (int j = 0; j < 8; j++)
       if (l == j) mine = xl[j];
     if (l < 8) o.xlen[r * 8 + l] = mine;
-    if (llen) var_sum += warp_sum(mine);
+    if (llen) var_sum += warp_sum(l < XL_COUNT ? mine : 0u);
     if (l == 0) {
       if (llen == 0) o.status[r] = TGI_ST_NOLINE;
       o.linelen[r] = llen;
@@ -216,41 +216,86 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_lane_kernel(TgBatchDev
     if (!active) r = b.n - 1;
     active = active && in.status[r] == TGI_ST_EMITTED;
     if (!__any_sync(FULL, active)) continue;
-    emit_tg_lane(sh, sh.rows[wid][l], s, b, cfg, r, active, in.out, in.line_off, in.xlen + r * 8,
-                 in.xpos + r * 8, in.err);
+    emit_tg_lane(sh, sh.rows[wid][l], s, b, cfg, r, active, in.out, in.line_off, in.xlen + r * 8, in.xpos + r * 8,
+                 in.arena + in.link_start[r], active ? in.link_count[r] : 0u, in.err);
   }
 }
 
+// The esc and maps kernels take what the lane emitter left: each lane first checks one record of a
+// group of 32, then the warp walks the records that need it (most do not).
 __global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_esc_kernel(TgBatchDev b, EmitIn in) {
-  const int wid = threadIdx.x >> 5;
-  const uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
-  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
-    if (in.status[r] != TGI_ST_EMITTED) continue;
-    TgWalkArgs a;
-    a.b = &b;
-    a.cfg = nullptr;
-    a.r = r;
-    a.v = load_rec_view(b, r);
-    emit_tg_escapes(in.out + in.line_off[r], a, in.xlen + r * 8, in.xpos + r * 8, in.lane_text_max);
+  const int wid = threadIdx.x >> 5, l = lane_id();
+  const bool lane_mode = in.lane_text_max != 0xffffffffu;
+  const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
+    const uint64_t r = g * 32 + l;
+    bool need = false;
+    if (r < b.n && in.status[r] == TGI_ST_EMITTED) {
+      need = true;
+      if (lane_mode) {  // same rule as emit_tg_lane: clean and short strings are already in place
+        const tgi_tg_rec* rec = &b.recs[r];
+        const uint4 xl = *(const uint4*)(in.xlen + r * 8);
+        const uint32_t ct = rec->content_type;
+        const bool text_desc = ct == TGI_CT_TEXT || ct == TGI_CT_VIDEO || ct == TGI_CT_PHOTO || ct == TGI_CT_ANIMATION;
+        const uint32_t dlen = text_desc ? ((rec->flags & TGI_RF_HAS_TEXT) ? rec->text_len : 0u)
+                                        : (ct == TGI_CT_ANIMATED_EMOJI || ct == TGI_CT_POLL || ct == TGI_CT_GIVEAWAY ||
+                                           ct == TGI_CT_PAID_MEDIA || ct == TGI_CT_DOCUMENT) ? rec->alt_len : 0u;
+        auto left = [&](uint32_t x, uint32_t n) { return x != 0 && !(x == n && n <= in.lane_text_max); };
+        need = left(xl.x, dlen) || left(xl.y, rec->media_len) || left(xl.z, rec->handle_len) || left(xl.w, rec->alt_len);
+      }
+    }
+    uint32_t todo = __ballot_sync(FULL, need);
+    while (todo) {
+      const uint64_t rr = g * 32 + (uint32_t)(__ffs(todo) - 1);
+      todo &= todo - 1;
+      TgWalkArgs a;
+      a.b = &b;
+      a.cfg = nullptr;
+      a.r = rr;
+      a.v = load_rec_view(b, rr);
+      emit_tg_escapes(in.out + in.line_off[rr], a, in.xlen + rr * 8, in.xpos + rr * 8, in.lane_text_max);
+    }
   }
 }
 
 __global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_maps_kernel(TgBatchDev b, EmitIn in) {
   __shared__ MapScratch mss[WARPS_PER_CTA];
-  const int wid = threadIdx.x >> 5;
-  const uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
-  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
-    if (in.status[r] != TGI_ST_EMITTED) continue;
-    uint8_t* line = in.out + in.line_off[r];
-    const uint32_t* xp = in.xpos + r * 8;
-    const bool comments_nil = (b.recs[r].flags & TGI_RF_COMMENTS_NIL) != 0;
-    const uint32_t c0 = b.comment_off[r], c1 = b.comment_off[r + 1];
-    if (comments_nil) gcopy_g(line + xp[XL_COMMENTS], (const uint8_t*)kNullLit, 4);
-    else if (c1 == c0) gput2(line + xp[XL_COMMENTS], '[', ']');
-    else emit_tg_comments(line + xp[XL_COMMENTS], &mss[wid], b, c0, c1);
-    emit_reaction_map(line + xp[XL_REACTIONS], &mss[wid], b.reacts, b.react_off[r], b.react_off[r + 1], b.aux);
-    const uint32_t nl = in.link_count[r];
-    if (nl) emit_tg_outlinks(line + xp[XL_OUTLINKS], in.arena + in.link_start[r], nl);
+  const int wid = threadIdx.x >> 5, l = lane_id();
+  const bool lane = in.lane_text_max != 0xffffffffu;  // the lane emitter ran: it wrote the simple cases (tg_lane.cuh)
+  const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
+    const uint64_t rl = g * 32 + l;
+    bool need = false;
+    if (rl < b.n && in.status[rl] == TGI_ST_EMITTED) {
+      need = true;
+      if (lane) {
+        const bool list = !(b.recs[rl].flags & TGI_RF_COMMENTS_NIL) && b.comment_off[rl + 1] != b.comment_off[rl];
+        const bool map = b.react_off[rl + 1] != b.react_off[rl] && !(in.xlen[rl * 8 + XL_FLAGS] & XLF_SIMPLE_MAP);
+        need = list || map || in.link_count[rl] > LANE_LINKS_MAX;
+      }
+    }
+    uint32_t todo = __ballot_sync(FULL, need);
+    while (todo) {
+      const uint64_t r = g * 32 + (uint32_t)(__ffs(todo) - 1);
+      todo &= todo - 1;
+      uint8_t* line = in.out + in.line_off[r];
+      const uint32_t* xp = in.xpos + r * 8;
+      const bool comments_nil = (b.recs[r].flags & TGI_RF_COMMENTS_NIL) != 0;
+      const uint32_t c0 = b.comment_off[r], c1 = b.comment_off[r + 1];
+      if (comments_nil) {
+        if (!lane) gcopy_g(line + xp[XL_COMMENTS], (const uint8_t*)kNullLit, 4);
+      } else if (c1 == c0) {
+        if (!lane) gput2(line + xp[XL_COMMENTS], '[', ']');
+      } else {
+        emit_tg_comments(line + xp[XL_COMMENTS], &mss[wid], b, c0, c1);
+      }
+      const uint32_t r0 = b.react_off[r], r1 = b.react_off[r + 1];
+      if (!(lane && (r1 == r0 || (in.xlen[r * 8 + XL_FLAGS] & XLF_SIMPLE_MAP))))
+        emit_reaction_map(line + xp[XL_REACTIONS], &mss[wid], b.reacts, r0, r1, b.aux);
+      const uint32_t nl = in.link_count[r];
+      if (nl && !(lane && nl <= LANE_LINKS_MAX)) emit_tg_outlinks(line + xp[XL_OUTLINKS], in.arena + in.link_start[r], nl);
+      __syncwarp();
+    }
   }
 }
 

@@ -166,6 +166,7 @@ DEVI void ls_skip(LaneStream& s, uint32_t g) {
 constexpr int LANE_ROW_WORDS = 36;  // per lane: 8 blocks of rendered fields + 8 length bytes; 36 = 4 * odd
                                     // keeps the lanes' LDS.128 on distinct banks
 constexpr int LANE_WARPS = 8;
+constexpr uint32_t LANE_LINKS_MAX = 4;   // more outlinks than this are left to the maps kernel
 constexpr uint32_t LANE_TEXT_MAX = 512;  // longer (or escaped) strings are left to the warp-per-record esc kernel
 struct LaneShared {
   uint4 tmpl[kTgLaneTemplateLen / 16];
@@ -187,7 +188,8 @@ DEVI void lane_shared_fill(LaneShared& sh) {
 
 // One lane, one record.  `active` lanes emit; the others only keep the warp's control flow company.
 DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBatchDev& b, const CfgDev& cfg, uint64_t r, bool active,
-                       uint8_t* out, const uint64_t* line_off, const uint32_t* xlen_g, uint32_t* xpos_g, int* err) {
+                       uint8_t* out, const uint64_t* line_off, const uint32_t* xlen_g, uint32_t* xpos_g, const tgi_link* links,
+                       uint32_t nl, int* err) {
   TgWalkArgs a;
   a.b = &b;
   a.cfg = &cfg;
@@ -310,15 +312,108 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
           ls_maybe_drain(s);
         }
       }
-    } else {  // pieces written by the maps kernel: remember where they go
-      const uint32_t xi = kind == K_ESC ? arg : kind == K_COMMENTS ? (uint32_t)XL_COMMENTS
-                                                 : kind == K_REACTIONS ? (uint32_t)XL_REACTIONS : (uint32_t)XL_OUTLINKS;
+    } else if (kind == K_COMMENTS) {  // nil -> null, empty -> []; a real list is left to the maps kernel
+      const bool mine = on && (d.comments_nil || d.c1 == d.c0);
       uint32_t g = 0;
       if (active) {
-        xpos_g[xi] = (uint32_t)(s.pos - line_start);
-        if (on) g = xlen_g[xi];
+        xpos_g[XL_COMMENTS] = (uint32_t)(s.pos - line_start);
+        if (on && !mine) g = xlen_g[XL_COMMENTS];
       }
       ls_skip(s, g);
+      if (mine) ls_append(s, make_uint4(d.comments_nil ? 0x6c6c756eu : 0x5d5bu, 0, 0, 0), d.comments_nil ? 4u : 2u);
+      ls_maybe_drain(s);
+    } else if (kind == K_REACTIONS) {  // map[string]int, keys in byte order (see size_reaction_map for "simple")
+      const uint32_t r0 = b.react_off[r], nr = b.react_off[r + 1] - r0;
+      uint32_t g = 0;
+      bool mine = false;
+      if (active) {
+        xpos_g[XL_REACTIONS] = (uint32_t)(s.pos - line_start);
+        mine = on && (nr == 0 || (xlen_g[XL_FLAGS] & XLF_SIMPLE_MAP));
+        if (on && !mine) g = xlen_g[XL_REACTIONS];
+      }
+      ls_skip(s, g);
+      const uint32_t nn = mine ? nr : 0u;  // <= LANE_MAP_MAX
+      const uint32_t nmax = __reduce_max_sync(FULL, nn);
+      // the rendered fields are not needed any more (every K_FIELD piece precedes the reactions): the
+      // row becomes the entry table (16 bytes each: key, count, key length) plus a render slot
+      uint4* ent = (uint4*)row;
+      for (uint32_t j = 0; j < nmax; j++) {
+        if (j < nn) {
+          const tgi_reaction rc = b.reacts[r0 + j];
+          const uint8_t* kp = b.aux + rc.emoji_off;
+          const uint32_t kl = rc.emoji_len;
+          uint32_t k0 = ld_u32_unaligned(kp), k1 = kl > 4 ? ld_u32_unaligned(kp + 4) : 0u;
+          if (kl < 4) k0 &= (1u << (8u * kl)) - 1u;
+          if (kl > 4 && kl < 8) k1 &= (1u << (8u * (kl - 4u))) - 1u;
+          ent[j] = make_uint4(k0, k1, (uint32_t)rc.count, kl);
+        }
+      }
+      if (mine) ls_append(s, make_uint4(nn ? 0x7bu : 0x7d7bu, 0, 0, 0), nn ? 1u : 2u);  // { or {}
+      ls_maybe_drain(s);
+      uint64_t prev = 0;  // keys are non-empty and contain no NUL: every compare key is > 0
+      for (uint32_t k = 0; k < nmax; k++) {
+        uint4 be = make_uint4(0, 0, 0, 0);
+        if (k < nn) {
+          uint64_t best = ~0ull;
+          for (uint32_t j = 0; j < nmax; j++) {
+            if (j < nn) {
+              const uint4 e = ent[j];
+              const uint64_t ck = ((uint64_t)__byte_perm(e.x, 0, 0x0123) << 32) | __byte_perm(e.y, 0, 0x0123);
+              if (ck > prev && ck < best) {
+                best = ck;
+                be = e;
+              }
+            }
+          }
+          prev = best;
+        }
+#pragma unroll 1
+        for (int step = 0; step < 2; step++) {
+          if (k < nn) {
+            if (step == 0) {  // "key
+              ls_append(s, make_uint4(0x22u | (be.x << 8), (be.x >> 24) | (be.y << 8), be.y >> 24, 0), be.w + 1u);
+            } else {  // ":count, or ":count}
+              uint8_t* sc = rb + 96;
+              *(uint4*)sc = make_uint4(0x3a22u, 0, 0, 0);
+              const uint32_t dl = (uint32_t)render_i64(sc + 2, (int64_t)(int32_t)be.z);
+              sc[2 + dl] = k + 1 == nn ? '}' : ',';
+              ls_append(s, *(const uint4*)sc, 3u + dl);
+            }
+          }
+          ls_maybe_drain(s);
+        }
+      }
+    } else {  // K_OUTLINKS: "name","name" (the names are [a-z0-9_], tg_links.cuh)
+      const bool mine = on && nl <= LANE_LINKS_MAX;
+      uint32_t g = 0;
+      if (active) {
+        xpos_g[XL_OUTLINKS] = (uint32_t)(s.pos - line_start);
+        if (on && !mine) g = xlen_g[XL_OUTLINKS];
+      }
+      ls_skip(s, g);
+      const uint32_t nn = mine ? nl : 0u;
+      const uint32_t nmax = __reduce_max_sync(FULL, nn);
+      for (uint32_t k = 0; k < nmax; k++) {
+        const uint32_t* lw = (const uint32_t*)(links + (k < nn ? k : 0u));
+        const uint32_t len = k < nn ? links[k].len : 0u;
+#pragma unroll 1
+        for (int step = 0; step < 4; step++) {
+          uint4 w = make_uint4(0x22u, 0, 0, 0);
+          uint32_t n = k < nn ? 1u : 0u;
+          if (step == 0 && k) {
+            w.x = 0x222cu;  // ,"
+            n *= 2u;
+          } else if (step == 1) {
+            if (n) w = make_uint4(__ldg(lw), __ldg(lw + 1), __ldg(lw + 2), __ldg(lw + 3));
+            n = min(len, 16u);
+          } else if (step == 2) {
+            if (len > 16u) w = make_uint4(__ldg(lw + 4), __ldg(lw + 5), __ldg(lw + 6), __ldg(lw + 7));
+            n = len > 16u ? len - 16u : 0u;
+          }
+          if (n) ls_append(s, w, n);
+          ls_maybe_drain(s);
+        }
+      }
     }
   }
   ls_flush(s);

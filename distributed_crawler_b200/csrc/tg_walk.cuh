@@ -81,7 +81,8 @@ struct MapScratch {        // maps kernel: per-lane rendered map entries  "key":
 enum { K_LIT, K_FIELD, K_CHAN, K_CFG, K_ESC, K_POSTTYPE, K_COMMENTS, K_REACTIONS, K_OUTLINKS };
 enum { C_NONE, C_USER, C_ALBUM, C_CT_OTHER, C_NOT_CT_OTHER, C_HAS_MEDIA };
 enum { F_MSGNO, F_CHAT, F_VIEW, F_SHARE, F_NCOMM, F_TIME, F_POSTTYPE };
-enum { XL_DESC, XL_MEDIA, XL_HANDLE, XL_ALT, XL_COMMENTS, XL_REACTIONS, XL_OUTLINKS, XL_COUNT };
+enum { XL_DESC, XL_MEDIA, XL_HANDLE, XL_ALT, XL_COMMENTS, XL_REACTIONS, XL_OUTLINKS, XL_COUNT, XL_FLAGS = 7 };
+#define XLF_SIMPLE_MAP 1u  // xlen[XL_FLAGS]: the reactions map is lane-renderable (size_reaction_map)
 constexpr uint32_t K_NOP = 15;
 #include "tg_pieces.inc"
 
@@ -147,10 +148,23 @@ DEVI MapLane warp_map_prepare(const tgi_reaction* reacts, uint32_t r0, uint32_t 
   return m;
 }
 
-__device__ __noinline__ uint32_t size_reaction_map(const tgi_reaction* reacts, uint32_t r0, uint32_t r1, const uint8_t* aux) {
-  if (r1 == r0) return 2;
+// *simple (optional): the map can be rendered by one lane (tg_lane.cuh): at most LANE_MAP_MAX entries,
+// keys of 1..8 bytes that need no escaping, no duplicate keys
+constexpr uint32_t LANE_MAP_MAX = 6;
+__device__ __noinline__ uint32_t size_reaction_map(const tgi_reaction* reacts, uint32_t r0, uint32_t r1, const uint8_t* aux,
+                                                   uint32_t* simple = nullptr) {
+  if (r1 == r0) {
+    if (simple) *simple = 1;
+    return 2;
+  }
   MapLane m = warp_map_prepare(reacts, r0, r1, aux, false);
-  uint32_t mine = m.live ? 3u + thread_esc_len(m.kp, m.kl) + ndigits_i64(m.cnt) : 0u;  // "key":n
+  const uint32_t el = m.live ? thread_esc_len(m.kp, m.kl) : 0u;
+  uint32_t mine = m.live ? 3u + el + ndigits_i64(m.cnt) : 0u;  // "key":n
+  if (simple) {
+    const uint32_t n = r1 - r0;
+    const bool ok = (uint32_t)lane_id() >= n || (m.live && el == m.kl && m.kl >= 1 && m.kl <= 8);
+    *simple = (n <= LANE_MAP_MAX && __all_sync(FULL, ok)) ? 1u : 0u;
+  }
   return 2u + warp_sum(mine) + (m.nlive - 1);
 }
 
@@ -367,7 +381,9 @@ DEVI uint32_t size_tg_record(const TgWalkArgs& a, uint32_t* xl) {
   xl[XL_MEDIA] = d.has_media ? warp_esc_len(a.v.media, a.v.media_len) : 0u;
   xl[XL_HANDLE] = warp_esc_len(a.v.handle, a.v.handle_len);
   xl[XL_COMMENTS] = d.comments_nil ? 4u : size_tg_comments(b, d.c0, d.c1);
-  xl[XL_REACTIONS] = size_reaction_map(b.reacts, b.react_off[a.r], b.react_off[a.r + 1], b.aux);
+  uint32_t simple_map = 0;
+  xl[XL_REACTIONS] = size_reaction_map(b.reacts, b.react_off[a.r], b.react_off[a.r + 1], b.aux, &simple_map);
+  xl[XL_FLAGS] = simple_map ? XLF_SIMPLE_MAP : 0u;
   xl[XL_OUTLINKS] = size_tg_outlinks(a.links, a.n_links);
   tot += a.v.ct == TGI_CT_OTHER ? 0u : (uint32_t)kPostTypeLen[a.v.ct];
   for (int j = 0; j < XL_COUNT; j++) tot += xl[j];

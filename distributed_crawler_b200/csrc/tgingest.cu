@@ -586,8 +586,12 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
         tg_emit_lane_kernel<<<gl, CTA_THREADS, sizeof(LaneShared), st>>>(b, cfg, ei);
       }
       CK(cudaEventRecord(s.ev_f1, st));
-      tg_emit_esc_kernel<<<ge, CTA_THREADS, 0, st>>>(b, ei);
-      tg_emit_maps_kernel<<<ge, CTA_THREADS, 0, st>>>(b, ei);
+      {
+        const uint64_t groups = (n + 31) / 32;
+        unsigned gg = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
+        tg_emit_esc_kernel<<<gg, CTA_THREADS, 0, st>>>(b, ei);
+        tg_emit_maps_kernel<<<gg, CTA_THREADS, 0, st>>>(b, ei);
+      }
       CK(cudaEventRecord(s.ev_e1, st));
       launches += 3;
     }
