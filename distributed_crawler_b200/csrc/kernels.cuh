@@ -157,6 +157,125 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_kernel(TgBatchDev b, C
   if (l == 0 && var_sum) atomicAdd(o.var_total, (unsigned long long)var_sum);
 }
 
+// The same sizes, 32 records per warp: every lane sizes the small pieces of its own record (numbers,
+// handle / media strings, comments, reactions, outlinks); only the message text, the one long string,
+// is measured by the whole warp, record after record; the rare complicated pieces (a comment list, a
+// reactions map that is not "simple") go through the warp-wide routines as well.
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_lane_kernel(TgBatchDev b, CfgDev cfg, ParseOut o) {
+  const int wid = threadIdx.x >> 5, l = lane_id();
+  const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  uint64_t var_sum = 0;
+  for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
+    uint64_t r = g * 32 + l;
+    bool active = r < b.n;
+    if (!active) r = b.n - 1;
+    active = active && o.status[r] == TGI_ST_EMITTED;
+    if (!__any_sync(FULL, active)) continue;
+    TgWalkArgs a;
+    a.b = &b;
+    a.cfg = &cfg;
+    a.r = r;
+    a.v = load_rec_view(b, r);
+    a.links = o.arena + o.link_start[r];
+    a.n_links = active ? o.link_count[r] : 0u;
+    const tgi_tg_rec* rec = a.v.rec;
+    const ChanDerived cd = b.chan_derived[rec->chan_idx];
+    const TgDerived d = tg_derive(a, cd);
+    uint32_t xl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t tot = 0;
+    bool warp_comments = false, warp_map = false;
+    const uint32_t r0 = b.react_off[r], nr = b.react_off[r + 1] - r0;
+    if (active && !(cfg.flags & CFGDEV_CLOCK_INVALID)) {
+      uint32_t L[8] = {ndigits_i64(rec->id / 1048576), ndigits_i64(rec->chat_id), ndigits_i64(rec->view_count),
+                       ndigits_i64(rec->share_count), ndigits_i64(d.ncomments), cfg.tz == 0 ? 22u : 27u, 0, 0};
+      uint32_t chan[4] = {cd.user_len, cd.name_len, cd.title_len, cd.cdata_len};
+      uint32_t cf[4] = {cfg.label_len, cfg.created_tg_len, cfg.created_yt_len, cfg.capture_len};
+      tot = tg_size_fixed(L, chan, cf, d.has_user, d.album);
+      tot += a.v.ct == TGI_CT_OTHER ? 0u : (uint32_t)kPostTypeLen[a.v.ct];
+      if (a.v.ct == TGI_CT_OTHER) xl[XL_ALT] = thread_esc_len(a.v.alt, a.v.alt_len);
+      if (d.has_media) xl[XL_MEDIA] = thread_esc_len(a.v.media, a.v.media_len);
+      xl[XL_HANDLE] = thread_esc_len(a.v.handle, a.v.handle_len);
+      if (d.comments_nil) xl[XL_COMMENTS] = 4;
+      else if (d.c1 == d.c0) xl[XL_COMMENTS] = 2;
+      else warp_comments = true;
+      if (nr == 0) {
+        xl[XL_REACTIONS] = 2;
+        xl[XL_FLAGS] = XLF_SIMPLE_MAP;
+      } else if (nr <= LANE_MAP_MAX) {  // size_reaction_map, one lane: "key":n , ... ; simple = short clean distinct keys
+        uint32_t sz = 2u + (nr - 1u);
+        bool simple = true;
+        for (uint32_t j = 0; j < nr; j++) {
+          const tgi_reaction rc = b.reacts[r0 + j];
+          const uint8_t* kp = b.aux + rc.emoji_off;
+          const uint32_t el = thread_esc_len(kp, rc.emoji_len);
+          simple = simple && el == rc.emoji_len && rc.emoji_len >= 1 && rc.emoji_len <= 8;
+          sz += 3u + el + ndigits_i64(rc.count);
+          for (uint32_t i = 0; i < j; i++) {
+            const tgi_reaction ri = b.reacts[r0 + i];
+            if (key_cmp(b.aux + ri.emoji_off, ri.emoji_len, kp, rc.emoji_len) == 0) simple = false;
+          }
+        }
+        if (simple) {
+          xl[XL_REACTIONS] = sz;
+          xl[XL_FLAGS] = XLF_SIMPLE_MAP;
+        } else {
+          warp_map = true;  // duplicates drop out of the map: let the warp routine size it
+        }
+      } else {
+        warp_map = true;
+      }
+      if (a.n_links) {
+        uint32_t s = a.n_links - 1u;
+        for (uint32_t k = 0; k < a.n_links; k++) s += a.links[k].len + 2u;
+        xl[XL_OUTLINKS] = s;
+      }
+    }
+    // the message text (or the other description sources), one record at a time, all lanes
+    const bool sized = active && !(cfg.flags & CFGDEV_CLOCK_INVALID);
+    uint32_t todo = __ballot_sync(FULL, sized && d.desc_len != 0);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint8_t* p = (const uint8_t*)__shfl_sync(FULL, (unsigned long long)(uintptr_t)d.desc, src);
+      const uint32_t n = __shfl_sync(FULL, d.desc_len, src);
+      const uint32_t e = warp_esc_len(p, n);
+      if (l == src) xl[XL_DESC] = e;
+    }
+    todo = __ballot_sync(FULL, warp_comments);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t e = size_tg_comments(b, __shfl_sync(FULL, d.c0, src), __shfl_sync(FULL, d.c1, src));
+      if (l == src) xl[XL_COMMENTS] = e;
+    }
+    todo = __ballot_sync(FULL, warp_map);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t q0 = __shfl_sync(FULL, r0, src), qn = __shfl_sync(FULL, nr, src);
+      uint32_t simple = 0;
+      const uint32_t e = size_reaction_map(b.reacts, q0, q0 + qn, b.aux, &simple);
+      if (l == src) {
+        xl[XL_REACTIONS] = e;
+        xl[XL_FLAGS] = simple ? XLF_SIMPLE_MAP : 0u;
+      }
+    }
+    if (active) {
+      uint32_t var = 0;
+#pragma unroll
+      for (int j = 0; j < XL_COUNT; j++) var += xl[j];
+      const uint32_t llen = sized ? tot + var : 0u;
+      *(uint4*)(o.xlen + r * 8) = make_uint4(xl[0], xl[1], xl[2], xl[3]);
+      *(uint4*)(o.xlen + r * 8 + 4) = make_uint4(xl[4], xl[5], xl[6], xl[7]);
+      if (llen == 0) o.status[r] = TGI_ST_NOLINE;
+      o.linelen[r] = llen;
+      if (llen) var_sum += var;
+    }
+  }
+  for (int dd = 16; dd; dd >>= 1) var_sum += __shfl_down_sync(FULL, var_sum, dd);
+  if (l == 0 && var_sum) atomicAdd(o.var_total, (unsigned long long)var_sum);
+}
+
 // ---- emit: three small kernels, one warp per record, direct stores into the output blob ----------
 // Small kernels on purpose: the B200 instruction caches are tiny (L0 ~6 KB per sub-partition, L1.5
 // 32 KB per SM).  A single fused emit kernel (70-100 KB of SASS) spent most of its cycles in

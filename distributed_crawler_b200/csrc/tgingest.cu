@@ -517,7 +517,14 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       tg_parse_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
       launches++;
       if (want_json) {
-        tg_size_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, po);
+        static const bool warp_size = getenv("TGI_SIZE_WARP") != nullptr;  // A/B switch: one warp per record
+        if (warp_size) {
+          tg_size_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, po);
+        } else {
+          const uint64_t groups = (n + 31) / 32;
+          unsigned gs = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
+          tg_size_lane_kernel<<<gs, CTA_THREADS, 0, st>>>(b, cfg, po);
+        }
         launches++;
       }
       CK(cudaEventRecord(s.ev_p1, st));
