@@ -250,15 +250,20 @@ DEVI void strip_lane_totals(const Strip& st, const uint8_t* s, int64_t base, int
   u16 = st.nvalid - __popc(st.cont) + __popc(st.l4);
 }
 
-// JSON-escaped length of s[0..n) (without the quotes)
-__device__ __noinline__ uint32_t warp_esc_len(const uint8_t* s, int64_t n) {
+// JSON-escaped length of s[0..n) (without the quotes).  *needs_exact (optional): some strip took the
+// exact per-byte path, i.e. the string holds invalid UTF-8 or U+2028/9 candidates; if it stays false
+// every non-ASCII byte is copied verbatim by the escaper (esc_ascii_to_global may be used).
+__device__ __noinline__ uint32_t warp_esc_len(const uint8_t* s, int64_t n, bool* needs_exact = nullptr) {
   uint32_t tot = 0, carry = 0;
+  bool ex = false;
   for (int64_t base = 0; base < n; base += 128) {
     Strip st = warp_load_strip(s, base, n, carry);
     uint32_t e, u;
     strip_lane_totals(st, s, base, n, e, u);
     tot += e;
+    ex = ex || st.exact;
   }
+  if (needs_exact) *needs_exact = ex;
   return warp_sum(tot);
 }
 
@@ -409,6 +414,16 @@ DEVI uint4 lds128(uint32_t a) {
 DEVI uint32_t thread_esc_len(const uint8_t* s, uint32_t n) {
   uint32_t o = 0;
   for (uint32_t i = 0; i < n;) {
+    if (i + 4 <= n) {  // four plain ASCII bytes at once (ids, handles and file names are mostly that)
+      const uint32_t w = ld_u32_unaligned(s + i);
+      const uint32_t odd = (w & 0x80808080u) | ((w - 0x20202020u) & ~w & 0x80808080u) | swar_has_byte(w, 0x22) |
+                           swar_has_byte(w, 0x5C) | swar_has_byte(w, 0x3C) | swar_has_byte(w, 0x3E) | swar_has_byte(w, 0x26);
+      if (!odd) {
+        o += 4;
+        i += 4;
+        continue;
+      }
+    }
     uint32_t b = ldb(s + i);
     if (b < 0x80) {
       o += ascii_esc_len(b);
@@ -514,6 +529,70 @@ __device__ __noinline__ uint32_t esc_to_global(uint8_t* dstp, const uint8_t* s, 
       }
     }
     out += tot;
+  }
+  return out;
+}
+
+// The same for a string whose non-ASCII bytes all pass through unchanged (warp_esc_len reported
+// needs_exact == false): no UTF-8 bookkeeping, so a lane can own 16 bytes and a strip is 512 bytes.
+__device__ __noinline__ uint32_t esc_ascii_to_global(uint8_t* dstp, const uint8_t* s, uint32_t n) {
+  DstG dst{dstp};
+  const uint32_t l = lane_id();
+  uint32_t out = 0;
+  for (uint32_t base = 0; base < n; base += 512) {
+    const uint32_t p0 = base + 16u * l;
+    const uint32_t nv = p0 >= n ? 0u : min(16u, n - p0);
+    // the lane's four words and their "holds a byte that needs escaping" flags; the two passes below walk
+    // them by rotating the vectors, so that the loop bodies exist once (instruction-cache footprint)
+    uint4 W = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u), O;
+    if (nv) W.x = ld_u32_unaligned(s + p0);
+    if (nv > 4) W.y = ld_u32_unaligned(s + p0 + 4);
+    if (nv > 8) W.z = ld_u32_unaligned(s + p0 + 8);
+    if (nv > 12) W.w = ld_u32_unaligned(s + p0 + 12);
+    uint32_t el = 0;
+#pragma unroll 1
+    for (uint32_t j = 0; j < 4; j++) {
+      const uint32_t nj = nv > 4u * j ? min(4u, nv - 4u * j) : 0u;
+      uint32_t x = W.x;
+      if (nj < 4) x = (x & ((1u << (8u * nj)) - 1u)) | (0x20202020u << (8u * nj));  // fill with spaces
+      const uint32_t odd = ((x - 0x20202020u) & ~x & 0x80808080u) | swar_has_byte(x, 0x22) | swar_has_byte(x, 0x5C) |
+                           swar_has_byte(x, 0x3C) | swar_has_byte(x, 0x3E) | swar_has_byte(x, 0x26);
+      if (!odd) {
+        el += nj;
+      } else {
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+          const uint32_t b = (x >> (8u * k)) & 0xFFu;
+          if (k < nj) el += b < 0x80 ? ascii_esc_len(b) : 1u;
+        }
+      }
+      W = make_uint4(W.y, W.z, W.w, x);
+      O = make_uint4(O.y, O.z, O.w, odd);
+    }
+    const uint32_t incl = warp_incl_scan(el);
+    uint32_t d = out + incl - el;
+#pragma unroll 1
+    for (uint32_t j = 0; j < 4; j++) {
+      const uint32_t nj = nv > 4u * j ? min(4u, nv - 4u * j) : 0u;
+      const uint32_t x = W.x;
+      if (!O.x) {
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++)
+          if (k < nj) dst.st(d + k, (x >> (8u * k)) & 0xFFu);
+        d += nj;
+      } else {
+#pragma unroll 1
+        for (uint32_t k = 0; k < nj; k++) {
+          const uint32_t b = (x >> (8u * k)) & 0xFFu;
+          const uint32_t len = b < 0x80 ? ascii_esc_len(b) : 1u;
+          put_escaped(dst, d, b, len);
+          d += len;
+        }
+      }
+      W = make_uint4(W.y, W.z, W.w, x);
+      O = make_uint4(O.y, O.z, O.w, O.x);
+    }
+    out += __shfl_sync(FULL, incl, 31);
   }
   return out;
 }

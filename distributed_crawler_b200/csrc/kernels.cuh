@@ -238,8 +238,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_lane_kernel(TgBatchDev
       todo &= todo - 1;
       const uint8_t* p = (const uint8_t*)__shfl_sync(FULL, (unsigned long long)(uintptr_t)d.desc, src);
       const uint32_t n = __shfl_sync(FULL, d.desc_len, src);
-      const uint32_t e = warp_esc_len(p, n);
-      if (l == src) xl[XL_DESC] = e;
+      bool ex = false;
+      const uint32_t e = warp_esc_len(p, n, &ex);
+      if (l == src) {
+        xl[XL_DESC] = e;
+        if (ex) xl[XL_FLAGS] |= XLF_DESC_EXACT;
+      }
     }
     todo = __ballot_sync(FULL, warp_comments);
     while (todo) {
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_lane_kernel(TgBatchDev
       const uint32_t e = size_reaction_map(b.reacts, q0, q0 + qn, b.aux, &simple);
       if (l == src) {
         xl[XL_REACTIONS] = e;
-        xl[XL_FLAGS] = simple ? XLF_SIMPLE_MAP : 0u;
+        xl[XL_FLAGS] = (xl[XL_FLAGS] & ~XLF_SIMPLE_MAP) | (simple ? XLF_SIMPLE_MAP : 0u);
       }
     }
     if (active) {

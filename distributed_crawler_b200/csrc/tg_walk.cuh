@@ -83,6 +83,7 @@ enum { C_NONE, C_USER, C_ALBUM, C_CT_OTHER, C_NOT_CT_OTHER, C_HAS_MEDIA };
 enum { F_MSGNO, F_CHAT, F_VIEW, F_SHARE, F_NCOMM, F_TIME, F_POSTTYPE };
 enum { XL_DESC, XL_MEDIA, XL_HANDLE, XL_ALT, XL_COMMENTS, XL_REACTIONS, XL_OUTLINKS, XL_COUNT, XL_FLAGS = 7 };
 #define XLF_SIMPLE_MAP 1u  // xlen[XL_FLAGS]: the reactions map is lane-renderable (size_reaction_map)
+#define XLF_DESC_EXACT 2u  // the description holds invalid UTF-8 or U+2028/9: only the exact escaper may write it
 constexpr uint32_t K_NOP = 15;
 #include "tg_pieces.inc"
 
@@ -376,14 +377,15 @@ DEVI uint32_t size_tg_record(const TgWalkArgs& a, uint32_t* xl) {
   uint32_t chan[4] = {cd.user_len, cd.name_len, cd.title_len, cd.cdata_len};
   uint32_t cf[4] = {cfg.label_len, cfg.created_tg_len, cfg.created_yt_len, cfg.capture_len};
   uint32_t tot = tg_size_fixed(L, chan, cf, d.has_user, d.album);
-  xl[XL_DESC] = warp_esc_len(d.desc, d.desc_len);
+  bool desc_exact = false;
+  xl[XL_DESC] = warp_esc_len(d.desc, d.desc_len, &desc_exact);
   xl[XL_ALT] = a.v.ct == TGI_CT_OTHER ? warp_esc_len(a.v.alt, a.v.alt_len) : 0u;
   xl[XL_MEDIA] = d.has_media ? warp_esc_len(a.v.media, a.v.media_len) : 0u;
   xl[XL_HANDLE] = warp_esc_len(a.v.handle, a.v.handle_len);
   xl[XL_COMMENTS] = d.comments_nil ? 4u : size_tg_comments(b, d.c0, d.c1);
   uint32_t simple_map = 0;
   xl[XL_REACTIONS] = size_reaction_map(b.reacts, b.react_off[a.r], b.react_off[a.r + 1], b.aux, &simple_map);
-  xl[XL_FLAGS] = simple_map ? XLF_SIMPLE_MAP : 0u;
+  xl[XL_FLAGS] = (simple_map ? XLF_SIMPLE_MAP : 0u) | (desc_exact ? XLF_DESC_EXACT : 0u);
   xl[XL_OUTLINKS] = size_tg_outlinks(a.links, a.n_links);
   tot += a.v.ct == TGI_CT_OTHER ? 0u : (uint32_t)kPostTypeLen[a.v.ct];
   for (int j = 0; j < XL_COUNT; j++) tot += xl[j];
@@ -573,7 +575,8 @@ DEVI void emit_tg_escapes(uint8_t* line, const TgWalkArgs& a, const uint32_t* xl
         continue;
       }
     }
-    esc_to_global(line + o, p, n);
+    if (j == 0 && !(xlen_g[XL_FLAGS] & XLF_DESC_EXACT)) esc_ascii_to_global(line + o, p, n);
+    else esc_to_global(line + o, p, n);
   }
 }
 
