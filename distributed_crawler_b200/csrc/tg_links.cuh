@@ -91,26 +91,47 @@ DEVI uint32_t warp_word_run(const uint8_t* p, const uint8_t* end) {
   return m ? (uint32_t)(__ffs(m) - 1) : 32u;
 }
 
-// per-lane 4-bit mask: bit k set if "t.me/" starts at byte base+4*lane+k (bytes past n are 0)
-DEVI uint32_t strip_tme_candidates(const uint8_t* s, int64_t base, int64_t n) {
-  int64_t p0 = base + 4 * lane_id();
+// exact per-byte equality: bit 7 of every byte of w that equals c
+DEVI uint32_t swar_eq(uint32_t w, uint32_t c) {
+  const uint32_t x = w ^ (c * 0x01010101u);
+  return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
+DEVI uint32_t swar_movemask(uint32_t m) { return (((m >> 7) & 0x01010101u) * 0x01020408u) >> 24; }  // bit 7s -> 4 bits
+
+// A strip for the link scan = 512 bytes, 16 per lane (no UTF-8 bookkeeping is needed to find "t.me/").
+// Returns the lane's 16-bit mask: bit k set if s[p0+k] is the '/' of a "t.me/" (p0 = base + 16*lane).
+// '/' is rare in message text, so almost every strip ends after four SWAR compares per lane.
+DEVI uint32_t strip16_tme(const uint8_t* s, int64_t base, int64_t n) {
+  const int64_t p0 = base + 16 * lane_id();
   if (p0 >= n) return 0;
-  uint64_t lo = ld_u32_unaligned(s + p0);
-  uint64_t hi = ld_u32_unaligned(s + p0 + 4);  // blob padding makes the over-read safe
-  uint64_t v = lo | (hi << 32);
-  int64_t rem = n - p0;  // mask bytes >= n
-  if (rem < 8) v &= (rem <= 0) ? 0ull : ((1ull << (8 * rem)) - 1ull);
-  uint32_t m = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++)
-    if (((v >> (8 * k)) & 0xFFFFFFFFFFull) == 0x2F656D2E74ull) m |= 1u << k;
-  return m;
+  const uint8_t* q = s + p0;  // every lane has the same misalignment: two aligned 16-byte loads + one funnel
+  const uint32_t sa = (uint32_t)(uintptr_t)q & 15u, sh = (sa & 3u) * 8u, qw = sa >> 2;
+  const uint4 a = __ldg((const uint4*)(q - sa)), c = __ldg((const uint4*)(q - sa) + 1);  // blob padding covers the over-read
+  uint32_t v0, v1, v2, v3, v4;
+  if (qw == 0) { v0 = a.x; v1 = a.y; v2 = a.z; v3 = a.w; v4 = c.x; }
+  else if (qw == 1) { v0 = a.y; v1 = a.z; v2 = a.w; v3 = c.x; v4 = c.y; }
+  else if (qw == 2) { v0 = a.z; v1 = a.w; v2 = c.x; v3 = c.y; v4 = c.z; }
+  else { v0 = a.w; v1 = c.x; v2 = c.y; v3 = c.z; v4 = c.w; }
+  const uint32_t w0 = __funnelshift_r(v0, v1, sh), w1 = __funnelshift_r(v1, v2, sh), w2 = __funnelshift_r(v2, v3, sh),
+                 w3 = __funnelshift_r(v3, v4, sh);
+  const uint32_t s0 = swar_eq(w0, '/'), s1 = swar_eq(w1, '/'), s2 = swar_eq(w2, '/'), s3 = swar_eq(w3, '/');
+  if (!(s0 | s1 | s2 | s3)) return 0;
+  uint32_t m = swar_movemask(s0) | (swar_movemask(s1) << 4) | (swar_movemask(s2) << 8) | (swar_movemask(s3) << 12);
+  const int64_t rem = n - p0;
+  if (rem < 16) m &= (1u << rem) - 1u;
+  uint32_t out = 0;
+  while (m) {
+    const int k = __ffs(m) - 1;
+    m &= m - 1;
+    if (p0 + k >= 4 && ld_u32_unaligned(q + k - 4) == 0x656D2E74u) out |= 1u << k;  // "t.me"
+  }
+  return out;
 }
 
 // number of "t.me/" occurrences in s[0..n): upper bound on plaintext matches
 DEVI uint32_t warp_count_tme(const uint8_t* s, int64_t n) {
   uint32_t cnt = 0;
-  for (int64_t base = 0; base < n; base += 128) cnt += __popc(strip_tme_candidates(s, base, n));
+  for (int64_t base = 0; base < n; base += 512) cnt += __popc(strip16_tme(s, base, n));
   return warp_sum(cnt);
 }
 
@@ -118,8 +139,8 @@ DEVI uint32_t warp_count_tme(const uint8_t* s, int64_t n) {
 // are dropped WITHOUT looking further).  all == true: FindAllStringSubmatch.
 __device__ __noinline__ void warp_scan_channel_links(LinkSink& ls, const uint8_t* s, int64_t n, uint32_t src, bool all) {
   int64_t resume = 0;  // end of the previous match (non-overlapping search)
-  for (int64_t base = 0; base < n; base += 128) {
-    uint32_t m = strip_tme_candidates(s, base, n);
+  for (int64_t base = 0; base < n; base += 512) {
+    uint32_t m = strip16_tme(s, base, n);
     uint32_t lanes = __ballot_sync(FULL, m != 0);
     while (lanes) {
       int src_lane = __ffs(lanes) - 1;
@@ -128,7 +149,7 @@ __device__ __noinline__ void warp_scan_channel_links(LinkSink& ls, const uint8_t
       while (mm) {
         int k = __ffs(mm) - 1;
         mm &= mm - 1;
-        int64_t p = base + 4 * src_lane + k;
+        int64_t p = base + 16 * src_lane + k - 4;  // start of "t.me/"
         if (p < resume) continue;  // inside the previous match
         const uint8_t* q = s + p + 5;
         if (p + 5 >= n || !is_letter(ldb(q))) continue;
