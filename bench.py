@@ -301,22 +301,22 @@ def main():
         # whole step: every input byte read once, every output byte written once
         alg_bytes = in_bytes + jsonl_len + 8 * (n + 1)
         step_ms = dt_max / args.steps * 1e3
-        # dominant kernel tg_emit_fixed_kernel: reads per record the 64-byte header, 2 line offsets worth
-        # 8 bytes, 32 bytes of piece lengths, the 24-byte channel row + its pre-rendered strings
-        # (once per 100 records), writes the fixed part of the line and 32 bytes of piece offsets
-        fixed_out = jsonl_len - r.var_bytes
-        chan_bytes = int(batch.chans.nbytes + batch.chan_strs.nbytes * 2.2)
-        fixed_alg = n * (64 + 8 + 32 + 32) + chan_bytes + fixed_out
+        # dominant kernel tg_emit_lane_kernel (one lane per record, tg_lane.cuh): per record it reads the
+        # 64-byte header, 8 bytes of line offset and 32 bytes of piece lengths, writes 32 bytes of piece
+        # offsets, writes `lane_bytes_out` JSONL bytes (counted by the kernel itself) of which
+        # `lane_bytes_in` are copies of HBM-resident sources (message strings, pre-rendered channel blob)
+        lane_alg = n * (64 + 8 + 32 + 32) + r.lane_bytes_out + r.lane_bytes_in
         fm = sum(fixed_ms) / len(fixed_ms)
         em = sum(emit_ms) / len(emit_ms)
-        achieved = fixed_alg / (fm * 1e-3) / 1e9
+        achieved = lane_alg / (fm * 1e-3) / 1e9
         traffic = load_traffic()
-        roofline = {"bound": "hbm", "kernel": "tg_emit_fixed_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": "tg_emit_lane_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "peak_source": peak_src,
-                    "traffic": (traffic or {}).get("tg_emit_fixed_kernel_bytes_per_launch"),
-                    "algorithmic_bytes_per_launch": fixed_alg, "kernel_ms": fm,
+                    "traffic": (traffic or {}).get("tg_emit_lane_kernel_bytes_per_launch"),
+                    "algorithmic_bytes_per_launch": lane_alg, "kernel_ms": fm,
                     "kernel_share_of_step": fm / step_ms,
-                    "emit_pass": {"kernels": "tg_emit_fixed_kernel + tg_emit_esc_kernel + tg_emit_maps_kernel", "ms": em,
+                    "lane_bytes_out": r.lane_bytes_out, "lane_bytes_in": r.lane_bytes_in,
+                    "emit_pass": {"kernels": "tg_emit_lane_kernel + tg_emit_esc_kernel + tg_emit_maps_kernel", "ms": em,
                                   "achieved": (in_bytes + jsonl_len + 8 * (n + 1)) / (em * 1e-3) / 1e9},
                     "step": {"algorithmic_bytes": alg_bytes, "achieved": alg_bytes / (step_ms * 1e-3) / 1e9,
                              "frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak,

@@ -110,7 +110,8 @@ class ResultC(C.Structure):
         ("line_off", C.c_void_p), ("link_off", C.c_void_p), ("links", C.c_void_p),
         ("n_links", C.c_uint64), ("n_new", C.c_uint64), ("frontier_size", C.c_uint64),
         ("kernel_ms", C.c_float), ("gpu_launches", C.c_uint32), ("parse_ms", C.c_float),
-        ("emit_ms", C.c_float), ("slot", C.c_int32), ("emit_fixed_ms", C.c_float), ("var_bytes", C.c_uint64)]
+        ("emit_ms", C.c_float), ("slot", C.c_int32), ("emit_fixed_ms", C.c_float), ("var_bytes", C.c_uint64),
+        ("lane_bytes_out", C.c_uint64), ("lane_bytes_in", C.c_uint64)]
 
 
 class StatsC(C.Structure):

@@ -295,6 +295,7 @@ struct EmitIn {
   uint8_t* out;
   int* err;
   uint32_t lane_text_max;  // see emit_tg_escapes
+  unsigned long long* counters;  // [0] bytes written by the lane emitter, [1] bytes it copied from HBM sources
 };
 
 __global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_fixed_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_lane_kernel(TgBatchDev
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   LaneStream s;
   ls_init(s, smem_addr(sh.stage[wid][l]));
+  uint64_t bytes_out = 0, bytes_in = 0;
   for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
     uint64_t r = g * 32 + l;
     bool active = r < b.n;
@@ -340,7 +342,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_lane_kernel(TgBatchDev
     active = active && in.status[r] == TGI_ST_EMITTED;
     if (!__any_sync(FULL, active)) continue;
     emit_tg_lane(sh, sh.rows[wid][l], s, b, cfg, r, active, in.out, in.line_off, in.xlen + r * 8, in.xpos + r * 8,
-                 in.arena + in.link_start[r], active ? in.link_count[r] : 0u, in.err);
+                 in.arena + in.link_start[r], active ? in.link_count[r] : 0u, in.err, bytes_out, bytes_in);
+  }
+  for (int dd = 16; dd; dd >>= 1) {
+    bytes_out += __shfl_down_sync(FULL, bytes_out, dd);
+    bytes_in += __shfl_down_sync(FULL, bytes_in, dd);
+  }
+  if (l == 0) {
+    atomicAdd(in.counters, (unsigned long long)bytes_out);
+    atomicAdd(in.counters + 1, (unsigned long long)bytes_in);
   }
 }
 

@@ -189,7 +189,8 @@ DEVI void lane_shared_fill(LaneShared& sh) {
 // One lane, one record.  `active` lanes emit; the others only keep the warp's control flow company.
 DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBatchDev& b, const CfgDev& cfg, uint64_t r, bool active,
                        uint8_t* out, const uint64_t* line_off, const uint32_t* xlen_g, uint32_t* xpos_g, const tgi_link* links,
-                       uint32_t nl, int* err) {
+                       uint32_t nl, int* err, uint64_t& bytes_out, uint64_t& bytes_in) {
+  uint32_t gaps = 0, copied = 0;  // statistics: bytes left to the other emit kernels / bytes copied from HBM sources
   TgWalkArgs a;
   a.b = &b;
   a.cfg = &cfg;
@@ -273,6 +274,7 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
         n = arg == 0 ? cfg.label_len : arg == 1 ? cfg.created_tg_len : arg == 2 ? cfg.created_yt_len : cfg.capture_len;
       }
       if (!on) n = 0;
+      copied += n;
       const uint32_t nmax = __reduce_max_sync(FULL, n);
       for (uint32_t i = 0; i < nmax; i += 16, src++)
       {
@@ -289,6 +291,8 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
       }
       const bool mine = on && xl == n && n <= LANE_TEXT_MAX;  // same rule in emit_tg_escapes
       ls_skip(s, mine ? 0u : xl);                             // else the esc kernel writes it
+      gaps += mine ? 0u : xl;
+      copied += mine ? n : 0u;
       uint32_t rem = mine ? n : 0u;
       if (__any_sync(FULL, rem != 0)) {
         const uint32_t s0 = (uint32_t)(uintptr_t)p & 15u;
@@ -320,6 +324,7 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
         if (on && !mine) g = xlen_g[XL_COMMENTS];
       }
       ls_skip(s, g);
+      gaps += g;
       if (mine) ls_append(s, make_uint4(d.comments_nil ? 0x6c6c756eu : 0x5d5bu, 0, 0, 0), d.comments_nil ? 4u : 2u);
       ls_maybe_drain(s);
     } else if (kind == K_REACTIONS) {  // map[string]int, keys in byte order (see size_reaction_map for "simple")
@@ -332,6 +337,7 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
         if (on && !mine) g = xlen_g[XL_REACTIONS];
       }
       ls_skip(s, g);
+      gaps += g;
       const uint32_t nn = mine ? nr : 0u;  // <= LANE_MAP_MAX
       const uint32_t nmax = __reduce_max_sync(FULL, nn);
       // the rendered fields are not needed any more (every K_FIELD piece precedes the reactions): the
@@ -391,6 +397,7 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
         if (on && !mine) g = xlen_g[XL_OUTLINKS];
       }
       ls_skip(s, g);
+      gaps += g;
       const uint32_t nn = mine ? nl : 0u;
       const uint32_t nmax = __reduce_max_sync(FULL, nn);
       for (uint32_t k = 0; k < nmax; k++) {
@@ -418,7 +425,11 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
   }
   ls_flush(s);
   ls_drain_warp(s);
-  if (active && (uint32_t)(s.pos - line_start) != total) atomicOr(err, 16);  // sizing and emission disagree: never expected
+  if (active) {
+    if ((uint32_t)(s.pos - line_start) != total) atomicOr(err, 16);  // sizing and emission disagree: never expected
+    bytes_out += total - gaps;
+    bytes_in += copied;
+  }
 }
 
 }  // namespace tgi

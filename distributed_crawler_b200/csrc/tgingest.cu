@@ -332,7 +332,7 @@ int upload_tg(tgi_ctx* c, Slot& s, const tgi_tg_batch* in) {
 
 // scalars block (device + pinned mirror): [0] chan total, [1] line total, [2] cursor(u32)+err(int),
 // [3] n_new, [4] frontier size, [5] link total
-enum { SC_CHAN_TOTAL = 0, SC_LINE_TOTAL = 1, SC_CURSOR = 2, SC_NEW = 3, SC_FSIZE = 4, SC_LINK_TOTAL = 5, SC_LONG = 6, SC_URL_CURSOR = 7, SC_COUNT = 8 };
+enum { SC_CHAN_TOTAL = 0, SC_LINE_TOTAL = 1, SC_CURSOR = 2, SC_NEW = 3, SC_FSIZE = 4, SC_LINK_TOTAL = 5, SC_LONG = 6, SC_URL_CURSOR = 7, SC_LANE_OUT = 8, SC_LANE_IN = 9, SC_COUNT = 10 };
 
 // shared tail of the Telegram and YouTube pipelines: frontier phases, link compaction, D2H, result
 int finish_batch(tgi_ctx* c, Slot& s, uint64_t n, uint32_t flags, uint64_t line_total, uint32_t arena_used,
@@ -427,6 +427,8 @@ int finish_batch(tgi_ctx* c, Slot& s, uint64_t n, uint32_t flags, uint64_t line_
     cudaEventElapsedTime(&out->emit_ms, s.ev_e0, s.ev_e1);
     cudaEventElapsedTime(&out->emit_fixed_ms, s.ev_e0, s.ev_f1);
     out->var_bytes = var_bytes;
+    out->lane_bytes_out = hsc[SC_LANE_OUT];
+    out->lane_bytes_in = hsc[SC_LANE_IN];
   }
   out->jsonl_len = want_json ? line_total : 0;
   out->n_links = n_links_total;
@@ -576,6 +578,7 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       ei.arena = s.d_arena.as<tgi_link>();
       ei.out = s.d_jsonl.as<uint8_t>();
       ei.err = (int*)(dsc + SC_CURSOR) + 1;
+      ei.counters = (unsigned long long*)(dsc + SC_LANE_OUT);
       uint64_t want = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
       unsigned ge = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms * 8);
       CK(cudaEventRecord(s.ev_e0, st));

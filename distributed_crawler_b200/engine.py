@@ -98,6 +98,8 @@ class Result:
         self.emit_ms = float(r.emit_ms)
         self.emit_fixed_ms = float(r.emit_fixed_ms)
         self.var_bytes = int(r.var_bytes)
+        self.lane_bytes_out = int(r.lane_bytes_out)
+        self.lane_bytes_in = int(r.lane_bytes_in)
         self.gpu_launches = int(r.gpu_launches)
         self.slot = int(r.slot)
         if copy:

@@ -289,8 +289,10 @@ typedef struct tgi_result {
   float parse_ms;           /* device time of the parse pass (link extraction + size kernels)     */
   float emit_ms;            /* device time of the JSONL emit pass (three kernels)                 */
   int32_t slot;             /* staging slot that owns the buffers: pass to tgi_result_release     */
-  float emit_fixed_ms;      /* device time of tg_emit_fixed_kernel, the dominant kernel           */
-  uint64_t var_bytes;       /* JSONL bytes written by the escape + map kernels (rest: fixed part) */
+  float emit_fixed_ms;      /* device time of tg_emit_lane_kernel, the dominant kernel            */
+  uint64_t var_bytes;       /* JSONL bytes of the variable pieces (strings, comments, maps, outlinks) */
+  uint64_t lane_bytes_out;  /* JSONL bytes written by tg_emit_lane_kernel (the rest: esc + maps kernels) */
+  uint64_t lane_bytes_in;   /* of those, bytes it copied from HBM-resident sources (strings, channel blob) */
 } tgi_result;
 
 typedef struct tgi_stats {
