@@ -236,191 +236,180 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
   const uint32_t total = (uint32_t)(line_off[r + 1] - line_off[r]);
   ls_begin(s, active ? line_start : 0ull);
 
-#pragma unroll 1
-  for (int p = 0; p < kTgLaneNPieces; p++) {
+  // One state machine over (piece, sub-step) with a single copy loop behind it: every piece -- literal,
+  // rendered field, channel / context string, message string, map entry, outlink -- is described as
+  // "skip g bytes, then copy n bytes from src" (src: any address space, any alignment), so the shift
+  // network of ls_append exists once in the kernel (instruction-cache footprint, see profiles/README.md).
+  // Map entries and outlinks are composed in the lane's field row first: every rendered field has been
+  // used by the time the comments / reactions / outlinks pieces come (they follow all K_FIELD pieces).
+  uint32_t p = 0, t = 0;
+  uint32_t multi_n = 0, multi_max = 0;  // entries of the current multi-step piece: this lane's / the warp's maximum
+  uint64_t prev = 0;                    // reactions: compare key of the entry emitted last
+  while (p < (uint32_t)kTgLaneNPieces) {
     const uint32_t en = sh.pieces[p];
     const uint32_t kind = en & 15u, arg = (en >> 4) & 15u;
     const bool on = ((condmask >> ((en >> 8) & 15u)) & 1u) != 0;
-    if (kind == K_LIT || kind == K_FIELD || kind == K_POSTTYPE) {  // shared-memory sources
-      const uint4* src;
-      uint32_t n;
-      if (kind == K_LIT) {
-        src = sh.tmpl + ((en >> 12) & 0x7FFu);
-        n = en >> 23;
-      } else if (kind == K_FIELD) {
-        src = (const uint4*)(rb + (arg ? 16u + (arg >= 2 ? 16u * arg : 0u) : 0u));
-        n = rb[128 + arg];
-      } else {
-        src = sh.ptype + 2u * ct;
-        n = kPostTypeLen[ct];
-      }
-      if (!on) n = 0;
-      const uint32_t nmax = __reduce_max_sync(FULL, n);
-      for (uint32_t i = 0; i < nmax; i += 16, src++)
-      {
-        if (i < n) ls_append(s, *src, min(16u, n - i));
-        ls_maybe_drain(s);
-      }
-    } else if (kind == K_CHAN || kind == K_CFG) {  // global sources, 16-byte aligned and zero padded
-      const uint4* src;
-      uint32_t n;
-      if (kind == K_CHAN) {
-        const uint32_t o = arg == 0 ? 0u : arg == 1 ? pad16(cd.user_len) : arg == 2 ? pad16(cd.user_len) + pad16(cd.name_len)
-                                                               : pad16(cd.user_len) + pad16(cd.name_len) + pad16(cd.title_len);
-        src = (const uint4*)(b.chan_blob + cd.off + o);
-        n = arg == 0 ? cd.user_len : arg == 1 ? cd.name_len : arg == 2 ? cd.title_len : cd.cdata_len;
-      } else {
-        src = (const uint4*)(cfg.blob + (arg == 0 ? cfg.off[0] : arg == 1 ? cfg.off[1] : arg == 2 ? cfg.off[2] : cfg.off[3]));
-        n = arg == 0 ? cfg.label_len : arg == 1 ? cfg.created_tg_len : arg == 2 ? cfg.created_yt_len : cfg.capture_len;
-      }
-      if (!on) n = 0;
+    const uint8_t* src = nullptr;
+    uint32_t n = 0, g = 0;
+    bool more = false, padded = true;  // padded: the source is zero beyond n up to the next 16-byte boundary
+    if (kind == K_LIT) {
+      src = (const uint8_t*)(sh.tmpl + ((en >> 12) & 0x7FFu));
+      n = on ? en >> 23 : 0u;
+    } else if (kind == K_FIELD) {
+      src = rb + (arg ? 16u + (arg >= 2 ? 16u * arg : 0u) : 0u);
+      n = on ? rb[128 + arg] : 0u;
+    } else if (kind == K_POSTTYPE) {
+      src = (const uint8_t*)(sh.ptype + 2u * ct);
+      n = on ? kPostTypeLen[ct] : 0u;
+    } else if (kind == K_CHAN) {
+      const uint32_t o = arg == 0 ? 0u : arg == 1 ? pad16(cd.user_len) : arg == 2 ? pad16(cd.user_len) + pad16(cd.name_len)
+                                                             : pad16(cd.user_len) + pad16(cd.name_len) + pad16(cd.title_len);
+      src = b.chan_blob + cd.off + o;
+      n = !on ? 0u : arg == 0 ? cd.user_len : arg == 1 ? cd.name_len : arg == 2 ? cd.title_len : cd.cdata_len;
       copied += n;
-      const uint32_t nmax = __reduce_max_sync(FULL, n);
-      for (uint32_t i = 0; i < nmax; i += 16, src++)
-      {
-        if (i < n) ls_append(s, __ldg(src), min(16u, n - i));
-        ls_maybe_drain(s);
-      }
+    } else if (kind == K_CFG) {
+      src = cfg.blob + (arg == 0 ? cfg.off[0] : arg == 1 ? cfg.off[1] : arg == 2 ? cfg.off[2] : cfg.off[3]);
+      n = !on ? 0u : arg == 0 ? cfg.label_len : arg == 1 ? cfg.created_tg_len : arg == 2 ? cfg.created_yt_len : cfg.capture_len;
+      copied += n;
     } else if (kind == K_ESC) {  // a string of the record: copied here if it needs no escaping and is short
-      const uint8_t* p = arg == XL_DESC ? d.desc : arg == XL_MEDIA ? a.v.media : arg == XL_HANDLE ? a.v.handle : a.v.alt;
-      const uint32_t n = arg == XL_DESC ? d.desc_len : arg == XL_MEDIA ? a.v.media_len : arg == XL_HANDLE ? a.v.handle_len : a.v.alt_len;
+      const uint8_t* sp = arg == XL_DESC ? d.desc : arg == XL_MEDIA ? a.v.media : arg == XL_HANDLE ? a.v.handle : a.v.alt;
+      const uint32_t sn = arg == XL_DESC ? d.desc_len : arg == XL_MEDIA ? a.v.media_len : arg == XL_HANDLE ? a.v.handle_len : a.v.alt_len;
       uint32_t xl = 0;
       if (active) {
         xpos_g[arg] = (uint32_t)(s.pos - line_start);
         if (on) xl = xlen_g[arg];
       }
-      const bool mine = on && xl == n && n <= LANE_TEXT_MAX;  // same rule in emit_tg_escapes
-      ls_skip(s, mine ? 0u : xl);                             // else the esc kernel writes it
-      gaps += mine ? 0u : xl;
-      copied += mine ? n : 0u;
-      uint32_t rem = mine ? n : 0u;
-      if (__any_sync(FULL, rem != 0)) {
-        const uint32_t s0 = (uint32_t)(uintptr_t)p & 15u;
-        const uint4* A = (const uint4*)(p - s0);
-        if (rem) {  // bytes [s0, 16) of the first aligned block
-          const uint32_t k = min(rem, 16u - s0);
-          ls_append(s, mask128(shr128_bytes(__ldg(A), s0), k), k);
-          rem -= k;
-        }
-        A++;
-        ls_maybe_drain(s);
-        while (__any_sync(FULL, rem != 0)) {
-          if (rem) {
-            const uint32_t k = min(rem, 16u);
-            uint4 w = __ldg(A);
-            if (k < 16u) w = mask128(w, k);
-            ls_append(s, w, k);
-            rem -= k;
-          }
-          A++;
-          ls_maybe_drain(s);
-        }
+      const bool mine = on && xl == sn && sn <= LANE_TEXT_MAX;  // same rule in emit_tg_escapes
+      g = mine ? 0u : xl;                                       // else the esc kernel writes it
+      if (mine) {
+        src = sp;
+        n = sn;
+        copied += sn;
       }
+      padded = false;
     } else if (kind == K_COMMENTS) {  // nil -> null, empty -> []; a real list is left to the maps kernel
       const bool mine = on && (d.comments_nil || d.c1 == d.c0);
-      uint32_t g = 0;
       if (active) {
         xpos_g[XL_COMMENTS] = (uint32_t)(s.pos - line_start);
         if (on && !mine) g = xlen_g[XL_COMMENTS];
       }
-      ls_skip(s, g);
-      gaps += g;
-      if (mine) ls_append(s, make_uint4(d.comments_nil ? 0x6c6c756eu : 0x5d5bu, 0, 0, 0), d.comments_nil ? 4u : 2u);
-      ls_maybe_drain(s);
+      if (mine) {
+        *(uint4*)(rb + 96) = make_uint4(d.comments_nil ? 0x6c6c756eu : 0x5d5bu, 0, 0, 0);
+        src = rb + 96;
+        n = d.comments_nil ? 4u : 2u;
+      }
     } else if (kind == K_REACTIONS) {  // map[string]int, keys in byte order (see size_reaction_map for "simple")
-      const uint32_t r0 = b.react_off[r], nr = b.react_off[r + 1] - r0;
-      uint32_t g = 0;
-      bool mine = false;
-      if (active) {
-        xpos_g[XL_REACTIONS] = (uint32_t)(s.pos - line_start);
-        mine = on && (nr == 0 || (xlen_g[XL_FLAGS] & XLF_SIMPLE_MAP));
-        if (on && !mine) g = xlen_g[XL_REACTIONS];
-      }
-      ls_skip(s, g);
-      gaps += g;
-      const uint32_t nn = mine ? nr : 0u;  // <= LANE_MAP_MAX
-      const uint32_t nmax = __reduce_max_sync(FULL, nn);
-      // the rendered fields are not needed any more (every K_FIELD piece precedes the reactions): the
-      // row becomes the entry table (16 bytes each: key, count, key length) plus a render slot
-      uint4* ent = (uint4*)row;
-      for (uint32_t j = 0; j < nmax; j++) {
-        if (j < nn) {
-          const tgi_reaction rc = b.reacts[r0 + j];
-          const uint8_t* kp = b.aux + rc.emoji_off;
-          const uint32_t kl = rc.emoji_len;
-          uint32_t k0 = ld_u32_unaligned(kp), k1 = kl > 4 ? ld_u32_unaligned(kp + 4) : 0u;
-          if (kl < 4) k0 &= (1u << (8u * kl)) - 1u;
-          if (kl > 4 && kl < 8) k1 &= (1u << (8u * (kl - 4u))) - 1u;
-          ent[j] = make_uint4(k0, k1, (uint32_t)rc.count, kl);
+      uint4* ent = (uint4*)row;        // entry table: key (8 bytes), count, key length
+      uint8_t* sc = rb + 96;           // 32 bytes to compose one entry in
+      if (t == 0) {
+        const uint32_t r0 = b.react_off[r], nr = b.react_off[r + 1] - r0;
+        bool mine = false;
+        if (active) {
+          xpos_g[XL_REACTIONS] = (uint32_t)(s.pos - line_start);
+          mine = on && (nr == 0 || (xlen_g[XL_FLAGS] & XLF_SIMPLE_MAP));
+          if (on && !mine) g = xlen_g[XL_REACTIONS];
         }
-      }
-      if (mine) ls_append(s, make_uint4(nn ? 0x7bu : 0x7d7bu, 0, 0, 0), nn ? 1u : 2u);  // { or {}
-      ls_maybe_drain(s);
-      uint64_t prev = 0;  // keys are non-empty and contain no NUL: every compare key is > 0
-      for (uint32_t k = 0; k < nmax; k++) {
+        multi_n = mine ? nr : 0u;  // <= LANE_MAP_MAX
+        multi_max = __reduce_max_sync(FULL, multi_n);
+        for (uint32_t j = 0; j < multi_max; j++) {
+          if (j < multi_n) {
+            const tgi_reaction rc = b.reacts[r0 + j];
+            const uint8_t* kp = b.aux + rc.emoji_off;
+            const uint32_t kl = rc.emoji_len;
+            uint32_t k0 = ld_u32_unaligned(kp), k1 = kl > 4 ? ld_u32_unaligned(kp + 4) : 0u;
+            if (kl < 4) k0 &= (1u << (8u * kl)) - 1u;
+            if (kl > 4 && kl < 8) k1 &= (1u << (8u * (kl - 4u))) - 1u;
+            ent[j] = make_uint4(k0, k1, (uint32_t)rc.count, kl);
+          }
+        }
+        if (mine) {
+          *(uint4*)sc = make_uint4(multi_n ? 0x7bu : 0x7d7bu, 0, 0, 0);  // { or {}
+          src = sc;
+          n = multi_n ? 1u : 2u;
+        }
+        prev = 0;  // keys are non-empty and contain no NUL: every compare key is > 0
+      } else if (t <= multi_n) {  // entry t-1 in key order:  "key":count, or "key":count}
         uint4 be = make_uint4(0, 0, 0, 0);
-        if (k < nn) {
-          uint64_t best = ~0ull;
-          for (uint32_t j = 0; j < nmax; j++) {
-            if (j < nn) {
-              const uint4 e = ent[j];
-              const uint64_t ck = ((uint64_t)__byte_perm(e.x, 0, 0x0123) << 32) | __byte_perm(e.y, 0, 0x0123);
-              if (ck > prev && ck < best) {
-                best = ck;
-                be = e;
-              }
+        uint64_t best = ~0ull;
+        for (uint32_t j = 0; j < multi_max; j++) {
+          if (j < multi_n) {
+            const uint4 e = ent[j];
+            const uint64_t ck = ((uint64_t)__byte_perm(e.x, 0, 0x0123) << 32) | __byte_perm(e.y, 0, 0x0123);
+            if (ck > prev && ck < best) {
+              best = ck;
+              be = e;
             }
           }
-          prev = best;
         }
-#pragma unroll 1
-        for (int step = 0; step < 2; step++) {
-          if (k < nn) {
-            if (step == 0) {  // "key
-              ls_append(s, make_uint4(0x22u | (be.x << 8), (be.x >> 24) | (be.y << 8), be.y >> 24, 0), be.w + 1u);
-            } else {  // ":count, or ":count}
-              uint8_t* sc = rb + 96;
-              *(uint4*)sc = make_uint4(0x3a22u, 0, 0, 0);
-              const uint32_t dl = (uint32_t)render_i64(sc + 2, (int64_t)(int32_t)be.z);
-              sc[2 + dl] = k + 1 == nn ? '}' : ',';
-              ls_append(s, *(const uint4*)sc, 3u + dl);
-            }
-          }
-          ls_maybe_drain(s);
-        }
+        prev = best;
+        const uint32_t kl = be.w;
+        *(uint4*)sc = make_uint4(0x22u | (be.x << 8), (be.x >> 24) | (be.y << 8), be.y >> 24, 0);
+        *(uint4*)(sc + 16) = make_uint4(0, 0, 0, 0);
+        sc[1 + kl] = '"';
+        sc[2 + kl] = ':';
+        const uint32_t dl = (uint32_t)render_i64(sc + 3 + kl, (int64_t)(int32_t)be.z);
+        sc[3 + kl + dl] = t == multi_n ? '}' : ',';
+        src = sc;
+        n = 4u + kl + dl;
       }
+      more = t < multi_max;
+      padded = false;
     } else {  // K_OUTLINKS: "name","name" (the names are [a-z0-9_], tg_links.cuh)
-      const bool mine = on && nl <= LANE_LINKS_MAX;
-      uint32_t g = 0;
-      if (active) {
-        xpos_g[XL_OUTLINKS] = (uint32_t)(s.pos - line_start);
-        if (on && !mine) g = xlen_g[XL_OUTLINKS];
-      }
-      ls_skip(s, g);
-      gaps += g;
-      const uint32_t nn = mine ? nl : 0u;
-      const uint32_t nmax = __reduce_max_sync(FULL, nn);
-      for (uint32_t k = 0; k < nmax; k++) {
-        const uint32_t* lw = (const uint32_t*)(links + (k < nn ? k : 0u));
-        const uint32_t len = k < nn ? links[k].len : 0u;
-#pragma unroll 1
-        for (int step = 0; step < 4; step++) {
-          uint4 w = make_uint4(0x22u, 0, 0, 0);
-          uint32_t n = k < nn ? 1u : 0u;
-          if (step == 0 && k) {
-            w.x = 0x222cu;  // ,"
-            n *= 2u;
-          } else if (step == 1) {
-            if (n) w = make_uint4(__ldg(lw), __ldg(lw + 1), __ldg(lw + 2), __ldg(lw + 3));
-            n = min(len, 16u);
-          } else if (step == 2) {
-            if (len > 16u) w = make_uint4(__ldg(lw + 4), __ldg(lw + 5), __ldg(lw + 6), __ldg(lw + 7));
-            n = len > 16u ? len - 16u : 0u;
-          }
-          if (n) ls_append(s, w, n);
-          ls_maybe_drain(s);
+      if (t == 0) {
+        const bool mine = on && nl <= LANE_LINKS_MAX;
+        if (active) {
+          xpos_g[XL_OUTLINKS] = (uint32_t)(s.pos - line_start);
+          if (on && !mine) g = xlen_g[XL_OUTLINKS];
         }
+        multi_n = mine ? nl : 0u;
+        multi_max = __reduce_max_sync(FULL, multi_n);
       }
+      if (t < multi_n) {  // compose  ,"name"  (without the comma for the first) in the field row
+        const uint32_t* lw = (const uint32_t*)(links + t);
+        const uint32_t len = links[t].len, lead = t ? 2u : 1u;
+        uint8_t* sc = rb;
+        sc[0] = t ? ',' : '"';
+        sc[1] = '"';
+#pragma unroll 1
+        for (uint32_t k = 0; k < len; k += 4) {  // the name field is zero padded to 32 bytes
+          const uint32_t w = __ldg(lw + (k >> 2));
+          sc[lead + k] = (uint8_t)w;
+          sc[lead + k + 1] = (uint8_t)(w >> 8);
+          sc[lead + k + 2] = (uint8_t)(w >> 16);
+          sc[lead + k + 3] = (uint8_t)(w >> 24);
+        }
+        sc[lead + len] = '"';
+        src = sc;
+        n = lead + len + 1u;
+      }
+      more = t + 1 < multi_max;
+      padded = false;
+    }
+    ls_skip(s, g);
+    gaps += g;
+    {  // the copy loop: 16 source bytes per step, bytes [0, n) of src
+      const uint32_t s0 = (uint32_t)(uintptr_t)src & 15u;
+      const uint4* A = (const uint4*)(src - s0);
+      uint32_t rem = n, first = s0;
+      while (__any_sync(FULL, rem != 0)) {
+        if (rem) {
+          uint4 w = *A;
+          if (first) w = shr128_bytes(w, first);
+          const uint32_t k = min(rem, 16u - first);
+          if (k < 16u && !padded) w = mask128(w, k);
+          ls_append(s, w, k);
+          rem -= k;
+          first = 0;
+        }
+        A++;
+        ls_maybe_drain(s);
+      }
+    }
+    if (more) {
+      t++;
+    } else {
+      p++;
+      t = 0;
     }
   }
   ls_flush(s);
