@@ -42,7 +42,7 @@ DEVI void ls_stage(LaneStream& s, uint64_t blk) {
 // Warp-collective: write every lane's staged blocks to HBM.  Eight lanes take one row (8 x 16 B), so
 // one LDS.128 / STG.128 pair moves four rows and the global stores are coalesced per row (the per-lane
 // alternatives, measured: ST.128 straight from the lanes = 32 lines per instruction, 1.2 TB/s in
-// scratch/tma_bench.cu; per-lane TMA bulk stores reach 4.8-6.1 TB/s there but cost ~10 issue slots
+// tools/tma_bench.cu; per-lane TMA bulk stores reach 4.8-6.1 TB/s there but cost ~10 issue slots
 // each, because UBLKCP is a uniform-datapath instruction and the compiler serialises the lanes).
 DEVI void ls_drain_warp(LaneStream& s) {
   if (!__any_sync(FULL, s.fill != 0)) return;
@@ -387,11 +387,12 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
     }
     ls_skip(s, g);
     gaps += g;
-    {  // the copy loop: 16 source bytes per step, bytes [0, n) of src
+    {  // the copy loop: one aligned 16-byte block of the source per step, bytes [0, n) of src
       const uint32_t s0 = (uint32_t)(uintptr_t)src & 15u;
       const uint4* A = (const uint4*)(src - s0);
+      const uint32_t steps = __reduce_max_sync(FULL, n ? (s0 + n + 15u) >> 4 : 0u);
       uint32_t rem = n, first = s0;
-      while (__any_sync(FULL, rem != 0)) {
+      for (uint32_t i = 0; i < steps; i++, A++) {
         if (rem) {
           uint4 w = *A;
           if (first) w = shr128_bytes(w, first);
@@ -401,7 +402,6 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
           rem -= k;
           first = 0;
         }
-        A++;
         ls_maybe_drain(s);
       }
     }

@@ -1,5 +1,5 @@
 import sys, numpy as np
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from distributed_crawler_b200 import abi
 from distributed_crawler_b200.corpus import Corpus
 from distributed_crawler_b200.engine import Engine
