@@ -73,7 +73,11 @@ LINK = np.dtype([("name", "u1", (32,)), ("len", "u1"), ("src", "u1"), ("flags", 
 
 assert TG_REC.itemsize == 64 and ENTITY.itemsize == 16 and REACTION.itemsize == 12
 assert COMMENT.itemsize == 32 and TG_CHAN.itemsize == 40 and YT_REC.itemsize == 80
-assert YT_CHAN.itemsize == 64 and LINK.itemsize == 36
+GM_REC = np.dtype([  # tgi_gm_rec: one client.Message
+    ("str_off", "<u8"), ("ts_sec", "<i8"), ("views", "<i8"), ("ts_nsec", "<i4"), ("text_len", "<u4"),
+    ("id_len", "<u2"), ("channel_len", "<u2"), ("sender_len", "<u2"), ("reserved", "<u2"), ("reserved2", "<u4"), ("reserved3", "<u4")])
+GM_REACTION = np.dtype([("key_off", "<u4"), ("key_len", "<u2"), ("reserved", "<u2"), ("count", "<i8")])
+assert YT_CHAN.itemsize == 64 and LINK.itemsize == 36 and GM_REC.itemsize == 48 and GM_REACTION.itemsize == 16
 
 
 # ---- ctypes structs ---------------------------------------------------------------------------
@@ -92,6 +96,13 @@ class YtBatchC(C.Structure):
         ("n", C.c_uint64), ("recs", C.c_void_p), ("strs", C.c_void_p), ("strs_len", C.c_uint64),
         ("n_chans", C.c_uint32), ("reserved", C.c_uint32), ("chans", C.c_void_p),
         ("chan_strs", C.c_void_p), ("chan_strs_len", C.c_uint64)]
+
+
+class GmBatchC(C.Structure):
+    _fields_ = [
+        ("n", C.c_uint64), ("recs", C.c_void_p), ("strs", C.c_void_p), ("strs_len", C.c_uint64),
+        ("react_off", C.c_void_p), ("reacts", C.c_void_p), ("n_reacts", C.c_uint64), ("aux", C.c_void_p),
+        ("aux_len", C.c_uint64)]
 
 
 class ConfigC(C.Structure):

@@ -9,6 +9,7 @@
 #include "tg_walk.cuh"
 #include "tg_lane.cuh"
 #include "yt_walk.cuh"
+#include "gm_walk.cuh"
 
 namespace tgi {
 
@@ -541,6 +542,36 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_kernel(YtBatchDev b, C
     w.sc = &scs[wid];
     w.p = out + line_off[r];
     walk_yt_record(w, a);
+    if (l == 0 && (uint64_t)(w.p - out) != line_off[r + 1]) atomicOr(err, 16);
+  }
+}
+
+// ---- generic client.Message -> sparse Post (a12) ---------------------------------------------------
+__global__ void __launch_bounds__(CTA_THREADS, 4) gm_size_kernel(GmBatchDev b, CfgDev cfg, uint8_t* status, uint32_t* linelen) {
+  __shared__ YtScratch scs[WARPS_PER_CTA];
+  int wid = threadIdx.x >> 5, l = lane_id();
+  uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
+    YtSizer z;
+    z.sc = &scs[wid];
+    bool ok = walk_gm_record(z, b, cfg, r);
+    if (l == 0) {
+      status[r] = ok ? TGI_ST_EMITTED : TGI_ST_NOLINE;
+      linelen[r] = ok ? (uint32_t)z.total : 0u;
+    }
+  }
+}
+__global__ void __launch_bounds__(CTA_THREADS, 4) gm_emit_kernel(GmBatchDev b, CfgDev cfg, const uint8_t* status, const uint64_t* line_off,
+                                                                 uint8_t* out, int* err) {
+  __shared__ YtScratch scs[WARPS_PER_CTA];
+  int wid = threadIdx.x >> 5, l = lane_id();
+  uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
+    if (status[r] != TGI_ST_EMITTED) continue;
+    YtWriter w;
+    w.sc = &scs[wid];
+    w.p = out + line_off[r];
+    walk_gm_record(w, b, cfg, r);
     if (l == 0 && (uint64_t)(w.p - out) != line_off[r + 1]) atomicOr(err, 16);
   }
 }

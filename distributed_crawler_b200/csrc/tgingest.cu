@@ -64,7 +64,7 @@ struct HostBuf {  // pinned
   T* as() const { return (T*)p; }
 };
 
-enum JobKind { JOB_NONE = 0, JOB_TG, JOB_TG_RESIDENT, JOB_TG_UPLOAD, JOB_YT, JOB_YT_RESIDENT, JOB_YT_UPLOAD, JOB_QUIT };
+enum JobKind { JOB_NONE = 0, JOB_TG, JOB_TG_RESIDENT, JOB_TG_UPLOAD, JOB_YT, JOB_YT_RESIDENT, JOB_YT_UPLOAD, JOB_GM, JOB_QUIT };
 
 struct Slot {
   int idx = 0;
@@ -82,6 +82,7 @@ struct Slot {
   // resident batch descriptor
   TgBatchDev tg{};
   YtBatchDev yt{};
+  GmBatchDev gm{};
   uint64_t yt_desc_bytes = 0;
   uint64_t n_ents = 0, n_reacts = 0, n_comments = 0, in_bytes = 0;
   bool resident = false;
@@ -93,6 +94,7 @@ struct Slot {
   bool busy = false, done = false, claimed = false;
   const tgi_tg_batch* in_tg = nullptr;
   const tgi_yt_batch* in_yt = nullptr;
+  const tgi_gm_batch* in_gm = nullptr;
   uint32_t run_flags = 0;
   int rc = 0;
   tgi_result res{};
@@ -720,6 +722,87 @@ int run_yt(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   return finish_batch(c, s, n, flags, line_total, arena_used, arena_cap, 0, launches, out);
 }
 
+// generic client.Message batch (a12): upload, size, scan, emit; no links
+int run_gm(tgi_ctx* c, Slot& s, const tgi_gm_batch* in, uint32_t flags, tgi_result* out) {
+  if (!in) { set_err(c, "null batch"); return TGI_E_ARG; }
+  if (in->n && !in->recs) { set_err(c, "generic batch: recs must be non-null"); return TGI_E_ARG; }
+  if (in->n >= (1ull << 40)) { set_err(c, "generic batch: too many records"); return TGI_E_ARG; }
+  const uint64_t n = in->n;
+  cudaStream_t st = s.stream;
+  s.in_bytes = 0;
+  s.resident = false;
+  int rc;
+#define UP(buf, ptr, cnt)                      \
+  rc = h2d(c, s, s.buf, ptr, (size_t)(cnt));   \
+  if (rc) return rc;
+  UP(d_recs, in->recs, n);
+  UP(d_strs, in->strs, in->strs_len);
+  UP(d_react_off, in->react_off, in->react_off ? n + 1 : 0);
+  UP(d_reacts, in->reacts, in->n_reacts);
+  UP(d_aux, in->aux, in->aux_len);
+#undef UP
+  GmBatchDev& b = s.gm;
+  b.n = n;
+  b.recs = s.d_recs.as<tgi_gm_rec>();
+  b.strs = s.d_strs.as<uint8_t>();
+  b.react_off = in->react_off ? s.d_react_off.as<uint32_t>() : nullptr;
+  b.reacts = s.d_reacts.as<tgi_gm_reaction>();
+  b.aux = s.d_aux.as<uint8_t>();
+  uint32_t launches = 0;
+  const bool want_json = flags & TGI_RUN_JSONL;
+  CfgDev cfg;
+  {
+    std::lock_guard<std::mutex> g(c->cfg_mu);
+    cfg = c->cfgdev;
+  }
+  CK(s.d_scalars.ensure(SC_COUNT * 8));
+  CK(s.h_scalars.ensure(SC_COUNT * 8));
+  uint64_t* dsc = s.d_scalars.as<uint64_t>();
+  uint64_t* hsc = s.h_scalars.as<uint64_t>();
+  CK(s.d_status.ensure(n));
+  CK(s.d_linelen.ensure(n * 4));
+  CK(s.d_line_off.ensure((n + 1) * 8));
+  CK(s.d_link_start.ensure(n * 4));
+  CK(s.d_link_count.ensure(n * 4));
+  CK(s.d_arena.ensure(1024 * sizeof(tgi_link)));
+  CK(cudaEventRecord(s.ev_k0, st));
+  CK(cudaMemsetAsync(dsc, 0, SC_COUNT * 8, st));
+  if (n) {
+    CK(cudaMemsetAsync(s.d_link_start.p, 0, n * 4, st));
+    CK(cudaMemsetAsync(s.d_link_count.p, 0, n * 4, st));
+  }
+  int* derr = (int*)(dsc + SC_CURSOR) + 1;
+  unsigned g = (unsigned)std::min<uint64_t>((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
+  CK(cudaEventRecord(s.ev_p0, st));
+  if (n) {  // the status does not depend on TGI_RUN_JSONL: the size pass always runs
+    gm_size_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, s.d_status.as<uint8_t>(), s.d_linelen.as<uint32_t>());
+    launches++;
+  }
+  CK(cudaEventRecord(s.ev_p1, st));
+  uint64_t line_total = 0;
+  if (want_json) {
+    rc = launch_scan(c, s, s.d_linelen.as<uint32_t>(), n, s.d_line_off.as<uint64_t>(), dsc + SC_LINE_TOTAL, launches);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(hsc, dsc, SC_COUNT * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    line_total = hsc[SC_LINE_TOTAL];
+    if (c->cfg.max_out_bytes && line_total > c->cfg.max_out_bytes) {
+      set_err(c, "JSONL output %llu bytes exceeds max_out_bytes", (unsigned long long)line_total);
+      return TGI_E_CAPACITY;
+    }
+    CK(s.d_jsonl.ensure(line_total));
+    CK(cudaEventRecord(s.ev_e0, st));
+    if (n) {
+      gm_emit_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, s.d_status.as<uint8_t>(), s.d_line_off.as<uint64_t>(), s.d_jsonl.as<uint8_t>(), derr);
+      launches++;
+    }
+    CK(cudaEventRecord(s.ev_f1, st));
+    CK(cudaEventRecord(s.ev_e1, st));
+    CK(cudaGetLastError());
+  }
+  return finish_batch(c, s, n, flags & ~(uint32_t)TGI_RUN_FRONTIER, line_total, 0, 1024, 0, launches, out);
+}
+
 void worker_main(tgi_ctx* c, Slot* s) {
   cudaSetDevice(c->device);
   for (;;) {
@@ -743,6 +826,7 @@ void worker_main(tgi_ctx* c, Slot* s) {
       if (e != cudaSuccess) { set_err(c, "upload sync: %s", cudaGetErrorString(e)); rc = TGI_E_CUDA; }
     }
     if (rc == TGI_OK && (job == JOB_YT || job == JOB_YT_RESIDENT)) rc = run_yt(c, *s, s->run_flags, &s->res);
+    if (job == JOB_GM) rc = run_gm(c, *s, s->in_gm, s->run_flags, &s->res);
     {
       std::lock_guard<std::mutex> lk(s->mu);
       s->rc = rc;
@@ -753,7 +837,8 @@ void worker_main(tgi_ctx* c, Slot* s) {
   }
 }
 
-int post_job(tgi_ctx* c, int slot, JobKind kind, const tgi_tg_batch* in, uint32_t flags, const tgi_yt_batch* in_yt = nullptr) {
+int post_job(tgi_ctx* c, int slot, JobKind kind, const tgi_tg_batch* in, uint32_t flags, const tgi_yt_batch* in_yt = nullptr,
+             const tgi_gm_batch* in_gm = nullptr) {
   if (!c) return TGI_E_ARG;
   if (slot < 0 || slot >= TGI_SLOTS) { set_err(c, "bad slot %d", slot); return TGI_E_ARG; }
   Slot& s = c->slots[slot];
@@ -764,6 +849,7 @@ int post_job(tgi_ctx* c, int slot, JobKind kind, const tgi_tg_batch* in, uint32_
   s.done = false;
   s.in_tg = in;
   s.in_yt = in_yt;
+  s.in_gm = in_gm;
   s.run_flags = flags;
   s.job = kind;
   s.cv.notify_all();
@@ -983,6 +1069,14 @@ int tgi_youtube_batch(tgi_ctx* c, const tgi_yt_batch* in, uint32_t run_flags, tg
   if (!c) return TGI_E_ARG;
   int slot = claim_slot(c);
   int rc = post_job(c, slot, JOB_YT, nullptr, run_flags, in);
+  if (rc == TGI_OK) rc = wait_job(c, slot, out);
+  if (rc != TGI_OK) tgi_result_release(c, slot);
+  return rc;
+}
+int tgi_generic_batch(tgi_ctx* c, const tgi_gm_batch* in, uint32_t run_flags, tgi_result* out) {
+  if (!c) return TGI_E_ARG;
+  int slot = claim_slot(c);
+  int rc = post_job(c, slot, JOB_GM, nullptr, run_flags, nullptr, in);
   if (rc == TGI_OK) rc = wait_job(c, slot, out);
   if (rc != TGI_OK) tgi_result_release(c, slot);
   return rc;

@@ -357,3 +357,59 @@ def pack_youtube(videos: list[YouTubeVideo], channels: list[YouTubeChannel] | No
             ch.published_sec, ch.published_nsec, 1 if ch.cached else 0)
         cstrs += b"".join(parts)
     return YtBatch(recs=recs, strs=_blob(strs), chans=chans, chan_strs=_blob(cstrs))
+
+
+# ---- generic client.Message -----------------------------------------------------------
+@dataclass
+class GenericMessage:  # client.TelegramMessage as getMessagesWithClient fills it (client/clients.go:325-334)
+    id: str | bytes = ""
+    channel_id: str | bytes = ""
+    text: str | bytes = ""
+    sender_name: str | bytes = ""
+    ts_sec: int = 0
+    ts_nsec: int = 0
+    views: int = 0
+    reactions: list[tuple[str | bytes, int]] = field(default_factory=list)  # map entries (later duplicates overwrite)
+
+
+class GmBatch:
+    FIELDS = ("recs", "strs", "react_off", "reacts", "aux")
+
+    def __init__(self, **arrays):
+        for k in self.FIELDS:
+            setattr(self, k, arrays[k])
+        self.n = len(self.recs)
+
+    def descriptor(self) -> abi.GmBatchC:
+        d = abi.GmBatchC()
+        d.n = self.n
+        d.recs = abi.ptr(self.recs)
+        d.strs = abi.ptr(self.strs)
+        d.strs_len = self.strs.size
+        d.react_off = abi.ptr(self.react_off)
+        d.reacts = abi.ptr(self.reacts)
+        d.n_reacts = len(self.reacts)
+        d.aux = abi.ptr(self.aux)
+        d.aux_len = self.aux.size
+        return d
+
+
+def pack_generic(msgs: list[GenericMessage]) -> GmBatch:
+    recs = np.zeros(len(msgs), abi.GM_REC)
+    react_off = np.zeros(len(msgs) + 1, np.uint32)
+    reacts = []
+    strs, aux = bytearray(), bytearray()
+    for i, m in enumerate(msgs):
+        parts = [_b(m.id), _b(m.channel_id), _b(m.text), _b(m.sender_name)]
+        r = recs[i]
+        r["str_off"] = len(strs)
+        r["ts_sec"], r["ts_nsec"], r["views"] = m.ts_sec, m.ts_nsec, m.views
+        r["id_len"], r["channel_len"], r["text_len"], r["sender_len"] = (len(parts[0]), len(parts[1]), len(parts[2]), len(parts[3]))
+        strs += b"".join(parts)
+        for k, cnt in m.reactions:
+            kb = _b(k)
+            reacts.append((len(aux), len(kb), 0, cnt))
+            aux += kb
+        react_off[i + 1] = len(reacts)
+    ra = np.array(reacts, abi.GM_REACTION) if reacts else np.zeros(0, abi.GM_REACTION)
+    return GmBatch(recs=recs, strs=_blob(strs), react_off=react_off, reacts=ra, aux=_blob(aux))

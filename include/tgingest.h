@@ -229,6 +229,49 @@ typedef struct tgi_yt_batch {
   uint64_t chan_strs_len;
 } tgi_yt_batch;
 
+/* ---- generic client.Message -------------------------------------------------------
+ * The secondary Telegram path: client.Message (client/interfaces.go:56-100) as
+ * TelegramClient.getMessagesWithClient fills it (client/clients.go:296-339), converted by
+ * TelegramCrawler.convertMessageToPost (crawler/telegram/telegram_crawler.go:179-262) into a SPARSE
+ * model.Post: channel_id / channel_name = GetChannelID(), post_uid = GetID(), published_at =
+ * GetTimestamp(), created_at = capture_time = time.Now(), view_count = views_count = GetViews(),
+ * platform_name "telegram", description = searchable_text = all_text = GetText(), handle =
+ * GetSenderName(), reactions = the map if it is non-empty else nil; every other key keeps its zero
+ * value.  No link extraction on this path.                                                          */
+typedef struct tgi_gm_reaction { /* 16 bytes: one entry of map[string]int64 */
+  uint32_t key_off; /* offset in `aux`                                                               */
+  uint16_t key_len;
+  uint16_t reserved;
+  int64_t count;
+} tgi_gm_reaction;
+
+typedef struct tgi_gm_rec { /* 48 bytes */
+  uint64_t str_off;   /* in `strs`: id | channel_id | text | sender_name                            */
+  int64_t ts_sec;     /* GetTimestamp(): time.Unix(sec, nsec) shown in the context's zone           */
+  int64_t views;      /* GetViews()                                                                  */
+  int32_t ts_nsec;
+  uint32_t text_len;
+  uint16_t id_len;
+  uint16_t channel_len;
+  uint16_t sender_len;
+  uint16_t reserved;
+  uint32_t reserved2;
+  uint32_t reserved3;
+} tgi_gm_rec;
+
+typedef struct tgi_gm_batch {
+  uint64_t n;
+  const tgi_gm_rec* recs;
+  const uint8_t* strs;
+  uint64_t strs_len;
+  const uint32_t* react_off; /* [n+1] ranges into reacts; entries of one record = its map, later
+                                duplicates of a key overwrite earlier ones                          */
+  const tgi_gm_reaction* reacts;
+  uint64_t n_reacts;
+  const uint8_t* aux;        /* reaction keys                                                      */
+  uint64_t aux_len;
+} tgi_gm_batch;
+
 /* ---- configuration -------------------------------------------------------------------------- */
 #define TGI_CFG_HAS_MIN_POST_DATE 0x01 /* !cfg.MinPostDate.IsZero()                               */
 #define TGI_CFG_SKIP_MEDIA 0x02        /* cfg.SkipMediaDownload; REQUIRED (media download is RPC) */
@@ -330,6 +373,11 @@ int tgi_telegram_batch(tgi_ctx* ctx, const tgi_tg_batch* in, uint32_t run_flags,
 int tgi_youtube_submit(tgi_ctx* ctx, int slot, const tgi_yt_batch* in, uint32_t run_flags);
 int tgi_youtube_wait(tgi_ctx* ctx, int slot, tgi_result* out);
 int tgi_youtube_batch(tgi_ctx* ctx, const tgi_yt_batch* in, uint32_t run_flags, tgi_result* out);
+
+/* Generic client.Message -> sparse Post line: replaces the loop body
+ * crawler/telegram/telegram_crawler.go:148-156 (convertMessageToPost :179-262) + json.Marshal+'\n'.
+ * Blocking; picks a free slot.  status[] is TGI_ST_EMITTED or TGI_ST_NOLINE; no links.             */
+int tgi_generic_batch(tgi_ctx* ctx, const tgi_gm_batch* in, uint32_t run_flags, tgi_result* out);
 
 void tgi_result_release(tgi_ctx* ctx, int slot);
 

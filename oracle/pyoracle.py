@@ -45,6 +45,8 @@ def lib() -> C.CDLL:
         L.orc_set_clock.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32]
         L.orc_telegram_batch.argtypes = [C.c_void_p, C.POINTER(abi.TgBatchC), C.c_uint32, C.c_int,
                                          C.POINTER(OrcResultC)]
+        L.orc_generic_batch.argtypes = [C.c_void_p, C.POINTER(abi.GmBatchC), C.c_uint32, C.c_int,
+                                        C.POINTER(OrcResultC)]
         L.orc_youtube_batch.argtypes = [C.c_void_p, C.POINTER(abi.YtBatchC), C.c_uint32, C.c_int,
                                         C.POINTER(OrcResultC)]
         L.orc_result_free.argtypes = [C.POINTER(OrcResultC)]
@@ -122,6 +124,15 @@ class Oracle:
         d = batch.descriptor()
         r = OrcResultC()
         rc = lib().orc_youtube_batch(self.h, C.byref(d), run_flags, nthreads, C.byref(r))
+        assert rc == 0
+        out = result_from_c(r) if copy else (int(r.n), int(r.jsonl_len), int(r.n_links))
+        lib().orc_result_free(C.byref(r))
+        return out
+
+    def generic(self, batch, run_flags=abi.RUN_JSONL, nthreads=1, copy=True):
+        d = batch.descriptor()
+        r = OrcResultC()
+        rc = lib().orc_generic_batch(self.h, C.byref(d), run_flags, nthreads, C.byref(r))
         assert rc == 0
         out = result_from_c(r) if copy else (int(r.n), int(r.jsonl_len), int(r.n_links))
         lib().orc_result_free(C.byref(r))

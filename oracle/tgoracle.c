@@ -472,6 +472,7 @@ struct work {
   const orc_ctx* c;
   const tgi_tg_batch* tg;
   const tgi_yt_batch* yt;
+  const tgi_gm_batch* gm;
   uint64_t r0, r1;
   uint32_t run_flags;
   buf_t json;        /* lines of this range */
@@ -1012,6 +1013,102 @@ static int yt_record(const orc_ctx* c, const tgi_yt_batch* b, uint64_t r, buf_t*
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* generic client.Message -> sparse Post                                            */
+/* TelegramCrawler.convertMessageToPost, crawler/telegram/telegram_crawler.go:179-262: the fields
+ * it sets are listed at :183-246, the reactions map at :250-257 (only when non-empty); everything
+ * else keeps Go's zero value, encoded per model/data.go:9-139 (nil slice / pointer / map -> null,
+ * zero time -> "0001-01-01T00:00:00Z", nested structs with their zero fields).                  */
+typedef struct {
+  const uint8_t* p;
+  uint64_t n;
+  int64_t count;
+} kv64_t;
+static int kv64_cmp(const void* a, const void* b) {
+  const kv64_t *x = a, *y = b;
+  uint64_t m = x->n < y->n ? x->n : y->n;
+  int c = memcmp(x->p, y->p, m);
+  if (c) return c;
+  return x->n < y->n ? -1 : (x->n > y->n ? 1 : 0);
+}
+static int gm_record(const orc_ctx* c, const tgi_gm_batch* b, uint64_t r, buf_t* o) {
+  const tgi_config* cfg = &c->cfg;
+  const tgi_gm_rec* rec = &b->recs[r];
+  const uint8_t* id = b->strs + rec->str_off;
+  const uint8_t* chan = id + rec->id_len;
+  const uint8_t* text = chan + rec->channel_len;
+  const uint8_t* sender = text + rec->text_len;
+  size_t line_start = o->len;
+  int ok = 1;
+  LIT(o, "{\"post_link\":\"\",\"channel_id\":"); put_jstr(o, chan, rec->channel_len);          /* :184 */
+  LIT(o, ",\"post_uid\":"); put_jstr(o, id, rec->id_len);                                        /* :185 */
+  LIT(o, ",\"url\":\"\",\"published_at\":");
+  ok &= put_time(o, rec->ts_sec, rec->ts_nsec, cfg->tz_offset_sec) > 0;                           /* :187 */
+  LIT(o, ",\"created_at\":");
+  ok &= put_time(o, cfg->created_at_sec, cfg->created_at_nsec, cfg->tz_offset_sec) > 0;           /* :188 time.Now() */
+  LIT(o, ",\"language_code\":\"\",\"engagement\":0,\"view_count\":"); put_int(o, rec->views);      /* :191 */
+  LIT(o, ",\"like_count\":0,\"share_count\":0,\"comment_count\":0,\"crawl_label\":\"\",\"list_ids\":null,"
+         "\"channel_name\":");
+  put_jstr(o, chan, rec->channel_len);                                                            /* :197 */
+  LIT(o, ",\"search_terms\":null,\"search_term_ids\":null,\"project_ids\":null,\"exercise_ids\":null,"
+         "\"label_data\":null,\"labels_metadata\":null,\"project_labeled_post_ids\":null,"
+         "\"labeler_ids\":null,\"all_labels\":null,\"label_ids\":null,\"is_ad\":false,"
+         "\"transcript_text\":\"\",\"image_text\":\"\",\"video_length\":null,\"is_verified\":null,"
+         "\"channel_data\":{\"channel_id\":\"\",\"channel_name\":\"\",\"channel_description\":\"\","
+         "\"channel_profile_image\":\"\",\"channel_engagement_data\":{\"follower_count\":0,"
+         "\"following_count\":0,\"like_count\":0,\"post_count\":0,\"views_count\":0,\"comment_count\":0,"
+         "\"share_count\":0},\"channel_url_external\":\"\",\"channel_url\":\"\",\"country_code\":\"\","
+         "\"published_at\":\"0001-01-01T00:00:00Z\"},\"platform_name\":\"telegram\",\"shared_id\":null,"  /* :213 */
+         "\"quoted_id\":null,\"replied_id\":null,\"ai_label\":null,\"root_post_id\":null,"
+         "\"engagement_steps_count\":0,\"ocr_data\":null,\"performance_scores\":{\"likes\":null,"
+         "\"shares\":null,\"comments\":null,\"views\":0},\"has_embed_media\":null,\"description\":");
+  put_jstr(o, text, rec->text_len);                                                               /* :223 */
+  LIT(o, ",\"repost_channel_data\":null,\"post_type\":null,\"inner_link\":{},\"post_title\":null,"
+         "\"media_data\":{\"document_name\":\"\"},\"is_reply\":null,\"ad_fields\":null,\"likes_count\":0,"
+         "\"shares_count\":0,\"comments_count\":0,\"views_count\":");
+  put_int(o, rec->views);                                                                         /* :234 */
+  LIT(o, ",\"searchable_text\":"); put_jstr(o, text, rec->text_len);                             /* :235 */
+  LIT(o, ",\"all_text\":"); put_jstr(o, text, rec->text_len);                                    /* :236 */
+  LIT(o, ",\"contrast_agent_project_ids\":null,\"agent_ids\":null,\"segment_ids\":null,\"thumb_url\":\"\","
+         "\"media_url\":\"\",\"comments\":null,\"reactions\":");
+  {
+    uint32_t r0 = b->react_off ? b->react_off[r] : 0, r1 = b->react_off ? b->react_off[r + 1] : 0;
+    if (r1 == r0) {                                                                               /* :250 */
+      LIT(o, "null");
+    } else {
+      kv64_t* kv = (kv64_t*)malloc(sizeof(kv64_t) * (r1 - r0));
+      uint32_t m = 0;
+      for (uint32_t i = r0; i < r1; i++) {
+        const tgi_gm_reaction* rc = &b->reacts[i];
+        const uint8_t* p = b->aux + rc->key_off;
+        uint32_t j = 0;
+        for (; j < m; j++)
+          if (kv[j].n == rc->key_len && memcmp(kv[j].p, p, rc->key_len) == 0) break;
+        if (j == m) m++;
+        kv[j].p = p;
+        kv[j].n = rc->key_len;
+        kv[j].count = rc->count;
+      }
+      qsort(kv, m, sizeof(kv64_t), kv64_cmp);
+      LIT(o, "{");
+      for (uint32_t j = 0; j < m; j++) {
+        if (j) LIT(o, ",");
+        put_jstr(o, kv[j].p, kv[j].n);
+        LIT(o, ":");
+        put_int(o, kv[j].count);
+      }
+      LIT(o, "}");
+      free(kv);
+    }
+  }
+  LIT(o, ",\"outlinks\":null,\"capture_time\":");
+  ok &= put_time(o, cfg->capture_sec, cfg->capture_nsec, cfg->tz_offset_sec) > 0;                 /* :245 time.Now() */
+  LIT(o, ",\"handle\":"); put_jstr(o, sender, rec->sender_len);                                  /* :246 */
+  LIT(o, "}\n");
+  if (!ok) { o->len = line_start; return TGI_ST_NOLINE; }
+  return TGI_ST_EMITTED;
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* batch drivers                                                                                 */
 
 #define ORC_MAX_LINKS 4096
@@ -1031,7 +1128,7 @@ static void* worker(void* arg) {
     w->scratch.len = 0;
     w->nlinks[r - w->r0] = 0;
     size_t before = o->len;
-    int st = w->tg ? tg_record(w->c, w->tg, r, o, &ls) : yt_record(w->c, w->yt, r, o, &ls);
+    int st = w->tg ? tg_record(w->c, w->tg, r, o, &ls) : w->yt ? yt_record(w->c, w->yt, r, o, &ls) : gm_record(w->c, w->gm, r, o);
     w->status[r - w->r0] = (uint8_t)st;
     w->linelen[r - w->r0] = (w->run_flags & TGI_RUN_JSONL) ? o->len - before : 0;
     if (st == TGI_ST_EMITTED || st == TGI_ST_NOLINE) {
@@ -1055,9 +1152,9 @@ static void* worker(void* arg) {
   return NULL;
 }
 
-static int run_batch(orc_ctx* c, const tgi_tg_batch* tg, const tgi_yt_batch* yt, uint32_t run_flags,
+static int run_batch(orc_ctx* c, const tgi_tg_batch* tg, const tgi_yt_batch* yt, const tgi_gm_batch* gm, uint32_t run_flags,
                      int nthreads, orc_result* out) {
-  uint64_t n = tg ? tg->n : yt->n;
+  uint64_t n = tg ? tg->n : yt ? yt->n : gm->n;
   if (nthreads < 1) nthreads = 1;
   if ((uint64_t)nthreads > n) nthreads = n ? (int)n : 1;
   if (c->nw < nthreads) {
@@ -1068,7 +1165,7 @@ static int run_batch(orc_ctx* c, const tgi_tg_batch* tg, const tgi_yt_batch* yt,
   work_t* w = c->w;
   pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
   for (int t = 0; t < nthreads; t++) {
-    w[t].c = c; w[t].tg = tg; w[t].yt = yt; w[t].run_flags = run_flags;
+    w[t].c = c; w[t].tg = tg; w[t].yt = yt; w[t].gm = gm; w[t].run_flags = run_flags;
     w[t].r0 = n * (uint64_t)t / (uint64_t)nthreads;
     w[t].r1 = n * (uint64_t)(t + 1) / (uint64_t)nthreads;
     if (nthreads > 1) pthread_create(&th[t], NULL, worker, &w[t]);
@@ -1121,11 +1218,14 @@ static int run_batch(orc_ctx* c, const tgi_tg_batch* tg, const tgi_yt_batch* yt,
 
 int orc_telegram_batch(orc_ctx* c, const tgi_tg_batch* in, uint32_t run_flags, int nthreads,
                        orc_result* out) {
-  return run_batch(c, in, NULL, run_flags, nthreads, out);
+  return run_batch(c, in, NULL, NULL, run_flags, nthreads, out);
 }
 int orc_youtube_batch(orc_ctx* c, const tgi_yt_batch* in, uint32_t run_flags, int nthreads,
                       orc_result* out) {
-  return run_batch(c, NULL, in, run_flags, nthreads, out);
+  return run_batch(c, NULL, in, NULL, run_flags, nthreads, out);
+}
+int orc_generic_batch(orc_ctx* c, const tgi_gm_batch* in, uint32_t run_flags, int nthreads, orc_result* out) {
+  return run_batch(c, NULL, NULL, in, run_flags, nthreads, out);
 }
 void orc_result_free(orc_result* r) { /* arrays are context-owned; valid until the next batch call */
   memset(r, 0, sizeof *r);

@@ -49,6 +49,7 @@ void orc_set_clock(orc_ctx* c, int64_t created_at_sec, int32_t created_at_nsec, 
  * are split into contiguous ranges (the --concurrency analogue); output is identical.            */
 int orc_telegram_batch(orc_ctx* c, const tgi_tg_batch* in, uint32_t run_flags, int nthreads,
                        orc_result* out);
+int orc_generic_batch(orc_ctx* c, const tgi_gm_batch* in, uint32_t run_flags, int nthreads, orc_result* out);
 int orc_youtube_batch(orc_ctx* c, const tgi_yt_batch* in, uint32_t run_flags, int nthreads,
                       orc_result* out);
 void orc_result_free(orc_result* r);

@@ -201,3 +201,50 @@ def test_frontier_first_occurrence_order():
     assert list(o.frontier_insert(k)) == [1, 1, 0, 1, 0]
     assert [bytes(x).rstrip(b"\0") for x in o.frontier_export()] == [b"bbbbb", b"aaaaa", b"ccccc"]
     assert list(o.frontier_insert(names_to_keys32([b"ccccc", b"ddddd"]))) == [0, 1]
+
+
+def test_oracle_generic_message_sparse_post():
+    """the sparse Post of convertMessageToPost (crawler/telegram/telegram_crawler.go:179-262),
+    cross-checked against an independent restatement built from the Go rules in go_rules.py."""
+    import json
+
+    from distributed_crawler_b200.pack import GenericMessage, pack_generic
+    from gm_corpus import make_generic
+    import go_rules
+
+    batch, msgs = make_generic(300, seed=9)
+    tz, cs, cn, ps, pn = 7200, 1_750_000_000, 5_000, 1_750_000_123, 0
+    o = pyoracle.Oracle(tz_offset_sec=tz, created_at_sec=cs, created_at_nsec=cn, capture_sec=ps, capture_nsec=pn)
+    r = o.generic(batch)
+    zero_keys_null = ["list_ids", "search_terms", "search_term_ids", "project_ids", "exercise_ids", "label_data",
+                      "labels_metadata", "project_labeled_post_ids", "labeler_ids", "all_labels", "label_ids", "video_length",
+                      "is_verified", "shared_id", "quoted_id", "replied_id", "ai_label", "root_post_id", "ocr_data",
+                      "has_embed_media", "repost_channel_data", "post_type", "post_title", "is_reply", "ad_fields",
+                      "contrast_agent_project_ids", "agent_ids", "segment_ids", "comments", "outlinks"]
+    for i, m in enumerate(msgs):
+        line = r.line(i)
+        assert line.endswith(b"}\n")
+        js = lambda b: go_rules.go_json_string(b if isinstance(b, bytes) else b.encode())
+        # the variable parts, byte for byte
+        assert line.startswith(b'{"post_link":"","channel_id":' + js(m.channel_id) + b',"post_uid":' + js(m.id) +
+                               b',"url":"","published_at":' + go_rules.go_time_json(m.ts_sec, m.ts_nsec, tz) +
+                               b',"created_at":' + go_rules.go_time_json(cs, cn, tz) + b',"language_code":"","engagement":0,"view_count":' +
+                               str(m.views).encode() + b',')
+        assert b',"description":' + js(m.text) + b',"repost_channel_data":null' in line
+        assert b',"searchable_text":' + js(m.text) + b',"all_text":' + js(m.text) + b',"contrast_agent_project_ids"' in line
+        assert line.endswith(b',"outlinks":null,"capture_time":' + go_rules.go_time_json(ps, pn, tz) + b',"handle":' + js(m.sender_name) + b"}\n")
+        if not m.reactions:
+            assert b',"reactions":null,' in line
+        else:
+            d = {}
+            for k, v in m.reactions:
+                d[k.encode() if isinstance(k, str) else k] = v
+            want = b"{" + b",".join(go_rules.go_json_string(k) + b":" + str(d[k]).encode() for k in sorted(d)) + b"}"
+            assert b',"reactions":' + want + b',"outlinks"' in line
+        # the shape: 65 keys in declaration order, zero values elsewhere (invalid UTF-8 is � by then: valid JSON)
+        doc = json.loads(line.decode("utf-8"))
+        assert len(doc) == 65 and list(doc)[:4] == ["post_link", "channel_id", "post_uid", "url"] and list(doc)[-1] == "handle"
+        assert all(doc[k] is None for k in zero_keys_null)
+        assert doc["platform_name"] == "telegram" and doc["channel_name"] == doc["channel_id"] and doc["views_count"] == m.views
+        assert doc["channel_data"]["published_at"] == "0001-01-01T00:00:00Z" and doc["inner_link"] == {}
+        assert doc["performance_scores"] == {"likes": None, "shares": None, "comments": None, "views": 0}
