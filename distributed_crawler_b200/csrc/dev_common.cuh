@@ -150,6 +150,14 @@ DEVI uint32_t swar_has_byte(uint32_t w, uint32_t c) {  // bit7 of each byte equa
   return (x - 0x01010101u) & ~x & 0x80808080u;
 }
 
+// exact per-byte equality: bit 7 of every byte of w that equals c (swar_has_byte above is exact only
+// as an "any" test: its borrow can flag the byte above a match)
+DEVI uint32_t swar_eq(uint32_t w, uint32_t c) {
+  const uint32_t x = w ^ (c * 0x01010101u);
+  return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
+DEVI uint32_t swar_movemask(uint32_t m) { return (((m >> 7) & 0x01010101u) * 0x01020408u) >> 24; }  // bit 7s -> 4 bits
+
 // carry: structure flags of the previous strip's lane 31 (bit 0: previous strip was exact with a
 // pending sequence, which forces this strip to be exact as well); 0 at string start
 DEVI Strip warp_load_strip(const uint8_t* s, int64_t base, int64_t n, uint32_t& carry) {
@@ -538,59 +546,51 @@ __device__ __noinline__ uint32_t esc_to_global(uint8_t* dstp, const uint8_t* s, 
 __device__ __noinline__ uint32_t esc_ascii_to_global(uint8_t* dstp, const uint8_t* s, uint32_t n) {
   DstG dst{dstp};
   const uint32_t l = lane_id();
+  const uint32_t M = 0x80808080u, L7 = 0x7F7F7F7Fu;
   uint32_t out = 0;
   for (uint32_t base = 0; base < n; base += 512) {
     const uint32_t p0 = base + 16u * l;
     const uint32_t nv = p0 >= n ? 0u : min(16u, n - p0);
-    // the lane's four words and their "holds a byte that needs escaping" flags; the two passes below walk
-    // them by rotating the vectors, so that the loop bodies exist once (instruction-cache footprint)
-    uint4 W = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u), O;
-    if (nv) W.x = ld_u32_unaligned(s + p0);
-    if (nv > 4) W.y = ld_u32_unaligned(s + p0 + 4);
-    if (nv > 8) W.z = ld_u32_unaligned(s + p0 + 8);
-    if (nv > 12) W.w = ld_u32_unaligned(s + p0 + 12);
-    uint32_t el = 0;
-#pragma unroll 1
+    uint32_t w[4];
+    uint32_t m2 = 0, m6 = 0;  // 16-bit masks: bytes that become 2 / 6 bytes (exact, branch-free: every lane of the
+                              // warp does the same work whether or not it holds such a byte)
+#pragma unroll
     for (uint32_t j = 0; j < 4; j++) {
       const uint32_t nj = nv > 4u * j ? min(4u, nv - 4u * j) : 0u;
-      uint32_t x = W.x;
+      uint32_t x = nj ? ld_u32_unaligned(s + p0 + 4u * j) : 0u;
       if (nj < 4) x = (x & ((1u << (8u * nj)) - 1u)) | (0x20202020u << (8u * nj));  // fill with spaces
-      const uint32_t odd = ((x - 0x20202020u) & ~x & 0x80808080u) | swar_has_byte(x, 0x22) | swar_has_byte(x, 0x5C) |
-                           swar_has_byte(x, 0x3C) | swar_has_byte(x, 0x3E) | swar_has_byte(x, 0x26);
-      if (!odd) {
-        el += nj;
-      } else {
-#pragma unroll
-        for (uint32_t k = 0; k < 4; k++) {
-          const uint32_t b = (x >> (8u * k)) & 0xFFu;
-          if (k < nj) el += b < 0x80 ? ascii_esc_len(b) : 1u;
-        }
-      }
-      W = make_uint4(W.y, W.z, W.w, x);
-      O = make_uint4(O.y, O.z, O.w, odd);
+      w[j] = x;
+      const uint32_t lo7 = x & L7;
+      const uint32_t ctl = ~(((lo7 + 0x60606060u) | x)) & M;                              // < 0x20
+      const uint32_t in8_13 = (lo7 + 0x78787878u) & ~(lo7 + 0x72727272u) & M;             // 0x08..0x0d (7-bit value)
+      const uint32_t sctl = ctl & in8_13 & ~swar_eq(x, 0x0B);                              // \b \t \n \f \r
+      const uint32_t s2 = sctl | swar_eq(x, 0x22) | swar_eq(x, 0x5C);
+      const uint32_t s6 = (ctl & ~sctl) | swar_eq(x, 0x3C) | swar_eq(x, 0x3E) | swar_eq(x, 0x26);
+      m2 |= swar_movemask(s2) << (4u * j);
+      m6 |= swar_movemask(s6) << (4u * j);
     }
+    const uint32_t el = nv + (uint32_t)__popc(m2) + 5u * (uint32_t)__popc(m6);
     const uint32_t incl = warp_incl_scan(el);
-    uint32_t d = out + incl - el;
-#pragma unroll 1
-    for (uint32_t j = 0; j < 4; j++) {
-      const uint32_t nj = nv > 4u * j ? min(4u, nv - 4u * j) : 0u;
-      const uint32_t x = W.x;
-      if (!O.x) {
+    const uint32_t d = out + incl - el;
+    const uint32_t sp = m2 | m6;
+    // plain bytes: byte k lands at d + k + (bytes inserted before it)
 #pragma unroll
-        for (uint32_t k = 0; k < 4; k++)
-          if (k < nj) dst.st(d + k, (x >> (8u * k)) & 0xFFu);
-        d += nj;
-      } else {
-#pragma unroll 1
-        for (uint32_t k = 0; k < nj; k++) {
-          const uint32_t b = (x >> (8u * k)) & 0xFFu;
-          const uint32_t len = b < 0x80 ? ascii_esc_len(b) : 1u;
-          put_escaped(dst, d, b, len);
-          d += len;
-        }
+    for (uint32_t k = 0; k < 16; k++) {
+      const uint32_t below = (1u << k) - 1u;
+      if (k < nv && !((sp >> k) & 1u))
+        dst.st(d + k + (uint32_t)__popc(m2 & below) + 5u * (uint32_t)__popc(m6 & below), (w[k >> 2] >> (8u * (k & 3u))) & 0xFFu);
+    }
+    // escaped bytes: one per lane and round
+    uint32_t todo = sp;
+    while (__any_sync(FULL, todo != 0)) {
+      if (todo) {
+        const uint32_t k = (uint32_t)__ffs(todo) - 1u;
+        todo &= todo - 1u;
+        const uint32_t below = (1u << k) - 1u;
+        const uint32_t wk = k < 4 ? w[0] : k < 8 ? w[1] : k < 12 ? w[2] : w[3];
+        put_escaped(dst, d + k + (uint32_t)__popc(m2 & below) + 5u * (uint32_t)__popc(m6 & below), (wk >> (8u * (k & 3u))) & 0xFFu,
+                    ((m2 >> k) & 1u) ? 2u : 6u);
       }
-      W = make_uint4(W.y, W.z, W.w, x);
-      O = make_uint4(O.y, O.z, O.w, O.x);
     }
     out += __shfl_sync(FULL, incl, 31);
   }

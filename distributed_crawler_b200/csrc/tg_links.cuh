@@ -91,13 +91,6 @@ DEVI uint32_t warp_word_run(const uint8_t* p, const uint8_t* end) {
   return m ? (uint32_t)(__ffs(m) - 1) : 32u;
 }
 
-// exact per-byte equality: bit 7 of every byte of w that equals c
-DEVI uint32_t swar_eq(uint32_t w, uint32_t c) {
-  const uint32_t x = w ^ (c * 0x01010101u);
-  return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
-}
-DEVI uint32_t swar_movemask(uint32_t m) { return (((m >> 7) & 0x01010101u) * 0x01020408u) >> 24; }  // bit 7s -> 4 bits
-
 // A strip for the link scan = 512 bytes, 16 per lane (no UTF-8 bookkeeping is needed to find "t.me/").
 // Returns the lane's 16-bit mask: bit k set if s[p0+k] is the '/' of a "t.me/" (p0 = base + 16*lane).
 // '/' is rare in message text, so almost every strip ends after four SWAR compares per lane.
