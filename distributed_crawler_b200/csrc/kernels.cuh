@@ -54,6 +54,7 @@ struct ParseOut {
   tgi_link* arena;
   uint32_t arena_cap;
   uint32_t* cursor;      // arena allocation cursor (keeps counting past arena_cap)
+  int2* ent_range;       // [n_ents] byte range of every mention / url entity (tg_ent_map_kernel)
   int* err;
 };
 
@@ -76,55 +77,93 @@ DEVI TgRecView load_rec_view(const TgBatchDev& b, uint64_t r) {
   return v;
 }
 
-// The parse step is two kernels so that each one's instruction footprint stays small (the B200
-// instruction caches are 6 KB L0 / 32 KB L1.5): tg_parse_kernel = status + link extraction,
-// tg_size_kernel = line length.  The text is read twice; both kernels are far below the HBM roofline.
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) {
-  int wid = threadIdx.x >> 5, l = lane_id();
-  uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
-  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
-    TgRecView v = load_rec_view(b, r);
-    uint32_t status = TGI_ST_EMITTED, nlinks = 0, lstart = 0;
-    if ((cfg.flags & TGI_CFG_HAS_MIN_POST_DATE) && (int64_t)v.rec->date < cfg.min_post_date) {
-      status = TGI_ST_SKIPPED;  // tdutils.go:419-421
-    } else if (v.flags & TGI_RF_PANIC) {
-      status = TGI_ST_FAILED;
-    } else {
-      if (b.react_off[r + 1] - b.react_off[r] > 32) {
-        if (l == 0) atomicOr(o.err, ERR_TOO_MANY_REACTIONS);
-      }
-      uint32_t ub = warp_link_upper_bound(v, b.ents);
-      if (ub > 4096) {  // seq packing of the frontier needs ordinal < 4096
-        if (l == 0) atomicOr(o.err, ERR_TOO_MANY_LINKS);
-        ub = 0;
-      }
-      if (ub) {
-        if (l == 0) lstart = atomicAdd(o.cursor, ub);
-        lstart = __shfl_sync(FULL, lstart, 0);
-        if (lstart + ub > o.arena_cap || lstart + ub < lstart) {
-          if (l == 0) atomicOr(o.err, ERR_ARENA_OVERFLOW);
-        } else {
-          const tgi_tg_chan* ch = &b.chans[v.rec->chan_idx];
-          LinkSink ls;
-          ls.out = o.arena + lstart;
-          ls.cap = ub;
-          ls.count = 0;
-          ls.self = b.chan_strs + ch->str_off + ch->title_len;
-          ls.self_len = ch->name_len;
-          bool ok = warp_extract_links(v, b.ents, b.aux, ls);
-          nlinks = ls.count;
-          if (!ok) {
-            status = TGI_ST_FAILED;
-            nlinks = 0;
-          }
+// One record.  ENTITIES == false: the record has no entities, so the whole UTF-16 offset machinery
+// (warp_utf16_to_bytes, the exact UTF-8 path) is compiled out.
+template <bool ENTITIES>
+DEVI void parse_one_record(const TgBatchDev& b, const CfgDev& cfg, const ParseOut& o, uint64_t r, TgRecView v) {
+  const int l = lane_id();
+  uint32_t status = TGI_ST_EMITTED, nlinks = 0, lstart = 0;
+  if ((cfg.flags & TGI_CFG_HAS_MIN_POST_DATE) && (int64_t)v.rec->date < cfg.min_post_date) {
+    status = TGI_ST_SKIPPED;  // tdutils.go:419-421
+  } else if (v.flags & TGI_RF_PANIC) {
+    status = TGI_ST_FAILED;
+  } else {
+    if (b.react_off[r + 1] - b.react_off[r] > 32) {
+      if (l == 0) atomicOr(o.err, ERR_TOO_MANY_REACTIONS);
+    }
+    if (!ENTITIES) v.e1 = v.e0;
+    uint32_t ub = warp_link_upper_bound(v, b.ents);
+    if (ub > 4096) {  // seq packing of the frontier needs ordinal < 4096
+      if (l == 0) atomicOr(o.err, ERR_TOO_MANY_LINKS);
+      ub = 0;
+    }
+    if (ub) {
+      if (l == 0) lstart = atomicAdd(o.cursor, ub);
+      lstart = __shfl_sync(FULL, lstart, 0);
+      if (lstart + ub > o.arena_cap || lstart + ub < lstart) {
+        if (l == 0) atomicOr(o.err, ERR_ARENA_OVERFLOW);
+      } else {
+        const tgi_tg_chan* ch = &b.chans[v.rec->chan_idx];
+        LinkSink ls;
+        ls.out = o.arena + lstart;
+        ls.cap = ub;
+        ls.count = 0;
+        ls.self = b.chan_strs + ch->str_off + ch->title_len;
+        ls.self_len = ch->name_len;
+        bool ok = warp_extract_links(v, b.ents, b.aux, o.ent_range, ls);
+        nlinks = ls.count;
+        if (!ok) {
+          status = TGI_ST_FAILED;
+          nlinks = 0;
         }
       }
     }
-    if (l == 0) {
-      o.status[r] = (uint8_t)status;
-      o.linelen[r] = 0;
-      o.link_start[r] = lstart;
-      o.link_count[r] = nlinks;
+  }
+  if (l == 0) {
+    o.status[r] = (uint8_t)status;
+    o.linelen[r] = 0;
+    o.link_start[r] = lstart;
+    o.link_count[r] = nlinks;
+  }
+}
+
+// The parse step is split by instruction footprint (the B200 instruction caches are 6 KB L0 / 32 KB L1.5):
+// tg_parse_kernel = status + links of the records WITHOUT entities (three quarters of the corpus; small code),
+// tg_ent_map_kernel = UTF-16 entity offsets -> byte ranges, tg_parse_ent_kernel = links of the records with
+// entities (lanes pick them out of groups of 32),
+// tg_size_lane_kernel = line lengths.  With everything in one parse kernel (2 560 SASS instructions) ncu
+// showed 3.5 stall_no_instruction cycles per issue.
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) {
+  int wid = threadIdx.x >> 5;
+  uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
+    if (b.ent_off[r + 1] != b.ent_off[r]) continue;  // tg_parse_ent_kernel
+    parse_one_record<false>(b, cfg, o, r, load_rec_view(b, r));
+  }
+}
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_ent_map_kernel(TgBatchDev b, ParseOut o) {
+  const int wid = threadIdx.x >> 5, l = lane_id();
+  const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
+    const uint64_t rl = g * 32 + l;
+    uint32_t todo = __ballot_sync(FULL, rl < b.n && b.ent_off[rl + 1] != b.ent_off[rl]);
+    while (todo) {
+      const uint64_t r = g * 32 + (uint32_t)(__ffs(todo) - 1);
+      todo &= todo - 1;
+      warp_map_entities(load_rec_view(b, r), b.ents, o.ent_range);
+    }
+  }
+}
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_ent_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) {
+  const int wid = threadIdx.x >> 5, l = lane_id();
+  const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
+    const uint64_t rl = g * 32 + l;
+    uint32_t todo = __ballot_sync(FULL, rl < b.n && b.ent_off[rl + 1] != b.ent_off[rl]);
+    while (todo) {
+      const uint64_t r = g * 32 + (uint32_t)(__ffs(todo) - 1);
+      todo &= todo - 1;
+      parse_one_record<true>(b, cfg, o, r, load_rec_view(b, r));
     }
   }
 }

@@ -94,20 +94,24 @@ DEVI uint32_t warp_word_run(const uint8_t* p, const uint8_t* end) {
 // A strip for the link scan = 512 bytes, 16 per lane (no UTF-8 bookkeeping is needed to find "t.me/").
 // Returns the lane's 16-bit mask: bit k set if s[p0+k] is the '/' of a "t.me/" (p0 = base + 16*lane).
 // '/' is rare in message text, so almost every strip ends after four SWAR compares per lane.
-DEVI uint32_t strip16_tme(const uint8_t* s, int64_t base, int64_t n) {
-  const int64_t p0 = base + 16 * lane_id();
-  if (p0 >= n) return 0;
-  const uint8_t* q = s + p0;  // every lane has the same misalignment: two aligned 16-byte loads + one funnel
+// the lane's 16 bytes s[p0 .. p0+16) as four little-endian words (p0 = base + 16*lane; every lane has the same
+// misalignment: two aligned 16-byte loads + one funnel; the blob padding covers the over-read)
+DEVI uint4 load16_lane(const uint8_t* q) {
   const uint32_t sa = (uint32_t)(uintptr_t)q & 15u, sh = (sa & 3u) * 8u, qw = sa >> 2;
-  const uint4 a = __ldg((const uint4*)(q - sa)), c = __ldg((const uint4*)(q - sa) + 1);  // blob padding covers the over-read
+  const uint4 a = __ldg((const uint4*)(q - sa)), c = __ldg((const uint4*)(q - sa) + 1);
   uint32_t v0, v1, v2, v3, v4;
   if (qw == 0) { v0 = a.x; v1 = a.y; v2 = a.z; v3 = a.w; v4 = c.x; }
   else if (qw == 1) { v0 = a.y; v1 = a.z; v2 = a.w; v3 = c.x; v4 = c.y; }
   else if (qw == 2) { v0 = a.z; v1 = a.w; v2 = c.x; v3 = c.y; v4 = c.z; }
   else { v0 = a.w; v1 = c.x; v2 = c.y; v3 = c.z; v4 = c.w; }
-  const uint32_t w0 = __funnelshift_r(v0, v1, sh), w1 = __funnelshift_r(v1, v2, sh), w2 = __funnelshift_r(v2, v3, sh),
-                 w3 = __funnelshift_r(v3, v4, sh);
-  const uint32_t s0 = swar_eq(w0, '/'), s1 = swar_eq(w1, '/'), s2 = swar_eq(w2, '/'), s3 = swar_eq(w3, '/');
+  return make_uint4(__funnelshift_r(v0, v1, sh), __funnelshift_r(v1, v2, sh), __funnelshift_r(v2, v3, sh), __funnelshift_r(v3, v4, sh));
+}
+DEVI uint32_t strip16_tme(const uint8_t* s, int64_t base, int64_t n) {
+  const int64_t p0 = base + 16 * lane_id();
+  if (p0 >= n) return 0;
+  const uint8_t* q = s + p0;
+  const uint4 w = load16_lane(q);
+  const uint32_t s0 = swar_eq(w.x, '/'), s1 = swar_eq(w.y, '/'), s2 = swar_eq(w.z, '/'), s3 = swar_eq(w.w, '/');
   if (!(s0 | s1 | s2 | s3)) return 0;
   uint32_t m = swar_movemask(s0) | (swar_movemask(s1) << 4) | (swar_movemask(s2) << 8) | (swar_movemask(s3) << 12);
   const int64_t rem = n - p0;
@@ -119,6 +123,27 @@ DEVI uint32_t strip16_tme(const uint8_t* s, int64_t base, int64_t n) {
     if (p0 + k >= 4 && ld_u32_unaligned(q + k - 4) == 0x656D2E74u) out |= 1u << k;  // "t.me"
   }
   return out;
+}
+
+// index of the first byte >= 0x80 of s[0..n), n if there is none.  In front of it UTF-16 offsets are byte offsets.
+DEVI int64_t warp_first_non_ascii(const uint8_t* s, int64_t n) {
+  for (int64_t base = 0; base < n; base += 512) {
+    const int64_t p0 = base + 16 * lane_id();
+    uint32_t m = 0;
+    if (p0 < n) {
+      const uint4 w = load16_lane(s + p0);
+      m = swar_movemask(w.x & 0x80808080u) | (swar_movemask(w.y & 0x80808080u) << 4) | (swar_movemask(w.z & 0x80808080u) << 8) |
+          (swar_movemask(w.w & 0x80808080u) << 12);
+      const int64_t rem = n - p0;
+      if (rem < 16) m &= (1u << rem) - 1u;
+    }
+    const uint32_t lanes = __ballot_sync(FULL, m != 0);
+    if (lanes) {
+      const int src = __ffs(lanes) - 1;
+      return base + 16 * src + (__ffs(__shfl_sync(FULL, m, src)) - 1);
+    }
+  }
+  return n;
 }
 
 // number of "t.me/" occurrences in s[0..n): upper bound on plaintext matches
@@ -254,16 +279,40 @@ DEVI uint32_t warp_link_upper_bound(const TgRecView& v, const tgi_entity* ents) 
   return warp_sum(c) + warp_count_tme(v.text, v.text_len);
 }
 
-// returns false if the reference would panic (record FAILED)
-DEVI bool warp_extract_links(const TgRecView& v, const tgi_entity* ents, const uint8_t* aux, LinkSink& ls) {
+// utf16OffsetToBytes for every mention / url entity of the record -> ranges[e - v.e0... absolute e] = (start, end)
+// (tg_ent_map_kernel; a kernel of its own so that the UTF-8 machinery and the link scan never share an
+// instruction cache: profiles/README.md)
+DEVI void warp_map_entities(const TgRecView& v, const tgi_entity* ents, int2* ranges) {
+  if (!ct_carries_links(v.ct) || !(v.flags & TGI_RF_HAS_TEXT)) return;
+  int64_t ascii_prefix = -1;  // computed when the first offset has to be mapped
+  for (uint32_t e = v.e0; e < v.e1; e++) {
+    const tgi_entity en = ents[e];
+    if (en.type != TGI_ENT_MENTION && en.type != TGI_ENT_URL) continue;
+    int64_t st, en_;
+    if (ascii_prefix < 0) ascii_prefix = warp_first_non_ascii(v.text, v.text_len);
+    const int64_t stop = (int64_t)en.offset + (int64_t)en.length;
+    if (en.offset >= 0 && en.length >= 0 && stop <= ascii_prefix) {
+      // every rune before `stop` is one byte and one UTF-16 unit: utf16OffsetToBytes returns (offset, stop)
+      // (stop == len(text) comes out of its after-the-loop fallback with the same values)
+      st = en.offset;
+      en_ = stop;
+    } else {
+      warp_utf16_to_bytes(v.text, v.text_len, en.offset, en.length, st, en_);
+    }
+    if (lane_id() == 0) ranges[e] = make_int2((int)st, (int)en_);  // texts are < 2^31 bytes; st may be -1
+  }
+}
+
+// returns false if the reference would panic (record FAILED).  ranges: warp_map_entities' output
+DEVI bool warp_extract_links(const TgRecView& v, const tgi_entity* ents, const uint8_t* aux, const int2* ranges, LinkSink& ls) {
   if (!ct_carries_links(v.ct) || !(v.flags & TGI_RF_HAS_TEXT)) return true;
   for (uint32_t e = v.e0; e < v.e1; e++) {
     tgi_entity en = ents[e];
     if (en.type == TGI_ENT_TEXT_URL) {
       warp_scan_channel_links(ls, aux + en.url_off, en.url_len, TGI_SRC_TEXT_URL, false);
     } else if (en.type == TGI_ENT_MENTION || en.type == TGI_ENT_URL) {
-      int64_t st, en_;
-      warp_utf16_to_bytes(v.text, v.text_len, en.offset, en.length, st, en_);
+      const int2 rg = ranges[e];
+      const int64_t st = rg.x, en_ = rg.y;
       if (st < en_ && en_ <= (int64_t)v.text_len) {
         if (st < 0) return false;
         if (en.type == TGI_ENT_MENTION) warp_scan_username(ls, v.text + st, en_ - st);

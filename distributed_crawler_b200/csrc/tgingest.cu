@@ -76,7 +76,7 @@ struct Slot {
   // device intermediates / outputs
   DevBuf d_chan_derived, d_chan_len, d_chan_off, d_chan_blob, d_status, d_linelen, d_line_off,
       d_link_start, d_link_count, d_xlen, d_xpos, d_arena, d_lstate, d_rec_new, d_new_off, d_link_off, d_links_out,
-      d_link_off32, d_btable, d_tiles, d_scalars, d_jsonl, d_url_start, d_url_count, d_urls;
+      d_link_off32, d_btable, d_tiles, d_scalars, d_jsonl, d_url_start, d_url_count, d_urls, d_ent_range;
   // pinned host outputs
   HostBuf h_status, h_line_off, h_jsonl, h_link_off, h_links, h_scalars;
   // resident batch descriptor
@@ -514,12 +514,20 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     po.arena_cap = (uint32_t)arena_cap;
     po.cursor = (uint32_t*)(dsc + SC_CURSOR);
     po.err = (int*)(dsc + SC_CURSOR) + 1;
+    CK(s.d_ent_range.ensure((size_t)s.n_ents * sizeof(int2)));
+    po.ent_range = s.d_ent_range.as<int2>();
     if (n) {
       uint64_t want = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
       unsigned g = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms * 8);
       CK(cudaEventRecord(s.ev_p0, st));
       tg_parse_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
-      launches++;
+      {
+        const uint64_t groups = (n + 31) / 32;
+        unsigned ge = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
+        tg_ent_map_kernel<<<ge, CTA_THREADS, 0, st>>>(b, po);
+        tg_parse_ent_kernel<<<ge, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
+      }
+      launches += 3;
       if (want_json) {
         static const bool warp_size = getenv("TGI_SIZE_WARP") != nullptr;  // A/B switch: one warp per record
         if (warp_size) {
@@ -963,7 +971,7 @@ void tgi_destroy(tgi_ctx* c) {
                     &s.d_chan_off, &s.d_chan_blob, &s.d_status, &s.d_linelen, &s.d_line_off, &s.d_link_start,
                     &s.d_link_count, &s.d_xlen, &s.d_xpos, &s.d_arena, &s.d_lstate, &s.d_rec_new, &s.d_new_off, &s.d_link_off,
                     &s.d_links_out, &s.d_link_off32, &s.d_btable, &s.d_tiles, &s.d_scalars, &s.d_jsonl,
-                    &s.d_url_start, &s.d_url_count, &s.d_urls};
+                    &s.d_url_start, &s.d_url_count, &s.d_urls, &s.d_ent_range};
     for (DevBuf* d : db) d->release();
     HostBuf* hb[] = {&s.h_status, &s.h_line_off, &s.h_jsonl, &s.h_link_off, &s.h_links, &s.h_scalars};
     for (HostBuf* h : hb) h->release();
