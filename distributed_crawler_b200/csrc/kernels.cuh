@@ -10,6 +10,7 @@
 #include "tg_lane.cuh"
 #include "yt_walk.cuh"
 #include "gm_walk.cuh"
+#include "yt_lane.cuh"
 
 namespace tgi {
 
@@ -481,6 +482,7 @@ struct YtOut {
   YtUrl* urls;
   uint32_t urls_cap;
   uint32_t* url_cursor;
+  uint32_t* esc_len;     // [n][3] escaped length of the description / title, clean flag (size pass -> emit pass)
   uint32_t* link_start;  // [n] channel-id links (frontier candidates)
   uint32_t* link_count;
   tgi_link* arena;
@@ -557,31 +559,72 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) yt_size_kernel(YtBatchDev b, C
     a.n_urls = o.url_count[r];
     YtSizer z;
     z.sc = &scs[wid];
+    {
+      const tgi_yt_rec* rec = &b.recs[r];
+      const uint8_t* title = b.strs + rec->str_off + rec->id_len;
+      z.el[1] = warp_esc_len(title, rec->title_len);
+      z.el[0] = warp_esc_len(title + rec->title_len, rec->desc_len);
+    }
     bool ok = walk_yt_record(z, a);
     if (l == 0) {
+      o.esc_len[3 * r] = z.el[0];
+      o.esc_len[3 * r + 1] = z.el[1];
+      o.esc_len[3 * r + 2] = z.dirty ? 0u : 1u;  // clean: the lane writer takes the record
       o.linelen[r] = ok ? (uint32_t)z.total : 0u;
       if (!ok) o.status[r] = TGI_ST_NOLINE;
     }
   }
 }
 
-__global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_kernel(YtBatchDev b, CfgDev cfg, YtOut o, const uint64_t* line_off, uint8_t* out, int* err) {
+// warp writer: the records the lane writer does not take (a string needs escaping); lanes pick them out of
+// groups of 32.  lane_mode == 0: every record (A/B reference, TGI_YT_WARP=1).
+__global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_kernel(YtBatchDev b, CfgDev cfg, YtOut o, const uint64_t* line_off, uint8_t* out, int* err,
+                                                                 int lane_mode) {
   __shared__ YtScratch scs[WARPS_PER_CTA];
   int wid = threadIdx.x >> 5, l = lane_id();
-  uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
-  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
-    if (o.status[r] != TGI_ST_EMITTED) continue;
+  const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
+    const uint64_t rl = g * 32 + l;
+    uint32_t todo = __ballot_sync(FULL, rl < b.n && o.status[rl] == TGI_ST_EMITTED && !(lane_mode && o.esc_len[3 * rl + 2]));
+    while (todo) {
+      const uint64_t r = g * 32 + (uint32_t)(__ffs(todo) - 1);
+      todo &= todo - 1;
+      YtArgs a;
+      a.b = &b;
+      a.cfg = &cfg;
+      a.r = r;
+      a.urls = o.urls + o.url_start[r];
+      a.n_urls = o.url_count[r];
+      YtWriter w;
+      w.sc = &scs[wid];
+      w.el[0] = o.esc_len[3 * r];
+      w.el[1] = o.esc_len[3 * r + 1];
+      w.p = out + line_off[r];
+      walk_yt_record(w, a);
+      if (l == 0 && (uint64_t)(w.p - out) != line_off[r + 1]) atomicOr(err, 16);
+      __syncwarp();
+    }
+  }
+}
+
+// lane writer (yt_lane.cuh): one lane per clean record
+__global__ void __launch_bounds__(CTA_THREADS, 2) yt_emit_lane_kernel(YtBatchDev b, CfgDev cfg, YtOut o, const uint64_t* line_off, uint8_t* out, int* err) {
+  const int wid = threadIdx.x >> 5, l = lane_id();
+  const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
+    const uint64_t r = g * 32 + l;
+    if (r >= b.n || o.status[r] != TGI_ST_EMITTED || !o.esc_len[3 * r + 2]) continue;
     YtArgs a;
     a.b = &b;
     a.cfg = &cfg;
     a.r = r;
     a.urls = o.urls + o.url_start[r];
     a.n_urls = o.url_count[r];
-    YtWriter w;
-    w.sc = &scs[wid];
-    w.p = out + line_off[r];
+    YtLaneWriter w;
+    w.begin((uint64_t)(uintptr_t)out + line_off[r]);
     walk_yt_record(w, a);
-    if (l == 0 && (uint64_t)(w.p - out) != line_off[r + 1]) atomicOr(err, 16);
+    w.end();
+    if (w.s.pos != (uint64_t)(uintptr_t)out + line_off[r + 1]) atomicOr(err, 16);
   }
 }
 

@@ -678,6 +678,8 @@ int run_yt(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   YtOut yo;
   yo.status = s.d_status.as<uint8_t>();
   yo.linelen = s.d_linelen.as<uint32_t>();
+  CK(s.d_xlen.ensure(n * 12));
+  yo.esc_len = s.d_xlen.as<uint32_t>();
   yo.url_start = s.d_url_start.as<uint32_t>();
   yo.url_count = s.d_url_count.as<uint32_t>();
   yo.urls = s.d_urls.as<YtUrl>();
@@ -720,7 +722,14 @@ int run_yt(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     CK(s.d_jsonl.ensure(line_total));
     if (n) {
       CK(cudaEventRecord(s.ev_e0, st));
-      yt_emit_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, yo, s.d_line_off.as<uint64_t>(), s.d_jsonl.as<uint8_t>(), yo.err);
+      static const bool yt_warp = getenv("TGI_YT_WARP") != nullptr;  // A/B switch: the warp writer for every record
+      const uint64_t groups = (n + 31) / 32;
+      unsigned gg = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
+      if (!yt_warp) {
+        yt_emit_lane_kernel<<<gg, CTA_THREADS, 0, st>>>(b, cfg, yo, s.d_line_off.as<uint64_t>(), s.d_jsonl.as<uint8_t>(), yo.err);
+        launches++;
+      }
+      yt_emit_kernel<<<gg, CTA_THREADS, 0, st>>>(b, cfg, yo, s.d_line_off.as<uint64_t>(), s.d_jsonl.as<uint8_t>(), yo.err, yt_warp ? 0 : 1);
       CK(cudaEventRecord(s.ev_f1, st));
       CK(cudaEventRecord(s.ev_e1, st));
       launches++;

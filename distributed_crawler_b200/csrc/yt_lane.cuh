@@ -1,0 +1,94 @@
+// yt_lane.cuh — one lane per record for the YouTube line (records whose strings need no escaping).
+//
+// The line is the templated walk of yt_walk.cuh, instantiated with a writer that streams the lane's own
+// line: same byte-stream packing as tg_lane.cuh (16-byte blocks, byte-exact stores where a block is shared
+// with the neighbouring line), but the blocks are stored directly (ST.128 from the lane) and nothing in the
+// writer is warp-collective, so the walk's per-record branches and loops (cached channel or not, 0-5
+// thumbnails, n outlinks) may diverge freely between the lanes.  Records with a string that needs escaping
+// are left to the warp writer (yt_emit_kernel), which visits only those.
+#pragma once
+#include "tg_lane.cuh"
+#include "yt_walk.cuh"
+
+namespace tgi {
+
+struct LaneDirect {
+  uint64_t pos;             // absolute address of the next output byte
+  uint32_t c0, c1, c2, c3;  // bytes [head, pos & 15) of the current block, zero elsewhere
+  uint32_t head;            // first byte of the current block that belongs to this stream
+};
+
+// append bytes [0, n) of src (any address space, any alignment; the 16-byte blocks around it must be readable)
+__device__ __noinline__ void ld_copy(LaneDirect* sp, const uint8_t* src, uint32_t n) {
+  if (!n) return;
+  LaneDirect s = *sp;
+  const uint32_t s0 = (uint32_t)(uintptr_t)src & 15u;
+  const uint4* A = (const uint4*)(src - s0);
+  uint32_t rem = n, first = s0;
+  while (rem) {
+    uint4 w = *A++;
+    if (first) w = shr128_bytes(w, first);
+    const uint32_t k = min(rem, 16u - first);
+    if (k < 16u) w = mask128(w, k);
+    rem -= k;
+    first = 0;
+    // place the block at the stream's phase (ls_append, tg_lane.cuh)
+    const uint32_t ph = (uint32_t)s.pos & 15u, sh = (ph & 3u) * 8u;
+    const uint32_t v0 = w.x << sh, v1 = __funnelshift_l(w.x, w.y, sh), v2 = __funnelshift_l(w.y, w.z, sh),
+                   v3 = __funnelshift_l(w.z, w.w, sh), v4 = __funnelshift_l(w.w, 0u, sh);
+    const bool b0 = (ph & 4u) != 0, b1 = (ph & 8u) != 0;
+    const uint32_t z0 = b0 ? 0u : v0, z1 = b0 ? v0 : v1, z2 = b0 ? v1 : v2, z3 = b0 ? v2 : v3, z4 = b0 ? v3 : v4,
+                   z5 = b0 ? v4 : 0u;
+    s.c0 |= b1 ? 0u : z0;
+    s.c1 |= b1 ? 0u : z1;
+    s.c2 |= b1 ? z0 : z2;
+    s.c3 |= b1 ? z1 : z3;
+    if (ph + k >= 16u) {
+      const uint64_t blk = s.pos & ~15ull;
+      if (s.head == 0) {
+        *(uint4*)(uintptr_t)blk = make_uint4(s.c0, s.c1, s.c2, s.c3);
+      } else {
+        store_bytes(blk, s.c0, s.c1, s.c2, s.c3, s.head, 16u);
+        s.head = 0;
+      }
+      s.c0 = b1 ? z2 : z4;
+      s.c1 = b1 ? z3 : z5;
+      s.c2 = b1 ? z4 : 0u;
+      s.c3 = b1 ? z5 : 0u;
+    }
+    s.pos += k;
+  }
+  *sp = s;
+}
+
+struct YtLaneWriter {
+  static constexpr bool kLane = true;
+  LaneDirect s;
+  uint32_t el[2];               // unused (clean records only)
+  __align__(16) uint8_t num[64];  // number / time / file-name rendering
+  DEVI void begin(uint64_t addr) {
+    s.pos = addr;
+    s.head = (uint32_t)addr & 15u;
+    s.c0 = s.c1 = s.c2 = s.c3 = 0;
+  }
+  DEVI void end() {  // what the last block holds
+    const uint32_t ph = (uint32_t)s.pos & 15u;
+    if (ph > s.head) store_bytes(s.pos & ~15ull, s.c0, s.c1, s.c2, s.c3, s.head, ph);
+  }
+  DEVI void raw(const uint8_t* p, uint32_t n) { ld_copy(&s, p, n); }
+  DEVI void esc(const uint8_t* p, uint32_t n) { ld_copy(&s, p, n); }  // nothing to escape on this path
+  DEVI void esc_slot(int, const uint8_t* p, uint32_t n) { ld_copy(&s, p, n); }
+  DEVI void ch(uint32_t c) {
+    num[0] = (uint8_t)c;
+    ld_copy(&s, num, 1);
+  }
+  DEVI void dec(int64_t v) { ld_copy(&s, num, (uint32_t)render_i64(num, v)); }
+  DEVI void smem(uint32_t n) { ld_copy(&s, num, n); }
+  DEVI uint32_t time_len(int64_t sec, int32_t nsec) { return (uint32_t)render_time(num, sec, nsec, 0); }
+  DEVI void time(int64_t sec, int32_t nsec) { ld_copy(&s, num, (uint32_t)render_time(num, sec, nsec, 0)); }
+  DEVI void fviews(int64_t v) { ld_copy(&s, num, (uint32_t)yt_render_float_of_int64(num, v)); }
+  DEVI void sanitized(const uint8_t* t, uint32_t tn) { ld_copy(&s, num, yt_sanitize(t, tn, num)); }
+  DEVI bool duration(const uint8_t* d, uint32_t dn, int64_t& vlen) { return yt_parse_duration(d, dn, vlen); }
+};
+
+}  // namespace tgi

@@ -26,10 +26,10 @@ struct YtUrl {  // one unique URL of a description (extractURLs), offsets into t
   uint32_t off, len;
 };
 
-#define YLIT(w, str)                               \
-  do {                                             \
-    static __device__ const char _lit[] = str;     \
-    (w).raw((const uint8_t*)_lit, sizeof(_lit) - 1); \
+#define YLIT(w, str)                                                                           \
+  do { /* 16-byte aligned and zero padded: the lane writer fetches literals in 16-byte blocks */  \
+    static __device__ __align__(16) const char _lit[(sizeof(str) + 15) / 16 * 16] = str;          \
+    (w).raw((const uint8_t*)_lit, sizeof(str) - 1);                                                \
   } while (0)
 
 struct YtScratch {
@@ -37,35 +37,119 @@ struct YtScratch {
 };
 
 // ---- writers ------------------------------------------------------------------------------------------
+__device__ __noinline__ bool yt_parse_duration(const uint8_t* s, uint32_t n, int64_t& seconds);
+__device__ __noinline__ int yt_render_float_of_int64(uint8_t* dst, int64_t v);
+__device__ __noinline__ uint32_t yt_sanitize(const uint8_t* s, uint32_t n, uint8_t* dst);
+// The walk is instantiated twice (sizer / writer) and every call below appears ~150 times in it: the
+// byte movers are free __noinline__ functions so that the walk stays a few thousand instructions.
+__device__ __noinline__ void yt_copy(uint8_t* p, const uint8_t* s, uint32_t n) {
+  if (n >= 48) warp_copy_vec(p, s, n);
+  else gcopy_g(p, s, n);
+}
+__device__ __noinline__ uint32_t yt_put_dec(uint8_t* p, uint8_t* scratch, int64_t v) {
+  uint32_t n = 0;
+  __syncwarp();
+  if (lane_id() == 0) n = (uint32_t)render_i64(scratch, v);
+  __syncwarp();
+  n = __shfl_sync(FULL, n, 0);
+  gcopy_s(p, smem_addr(scratch), n);
+  __syncwarp();
+  return n;
+}
+__device__ __noinline__ uint32_t yt_ndigits(int64_t v) { return ndigits_i64(v); }
+// warp-mode helpers shared by the sizer and the warp writer: lane 0 renders into sc->num, everybody learns the length
+DEVI uint32_t yt_warp_time(YtScratch* sc, int64_t sec, int32_t nsec) {
+  uint32_t n = 0;
+  __syncwarp();
+  if (lane_id() == 0) n = (uint32_t)render_time(sc->num, sec, nsec, 0);
+  __syncwarp();
+  return __shfl_sync(FULL, n, 0);
+}
 struct YtSizer {
+  static constexpr bool kLane = false;
   uint64_t total = 0;
   YtScratch* sc;
+  uint32_t el[2];  // escaped lengths of the description / the title (each is written several times)
+  bool dirty = false;  // some string needs escaping: the record is left to the warp writer
+  DEVI uint32_t time_len(int64_t sec, int32_t nsec) { return yt_warp_time(sc, sec, nsec); }
+  DEVI void time(int64_t sec, int32_t nsec) { total += yt_warp_time(sc, sec, nsec); }
+  DEVI void fviews(int64_t v) {
+    uint32_t n = 0;
+    if (lane_id() == 0) n = (uint32_t)yt_render_float_of_int64(sc->num, v);
+    total += __shfl_sync(FULL, n, 0);
+    __syncwarp();
+  }
+  DEVI void sanitized(const uint8_t* t, uint32_t tn) {
+    uint32_t n = 0;
+    if (lane_id() == 0) n = yt_sanitize(t, tn, sc->num);
+    total += __shfl_sync(FULL, n, 0);
+    __syncwarp();
+  }
+  DEVI bool duration(const uint8_t* d, uint32_t dn, int64_t& vlen) {
+    int ok = 0;
+    if (lane_id() == 0) ok = yt_parse_duration(d, dn, vlen) ? 1 : 0;
+    vlen = __shfl_sync(FULL, vlen, 0);
+    return __shfl_sync(FULL, ok, 0) != 0;
+  }
   DEVI void raw(const uint8_t*, uint32_t n) { total += n; }
-  DEVI void esc(const uint8_t* s, uint32_t n) { total += warp_esc_len(s, n); }
+  DEVI void esc(const uint8_t* s, uint32_t n) {
+    const uint32_t e = warp_esc_len(s, n);
+    dirty = dirty || e != n;
+    total += e;
+  }
+  DEVI void esc_slot(int k, const uint8_t*, uint32_t n) {
+    dirty = dirty || el[k] != n;
+    total += el[k];
+  }
   DEVI void ch(uint32_t) { total += 1; }
-  DEVI void dec(int64_t v) { total += ndigits_i64(v); }
+  DEVI void dec(int64_t v) { total += yt_ndigits(v); }
   DEVI void smem(uint32_t n) { total += n; }
 };
 struct YtWriter {
+  static constexpr bool kLane = false;
   uint8_t* p;
   YtScratch* sc;
+  uint32_t el[2];  // from the size pass
+  DEVI uint32_t time_len(int64_t sec, int32_t nsec) { return yt_warp_time(sc, sec, nsec); }
+  DEVI void time(int64_t sec, int32_t nsec) { smem(yt_warp_time(sc, sec, nsec)); }
+  DEVI void fviews(int64_t v) {
+    uint32_t n = 0;
+    __syncwarp();
+    if (lane_id() == 0) n = (uint32_t)yt_render_float_of_int64(sc->num, v);
+    __syncwarp();
+    smem(__shfl_sync(FULL, n, 0));
+  }
+  DEVI void sanitized(const uint8_t* t, uint32_t tn) {
+    uint32_t n = 0;
+    __syncwarp();
+    if (lane_id() == 0) n = yt_sanitize(t, tn, sc->num);
+    __syncwarp();
+    smem(__shfl_sync(FULL, n, 0));
+  }
+  DEVI bool duration(const uint8_t* d, uint32_t dn, int64_t& vlen) {
+    int ok = 0;
+    if (lane_id() == 0) ok = yt_parse_duration(d, dn, vlen) ? 1 : 0;
+    vlen = __shfl_sync(FULL, vlen, 0);
+    return __shfl_sync(FULL, ok, 0) != 0;
+  }
   DEVI void raw(const uint8_t* s, uint32_t n) {
-    gcopy_g(p, s, n);
+    yt_copy(p, s, n);
     p += n;
   }
   DEVI void esc(const uint8_t* s, uint32_t n) { p += esc_to_global(p, s, n); }
+  DEVI void esc_slot(int k, const uint8_t* s, uint32_t n) {  // nothing to escape: plain copy
+    if (el[k] == n) {
+      yt_copy(p, s, n);
+      p += n;
+    } else {
+      p += esc_to_global(p, s, n);
+    }
+  }
   DEVI void ch(uint32_t c) {
     gput1(p, c);
     p += 1;
   }
-  DEVI void dec(int64_t v) {
-    uint32_t n = 0;
-    __syncwarp();
-    if (lane_id() == 0) n = (uint32_t)render_i64(sc->num, v);
-    __syncwarp();
-    n = __shfl_sync(FULL, n, 0);
-    smem(n);
-  }
+  DEVI void dec(int64_t v) { p += yt_put_dec(p, sc->num, v); }
   DEVI void smem(uint32_t n) {  // n bytes already rendered in sc->num
     gcopy_s(p, smem_addr(sc->num), n);
     p += n;
@@ -88,7 +172,7 @@ DEVI int64_t yt_atoi_clamp(const uint8_t* s, uint32_t n) {
   return (int64_t)v;
 }
 // parseISO8601Duration (:461-486): ^P(?:(\d+)D)?(?:T(?:(\d+)H)?(?:(\d+)M)?(?:(\d+)S)?)?$ ; single thread
-DEVI bool yt_parse_duration(const uint8_t* s, uint32_t n, int64_t& seconds) {
+__device__ __noinline__ bool yt_parse_duration(const uint8_t* s, uint32_t n, int64_t& seconds) {
   uint32_t i = 0;
   uint64_t total = 0;  // Go int arithmetic wraps
   if (i >= n || ldb(s + i) != 'P') return false;
@@ -121,7 +205,7 @@ DEVI bool yt_parse_duration(const uint8_t* s, uint32_t n, int64_t& seconds) {
 // strconv.FormatFloat(float64(v), 'f', -1, 64): shortest decimal that round-trips, positional.
 // Integers below 2^53 print exactly; above, the shortest digit string inside the rounding interval of
 // the nearest double (closest to it), padded with zeros.  Single thread; returns the length.
-DEVI int yt_render_float_of_int64(uint8_t* dst, int64_t v) {
+__device__ __noinline__ int yt_render_float_of_int64(uint8_t* dst, int64_t v) {
   int o = 0;
   uint64_t a = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
   if (v < 0) dst[o++] = '-';
@@ -156,7 +240,7 @@ DEVI int yt_render_float_of_int64(uint8_t* dst, int64_t v) {
 
 // sanitizeFilename (:516-527): every rune outside [0-9A-Za-z_\-.] -> '_', truncated to 50 bytes.
 // Single thread, output into dst (<= 50 bytes); returns the length.
-DEVI uint32_t yt_sanitize(const uint8_t* s, uint32_t n, uint8_t* dst) {
+__device__ __noinline__ uint32_t yt_sanitize(const uint8_t* s, uint32_t n, uint8_t* dst) {
   uint32_t o = 0;
   for (uint32_t i = 0; i < n && o < 50;) {
     uint32_t b = ldb(s + i);
@@ -342,19 +426,10 @@ DEVI bool walk_yt_record(W& w, const YtArgs& a) {
       q += thn[k];
     }
   }
-  const int l = lane_id();
   // times: published (UTC), channel published (UTC): rendered where needed; validity first
-  uint32_t tl = 0;
-  __syncwarp();
-  if (l == 0) tl = (uint32_t)render_time(w.sc->num, v.published_sec, v.published_nsec, 0);
-  __syncwarp();
-  const uint32_t pub_len = __shfl_sync(FULL, tl, 0);
+  const uint32_t pub_len = w.time_len(v.published_sec, v.published_nsec);
   uint32_t chpub_len = 1;
-  if (ch.cached) {
-    uint8_t tmp[40];
-    if (l == 0) tl = (uint32_t)render_time(tmp, ch.published_sec, ch.published_nsec, 0);
-    chpub_len = __shfl_sync(FULL, tl, 0);
-  }
+  if (ch.cached) chpub_len = w.time_len(ch.published_sec, ch.published_nsec);
   if (pub_len == 0 || chpub_len == 0 || (cfg.flags & CFGDEV_CLOCK_INVALID) || cfg.created_yt_len == 0) return false;
 
   const int64_t engagement = (int64_t)((uint64_t)v.like_count + (uint64_t)v.comment_count + (uint64_t)(v.view_count / 100));  // :561
@@ -371,9 +446,7 @@ DEVI bool walk_yt_record(W& w, const YtArgs& a) {
   int has_len = 0;
   int64_t vlen = 0;
   if (v.duration_len && !(v.duration_len == 3 && ldb(dur) == 'P' && ldb(dur + 1) == '0' && ldb(dur + 2) == 'D')) {
-    if (l == 0) has_len = yt_parse_duration(dur, v.duration_len, vlen) ? 1 : 0;
-    has_len = __shfl_sync(FULL, has_len, 0);
-    vlen = __shfl_sync(FULL, vlen, 0);
+    has_len = w.duration(dur, v.duration_len, vlen) ? 1 : 0;
   }
   const uint8_t* cblob = cfg.blob;
   const uint8_t* created = cblob + cfg.off[2];
@@ -391,14 +464,7 @@ DEVI bool walk_yt_record(W& w, const YtArgs& a) {
     else YLIT(w, "https://www.youtube.com/channel/");                    \
     w.esc(chid, ch.id_len);                                              \
   } while (0)
-#define PUBTIME(sec, nsec)                                                         \
-  do {                                                                             \
-    uint32_t _n = 0;                                                               \
-    __syncwarp();                                                                  \
-    if (l == 0) _n = (uint32_t)render_time(w.sc->num, (sec), (nsec), 0);           \
-    __syncwarp();                                                                  \
-    w.smem(__shfl_sync(FULL, _n, 0));                                              \
-  } while (0)
+#define PUBTIME(sec, nsec) w.time((sec), (nsec))
 
   YLIT(w, "{\"post_link\":\""); VURL();
   YLIT(w, "\",\"channel_id\":\""); w.esc(chid, ch.id_len);
@@ -462,30 +528,18 @@ DEVI bool walk_yt_record(W& w, const YtArgs& a) {
   YLIT(w, ",\"performance_scores\":{\"likes\":"); w.dec(v.like_count);
   YLIT(w, ",\"shares\":null,\"comments\":"); w.dec(v.comment_count);
   YLIT(w, ",\"views\":");
-  {
-    uint32_t n = 0;
-    __syncwarp();
-    if (l == 0) n = (uint32_t)yt_render_float_of_int64(w.sc->num, v.view_count);
-    __syncwarp();
-    w.smem(__shfl_sync(FULL, n, 0));
-  }
-  YLIT(w, "},\"has_embed_media\":true,\"description\":\""); w.esc(desc, v.desc_len);
+  w.fviews(v.view_count);
+  YLIT(w, "},\"has_embed_media\":true,\"description\":\""); w.esc_slot(0, desc, v.desc_len);
   YLIT(w, "\",\"repost_channel_data\":null,\"post_type\":[\"video\"],\"inner_link\":{},\"post_title\":\"");
-  w.esc(title, v.title_len);
+  w.esc_slot(1, title, v.title_len);
   YLIT(w, "\",\"media_data\":{\"document_name\":\""); w.esc(id, v.id_len);
   w.ch('-');
-  {
-    uint32_t n = 0;
-    __syncwarp();
-    if (l == 0) n = yt_sanitize(title, v.title_len, w.sc->num);
-    __syncwarp();
-    w.smem(__shfl_sync(FULL, n, 0));
-  }
+  w.sanitized(title, v.title_len);
   YLIT(w, ".mp4\"},\"is_reply\":null,\"ad_fields\":null,\"likes_count\":"); w.dec(v.like_count);
   YLIT(w, ",\"shares_count\":0,\"comments_count\":"); w.dec(v.comment_count);
   YLIT(w, ",\"views_count\":"); w.dec(v.view_count);
-  YLIT(w, ",\"searchable_text\":\""); w.esc(title, v.title_len); w.ch(' '); w.esc(desc, v.desc_len);
-  YLIT(w, "\",\"all_text\":\""); w.esc(title, v.title_len); w.ch(' '); w.esc(desc, v.desc_len);
+  YLIT(w, ",\"searchable_text\":\""); w.esc_slot(1, title, v.title_len); w.ch(' '); w.esc_slot(0, desc, v.desc_len);
+  YLIT(w, "\",\"all_text\":\""); w.esc_slot(1, title, v.title_len); w.ch(' '); w.esc_slot(0, desc, v.desc_len);
   YLIT(w, "\",\"contrast_agent_project_ids\":null,\"agent_ids\":null,\"segment_ids\":null,\"thumb_url\":\"");
   w.esc(thumb, thumb_n);
   YLIT(w, "\",\"media_url\":\""); VURL();

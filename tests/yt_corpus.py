@@ -54,3 +54,62 @@ def make_youtube(n: int, seed: int = 7, n_chans: int = 37):
             published_nsec=rng.choice([0, 0, 0, 500_000_000]), view_count=views, like_count=views // 30, comment_count=views // 300,
             duration=dur, thumbnails=thumbs, language=rng.choice(["", "en", "ru", "zh-Hans"]), channel=rng.randrange(n_chans)))
     return pack_youtube(vids, chans), vids, chans
+
+
+_PLAIN = ["the", "video", "about", "channel", "new", "watch", "and", "more", "from", "this", "week", "episode", "review", "how", "to",
+          "guide", "music", "official", "live", "part", "best", "of", "2024", "full", "with", "our", "your", "for", "you", "in"]
+
+
+def make_youtube_config4(n: int, seed: int = 0x5EED0004, n_chans: int = 1000):
+    """BASELINE config 4 shape: title lognormal median 45 B, description lognormal median 400 B
+    clipped at 5000 with URLs Poisson(1.5) of which 10 % are youtube.com/channel/UC… or youtube.com/@handle,
+    views lognormal(8, 3), likes = views/30, comments = views/300, PT#H#M#S durations (1 % P0D, 0.5 % empty,
+    0.5 % P1DT…), 3-5 thumbnails.  2 % of the descriptions carry characters that need escaping."""
+    rng = random.Random(seed)
+    chans = [YouTubeChannel(id="UC" + "".join(rng.choice(_B64) for _ in range(22)), title="Channel %d" % c,
+                            description=" ".join(rng.choice(_PLAIN) for _ in range(20)),
+                            thumb_default="https://yt3.ggpht.com/" + "".join(rng.choice(_B64) for _ in range(30)), country="US",
+                            subscriber_count=rng.randrange(0, 10 ** 7), view_count=rng.randrange(0, 10 ** 10),
+                            video_count=rng.randrange(0, 10 ** 4), published_sec=rng.randrange(1_100_000_000, 1_700_000_000),
+                            cached=True) for c in range(n_chans)]
+
+    def text(nbytes, urls):
+        words, size = [], 0
+        while size < nbytes:
+            w = rng.choice(_PLAIN)
+            words.append(w)
+            size += len(w) + 1
+        for _ in range(urls):
+            u = rng.random()
+            if u < 0.05:
+                link = "https://www.youtube.com/channel/UC" + "".join(rng.choice(_B64) for _ in range(22))
+            elif u < 0.10:
+                link = "https://youtube.com/@" + "".join(rng.choice("abcdefghij_") for _ in range(rng.randrange(5, 15)))
+            else:
+                link = "https://example.com/" + "".join(rng.choice(_B64) for _ in range(rng.randrange(4, 20)))
+            words.insert(rng.randrange(len(words) + 1), link)
+        return " ".join(words)
+
+    def poisson(lam):
+        k, p, L = 0, 1.0, 2.718281828 ** -lam
+        while True:
+            p *= rng.random()
+            if p <= L:
+                return k
+            k += 1
+
+    vids = []
+    for i in range(n):
+        desc = text(min(int(rng.lognormvariate(5.99, 0.9)), 5000), poisson(1.5))
+        if rng.random() < 0.02:
+            desc = desc.replace(" ", "\n", 3) + ' "quoted" <tag> & more'
+        views = int(rng.lognormvariate(8, 3))
+        u = rng.random()
+        dur = "P0D" if u < 0.01 else "" if u < 0.015 else "P1DT2H" if u < 0.02 else "PT%dH%dM%dS" % (rng.randrange(3), rng.randrange(60), rng.randrange(60))
+        keys = ["default", "medium", "high", "standard", "maxres"][: rng.randrange(3, 6)]
+        vids.append(YouTubeVideo(
+            id="".join(rng.choice(_B64) for _ in range(11)), title=text(int(rng.lognormvariate(3.8, 0.5)), 0), description=desc,
+            published_sec=rng.randrange(1_300_000_000, 1_760_000_000), view_count=views, like_count=views // 30, comment_count=views // 300,
+            duration=dur, thumbnails={k: "https://i.ytimg.com/vi/%s/%s.jpg" % (i, k) for k in keys}, language="en",
+            channel=rng.randrange(n_chans)))
+    return pack_youtube(vids, chans), vids, chans
