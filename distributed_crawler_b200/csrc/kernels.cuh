@@ -576,6 +576,50 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) yt_size_kernel(YtBatchDev b, C
   }
 }
 
+// length pass, one lane per record (yt_lane.cuh); the description and the title are measured by the warp
+__global__ void __launch_bounds__(CTA_THREADS, 2) yt_size_lane_kernel(YtBatchDev b, CfgDev cfg, YtOut o) {
+  const int wid = threadIdx.x >> 5, l = lane_id();
+  const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
+    uint64_t r = g * 32 + l;
+    bool active = r < b.n;
+    if (!active) r = b.n - 1;
+    active = active && o.status[r] == TGI_ST_EMITTED;
+    const tgi_yt_rec* rec = &b.recs[r];
+    const uint8_t* title = b.strs + rec->str_off + rec->id_len;
+    const uint32_t tn = rec->title_len, dn = rec->desc_len;
+    uint32_t el0 = 0, el1 = 0;
+    uint32_t todo = __ballot_sync(FULL, active);
+    while (todo) {  // the two long strings of every record, all lanes
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint8_t* t = (const uint8_t*)__shfl_sync(FULL, (unsigned long long)(uintptr_t)title, src);
+      const uint32_t a = __shfl_sync(FULL, tn, src), d = __shfl_sync(FULL, dn, src);
+      const uint32_t e1 = warp_esc_len(t, a), e0 = warp_esc_len(t + a, d);
+      if (l == src) {
+        el0 = e0;
+        el1 = e1;
+      }
+    }
+    if (!active) continue;
+    YtArgs a;
+    a.b = &b;
+    a.cfg = &cfg;
+    a.r = r;
+    a.urls = o.urls + o.url_start[r];
+    a.n_urls = o.url_count[r];
+    YtLaneSizer z;
+    z.el[0] = el0;
+    z.el[1] = el1;
+    const bool ok = walk_yt_record(z, a);
+    o.esc_len[3 * r] = el0;
+    o.esc_len[3 * r + 1] = el1;
+    o.esc_len[3 * r + 2] = z.dirty ? 0u : 1u;
+    o.linelen[r] = ok ? (uint32_t)z.total : 0u;
+    if (!ok) o.status[r] = TGI_ST_NOLINE;
+  }
+}
+
 // warp writer: the records the lane writer does not take (a string needs escaping); lanes pick them out of
 // groups of 32.  lane_mode == 0: every record (A/B reference, TGI_YT_WARP=1).
 __global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_kernel(YtBatchDev b, CfgDev cfg, YtOut o, const uint64_t* line_off, uint8_t* out, int* err,

@@ -697,7 +697,14 @@ int run_yt(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     yt_parse_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, flags, yo);
     launches++;
     if (want_json) {
-      yt_size_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, yo);
+      static const bool yt_warp = getenv("TGI_YT_WARP") != nullptr;
+      if (yt_warp) {
+        yt_size_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, yo);
+      } else {
+        const uint64_t groups = (n + 31) / 32;
+        unsigned gs = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
+        yt_size_lane_kernel<<<gs, CTA_THREADS, 0, st>>>(b, cfg, yo);
+      }
       launches++;
     }
     CK(cudaEventRecord(s.ev_p1, st));

@@ -91,4 +91,32 @@ struct YtLaneWriter {
   DEVI bool duration(const uint8_t* d, uint32_t dn, int64_t& vlen) { return yt_parse_duration(d, dn, vlen); }
 };
 
+// length pass of the same walk, one lane per record.  The escaped lengths of the two long strings
+// (description, title) come from the warp (el[]); every other string is short and measured by the lane.
+struct YtLaneSizer {
+  static constexpr bool kLane = true;
+  uint64_t total = 0;
+  uint32_t el[2];
+  bool dirty = false;
+  __align__(16) uint8_t num[64];
+  DEVI void raw(const uint8_t*, uint32_t n) { total += n; }
+  DEVI void esc(const uint8_t* p, uint32_t n) {
+    const uint32_t e = thread_esc_len(p, n);
+    dirty = dirty || e != n;
+    total += e;
+  }
+  DEVI void esc_slot(int k, const uint8_t*, uint32_t n) {
+    dirty = dirty || el[k] != n;
+    total += el[k];
+  }
+  DEVI void ch(uint32_t) { total += 1; }
+  DEVI void dec(int64_t v) { total += yt_ndigits(v); }
+  DEVI void smem(uint32_t n) { total += n; }
+  DEVI uint32_t time_len(int64_t sec, int32_t nsec) { return (uint32_t)render_time(num, sec, nsec, 0); }
+  DEVI void time(int64_t sec, int32_t nsec) { total += (uint32_t)render_time(num, sec, nsec, 0); }
+  DEVI void fviews(int64_t v) { total += (uint32_t)yt_render_float_of_int64(num, v); }
+  DEVI void sanitized(const uint8_t* t, uint32_t tn) { total += yt_sanitize(t, tn, num); }
+  DEVI bool duration(const uint8_t* d, uint32_t dn, int64_t& vlen) { return yt_parse_duration(d, dn, vlen); }
+};
+
 }  // namespace tgi

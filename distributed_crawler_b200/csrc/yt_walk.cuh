@@ -10,6 +10,7 @@
 // obviously-correct formulation over the lane-parallel machinery of the Telegram path.
 #pragma once
 #include "dev_common.cuh"
+#include "tg_links.cuh"
 
 namespace tgi {
 
@@ -259,30 +260,47 @@ __device__ __noinline__ uint32_t yt_sanitize(const uint8_t* s, uint32_t n, uint8
 // extractURLs (:489-513): (https?://\S+) over the description, TrimRight(",.;:!?()'\""), unique in
 // first-occurrence order.  Warp-cooperative candidate search; the unique list goes to `out` (cap
 // entries, reserved from an upper bound = number of "http" occurrences).  Returns the count.
-DEVI uint32_t yt_count_http(const uint8_t* s, uint32_t n) {
+// 512-byte strips, 16 bytes per lane, with a ':' prefilter (':' is rare in running text): bit k of the lane's
+// mask is set if s[p0+k] is the colon of "http://" / "https://" followed by a non-space (p0 = base + 16*lane)
+DEVI uint32_t yt_strip16_scheme(const uint8_t* s, uint32_t base, uint32_t n) {
+  const uint32_t p0 = base + 16u * (uint32_t)lane_id();
+  if (p0 >= n) return 0;
+  const uint4 w = load16_lane(s + p0);
+  const uint32_t c0 = swar_eq(w.x, ':'), c1 = swar_eq(w.y, ':'), c2 = swar_eq(w.z, ':'), c3 = swar_eq(w.w, ':');
+  if (!(c0 | c1 | c2 | c3)) return 0;
+  uint32_t m = swar_movemask(c0) | (swar_movemask(c1) << 4) | (swar_movemask(c2) << 8) | (swar_movemask(c3) << 12);
+  if (n - p0 < 16) m &= (1u << (n - p0)) - 1u;
+  uint32_t out = 0;
+  while (m) {
+    const uint32_t k = (uint32_t)__ffs(m) - 1u, c = p0 + k;
+    m &= m - 1;
+    if (c < 4 || c + 3 >= n) continue;
+    if (ldb(s + c + 1) != '/' || ldb(s + c + 2) != '/' || yt_is_space(ldb(s + c + 3))) continue;
+    const bool http = ld_u32_unaligned(s + c - 4) == 0x70747468u;                                   // "http"
+    const bool https = c >= 5 && ldb(s + c - 1) == 's' && ld_u32_unaligned(s + c - 5) == 0x70747468u;  // "https"
+    if (http || https) out |= 1u << k;
+  }
+  return out;
+}
+DEVI uint32_t yt_count_http(const uint8_t* s, uint32_t n) {  // number of places where a URL can start (upper bound on matches)
   uint32_t c = 0;
-  for (uint32_t i = lane_id(); i + 4 <= n; i += 32)
-    c += (ldb(s + i) == 'h' && ldb(s + i + 1) == 't' && ldb(s + i + 2) == 't' && ldb(s + i + 3) == 'p');
+  for (uint32_t base = 0; base < n; base += 512) c += __popc(yt_strip16_scheme(s, base, n));
   return warp_sum(c);
 }
 DEVI uint32_t yt_extract_urls(const uint8_t* s, uint32_t n, YtUrl* out, uint32_t cap) {
   uint32_t m = 0, resume = 0;
   int l = lane_id();
-  for (uint32_t base = 0; base < n; base += 32) {
-    uint32_t i = base + l;
-    uint32_t k = 0;  // scheme length if a match can start here
-    // "http://" or "https://" followed by at least one \S
-    if (i + 8 <= n && ldb(s + i) == 'h' && ldb(s + i + 1) == 't' && ldb(s + i + 2) == 't' && ldb(s + i + 3) == 'p') {
-      uint32_t j = i + 4;
-      if (ldb(s + j) == 's') j++;
-      if (j + 3 < n && ldb(s + j) == ':' && ldb(s + j + 1) == '/' && ldb(s + j + 2) == '/' && !yt_is_space(ldb(s + j + 3)))
-        k = j + 3 - i;
-    }
-    uint32_t cand = __ballot_sync(FULL, k != 0);
-    while (cand) {
-      int src = __ffs(cand) - 1;
-      cand &= cand - 1;
-      uint32_t p = base + src;
+  for (uint32_t base = 0; base < n; base += 512) {
+    const uint32_t cm = yt_strip16_scheme(s, base, n);
+    uint32_t lanes = __ballot_sync(FULL, cm != 0);
+    while (lanes) {
+      const int src_lane = __ffs(lanes) - 1;
+      lanes &= lanes - 1;
+      uint32_t mm = __shfl_sync(FULL, cm, src_lane);
+     while (mm) {
+      const uint32_t colon = base + 16u * (uint32_t)src_lane + (uint32_t)__ffs(mm) - 1u;
+      mm &= mm - 1;
+      const uint32_t p = colon - (ldb(s + colon - 1) == 's' ? 5u : 4u);  // start of the scheme
       if (p < resume) continue;  // inside the previous match
       // \S+ is greedy: up to the next RE2 whitespace
       uint32_t e = p;
@@ -319,6 +337,7 @@ DEVI uint32_t yt_extract_urls(const uint8_t* s, uint32_t n, YtUrl* out, uint32_t
         __syncwarp();
         m++;
       }
+     }
     }
   }
   return m;
@@ -328,32 +347,55 @@ DEVI uint32_t yt_extract_urls(const uint8_t* s, uint32_t n, YtUrl* out, uint32_t
 // youtube\.com/@([\w.-]+) ("@"+handle); no dedup here.  Keys are cut to 32 bytes (frontier key width).
 DEVI bool yt_is_uc_char(uint32_t c) { return is_word(c) || c == '-'; }
 DEVI bool yt_is_handle_char(uint32_t c) { return is_word(c) || c == '-' || c == '.'; }
+// 512-byte strips with a '/' prefilter: bit k of the lane's mask is set if s[p0+k] is the slash of "youtube.com/"
+DEVI uint32_t yt_strip16_ytcom(const uint8_t* s, uint32_t base, uint32_t n) {
+  const uint32_t p0 = base + 16u * (uint32_t)lane_id();
+  if (p0 >= n) return 0;
+  const uint4 w = load16_lane(s + p0);
+  const uint32_t c0 = swar_eq(w.x, '/'), c1 = swar_eq(w.y, '/'), c2 = swar_eq(w.z, '/'), c3 = swar_eq(w.w, '/');
+  if (!(c0 | c1 | c2 | c3)) return 0;
+  uint32_t m = swar_movemask(c0) | (swar_movemask(c1) << 4) | (swar_movemask(c2) << 8) | (swar_movemask(c3) << 12);
+  if (n - p0 < 16) m &= (1u << (n - p0)) - 1u;
+  uint32_t out = 0;
+  while (m) {
+    const uint32_t k = (uint32_t)__ffs(m) - 1u, c = p0 + k;
+    m &= m - 1;
+    if (c >= 11 && ld_u32_unaligned(s + c - 11) == 0x74756F79u && ld_u32_unaligned(s + c - 7) == 0x2E656275u &&
+        (ld_u32_unaligned(s + c - 3) & 0xFFFFFFu) == 0x6D6F63u)  // "yout" "ube." "com"
+      out |= 1u << k;
+  }
+  return out;
+}
 DEVI uint32_t yt_count_ytcom(const uint8_t* s, uint32_t n) {  // upper bound on channel-id matches
   uint32_t c = 0;
-  for (uint32_t i = lane_id(); i + 12 < n; i += 32)
-    c += (ldb(s + i) == 'y' && ldb(s + i + 1) == 'o' && ldb(s + i + 2) == 'u' && ldb(s + i + 7) == '.' && ldb(s + i + 11) == '/');
+  for (uint32_t base = 0; base < n; base += 512) c += __popc(yt_strip16_ytcom(s, base, n));
   return warp_sum(c);
 }
 DEVI uint32_t yt_channel_ids(const uint8_t* s, uint32_t n, tgi_link* out, uint32_t cap) {
-  static __device__ const char p1[] = "youtube.com/channel/";
-  static __device__ const char p2[] = "youtube.com/@";
   uint32_t m = 0;
   int l = lane_id();
   for (int pass = 0; pass < 2; pass++) {
-    const char* pat = pass ? p2 : p1;
-    const uint32_t pl = pass ? 13u : 20u;
+    const uint32_t pl = pass ? 13u : 20u;  // "youtube.com/@" / "youtube.com/channel/"
     uint32_t resume = 0;
-    for (uint32_t base = 0; base + pl < n; base += 32) {
-      uint32_t i = base + l;
-      bool hit = i + pl < n && ldb(s + i) == 'y' && ldb(s + i + 1) == 'o';
-      if (hit)
-        for (uint32_t t = 2; t < pl && hit; t++) hit = ldb(s + i + t) == (uint32_t)pat[t];
-      if (hit) hit = pass ? yt_is_handle_char(ldb(s + i + pl)) : yt_is_uc_char(ldb(s + i + pl));
-      uint32_t cand = __ballot_sync(FULL, hit);
-      while (cand) {
-        int src = __ffs(cand) - 1;
-        cand &= cand - 1;
-        uint32_t p = base + src;
+    for (uint32_t base = 0; base < n; base += 512) {
+      const uint32_t cm = yt_strip16_ytcom(s, base, n);
+      uint32_t lanes = __ballot_sync(FULL, cm != 0);
+      while (lanes) {
+        const int src_lane = __ffs(lanes) - 1;
+        lanes &= lanes - 1;
+        uint32_t mm = __shfl_sync(FULL, cm, src_lane);
+       while (mm) {
+        const uint32_t slash = base + 16u * (uint32_t)src_lane + (uint32_t)__ffs(mm) - 1u;
+        mm &= mm - 1;
+        const uint32_t p = slash - 11u;  // start of "youtube.com/"
+        if (p + pl >= n) continue;
+        if (pass) {
+          if (ldb(s + slash + 1) != '@' || !yt_is_handle_char(ldb(s + p + pl))) continue;
+        } else {
+          if (ld_u32_unaligned(s + slash + 1) != 0x6E616863u || ld_u32_unaligned(s + slash + 5) != 0x2F6C656Eu ||  // "chan" "nel/"
+              !yt_is_uc_char(ldb(s + p + pl)))
+            continue;
+        }
         if (p < resume) continue;
         uint32_t q = p + pl, e = q;
         for (;;) {
@@ -385,6 +427,7 @@ DEVI uint32_t yt_channel_ids(const uint8_t* s, uint32_t n, tgi_link* out, uint32
           __syncwarp();
           m++;
         }
+       }
       }
     }
   }

@@ -44,3 +44,11 @@ def test_youtube_configs_and_edge_cases():
                          title="  \xe9", channel=1)]
     ro, rg = both(pack_youtube(vids, [YouTubeChannel(id="UCx", title="T", cached=True), YouTubeChannel(id="@h", cached=False)]))
     assert [bytes(l["name"][: l["len"]]) for l in rg.links] == [b"UCabc-_123", b"@some.handle-1"]
+
+
+def test_youtube_config4_shape_parity():
+    """BASELINE config 4 shape: almost every record takes the lane writer (nothing to escape)."""
+    from yt_corpus import make_youtube_config4
+    batch, _, _ = make_youtube_config4(3000, seed=77)
+    ro, rg = both(batch)
+    assert (rg.status == abi.ST_EMITTED).all()
