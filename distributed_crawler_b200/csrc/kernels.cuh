@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) yt_size_kernel(YtBatchDev b, C
 }
 
 // length pass, one lane per record (yt_lane.cuh); the description and the title are measured by the warp
-__global__ void __launch_bounds__(CTA_THREADS, 2) yt_size_lane_kernel(YtBatchDev b, CfgDev cfg, YtOut o) {
+__global__ void __launch_bounds__(CTA_THREADS, 4) yt_size_lane_kernel(YtBatchDev b, CfgDev cfg, YtOut o) {
   const int wid = threadIdx.x >> 5, l = lane_id();
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
@@ -652,7 +652,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_kernel(YtBatchDev b, C
 }
 
 // lane writer (yt_lane.cuh): one lane per clean record
-__global__ void __launch_bounds__(CTA_THREADS, 2) yt_emit_lane_kernel(YtBatchDev b, CfgDev cfg, YtOut o, const uint64_t* line_off, uint8_t* out, int* err) {
+__global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_lane_kernel(YtBatchDev b, CfgDev cfg, YtOut o, const uint64_t* line_off, uint8_t* out, int* err) {
   const int wid = threadIdx.x >> 5, l = lane_id();
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {

@@ -201,3 +201,29 @@ def test_full_size_config2_properties():
         rg = e2.telegram(sub, abi.RUN_JSONL)
         assert np.array_equal(ro.jsonl, rg.jsonl)
     assert e.read_jsonl(0, r.jsonl_len - 1, 1) == b"\n"
+
+
+def test_warp_per_record_reference_kernels_still_agree():
+    """The A/B switches (TGI_EMIT_FIXED_WARP, TGI_SIZE_WARP, TGI_YT_WARP) select the warp-per-record kernels the
+    lane kernels replaced; they are read once per process, so this runs in a child process."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, 'tests')\n"
+        "from distributed_crawler_b200 import abi\n"
+        "from distributed_crawler_b200.corpus import Corpus\n"
+        "from distributed_crawler_b200.engine import Engine\n"
+        "from oracle.pyoracle import Oracle\n"
+        "from helpers import assert_results_equal\n"
+        "from yt_corpus import make_youtube\n"
+        "f = abi.RUN_JSONL | abi.RUN_LINKS\n"
+        "c = Corpus(5000, profile=2)\n"
+        "assert_results_equal(Oracle().telegram(c.batch, f), Engine().telegram(c.batch, f), f)\n"
+        "b, _, _ = make_youtube(800, seed=5)\n"
+        "assert_results_equal(Oracle().youtube(b, f), Engine().youtube(b, f), f)\n"
+        "print('ok')\n")
+    env = dict(os.environ, TGI_EMIT_FIXED_WARP="1", TGI_SIZE_WARP="1", TGI_YT_WARP="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]
