@@ -66,3 +66,16 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".inc", "Makefile")):
                 txt = open(os.path.join(dp, f), encoding="utf-8").read()
                 assert not bad.search(txt), os.path.join(dp, f)
+
+
+def test_generated_piece_table_is_current(tmp_path):
+    """csrc/tg_pieces.inc is generated from the Post line program in tools/gen_pieces.py."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_pieces", os.path.join(root, "tools", "gen_pieces.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    want = g.emit_table("Tg", g.TG) + g.emit_lane_table("Tg", g.TG)
+    have = open(os.path.join(root, "distributed_crawler_b200", "csrc", "tg_pieces.inc")).read()
+    assert have == want, "run python tools/gen_pieces.py"
