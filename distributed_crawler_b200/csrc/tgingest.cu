@@ -1097,6 +1097,43 @@ int tgi_youtube_batch(tgi_ctx* c, const tgi_yt_batch* in, uint32_t run_flags, tg
   if (rc != TGI_OK) tgi_result_release(c, slot);
   return rc;
 }
+int tgi_plan_chunks(const uint64_t* line_off, uint64_t n, uint64_t trigger, uint64_t hard_cap, uint64_t* groups,
+                    uint64_t max_groups, uint64_t* n_groups, uint8_t* dropped) {
+  if (!line_off || !groups || !n_groups) return TGI_E_ARG;
+  uint64_t g = 0, size = 0, files = 0, begin = 0;
+  auto flush = [&](uint64_t end) -> bool {  // chunk/main.go:298-311; end = one past the last line of the group
+    if (!files) return true;
+    if (g >= max_groups) return false;
+    groups[2 * g] = begin;
+    groups[2 * g + 1] = end;
+    g++;
+    size = 0;
+    files = 0;
+    return true;
+  };
+  for (uint64_t i = 0; i < n; i++) {
+    const uint64_t len = line_off[i + 1] - line_off[i];
+    if (dropped) dropped[i] = 0;
+    if (len == 0) continue;  // no line for this record: no file
+    if (len > hard_cap) {    // :316-322
+      if (dropped) dropped[i] = 1;
+      continue;
+    }
+    if (size > 0 && size + len > hard_cap) {  // :324-327
+      if (!flush(i)) return TGI_E_CAPACITY;
+    }
+    if (!files) begin = i;
+    files++;
+    size += len;
+    if (size >= trigger) {  // :334-337
+      if (!flush(i + 1)) return TGI_E_CAPACITY;
+    }
+  }
+  if (!flush(n)) return TGI_E_CAPACITY;  // :339-343
+  *n_groups = g;
+  return TGI_OK;
+}
+
 int tgi_generic_batch(tgi_ctx* c, const tgi_gm_batch* in, uint32_t run_flags, tgi_result* out) {
   if (!c) return TGI_E_ARG;
   int slot = claim_slot(c);

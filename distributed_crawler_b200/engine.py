@@ -28,7 +28,7 @@ class EngineError(RuntimeError):
 EXPORTED_SYMBOLS = [
     "tgi_create", "tgi_destroy", "tgi_last_error", "tgi_get_stats", "tgi_set_clock",
     "tgi_telegram_submit", "tgi_telegram_wait", "tgi_telegram_batch", "tgi_youtube_submit",
-    "tgi_youtube_wait", "tgi_youtube_batch", "tgi_generic_batch", "tgi_result_release", "tgi_telegram_upload",
+    "tgi_youtube_wait", "tgi_youtube_batch", "tgi_generic_batch", "tgi_plan_chunks", "tgi_result_release", "tgi_telegram_upload",
     "tgi_telegram_run_resident", "tgi_youtube_upload", "tgi_youtube_run_resident",
     "tgi_result_read_jsonl", "tgi_frontier_insert", "tgi_frontier_size", "tgi_frontier_export",
     "tgi_frontier_clear", "tgi_frontier_export_dev", "tgi_frontier_insert_dev", "tgi_frontier_sync",
@@ -63,6 +63,7 @@ def lib() -> C.CDLL:
         L.tgi_telegram_upload.argtypes = [vp, i32, C.POINTER(abi.TgBatchC)]
         L.tgi_telegram_run_resident.argtypes = [vp, i32, u32, C.POINTER(abi.ResultC)]
         L.tgi_generic_batch.argtypes = [vp, C.POINTER(abi.GmBatchC), u32, C.POINTER(abi.ResultC)]
+        L.tgi_plan_chunks.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, C.c_uint64, C.POINTER(C.c_uint64), vp]
         L.tgi_youtube_upload.argtypes = [vp, i32, C.POINTER(abi.YtBatchC)]
         L.tgi_youtube_run_resident.argtypes = [vp, i32, u32, C.POINTER(abi.ResultC)]
         L.tgi_result_read_jsonl.argtypes = [vp, i32, u64, u64, vp]

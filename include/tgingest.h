@@ -374,6 +374,20 @@ int tgi_youtube_submit(tgi_ctx* ctx, int slot, const tgi_yt_batch* in, uint32_t 
 int tgi_youtube_wait(tgi_ctx* ctx, int slot, tgi_result* out);
 int tgi_youtube_batch(tgi_ctx* ctx, const tgi_yt_batch* in, uint32_t run_flags, tgi_result* out);
 
+/* SURVEY §8f rank 1 — the chunk combiner's batching rule (chunk/main.go:292-345, processBatches) applied to the lines
+ * of one result, instead of one temp file per post (state/daprstate.go:1117-1138) + fsnotify + io.Copy concat
+ * (chunk/main.go:378-421): consecutive lines are grouped into the blobs that become combined_<ns>.jsonl.
+ *   - a line longer than hard_cap is dropped (:316-322);
+ *   - a group is closed BEFORE a line that would push it over hard_cap (:324-327);
+ *   - a group is closed AFTER the line that makes it reach trigger (:334-337);
+ *   - what is left forms the last group (:339-343).
+ * Records without a line (line length 0) are not files and are ignored.  Group g = lines [groups[2g], groups[2g+1])
+ * minus the dropped / empty ones; groups are disjoint and increasing.  dropped (optional, n bytes) is set to 1 for
+ * dropped lines.  Pure host arithmetic over line_off (as returned in tgi_result); returns TGI_E_CAPACITY if more than
+ * max_groups groups are needed.                                                                        */
+int tgi_plan_chunks(const uint64_t* line_off, uint64_t n, uint64_t trigger, uint64_t hard_cap, uint64_t* groups,
+                    uint64_t max_groups, uint64_t* n_groups, uint8_t* dropped);
+
 /* Generic client.Message -> sparse Post line: replaces the loop body
  * crawler/telegram/telegram_crawler.go:148-156 (convertMessageToPost :179-262) + json.Marshal+'\n'.
  * Blocking; picks a free slot.  status[] is TGI_ST_EMITTED or TGI_ST_NOLINE; no links.             */
