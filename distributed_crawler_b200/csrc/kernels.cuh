@@ -242,25 +242,29 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_lane_kernel(TgBatchDev
       if (nr == 0) {
         xl[XL_REACTIONS] = 2;
         xl[XL_FLAGS] = XLF_SIMPLE_MAP;
-      } else if (nr <= LANE_MAP_MAX) {  // size_reaction_map, one lane: "key":n , ... ; simple = short clean distinct keys
-        uint32_t sz = 2u + (nr - 1u);
+      } else if (nr <= LANE_MAP_MAX) {  // size_reaction_map, one lane: "key":n , ... ; simple = short clean keys
+        uint32_t sz = 2u, live = 0;
         bool simple = true;
         for (uint32_t j = 0; j < nr; j++) {
           const tgi_reaction rc = b.reacts[r0 + j];
           const uint8_t* kp = b.aux + rc.emoji_off;
           const uint32_t el = thread_esc_len(kp, rc.emoji_len);
           simple = simple && el == rc.emoji_len && rc.emoji_len >= 1 && rc.emoji_len <= 8;
-          sz += 3u + el + ndigits_i64(rc.count);
-          for (uint32_t i = 0; i < j; i++) {
+          bool last = true;  // a later entry with the same key overwrites this one (Go map assignment)
+          for (uint32_t i = j + 1; i < nr; i++) {
             const tgi_reaction ri = b.reacts[r0 + i];
-            if (key_cmp(b.aux + ri.emoji_off, ri.emoji_len, kp, rc.emoji_len) == 0) simple = false;
+            if (key_cmp(b.aux + ri.emoji_off, ri.emoji_len, kp, rc.emoji_len) == 0) last = false;
+          }
+          if (last) {
+            sz += 3u + el + ndigits_i64(rc.count);
+            live++;
           }
         }
         if (simple) {
-          xl[XL_REACTIONS] = sz;
+          xl[XL_REACTIONS] = sz + (live - 1u);
           xl[XL_FLAGS] = XLF_SIMPLE_MAP;
         } else {
-          warp_map = true;  // duplicates drop out of the map: let the warp routine size it
+          warp_map = true;
         }
       } else {
         warp_map = true;
@@ -652,8 +656,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_kernel(YtBatchDev b, C
 }
 
 // lane writer (yt_lane.cuh): one lane per clean record
-__global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_lane_kernel(YtBatchDev b, CfgDev cfg, YtOut o, const uint64_t* line_off, uint8_t* out, int* err) {
+__global__ void __launch_bounds__(CTA_THREADS, 3) yt_emit_lane_kernel(YtBatchDev b, CfgDev cfg, YtOut o, const uint64_t* line_off, uint8_t* out, int* err) {
+  extern __shared__ __align__(128) uint8_t yt_stage[];  // CTA_THREADS staging rows
   const int wid = threadIdx.x >> 5, l = lane_id();
+  YtLaneWriter w;
+  w.init(smem_addr(yt_stage) + (uint32_t)threadIdx.x * YT_STAGE_ROW);
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
     const uint64_t r = g * 32 + l;
@@ -664,12 +671,51 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_lane_kernel(YtBatchDev
     a.r = r;
     a.urls = o.urls + o.url_start[r];
     a.n_urls = o.url_count[r];
-    YtLaneWriter w;
     w.begin((uint64_t)(uintptr_t)out + line_off[r]);
     walk_yt_record(w, a);
     w.end();
     if (w.s.pos != (uint64_t)(uintptr_t)out + line_off[r + 1]) atomicOr(err, 16);
   }
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging rows must outlive the bulk reads
+}
+
+// ---- message-status join: first index in A of every key of B ---------------------------------
+DEVI uint64_t join_hash(long long chat, long long msg) {  // splitmix64 finaliser over both words
+  uint64_t x = (uint64_t)chat * 0x9E3779B97F4A7C15ull ^ (uint64_t)msg;
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+// table[slot] = 1 + smallest index of an A element with that slot's key, 0 = empty
+__global__ void join_build_kernel(const longlong2* a, uint64_t na, uint32_t* table, uint64_t mask) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= na) return;
+  const longlong2 k = a[i];
+  for (uint64_t s = join_hash(k.x, k.y) & mask;; s = (s + 1) & mask) {
+    uint32_t cur = atomicCAS(&table[s], 0u, (uint32_t)i + 1u);
+    if (cur == 0) return;  // claimed
+    const longlong2 o = a[cur - 1];  // the occupant's key never changes (only its index may get smaller)
+    if (o.x == k.x && o.y == k.y) {
+      atomicMin(&table[s], (uint32_t)i + 1u);
+      return;
+    }
+  }
+}
+__global__ void join_probe_kernel(const longlong2* a, const uint32_t* table, uint64_t mask, const longlong2* b, uint64_t nb, long long* out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  const longlong2 k = b[i];
+  long long res = -1;
+  for (uint64_t s = join_hash(k.x, k.y) & mask;; s = (s + 1) & mask) {
+    const uint32_t cur = table[s];
+    if (cur == 0) break;
+    const longlong2 o = a[cur - 1];
+    if (o.x == k.x && o.y == k.y) {
+      res = (long long)cur - 1;
+      break;
+    }
+  }
+  out[i] = res;
 }
 
 // ---- generic client.Message -> sparse Post (a12) ---------------------------------------------------

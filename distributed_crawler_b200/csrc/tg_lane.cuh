@@ -244,6 +244,7 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
   // used by the time the comments / reactions / outlinks pieces come (they follow all K_FIELD pieces).
   uint32_t p = 0, t = 0;
   uint32_t multi_n = 0, multi_max = 0;  // entries of the current multi-step piece: this lane's / the warp's maximum
+  uint32_t map_nr = 0;                  // reactions: entries in the lane's table (>= multi_n when keys repeat)
   uint64_t prev = 0;                    // reactions: compare key of the entry emitted last
   while (p < (uint32_t)kTgLaneNPieces) {
     const uint32_t en = sh.pieces[p];
@@ -309,10 +310,11 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
           mine = on && (nr == 0 || (xlen_g[XL_FLAGS] & XLF_SIMPLE_MAP));
           if (on && !mine) g = xlen_g[XL_REACTIONS];
         }
-        multi_n = mine ? nr : 0u;  // <= LANE_MAP_MAX
-        multi_max = __reduce_max_sync(FULL, multi_n);
-        for (uint32_t j = 0; j < multi_max; j++) {
-          if (j < multi_n) {
+        const uint32_t nn = mine ? nr : 0u;  // <= LANE_MAP_MAX
+        map_nr = nn;
+        const uint32_t nmax = __reduce_max_sync(FULL, nn);
+        for (uint32_t j = 0; j < nmax; j++) {
+          if (j < nn) {
             const tgi_reaction rc = b.reacts[r0 + j];
             const uint8_t* kp = b.aux + rc.emoji_off;
             const uint32_t kl = rc.emoji_len;
@@ -322,6 +324,21 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
             ent[j] = make_uint4(k0, k1, (uint32_t)rc.count, kl);
           }
         }
+        // entries to emit = distinct keys (a later entry of the same key overwrites the earlier one)
+        uint32_t live = 0;
+        for (uint32_t j = 0; j < nmax; j++) {
+          if (j < nn) {
+            const uint4 e = ent[j];
+            bool last = true;
+            for (uint32_t i = j + 1; i < nn; i++) {
+              const uint4 f = ent[i];
+              if (f.x == e.x && f.y == e.y && f.w == e.w) last = false;
+            }
+            live += last ? 1u : 0u;
+          }
+        }
+        multi_n = live;
+        multi_max = __reduce_max_sync(FULL, multi_n);
         if (mine) {
           *(uint4*)sc = make_uint4(multi_n ? 0x7bu : 0x7d7bu, 0, 0, 0);  // { or {}
           src = sc;
@@ -331,11 +348,11 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
       } else if (t <= multi_n) {  // entry t-1 in key order:  "key":count, or "key":count}
         uint4 be = make_uint4(0, 0, 0, 0);
         uint64_t best = ~0ull;
-        for (uint32_t j = 0; j < multi_max; j++) {
-          if (j < multi_n) {
+        for (uint32_t j = 0; j < LANE_MAP_MAX; j++) {
+          if (j < map_nr) {
             const uint4 e = ent[j];
             const uint64_t ck = ((uint64_t)__byte_perm(e.x, 0, 0x0123) << 32) | __byte_perm(e.y, 0, 0x0123);
-            if (ck > prev && ck < best) {
+            if (ck > prev && ck <= best) {  // <=: the last entry of a key wins
               best = ck;
               be = e;
             }

@@ -733,7 +733,12 @@ int run_yt(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       const uint64_t groups = (n + 31) / 32;
       unsigned gg = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
       if (!yt_warp) {
-        yt_emit_lane_kernel<<<gg, CTA_THREADS, 0, st>>>(b, cfg, yo, s.d_line_off.as<uint64_t>(), s.d_jsonl.as<uint8_t>(), yo.err);
+        const size_t stage = (size_t)CTA_THREADS * YT_STAGE_ROW;
+        static const bool attr_set = [] {
+          return cudaFuncSetAttribute(yt_emit_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)CTA_THREADS * YT_STAGE_ROW)) == cudaSuccess;
+        }();
+        if (!attr_set) { set_err(c, "cannot reserve %zu bytes of shared memory for the YouTube lane writer", stage); return TGI_E_CUDA; }
+        yt_emit_lane_kernel<<<gg, CTA_THREADS, stage, st>>>(b, cfg, yo, s.d_line_off.as<uint64_t>(), s.d_jsonl.as<uint8_t>(), yo.err);
         launches++;
       }
       yt_emit_kernel<<<gg, CTA_THREADS, 0, st>>>(b, cfg, yo, s.d_line_off.as<uint64_t>(), s.d_jsonl.as<uint8_t>(), yo.err, yt_warp ? 0 : 1);
@@ -1097,6 +1102,32 @@ int tgi_youtube_batch(tgi_ctx* c, const tgi_yt_batch* in, uint32_t run_flags, tg
   if (rc != TGI_OK) tgi_result_release(c, slot);
   return rc;
 }
+int tgi_key_join(tgi_ctx* c, const int64_t* a_keys, uint64_t na, const int64_t* b_keys, uint64_t nb, int64_t* b_index) {
+  if (!c || (na && !a_keys) || (nb && (!b_keys || !b_index))) return TGI_E_ARG;
+  if (na >= 0xFFFFFFFFull) { set_err(c, "key join: list A has too many elements"); return TGI_E_ARG; }
+  cudaSetDevice(c->device);
+  if (!nb) return TGI_OK;
+  const uint64_t slots = next_pow2(std::max<uint64_t>(2 * na, 1024));
+  DevBuf da, db, dt, dout;
+  CK(da.ensure(na * 16 + 16));
+  CK(db.ensure(nb * 16));
+  CK(dt.ensure(slots * 4));
+  CK(dout.ensure(nb * 8));
+  CK(cudaMemset(dt.p, 0, slots * 4));
+  if (na) CK(cudaMemcpy(da.p, a_keys, na * 16, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db.p, b_keys, nb * 16, cudaMemcpyHostToDevice));
+  if (na) join_build_kernel<<<(unsigned)((na + 255) / 256), 256>>>((const longlong2*)da.p, na, dt.as<uint32_t>(), slots - 1);
+  join_probe_kernel<<<(unsigned)((nb + 255) / 256), 256>>>((const longlong2*)da.p, dt.as<uint32_t>(), slots - 1, (const longlong2*)db.p, nb,
+                                                       (long long*)dout.p);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(b_index, dout.p, nb * 8, cudaMemcpyDeviceToHost));
+  da.release();
+  db.release();
+  dt.release();
+  dout.release();
+  return TGI_OK;
+}
+
 int tgi_plan_chunks(const uint64_t* line_off, uint64_t n, uint64_t trigger, uint64_t hard_cap, uint64_t* groups,
                     uint64_t max_groups, uint64_t* n_groups, uint8_t* dropped) {
   if (!line_off || !groups || !n_groups) return TGI_E_ARG;

@@ -28,7 +28,7 @@ class EngineError(RuntimeError):
 EXPORTED_SYMBOLS = [
     "tgi_create", "tgi_destroy", "tgi_last_error", "tgi_get_stats", "tgi_set_clock",
     "tgi_telegram_submit", "tgi_telegram_wait", "tgi_telegram_batch", "tgi_youtube_submit",
-    "tgi_youtube_wait", "tgi_youtube_batch", "tgi_generic_batch", "tgi_plan_chunks", "tgi_result_release", "tgi_telegram_upload",
+    "tgi_youtube_wait", "tgi_youtube_batch", "tgi_generic_batch", "tgi_key_join", "tgi_plan_chunks", "tgi_result_release", "tgi_telegram_upload",
     "tgi_telegram_run_resident", "tgi_youtube_upload", "tgi_youtube_run_resident",
     "tgi_result_read_jsonl", "tgi_frontier_insert", "tgi_frontier_size", "tgi_frontier_export",
     "tgi_frontier_clear", "tgi_frontier_export_dev", "tgi_frontier_insert_dev", "tgi_frontier_sync",
@@ -63,6 +63,7 @@ def lib() -> C.CDLL:
         L.tgi_telegram_upload.argtypes = [vp, i32, C.POINTER(abi.TgBatchC)]
         L.tgi_telegram_run_resident.argtypes = [vp, i32, u32, C.POINTER(abi.ResultC)]
         L.tgi_generic_batch.argtypes = [vp, C.POINTER(abi.GmBatchC), u32, C.POINTER(abi.ResultC)]
+        L.tgi_key_join.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, vp]
         L.tgi_plan_chunks.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, vp, C.c_uint64, C.POINTER(C.c_uint64), vp]
         L.tgi_youtube_upload.argtypes = [vp, i32, C.POINTER(abi.YtBatchC)]
         L.tgi_youtube_run_resident.argtypes = [vp, i32, u32, C.POINTER(abi.ResultC)]
@@ -201,6 +202,15 @@ class Engine:
         self._check(lib().tgi_generic_batch(self.h, C.byref(d), run_flags, C.byref(r)))
         out = Result(r, copy)
         lib().tgi_result_release(self.h, r.slot)
+        return out
+
+    # --- message-status join -------------------------------------------------
+    def key_join(self, a_keys: np.ndarray, b_keys: np.ndarray) -> np.ndarray:
+        """for every (chat_id, message_id) row of b: index of the first equal row of a, or -1"""
+        a = np.ascontiguousarray(a_keys, dtype=np.int64).reshape(-1, 2)
+        b = np.ascontiguousarray(b_keys, dtype=np.int64).reshape(-1, 2)
+        out = np.full(len(b), -1, np.int64)
+        self._check(lib().tgi_key_join(self.h, a.ctypes.data, len(a), b.ctypes.data, len(b), out.ctypes.data))
         return out
 
     # --- frontier -------------------------------------------------------------------------------

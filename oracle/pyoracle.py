@@ -45,6 +45,8 @@ def lib() -> C.CDLL:
         L.orc_set_clock.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32]
         L.orc_telegram_batch.argtypes = [C.c_void_p, C.POINTER(abi.TgBatchC), C.c_uint32, C.c_int,
                                          C.POINTER(OrcResultC)]
+        L.orc_key_join.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.orc_key_join.restype = None
         L.orc_generic_batch.argtypes = [C.c_void_p, C.POINTER(abi.GmBatchC), C.c_uint32, C.c_int,
                                         C.POINTER(OrcResultC)]
         L.orc_youtube_batch.argtypes = [C.c_void_p, C.POINTER(abi.YtBatchC), C.c_uint32, C.c_int,
@@ -127,6 +129,14 @@ class Oracle:
         assert rc == 0
         out = result_from_c(r) if copy else (int(r.n), int(r.jsonl_len), int(r.n_links))
         lib().orc_result_free(C.byref(r))
+        return out
+
+    @staticmethod
+    def key_join(a_keys, b_keys):
+        a = np.ascontiguousarray(a_keys, dtype=np.int64).reshape(-1, 2)
+        b = np.ascontiguousarray(b_keys, dtype=np.int64).reshape(-1, 2)
+        out = np.full(len(b), -1, np.int64)
+        lib().orc_key_join(a.ctypes.data, len(a), b.ctypes.data, len(b), out.ctypes.data)
         return out
 
     def generic(self, batch, run_flags=abi.RUN_JSONL, nthreads=1, copy=True):

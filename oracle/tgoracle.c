@@ -1224,6 +1224,34 @@ int orc_youtube_batch(orc_ctx* c, const tgi_yt_batch* in, uint32_t run_flags, in
                       orc_result* out) {
   return run_batch(c, NULL, in, NULL, run_flags, nthreads, out);
 }
+/* crawl/runner.go:1580-1584,1667-1671 build map["%d_%d"]bool and :1171-1176 scans linearly; both are "is / where is
+ * this (ChatID, MessageID) in that list".  Sequential restatement: sort the indices of a by (key, index), binary search. */
+static const int64_t* g_join_keys;
+static int join_cmp(const void* x, const void* y) {
+  uint64_t i = *(const uint64_t*)x, j = *(const uint64_t*)y;
+  const int64_t *p = g_join_keys + 2 * i, *q = g_join_keys + 2 * j;
+  if (p[0] != q[0]) return p[0] < q[0] ? -1 : 1;
+  if (p[1] != q[1]) return p[1] < q[1] ? -1 : 1;
+  return i < j ? -1 : (i > j ? 1 : 0);
+}
+void orc_key_join(const int64_t* a, uint64_t na, const int64_t* b, uint64_t nb, int64_t* out) {
+  uint64_t* idx = (uint64_t*)malloc(sizeof(uint64_t) * (na ? na : 1));
+  for (uint64_t i = 0; i < na; i++) idx[i] = i;
+  g_join_keys = a;
+  qsort(idx, na, sizeof(uint64_t), join_cmp);
+  for (uint64_t k = 0; k < nb; k++) {
+    const int64_t c = b[2 * k], m = b[2 * k + 1];
+    uint64_t lo = 0, hi = na;  /* first position whose key >= (c, m) */
+    while (lo < hi) {
+      uint64_t mid = (lo + hi) / 2;
+      const int64_t* p = a + 2 * idx[mid];
+      if (p[0] < c || (p[0] == c && p[1] < m)) lo = mid + 1; else hi = mid;
+    }
+    out[k] = (lo < na && a[2 * idx[lo]] == c && a[2 * idx[lo] + 1] == m) ? (int64_t)idx[lo] : -1;
+  }
+  free(idx);
+}
+
 int orc_generic_batch(orc_ctx* c, const tgi_gm_batch* in, uint32_t run_flags, int nthreads, orc_result* out) {
   return run_batch(c, NULL, NULL, in, run_flags, nthreads, out);
 }

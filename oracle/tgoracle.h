@@ -49,6 +49,8 @@ void orc_set_clock(orc_ctx* c, int64_t created_at_sec, int32_t created_at_nsec, 
  * are split into contiguous ranges (the --concurrency analogue); output is identical.            */
 int orc_telegram_batch(orc_ctx* c, const tgi_tg_batch* in, uint32_t run_flags, int nthreads,
                        orc_result* out);
+/* first index in a of every key of b, -1 if absent (keys = {chat_id, message_id}) */
+void orc_key_join(const int64_t* a_keys, uint64_t na, const int64_t* b_keys, uint64_t nb, int64_t* b_index);
 int orc_generic_batch(orc_ctx* c, const tgi_gm_batch* in, uint32_t run_flags, int nthreads, orc_result* out);
 int orc_youtube_batch(orc_ctx* c, const tgi_yt_batch* in, uint32_t run_flags, int nthreads,
                       orc_result* out);
