@@ -465,7 +465,7 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   uint64_t n = b.n;
   cudaStream_t st = s.stream;
   uint32_t launches = 0;
-  const bool want_json = flags & TGI_RUN_JSONL, want_links = flags & TGI_RUN_LINKS, want_fr = flags & TGI_RUN_FRONTIER;
+  const bool want_json = flags & TGI_RUN_JSONL;
   CfgDev cfg;
   {
     std::lock_guard<std::mutex> g(c->cfg_mu);
@@ -1194,7 +1194,6 @@ static int frontier_insert_impl(tgi_ctx* c, const void* d_keys, uint64_t n, void
   Slot& s = c->slots[0];
   cudaStream_t st = s.stream;
   static thread_local DevBuf arena, cnt, lstate, recnew, newoff, btable, tiles, sc;
-  uint32_t launches = 0;
   std::unique_lock<std::mutex> fg(c->fr_mu);
   if (c->fr_event_valid) CK(cudaStreamWaitEvent(st, c->fr_event, 0));
   CK(arena.ensure(n * sizeof(tgi_link)));
@@ -1230,7 +1229,6 @@ static int frontier_insert_impl(tgi_ctx* c, const void* d_keys, uint64_t n, void
   frontier_append_kernel<<<g, 256, 0, st>>>(n, nullptr, cnt.as<uint32_t>(), arena.as<tgi_link>(), c->fr, fb, newoff.as<uint64_t>(), derr);
   frontier_commit_kernel<<<1, 1, 0, st>>>(c->fr, newoff.as<uint64_t>(), n, sc.as<uint64_t>() + 1, derr);
   if (d_is_new) links_new_flags_kernel<<<g, 256, 0, st>>>(arena.as<tgi_link>(), n, (uint8_t*)d_is_new);
-  (void)launches;
   CK(cudaGetLastError());
   int herr = 0;
   CK(cudaMemcpyAsync(&herr, derr, 4, cudaMemcpyDeviceToHost, st));
