@@ -656,11 +656,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_kernel(YtBatchDev b, C
 }
 
 // lane writer (yt_lane.cuh): one lane per clean record
-__global__ void __launch_bounds__(CTA_THREADS, 3) yt_emit_lane_kernel(YtBatchDev b, CfgDev cfg, YtOut o, const uint64_t* line_off, uint8_t* out, int* err) {
-  extern __shared__ __align__(128) uint8_t yt_stage[];  // CTA_THREADS staging rows
+__global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_lane_kernel(YtBatchDev b, CfgDev cfg, YtOut o, const uint64_t* line_off, uint8_t* out, int* err) {
   const int wid = threadIdx.x >> 5, l = lane_id();
-  YtLaneWriter w;
-  w.init(smem_addr(yt_stage) + (uint32_t)threadIdx.x * YT_STAGE_ROW);
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
     const uint64_t r = g * 32 + l;
@@ -671,12 +668,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) yt_emit_lane_kernel(YtBatchDev
     a.r = r;
     a.urls = o.urls + o.url_start[r];
     a.n_urls = o.url_count[r];
+    YtLaneWriter w;
     w.begin((uint64_t)(uintptr_t)out + line_off[r]);
     walk_yt_record(w, a);
     w.end();
     if (w.s.pos != (uint64_t)(uintptr_t)out + line_off[r + 1]) atomicOr(err, 16);
   }
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging rows must outlive the bulk reads
 }
 
 // ---- message-status join: first index in A of every key of B ---------------------------------

@@ -733,12 +733,7 @@ int run_yt(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       const uint64_t groups = (n + 31) / 32;
       unsigned gg = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
       if (!yt_warp) {
-        const size_t stage = (size_t)CTA_THREADS * YT_STAGE_ROW;
-        static const bool attr_set = [] {
-          return cudaFuncSetAttribute(yt_emit_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)CTA_THREADS * YT_STAGE_ROW)) == cudaSuccess;
-        }();
-        if (!attr_set) { set_err(c, "cannot reserve %zu bytes of shared memory for the YouTube lane writer", stage); return TGI_E_CUDA; }
-        yt_emit_lane_kernel<<<gg, CTA_THREADS, stage, st>>>(b, cfg, yo, s.d_line_off.as<uint64_t>(), s.d_jsonl.as<uint8_t>(), yo.err);
+        yt_emit_lane_kernel<<<gg, CTA_THREADS, 0, st>>>(b, cfg, yo, s.d_line_off.as<uint64_t>(), s.d_jsonl.as<uint8_t>(), yo.err);
         launches++;
       }
       yt_emit_kernel<<<gg, CTA_THREADS, 0, st>>>(b, cfg, yo, s.d_line_off.as<uint64_t>(), s.d_jsonl.as<uint8_t>(), yo.err, yt_warp ? 0 : 1);

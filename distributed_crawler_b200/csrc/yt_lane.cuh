@@ -2,11 +2,10 @@
 //
 // The line is the templated walk of yt_walk.cuh, instantiated with a writer that streams the lane's own
 // line: same byte-stream packing as tg_lane.cuh (16-byte blocks, byte-exact stores where a block is shared
-// with the neighbouring line).  Nothing in the writer is warp-collective, so the walk's per-record branches
-// and loops (cached channel or not, 0-5 thumbnails, n outlinks) may diverge freely between the lanes: full
-// blocks are staged in the lane's own shared-memory row (two halves of 128 bytes) and every full half leaves
-// the SM as ONE per-lane TMA bulk store (cp.async.bulk global <- shared::cta), which is a per-thread
-// instruction and therefore divergence-safe (the warp-collective drain of tg_lane.cuh is not).  Records with a string that needs escaping
+// with the neighbouring line), but the blocks are stored directly (ST.128 from the lane; staging them in
+// shared memory for per-lane TMA bulk stores was measured and is slower here: 63 vs 69 M records/s, profiles/README.md)
+// and nothing in the writer is warp-collective, so the walk's per-record branches and loops (cached channel or not, 0-5
+// thumbnails, n outlinks) may diverge freely between the lanes.  Records with a string that needs escaping
 // are left to the warp writer (yt_emit_kernel), which visits only those.
 #pragma once
 #include "tg_lane.cuh"
@@ -14,28 +13,11 @@
 
 namespace tgi {
 
-constexpr uint32_t YT_STAGE_HALF = 128;                    // bytes per bulk store
-constexpr uint32_t YT_STAGE_ROW = 2 * YT_STAGE_HALF + 16;  // per lane; +16 spreads the rows over the banks
 struct LaneDirect {
   uint64_t pos;             // absolute address of the next output byte
   uint32_t c0, c1, c2, c3;  // bytes [head, pos & 15) of the current block, zero elsewhere
   uint32_t head;            // first byte of the current block that belongs to this stream
-  uint64_t seg;             // global address of the first block staged in the active half
-  uint32_t row_s, half_s;   // shared-space address of the lane's staging row / of its active half
-  uint32_t fill;            // bytes staged in the active half
 };
-// hand the active half to the TMA and switch halves; the half we switch to was read by the group before the one
-// committed here, so at most that one may still be pending
-DEVI void ld_drain(LaneDirect& s) {
-  if (s.fill) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(s.seg), "r"(s.half_s), "r"(s.fill) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    s.half_s = s.half_s == s.row_s ? s.row_s + YT_STAGE_HALF : s.row_s;
-    s.fill = 0;
-    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-  }
-}
 
 // append bytes [0, n) of src (any address space, any alignment; the 16-byte blocks around it must be readable)
 __device__ __noinline__ void ld_copy(LaneDirect* sp, const uint8_t* src, uint32_t n) {
@@ -65,10 +47,7 @@ __device__ __noinline__ void ld_copy(LaneDirect* sp, const uint8_t* src, uint32_
     if (ph + k >= 16u) {
       const uint64_t blk = s.pos & ~15ull;
       if (s.head == 0) {
-        if (s.fill == 0) s.seg = blk;
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(s.half_s + s.fill), "r"(s.c0), "r"(s.c1), "r"(s.c2), "r"(s.c3) : "memory");
-        s.fill += 16;
-        if (s.fill == YT_STAGE_HALF) ld_drain(s);
+        *(uint4*)(uintptr_t)blk = make_uint4(s.c0, s.c1, s.c2, s.c3);
       } else {
         store_bytes(blk, s.c0, s.c1, s.c2, s.c3, s.head, 16u);
         s.head = 0;
@@ -88,18 +67,12 @@ struct YtLaneWriter {
   LaneDirect s;
   uint32_t el[2];               // unused (clean records only)
   __align__(16) uint8_t num[64];  // number / time / file-name rendering
-  DEVI void init(uint32_t row_s) {  // once per kernel: the active half survives from record to record
-    s.row_s = s.half_s = row_s;
-    s.fill = 0;
-    s.seg = 0;
-  }
   DEVI void begin(uint64_t addr) {
     s.pos = addr;
     s.head = (uint32_t)addr & 15u;
     s.c0 = s.c1 = s.c2 = s.c3 = 0;
   }
-  DEVI void end() {  // the staged blocks, then what the last block holds
-    ld_drain(s);
+  DEVI void end() {  // what the last block holds
     const uint32_t ph = (uint32_t)s.pos & 15u;
     if (ph > s.head) store_bytes(s.pos & ~15ull, s.c0, s.c1, s.c2, s.c3, s.head, ph);
   }
