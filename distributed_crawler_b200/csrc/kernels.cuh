@@ -1,10 +1,16 @@
-// kernels.cuh — __global__ kernels of the ingest engine (sm_100a).  See DESIGN.md for the data
-// layout and the per-kernel roofline model.  All kernels are HBM-bound integer/byte work:
-//   tg_chan_size / tg_chan_emit   per-channel constant strings (once per batch, tiny)
-//   tg_parse      link extraction (K2-K4) + JSONL line length (K6 size), one warp per record
-//   scan_*        exclusive scan u32 -> u64 offsets (K6)
-//   tg_emit       gather-style JSONL emit through per-warp shared-memory staging (K7)
-//   frontier_*    exact open-addressed hash set over 32-byte keys (K5)
+// kernels.cuh — __global__ kernels of the ingest engine (sm_100a).  See DESIGN.md §4 for the data layout and the
+// roofline bookkeeping.  All of it is integer/byte work:
+//   tg_chan_size / tg_chan_emit            per-channel constant strings (once per batch, tiny)
+//   tg_parse / tg_ent_map / tg_parse_ent   status + link extraction, one warp per record (split by code footprint)
+//   tg_size_lane                           JSONL line length, one LANE per record (+ the warp for the message text)
+//   scan_*                                 exclusive scan u32 -> u64 offsets
+//   tg_emit_lane                           the line, one LANE per record (tg_lane.cuh)
+//   tg_emit_esc / tg_emit_maps             what the lane emitter leaves: strings that need escaping, comment lists ...
+//   frontier_*                             exact open-addressed hash set over 32-byte keys
+//   yt_* / gm_*                            YouTube (config 4) and generic-message (a12) lines
+//   join_*                                 message-status join
+// tg_size_kernel / tg_emit_fixed_kernel / yt_size_kernel are the warp-per-record predecessors of the lane
+// kernels, kept as an A/B reference (TGI_SIZE_WARP, TGI_EMIT_FIXED_WARP, TGI_YT_WARP).
 #pragma once
 #include "tg_walk.cuh"
 #include "tg_lane.cuh"
@@ -16,7 +22,6 @@ namespace tgi {
 
 constexpr int WARPS_PER_CTA = 8;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
-constexpr int EMIT_RECS_PER_WARP = 8;  // contiguous records per warp task in the emit kernel
 
 #define ERR_ARENA_OVERFLOW 1
 #define ERR_TOO_MANY_REACTIONS 2
