@@ -666,18 +666,22 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_lane_kernel(YtBatchDev
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
     const uint64_t r = g * 32 + l;
-    if (r >= b.n || o.status[r] != TGI_ST_EMITTED || !o.esc_len[3 * r + 2]) continue;
-    YtArgs a;
-    a.b = &b;
-    a.cfg = &cfg;
-    a.r = r;
-    a.urls = o.urls + o.url_start[r];
-    a.n_urls = o.url_count[r];
+    const bool active = r < b.n && o.status[r] == TGI_ST_EMITTED && o.esc_len[3 * r + 2];
     YtLaneWriter w;
-    w.begin((uint64_t)(uintptr_t)out + line_off[r]);
-    walk_yt_record(w, a);
-    w.end();
-    if (w.s.pos != (uint64_t)(uintptr_t)out + line_off[r + 1]) atomicOr(err, 16);
+    if (active) {
+      YtArgs a;
+      a.b = &b;
+      a.cfg = &cfg;
+      a.r = r;
+      a.urls = o.urls + o.url_start[r];
+      a.n_urls = o.url_count[r];
+      w.begin((uint64_t)(uintptr_t)out + line_off[r]);
+      walk_yt_record(w, a);
+      w.end();
+      if (w.s.pos != (uint64_t)(uintptr_t)out + line_off[r + 1]) atomicOr(err, 16);
+    }
+    __syncwarp();
+    w.flush_pending(active);
   }
 }
 

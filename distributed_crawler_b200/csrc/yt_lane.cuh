@@ -62,9 +62,28 @@ __device__ __noinline__ void ld_copy(LaneDirect* sp, const uint8_t* src, uint32_
   *sp = s;
 }
 
+// leave n bytes to another writer: what the current block holds goes out byte-exact, the stream resumes behind the gap
+DEVI void ld_skip(LaneDirect& s, uint32_t n) {
+  const uint32_t ph = (uint32_t)s.pos & 15u;
+  if (ph > s.head) store_bytes(s.pos & ~15ull, s.c0, s.c1, s.c2, s.c3, s.head, ph);
+  s.c0 = s.c1 = s.c2 = s.c3 = 0;
+  s.pos += n;
+  s.head = (uint32_t)s.pos & 15u;
+}
+
+constexpr uint32_t YT_LANE_LONG = 128;  // longer strings are copied by the whole warp after the walk (see YtLaneWriter)
+constexpr int YT_LANE_PENDING = 4;
+
 struct YtLaneWriter {
   static constexpr bool kLane = true;
   LaneDirect s;
+  // The description is written three times and its length varies from 0 to 5000 bytes: copied by its own lane, every
+  // warp would run at the pace of its longest description.  Long strings are therefore skipped by the lane and
+  // copied afterwards by the whole warp, lane after lane (flush_pending).
+  uint64_t pend_dst[YT_LANE_PENDING];
+  const uint8_t* pend_src[YT_LANE_PENDING];
+  uint32_t pend_n[YT_LANE_PENDING];
+  int npend = 0;
   uint32_t el[2];               // unused (clean records only)
   __align__(16) uint8_t num[64];  // number / time / file-name rendering
   DEVI void begin(uint64_t addr) {
@@ -78,7 +97,32 @@ struct YtLaneWriter {
   }
   DEVI void raw(const uint8_t* p, uint32_t n) { ld_copy(&s, p, n); }
   DEVI void esc(const uint8_t* p, uint32_t n) { ld_copy(&s, p, n); }  // nothing to escape on this path
-  DEVI void esc_slot(int, const uint8_t* p, uint32_t n) { ld_copy(&s, p, n); }
+  DEVI void esc_slot(int, const uint8_t* p, uint32_t n) {
+    if (n > YT_LANE_LONG && npend < YT_LANE_PENDING) {
+      pend_dst[npend] = s.pos;
+      pend_src[npend] = p;
+      pend_n[npend] = n;
+      npend++;
+      ld_skip(s, n);
+    } else {
+      ld_copy(&s, p, n);
+    }
+  }
+  // warp-collective, after the (possibly divergent) walk: every lane's pending long copies, 512 bytes per step
+  DEVI void flush_pending(bool active) {
+#pragma unroll 1
+    for (int k = 0; k < YT_LANE_PENDING; k++) {
+      uint32_t todo = __ballot_sync(FULL, active && k < npend);
+      while (todo) {
+        const int src_lane = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint64_t d = __shfl_sync(FULL, pend_dst[k < npend ? k : 0], src_lane);
+        const uint8_t* p = (const uint8_t*)__shfl_sync(FULL, (unsigned long long)(uintptr_t)pend_src[k < npend ? k : 0], src_lane);
+        const uint32_t n = __shfl_sync(FULL, pend_n[k < npend ? k : 0], src_lane);
+        warp_copy_vec((uint8_t*)(uintptr_t)d, p, n);
+      }
+    }
+  }
   DEVI void ch(uint32_t c) {
     num[0] = (uint8_t)c;
     ld_copy(&s, num, 1);
