@@ -443,7 +443,7 @@ struct YtArgs {
   uint32_t n_urls;
 };
 
-__device__ const char kYtThumbKey[5][12] = {"default", "medium", "high", "standard", "maxres"};
+__device__ __align__(16) const char kYtThumbKey[5][16] = {"default", "medium", "high", "standard", "maxres"};  // 16-byte rows: the lane writer fetches sources in aligned 16-byte blocks
 __device__ const uint8_t kYtThumbKeyLen[5] = {7, 6, 4, 8, 6};
 
 // returns false if a time field is not representable (Marshal error -> TGI_ST_NOLINE)
