@@ -8,7 +8,7 @@ import pytest
 from distributed_crawler_b200 import abi
 from distributed_crawler_b200.corpus import Corpus
 from distributed_crawler_b200.engine import Engine, names_to_keys32
-from distributed_crawler_b200.pack import Channel, Comment, pack_telegram
+from distributed_crawler_b200.pack import Channel, Comment, FormattedText, Message, pack_telegram
 from helpers import ALL, TANDEM, assert_results_equal, msg, names, vector_message
 from oracle.pyoracle import Oracle
 
@@ -227,3 +227,34 @@ def test_warp_per_record_reference_kernels_still_agree():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     p = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]
+
+
+def test_lane_emitter_hand_over_boundaries():
+    """The lane emitter writes the simple cases itself and leaves the rest to the esc / maps kernels: the rules sit at
+    LANE_TEXT_MAX (512 bytes), LANE_LINKS_MAX (4 outlinks), LANE_MAP_MAX (6 entries), 8-byte keys, repeated keys,
+    strings that need escaping.  Messages on both sides of every boundary, in one warp and spread over several."""
+    from distributed_crawler_b200.pack import Comment
+    msgs = []
+    for k, n in enumerate([0, 1, 15, 16, 17, 127, 128, 129, 511, 512, 513, 1024, 3000]):
+        body = ("x" * n)
+        msgs.append(Message(id=(k + 1) << 20, text=FormattedText(body)))                       # clean, around the text limit
+        msgs.append(Message(id=(k + 100) << 20, text=FormattedText(body[: max(n - 1, 0)] + "\n")))   # needs escaping
+        msgs.append(Message(id=(k + 200) << 20, text=FormattedText(body[: max(n - 2, 0)] + "é")))    # non-ASCII, clean
+    for nl in range(0, 8):  # outlinks around LANE_LINKS_MAX
+        text = " ".join("t.me/channel_%02d_%d" % (nl, j) for j in range(nl))
+        msgs.append(Message(id=(300 + nl) << 20, text=FormattedText(text)))
+    emoji = ["👍", "❤️", "🔥", "😀", "🎉", "🤔", "👎", "😢", "abcdefgh", "abcdefghi", 'q"k', "a"]
+    for nr in range(0, 9):  # reactions around LANE_MAP_MAX
+        msgs.append(Message(id=(400 + nr) << 20, text=FormattedText("r"), reactions=[(emoji[j], j + 1) for j in range(nr)]))
+    msgs.append(Message(id=500 << 20, reactions=[("👍", 1), ("🔥", 2), ("👍", 3)]))                 # repeated key: last wins
+    msgs.append(Message(id=501 << 20, reactions=[("abcdefgh", 1), ("abcdefghi", 2)]))            # 8- and 9-byte keys
+    msgs.append(Message(id=502 << 20, reactions=[('q"k', 5), ("a", -7)]))                        # key that needs escaping
+    msgs.append(Message(id=503 << 20, reactions=[("", 1), ("b", 2)]))                            # empty key
+    msgs.append(Message(id=504 << 20, comments=None))
+    msgs.append(Message(id=505 << 20, comments=[Comment("c1", [("👍", 1)], 3, 4, "h"), Comment("c\n2", None, 0, 0, "unknown")]))
+    msgs.append(Message(id=506 << 20, handle='ha"ndle', media="m<edia", content_type="messageVideo", text=FormattedText("cap")))
+    rnd = random.Random(5)
+    for order in range(3):
+        rnd.shuffle(msgs)
+        both(pack_telegram(msgs), ALL)
+        both(pack_telegram(msgs[:31]), ALL)
