@@ -143,8 +143,22 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_kernel(TgBatchDev b, 
   int wid = threadIdx.x >> 5;
   uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
-    if (b.ent_off[r + 1] != b.ent_off[r]) continue;  // tg_parse_ent_kernel
-    parse_one_record<false>(b, cfg, o, r, load_rec_view(b, r));
+    // The chain header -> string offset -> text is two DRAM round trips per record and this kernel has little else to
+    // do (long_scoreboard 9 cycles per issue): read the NEXT record's header now, touch its text at the bottom of
+    // the loop, when that load has long completed.
+    const uint64_t rn = r + nwarps;
+    unsigned long long nx_off = 0;
+    uint32_t nx_len = 0;
+    if (rn < b.n) {
+      asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(nx_off) : "l"(&b.recs[rn].str_off));
+      asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(nx_len) : "l"(&b.recs[rn].text_len));
+    }
+    if (b.ent_off[r + 1] == b.ent_off[r])  // the others: tg_parse_ent_kernel
+      parse_one_record<false>(b, cfg, o, r, load_rec_view(b, r));
+    if (rn < b.n) {
+      const uint32_t off = (uint32_t)lane_id() * 128u;
+      if (off < nx_len + 127u && off < 2048u) asm volatile("prefetch.global.L1 [%0];" ::"l"(b.strs + nx_off + off));
+    }
   }
 }
 __global__ void __launch_bounds__(CTA_THREADS, 4) tg_ent_map_kernel(TgBatchDev b, ParseOut o) {
