@@ -1,19 +1,25 @@
 #!/usr/bin/env python3
 """bench.py — messages/sec through the hot path (parse -> link-extract -> filter/dedup -> JSONL).
 
-Contract (see the task statement):  python bench.py --gpus N --steps K --warmup W [--impl reference]
-  * N = 1 workload: BASELINE.json configs[1] — 10 M synthetic Telegram mixed text/photo/video-metadata
-    messages, parse + JSONL on 1 x B200.  N > 1: weak scaling, every rank takes its own 10 M-message
-    shard of the same generator (record-index sharding, no data-path collective) and the ranks merge
-    their dedup sets with one NCCL all-gather per step.
-  * value  = whole-job messages/s with the packed batch already resident in HBM (kernels only).
-  * e2e    = the same metric through the public C ABI call with HOST buffers: pinned-host -> device
-    copy of every input array and device -> pinned-host copy of the JSONL blob, line offsets and
-    status inside the timed region, pipelined over the library's three staging slots.
-  * roofline: the dominant kernel (tg_emit_kernel) — algorithmic bytes per launch / its CUDA-event
-    duration measured live on the launching stream, against MEASURED_PEAKS.json.
-  * cpu_baseline / --impl reference: the CPU oracle (C restatement of the reference's Go path — the
-    reference itself cannot be built here, there is no Go toolchain) on the box's host cores.
+Contract (see the task statement):
+    python bench.py [--config {2,3,4,5}] --gpus N --steps K --warmup W [--impl reference]
+
+--config selects the BASELINE.json workload (default 2 = configs[1], the configuration the metric is quoted on):
+  2  10 M synthetic Telegram mixed text/photo/video-metadata messages per GPU, parse + link-extract + dedup + JSONL
+  3  100 M Telegram text messages per GPU, t.me/@username link-extract + hash-dedup snowball frontier (no JSONL)
+  4  50 M synthetic YouTube video-metadata records per GPU, parse + JSONL, streamed in resident-sized batches
+  5  1 B-message snowball sharded over the ranks (1e9 / N messages per GPU), NCCL set merge, frontier capacity 2^25
+N > 1 is weak scaling for configs 2-4 (every rank takes its own shard of the same generator: record-index
+sharding, no data-path collective) and strong scaling for config 5; the ranks merge their dedup sets once per step.
+
+  * value  = whole-job records/s with the packed batches already resident in HBM (kernels only).
+  * e2e    = the same metric through the public C ABI with HOST buffers: host -> device copy of every input array
+    and device -> pinned-host copy of the results (JSONL blob, line offsets, status, per-record links) inside the
+    timed region, pipelined over the library's three staging slots.
+  * roofline: the dominant kernel of the workload — algorithmic bytes per launch / its CUDA-event duration measured
+    live on the launching stream, against MEASURED_PEAKS.json; plus the whole-step figure (SURVEY.md §8d bytes).
+  * cpu_baseline / --impl reference: the CPU oracle (C restatement of the reference's Go path — the reference itself
+    cannot be built here, there is no Go toolchain) on the box's host cores, same run flags, same corpus.
 One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
@@ -29,12 +35,35 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_MESSAGES = int(os.environ.get("TGI_BENCH_N", 10_000_000))   # configs[1]
-E2E_CHUNK = int(os.environ.get("TGI_BENCH_CHUNK", 500_000))   # records per C-ABI call in the e2e leg
-CPU_SAMPLE = int(os.environ.get("TGI_BENCH_CPU_SAMPLE", 2_000_000))
-SEED = 0x5EED0002
 METRIC = "messages/sec parsed+link-extracted+JSONL"
 UNIT = "messages/s"
+E2E_CHUNK = int(os.environ.get("TGI_BENCH_CHUNK", 500_000))   # records per C-ABI call in the e2e leg
+SLOT_MAX = int(os.environ.get("TGI_BENCH_SLOT_MAX", 34_000_000))  # records per resident slot (links-only configs)
+ORC_RUN_SLICES, ORC_RUN_PIN = 0x10000, 0x20000
+
+J, L, F, S = 0x01, 0x02, 0x04, 0x10  # TGI_RUN_JSONL / LINKS / FRONTIER / SKIP_SELF
+
+
+def configs():
+    env = lambda k, d: int(os.environ.get(k, d))
+    return {
+        2: dict(kind="tg", profile=2, seed=0x5EED0002, n=env("TGI_BENCH_N", 10_000_000), flags=J | L | F | S, scaling="weak",
+                cpu_n=env("TGI_BENCH_CPU_SAMPLE", 2_000_000), ref_n=env("TGI_BENCH_REF_N", 10_000_000), e2e_n=None,
+                fcap=1 << 23,
+                workload="configs[1]: 10M synthetic Telegram mixed text/photo/video-metadata messages, parse+link-extract+dedup+JSONL"),
+        3: dict(kind="tg", profile=3, seed=0x5EED0003, n=env("TGI_BENCH_N", 100_000_000), flags=L | F | S, scaling="weak",
+                cpu_n=env("TGI_BENCH_CPU_SAMPLE", 5_000_000), ref_n=env("TGI_BENCH_REF_N", 20_000_000),
+                e2e_n=env("TGI_BENCH_E2E_N", 20_000_000), fcap=1 << 25,
+                workload="configs[2]: 100M-message t.me/@username link-extract + hash-dedup snowball frontier"),
+        4: dict(kind="yt", profile=0, seed=0x5EED0004, n=env("TGI_BENCH_N", 50_000_000), flags=J | L | F, scaling="weak",
+                cpu_n=env("TGI_BENCH_CPU_SAMPLE", 1_000_000), ref_n=env("TGI_BENCH_REF_N", 2_000_000),
+                e2e_n=env("TGI_BENCH_E2E_N", 5_000_000), fcap=1 << 23, batch=env("TGI_BENCH_YT_BATCH", 5_000_000),
+                workload="configs[3]: 50M synthetic YouTube video-metadata records, parse+JSONL"),
+        5: dict(kind="tg", profile=3, seed=0x5EED0005, n=env("TGI_BENCH_N", 1_000_000_000), flags=L | F | S, scaling="strong",
+                cpu_n=env("TGI_BENCH_CPU_SAMPLE", 5_000_000), ref_n=env("TGI_BENCH_REF_N", 20_000_000),
+                e2e_n=env("TGI_BENCH_E2E_N", 20_000_000), fcap=1 << 25,
+                workload="configs[4]: 1B-message snowball: parse+extract+global hash-dedup sharded across the ranks with NCCL set-merge"),
+    }
 
 
 def ensure_built():
@@ -111,63 +140,107 @@ def load_traffic():
     return None
 
 
-def pin(batch):
-    """page-lock the corpus arrays so the e2e leg's H2D copies come from pinned host memory"""
-    import torch
-    rt = torch.cuda.cudart()
-    pinned = 0
-    for k in batch.FIELDS:
-        a = getattr(batch, k)
-        if a.nbytes:
-            rc = rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
-            if int(rc) == 0:
-                pinned += a.nbytes
-    return pinned
+def bind_numa(local_rank: int):
+    """Keep this rank's threads (and so its pinned staging pages) on the NUMA node of its GPU."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        for line in out.splitlines():
+            f = line.split()
+            if f and f[0] == f"GPU{local_rank}":
+                # columns: GPU0.. NICs.. "CPU Affinity" "NUMA Affinity" ...: take the first a-b[,c-d] token
+                for tok in f[1:]:
+                    if tok and tok[0].isdigit() and ("-" in tok or "," in tok):
+                        cpus = set()
+                        for part in tok.split(","):
+                            a, _, b = part.partition("-")
+                            cpus.update(range(int(a), int(b or a) + 1))
+                        os.sched_setaffinity(0, cpus)
+                        return tok
+    except Exception:
+        pass
+    return None
 
 
-def cpu_baseline(batch, nthreads: int, sample: int, flags: int):
-    from oracle.pyoracle import Oracle
-    sub = batch.slice(0, min(sample, batch.n))
-    o = Oracle()
-    o.telegram(sub, flags, nthreads=nthreads, copy=False)  # warm-up: page in the context-owned buffers
+def make_corpus(cfg, n, first, threads):
+    from distributed_crawler_b200.corpus import Corpus, YtCorpus
+    if cfg["kind"] == "yt":
+        return YtCorpus(n, seed=cfg["seed"], first=first, nthreads=threads)
+    return Corpus(n, seed=cfg["seed"], first=first, profile=cfg["profile"], nthreads=threads)
+
+
+def orc_run(o, cfg, batch, flags, nthreads):
+    return (o.youtube if cfg["kind"] == "yt" else o.telegram)(batch, flags, nthreads=nthreads, copy=False)
+
+
+def cpu_baseline(cfg, batch, cores):
+    """The oracle on the host cores, same run flags: all cores, and one thread on a twentieth of the sample."""
     from oracle import pyoracle
+    from oracle.pyoracle import Oracle
+    flags = cfg["flags"] | ORC_RUN_SLICES | ORC_RUN_PIN
+    o = Oracle()
+    orc_run(o, cfg, batch, flags, cores)  # warm-up: grow the context-owned buffers
     pyoracle.lib().orc_frontier_clear(o.h)
     t0 = time.perf_counter()
-    o.telegram(sub, flags, nthreads=nthreads, copy=False)
+    orc_run(o, cfg, batch, flags, cores)
     dt = time.perf_counter() - t0
     o.close()
-    return sub.n / dt, sub.n, dt
+    o1 = Oracle()
+    n1 = max(1, batch.n // 20)
+    sub = batch.slice(0, n1) if hasattr(batch, "slice") else None
+    v1 = None
+    if sub is not None:
+        orc_run(o1, cfg, sub, cfg["flags"], 1)
+        pyoracle.lib().orc_frontier_clear(o1.h)
+        t1 = time.perf_counter()
+        orc_run(o1, cfg, sub, cfg["flags"], 1)
+        v1 = n1 / (time.perf_counter() - t1)
+    o1.close()
+    return batch.n / dt, dt, v1
 
 
-def run_reference(args, rank, world):
+def run_reference(args, cfg, rank):
     """--impl reference: the reference path's CPU implementation (oracle port) on the host cores."""
     if rank != 0:
         return
-    from distributed_crawler_b200 import abi
-    from distributed_crawler_b200.corpus import Corpus
-    from oracle.pyoracle import Oracle
     from oracle import pyoracle
+    from oracle.pyoracle import Oracle
     cores = os.cpu_count() or 1
-    sample = min(CPU_SAMPLE, N_MESSAGES)
-    c = Corpus(sample, seed=SEED, profile=2, nthreads=min(cores, 64))
-    flags = abi.RUN_JSONL | abi.RUN_LINKS | abi.RUN_FRONTIER | abi.RUN_SKIP_SELF
+    n = min(cfg["ref_n"], cfg["n"])
+    c = make_corpus(cfg, n, 0, min(cores, 64))
+    flags = cfg["flags"] | ORC_RUN_SLICES | ORC_RUN_PIN
     o = Oracle()
     for _ in range(max(args.warmup, 1)):
         pyoracle.lib().orc_frontier_clear(o.h)
-        o.telegram(c.batch, flags, nthreads=cores, copy=False)
+        orc_run(o, cfg, c.batch, flags, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         pyoracle.lib().orc_frontier_clear(o.h)
-        o.telegram(c.batch, flags, nthreads=cores, copy=False)
+        orc_run(o, cfg, c.batch, flags, cores)
     dt = time.perf_counter() - t0
-    v = sample * args.steps / dt
+    v = n * args.steps / dt
+    # one thread, for the per-thread efficiency of the parallel arm
+    v1 = None
+    if hasattr(c.batch, "slice"):
+        sub = c.batch.slice(0, max(1, n // 50))
+        o1 = Oracle()
+        orc_run(o1, cfg, sub, cfg["flags"], 1)
+        pyoracle.lib().orc_frontier_clear(o1.h)
+        t1 = time.perf_counter()
+        orc_run(o1, cfg, sub, cfg["flags"], 1)
+        v1 = sub.n / (time.perf_counter() - t1)
+        o1.close()
+    same = n == cfg["n"]
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": cfg["scaling"],
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1]: 10M synthetic Telegram mixed text/photo/video-metadata messages, parse+JSONL",
-                       "sample": f"first {sample} messages of the same seeded corpus per step"},
+            "config": {"workload": cfg["workload"], "bench_config": args.config, "run_flags": cfg["flags"],
+                       "sample": ("the whole corpus" if same else f"first {n} records of the same seeded corpus") + " per step",
+                       "same_corpus_as_gpu_arm": same},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} messages x {args.steps} steps, C restatement of the Go path, {cores} threads"},
+                             "one_thread": v1, "per_thread_efficiency": (v / cores / v1) if v1 else None,
+                             "sample": f"{n} records x {args.steps} steps, C restatement of the Go path, {cores} threads pinned one per core, "
+                                       "each worker keeps its own output (no global concatenation, like the reference's per-channel files), "
+                                       "sharded frontier insert"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -177,26 +250,29 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    cfg = configs()[args.config]
     ensure_built() if rank == 0 or world == 1 else time.sleep(0)
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, cfg, rank)
         return
 
     import numpy as np
     import torch
     import torch.distributed as dist
     from distributed_crawler_b200 import abi
-    from distributed_crawler_b200.corpus import Corpus
     from distributed_crawler_b200.engine import Engine
-    from distributed_crawler_b200.frontier_merge import EngineFrontier, merge_frontier
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    numa = bind_numa(local) if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -217,18 +293,34 @@ def main():
             os.close(saved_stdout)
 
     cores = os.cpu_count() or 1
-    n = N_MESSAGES
-    t_gen = time.perf_counter()
-    corpus = Corpus(n, seed=SEED, first=rank * n, profile=2, nthreads=max(1, min(cores // max(world, 1), 64)))
-    batch = corpus.batch
-    t_gen = time.perf_counter() - t_gen
-    in_bytes = batch.input_bytes()
-    pinned = pin(batch)
+    gen_threads = max(1, min(cores // max(world, 1), 64))
+    is_yt = cfg["kind"] == "yt"
+    RUN = cfg["flags"]
+    want_json = bool(RUN & J)
+    n = cfg["n"] // world if cfg["scaling"] == "strong" else cfg["n"]   # records per GPU
+    first = rank * n
+    eng = Engine(device=local, frontier_capacity=cfg["fcap"])
+    merger = None
+    if world > 1:
+        from distributed_crawler_b200.frontier_merge import make_merger
+        merger = make_merger(eng, dev)
 
-    eng = Engine(device=local, frontier_capacity=1 << 23)
-    fset = EngineFrontier(eng, dev)
-    RUN = abi.RUN_JSONL | abi.RUN_FRONTIER | abi.RUN_SKIP_SELF
-    eng.telegram_upload(0, batch)
+    # ---- resident batches: up to three slots for Telegram; YouTube streams `batch`-sized uploads through slot 0 ----
+    t_gen = time.perf_counter()
+    if is_yt:
+        per = min(cfg["batch"], n)
+        parts = [(a, min(a + per, n)) for a in range(0, n, per)]
+    else:
+        k = max(1, -(-n // SLOT_MAX)) if not want_json else 1
+        if k > abi.SLOTS:
+            raise SystemExit(f"{n} records per GPU need more than {abi.SLOTS} resident slots of {SLOT_MAX}")
+        parts = [(n * i // k, n * (i + 1) // k) for i in range(k)]
+    corpora = [make_corpus(cfg, b - a, first + a, gen_threads) for a, b in parts]
+    in_bytes = sum(c.batch.input_bytes() for c in corpora)
+    if not is_yt:
+        for i, c in enumerate(corpora):
+            eng.telegram_upload(i, c.batch)
+    t_gen = time.perf_counter() - t_gen
 
     def barrier():
         torch.cuda.synchronize()
@@ -236,124 +328,182 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: kernels only, batch resident in HBM ------------------------------------------------
-    def step_resident():
+    # ---- value: kernels only, batches resident in HBM ------------------------------------------------
+    class Acc:
+        def __init__(self):
+            self.launches = 0
+            self.ms = {"kernel": 0.0, "parse": 0.0, "emit": 0.0, "main": 0.0, "frontier": 0.0}
+            self.jsonl = self.links = self.lane_out = self.lane_in = 0
+            self.upload_s = 0.0
+
+        def add(self, r):
+            self.launches += r.gpu_launches
+            for k2, v in (("kernel", r.kernel_ms), ("parse", r.parse_ms), ("emit", r.emit_ms), ("main", r.emit_main_ms),
+                          ("frontier", getattr(r, "frontier_ms", 0.0))):
+                self.ms[k2] += v
+            self.jsonl += r.jsonl_len; self.links += r.n_links
+            self.lane_out += r.main_bytes_out; self.lane_in += r.main_bytes_in
+
+    def step_resident(acc=None):
         eng.frontier_clear()
-        r = eng.telegram_run_resident(0, RUN | abi.RUN_NO_D2H)
+        r = None
+        if is_yt:
+            for c in corpora:
+                t_up = time.perf_counter()
+                eng.youtube_upload(0, c.batch)
+                if acc:
+                    acc.upload_s += time.perf_counter() - t_up
+                r = eng.youtube_run_resident(0, RUN | abi.RUN_NO_D2H)
+                if acc:
+                    acc.add(r)
+        else:
+            for i in range(len(corpora)):
+                r = eng.telegram_run_resident(i, RUN | abi.RUN_NO_D2H)
+                if acc:
+                    acc.add(r)
         gsize = r.frontier_size
-        if world > 1:
-            gsize, _ = merge_frontier(fset, 0)
-        return r, gsize
+        if merger:
+            gsize = merger.merge()
+        return gsize
 
     for _ in range(max(args.warmup, 3)):
-        r, gsize = step_resident()
+        gsize = step_resident()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    launches = 0
-    emit_ms, parse_ms, kern_ms, fixed_ms = [], [], [], []
+    acc = Acc()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r, gsize = step_resident()
-        launches += r.gpu_launches
-        emit_ms.append(r.emit_ms); parse_ms.append(r.parse_ms); kern_ms.append(r.kernel_ms); fixed_ms.append(r.emit_fixed_ms)
+        gsize = step_resident(acc)
     barrier()
-    dt = time.perf_counter() - t0
+    dt = time.perf_counter() - t0 - acc.upload_s   # YouTube: the uploads between resident batches are not part of `value`
     clocks = sampler.stop()
-    jsonl_len = r.jsonl_len
     dt_t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
     dt_max = float(dt_t.item())
     value = n * world * args.steps / dt_max
+    jsonl_len = acc.jsonl // args.steps
+    n_links = acc.links // args.steps
+    merge_stats = merger.stats() if merger else None
 
     # ---- e2e: host buffers through the C ABI, 3 slots pipelined ----------------------------------
-    chunks = [(a, min(a + E2E_CHUNK, n)) for a in range(0, n, E2E_CHUNK)]
-    subs = [batch.slice(a, b) for a, b in chunks]  # views copied once, outside the timed region
-    for s in subs:
-        pin(s)
+    e2e = None
+    if not args.no_e2e:
+        e2e_n = min(cfg["e2e_n"] or n, n)
+        if is_yt:
+            subs = [make_corpus(cfg, min(E2E_CHUNK, e2e_n - a), first + a, gen_threads).batch for a in range(0, e2e_n, E2E_CHUNK)]
+        else:
+            subs, left = [], e2e_n
+            for c in corpora:  # views copied once, outside the timed region
+                m = min(left, c.batch.n)
+                subs += [c.batch.slice(a, min(a + E2E_CHUNK, m)) for a in range(0, m, E2E_CHUNK)]
+                left -= m
+                if not left:
+                    break
+        staged = [eng.stage(s) for s in subs]  # library-owned pinned input staging (tgi_acquire_staging)
+        submit = eng.youtube_submit if is_yt else eng.telegram_submit
+        wait = eng.youtube_wait if is_yt else eng.telegram_wait
 
-    def step_e2e():
-        eng.frontier_clear()
-        d2h = 0
-        inflight = []
-        for i, sub in enumerate(subs):
-            slot = i % abi.SLOTS
-            if len(inflight) == abi.SLOTS:
-                s0 = inflight.pop(0)
-                rr = eng.telegram_wait(s0)
-                d2h += rr.jsonl_len + rr.n * 9 + 8
+        def step_e2e():
+            eng.frontier_clear()
+            d2h = 0
+            inflight = []
+            for i, sub in enumerate(staged):
+                slot = i % abi.SLOTS
+                if len(inflight) == abi.SLOTS:
+                    s0 = inflight.pop(0)
+                    rr = wait(s0)
+                    d2h += rr.d2h_bytes()
+                    eng.release(s0)
+                submit(slot, sub, RUN)
+                inflight.append(slot)
+            for s0 in inflight:
+                rr = wait(s0)
+                d2h += rr.d2h_bytes()
                 eng.release(s0)
-            eng.telegram_submit(slot, sub, RUN)
-            inflight.append(slot)
-        for s0 in inflight:
-            rr = eng.telegram_wait(s0)
-            d2h += rr.jsonl_len + rr.n * 9 + 8
-            eng.release(s0)
-        if world > 1:
-            merge_frontier(fset, 0)
-        return d2h
+            if merger:
+                merger.merge()
+            return d2h
 
-    for _ in range(2):
-        d2h_bytes = step_e2e()
-    barrier()
-    e2e_steps = max(1, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        d2h_bytes = step_e2e()
-    barrier()
-    dte = time.perf_counter() - t0
-    dte_t = torch.tensor([dte], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dte_t, op=dist.ReduceOp.MAX)
-    e2e_value = n * world * e2e_steps / float(dte_t.item())
-    h2d_bytes = sum(s.input_bytes() for s in subs)
+        for _ in range(2):
+            d2h_bytes = step_e2e()
+        barrier()
+        e2e_steps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            d2h_bytes = step_e2e()
+        barrier()
+        dte = time.perf_counter() - t0
+        dte_t = torch.tensor([dte], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dte_t, op=dist.ReduceOp.MAX)
+        h2d_bytes = sum(s.input_bytes() for s in subs)
+        e2e = {"value": e2e_n * world * e2e_steps / float(dte_t.item()), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "chunk_records": E2E_CHUNK, "slots": abi.SLOTS,
+               "records_per_step_per_gpu": e2e_n, "input_staging": "tgi_acquire_staging (library-owned pinned memory)",
+               "h2d_gbs_per_gpu": h2d_bytes * e2e_steps / dte / 1e9, "d2h_gbs_per_gpu": d2h_bytes * e2e_steps / dte / 1e9,
+               "numa_cpus": numa}
+        for s in staged:
+            eng.unstage(s)
+        del staged, subs
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        # whole step: every input byte read once, every output byte written once
-        alg_bytes = in_bytes + jsonl_len + 8 * (n + 1)
         step_ms = dt_max / args.steps * 1e3
-        # dominant kernel tg_emit_lane_kernel (one lane per record, tg_lane.cuh): per record it reads the
-        # 64-byte header, 8 bytes of line offset and 32 bytes of piece lengths, writes 32 bytes of piece
-        # offsets, writes `lane_bytes_out` JSONL bytes (counted by the kernel itself) of which
-        # `lane_bytes_in` are copies of HBM-resident sources (message strings, pre-rendered channel blob)
-        lane_alg = n * (64 + 8 + 32 + 32) + r.lane_bytes_out + r.lane_bytes_in
-        fm = sum(fixed_ms) / len(fixed_ms)
-        em = sum(emit_ms) / len(emit_ms)
-        achieved = lane_alg / (fm * 1e-3) / 1e9
-        traffic = load_traffic()
-        roofline = {"bound": "hbm", "kernel": "tg_emit_lane_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "peak_source": peak_src,
-                    "traffic": (traffic or {}).get("tg_emit_lane_kernel_bytes_per_launch"),
-                    "algorithmic_bytes_per_launch": lane_alg, "kernel_ms": fm,
-                    "kernel_share_of_step": fm / step_ms,
-                    "lane_bytes_out": r.lane_bytes_out, "lane_bytes_in": r.lane_bytes_in,
-                    "emit_pass": {"kernels": "tg_emit_lane_kernel + tg_emit_esc_kernel + tg_emit_maps_kernel", "ms": em,
-                                  "achieved": (in_bytes + jsonl_len + 8 * (n + 1)) / (em * 1e-3) / 1e9},
+        per = lambda k2: acc.ms[k2] / args.steps
+        traffic = load_traffic() or {}
+        if want_json:
+            # whole step: every input byte read once, every output byte written once, 8 B line offset
+            alg_bytes = in_bytes + jsonl_len + 8 * (n + 1)
+            kname = "yt_emit_tile_kernel" if is_yt else "tg_emit_tile_kernel"
+            # the emit kernel: per record it reads the header, the line offset and the piece lengths of the size pass,
+            # reads every source byte it copies and writes every JSONL byte (both counted by the kernel itself)
+            k_alg = (acc.lane_out + acc.lane_in) // args.steps + n * (64 + 8 + 32)
+            k_ms = per("main")
+        else:
+            # link-extract + dedup: mini header 24 B + text + entities + entity URLs read once,
+            # 32 B key write + 64 B hash-slot read-modify-write per link reaching the set
+            alg_bytes = sum(24 * c.batch.n + c.batch.strs.nbytes + c.batch.ents.nbytes + c.batch.aux.nbytes for c in corpora) + 96 * n_links
+            kname = "tg_scan_kernel"
+            k_alg = alg_bytes - 96 * n_links + 36 * n_links
+            k_ms = per("parse")
+        achieved = k_alg / (k_ms * 1e-3) / 1e9 if k_ms else 0.0
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic.get(kname + "_bytes_per_launch"),
+                    "algorithmic_bytes_per_launch": k_alg, "kernel_ms": k_ms, "kernel_share_of_step": k_ms / step_ms,
+                    "passes_ms": {"scan+size": per("parse"), "emit": per("emit"), "frontier": per("frontier"), "all_kernels": per("kernel")},
                     "step": {"algorithmic_bytes": alg_bytes, "achieved": alg_bytes / (step_ms * 1e-3) / 1e9,
-                             "frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak,
-                             "parse_pass_ms": sum(parse_ms) / len(parse_ms), "kernels_ms": sum(kern_ms) / len(kern_ms)}}
-        cpu_v = cpu_n = cpu_dt = None
-        if world == 1 or True:
-            cpu_v, cpu_n, cpu_dt = cpu_baseline(batch, cores, CPU_SAMPLE, abi.RUN_JSONL | abi.RUN_LINKS | abi.RUN_FRONTIER | abi.RUN_SKIP_SELF)
+                             "frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak}}
+        cpu = None
+        if not args.no_cpu:
+            sample_n = min(cfg["cpu_n"], corpora[0].batch.n)
+            sample = corpora[0].batch.slice(0, sample_n) if hasattr(corpora[0].batch, "slice") else make_corpus(cfg, sample_n, first, gen_threads).batch
+            cpu_v, cpu_dt, cpu_v1 = cpu_baseline(cfg, sample, cores)
+            cpu = {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "one_thread": cpu_v1,
+                   "per_thread_efficiency": (cpu_v / cores / cpu_v1) if cpu_v1 else None,
+                   "sample": f"first {sample_n} records of the same corpus, {cpu_dt:.1f} s, C restatement of the Go path (oracle), same run flags, "
+                             f"{cores} threads pinned one per core, warm"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": "configs[1]: 10M synthetic Telegram mixed text/photo/video-metadata messages, parse+link-extract+dedup+JSONL",
-                       "messages_per_gpu": n, "seed": hex(SEED), "input_bytes_per_gpu": in_bytes, "jsonl_bytes_per_gpu": jsonl_len,
+            "config": {"workload": cfg["workload"], "bench_config": args.config, "run_flags": RUN,
+                       "records_per_gpu": n, "resident_batches": len(corpora), "seed": hex(cfg["seed"]), "input_bytes_per_gpu": in_bytes,
+                       "jsonl_bytes_per_gpu": jsonl_len, "links_per_gpu": n_links,
                        "l2": "inputs (%.1f GB) and outputs (%.1f GB) per step are far larger than the 126 MB L2" % (in_bytes / 1e9, jsonl_len / 1e9),
-                       "parallelism": f"record-index sharding x{world}" + ("; NCCL all-gather set merge per step" if world > 1 else ""),
+                       "timing": "wall clock around the K steps between barriers + synchronize, max over ranks"
+                                 + ("; host->device uploads between the resident YouTube batches excluded" if is_yt else ""),
+                       "parallelism": f"record-index sharding x{world}" + ("; NCCL set merge per step: " + merger.describe() if merger else ""),
                        "frontier_unique": int(gsize), "corpus_gen_s": round(t_gen, 2)},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "steps": e2e_steps, "chunk_records": E2E_CHUNK, "slots": abi.SLOTS, "pinned_input_bytes": pinned},
-            "gpu_launches": launches,
+            "e2e": e2e,
+            "gpu_launches": acc.launches,
             "roofline": roofline,
-            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"first {cpu_n} messages of the same corpus, {cpu_dt:.1f} s, C restatement of the Go path (oracle), {cores} threads, warm"},
+            "cpu_baseline": cpu,
         }
+        if merge_stats:
+            line["merge"] = merge_stats
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -562,3 +562,210 @@ tgc_corpus* tgc_telegram(uint64_t seed, uint64_t first, uint64_t n, int profile,
 
 const tgi_tg_batch* tgc_batch(const tgc_corpus* c) { return &c->b; }
 uint64_t tgc_total_bytes(const tgc_corpus* c) { return c->total_bytes; }
+
+/* ---- YouTube (BASELINE config 4; shape: SURVEY.md §8d) ---------------------------------------------
+ * id 11 base64url chars; title lognormal median 45 B; description lognormal median 400 B clipped at 5000 with
+ * Poisson(1.5) URLs of which 5 % are youtube.com/channel/UC..., 5 % youtube.com/@handle; views lognormal(8, 3),
+ * likes = views / 30, comments = views / 300; durations PT#H#M#S (1 % P0D, 0.5 % empty, 0.5 % P1DT2H);
+ * 3-5 thumbnails; 1000 cached channels.  2 % of the descriptions carry characters that need escaping, 10 % are
+ * Cyrillic (valid multi-byte UTF-8 that passes through unescaped).  Same determinism rule as the Telegram
+ * generator: record k draws from its own stream keyed by (seed, k).                                        */
+typedef struct tgc_yt_corpus {
+  tgi_yt_batch b;
+  uint64_t total_bytes;
+} tgc_yt_corpus;
+
+typedef struct {
+  uint64_t seed, first, r0, r1;
+  uint32_t n_chans;
+  buf_t recs, strs;
+} ytgen_t;
+
+static const char B64U[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789-_";
+static const char* YT_PLAIN[] = {"the", "video", "about", "channel", "new", "watch", "and", "more", "from", "this",
+                                 "week", "episode", "review", "how", "to", "guide", "music", "official", "live", "part",
+                                 "best", "of", "2024", "full", "with", "our", "your", "for", "you", "in"};
+
+static uint32_t rnd_poisson(rng_t* r, double lam) {
+  const double L = exp(-lam);
+  uint32_t k = 0;
+  double p = 1.0;
+  for (;;) {
+    p *= rnd01(r);
+    if (p <= L) return k;
+    k++;
+  }
+}
+static void yt_words(rng_t* r, buf_t* t, size_t nbytes, int cyr) {
+  const size_t t0 = t->len;
+  while (t->len - t0 < nbytes) {
+    if (cyr) {
+      int wl = 2 + (int)rnd_n(r, 9);
+      for (int i = 0; i < wl; i++) put_cp(t, 0x0430 + rnd_n(r, 32));
+    } else {
+      const char* w = YT_PLAIN[rnd_n(r, 30)];
+      b_put(t, w, strlen(w));
+    }
+    b_putc(t, ' ');
+  }
+  if (t->len > t0) t->len--; /* no trailing blank */
+}
+static void yt_gen_record(ytgen_t* g, uint64_t k) {
+  rng_t r = {mix64(g->seed ^ mix64(k + 0x7654321ull))};
+  tgi_yt_rec rec;
+  memset(&rec, 0, sizeof rec);
+  rec.str_off = g->strs.len;
+  char id[12];
+  for (int i = 0; i < 11; i++) id[i] = B64U[rnd_n(&r, 64)];
+  b_put(&g->strs, id, 11);
+  rec.id_len = 11;
+  size_t s0 = g->strs.len;
+  const int cyr = rnd01(&r) < 0.10;
+  double tl = exp(3.8 + 0.5 * rnd_normal(&r));
+  yt_words(&r, &g->strs, (size_t)(tl > 300 ? 300 : tl), cyr);
+  rec.title_len = (uint16_t)(g->strs.len - s0);
+  s0 = g->strs.len;
+  double dl = exp(5.99 + 0.9 * rnd_normal(&r));
+  const size_t target = (size_t)(dl > 5000 ? 5000 : dl);
+  const uint32_t nurls = rnd_poisson(&r, 1.5);
+  for (uint32_t u = 0; u <= nurls; u++) {
+    const size_t done = g->strs.len - s0;
+    const size_t seg = done < target ? (target - done) / (nurls - u + 1) : 0;
+    if (seg) yt_words(&r, &g->strs, seg, cyr);
+    if (u == nurls) break;
+    if (g->strs.len > s0) b_putc(&g->strs, ' ');
+    const double w = rnd01(&r);
+    char link[96];
+    int ll;
+    if (w < 0.05) {
+      ll = snprintf(link, sizeof link, "https://www.youtube.com/channel/UC");
+      for (int i = 0; i < 22; i++) link[ll++] = B64U[zipf(&r, 2000000u, 1.05) * 2654435761u >> (i & 7) & 63];
+    } else if (w < 0.10) {
+      ll = snprintf(link, sizeof link, "https://youtube.com/@");
+      char nm[64];
+      int nn = make_name(zipf(&r, 2000000u, 1.05), nm);
+      memcpy(link + ll, nm, (size_t)nn);
+      ll += nn;
+    } else {
+      ll = snprintf(link, sizeof link, "https://example.com/");
+      int tail = 4 + (int)rnd_n(&r, 16);
+      for (int i = 0; i < tail; i++) link[ll++] = B64U[rnd_n(&r, 64)];
+    }
+    b_put(&g->strs, link, (size_t)ll);
+    b_putc(&g->strs, ' ');
+  }
+  while (g->strs.len > s0 && g->strs.p[g->strs.len - 1] == ' ') g->strs.len--;
+  if (rnd01(&r) < 0.02) {
+    static const char esc[] = "\n\"quoted\" <tag> & more\n";
+    b_put(&g->strs, esc, sizeof esc - 1);
+  }
+  rec.desc_len = (uint32_t)(g->strs.len - s0);
+  s0 = g->strs.len;
+  {
+    const double u = rnd01(&r);
+    char d[32];
+    int n = u < 0.01 ? snprintf(d, sizeof d, "P0D") : u < 0.015 ? 0 : u < 0.02 ? snprintf(d, sizeof d, "P1DT2H")
+            : snprintf(d, sizeof d, "PT%uH%uM%uS", rnd_n(&r, 3), rnd_n(&r, 60), rnd_n(&r, 60));
+    b_put(&g->strs, d, (size_t)n);
+  }
+  rec.duration_len = (uint16_t)(g->strs.len - s0);
+  b_put(&g->strs, "en", 2);
+  rec.lang_len = 2;
+  static const char* KEY[5] = {"default", "medium", "high", "standard", "maxres"};
+  const uint32_t nth = 3 + rnd_n(&r, 3);
+  for (uint32_t t = 0; t < 5; t++) {
+    if (t < nth) {
+      char url[96];
+      int n = snprintf(url, sizeof url, "https://i.ytimg.com/vi/%.11s/%s.jpg", id, KEY[t]);
+      b_put(&g->strs, url, (size_t)n);
+      rec.thumb_len[t] = (uint16_t)n;
+    } else {
+      rec.thumb_len[t] = TGI_YT_THUMB_ABSENT;
+    }
+  }
+  rec.published_sec = 1300000000ll + (int64_t)rnd_n(&r, 460000000u);
+  const double v = exp(8.0 + 3.0 * rnd_normal(&r));
+  rec.view_count = v > 9e18 ? (int64_t)9e18 : (int64_t)v;
+  rec.like_count = rec.view_count / 30;
+  rec.comment_count = rec.view_count / 300;
+  rec.chan_idx = rnd_n(&r, g->n_chans);
+  b_put(&g->recs, &rec, sizeof rec);
+}
+static void* yt_gen_worker(void* arg) {
+  ytgen_t* g = (ytgen_t*)arg;
+  for (uint64_t k = g->r0; k < g->r1; k++) yt_gen_record(g, g->first + k);
+  return NULL;
+}
+
+void tgc_yt_free(tgc_yt_corpus* c) {
+  if (!c) return;
+  free((void*)c->b.recs); free((void*)c->b.strs); free((void*)c->b.chans); free((void*)c->b.chan_strs);
+  free(c);
+}
+
+tgc_yt_corpus* tgc_youtube(uint64_t seed, uint64_t first, uint64_t n, int nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  if ((uint64_t)nthreads > n) nthreads = n ? (int)n : 1;
+  const uint32_t n_chans = 1000;
+  ytgen_t* g = (ytgen_t*)calloc((size_t)nthreads, sizeof(ytgen_t));
+  pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
+  for (int t = 0; t < nthreads; t++) {
+    g[t].seed = seed; g[t].first = first; g[t].n_chans = n_chans;
+    g[t].r0 = n * (uint64_t)t / (uint64_t)nthreads;
+    g[t].r1 = n * (uint64_t)(t + 1) / (uint64_t)nthreads;
+    if (nthreads > 1) pthread_create(&th[t], NULL, yt_gen_worker, &g[t]); else yt_gen_worker(&g[t]);
+  }
+  if (nthreads > 1) for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  size_t S = 0;
+  for (int t = 0; t < nthreads; t++) S += g[t].strs.len;
+  tgc_yt_corpus* c = (tgc_yt_corpus*)calloc(1, sizeof *c);
+  tgi_yt_rec* recs = (tgi_yt_rec*)xalloc(n * sizeof(tgi_yt_rec));
+  uint8_t* strs = (uint8_t*)xalloc(S);
+  size_t so = 0;
+  uint64_t ri = 0;
+  for (int t = 0; t < nthreads; t++) {
+    const uint64_t m = g[t].r1 - g[t].r0;
+    memcpy(strs + so, g[t].strs.p, g[t].strs.len);
+    memcpy(recs + ri, g[t].recs.p, m * sizeof(tgi_yt_rec));
+    for (uint64_t i = 0; i < m; i++) recs[ri + i].str_off += so;
+    so += g[t].strs.len; ri += m;
+    free(g[t].recs.p); free(g[t].strs.p);
+  }
+  tgi_yt_chan* chans = (tgi_yt_chan*)xalloc(n_chans * sizeof(tgi_yt_chan));
+  buf_t cs = {0};
+  for (uint32_t i = 0; i < n_chans; i++) {
+    tgi_yt_chan ch;
+    memset(&ch, 0, sizeof ch);
+    rng_t cr = {mix64(seed ^ (0xCAFEull + i))};
+    ch.str_off = (uint32_t)cs.len;
+    char tmp[96];
+    int n2 = 2;
+    tmp[0] = 'U'; tmp[1] = 'C';
+    for (int k = 0; k < 22; k++) tmp[n2++] = B64U[rnd_n(&cr, 64)];
+    b_put(&cs, tmp, (size_t)n2); ch.id_len = (uint16_t)n2;
+    n2 = snprintf(tmp, sizeof tmp, "Channel %u", i);
+    b_put(&cs, tmp, (size_t)n2); ch.title_len = (uint16_t)n2;
+    size_t a = cs.len;
+    yt_words(&cr, &cs, 100, 0);
+    ch.desc_len = (uint32_t)(cs.len - a);
+    n2 = snprintf(tmp, sizeof tmp, "https://yt3.ggpht.com/");
+    for (int k = 0; k < 30; k++) tmp[n2++] = B64U[rnd_n(&cr, 64)];
+    b_put(&cs, tmp, (size_t)n2); ch.thumb_len = (uint16_t)n2;
+    b_put(&cs, "US", 2); ch.country_len = 2;
+    ch.subscriber_count = (int64_t)rnd_n(&cr, 10000000u);
+    ch.view_count = (int64_t)(rnd(&cr) % 10000000000ull);
+    ch.video_count = (int64_t)rnd_n(&cr, 10000u);
+    ch.published_sec = 1100000000ll + (int64_t)rnd_n(&cr, 600000000u);
+    ch.cached = 1;
+    chans[i] = ch;
+  }
+  uint8_t* chan_strs = (uint8_t*)xalloc(cs.len);
+  memcpy(chan_strs, cs.p, cs.len);
+  c->b.n = n; c->b.recs = recs; c->b.strs = strs; c->b.strs_len = S;
+  c->b.n_chans = n_chans; c->b.chans = chans; c->b.chan_strs = chan_strs; c->b.chan_strs_len = cs.len;
+  c->total_bytes = n * sizeof(tgi_yt_rec) + S + n_chans * sizeof(tgi_yt_chan) + cs.len;
+  free(cs.p); free(g); free(th);
+  return c;
+}
+const tgi_yt_batch* tgc_yt_batch(const tgc_yt_corpus* c) { return &c->b; }
+uint64_t tgc_yt_total_bytes(const tgc_yt_corpus* c) { return c->total_bytes; }

@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # error codes
 OK, E_ARG, E_CUDA, E_NOMEM, E_CAPACITY, E_NODEVICE, E_STATE = 0, -1, -2, -3, -4, -5, -6
@@ -121,8 +121,13 @@ class ResultC(C.Structure):
         ("line_off", C.c_void_p), ("link_off", C.c_void_p), ("links", C.c_void_p),
         ("n_links", C.c_uint64), ("n_new", C.c_uint64), ("frontier_size", C.c_uint64),
         ("kernel_ms", C.c_float), ("gpu_launches", C.c_uint32), ("parse_ms", C.c_float),
-        ("emit_ms", C.c_float), ("slot", C.c_int32), ("emit_fixed_ms", C.c_float), ("var_bytes", C.c_uint64),
-        ("lane_bytes_out", C.c_uint64), ("lane_bytes_in", C.c_uint64)]
+        ("emit_ms", C.c_float), ("slot", C.c_int32), ("emit_main_ms", C.c_float), ("var_bytes", C.c_uint64),
+        ("main_bytes_out", C.c_uint64), ("main_bytes_in", C.c_uint64), ("frontier_ms", C.c_float), ("reserved", C.c_uint32)]
+
+
+class MergeStatsC(C.Structure):
+    _fields_ = [("merges", C.c_uint64), ("keys_sent", C.c_uint64), ("keys_received", C.c_uint64), ("keys_owned", C.c_uint64),
+                ("bytes_sent", C.c_uint64), ("bucket_ms", C.c_double), ("exchange_ms", C.c_double), ("insert_ms", C.c_double)]
 
 
 class StatsC(C.Structure):

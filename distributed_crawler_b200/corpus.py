@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 from . import abi
-from .pack import TgBatch
+from .pack import TgBatch, YtBatch
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _DIR = os.path.join(_ROOT, "corpus")
@@ -40,6 +40,11 @@ def _lib():
         L.tgc_free.argtypes = [C.c_void_p]
         L.tgc_total_bytes.restype = C.c_uint64
         L.tgc_total_bytes.argtypes = [C.c_void_p]
+        L.tgc_youtube.restype = C.c_void_p
+        L.tgc_youtube.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]
+        L.tgc_yt_batch.restype = C.POINTER(abi.YtBatchC)
+        L.tgc_yt_batch.argtypes = [C.c_void_p]
+        L.tgc_yt_free.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -75,6 +80,28 @@ class Corpus:
         if getattr(self, "_h", None):
             self.batch = None
             _lib().tgc_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class YtCorpus:
+    """YouTube corpus shard [first, first+n) in the BASELINE config-4 shape. `.batch` is a YtBatch over
+    generator-owned memory."""
+
+    def __init__(self, n: int, *, seed: int = 0x5EED0004, first: int = 0, nthreads: int | None = None):
+        nthreads = nthreads or min(os.cpu_count() or 1, 64)
+        self._h = _lib().tgc_youtube(seed, first, n, nthreads)
+        b = _lib().tgc_yt_batch(self._h).contents
+        self.batch = YtBatch(recs=_view(b.recs, n * 80, abi.YT_REC), strs=_view(b.strs, b.strs_len, np.uint8),
+                             chans=_view(b.chans, b.n_chans * 64, abi.YT_CHAN),
+                             chan_strs=_view(b.chan_strs, b.chan_strs_len, np.uint8))
+        self.batch._owner = self
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.batch = None
+            _lib().tgc_yt_free(self._h)
             self._h = None
 
     __del__ = close

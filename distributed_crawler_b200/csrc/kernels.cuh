@@ -99,7 +99,7 @@ DEVI void parse_one_record(const TgBatchDev& b, const CfgDev& cfg, const ParseOu
     }
     if (!ENTITIES) v.e1 = v.e0;
     uint32_t ub = warp_link_upper_bound(v, b.ents);
-    if (ub > 4096) {  // seq packing of the frontier needs ordinal < 4096
+    if (ub >= (1u << 20)) {  // seq packing of the frontier needs ordinal < 2^20 (SEQ_ORD_BITS)
       if (l == 0) atomicOr(o.err, ERR_TOO_MANY_LINKS);
       ub = 0;
     }
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) yt_parse_kernel(YtBatchDev b, 
     }
     if (run_flags & (TGI_RUN_LINKS | TGI_RUN_FRONTIER)) {
       uint32_t lb = yt_count_ytcom(desc, v.desc_len);
-      if (lb > 4096) {
+      if (lb >= (1u << 20)) {
         if (l == 0) atomicOr(o.err, ERR_TOO_MANY_LINKS);
         lb = 0;
       }
@@ -876,13 +876,17 @@ struct FrontierDev {
   uint64_t* table;   // persistent table: 0 = empty, else (pool_idx+1) | fp << 40
   uint64_t tmask;
   uint64_t* count;   // device scalar: number of keys in the pool
+  uint64_t* payload; // optional [cap]: 64-bit payload of every key (the owned partition of the multi-GPU merge)
 };
 struct FrontierBatch {
-  uint64_t* btable;  // per-batch table: 0 = empty, else ((rec << 12) | ordinal) + 1 (atomicMin'd)
+  uint64_t* btable;  // per-batch table: 0 = empty, else ((rec << SEQ_ORD_BITS) | ordinal) + 1 (atomicMin'd)
   uint64_t bmask;
   uint32_t* lstate;  // per arena slot: LS_* or batch-table slot index
   uint32_t* rec_new; // [n] new keys first seen in this record
 };
+// sequence number of a link inside a batch: (record << 20) | ordinal.  Records < 2^40 (checked by the host), so a
+// record may carry up to 2^20 link candidates (> 10 MB of text: beyond anything TDLib delivers; the host checks)
+constexpr int SEQ_ORD_BITS = 20;
 #define LS_INELIGIBLE 0xFFFFFFFFu
 #define LS_KNOWN 0xFFFFFFFEu
 
@@ -954,7 +958,7 @@ __global__ void frontier_probe_kernel(uint64_t n, const uint32_t* link_start, co
       fb.lstate[idx] = LS_KNOWN;
       continue;
     }
-    uint64_t v = (((uint64_t)r << 12) | k) + 1;
+    uint64_t v = (((uint64_t)r << SEQ_ORD_BITS) | k) + 1;
     for (uint64_t s = (h >> 7) & fb.bmask;; s = (s + 1) & fb.bmask) {
       uint64_t cur = fb.btable[s];
       if (cur == 0) {
@@ -964,7 +968,7 @@ __global__ void frontier_probe_kernel(uint64_t n, const uint32_t* link_start, co
           break;
         }
       }
-      uint64_t r2 = (cur - 1) >> 12, k2 = (cur - 1) & 4095;
+      uint64_t r2 = (cur - 1) >> SEQ_ORD_BITS, k2 = (cur - 1) & ((1u << SEQ_ORD_BITS) - 1u);
       uint32_t ls2 = link_start ? link_start[r2] : (uint32_t)r2;
       if (key_eq(key, load_key(arena[ls2 + k2].name))) {
         atomicMin((unsigned long long*)&fb.btable[s], (unsigned long long)v);
@@ -985,7 +989,7 @@ __global__ void frontier_count_kernel(uint64_t n, const uint32_t* link_start, co
   for (uint32_t k = 0; k < cnt; k++) {
     uint32_t st = fb.lstate[ls + k];
     if (st >= LS_KNOWN) continue;
-    if (fb.btable[st] == (((uint64_t)r << 12) | k) + 1) c++;
+    if (fb.btable[st] == (((uint64_t)r << SEQ_ORD_BITS) | k) + 1) c++;
   }
   fb.rec_new[r] = c;
 }
@@ -993,7 +997,7 @@ __global__ void frontier_count_kernel(uint64_t n, const uint32_t* link_start, co
 // phase 3: append the new keys to the pool in (record, ordinal) order and publish them
 __global__ void frontier_append_kernel(uint64_t n, const uint32_t* link_start, const uint32_t* link_count,
                                        tgi_link* arena, FrontierDev f, FrontierBatch fb,
-                                       const uint64_t* new_off, int* err) {
+                                       const uint64_t* new_off, int* err, const uint64_t* payload_in = nullptr) {
   uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   if (!fb.rec_new[r]) return;
@@ -1008,12 +1012,13 @@ __global__ void frontier_append_kernel(uint64_t n, const uint32_t* link_start, c
   for (uint32_t k = 0; k < cnt; k++) {
     uint32_t st = fb.lstate[ls + k];
     if (st >= LS_KNOWN) continue;
-    if (fb.btable[st] != (((uint64_t)r << 12) | k) + 1) continue;
+    if (fb.btable[st] != (((uint64_t)r << SEQ_ORD_BITS) | k) + 1) continue;
     tgi_link& lk = arena[ls + k];
     Key32 key = load_key(lk.name);
     uint32_t* dst = (uint32_t*)(f.pool + 32 * pi);
 #pragma unroll
     for (int i = 0; i < 8; i++) dst[i] = key.w[i];
+    if (f.payload) f.payload[pi] = payload_in ? payload_in[r] : 0ull;  // keys mode: one key per "record"
     uint64_t h = key_hash(key);
     uint64_t e = (pi + 1) | (((h >> 40) | 1ull) << 40);
     for (uint64_t s = h & f.tmask;; s = (s + 1) & f.tmask) {
@@ -1033,6 +1038,31 @@ __global__ void frontier_commit_kernel(FrontierDev f, const uint64_t* new_off, u
     atomicOr(err, ERR_FRONTIER_FULL);
   }
   out_new[1] = *f.count;
+}
+
+// ---- multi-GPU merge (SURVEY 8e option A): bucket the new local keys by owner rank ----------------------------------
+DEVI uint32_t key_owner(const Key32& k, uint32_t nranks) { return (uint32_t)((key_hash(k) >> 17) % nranks); }
+__global__ void merge_count_kernel(const uint8_t* pool, uint64_t first, uint64_t m, uint32_t nranks, unsigned long long* cnt) {
+  __shared__ unsigned int sc[64];
+  if (threadIdx.x < 64) sc[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) atomicAdd(&sc[key_owner(load_key(pool + 32 * (first + i)), nranks)], 1u);
+  __syncthreads();
+  if (threadIdx.x < nranks && sc[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], (unsigned long long)sc[threadIdx.x]);
+}
+// cursor[p] starts at the offset of bucket p in the send buffers; the order inside a bucket is irrelevant (the keys
+// of one rank are distinct and every key carries its sequence number)
+__global__ void merge_scatter_kernel(const uint8_t* pool, uint64_t first, uint64_t m, uint32_t nranks, unsigned long long* cursor,
+                                     uint8_t* send_keys, uint64_t* send_pay, uint64_t pay_base) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const Key32 k = load_key(pool + 32 * (first + i));
+  const unsigned long long pos = atomicAdd(&cursor[key_owner(k, nranks)], 1ull);
+  uint32_t* dst = (uint32_t*)(send_keys + 32 * pos);
+#pragma unroll
+  for (int j = 0; j < 8; j++) dst[j] = k.w[j];
+  send_pay[pos] = pay_base | (first + i);
 }
 
 // keys32 -> pseudo arena (one link per "record") for tgi_frontier_insert

@@ -3,13 +3,17 @@
 // and worker thread, so H2D of one batch, kernels of another and D2H of a third overlap.
 // There is no CPU fallback: without a CUDA device tgi_create fails with TGI_E_NODEVICE.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library itself is loaded with dlopen at tgi_comm_init
 
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <map>
 #include <string>
 #include <thread>
 #include <vector>
@@ -25,6 +29,10 @@ constexpr size_t PAD = 64;  // zero bytes behind every device blob (kernels over
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }  // error paths of the one-shot entry points must not leak device memory
   cudaError_t ensure(size_t bytes) {
     bytes += PAD;
     if (bytes <= cap) return cudaSuccess;
@@ -66,10 +74,30 @@ struct HostBuf {  // pinned
 
 enum JobKind { JOB_NONE = 0, JOB_TG, JOB_TG_RESIDENT, JOB_TG_UPLOAD, JOB_YT, JOB_YT_RESIDENT, JOB_YT_UPLOAD, JOB_GM, JOB_QUIT };
 
+struct InsertScratch {
+  DevBuf arena, cnt, lstate, recnew, newoff, btable, tiles, sc;
+};
+
+// the NCCL entry points the merge uses, resolved at run time
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
 struct Slot {
   int idx = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_mid = nullptr, ev_p0 = nullptr, ev_p1 = nullptr, ev_e0 = nullptr, ev_e1 = nullptr, ev_f1 = nullptr;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_mid = nullptr, ev_p0 = nullptr, ev_p1 = nullptr, ev_e0 = nullptr, ev_e1 = nullptr, ev_f1 = nullptr, ev_fr0 = nullptr, ev_fr1 = nullptr;
   // device inputs
   DevBuf d_recs, d_strs, d_ent_off, d_ents, d_react_off, d_reacts, d_comment_off, d_comments, d_aux,
       d_chans, d_chan_strs;
@@ -115,12 +143,28 @@ struct tgi_ctx {
   DevBuf d_cfg;
   CfgDev cfgdev{};
   std::mutex cfg_mu;
-  // frontier
+  // frontier: the local set (every key this GPU has seen)
   DevBuf d_pool, d_table, d_fcount, d_err;
   FrontierDev fr{};
   std::mutex fr_mu;
   cudaEvent_t fr_event = nullptr;
   bool fr_event_valid = false;
+  InsertScratch ins;  // scratch of tgi_frontier_insert* / the merge (under fr_mu)
+  // multi-GPU merge: communicator + this rank's partition of the global set
+  NcclApi* nccl = nullptr;
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  DevBuf o_pool, o_table, o_count, o_payload;
+  FrontierDev owned{};
+  uint64_t merged_upto = 0, merge_round = 0;
+  DevBuf m_cnt, m_all, m_cursor, m_send_keys, m_send_pay, m_recv_keys, m_recv_pay, m_gsize;
+  HostBuf m_host;
+  cudaEvent_t m_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  tgi_merge_stats mstats{};
+  // pinned input staging blocks handed to the packer
+  std::mutex stg_mu;
+  std::map<void*, size_t> stg_live;
+  std::multimap<size_t, void*> stg_free;
   // stats
   std::mutex st_mu;
   tgi_stats stats{};
@@ -355,6 +399,7 @@ int finish_batch(tgi_ctx* c, Slot& s, uint64_t n, uint32_t flags, uint64_t line_
     CK(s.d_lstate.ensure((size_t)arena_cap * 4));
     CK(s.d_rec_new.ensure(n * 4));
     CK(s.d_new_off.ensure((n + 1) * 8));
+    CK(cudaEventRecord(s.ev_fr0, st));
     CK(cudaMemsetAsync(s.d_btable.p, 0, bslots * 8, st));
     FrontierBatch fb;
     fb.btable = s.d_btable.as<uint64_t>();
@@ -374,6 +419,7 @@ int finish_batch(tgi_ctx* c, Slot& s, uint64_t n, uint32_t flags, uint64_t line_
     frontier_commit_kernel<<<1, 1, 0, st>>>(c->fr, s.d_new_off.as<uint64_t>(), n, dsc + SC_NEW, derr);
     launches += 2;
     CK(cudaGetLastError());
+    CK(cudaEventRecord(s.ev_fr1, st));
     CK(cudaEventRecord(c->fr_event, st));
     c->fr_event_valid = true;
   }
@@ -427,11 +473,12 @@ int finish_batch(tgi_ctx* c, Slot& s, uint64_t n, uint32_t flags, uint64_t line_
   if (n) cudaEventElapsedTime(&out->parse_ms, s.ev_p0, s.ev_p1);
   if (n && want_json) {
     cudaEventElapsedTime(&out->emit_ms, s.ev_e0, s.ev_e1);
-    cudaEventElapsedTime(&out->emit_fixed_ms, s.ev_e0, s.ev_f1);
+    cudaEventElapsedTime(&out->emit_main_ms, s.ev_e0, s.ev_f1);
     out->var_bytes = var_bytes;
-    out->lane_bytes_out = hsc[SC_LANE_OUT];
-    out->lane_bytes_in = hsc[SC_LANE_IN];
+    out->main_bytes_out = hsc[SC_LANE_OUT];
+    out->main_bytes_in = hsc[SC_LANE_IN];
   }
+  if (want_fr && n) cudaEventElapsedTime(&out->frontier_ms, s.ev_fr0, s.ev_fr1);
   out->jsonl_len = want_json ? line_total : 0;
   out->n_links = n_links_total;
   out->n_new = want_fr ? hsc[SC_NEW] : 0;
@@ -558,7 +605,7 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   }
   if (dev_err & ERR_ARENA_OVERFLOW) { set_err(c, "link arena overflow persisted"); return TGI_E_CAPACITY; }
   if (dev_err & ERR_TOO_MANY_REACTIONS) { set_err(c, "a reactions map has more than 32 entries (format limit)"); return TGI_E_ARG; }
-  if (dev_err & ERR_TOO_MANY_LINKS) { set_err(c, "a record has more than 4096 link candidates (format limit)"); return TGI_E_ARG; }
+  if (dev_err & ERR_TOO_MANY_LINKS) { set_err(c, "a record has 2^20 or more link candidates"); return TGI_E_ARG; }
   uint64_t chan_total = hsc[SC_CHAN_TOTAL], line_total = hsc[SC_LINE_TOTAL];
   uint32_t arena_used = ((uint32_t*)(hsc + SC_CURSOR))[0];
   const uint64_t var_bytes = hsc[SC_LONG];
@@ -718,7 +765,7 @@ int run_yt(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   CK(cudaStreamSynchronize(st));
   int dev_err = ((int*)(hsc + SC_CURSOR))[1];
   if (dev_err & ERR_ARENA_OVERFLOW) { set_err(c, "youtube url/link arena overflow (cannot happen: capacities are upper bounds)"); return TGI_E_CAPACITY; }
-  if (dev_err & ERR_TOO_MANY_LINKS) { set_err(c, "a record has more than 4096 channel-link candidates (format limit)"); return TGI_E_ARG; }
+  if (dev_err & ERR_TOO_MANY_LINKS) { set_err(c, "a record has 2^20 or more channel-link candidates"); return TGI_E_ARG; }
   uint64_t line_total = hsc[SC_LINE_TOTAL];
   uint32_t arena_used = ((uint32_t*)(hsc + SC_CURSOR))[0];
   if (want_json) {
@@ -888,7 +935,8 @@ int wait_job(tgi_ctx* c, int slot, tgi_result* out) {
   s.cv.wait(lk, [&] { return s.done; });
   if (out) *out = s.res;
   int rc = s.rc;
-  if (rc != TGI_OK) s.busy = false;  // nothing to release after a failed job
+  if (rc != TGI_OK) s.busy = false;  // nothing to release after a failed job (blocking callers still call
+                                     // tgi_result_release, which also clears `claimed` and wakes the waiters)
   return rc;
 }
 
@@ -939,6 +987,7 @@ int tgi_create(const tgi_config* cfg, tgi_ctx** out) {
         cudaEventCreate(&s.ev_k0) != cudaSuccess || cudaEventCreate(&s.ev_k1) != cudaSuccess ||
         cudaEventCreate(&s.ev_p0) != cudaSuccess || cudaEventCreate(&s.ev_p1) != cudaSuccess ||
         cudaEventCreate(&s.ev_e0) != cudaSuccess || cudaEventCreate(&s.ev_e1) != cudaSuccess || cudaEventCreate(&s.ev_f1) != cudaSuccess ||
+        cudaEventCreate(&s.ev_fr0) != cudaSuccess || cudaEventCreate(&s.ev_fr1) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.ev_mid, cudaEventDisableTiming) != cudaSuccess) {
       set_err(c, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
       return fail(TGI_E_CUDA);
@@ -953,13 +1002,15 @@ int tgi_create(const tgi_config* cfg, tgi_ctx** out) {
     set_err(c, "frontier allocation failed (%llu keys)", (unsigned long long)fcap);
     return fail(TGI_E_NOMEM);
   }
-  cudaMemset(ctx->d_table.p, 0, tslots * 8);
-  cudaMemset(ctx->d_fcount.p, 0, 16);
+  cudaMemsetAsync(ctx->d_table.p, 0, tslots * 8, ctx->slots[0].stream);
+  cudaMemsetAsync(ctx->d_fcount.p, 0, 16, ctx->slots[0].stream);
+  cudaStreamSynchronize(ctx->slots[0].stream);
   ctx->fr.pool = ctx->d_pool.as<uint8_t>();
   ctx->fr.cap = fcap;
   ctx->fr.table = ctx->d_table.as<uint64_t>();
   ctx->fr.tmask = tslots - 1;
   ctx->fr.count = ctx->d_fcount.as<uint64_t>();
+  ctx->fr.payload = nullptr;
   int rc = build_cfg_blob(ctx);
   if (rc) return fail(rc);
   for (int i = 0; i < TGI_SLOTS; i++) ctx->slots[i].worker = std::thread(worker_main, ctx, &ctx->slots[i]);
@@ -994,9 +1045,15 @@ void tgi_destroy(tgi_ctx* c) {
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_mid) cudaEventDestroy(s.ev_mid);
-    for (cudaEvent_t e : {s.ev_p0, s.ev_p1, s.ev_e0, s.ev_e1, s.ev_f1}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {s.ev_p0, s.ev_p1, s.ev_e0, s.ev_e1, s.ev_f1, s.ev_fr0, s.ev_fr1}) if (e) cudaEventDestroy(e);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
+  tgi_comm_destroy(c);
+  for (auto& f : c->stg_free) cudaFreeHost(f.second);
+  for (auto& f : c->stg_live) cudaFreeHost(f.first);
+  c->stg_free.clear();
+  c->stg_live.clear();
+  c->m_host.release();
   c->d_cfg.release();
   c->d_pool.release();
   c->d_table.release();
@@ -1042,6 +1099,9 @@ void tgi_result_release(tgi_ctx* c, int slot) {
   if (!c || slot < 0 || slot >= TGI_SLOTS) return;
   Slot& s = c->slots[slot];
   {
+    // alloc_mu is held across the state change: a claim_slot() that has scanned the slots and not yet started to
+    // wait would otherwise miss this notification
+    std::lock_guard<std::mutex> ag(c->alloc_mu);
     std::lock_guard<std::mutex> lk(s.mu);
     s.busy = false;
     s.claimed = false;
@@ -1184,54 +1244,62 @@ int tgi_youtube_run_resident(tgi_ctx* c, int slot, uint32_t run_flags, tgi_resul
 }
 
 // ---- frontier host API ------------------------------------------------------------------------------
-static int frontier_insert_impl(tgi_ctx* c, const void* d_keys, uint64_t n, void* d_is_new) {
-  // runs on slot 0's stream under the frontier lock; uses private scratch buffers
+// Inserts n device-resident 32-byte keys into set `f` (the local set, or this rank's partition of the global set).
+// Runs on slot 0's stream under the frontier lock (taken by the caller); the scratch lives in the context.
+static int frontier_insert_locked(tgi_ctx* c, FrontierDev& f, const void* d_keys, const uint64_t* d_payload, uint64_t n, void* d_is_new) {
   Slot& s = c->slots[0];
   cudaStream_t st = s.stream;
-  static thread_local DevBuf arena, cnt, lstate, recnew, newoff, btable, tiles, sc;
-  std::unique_lock<std::mutex> fg(c->fr_mu);
+  InsertScratch& z = c->ins;
   if (c->fr_event_valid) CK(cudaStreamWaitEvent(st, c->fr_event, 0));
-  CK(arena.ensure(n * sizeof(tgi_link)));
-  CK(cnt.ensure(n * 4));
-  CK(lstate.ensure(n * 4));
-  CK(recnew.ensure(n * 4));
-  CK(newoff.ensure((n + 1) * 8));
-  CK(sc.ensure(64));
+  CK(z.arena.ensure(n * sizeof(tgi_link)));
+  CK(z.cnt.ensure(n * 4));
+  CK(z.lstate.ensure(n * 4));
+  CK(z.recnew.ensure(n * 4));
+  CK(z.newoff.ensure((n + 1) * 8));
+  CK(z.sc.ensure(64));
   uint64_t bslots = next_pow2(std::max<uint64_t>(2 * n, 1024));
-  CK(btable.ensure(bslots * 8));
-  CK(cudaMemsetAsync(btable.p, 0, bslots * 8, st));
-  CK(cudaMemsetAsync(sc.p, 0, 64, st));
+  CK(z.btable.ensure(bslots * 8));
+  CK(cudaMemsetAsync(z.btable.p, 0, bslots * 8, st));
+  CK(cudaMemsetAsync(z.sc.p, 0, 64, st));
   unsigned g = (unsigned)((n + 255) / 256);
   if (!g) g = 1;
-  keys_to_links_kernel<<<g, 256, 0, st>>>((const uint8_t*)d_keys, n, arena.as<tgi_link>(), cnt.as<uint32_t>());
+  keys_to_links_kernel<<<g, 256, 0, st>>>((const uint8_t*)d_keys, n, z.arena.as<tgi_link>(), z.cnt.as<uint32_t>());
   FrontierBatch fb;
-  fb.btable = btable.as<uint64_t>();
+  fb.btable = z.btable.as<uint64_t>();
   fb.bmask = bslots - 1;
-  fb.lstate = lstate.as<uint32_t>();
-  fb.rec_new = recnew.as<uint32_t>();
-  frontier_probe_kernel<<<g, 256, 0, st>>>(n, nullptr, cnt.as<uint32_t>(), arena.as<tgi_link>(), 0, c->fr, fb);
-  frontier_count_kernel<<<g, 256, 0, st>>>(n, nullptr, cnt.as<uint32_t>(), fb);
-  // scan with private tile buffer
+  fb.lstate = z.lstate.as<uint32_t>();
+  fb.rec_new = z.recnew.as<uint32_t>();
+  frontier_probe_kernel<<<g, 256, 0, st>>>(n, nullptr, z.cnt.as<uint32_t>(), z.arena.as<tgi_link>(), 0, f, fb);
+  frontier_count_kernel<<<g, 256, 0, st>>>(n, nullptr, z.cnt.as<uint32_t>(), fb);
   {
     uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (!ntiles) ntiles = 1;
-    CK(tiles.ensure(ntiles * 8));
-    scan_tile_sums_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(fb.rec_new, n, tiles.as<uint64_t>());
-    scan_tiles_kernel<<<1, 1024, 0, st>>>(tiles.as<uint64_t>(), ntiles, sc.as<uint64_t>());
-    scan_apply_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(fb.rec_new, n, tiles.as<uint64_t>(), sc.as<uint64_t>(), newoff.as<uint64_t>());
+    CK(z.tiles.ensure(ntiles * 8));
+    scan_tile_sums_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(fb.rec_new, n, z.tiles.as<uint64_t>());
+    scan_tiles_kernel<<<1, 1024, 0, st>>>(z.tiles.as<uint64_t>(), ntiles, z.sc.as<uint64_t>());
+    scan_apply_kernel<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(fb.rec_new, n, z.tiles.as<uint64_t>(), z.sc.as<uint64_t>(), z.newoff.as<uint64_t>());
   }
-  int* derr = (int*)(sc.as<uint64_t>() + 4);
-  frontier_append_kernel<<<g, 256, 0, st>>>(n, nullptr, cnt.as<uint32_t>(), arena.as<tgi_link>(), c->fr, fb, newoff.as<uint64_t>(), derr);
-  frontier_commit_kernel<<<1, 1, 0, st>>>(c->fr, newoff.as<uint64_t>(), n, sc.as<uint64_t>() + 1, derr);
-  if (d_is_new) links_new_flags_kernel<<<g, 256, 0, st>>>(arena.as<tgi_link>(), n, (uint8_t*)d_is_new);
+  int* derr = (int*)(z.sc.as<uint64_t>() + 4);
+  frontier_append_kernel<<<g, 256, 0, st>>>(n, nullptr, z.cnt.as<uint32_t>(), z.arena.as<tgi_link>(), f, fb, z.newoff.as<uint64_t>(), derr, d_payload);
+  frontier_commit_kernel<<<1, 1, 0, st>>>(f, z.newoff.as<uint64_t>(), n, z.sc.as<uint64_t>() + 1, derr);
+  if (d_is_new) links_new_flags_kernel<<<g, 256, 0, st>>>(z.arena.as<tgi_link>(), n, (uint8_t*)d_is_new);
   CK(cudaGetLastError());
-  int herr = 0;
-  CK(cudaMemcpyAsync(&herr, derr, 4, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(c->fr_event, st));
   c->fr_event_valid = true;
-  CK(cudaStreamSynchronize(st));
-  if (herr & ERR_FRONTIER_FULL) { set_err(c, "frontier capacity %llu exceeded", (unsigned long long)c->fr.cap); return TGI_E_CAPACITY; }
   return TGI_OK;
+}
+static int frontier_insert_check(tgi_ctx* c, const FrontierDev& f) {  // after a stream synchronize
+  int herr = 0;
+  CK(cudaMemcpy(&herr, (int*)(c->ins.sc.as<uint64_t>() + 4), 4, cudaMemcpyDeviceToHost));
+  if (herr & ERR_FRONTIER_FULL) { set_err(c, "frontier capacity %llu exceeded", (unsigned long long)f.cap); return TGI_E_CAPACITY; }
+  return TGI_OK;
+}
+static int frontier_insert_impl(tgi_ctx* c, const void* d_keys, uint64_t n, void* d_is_new) {
+  std::unique_lock<std::mutex> fg(c->fr_mu);
+  int rc = frontier_insert_locked(c, c->fr, d_keys, nullptr, n, d_is_new);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(c->slots[0].stream));
+  return frontier_insert_check(c, c->fr);
 }
 
 int tgi_frontier_insert(tgi_ctx* c, const uint8_t* keys32, uint64_t n, uint8_t* is_new) {
@@ -1239,14 +1307,16 @@ int tgi_frontier_insert(tgi_ctx* c, const uint8_t* keys32, uint64_t n, uint8_t* 
   if (n >= (1ull << 32)) { set_err(c, "too many keys in one call"); return TGI_E_ARG; }
   cudaSetDevice(c->device);
   if (!n) return TGI_OK;
+  cudaStream_t st = c->slots[0].stream;
   DevBuf dk, dn;
   CK(dk.ensure(n * 32));
   CK(dn.ensure(n));
-  CK(cudaMemcpy(dk.p, keys32, n * 32, cudaMemcpyHostToDevice));
+  CK(cudaMemcpyAsync(dk.p, keys32, n * 32, cudaMemcpyHostToDevice, st));
   int rc = frontier_insert_impl(c, dk.p, n, dn.p);
-  if (rc == TGI_OK && is_new) CK(cudaMemcpy(is_new, dn.p, n, cudaMemcpyDeviceToHost));
-  dk.release();
-  dn.release();
+  if (rc == TGI_OK && is_new) {
+    CK(cudaMemcpyAsync(is_new, dn.p, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
   return rc;
 }
 int tgi_frontier_insert_dev(tgi_ctx* c, const void* d_keys32, uint64_t n, void* d_is_new) {
@@ -1262,41 +1332,354 @@ int tgi_frontier_sync(tgi_ctx* c) {
   if (c->fr_event_valid) CK(cudaEventSynchronize(c->fr_event));
   return TGI_OK;
 }
+// all copies / memsets of the frontier go through slot 0's stream (the library's streams are non-blocking: work on
+// the legacy default stream would not be ordered with them) and are synchronised before returning
+static int frontier_read_count(tgi_ctx* c, const FrontierDev& f, uint64_t* n) {
+  cudaStream_t st = c->slots[0].stream;
+  if (c->fr_event_valid) CK(cudaStreamWaitEvent(st, c->fr_event, 0));
+  CK(cudaMemcpyAsync(n, f.count, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return TGI_OK;
+}
 int tgi_frontier_size(tgi_ctx* c, uint64_t* n) {
   if (!c || !n) return TGI_E_ARG;
-  int rc = tgi_frontier_sync(c);
-  if (rc) return rc;
-  CK(cudaMemcpy(n, c->fr.count, 8, cudaMemcpyDeviceToHost));
-  return TGI_OK;
+  cudaSetDevice(c->device);
+  std::lock_guard<std::mutex> g(c->fr_mu);
+  return frontier_read_count(c, c->fr, n);
 }
 int tgi_frontier_export(tgi_ctx* c, uint8_t* keys32, uint64_t cap, uint64_t* n) {
   if (!c || !n) return TGI_E_ARG;
+  cudaSetDevice(c->device);
+  std::lock_guard<std::mutex> g(c->fr_mu);
   uint64_t sz = 0;
-  int rc = tgi_frontier_size(c, &sz);
+  int rc = frontier_read_count(c, c->fr, &sz);
   if (rc) return rc;
   uint64_t m = sz < cap ? sz : cap;
-  if (m && keys32) CK(cudaMemcpy(keys32, c->fr.pool, m * 32, cudaMemcpyDeviceToHost));
+  if (m && keys32) {
+    CK(cudaMemcpyAsync(keys32, c->fr.pool, m * 32, cudaMemcpyDeviceToHost, c->slots[0].stream));
+    CK(cudaStreamSynchronize(c->slots[0].stream));
+  }
   *n = sz;
   return TGI_OK;
 }
 int tgi_frontier_export_dev(tgi_ctx* c, void* d_keys32, uint64_t cap, uint64_t first, uint64_t* n) {
   if (!c || !n) return TGI_E_ARG;
+  cudaSetDevice(c->device);
+  std::lock_guard<std::mutex> g(c->fr_mu);
   uint64_t sz = 0;
-  int rc = tgi_frontier_size(c, &sz);
+  int rc = frontier_read_count(c, c->fr, &sz);
   if (rc) return rc;
   uint64_t avail = first < sz ? sz - first : 0;
   uint64_t m = avail < cap ? avail : cap;
-  if (m && d_keys32) CK(cudaMemcpy(d_keys32, c->fr.pool + 32 * first, m * 32, cudaMemcpyDeviceToDevice));
+  if (m && d_keys32) {
+    CK(cudaMemcpyAsync(d_keys32, c->fr.pool + 32 * first, m * 32, cudaMemcpyDeviceToDevice, c->slots[0].stream));
+    CK(cudaStreamSynchronize(c->slots[0].stream));  // the caller's stream may read the keys as soon as this returns
+  }
   *n = m;
+  return TGI_OK;
+}
+static int frontier_clear_set(tgi_ctx* c, FrontierDev& f) {
+  cudaStream_t st = c->slots[0].stream;
+  CK(cudaMemsetAsync(f.table, 0, (f.tmask + 1) * 8, st));
+  CK(cudaMemsetAsync(f.count, 0, 8, st));
   return TGI_OK;
 }
 int tgi_frontier_clear(tgi_ctx* c) {
   if (!c) return TGI_E_ARG;
-  int rc = tgi_frontier_sync(c);
-  if (rc) return rc;
+  cudaSetDevice(c->device);
   std::lock_guard<std::mutex> g(c->fr_mu);
-  CK(cudaMemset(c->fr.table, 0, (c->fr.tmask + 1) * 8));
-  CK(cudaMemset(c->fr.count, 0, 8));
+  cudaStream_t st = c->slots[0].stream;
+  if (c->fr_event_valid) CK(cudaStreamWaitEvent(st, c->fr_event, 0));
+  int rc = frontier_clear_set(c, c->fr);
+  if (rc == TGI_OK && c->owned.table) rc = frontier_clear_set(c, c->owned);
+  if (rc) return rc;
+  c->merged_upto = 0;
+  CK(cudaEventRecord(c->fr_event, st));
+  c->fr_event_valid = true;
+  CK(cudaStreamSynchronize(st));
+  return TGI_OK;
+}
+
+// ---- pinned input staging ---------------------------------------------------------------------------------
+int tgi_acquire_staging(tgi_ctx* c, uint64_t bytes, void** out) {
+  if (!c || !out) return TGI_E_ARG;
+  cudaSetDevice(c->device);
+  if (bytes == 0) bytes = 1;
+  std::lock_guard<std::mutex> g(c->stg_mu);
+  auto it = c->stg_free.lower_bound(bytes);
+  if (it != c->stg_free.end() && it->first <= bytes + bytes / 2 + 4096) {  // recycle a block that is not much larger
+    *out = it->second;
+    c->stg_live[it->second] = it->first;
+    c->stg_free.erase(it);
+    return TGI_OK;
+  }
+  const size_t want = (bytes + 4095 + 64) & ~(size_t)4095;
+  void* p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    set_err(c, "cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    return TGI_E_NOMEM;
+  }
+  c->stg_live[p] = want;
+  *out = p;
+  return TGI_OK;
+}
+int tgi_release_staging(tgi_ctx* c, void* block) {
+  if (!c || !block) return TGI_E_ARG;
+  std::lock_guard<std::mutex> g(c->stg_mu);
+  auto it = c->stg_live.find(block);
+  if (it == c->stg_live.end()) { set_err(c, "tgi_release_staging: not a live staging block"); return TGI_E_ARG; }
+  size_t held = 0;
+  for (auto& f : c->stg_free) held += f.first;
+  if (held + it->second > (4ull << 30)) cudaFreeHost(block);  // keep at most 4 GiB of idle pinned memory around
+  else c->stg_free.emplace(it->second, block);
+  c->stg_live.erase(it);
+  return TGI_OK;
+}
+
+// ---- multi-GPU merge (SURVEY 8e option A) ---------------------------------------------------------------------
+#define NK(call)                                                                                  \
+  do {                                                                                            \
+    ncclResult_t _r = (call);                                                                     \
+    if (_r != ncclSuccess) {                                                                      \
+      set_err(c, "%s failed: %s", #call, c->nccl && c->nccl->GetErrorString ? c->nccl->GetErrorString(_r) : "?"); \
+      return TGI_E_CUDA;                                                                          \
+    }                                                                                             \
+  } while (0)
+
+static NcclApi* load_nccl(std::string& why) {
+  static std::mutex mu;
+  static NcclApi api;
+  std::lock_guard<std::mutex> g(mu);
+  if (api.h) return &api;
+  void* h = nullptr;
+  for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+    h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) { why = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "?"); return nullptr; }
+#define SYM(field, name)                                        \
+  api.field = (decltype(api.field))dlsym(h, name);              \
+  if (!api.field) { why = std::string("libnccl lacks ") + name; return nullptr; }
+  SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+  SYM(AllGather, "ncclAllGather") SYM(AllReduce, "ncclAllReduce") SYM(Broadcast, "ncclBroadcast") SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv") SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  api.h = h;
+  return &api;
+}
+
+int tgi_comm_unique_id(uint8_t id[TGI_COMM_ID_BYTES]) {
+  if (!id) return TGI_E_ARG;
+  std::string why;
+  NcclApi* a = load_nccl(why);
+  if (!a) { set_err(nullptr, "%s", why.c_str()); return TGI_E_STATE; }
+  ncclUniqueId u;
+  static_assert(sizeof(u) == TGI_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+  if (a->GetUniqueId(&u) != ncclSuccess) { set_err(nullptr, "ncclGetUniqueId failed"); return TGI_E_CUDA; }
+  memcpy(id, &u, sizeof u);
+  return TGI_OK;
+}
+
+int tgi_comm_init(tgi_ctx* c, const uint8_t id[TGI_COMM_ID_BYTES], int rank, int nranks) {
+  if (!c || !id || nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) return TGI_E_ARG;
+  cudaSetDevice(c->device);
+  std::lock_guard<std::mutex> g(c->fr_mu);
+  if (c->comm) { set_err(c, "communicator already initialised"); return TGI_E_STATE; }
+  std::string why;
+  c->nccl = load_nccl(why);
+  if (!c->nccl) { set_err(c, "%s", why.c_str()); return TGI_E_STATE; }
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof u);
+  NK(c->nccl->CommInitRank(&c->comm, nranks, u, rank));
+  c->rank = rank;
+  c->nranks = nranks;
+  // this rank's partition of the global set: sized like the local set (a skewed hash cannot overflow it before the
+  // local sets do)
+  const uint64_t fcap = c->fr.cap, tslots = c->fr.tmask + 1;
+  CK(c->o_pool.ensure(fcap * 32));
+  CK(c->o_table.ensure(tslots * 8));
+  CK(c->o_count.ensure(16));
+  CK(c->o_payload.ensure(fcap * 8));
+  cudaStream_t st = c->slots[0].stream;
+  CK(cudaMemsetAsync(c->o_table.p, 0, tslots * 8, st));
+  CK(cudaMemsetAsync(c->o_count.p, 0, 16, st));
+  c->owned.pool = c->o_pool.as<uint8_t>();
+  c->owned.cap = fcap;
+  c->owned.table = c->o_table.as<uint64_t>();
+  c->owned.tmask = tslots - 1;
+  c->owned.count = c->o_count.as<uint64_t>();
+  c->owned.payload = c->o_payload.as<uint64_t>();
+  CK(c->m_cnt.ensure(64 * 8));
+  CK(c->m_all.ensure(64 * 64 * 8));
+  CK(c->m_cursor.ensure(64 * 8));
+  CK(c->m_gsize.ensure(16));
+  CK(c->m_host.ensure(64 * 64 * 8 + 64));
+  for (auto& e : c->m_ev) CK(cudaEventCreate(&e));
+  CK(cudaStreamSynchronize(st));
+  c->merged_upto = 0;
+  c->merge_round = 0;
+  return TGI_OK;
+}
+
+int tgi_comm_destroy(tgi_ctx* c) {
+  if (!c) return TGI_E_ARG;
+  cudaSetDevice(c->device);
+  std::lock_guard<std::mutex> g(c->fr_mu);
+  if (c->comm) {
+    cudaStreamSynchronize(c->slots[0].stream);
+    c->nccl->CommDestroy(c->comm);
+    c->comm = nullptr;
+  }
+  for (auto& e : c->m_ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+  c->owned = FrontierDev{};
+  return TGI_OK;
+}
+
+int tgi_frontier_merge(tgi_ctx* c, uint64_t* global_size, uint64_t* owned) {
+  if (!c) return TGI_E_ARG;
+  cudaSetDevice(c->device);
+  std::lock_guard<std::mutex> g(c->fr_mu);
+  if (!c->comm) { set_err(c, "tgi_frontier_merge needs tgi_comm_init first"); return TGI_E_STATE; }
+  NcclApi& N = *c->nccl;
+  const int G = c->nranks, me = c->rank;
+  cudaStream_t st = c->slots[0].stream;
+  uint64_t* hb = c->m_host.as<uint64_t>();
+  uint64_t sz = 0;
+  int rc = frontier_read_count(c, c->fr, &sz);
+  if (rc) return rc;
+  const uint64_t first = c->merged_upto, m = sz > first ? sz - first : 0;
+  // 1. how many of my new keys go to each owner; every rank learns every count
+  CK(cudaEventRecord(c->m_ev[0], st));
+  CK(cudaMemsetAsync(c->m_cnt.p, 0, 64 * 8, st));
+  if (m) merge_count_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(c->fr.pool, first, m, (uint32_t)G, c->m_cnt.as<unsigned long long>());
+  CK(cudaGetLastError());
+  NK(N.AllGather(c->m_cnt.p, c->m_all.p, (size_t)G, ncclUint64, c->comm, st));
+  CK(cudaMemcpyAsync(hb, c->m_all.p, (size_t)G * G * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  std::vector<uint64_t> send_off(G + 1, 0), recv_off(G + 1, 0);
+  for (int p = 0; p < G; p++) {
+    send_off[p + 1] = send_off[p] + hb[(size_t)me * G + p];
+    recv_off[p + 1] = recv_off[p] + hb[(size_t)p * G + me];
+  }
+  const uint64_t R = recv_off[G];
+  if (send_off[G] != m) { set_err(c, "merge: bucket counts do not add up"); return TGI_E_STATE; }
+  // 2. bucket my new keys by owner
+  CK(c->m_send_keys.ensure(m * 32));
+  CK(c->m_send_pay.ensure(m * 8));
+  CK(c->m_recv_keys.ensure(R * 32));
+  CK(c->m_recv_pay.ensure(R * 8));
+  uint64_t* hcur = hb + (size_t)G * G;
+  for (int p = 0; p < G; p++) hcur[p] = send_off[p];
+  CK(cudaMemcpyAsync(c->m_cursor.p, hcur, (size_t)G * 8, cudaMemcpyHostToDevice, st));
+  const uint64_t pay_base = (c->merge_round << 52) | ((uint64_t)me << 44);
+  if (m) merge_scatter_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(c->fr.pool, first, m, (uint32_t)G, c->m_cursor.as<unsigned long long>(),
+                                                                      c->m_send_keys.as<uint8_t>(), c->m_send_pay.as<uint64_t>(), pay_base);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(c->m_ev[1], st));
+  // 3. exchange: grouped send / recv, the receive buffer laid out by source rank
+  NK(N.GroupStart());
+  for (int p = 0; p < G; p++) {
+    const uint64_t sc = send_off[p + 1] - send_off[p], rc2 = recv_off[p + 1] - recv_off[p];
+    if (p == me) continue;
+    if (sc) {
+      NK(N.Send(c->m_send_keys.as<uint8_t>() + 32 * send_off[p], sc * 32, ncclUint8, p, c->comm, st));
+      NK(N.Send(c->m_send_pay.as<uint64_t>() + send_off[p], sc, ncclUint64, p, c->comm, st));
+    }
+    if (rc2) {
+      NK(N.Recv(c->m_recv_keys.as<uint8_t>() + 32 * recv_off[p], rc2 * 32, ncclUint8, p, c->comm, st));
+      NK(N.Recv(c->m_recv_pay.as<uint64_t>() + recv_off[p], rc2, ncclUint64, p, c->comm, st));
+    }
+  }
+  NK(N.GroupEnd());
+  {
+    const uint64_t sc = send_off[me + 1] - send_off[me];
+    if (sc) {
+      CK(cudaMemcpyAsync(c->m_recv_keys.as<uint8_t>() + 32 * recv_off[me], c->m_send_keys.as<uint8_t>() + 32 * send_off[me], sc * 32, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(c->m_recv_pay.as<uint64_t>() + recv_off[me], c->m_send_pay.as<uint64_t>() + send_off[me], sc * 8, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  CK(cudaEventRecord(c->m_ev[2], st));
+  // 4. the owner inserts what it received (source-rank-major: the lowest rank's copy of a key wins)
+  if (R) {
+    rc = frontier_insert_locked(c, c->owned, c->m_recv_keys.p, c->m_recv_pay.as<uint64_t>(), R, nullptr);
+    if (rc) return rc;
+  }
+  // 5. global size = sum of the partitions
+  NK(N.AllReduce(c->owned.count, c->m_gsize.p, 1, ncclUint64, ncclSum, c->comm, st));
+  CK(cudaEventRecord(c->m_ev[3], st));
+  CK(cudaMemcpyAsync(hb, c->m_gsize.p, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hb + 1, c->owned.count, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (R) {
+    rc = frontier_insert_check(c, c->owned);
+    if (rc) return rc;
+  }
+  if (global_size) *global_size = hb[0];
+  if (owned) *owned = hb[1];
+  float t0 = 0, t1 = 0, t2 = 0;
+  cudaEventElapsedTime(&t0, c->m_ev[0], c->m_ev[1]);
+  cudaEventElapsedTime(&t1, c->m_ev[1], c->m_ev[2]);
+  cudaEventElapsedTime(&t2, c->m_ev[2], c->m_ev[3]);
+  c->mstats.merges++;
+  c->mstats.keys_sent += m - (send_off[me + 1] - send_off[me]);
+  c->mstats.keys_received += R - (recv_off[me + 1] - recv_off[me]);
+  c->mstats.keys_owned = hb[1];
+  c->mstats.bytes_sent += (m - (send_off[me + 1] - send_off[me])) * 40;
+  c->mstats.bucket_ms += t0;
+  c->mstats.exchange_ms += t1;
+  c->mstats.insert_ms += t2;
+  c->merged_upto = sz;
+  c->merge_round++;
+  return TGI_OK;
+}
+
+int tgi_merge_get_stats(tgi_ctx* c, tgi_merge_stats* out) {
+  if (!c || !out) return TGI_E_ARG;
+  std::lock_guard<std::mutex> g(c->fr_mu);
+  *out = c->mstats;
+  return TGI_OK;
+}
+
+int tgi_frontier_global_export(tgi_ctx* c, uint8_t* keys32, uint64_t cap, uint64_t* n) {
+  if (!c || !n) return TGI_E_ARG;
+  cudaSetDevice(c->device);
+  std::lock_guard<std::mutex> g(c->fr_mu);
+  if (!c->comm) { set_err(c, "tgi_frontier_global_export needs tgi_comm_init first"); return TGI_E_STATE; }
+  NcclApi& N = *c->nccl;
+  const int G = c->nranks;
+  cudaStream_t st = c->slots[0].stream;
+  uint64_t* hb = c->m_host.as<uint64_t>();
+  if (c->fr_event_valid) CK(cudaStreamWaitEvent(st, c->fr_event, 0));
+  NK(N.AllGather(c->owned.count, c->m_all.p, 1, ncclUint64, c->comm, st));
+  CK(cudaMemcpyAsync(hb, c->m_all.p, (size_t)G * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  std::vector<uint64_t> off(G + 1, 0);
+  for (int p = 0; p < G; p++) off[p + 1] = off[p] + hb[p];
+  const uint64_t T = off[G];
+  DevBuf dk, dp;
+  CK(dk.ensure(T * 32));
+  CK(dp.ensure(T * 8));
+  for (int p = 0; p < G; p++) {
+    const uint64_t cnt = off[p + 1] - off[p];
+    if (!cnt) continue;
+    NK(N.Broadcast(c->owned.pool, dk.as<uint8_t>() + 32 * off[p], cnt * 32, ncclUint8, p, c->comm, st));
+    NK(N.Broadcast(c->owned.payload, dp.as<uint64_t>() + off[p], cnt, ncclUint64, p, c->comm, st));
+  }
+  std::vector<uint8_t> hk(T * 32);
+  std::vector<uint64_t> hp(T);
+  if (T) {
+    CK(cudaMemcpyAsync(hk.data(), dk.p, T * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hp.data(), dp.p, T * 8, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  std::vector<uint64_t> idx(T);
+  for (uint64_t i = 0; i < T; i++) idx[i] = i;
+  std::sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return hp[a] < hp[b]; });
+  const uint64_t m = T < cap ? T : cap;
+  if (keys32)
+    for (uint64_t i = 0; i < m; i++) memcpy(keys32 + 32 * i, hk.data() + 32 * idx[i], 32);
+  *n = T;
   return TGI_OK;
 }
 

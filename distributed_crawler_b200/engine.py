@@ -32,7 +32,8 @@ EXPORTED_SYMBOLS = [
     "tgi_telegram_run_resident", "tgi_youtube_upload", "tgi_youtube_run_resident",
     "tgi_result_read_jsonl", "tgi_frontier_insert", "tgi_frontier_size", "tgi_frontier_export",
     "tgi_frontier_clear", "tgi_frontier_export_dev", "tgi_frontier_insert_dev", "tgi_frontier_sync",
-    "tgi_filter_usernames",
+    "tgi_filter_usernames", "tgi_acquire_staging", "tgi_release_staging", "tgi_comm_unique_id", "tgi_comm_init",
+    "tgi_comm_destroy", "tgi_frontier_merge", "tgi_frontier_global_export", "tgi_merge_get_stats",
 ]
 
 
@@ -76,6 +77,14 @@ def lib() -> C.CDLL:
         L.tgi_frontier_insert_dev.argtypes = [vp, vp, u64, vp]
         L.tgi_frontier_sync.argtypes = [vp]
         L.tgi_filter_usernames.argtypes = [vp, vp, vp, u64, vp]
+        L.tgi_acquire_staging.argtypes = [vp, u64, C.POINTER(vp)]
+        L.tgi_release_staging.argtypes = [vp, vp]
+        L.tgi_comm_unique_id.argtypes = [vp]
+        L.tgi_comm_init.argtypes = [vp, vp, i32, i32]
+        L.tgi_comm_destroy.argtypes = [vp]
+        L.tgi_frontier_merge.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+        L.tgi_frontier_global_export.argtypes = [vp, vp, u64, C.POINTER(u64)]
+        L.tgi_merge_get_stats.argtypes = [vp, C.POINTER(abi.MergeStatsC)]
         _LIB = L
     return _LIB
 
@@ -99,10 +108,13 @@ class Result:
         self.kernel_ms = float(r.kernel_ms)
         self.parse_ms = float(r.parse_ms)
         self.emit_ms = float(r.emit_ms)
-        self.emit_fixed_ms = float(r.emit_fixed_ms)
+        self.emit_main_ms = float(r.emit_main_ms)
+        self.frontier_ms = float(r.frontier_ms)
         self.var_bytes = int(r.var_bytes)
-        self.lane_bytes_out = int(r.lane_bytes_out)
-        self.lane_bytes_in = int(r.lane_bytes_in)
+        self.main_bytes_out = int(r.main_bytes_out)
+        self.main_bytes_in = int(r.main_bytes_in)
+        self.has_links = bool(r.link_off)
+        self.has_jsonl = bool(r.line_off)
         self.gpu_launches = int(r.gpu_launches)
         self.slot = int(r.slot)
         if copy:
@@ -111,6 +123,15 @@ class Result:
             self.line_off = _copy(r.line_off, n + 1, np.uint64) if r.line_off else np.zeros(n + 1, np.uint64)
             self.link_off = _copy(r.link_off, n + 1, np.uint32) if r.link_off else np.zeros(n + 1, np.uint32)
             self.links = _copy(r.links, self.n_links, abi.LINK)
+
+    def d2h_bytes(self) -> int:
+        """bytes the library copied device -> pinned host for this result"""
+        b = self.n + 80  # status + scalars
+        if self.has_jsonl:
+            b += self.jsonl_len + 8 * (self.n + 1)
+        if self.has_links:
+            b += 4 * (self.n + 1) + 36 * self.n_links
+        return b
 
     def line(self, i: int) -> bytes:
         return self.jsonl[int(self.line_off[i]):int(self.line_off[i + 1])].tobytes()
@@ -194,6 +215,88 @@ class Engine:
         out = Result(r, copy)
         lib().tgi_result_release(self.h, r.slot)
         return out
+
+    def youtube_submit(self, slot, batch, run_flags):
+        d = batch.descriptor()
+        self._keep[slot] = (batch, d)
+        self._check(lib().tgi_youtube_submit(self.h, slot, C.byref(d), run_flags))
+
+    def youtube_wait(self, slot, copy=False) -> Result:
+        r = abi.ResultC()
+        self._check(lib().tgi_youtube_wait(self.h, slot, C.byref(r)))
+        return Result(r, copy)
+
+    def youtube_upload(self, slot, batch):
+        d = batch.descriptor()
+        self._check(lib().tgi_youtube_upload(self.h, slot, C.byref(d)))
+
+    def youtube_run_resident(self, slot, run_flags, copy=False) -> Result:
+        r = abi.ResultC()
+        self._check(lib().tgi_youtube_run_resident(self.h, slot, run_flags, C.byref(r)))
+        out = Result(r, copy)
+        lib().tgi_result_release(self.h, slot)
+        return out
+
+    # --- library-owned pinned input staging (tgi_acquire_staging) --------------------------------
+    def stage(self, batch):
+        """A copy of `batch` whose arrays live in ONE pinned block owned by the library: what a packer that builds
+        its arrays in tgi_acquire_staging memory produces.  Release with unstage()."""
+        fields = batch.FIELDS
+        sizes = [(getattr(batch, k).nbytes + 16 + 63) & ~63 for k in fields]  # 16 readable pad bytes behind every array
+        block = C.c_void_p()
+        self._check(lib().tgi_acquire_staging(self.h, sum(sizes) + 64, C.byref(block)))
+        whole = np.ctypeslib.as_array(C.cast(block, C.POINTER(C.c_uint8)), (sum(sizes) + 64,))
+        whole[:] = 0
+        arrays, o = {}, 0
+        for k, sz in zip(fields, sizes):
+            a = getattr(batch, k)
+            v = whole[o:o + a.nbytes].view(a.dtype)
+            if a.ndim > 1:
+                v = v.reshape(a.shape)
+            v[...] = a
+            arrays[k] = v
+            o += sz
+        out = type(batch)(**arrays)
+        out._staging_block = block
+        return out
+
+    def unstage(self, staged):
+        blk = getattr(staged, "_staging_block", None)
+        if blk is not None:
+            for k in staged.FIELDS:
+                setattr(staged, k, None)
+            self._check(lib().tgi_release_staging(self.h, blk))
+            staged._staging_block = None
+
+    # --- multi-GPU dedup-set merge (tgi_comm_*, tgi_frontier_merge) ------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = lib().tgi_comm_unique_id(buf)
+        if rc != 0:
+            raise EngineError(rc, lib().tgi_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, uid: bytes, rank: int, nranks: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._check(lib().tgi_comm_init(self.h, buf, rank, nranks))
+
+    def frontier_merge(self) -> tuple[int, int]:
+        g, o = C.c_uint64(), C.c_uint64()
+        self._check(lib().tgi_frontier_merge(self.h, C.byref(g), C.byref(o)))
+        return g.value, o.value
+
+    def frontier_global_export(self) -> np.ndarray:
+        n = C.c_uint64()
+        self._check(lib().tgi_frontier_global_export(self.h, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 32), np.uint8)
+        self._check(lib().tgi_frontier_global_export(self.h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def merge_stats(self) -> dict:
+        s = abi.MergeStatsC()
+        self._check(lib().tgi_merge_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_}
 
     # --- generic client.Message -> sparse Post (SURVEY a12) -------------------------------------
     def generic(self, batch, run_flags=abi.RUN_JSONL, copy=True) -> Result:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TGI_ABI_VERSION 1
+#define TGI_ABI_VERSION 2
 
 /* ---- error codes ---------------------------------------------------------------------------- */
 #define TGI_OK 0
@@ -332,10 +332,12 @@ typedef struct tgi_result {
   float parse_ms;           /* device time of the parse pass (link extraction + size kernels)     */
   float emit_ms;            /* device time of the JSONL emit pass (three kernels)                 */
   int32_t slot;             /* staging slot that owns the buffers: pass to tgi_result_release     */
-  float emit_fixed_ms;      /* device time of tg_emit_lane_kernel, the dominant kernel            */
+  float emit_main_ms;       /* device time of the main emit kernel (tg_emit_tile_kernel / yt_emit_lane_kernel) */
   uint64_t var_bytes;       /* JSONL bytes of the variable pieces (strings, comments, maps, outlinks) */
-  uint64_t lane_bytes_out;  /* JSONL bytes written by tg_emit_lane_kernel (the rest: esc + maps kernels) */
-  uint64_t lane_bytes_in;   /* of those, bytes it copied from HBM-resident sources (strings, channel blob) */
+  uint64_t main_bytes_out;  /* JSONL bytes written by the main emit kernel                         */
+  uint64_t main_bytes_in;   /* bytes it read from HBM-resident sources to produce them (strings, channel blob) */
+  float frontier_ms;        /* device time of the frontier (dedup set) kernels of this call       */
+  uint32_t reserved;
 } tgi_result;
 
 typedef struct tgi_stats {
@@ -426,6 +428,42 @@ int tgi_frontier_clear(tgi_ctx* ctx);
 int tgi_frontier_export_dev(tgi_ctx* ctx, void* d_keys32, uint64_t cap, uint64_t first, uint64_t* n);
 int tgi_frontier_insert_dev(tgi_ctx* ctx, const void* d_keys32, uint64_t n, void* d_is_new);
 int tgi_frontier_sync(tgi_ctx* ctx);
+
+/* Library-owned pinned host memory for the packed input arrays (SURVEY 8b "Ownership").  The packer (the Go shim's
+ * Batch, host/tgingest.hpp, pack.py) builds its arrays directly in blocks obtained here, so the host -> device copies
+ * of tgi_*_submit run at link speed from page-locked memory; with pageable (Go heap / malloc) buffers the copy engine
+ * reaches about half of that.  Blocks are 4096-byte aligned, recycled through a per-context pool, and stay valid
+ * until tgi_release_staging / tgi_destroy.  Replaces nothing in the reference (its messages live on the Go heap).   */
+int tgi_acquire_staging(tgi_ctx* ctx, uint64_t bytes, void** out);
+int tgi_release_staging(tgi_ctx* ctx, void* block);
+
+/* Multi-GPU dedup-set merge (SURVEY 8e option A).  One process per GPU; the record path shards on record index with
+ * no collective, only the set is global: it replaces the shared urlCache / seenInBatch state that the reference's
+ * workers reach through the Dapr state store (state/daprstate.go:646-658, crawl/runner.go:1267-1272).
+ *   tgi_comm_unique_id   rank 0 creates the 128-byte NCCL id; the host distributes it to the other ranks by its own
+ *                        means (the Go shim: a Dapr pub/sub message or a file; the Python mirror: torch.distributed).
+ *   tgi_comm_init        every rank: create the communicator (ncclCommInitRank) on the context's device.
+ *   tgi_frontier_merge   collective.  Keys added to the local set since the last merge are bucketed on the device by
+ *                        owner = hash(key) % nranks, exchanged with grouped ncclSend / ncclRecv (counts first, one
+ *                        ncclAllGather), and inserted by the owner into its partition of the global set; a key keeps
+ *                        the sequence number (merge round, source rank, position in the source's set) of its first
+ *                        occurrence, so the union of the partitions ordered by that number is exactly the set a
+ *                        single process would have built over the ranks' shards in rank order.  *global_size = number
+ *                        of distinct keys over all ranks; *owned (optional) = keys in this rank's partition.
+ *   tgi_frontier_global_export   collective.  All partitions, ordered as above, on every rank (hand-off / tests).
+ * libnccl.so.2 is loaded with dlopen at tgi_comm_init (a process that already carries NCCL, e.g. through PyTorch,
+ * shares that copy); single-GPU users never need it.                                                                */
+#define TGI_COMM_ID_BYTES 128
+int tgi_comm_unique_id(uint8_t id[TGI_COMM_ID_BYTES]);
+int tgi_comm_init(tgi_ctx* ctx, const uint8_t id[TGI_COMM_ID_BYTES], int rank, int nranks);
+int tgi_comm_destroy(tgi_ctx* ctx);
+int tgi_frontier_merge(tgi_ctx* ctx, uint64_t* global_size, uint64_t* owned);
+int tgi_frontier_global_export(tgi_ctx* ctx, uint8_t* keys32, uint64_t cap, uint64_t* n);
+typedef struct tgi_merge_stats {
+  uint64_t merges, keys_sent, keys_received, keys_owned, bytes_sent;
+  double bucket_ms, exchange_ms, insert_ms; /* device time, summed over the merges */
+} tgi_merge_stats;
+int tgi_merge_get_stats(tgi_ctx* ctx, tgi_merge_stats* out);
 
 /* pure helpers exposed for host code and tests (each runs the device code path on tiny inputs) */
 int tgi_filter_usernames(tgi_ctx* ctx, const uint8_t* names, const uint32_t* off, uint64_t n,

@@ -10,6 +10,7 @@
 #include "tgoracle.h"
 
 #include <pthread.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -204,6 +205,7 @@ typedef struct {
   tgi_link* v;
   int n, cap;
   int overflow;
+  buf_t* store; /* batch driver: the set grows on demand (the reference has no cap); NULL = fixed caller array */
 } linkset_t;
 
 static void linkset_add(linkset_t* ls, const uint8_t* name, int len, int src) {
@@ -212,8 +214,14 @@ static void linkset_add(linkset_t* ls, const uint8_t* name, int len, int src) {
   for (int i = 0; i < ls->n; i++)
     if (ls->v[i].len == len && memcmp(ls->v[i].name, low, (size_t)len) == 0) return;
   if (ls->n >= ls->cap) {
-    ls->overflow = 1;
-    return;
+    if (!ls->store) {
+      ls->overflow = 1;
+      return;
+    }
+    ls->store->len = sizeof(tgi_link) * (size_t)ls->cap;
+    buf_reserve(ls->store, sizeof(tgi_link) * (size_t)ls->cap);
+    ls->cap *= 2;
+    ls->v = (tgi_link*)ls->store->p;
   }
   tgi_link* l = &ls->v[ls->n++];
   memset(l, 0, sizeof(*l));
@@ -275,7 +283,7 @@ static int extract_links(const tgi_tg_batch* b, uint64_t r, linkset_t* ls) {
 }
 
 int orc_extract_links(const tgi_tg_batch* b, uint64_t rec, tgi_link* out, int cap) {
-  linkset_t ls = {out, 0, cap, 0};
+  linkset_t ls = {out, 0, cap, 0, NULL};
   if (extract_links(b, rec, &ls) < 0) return -1;
   return ls.overflow ? -2 : ls.n;
 }
@@ -420,9 +428,18 @@ int orc_json_float_of_int64(int64_t v, uint8_t* dst) {
 }
 
 /* ------------------------------------------------------------------------------------------- */
-/* frontier set: exact string set, first occurrence wins, insertion order kept                   */
+/* frontier set: exact string set, first occurrence wins, insertion order kept.
+ * The set is split into ORC_SHARDS independent shards by the top bits of the key hash so that the
+ * batch driver can insert from many threads without a lock (one owner thread per shard).  Every key
+ * carries the global sequence number of its first occurrence; the insertion order of the whole set
+ * is the order of those numbers (orc_frontier_export sorts by them).  Sequentially (one thread, or
+ * orc_frontier_insert) this is exactly the mutex-guarded Go map + append of the reference
+ * (crawl/runner.go:1267-1272, state/daprstate.go:646-658).                                        */
+#define ORC_SHARD_BITS 8
+#define ORC_SHARDS (1 << ORC_SHARD_BITS)
 typedef struct {
   uint8_t (*keys)[32];
+  uint64_t* seq;   /* global first-occurrence sequence number of keys[i] */
   uint64_t n, cap;
   uint64_t* slots; /* index+1 into keys, 0 = empty */
   uint64_t nslots;
@@ -430,14 +447,17 @@ typedef struct {
 
 static uint64_t key_hash(const uint8_t* k) {
   uint64_t h = 1469598103934665603ull;
-  for (int i = 0; i < 32; i++) {
-    h ^= k[i];
-    h *= 1099511628211ull;
+  uint64_t w[4];
+  memcpy(w, k, 32);
+  for (int i = 0; i < 4; i++) {
+    h = (h ^ w[i]) * 0xFF51AFD7ED558CCDull;
+    h ^= h >> 32;
   }
+  h *= 0xC4CEB9FE1A85EC53ull;
   return h ^ (h >> 29);
 }
 static void fset_grow(fset_t* f) {
-  uint64_t ns = f->nslots ? f->nslots * 2 : 1 << 16;
+  uint64_t ns = f->nslots ? f->nslots * 2 : 1 << 10;
   uint64_t* s = (uint64_t*)calloc(ns, sizeof(uint64_t));
   for (uint64_t i = 0; i < f->n; i++) {
     uint64_t h = key_hash(f->keys[i]) & (ns - 1);
@@ -448,21 +468,24 @@ static void fset_grow(fset_t* f) {
   f->slots = s;
   f->nslots = ns;
 }
-static int fset_insert(fset_t* f, const uint8_t* k) {
+static int fset_insert_h(fset_t* f, const uint8_t* k, uint64_t hash, uint64_t seq) {
   if ((f->n + 1) * 2 > f->nslots) fset_grow(f);
-  uint64_t h = key_hash(k) & (f->nslots - 1);
+  uint64_t h = hash & (f->nslots - 1);
   while (f->slots[h]) {
     if (memcmp(f->keys[f->slots[h] - 1], k, 32) == 0) return 0;
     h = (h + 1) & (f->nslots - 1);
   }
   if (f->n == f->cap) {
-    f->cap = f->cap ? f->cap * 2 : 1 << 15;
+    f->cap = f->cap ? f->cap * 2 : 1 << 8;
     f->keys = realloc(f->keys, f->cap * 32);
+    f->seq = realloc(f->seq, f->cap * 8);
   }
   memcpy(f->keys[f->n], k, 32);
+  f->seq[f->n] = seq;
   f->slots[h] = ++f->n;
   return 1;
 }
+static inline unsigned key_shard(uint64_t hash) { return (unsigned)(hash >> (64 - ORC_SHARD_BITS)); }
 
 /* per-thread scratch + result arrays are owned by the context and only grow: after one warm-up call
  * a batch of the same size touches no fresh pages (first-touch page faults would otherwise dominate
@@ -481,11 +504,18 @@ struct work {
   uint64_t* linelen; /* [r1-r0] */
   uint8_t* status;   /* [r1-r0] */
   uint32_t* nlinks;  /* [r1-r0] */
+  /* parallel driver */
+  int tid, nthreads;
+  struct batch_job* job;
+  buf_t bucket[ORC_SHARDS]; /* indexes (into this thread's links) of the eligible links, per frontier shard */
+  uint64_t json_base, link_base; /* prefix sums over the threads */
+  uint64_t n_new;
 };
 struct orc_ctx {
   tgi_config cfg;
   char* label;
-  fset_t fs;
+  fset_t fs[ORC_SHARDS];
+  uint64_t seq; /* next global sequence number */
   work_t* w;
   int nw;
   buf_t r_status, r_jsonl, r_line_off, r_link_off, r_links;
@@ -505,12 +535,12 @@ void orc_destroy(orc_ctx* c) {
     work_t* w = &c->w[t];
     free(w->json.p); free(w->links.p); free(w->b_linelen.p); free(w->b_status.p); free(w->b_nlinks.p);
     free(w->b_tmp.p); free(w->scratch.p);
+    for (int i = 0; i < ORC_SHARDS; i++) free(w->bucket[i].p);
   }
   free(c->w);
   free(c->r_status.p); free(c->r_jsonl.p); free(c->r_line_off.p); free(c->r_link_off.p); free(c->r_links.p);
   free(c->label);
-  free(c->fs.keys);
-  free(c->fs.slots);
+  for (int i = 0; i < ORC_SHARDS; i++) { free(c->fs[i].keys); free(c->fs[i].seq); free(c->fs[i].slots); }
   free(c);
 }
 void orc_set_clock(orc_ctx* c, int64_t cs, int32_t cn, int64_t ps, int32_t pn) {
@@ -521,20 +551,40 @@ void orc_set_clock(orc_ctx* c, int64_t cs, int32_t cn, int64_t ps, int32_t pn) {
 }
 int orc_frontier_insert(orc_ctx* c, const uint8_t* keys32, uint64_t n, uint8_t* is_new) {
   for (uint64_t i = 0; i < n; i++) {
-    int nw = fset_insert(&c->fs, keys32 + 32 * i);
+    const uint64_t h = key_hash(keys32 + 32 * i);
+    int nw = fset_insert_h(&c->fs[key_shard(h)], keys32 + 32 * i, h, c->seq++);
     if (is_new) is_new[i] = (uint8_t)nw;
   }
   return 0;
 }
-uint64_t orc_frontier_size(orc_ctx* c) { return c->fs.n; }
+uint64_t orc_frontier_size(orc_ctx* c) {
+  uint64_t n = 0;
+  for (int i = 0; i < ORC_SHARDS; i++) n += c->fs[i].n;
+  return n;
+}
+typedef struct { uint64_t seq; const uint8_t* key; } seqkey_t;
+static int seqkey_cmp(const void* a, const void* b) {
+  const uint64_t x = ((const seqkey_t*)a)->seq, y = ((const seqkey_t*)b)->seq;
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+/* keys in first-occurrence order */
 uint64_t orc_frontier_export(orc_ctx* c, uint8_t* keys32, uint64_t cap) {
-  uint64_t n = c->fs.n < cap ? c->fs.n : cap;
-  memcpy(keys32, c->fs.keys, n * 32);
+  const uint64_t tot = orc_frontier_size(c);
+  seqkey_t* v = (seqkey_t*)malloc(sizeof(seqkey_t) * (tot ? tot : 1));
+  uint64_t m = 0;
+  for (int i = 0; i < ORC_SHARDS; i++)
+    for (uint64_t k = 0; k < c->fs[i].n; k++) { v[m].seq = c->fs[i].seq[k]; v[m].key = c->fs[i].keys[k]; m++; }
+  qsort(v, m, sizeof(seqkey_t), seqkey_cmp);
+  const uint64_t n = tot < cap ? tot : cap;
+  for (uint64_t k = 0; k < n; k++) memcpy(keys32 + 32 * k, v[k].key, 32);
+  free(v);
   return n;
 }
 void orc_frontier_clear(orc_ctx* c) {
-  c->fs.n = 0;
-  if (c->fs.slots) memset(c->fs.slots, 0, c->fs.nslots * sizeof(uint64_t));
+  for (int i = 0; i < ORC_SHARDS; i++) {
+    c->fs[i].n = 0;
+    if (c->fs[i].slots) memset(c->fs[i].slots, 0, c->fs[i].nslots * sizeof(uint64_t));
+  }
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -1113,24 +1163,44 @@ static int gm_record(const orc_ctx* c, const tgi_gm_batch* b, uint64_t r, buf_t*
 
 #define ORC_MAX_LINKS 4096
 
-static void* worker(void* arg) {
-  work_t* w = (work_t*)arg;
+/* One batch = three phases on nthreads threads (the --concurrency analogue of the reference's worker
+ * pool), separated by barriers; nthreads == 1 runs the same code sequentially:
+ *   1. produce: every thread walks its contiguous record range (tg_record / yt_record / gm_record), appends the
+ *      lines to its own buffer and buckets its frontier-eligible links by set shard;
+ *   2. (thread 0) prefix sums over the threads' byte / link counts;
+ *   3. place: every thread copies its lines and links to their final offsets (skipped for the lines with
+ *      ORC_RUN_SLICES: the reference's workers append to per-channel files, there is no global concatenation on
+ *      that path) and fills status / line_off / link_off of its range; then every thread inserts the links of the
+ *      shards it owns, visiting the producing threads in order = global record order, so "first occurrence wins"
+ *      and the NEW flags are the sequential ones.
+ * No step is serial in the number of records.                                                                  */
+struct batch_job {
+  orc_ctx* c;
+  orc_result* out;
+  uint64_t n;
+  uint32_t run_flags;
+  pthread_barrier_t bar;
+  int pin;
+};
+
+static void produce(work_t* w) {
   uint64_t m = w->r1 - w->r0;
   w->json.len = w->links.len = w->b_linelen.len = w->b_status.len = w->b_nlinks.len = w->b_tmp.len = 0;
+  for (int i = 0; i < ORC_SHARDS; i++) w->bucket[i].len = 0;
   buf_reserve(&w->b_linelen, (m + 1) * 8); w->linelen = (uint64_t*)w->b_linelen.p;
   buf_reserve(&w->b_status, m + 1); w->status = w->b_status.p;
   buf_reserve(&w->b_nlinks, (m + 1) * 4); w->nlinks = (uint32_t*)w->b_nlinks.p;
   buf_reserve(&w->b_tmp, sizeof(tgi_link) * ORC_MAX_LINKS);
-  tgi_link* tmp = (tgi_link*)w->b_tmp.p;
+  const uint32_t rf = w->run_flags;
   for (uint64_t r = w->r0; r < w->r1; r++) {
-    linkset_t ls = {tmp, 0, ORC_MAX_LINKS, 0};
-    buf_t* o = (w->run_flags & TGI_RUN_JSONL) ? &w->json : &w->scratch;
+    linkset_t ls = {(tgi_link*)w->b_tmp.p, 0, (int)(w->b_tmp.cap / sizeof(tgi_link)), 0, &w->b_tmp};
+    buf_t* o = (rf & TGI_RUN_JSONL) ? &w->json : &w->scratch;
     w->scratch.len = 0;
     w->nlinks[r - w->r0] = 0;
     size_t before = o->len;
     int st = w->tg ? tg_record(w->c, w->tg, r, o, &ls) : w->yt ? yt_record(w->c, w->yt, r, o, &ls) : gm_record(w->c, w->gm, r, o);
     w->status[r - w->r0] = (uint8_t)st;
-    w->linelen[r - w->r0] = (w->run_flags & TGI_RUN_JSONL) ? o->len - before : 0;
+    w->linelen[r - w->r0] = (rf & TGI_RUN_JSONL) ? o->len - before : 0;
     if (st == TGI_ST_EMITTED || st == TGI_ST_NOLINE) {
       const uint8_t* cname = NULL;
       uint32_t cname_n = 0;
@@ -1144,11 +1214,93 @@ static void* worker(void* arg) {
         l->filter_reason = (uint8_t)orc_filter_username(l->name, l->len);
         if (l->filter_reason == TGI_FU_VALID) l->flags |= TGI_LF_FILTER_OK;
         if (cname && l->len == cname_n && memcmp(l->name, cname, cname_n) == 0) l->flags |= TGI_LF_SELF;
+        if (rf & TGI_RUN_FRONTIER) {
+          if ((rf & TGI_RUN_SKIP_SELF) && (l->flags & TGI_LF_SELF)) continue;   /* runner.go:1231 */
+          if ((rf & TGI_RUN_FILTER) && !(l->flags & TGI_LF_FILTER_OK)) continue; /* runner.go:1261 */
+          const uint32_t idx = (uint32_t)(w->links.len / sizeof(tgi_link)) + (uint32_t)k;
+          buf_put(&w->bucket[key_shard(key_hash(l->name))], &idx, 4);
+        }
       }
       buf_put(&w->links, ls.v, sizeof(tgi_link) * (size_t)ls.n);
       w->nlinks[r - w->r0] = (uint32_t)ls.n;
     }
   }
+}
+
+static void place(work_t* w) {
+  struct batch_job* j = w->job;
+  orc_result* out = j->out;
+  if (out->jsonl && w->json.len) memcpy(out->jsonl + w->json_base, w->json.p, w->json.len);
+  if (w->links.len) memcpy(out->links + w->link_base, w->links.p, w->links.len);
+  uint64_t a = w->json_base, bq = w->link_base;
+  for (uint64_t r = w->r0; r < w->r1; r++) {
+    out->status[r] = w->status[r - w->r0];
+    out->line_off[r] = a;
+    out->link_off[r] = (uint32_t)bq;
+    a += w->linelen[r - w->r0];
+    bq += w->nlinks[r - w->r0];
+  }
+}
+
+static void insert_shards(work_t* w) {
+  struct batch_job* j = w->job;
+  orc_ctx* c = j->c;
+  work_t* all = c->w;
+  w->n_new = 0;
+  for (int s = w->tid; s < ORC_SHARDS; s += w->nthreads) {
+    fset_t* f = &c->fs[s];
+    for (int t = 0; t < w->nthreads; t++) {
+      const uint32_t* idx = (const uint32_t*)all[t].bucket[s].p;
+      const uint64_t cnt = all[t].bucket[s].len / 4;
+      tgi_link* links = j->out->links + all[t].link_base;
+      for (uint64_t k = 0; k < cnt; k++) {
+        tgi_link* l = &links[idx[k]];
+        if (fset_insert_h(f, l->name, key_hash(l->name), c->seq + all[t].link_base + idx[k])) {
+          l->flags |= TGI_LF_NEW;
+          w->n_new++;
+        }
+      }
+    }
+  }
+}
+
+static void* worker(void* arg) {
+  work_t* w = (work_t*)arg;
+  struct batch_job* j = w->job;
+  if (j->pin) { /* one thread per core, so that a thread's buffers stay on its NUMA node */
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    CPU_SET(w->tid, &set);
+    pthread_setaffinity_np(pthread_self(), sizeof set, &set);
+  }
+  produce(w);
+  if (w->nthreads > 1) pthread_barrier_wait(&j->bar);
+  if (w->tid == 0) {
+    orc_ctx* c = j->c;
+    orc_result* out = j->out;
+    uint64_t jl = 0, nl = 0;
+    for (int t = 0; t < w->nthreads; t++) {
+      c->w[t].json_base = jl;
+      c->w[t].link_base = nl;
+      jl += c->w[t].json.len;
+      nl += c->w[t].links.len / sizeof(tgi_link);
+    }
+    const uint64_t n = j->n;
+    c->r_status.len = c->r_jsonl.len = c->r_line_off.len = c->r_link_off.len = c->r_links.len = 0;
+    buf_reserve(&c->r_status, n + 1); out->status = c->r_status.p;
+    buf_reserve(&c->r_line_off, 8 * (n + 1)); out->line_off = (uint64_t*)c->r_line_off.p;
+    buf_reserve(&c->r_link_off, 4 * (n + 1)); out->link_off = (uint32_t*)c->r_link_off.p;
+    if (!(j->run_flags & ORC_RUN_SLICES)) { buf_reserve(&c->r_jsonl, jl + 1); out->jsonl = c->r_jsonl.p; }
+    buf_reserve(&c->r_links, sizeof(tgi_link) * (nl + 1)); out->links = (tgi_link*)c->r_links.p;
+    out->line_off[n] = jl;
+    out->link_off[n] = (uint32_t)nl;
+    out->jsonl_len = jl;
+    out->n_links = nl;
+  }
+  if (w->nthreads > 1) pthread_barrier_wait(&j->bar);
+  place(w);
+  if (w->nthreads > 1) pthread_barrier_wait(&j->bar);
+  if (j->run_flags & TGI_RUN_FRONTIER) insert_shards(w);
   return NULL;
 }
 
@@ -1163,55 +1315,30 @@ static int run_batch(orc_ctx* c, const tgi_tg_batch* tg, const tgi_yt_batch* yt,
     c->nw = nthreads;
   }
   work_t* w = c->w;
+  memset(out, 0, sizeof *out);
+  out->n = n;
+  struct batch_job job;
+  job.c = c; job.out = out; job.n = n; job.run_flags = run_flags;
+  job.pin = (run_flags & ORC_RUN_PIN) != 0;
+  if (nthreads > 1) pthread_barrier_init(&job.bar, NULL, (unsigned)nthreads);
   pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
   for (int t = 0; t < nthreads; t++) {
     w[t].c = c; w[t].tg = tg; w[t].yt = yt; w[t].gm = gm; w[t].run_flags = run_flags;
+    w[t].tid = t; w[t].nthreads = nthreads; w[t].job = &job;
     w[t].r0 = n * (uint64_t)t / (uint64_t)nthreads;
     w[t].r1 = n * (uint64_t)(t + 1) / (uint64_t)nthreads;
     if (nthreads > 1) pthread_create(&th[t], NULL, worker, &w[t]);
     else worker(&w[t]);
   }
-  if (nthreads > 1)
+  if (nthreads > 1) {
     for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
-  memset(out, 0, sizeof *out);
-  out->n = n;
-  uint64_t jl = 0, nl = 0;
-  for (int t = 0; t < nthreads; t++) { jl += w[t].json.len; nl += w[t].links.len / sizeof(tgi_link); }
-  c->r_status.len = c->r_jsonl.len = c->r_line_off.len = c->r_link_off.len = c->r_links.len = 0;
-  buf_reserve(&c->r_status, n + 1); out->status = c->r_status.p;
-  buf_reserve(&c->r_line_off, 8 * (n + 1)); out->line_off = (uint64_t*)c->r_line_off.p;
-  buf_reserve(&c->r_link_off, 4 * (n + 1)); out->link_off = (uint32_t*)c->r_link_off.p;
-  buf_reserve(&c->r_jsonl, jl + 1); out->jsonl = c->r_jsonl.p;
-  buf_reserve(&c->r_links, sizeof(tgi_link) * (nl + 1)); out->links = (tgi_link*)c->r_links.p;
-  uint64_t jo = 0, lo = 0;
-  for (int t = 0; t < nthreads; t++) {
-    memcpy(out->jsonl + jo, w[t].json.p, w[t].json.len);
-    memcpy(out->links + lo, w[t].links.p, w[t].links.len);
-    uint64_t a = jo, bq = lo;
-    for (uint64_t r = w[t].r0; r < w[t].r1; r++) {
-      out->status[r] = w[t].status[r - w[t].r0];
-      out->line_off[r] = a;
-      out->link_off[r] = (uint32_t)bq;
-      a += w[t].linelen[r - w[t].r0];
-      bq += w[t].nlinks[r - w[t].r0];
-    }
-    jo += w[t].json.len;
-    lo += w[t].links.len / sizeof(tgi_link);
+    pthread_barrier_destroy(&job.bar);
   }
-  out->line_off[n] = jo;
-  out->link_off[n] = (uint32_t)lo;
-  out->jsonl_len = jo;
-  out->n_links = lo;
-  /* frontier: sequential in record order, like the mutex-guarded Go maps */
   if (run_flags & TGI_RUN_FRONTIER) {
-    for (uint64_t k = 0; k < lo; k++) {
-      tgi_link* l = &out->links[k];
-      if ((run_flags & TGI_RUN_SKIP_SELF) && (l->flags & TGI_LF_SELF)) continue;
-      if ((run_flags & TGI_RUN_FILTER) && !(l->flags & TGI_LF_FILTER_OK)) continue;
-      if (fset_insert(&c->fs, l->name)) { l->flags |= TGI_LF_NEW; out->n_new++; }
-    }
+    for (int t = 0; t < nthreads; t++) out->n_new += w[t].n_new;
+    c->seq += out->n_links;
   }
-  out->frontier_size = c->fs.n;
+  out->frontier_size = orc_frontier_size(c);
   free(th);
   return 0;
 }

@@ -45,6 +45,12 @@ void orc_destroy(orc_ctx* c);
 void orc_set_clock(orc_ctx* c, int64_t created_at_sec, int32_t created_at_nsec, int64_t capture_sec,
                    int32_t capture_nsec);
 
+/* oracle-only run flags (beside TGI_RUN_*): how the timed CPU arm is run */
+#define ORC_RUN_SLICES 0x10000u /* leave the lines in the worker threads' own buffers (result.jsonl == NULL, jsonl_len and
+                                   line_off are still the global ones): the reference's workers append to per-channel files,
+                                   nothing on that path concatenates the output of different workers                      */
+#define ORC_RUN_PIN 0x20000u    /* pin worker t to core t (NUMA-local buffers)                                          */
+
 /* nthreads <= 1: sequential like the reference loop (crawl/runner.go:1161). nthreads > 1: records
  * are split into contiguous ranges (the --concurrency analogue); output is identical.            */
 int orc_telegram_batch(orc_ctx* c, const tgi_tg_batch* in, uint32_t run_flags, int nthreads,

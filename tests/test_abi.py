@@ -25,7 +25,7 @@ int main(void) {
          sizeof(tgi_link), sizeof(tgi_tg_batch), sizeof(tgi_yt_batch), sizeof(tgi_config), sizeof(tgi_result),
          sizeof(tgi_stats));
   printf("%zu %zu %zu\n", offsetof(tgi_config, crawl_label), offsetof(tgi_result, kernel_ms), offsetof(tgi_tg_rec, content_type));
-  printf("%zu %zu %zu %zu\n", sizeof(tgi_gm_rec), sizeof(tgi_gm_reaction), sizeof(tgi_gm_batch), offsetof(tgi_result, lane_bytes_in));
+  printf("%zu %zu %zu %zu\n", sizeof(tgi_gm_rec), sizeof(tgi_gm_reaction), sizeof(tgi_gm_batch), offsetof(tgi_result, frontier_ms));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -39,7 +39,7 @@ int main(void) {
             C.sizeof(abi.TgBatchC), C.sizeof(abi.YtBatchC), C.sizeof(abi.ConfigC), C.sizeof(abi.ResultC),
             C.sizeof(abi.StatsC), abi.ConfigC.crawl_label.offset, abi.ResultC.kernel_ms.offset,
             abi.TG_REC.fields["content_type"][1], abi.GM_REC.itemsize, abi.GM_REACTION.itemsize, C.sizeof(abi.GmBatchC),
-            abi.ResultC.lane_bytes_in.offset]
+            abi.ResultC.frontier_ms.offset]
     assert got == want
 
 
