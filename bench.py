@@ -457,9 +457,10 @@ def main():
             # whole step: every input byte read once, every output byte written once, 8 B line offset
             alg_bytes = in_bytes + jsonl_len + 8 * (n + 1)
             kname = "yt_emit_tile_kernel" if is_yt else "tg_emit_tile_kernel"
-            # the emit kernel: per record it reads the header, the line offset and the piece lengths of the size pass,
-            # reads every source byte it copies and writes every JSONL byte (both counted by the kernel itself)
-            k_alg = (acc.lane_out + acc.lane_in) // args.steps + n * (64 + 8 + 32)
+            # the emit kernel: per record it reads the header (64 B), the line offset (8 B) and the piece lengths of the
+            # size pass (32 B), reads every source byte it copies and writes every JSONL byte; both sums are counted by
+            # the kernel itself (tgi_result.main_bytes_in / main_bytes_out)
+            k_alg = (acc.lane_out + acc.lane_in) // args.steps
             k_ms = per("main")
         else:
             # link-extract + dedup: mini header 24 B + text + entities + entity URLs read once,

@@ -492,8 +492,8 @@ DEVI void put_u(const D& d, uint32_t o, uint32_t a, uint32_t b, uint32_t c, uint
 
 // JSON-escape s[0..n) to dst (no quotes); returns the bytes written.  128-byte strips, 4 bytes per
 // lane; a warp scan over the per-lane output lengths places every lane's bytes.
-__device__ __noinline__ uint32_t esc_to_global(uint8_t* dstp, const uint8_t* s, uint32_t n) {
-  DstG dst{dstp};
+template <class D>
+__device__ __noinline__ uint32_t esc_to(D dst, const uint8_t* s, uint32_t n) {
   uint32_t carry = 0, out = 0;
   for (int64_t base = 0; base < (int64_t)n; base += 128) {
     Strip st = warp_load_strip(s, base, n, carry);
@@ -543,8 +543,8 @@ __device__ __noinline__ uint32_t esc_to_global(uint8_t* dstp, const uint8_t* s, 
 
 // The same for a string whose non-ASCII bytes all pass through unchanged (warp_esc_len reported
 // needs_exact == false): no UTF-8 bookkeeping, so a lane can own 16 bytes and a strip is 512 bytes.
-__device__ __noinline__ uint32_t esc_ascii_to_global(uint8_t* dstp, const uint8_t* s, uint32_t n) {
-  DstG dst{dstp};
+template <class D>
+__device__ __noinline__ uint32_t esc_ascii_to(D dst, const uint8_t* s, uint32_t n) {
   const uint32_t l = lane_id();
   const uint32_t M = 0x80808080u, L7 = 0x7F7F7F7Fu;
   uint32_t out = 0;
@@ -596,6 +596,9 @@ __device__ __noinline__ uint32_t esc_ascii_to_global(uint8_t* dstp, const uint8_
   }
   return out;
 }
+
+DEVI uint32_t esc_to_global(uint8_t* dstp, const uint8_t* s, uint32_t n) { return esc_to(DstG{dstp}, s, n); }
+DEVI uint32_t esc_ascii_to_global(uint8_t* dstp, const uint8_t* s, uint32_t n) { return esc_ascii_to(DstG{dstp}, s, n); }
 
 // single-thread escape of a short string into shared memory (map keys); ~0u if it does not fit
 DEVI uint32_t thread_esc(const uint8_t* s, uint32_t n, uint32_t d, uint32_t cap) {
@@ -666,6 +669,23 @@ __device__ __noinline__ void warp_copy_vec(uint8_t* dst, const uint8_t* src, uin
   }
   const uint32_t t0 = nb << 4;
   if (t0 + l < n) dst[t0 + l] = (uint8_t)ldb(src + t0 + l);
+}
+// the same three through a byte sink (DstG: the output blob, DstS: a line being assembled in shared memory)
+template <class D>
+DEVI void copy_g(const D& d, const uint8_t* src, uint32_t n) {
+  for (uint32_t i = lane_id(); i < n; i += 32) d.st(i, ldb(src + i));
+}
+template <class D>
+DEVI void copy_s(const D& d, uint32_t src, uint32_t n) {
+  for (uint32_t i = lane_id(); i < n; i += 32) d.st(i, lds8(src + i));
+}
+template <class D>
+DEVI void put1(const D& d, uint32_t c) {
+  if (lane_id() == 0) d.st(0, c);
+}
+template <class D>
+DEVI void put2(const D& d, uint32_t c0, uint32_t c1) {
+  if (lane_id() < 2) d.st(lane_id(), lane_id() ? c1 : c0);
 }
 DEVI void gcopy_s(uint8_t* dst, uint32_t src, uint32_t n) {
   for (uint32_t i = lane_id(); i < n; i += 32) dst[i] = (uint8_t)lds8(src + i);

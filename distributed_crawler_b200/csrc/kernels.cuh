@@ -4,16 +4,15 @@
 //   tg_parse / tg_ent_map / tg_parse_ent   status + link extraction, one warp per record (split by code footprint)
 //   tg_size_lane                           JSONL line length, one LANE per record (+ the warp for the message text)
 //   scan_*                                 exclusive scan u32 -> u64 offsets
-//   tg_emit_lane                           the line, one LANE per record (tg_lane.cuh)
-//   tg_emit_esc / tg_emit_maps             what the lane emitter leaves: strings that need escaping, comment lists ...
+//   tg_emit_tile                           the lines, assembled in shared memory and retired with bulk stores (tg_tile.cuh)
+//   tg_emit_slow                           the few lines that do not fit a tile buffer: one warp per record, direct stores
 //   frontier_*                             exact open-addressed hash set over 32-byte keys
 //   yt_* / gm_*                            YouTube (config 4) and generic-message (a12) lines
 //   join_*                                 message-status join
-// tg_size_kernel / tg_emit_fixed_kernel / yt_size_kernel are the warp-per-record predecessors of the lane
-// kernels, kept as an A/B reference (TGI_SIZE_WARP, TGI_EMIT_FIXED_WARP, TGI_YT_WARP).
+// yt_size_kernel is the warp-per-record predecessor of the YouTube lane sizer, kept as an A/B reference (TGI_YT_WARP).
 #pragma once
 #include "tg_walk.cuh"
-#include "tg_lane.cuh"
+#include "tg_tile.cuh"
 #include "yt_walk.cuh"
 #include "gm_walk.cuh"
 #include "yt_lane.cuh"
@@ -57,6 +56,7 @@ struct ParseOut {
   uint32_t* link_count;  // [n]
   uint32_t* xlen;        // [n][8] emitted lengths of the variable pieces (XL_*)
   unsigned long long* var_total;  // sum of the variable pieces' lengths (statistics)
+  unsigned long long* slow_total; // records flagged XLF_SLOW
   tgi_link* arena;
   uint32_t arena_cap;
   uint32_t* cursor;      // arena allocation cursor (keeps counting past arena_cap)
@@ -188,35 +188,6 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_ent_kernel(TgBatchDev
   }
 }
 
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_kernel(TgBatchDev b, CfgDev cfg, ParseOut o) {
-  int wid = threadIdx.x >> 5, l = lane_id();
-  uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
-  uint64_t var_sum = 0;
-  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
-    if (o.status[r] != TGI_ST_EMITTED) continue;
-    TgWalkArgs a;
-    a.b = &b;
-    a.cfg = &cfg;
-    a.r = r;
-    a.v = load_rec_view(b, r);
-    a.links = o.arena + o.link_start[r];
-    a.n_links = o.link_count[r];
-    uint32_t xl[8];
-    uint32_t llen = size_tg_record(a, xl);
-    uint32_t mine = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++)
-      if (l == j) mine = xl[j];
-    if (l < 8) o.xlen[r * 8 + l] = mine;
-    if (llen) var_sum += warp_sum(l < XL_COUNT ? mine : 0u);
-    if (l == 0) {
-      if (llen == 0) o.status[r] = TGI_ST_NOLINE;
-      o.linelen[r] = llen;
-    }
-  }
-  if (l == 0 && var_sum) atomicAdd(o.var_total, (unsigned long long)var_sum);
-}
-
 // The same sizes, 32 records per warp: every lane sizes the small pieces of its own record (numbers,
 // handle / media strings, comments, reactions, outlinks); only the message text, the one long string,
 // is measured by the whole warp, record after record; the rare complicated pieces (a comment list, a
@@ -225,6 +196,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_lane_kernel(TgBatchDev
   const int wid = threadIdx.x >> 5, l = lane_id();
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   uint64_t var_sum = 0;
+  uint32_t nslow = 0;
   for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
     uint64_t r = g * 32 + l;
     bool active = r < b.n;
@@ -333,6 +305,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_lane_kernel(TgBatchDev
 #pragma unroll
       for (int j = 0; j < XL_COUNT; j++) var += xl[j];
       const uint32_t llen = sized ? tot + var : 0u;
+      // lines that do not fit a tile buffer (with the map scratch behind them, if they need it) take tg_emit_slow_kernel
+      if (llen + (tg_needs_scratch(nr, d.comments_nil, d.c0, d.c1) ? TILE_SCRATCH : 0u) > TILE_BUF - 16u) {
+        xl[XL_FLAGS] |= XLF_SLOW;
+        nslow++;
+      }
       *(uint4*)(o.xlen + r * 8) = make_uint4(xl[0], xl[1], xl[2], xl[3]);
       *(uint4*)(o.xlen + r * 8 + 4) = make_uint4(xl[4], xl[5], xl[6], xl[7]);
       if (llen == 0) o.status[r] = TGI_ST_NOLINE;
@@ -342,75 +319,79 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_lane_kernel(TgBatchDev
   }
   for (int dd = 16; dd; dd >>= 1) var_sum += __shfl_down_sync(FULL, var_sum, dd);
   if (l == 0 && var_sum) atomicAdd(o.var_total, (unsigned long long)var_sum);
+  nslow = warp_sum(nslow);
+  if (l == 0 && nslow) atomicAdd(o.slow_total, (unsigned long long)nslow);
 }
 
-// ---- emit: three small kernels, one warp per record, direct stores into the output blob ----------
-// Small kernels on purpose: the B200 instruction caches are tiny (L0 ~6 KB per sub-partition, L1.5
-// 32 KB per SM).  A single fused emit kernel (70-100 KB of SASS) spent most of its cycles in
-// stall_no_instruction; split by piece class, every kernel's hot loop fits the L1.5.
+// ---- emit --------------------------------------------------------------------------------------------------------
 struct EmitIn {
   const uint8_t* status;
   const uint64_t* line_off;
   const uint32_t* link_start;
   const uint32_t* link_count;
-  const uint32_t* xlen;  // [n][8] lengths of the variable pieces
-  uint32_t* xpos;        // [n][8] their offsets inside the line (written by kernel 1)
+  const uint32_t* xlen;  // [n][8] lengths of the variable pieces + flags
   const tgi_link* arena;
   uint8_t* out;
   int* err;
-  uint32_t lane_text_max;  // see emit_tg_escapes
-  unsigned long long* counters;  // [0] bytes written by the lane emitter, [1] bytes it copied from HBM sources
+  unsigned long long* counters;  // [0] JSONL bytes written by the tile kernel, [1] source bytes it read from HBM
 };
 
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_fixed_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
-  __shared__ WarpScratch wss[WARPS_PER_CTA];
-  __shared__ CtaShared cs;
-  const int wid = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < kTgNEnt; i += blockDim.x) cs.ents[i] = kTgPieces[i];
+// Tile emitter (tg_tile.cuh): one warp per 32 consecutive records, 16 prepared at a time.
+__global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_tile_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
+  extern __shared__ __align__(128) uint8_t tile_smem[];
+  TileShared& sh = *(TileShared*)tile_smem;
+  static_assert(TILE_WARPS == WARPS_PER_CTA, "one buffer per warp");
   for (int i = threadIdx.x; i < kTgNWords; i += blockDim.x) {
-    cs.tmpl[i] = ((const uint32_t*)kTgTemplate)[i];
-    cs.wmeta[i] = kTgWordMeta[i];
+    sh.tmpl[i] = ((const uint32_t*)kTgTemplate)[i];
+    sh.wmeta[i] = kTgWordMeta[i];
   }
-  __syncthreads();
-  const uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
-  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
-    if (in.status[r] != TGI_ST_EMITTED) continue;
-    TgWalkArgs a;
-    a.b = &b;
-    a.cfg = &cfg;
-    a.r = r;
-    a.v = load_rec_view(b, r);
-    a.links = nullptr;
-    a.n_links = 0;
-    const uint64_t lo = in.line_off[r];
-    emit_tg_fixed(in.out + lo, &wss[wid], &cs, a, (uint32_t)(in.line_off[r + 1] - lo), in.xlen + r * 8, in.xpos + r * 8, in.err);
+  for (int i = threadIdx.x; i < kTgNEnt; i += blockDim.x) sh.pieces[i] = kTgPieces[i];
+  for (int i = threadIdx.x; i < TGI_CT__COUNT * 8; i += blockDim.x) {
+    const int ct = i >> 3, w = i & 7;
+    sh.ptype[i] = w < 7 ? ((const uint32_t*)kPostType[ct])[w] : 0u;
   }
-}
-
-// the same job, one LANE per record (tg_lane.cuh): 32 records per warp task
-__global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_lane_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
-  extern __shared__ __align__(128) uint8_t lane_smem[];
-  LaneShared& sh = *(LaneShared*)lane_smem;
-  static_assert(LANE_WARPS == WARPS_PER_CTA, "one field row block per warp");
-  lane_shared_fill(sh);
   __syncthreads();
   const int wid = threadIdx.x >> 5, l = lane_id();
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
-  LaneStream s;
-  ls_init(s, smem_addr(sh.stage[wid][l]));
+  TileStream t;
+  t.buf_s = smem_addr(sh.buf[wid]);
+  TileIn ti;
+  ti.xlen = in.xlen;
+  ti.link_start = in.link_start;
+  ti.link_count = in.link_count;
+  ti.arena = in.arena;
+  ti.err = in.err;
+  const uint64_t out0 = (uint64_t)(uintptr_t)in.out;
   uint64_t bytes_out = 0, bytes_in = 0;
   for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
-    uint64_t r = g * 32 + l;
-    bool active = r < b.n;
-    if (!active) r = b.n - 1;
-    active = active && in.status[r] == TGI_ST_EMITTED;
-    if (!__any_sync(FULL, active)) continue;
-    emit_tg_lane(sh, sh.rows[wid][l], s, b, cfg, r, active, in.out, in.line_off, in.xlen + r * 8, in.xpos + r * 8,
-                 in.arena + in.link_start[r], active ? in.link_count[r] : 0u, in.err, bytes_out, bytes_in);
-  }
-  for (int dd = 16; dd; dd >>= 1) {
-    bytes_out += __shfl_down_sync(FULL, bytes_out, dd);
-    bytes_in += __shfl_down_sync(FULL, bytes_in, dd);
+    const uint64_t r0 = g * 32, r1 = r0 + 32 < b.n ? r0 + 32 : b.n;
+    ts_begin(t, out0 + in.line_off[r0]);
+    for (uint64_t h = r0; h < r1; h += TILE_GROUP) {
+      __syncwarp();
+      {  // lane-parallel preparation of up to 16 records
+        const uint64_t rr = h + (uint64_t)l;
+        if (l < TILE_GROUP && rr < r1 && in.status[rr] == TGI_ST_EMITTED && !(in.xlen[rr * 8 + XL_FLAGS] & XLF_SLOW)) {
+          const tgi_tg_rec* rec = &b.recs[rr];
+          const bool nil = (rec->flags & TGI_RF_COMMENTS_NIL) != 0;
+          tile_prep(sh.rows[wid][l], rec, nil, b.comment_off[rr + 1] - b.comment_off[rr], cfg.tz);
+        }
+      }
+      __syncwarp();
+      for (int j = 0; j < TILE_GROUP && h + j < r1; j++) {
+        const uint64_t r = h + j;
+        if (in.status[r] != TGI_ST_EMITTED) continue;  // no line: the stream is not interrupted
+        const uint64_t lo = in.line_off[r];
+        const uint32_t total = (uint32_t)(in.line_off[r + 1] - lo);
+        if (in.xlen[r * 8 + XL_FLAGS] & XLF_SLOW) {  // somebody else writes this line: close the stream around it
+          ts_flush(t, true);
+          ts_begin(t, out0 + lo + total);
+          continue;
+        }
+        tile_emit_record(sh, wid, t, b, cfg, r, smem_addr(sh.rows[wid][j]), total, ti, bytes_in);
+        bytes_out += total;
+      }
+    }
+    ts_flush(t, true);
   }
   if (l == 0) {
     atomicAdd(in.counters, (unsigned long long)bytes_out);
@@ -418,79 +399,51 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_lane_kernel(TgBatchDev
   }
 }
 
-// The esc and maps kernels take what the lane emitter left: each lane first checks one record of a
-// group of 32, then the warp walks the records that need it (most do not).
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_esc_kernel(TgBatchDev b, EmitIn in) {
+// Slow path: lines longer than a tile buffer.  Lanes pick them out of groups of 32 records, then one warp per record:
+// the table-driven walker for the fixed part, the escapers, the map / list writers, all with direct stores.
+struct SlowShared {
+  CtaShared cs;
+  WarpScratch ws[WARPS_PER_CTA];
+  MapScratch ms[WARPS_PER_CTA];
+  uint32_t xpos[WARPS_PER_CTA][8];
+};
+__global__ void __launch_bounds__(CTA_THREADS, 2) tg_emit_slow_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
+  extern __shared__ __align__(16) uint8_t slow_smem[];
+  SlowShared& sh = *(SlowShared*)slow_smem;
   const int wid = threadIdx.x >> 5, l = lane_id();
-  const bool lane_mode = in.lane_text_max != 0xffffffffu;
-  const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
-  for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
-    const uint64_t r = g * 32 + l;
-    bool need = false;
-    if (r < b.n && in.status[r] == TGI_ST_EMITTED) {
-      need = true;
-      if (lane_mode) {  // same rule as emit_tg_lane: clean and short strings are already in place
-        const tgi_tg_rec* rec = &b.recs[r];
-        const uint4 xl = *(const uint4*)(in.xlen + r * 8);
-        const uint32_t ct = rec->content_type;
-        const bool text_desc = ct == TGI_CT_TEXT || ct == TGI_CT_VIDEO || ct == TGI_CT_PHOTO || ct == TGI_CT_ANIMATION;
-        const uint32_t dlen = text_desc ? ((rec->flags & TGI_RF_HAS_TEXT) ? rec->text_len : 0u)
-                                        : (ct == TGI_CT_ANIMATED_EMOJI || ct == TGI_CT_POLL || ct == TGI_CT_GIVEAWAY ||
-                                           ct == TGI_CT_PAID_MEDIA || ct == TGI_CT_DOCUMENT) ? rec->alt_len : 0u;
-        auto left = [&](uint32_t x, uint32_t n) { return x != 0 && !(x == n && n <= in.lane_text_max); };
-        need = left(xl.x, dlen) || left(xl.y, rec->media_len) || left(xl.z, rec->handle_len) || left(xl.w, rec->alt_len);
-      }
-    }
-    uint32_t todo = __ballot_sync(FULL, need);
-    while (todo) {
-      const uint64_t rr = g * 32 + (uint32_t)(__ffs(todo) - 1);
-      todo &= todo - 1;
-      TgWalkArgs a;
-      a.b = &b;
-      a.cfg = nullptr;
-      a.r = rr;
-      a.v = load_rec_view(b, rr);
-      emit_tg_escapes(in.out + in.line_off[rr], a, in.xlen + rr * 8, in.xpos + rr * 8, in.lane_text_max);
-    }
+  for (int i = threadIdx.x; i < kTgNEnt; i += blockDim.x) sh.cs.ents[i] = kTgPieces[i];
+  for (int i = threadIdx.x; i < kTgNWords; i += blockDim.x) {
+    sh.cs.tmpl[i] = ((const uint32_t*)kTgTemplate)[i];
+    sh.cs.wmeta[i] = kTgWordMeta[i];
   }
-}
-
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_maps_kernel(TgBatchDev b, EmitIn in) {
-  __shared__ MapScratch mss[WARPS_PER_CTA];
-  const int wid = threadIdx.x >> 5, l = lane_id();
-  const bool lane = in.lane_text_max != 0xffffffffu;  // the lane emitter ran: it wrote the simple cases (tg_lane.cuh)
+  __syncthreads();
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
     const uint64_t rl = g * 32 + l;
-    bool need = false;
-    if (rl < b.n && in.status[rl] == TGI_ST_EMITTED) {
-      need = true;
-      if (lane) {
-        const bool list = !(b.recs[rl].flags & TGI_RF_COMMENTS_NIL) && b.comment_off[rl + 1] != b.comment_off[rl];
-        const bool map = b.react_off[rl + 1] != b.react_off[rl] && !(in.xlen[rl * 8 + XL_FLAGS] & XLF_SIMPLE_MAP);
-        need = list || map || in.link_count[rl] > LANE_LINKS_MAX;
-      }
-    }
-    uint32_t todo = __ballot_sync(FULL, need);
+    uint32_t todo = __ballot_sync(FULL, rl < b.n && in.status[rl] == TGI_ST_EMITTED && (in.xlen[rl * 8 + XL_FLAGS] & XLF_SLOW));
     while (todo) {
       const uint64_t r = g * 32 + (uint32_t)(__ffs(todo) - 1);
       todo &= todo - 1;
+      TgWalkArgs a;
+      a.b = &b;
+      a.cfg = &cfg;
+      a.r = r;
+      a.v = load_rec_view(b, r);
+      a.links = nullptr;
+      a.n_links = 0;
       uint8_t* line = in.out + in.line_off[r];
-      const uint32_t* xp = in.xpos + r * 8;
+      uint32_t* xp = sh.xpos[wid];
+      emit_tg_fixed(line, &sh.ws[wid], &sh.cs, a, (uint32_t)(in.line_off[r + 1] - in.line_off[r]), in.xlen + r * 8, xp, in.err);
+      __syncwarp();
+      emit_tg_escapes(line, a, in.xlen + r * 8, xp, 0xffffffffu);
       const bool comments_nil = (b.recs[r].flags & TGI_RF_COMMENTS_NIL) != 0;
       const uint32_t c0 = b.comment_off[r], c1 = b.comment_off[r + 1];
-      if (comments_nil) {
-        if (!lane) gcopy_g(line + xp[XL_COMMENTS], (const uint8_t*)kNullLit, 4);
-      } else if (c1 == c0) {
-        if (!lane) gput2(line + xp[XL_COMMENTS], '[', ']');
-      } else {
-        emit_tg_comments(line + xp[XL_COMMENTS], &mss[wid], b, c0, c1);
-      }
-      const uint32_t r0 = b.react_off[r], r1 = b.react_off[r + 1];
-      if (!(lane && (r1 == r0 || (in.xlen[r * 8 + XL_FLAGS] & XLF_SIMPLE_MAP))))
-        emit_reaction_map(line + xp[XL_REACTIONS], &mss[wid], b.reacts, r0, r1, b.aux);
+      if (comments_nil) gcopy_g(line + xp[XL_COMMENTS], (const uint8_t*)kNullLit, 4);
+      else if (c1 == c0) gput2(line + xp[XL_COMMENTS], '[', ']');
+      else emit_tg_comments(line + xp[XL_COMMENTS], &sh.ms[wid], b, c0, c1);
+      emit_reaction_map(line + xp[XL_REACTIONS], &sh.ms[wid], b.reacts, b.react_off[r], b.react_off[r + 1], b.aux);
       const uint32_t nl = in.link_count[r];
-      if (nl && !(lane && nl <= LANE_LINKS_MAX)) emit_tg_outlinks(line + xp[XL_OUTLINKS], in.arena + in.link_start[r], nl);
+      if (nl) emit_tg_outlinks(line + xp[XL_OUTLINKS], in.arena + in.link_start[r], nl);
       __syncwarp();
     }
   }

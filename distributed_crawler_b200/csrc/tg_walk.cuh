@@ -84,6 +84,7 @@ enum { F_MSGNO, F_CHAT, F_VIEW, F_SHARE, F_NCOMM, F_TIME, F_POSTTYPE };
 enum { XL_DESC, XL_MEDIA, XL_HANDLE, XL_ALT, XL_COMMENTS, XL_REACTIONS, XL_OUTLINKS, XL_COUNT, XL_FLAGS = 7 };
 #define XLF_SIMPLE_MAP 1u  // xlen[XL_FLAGS]: the reactions map is lane-renderable (size_reaction_map)
 #define XLF_DESC_EXACT 2u  // the description holds invalid UTF-8 or U+2028/9: only the exact escaper may write it
+#define XLF_SLOW 4u        // the line does not fit a tile buffer: tg_emit_slow_kernel writes it (tg_tile.cuh)
 constexpr uint32_t K_NOP = 15;
 #include "tg_pieces.inc"
 
@@ -170,11 +171,12 @@ __device__ __noinline__ uint32_t size_reaction_map(const tgi_reaction* reacts, u
 }
 
 // writes the map at dst, returns its length.  Every live lane renders its own  "key":count  into a
-// shared slot; the warp then concatenates the slots in key order.
-__device__ __noinline__ uint32_t emit_reaction_map(uint8_t* dst, MapScratch* ms, const tgi_reaction* reacts, uint32_t r0,
-                                                   uint32_t r1, const uint8_t* aux) {
+// shared slot; the warp then concatenates the slots in key order.  D = byte sink (DstG / DstS).
+template <class D>
+__device__ __noinline__ uint32_t emit_reaction_map_to(D dst, MapScratch* ms, const tgi_reaction* reacts, uint32_t r0,
+                                                      uint32_t r1, const uint8_t* aux) {
   if (r1 == r0) {
-    gput2(dst, '{', '}');
+    put2(dst, '{', '}');
     return 2;
   }
   int l = lane_id();
@@ -195,40 +197,43 @@ __device__ __noinline__ uint32_t emit_reaction_map(uint8_t* dst, MapScratch* ms,
   }
   __syncwarp();
   uint32_t o = 0;
-  gput1(dst, '{');
+  put1(dst, '{');
   o++;
   for (uint32_t r = 0; r < m.nlive; r++) {
     uint32_t who = __ballot_sync(FULL, m.live && m.rank == r);
     int src = __ffs(who) - 1;
     uint32_t len = __shfl_sync(FULL, sl, src);
     if (r) {
-      gput1(dst + o, ',');
+      put1(dst.at(o), ',');
       o++;
     }
     if (len != ~0u) {
-      gcopy_s(dst + o, smem_addr(ms->rslot[src]), len);
+      copy_s(dst.at(o), smem_addr(ms->rslot[src]), len);
       o += len;
     } else {  // key too long for a slot: escape it cooperatively
       const uint8_t* pj = (const uint8_t*)__shfl_sync(FULL, (unsigned long long)m.kp, src);
       uint32_t lj = __shfl_sync(FULL, m.kl, src);
       int32_t cj = __shfl_sync(FULL, m.cnt, src);
-      gput1(dst + o, '"');
+      put1(dst.at(o), '"');
       o++;
-      o += esc_to_global(dst + o, pj, lj);
-      gput2(dst + o, '"', ':');
+      o += esc_to(dst.at(o), pj, lj);
+      put2(dst.at(o), '"', ':');
       o += 2;
       uint32_t dl = 0;
       __syncwarp();
       if (l == 0) dl = (uint32_t)render_i64(ms->num[0], cj);
       __syncwarp();
       dl = __shfl_sync(FULL, dl, 0);
-      gcopy_s(dst + o, smem_addr(ms->num[0]), dl);
+      copy_s(dst.at(o), smem_addr(ms->num[0]), dl);
       o += dl;
       __syncwarp();
     }
   }
-  gput1(dst + o, '}');
+  put1(dst.at(o), '}');
   return o + 1;
+}
+DEVI uint32_t emit_reaction_map(uint8_t* dst, MapScratch* ms, const tgi_reaction* reacts, uint32_t r0, uint32_t r1, const uint8_t* aux) {
+  return emit_reaction_map_to(DstG{dst}, ms, reacts, r0, r1, aux);
 }
 
 // ---- []model.Comment --------------------------------------------------------------------------------
@@ -252,15 +257,16 @@ __device__ __noinline__ uint32_t size_tg_comments(const TgBatchDev& b, uint32_t 
   return tot;
 }
 
-__device__ __noinline__ uint32_t emit_tg_comments(uint8_t* dst, MapScratch* ms, const TgBatchDev& b, uint32_t c0, uint32_t c1) {
+template <class D>
+__device__ __noinline__ uint32_t emit_tg_comments_to(D dst, MapScratch* ms, const TgBatchDev& b, uint32_t c0, uint32_t c1) {
   int l = lane_id();
   uint32_t o = 0;
-  gput1(dst, '[');
+  put1(dst, '[');
   o++;
-#define CM_LIT(x)                                    \
-  do {                                               \
-    gcopy_g(dst + o, (const uint8_t*)(x), sizeof(x) - 1); \
-    o += sizeof(x) - 1;                              \
+#define CM_LIT(x)                                           \
+  do {                                                      \
+    copy_g(dst.at(o), (const uint8_t*)(x), sizeof(x) - 1);  \
+    o += sizeof(x) - 1;                                     \
   } while (0)
   for (uint32_t k = c0; k < c1; k++) {
     tgi_comment cm = b.comments[k];
@@ -270,51 +276,56 @@ __device__ __noinline__ uint32_t emit_tg_comments(uint8_t* dst, MapScratch* ms, 
     __syncwarp();
     uint32_t d0 = __shfl_sync(FULL, dl, 0), d1 = __shfl_sync(FULL, dl, 1);
     if (k > c0) {
-      gput1(dst + o, ',');
+      put1(dst.at(o), ',');
       o++;
     }
     CM_LIT(kCm0);
-    o += esc_to_global(dst + o, b.aux + cm.text_off, cm.text_len);
+    o += esc_to(dst.at(o), b.aux + cm.text_off, cm.text_len);
     CM_LIT(kCm1);
     // the two counts must leave the scratch before a long-key map entry reuses it
     const uint32_t n0 = l < 12 ? ms->num[0][l] : 0u, n1 = l < 12 ? ms->num[1][l] : 0u;
     __syncwarp();
-    if (cm.flags & 1) o += emit_reaction_map(dst + o, ms, b.reacts, cm.react_start, cm.react_start + cm.react_count, b.aux);
+    if (cm.flags & 1) o += emit_reaction_map_to(dst.at(o), ms, b.reacts, cm.react_start, cm.react_start + cm.react_count, b.aux);
     else CM_LIT(kNullLit);
     CM_LIT(kCm2);
-    if ((uint32_t)l < d0) dst[o + l] = (uint8_t)n0;
+    if ((uint32_t)l < d0) dst.st(o + l, n0);
     o += d0;
     CM_LIT(kCm3);
-    if ((uint32_t)l < d1) dst[o + l] = (uint8_t)n1;
+    if ((uint32_t)l < d1) dst.st(o + l, n1);
     o += d1;
     CM_LIT(kCm4);
-    o += esc_to_global(dst + o, b.aux + cm.handle_off, cm.handle_len);
+    o += esc_to(dst.at(o), b.aux + cm.handle_off, cm.handle_len);
     CM_LIT(kCm5);
     __syncwarp();
   }
 #undef CM_LIT
-  gput1(dst + o, ']');
+  put1(dst.at(o), ']');
   return o + 1;
 }
+DEVI uint32_t emit_tg_comments(uint8_t* dst, MapScratch* ms, const TgBatchDev& b, uint32_t c0, uint32_t c1) {
+  return emit_tg_comments_to(DstG{dst}, ms, b, c0, c1);
+}
 
-DEVI uint32_t emit_tg_outlinks(uint8_t* dst, const tgi_link* links, uint32_t n) {
+template <class D>
+DEVI uint32_t emit_tg_outlinks_to(D dst, const tgi_link* links, uint32_t n) {
   uint32_t o = 0;
   for (uint32_t k = 0; k < n; k++) {
     uint32_t len = links[k].len;
     if (k) {
-      gput2(dst + o, ',', '"');
+      put2(dst.at(o), ',', '"');
       o += 2;
     } else {
-      gput1(dst + o, '"');
+      put1(dst.at(o), '"');
       o += 1;
     }
-    gcopy_g(dst + o, links[k].name, len);  // [a-z0-9_] only: no escaping needed
+    copy_g(dst.at(o), links[k].name, len);  // [a-z0-9_] only: no escaping needed
     o += len;
-    gput1(dst + o, '"');
+    put1(dst.at(o), '"');
     o += 1;
   }
   return o;
 }
+DEVI uint32_t emit_tg_outlinks(uint8_t* dst, const tgi_link* links, uint32_t n) { return emit_tg_outlinks_to(DstG{dst}, links, n); }
 DEVI uint32_t size_tg_outlinks(const tgi_link* links, uint32_t n) {
   if (!n) return 0;
   uint32_t s = 0;

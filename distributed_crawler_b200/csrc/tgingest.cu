@@ -103,7 +103,7 @@ struct Slot {
       d_chans, d_chan_strs;
   // device intermediates / outputs
   DevBuf d_chan_derived, d_chan_len, d_chan_off, d_chan_blob, d_status, d_linelen, d_line_off,
-      d_link_start, d_link_count, d_xlen, d_xpos, d_arena, d_lstate, d_rec_new, d_new_off, d_link_off, d_links_out,
+      d_link_start, d_link_count, d_xlen, d_arena, d_lstate, d_rec_new, d_new_off, d_link_off, d_links_out,
       d_link_off32, d_btable, d_tiles, d_scalars, d_jsonl, d_url_start, d_url_count, d_urls, d_ent_range;
   // pinned host outputs
   HostBuf h_status, h_line_off, h_jsonl, h_link_off, h_links, h_scalars;
@@ -378,7 +378,7 @@ int upload_tg(tgi_ctx* c, Slot& s, const tgi_tg_batch* in) {
 
 // scalars block (device + pinned mirror): [0] chan total, [1] line total, [2] cursor(u32)+err(int),
 // [3] n_new, [4] frontier size, [5] link total
-enum { SC_CHAN_TOTAL = 0, SC_LINE_TOTAL = 1, SC_CURSOR = 2, SC_NEW = 3, SC_FSIZE = 4, SC_LINK_TOTAL = 5, SC_LONG = 6, SC_URL_CURSOR = 7, SC_LANE_OUT = 8, SC_LANE_IN = 9, SC_COUNT = 10 };
+enum { SC_CHAN_TOTAL = 0, SC_LINE_TOTAL = 1, SC_CURSOR = 2, SC_NEW = 3, SC_FSIZE = 4, SC_LINK_TOTAL = 5, SC_LONG = 6, SC_URL_CURSOR = 7, SC_LANE_OUT = 8, SC_LANE_IN = 9, SC_SLOW = 10, SC_COUNT = 12 };
 
 // shared tail of the Telegram and YouTube pipelines: frontier phases, link compaction, D2H, result
 int finish_batch(tgi_ctx* c, Slot& s, uint64_t n, uint32_t flags, uint64_t line_total, uint32_t arena_used,
@@ -528,7 +528,6 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   CK(s.d_link_start.ensure(n * 4));
   CK(s.d_link_count.ensure(n * 4));
   CK(s.d_xlen.ensure(n * 32));
-  CK(s.d_xpos.ensure(n * 32));
   uint64_t arena_cap = s.n_ents + n / 2 + 1024;
   if (s.d_arena.cap / sizeof(tgi_link) > arena_cap + 8) arena_cap = (s.d_arena.cap - PAD) / sizeof(tgi_link);
 
@@ -557,6 +556,7 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     po.link_count = s.d_link_count.as<uint32_t>();
     po.xlen = s.d_xlen.as<uint32_t>();
     po.var_total = (unsigned long long*)(dsc + SC_LONG);
+    po.slow_total = (unsigned long long*)(dsc + SC_SLOW);
     po.arena = s.d_arena.as<tgi_link>();
     po.arena_cap = (uint32_t)arena_cap;
     po.cursor = (uint32_t*)(dsc + SC_CURSOR);
@@ -576,14 +576,9 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       }
       launches += 3;
       if (want_json) {
-        static const bool warp_size = getenv("TGI_SIZE_WARP") != nullptr;  // A/B switch: one warp per record
-        if (warp_size) {
-          tg_size_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, po);
-        } else {
-          const uint64_t groups = (n + 31) / 32;
-          unsigned gs = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
-          tg_size_lane_kernel<<<gs, CTA_THREADS, 0, st>>>(b, cfg, po);
-        }
+        const uint64_t groups = (n + 31) / 32;
+        unsigned gs = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
+        tg_size_lane_kernel<<<gs, CTA_THREADS, 0, st>>>(b, cfg, po);
         launches++;
       }
       CK(cudaEventRecord(s.ev_p1, st));
@@ -631,36 +626,29 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       ei.link_start = s.d_link_start.as<uint32_t>();
       ei.link_count = s.d_link_count.as<uint32_t>();
       ei.xlen = s.d_xlen.as<uint32_t>();
-      ei.xpos = s.d_xpos.as<uint32_t>();
       ei.arena = s.d_arena.as<tgi_link>();
       ei.out = s.d_jsonl.as<uint8_t>();
       ei.err = (int*)(dsc + SC_CURSOR) + 1;
       ei.counters = (unsigned long long*)(dsc + SC_LANE_OUT);
-      uint64_t want = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-      unsigned ge = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms * 8);
+      static const bool attr_set = [] {
+        return cudaFuncSetAttribute(tg_emit_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess &&
+               cudaFuncSetAttribute(tg_emit_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SlowShared)) == cudaSuccess;
+      }();
+      if (!attr_set) { set_err(c, "cannot reserve %zu bytes of shared memory for the tile emitter", sizeof(TileShared)); return TGI_E_CUDA; }
+      const uint64_t groups = (n + 31) / 32;
+      const uint64_t ctas = (groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
       CK(cudaEventRecord(s.ev_e0, st));
-      static const bool warp_fixed = getenv("TGI_EMIT_FIXED_WARP") != nullptr;  // A/B switch: the warp-per-record walker
-      ei.lane_text_max = warp_fixed ? 0xffffffffu : LANE_TEXT_MAX;
-      if (warp_fixed) {
-        tg_emit_fixed_kernel<<<ge, CTA_THREADS, 0, st>>>(b, cfg, ei);
-      } else {
-        const uint64_t groups = (n + 31) / 32;
-        unsigned gl = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 3);
-        static const bool attr_set = [] {
-          return cudaFuncSetAttribute(tg_emit_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LaneShared)) == cudaSuccess;
-        }();
-        if (!attr_set) { set_err(c, "cannot reserve %zu bytes of shared memory for the lane emitter", sizeof(LaneShared)); return TGI_E_CUDA; }
-        tg_emit_lane_kernel<<<gl, CTA_THREADS, sizeof(LaneShared), st>>>(b, cfg, ei);
-      }
+      // one CTA per SM slot (3 resident CTAs per SM by shared memory), persistent over the record groups
+      unsigned gt = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * 3);
+      tg_emit_tile_kernel<<<gt, CTA_THREADS, sizeof(TileShared), st>>>(b, cfg, ei);
       CK(cudaEventRecord(s.ev_f1, st));
-      {
-        const uint64_t groups = (n + 31) / 32;
-        unsigned gg = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
-        tg_emit_esc_kernel<<<gg, CTA_THREADS, 0, st>>>(b, ei);
-        tg_emit_maps_kernel<<<gg, CTA_THREADS, 0, st>>>(b, ei);
+      launches++;
+      if (hsc[SC_SLOW]) {  // lines longer than a tile buffer (counted by the size pass)
+        unsigned gsl = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * 2);
+        tg_emit_slow_kernel<<<gsl, CTA_THREADS, sizeof(SlowShared), st>>>(b, cfg, ei);
+        launches++;
       }
       CK(cudaEventRecord(s.ev_e1, st));
-      launches += 3;
     }
     CK(cudaGetLastError());
   }
@@ -1036,7 +1024,7 @@ void tgi_destroy(tgi_ctx* c) {
     DevBuf* db[] = {&s.d_recs, &s.d_strs, &s.d_ent_off, &s.d_ents, &s.d_react_off, &s.d_reacts, &s.d_comment_off,
                     &s.d_comments, &s.d_aux, &s.d_chans, &s.d_chan_strs, &s.d_chan_derived, &s.d_chan_len,
                     &s.d_chan_off, &s.d_chan_blob, &s.d_status, &s.d_linelen, &s.d_line_off, &s.d_link_start,
-                    &s.d_link_count, &s.d_xlen, &s.d_xpos, &s.d_arena, &s.d_lstate, &s.d_rec_new, &s.d_new_off, &s.d_link_off,
+                    &s.d_link_count, &s.d_xlen, &s.d_arena, &s.d_lstate, &s.d_rec_new, &s.d_new_off, &s.d_link_off,
                     &s.d_links_out, &s.d_link_off32, &s.d_btable, &s.d_tiles, &s.d_scalars, &s.d_jsonl,
                     &s.d_url_start, &s.d_url_count, &s.d_urls, &s.d_ent_range};
     for (DevBuf* d : db) d->release();
