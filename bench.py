@@ -161,6 +161,22 @@ def bind_numa(local_rank: int):
     return None
 
 
+def host_cpus() -> tuple[int, str]:
+    """CPUs this process may really use: the cgroup CPU quota (cpu.max) caps what os.cpu_count() advertises —
+    more runnable threads than the quota only get throttled."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    why = f"{n} schedulable CPUs"
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            q = max(1, int(int(quota) / int(period)))
+            if q < n:
+                n, why = q, f"cgroup cpu.max {quota}/{period} = {q} CPUs (of {len(os.sched_getaffinity(0))} visible)"
+    except (OSError, ValueError):
+        pass
+    return n, why
+
+
 def make_corpus(cfg, n, first, threads):
     from distributed_crawler_b200.corpus import Corpus, YtCorpus
     if cfg["kind"] == "yt":
@@ -204,7 +220,7 @@ def run_reference(args, cfg, rank):
         return
     from oracle import pyoracle
     from oracle.pyoracle import Oracle
-    cores = os.cpu_count() or 1
+    cores, cores_why = host_cpus()
     n = min(cfg["ref_n"], cfg["n"])
     c = make_corpus(cfg, n, 0, min(cores, 64))
     flags = cfg["flags"] | ORC_RUN_SLICES | ORC_RUN_PIN
@@ -238,6 +254,7 @@ def run_reference(args, cfg, rank):
                        "same_corpus_as_gpu_arm": same},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "one_thread": v1, "per_thread_efficiency": (v / cores / v1) if v1 else None,
+                             "cores_basis": cores_why,
                              "sample": f"{n} records x {args.steps} steps, C restatement of the Go path, {cores} threads pinned one per core, "
                                        "each worker keeps its own output (no global concatenation, like the reference's per-channel files), "
                                        "sharded frontier insert"},
@@ -292,8 +309,8 @@ def main():
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
 
-    cores = os.cpu_count() or 1
-    gen_threads = max(1, min(cores // max(world, 1), 64))
+    cores, cores_why = host_cpus()
+    gen_threads = max(1, min((os.cpu_count() or 1) // max(world, 1), 64))
     is_yt = cfg["kind"] == "yt"
     RUN = cfg["flags"]
     want_json = bool(RUN & J)
@@ -481,7 +498,7 @@ def main():
             sample_n = min(cfg["cpu_n"], corpora[0].batch.n)
             sample = corpora[0].batch.slice(0, sample_n) if hasattr(corpora[0].batch, "slice") else make_corpus(cfg, sample_n, first, gen_threads).batch
             cpu_v, cpu_dt, cpu_v1 = cpu_baseline(cfg, sample, cores)
-            cpu = {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "one_thread": cpu_v1,
+            cpu = {"value": cpu_v, "unit": UNIT, "cores": cores, "cores_basis": cores_why, "kind": "port", "one_thread": cpu_v1,
                    "per_thread_efficiency": (cpu_v / cores / cpu_v1) if cpu_v1 else None,
                    "sample": f"first {sample_n} records of the same corpus, {cpu_dt:.1f} s, C restatement of the Go path (oracle), same run flags, "
                              f"{cores} threads pinned one per core, warm"}

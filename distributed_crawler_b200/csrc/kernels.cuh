@@ -12,6 +12,7 @@
 // yt_size_kernel is the warp-per-record predecessor of the YouTube lane sizer, kept as an A/B reference (TGI_YT_WARP).
 #pragma once
 #include "tg_walk.cuh"
+#include "tg_scan.cuh"
 #include "tg_tile.cuh"
 #include "yt_walk.cuh"
 #include "gm_walk.cuh"
@@ -114,6 +115,7 @@ DEVI void parse_one_record(const TgBatchDev& b, const CfgDev& cfg, const ParseOu
         ls.out = o.arena + lstart;
         ls.cap = ub;
         ls.count = 0;
+        ls.name_bytes = 0;
         ls.self = b.chan_strs + ch->str_off + ch->title_len;
         ls.self_len = ch->name_len;
         bool ok = warp_extract_links(v, b.ents, b.aux, o.ent_range, ls);
@@ -134,33 +136,9 @@ DEVI void parse_one_record(const TgBatchDev& b, const CfgDev& cfg, const ParseOu
 }
 
 // The parse step is split by instruction footprint (the B200 instruction caches are 6 KB L0 / 32 KB L1.5):
-// tg_parse_kernel = status + links of the records WITHOUT entities (three quarters of the corpus; small code),
-// tg_ent_map_kernel = UTF-16 entity offsets -> byte ranges, tg_parse_ent_kernel = links of the records with
-// entities (lanes pick them out of groups of 32),
-// tg_size_lane_kernel = line lengths.  With everything in one parse kernel (2 560 SASS instructions) ncu
-// showed 3.5 stall_no_instruction cycles per issue.
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) {
-  int wid = threadIdx.x >> 5;
-  uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
-  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
-    // The chain header -> string offset -> text is two DRAM round trips per record and this kernel has little else to
-    // do (long_scoreboard 9 cycles per issue): read the NEXT record's header now, touch its text at the bottom of
-    // the loop, when that load has long completed.
-    const uint64_t rn = r + nwarps;
-    unsigned long long nx_off = 0;
-    uint32_t nx_len = 0;
-    if (rn < b.n) {
-      asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(nx_off) : "l"(&b.recs[rn].str_off));
-      asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(nx_len) : "l"(&b.recs[rn].text_len));
-    }
-    if (b.ent_off[r + 1] == b.ent_off[r])  // the others: tg_parse_ent_kernel
-      parse_one_record<false>(b, cfg, o, r, load_rec_view(b, r));
-    if (rn < b.n) {
-      const uint32_t off = (uint32_t)lane_id() * 128u;
-      if (off < nx_len + 127u && off < 2048u) asm volatile("prefetch.global.L1 [%0];" ::"l"(b.strs + nx_off + off));
-    }
-  }
-}
+//   tg_ent_map_kernel   = UTF-16 entity offsets -> byte ranges            } records WITH entities (a quarter of the
+//   tg_parse_ent_kernel = status + links of those records                  } corpus; lanes pick them out of groups of 32)
+//   tg_scan_kernel      = everything else in ONE pass over the text (below)
 __global__ void __launch_bounds__(CTA_THREADS, 4) tg_ent_map_kernel(TgBatchDev b, ParseOut o) {
   const int wid = threadIdx.x >> 5, l = lane_id();
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
@@ -188,36 +166,54 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_ent_kernel(TgBatchDev
   }
 }
 
-// The same sizes, 32 records per warp: every lane sizes the small pieces of its own record (numbers,
-// handle / media strings, comments, reactions, outlinks); only the message text, the one long string,
-// is measured by the whole warp, record after record; the rare complicated pieces (a comment list, a
-// reactions map that is not "simple") go through the warp-wide routines as well.
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_lane_kernel(TgBatchDev b, CfgDev cfg, ParseOut o) {
+// tg_scan_kernel — status, plaintext links and line length, 32 records per warp.
+// Every lane handles the scalar part of its own record (status, numbers, small strings, reaction maps, outlinks);
+// the message text, the one long string, is scanned by the whole warp, record after record, ONCE: the same 512-byte
+// strips give the JSON-escaped length, the UTF-8 verdict and the "t.me/" candidates (tg_scan.cuh).  Records with
+// entities got their status and links from tg_parse_ent_kernel (it runs first); here they only get their sizes.
+// JSON == false (link extraction + dedup only, BASELINE configs 3 / 5): no sizes at all.
+template <bool JSON>
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_scan_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) {
   const int wid = threadIdx.x >> 5, l = lane_id();
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   uint64_t var_sum = 0;
   uint32_t nslow = 0;
   for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
     uint64_t r = g * 32 + l;
-    bool active = r < b.n;
-    if (!active) r = b.n - 1;
-    active = active && o.status[r] == TGI_ST_EMITTED;
-    if (!__any_sync(FULL, active)) continue;
+    const bool inb = r < b.n;
+    if (!inb) r = b.n - 1;
     TgWalkArgs a;
     a.b = &b;
     a.cfg = &cfg;
     a.r = r;
     a.v = load_rec_view(b, r);
-    a.links = o.arena + o.link_start[r];
-    a.n_links = active ? o.link_count[r] : 0u;
     const tgi_tg_rec* rec = a.v.rec;
-    const ChanDerived cd = b.chan_derived[rec->chan_idx];
-    const TgDerived d = tg_derive(a, cd);
+    const bool has_ent = a.v.e1 != a.v.e0;
+    uint32_t status = TGI_ST_EMITTED, nlinks = 0, lstart = 0, link_bytes = 0;
+    if (has_ent) {  // tg_parse_ent_kernel's verdict
+      status = o.status[r];
+      nlinks = o.link_count[r];
+      lstart = o.link_start[r];
+    } else if ((cfg.flags & TGI_CFG_HAS_MIN_POST_DATE) && (int64_t)rec->date < cfg.min_post_date) {
+      status = TGI_ST_SKIPPED;  // tdutils.go:419-421
+    } else if (a.v.flags & TGI_RF_PANIC) {
+      status = TGI_ST_FAILED;
+    }
+    const bool live = inb && status == TGI_ST_EMITTED;
+    const uint32_t r0 = b.react_off[r], nr = b.react_off[r + 1] - r0;
+    if (live && nr > 32) atomicOr(o.err, ERR_TOO_MANY_REACTIONS);
+    // ---- the lane's own part of the line length ----
+    ChanDerived cd{};
+    TgDerived d{};
     uint32_t xl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t tot = 0;
     bool warp_comments = false, warp_map = false;
-    const uint32_t r0 = b.react_off[r], nr = b.react_off[r + 1] - r0;
-    if (active && !(cfg.flags & CFGDEV_CLOCK_INVALID)) {
+    const bool sized = JSON && live && !(cfg.flags & CFGDEV_CLOCK_INVALID);
+    if (JSON) {
+      cd = b.chan_derived[rec->chan_idx];
+      d = tg_derive(a, cd);
+    }
+    if (sized) {
       uint32_t L[8] = {ndigits_i64(rec->id / 1048576), ndigits_i64(rec->chat_id), ndigits_i64(rec->view_count),
                        ndigits_i64(rec->share_count), ndigits_i64(d.ncomments), cfg.tz == 0 ? 22u : 27u, 0, 0};
       uint32_t chan[4] = {cd.user_len, cd.name_len, cd.title_len, cd.cdata_len};
@@ -234,7 +230,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_lane_kernel(TgBatchDev
         xl[XL_REACTIONS] = 2;
         xl[XL_FLAGS] = XLF_SIMPLE_MAP;
       } else if (nr <= LANE_MAP_MAX) {  // size_reaction_map, one lane: "key":n , ... ; simple = short clean keys
-        uint32_t sz = 2u, live = 0;
+        uint32_t sz = 2u, live_keys = 0;
         bool simple = true;
         for (uint32_t j = 0; j < nr; j++) {
           const tgi_reaction rc = b.reacts[r0 + j];
@@ -248,11 +244,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_lane_kernel(TgBatchDev
           }
           if (last) {
             sz += 3u + el + ndigits_i64(rc.count);
-            live++;
+            live_keys++;
           }
         }
         if (simple) {
-          xl[XL_REACTIONS] = sz + (live - 1u);
+          xl[XL_REACTIONS] = sz + (live_keys - 1u);
           xl[XL_FLAGS] = XLF_SIMPLE_MAP;
         } else {
           warp_map = true;
@@ -260,62 +256,124 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_lane_kernel(TgBatchDev
       } else {
         warp_map = true;
       }
-      if (a.n_links) {
-        uint32_t s = a.n_links - 1u;
-        for (uint32_t k = 0; k < a.n_links; k++) s += a.links[k].len + 2u;
-        xl[XL_OUTLINKS] = s;
+    }
+    // ---- the text, all lanes, one record at a time ----
+    const bool carrier = ct_carries_links(a.v.ct) && (a.v.flags & TGI_RF_HAS_TEXT);
+    const bool link_scan = live && !has_ent && carrier && a.v.text_len != 0;  // plaintext "t.me/" links
+    const bool want_esc = sized && d.desc_len != 0;
+    const bool esc_on_text = want_esc && d.desc == a.v.text;
+    // item = (string, what to compute): the description, plus the link scan when the description IS the text; texts that
+    // carry links but are not the description (document / audio / voice captions, or no JSONL at all) come second
+    uint32_t todo = __ballot_sync(FULL, want_esc || link_scan);
+    uint32_t second = __ballot_sync(FULL, link_scan && want_esc && !esc_on_text);
+    while (todo | second) {
+      const bool pass2 = todo == 0;
+      const int src = __ffs(pass2 ? second : todo) - 1;
+      if (pass2) second &= second - 1;
+      else todo &= todo - 1;
+      const bool it_esc = !pass2 && __shfl_sync(FULL, (int)want_esc, src);
+      const bool it_tme = __shfl_sync(FULL, (int)(link_scan && (pass2 || !want_esc || esc_on_text)), src);
+      const uint8_t* text = (const uint8_t*)__shfl_sync(FULL, (unsigned long long)(uintptr_t)a.v.text, src);
+      const uint32_t text_n = __shfl_sync(FULL, a.v.text_len, src);
+      const uint8_t* p = it_esc ? (const uint8_t*)__shfl_sync(FULL, (unsigned long long)(uintptr_t)d.desc, src) : text;
+      const uint32_t n = it_esc ? __shfl_sync(FULL, d.desc_len, src) : text_n;
+      TextScan ts;
+      if (it_esc && it_tme) ts = warp_text_scan<true, true>(p, n);
+      else if (it_esc) ts = warp_text_scan<true, false>(p, n);
+      else ts = warp_text_scan<false, true>(p, n);
+      if (it_esc) {
+        uint32_t e = ts.esc;
+        bool ex = false;
+        if (ts.exact) e = warp_esc_len(p, n, &ex);  // the exact path decides (and may still find the string harmless)
+        if (l == src) {
+          xl[XL_DESC] = e;
+          if (ex) xl[XL_FLAGS] |= XLF_DESC_EXACT;
+        }
+      }
+      if (it_tme && ts.tme) {
+        uint32_t ub = ts.tme, ls0 = 0;
+        if (ub >= (1u << 20)) {  // seq packing of the frontier needs ordinal < 2^20 (SEQ_ORD_BITS)
+          if (l == 0) atomicOr(o.err, ERR_TOO_MANY_LINKS);
+          ub = 0;
+        }
+        if (ub) {
+          if (l == 0) ls0 = atomicAdd(o.cursor, ub);
+          ls0 = __shfl_sync(FULL, ls0, 0);
+          if (ls0 + ub > o.arena_cap || ls0 + ub < ls0) {
+            if (l == 0) atomicOr(o.err, ERR_ARENA_OVERFLOW);
+          } else {
+            const uint32_t ci = __shfl_sync(FULL, rec->chan_idx, src);
+            const tgi_tg_chan* ch = &b.chans[ci];
+            LinkSink ls;
+            ls.out = o.arena + ls0;
+            ls.cap = ub;
+            ls.count = 0;
+            ls.name_bytes = 0;
+            ls.self = b.chan_strs + ch->str_off + ch->title_len;
+            ls.self_len = ch->name_len;
+            warp_scan_channel_links(ls, text, text_n, TGI_SRC_PLAINTEXT, true);
+            if (l == src) {
+              lstart = ls0;
+              nlinks = ls.count;
+              link_bytes = ls.name_bytes;
+            }
+          }
+        }
       }
     }
-    // the message text (or the other description sources), one record at a time, all lanes
-    const bool sized = active && !(cfg.flags & CFGDEV_CLOCK_INVALID);
-    uint32_t todo = __ballot_sync(FULL, sized && d.desc_len != 0);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const uint8_t* p = (const uint8_t*)__shfl_sync(FULL, (unsigned long long)(uintptr_t)d.desc, src);
-      const uint32_t n = __shfl_sync(FULL, d.desc_len, src);
-      bool ex = false;
-      const uint32_t e = warp_esc_len(p, n, &ex);
-      if (l == src) {
-        xl[XL_DESC] = e;
-        if (ex) xl[XL_FLAGS] |= XLF_DESC_EXACT;
+    if (JSON) {
+      uint32_t t2 = __ballot_sync(FULL, warp_comments);
+      while (t2) {
+        const int src = __ffs(t2) - 1;
+        t2 &= t2 - 1;
+        const uint32_t e = size_tg_comments(b, __shfl_sync(FULL, d.c0, src), __shfl_sync(FULL, d.c1, src));
+        if (l == src) xl[XL_COMMENTS] = e;
+      }
+      t2 = __ballot_sync(FULL, warp_map);
+      while (t2) {
+        const int src = __ffs(t2) - 1;
+        t2 &= t2 - 1;
+        const uint32_t q0 = __shfl_sync(FULL, r0, src), qn = __shfl_sync(FULL, nr, src);
+        uint32_t simple = 0;
+        const uint32_t e = size_reaction_map(b.reacts, q0, q0 + qn, b.aux, &simple);
+        if (l == src) {
+          xl[XL_REACTIONS] = e;
+          xl[XL_FLAGS] = (xl[XL_FLAGS] & ~XLF_SIMPLE_MAP) | (simple ? XLF_SIMPLE_MAP : 0u);
+        }
       }
     }
-    todo = __ballot_sync(FULL, warp_comments);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const uint32_t e = size_tg_comments(b, __shfl_sync(FULL, d.c0, src), __shfl_sync(FULL, d.c1, src));
-      if (l == src) xl[XL_COMMENTS] = e;
+    if (!inb) continue;
+    if (!has_ent) {
+      o.status[r] = (uint8_t)status;
+      o.link_start[r] = lstart;
+      o.link_count[r] = nlinks;
     }
-    todo = __ballot_sync(FULL, warp_map);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const uint32_t q0 = __shfl_sync(FULL, r0, src), qn = __shfl_sync(FULL, nr, src);
-      uint32_t simple = 0;
-      const uint32_t e = size_reaction_map(b.reacts, q0, q0 + qn, b.aux, &simple);
-      if (l == src) {
-        xl[XL_REACTIONS] = e;
-        xl[XL_FLAGS] = (xl[XL_FLAGS] & ~XLF_SIMPLE_MAP) | (simple ? XLF_SIMPLE_MAP : 0u);
+    if (!JSON) {
+      o.linelen[r] = 0;
+      continue;
+    }
+    if (sized && nlinks) {  // "name","name": the names are [a-z0-9_]
+      if (has_ent) {
+        link_bytes = 0;
+        const tgi_link* lk = o.arena + lstart;
+        for (uint32_t k = 0; k < nlinks; k++) link_bytes += lk[k].len;
       }
+      xl[XL_OUTLINKS] = link_bytes + 3u * nlinks - 1u;
     }
-    if (active) {
-      uint32_t var = 0;
+    uint32_t var = 0;
 #pragma unroll
-      for (int j = 0; j < XL_COUNT; j++) var += xl[j];
-      const uint32_t llen = sized ? tot + var : 0u;
-      // lines that do not fit a tile buffer (with the map scratch behind them, if they need it) take tg_emit_slow_kernel
-      if (llen + (tg_needs_scratch(nr, d.comments_nil, d.c0, d.c1) ? TILE_SCRATCH : 0u) > TILE_BUF - 16u) {
-        xl[XL_FLAGS] |= XLF_SLOW;
-        nslow++;
-      }
-      *(uint4*)(o.xlen + r * 8) = make_uint4(xl[0], xl[1], xl[2], xl[3]);
-      *(uint4*)(o.xlen + r * 8 + 4) = make_uint4(xl[4], xl[5], xl[6], xl[7]);
-      if (llen == 0) o.status[r] = TGI_ST_NOLINE;
-      o.linelen[r] = llen;
-      if (llen) var_sum += var;
+    for (int j = 0; j < XL_COUNT; j++) var += xl[j];
+    const uint32_t llen = sized ? tot + var : 0u;
+    // lines that do not fit a tile buffer (with the map scratch behind them, if they need it) take tg_emit_slow_kernel
+    if (llen + (tg_needs_scratch(nr, d.comments_nil, d.c0, d.c1) ? TILE_SCRATCH : 0u) > TILE_BUF - 16u) {
+      xl[XL_FLAGS] |= XLF_SLOW;
+      nslow++;
     }
+    *(uint4*)(o.xlen + r * 8) = make_uint4(xl[0], xl[1], xl[2], xl[3]);
+    *(uint4*)(o.xlen + r * 8 + 4) = make_uint4(xl[4], xl[5], xl[6], xl[7]);
+    if (live && llen == 0) o.status[r] = TGI_ST_NOLINE;
+    o.linelen[r] = llen;
+    if (llen) var_sum += var;
   }
   for (int dd = 16; dd; dd >>= 1) var_sum += __shfl_down_sync(FULL, var_sum, dd);
   if (l == 0 && var_sum) atomicAdd(o.var_total, (unsigned long long)var_sum);
@@ -336,8 +394,10 @@ struct EmitIn {
   unsigned long long* counters;  // [0] JSONL bytes written by the tile kernel, [1] source bytes it read from HBM
 };
 
-// Tile emitter (tg_tile.cuh): one warp per 32 consecutive records, 16 prepared at a time.
-__global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_tile_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
+// Tile emitter (tg_tile.cuh): one warp per 32 consecutive records, 16 prepared at a time.  MINB = resident CTAs per SM
+// the register allocation is tuned for (3: 80 registers, some spills; 2: no spills, fewer warps) — TGI_TILE_CTAS.
+template <int MINB>
+__global__ void __launch_bounds__(CTA_THREADS, MINB) tg_emit_tile_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
   extern __shared__ __align__(128) uint8_t tile_smem[];
   TileShared& sh = *(TileShared*)tile_smem;
   static_assert(TILE_WARPS == WARPS_PER_CTA, "one buffer per warp");
@@ -350,11 +410,20 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_tile_kernel(TgBatchDev
     const int ct = i >> 3, w = i & 7;
     sh.ptype[i] = w < 7 ? ((const uint32_t*)kPostType[ct])[w] : 0u;
   }
+  // the context strings (label, created_at, capture_time) are the same for every record of the batch
+  const uint32_t cfg_bytes = cfg.off[3] + pad16(cfg.capture_len);
+  const bool cfg_cached = cfg_bytes <= TILE_CFG_CACHE;
+  if (cfg_cached)
+    for (uint32_t i = threadIdx.x; i < cfg_bytes; i += blockDim.x) sh.cfgc[i] = cfg.blob[i];
   __syncthreads();
   const int wid = threadIdx.x >> 5, l = lane_id();
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   TileStream t;
   t.buf_s = smem_addr(sh.buf[wid]);
+  TileWarp tw;
+  tw.chan_idx = 0xffffffffu;
+  tw.chan_cached = false;
+  tw.cfg_cached = cfg_cached;
   TileIn ti;
   ti.xlen = in.xlen;
   ti.link_start = in.link_start;
@@ -370,10 +439,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_tile_kernel(TgBatchDev
       __syncwarp();
       {  // lane-parallel preparation of up to 16 records
         const uint64_t rr = h + (uint64_t)l;
+        if (l < TILE_GROUP && rr < r1) {  // what the warp will read record by record: into L1 now, all lanes at once
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(in.xlen + rr * 8));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(in.line_off + rr));
+        }
         if (l < TILE_GROUP && rr < r1 && in.status[rr] == TGI_ST_EMITTED && !(in.xlen[rr * 8 + XL_FLAGS] & XLF_SLOW)) {
           const tgi_tg_rec* rec = &b.recs[rr];
           const bool nil = (rec->flags & TGI_RF_COMMENTS_NIL) != 0;
-          tile_prep(sh.rows[wid][l], rec, nil, b.comment_off[rr + 1] - b.comment_off[rr], cfg.tz);
+          tile_prep(sh.rows[wid][l], rec, b.strs, nil, b.comment_off[rr + 1] - b.comment_off[rr], cfg.tz);
         }
       }
       __syncwarp();
@@ -387,7 +460,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_tile_kernel(TgBatchDev
           ts_begin(t, out0 + lo + total);
           continue;
         }
-        tile_emit_record(sh, wid, t, b, cfg, r, smem_addr(sh.rows[wid][j]), total, ti, bytes_in);
+        tile_emit_record(sh, wid, t, tw, b, cfg, r, smem_addr(sh.rows[wid][j]), total, ti, bytes_in);
         bytes_out += total;
       }
     }

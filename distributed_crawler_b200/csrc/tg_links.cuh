@@ -16,6 +16,7 @@ struct LinkSink {
   tgi_link* out;       // arena slots of this record (reserved: `cap` entries)
   uint32_t cap;
   uint32_t count;      // links written so far (warp-uniform)
+  uint32_t name_bytes; // sum of their name lengths (the size pass turns it into the outlinks piece length)
   const uint8_t* self; // channel name of the record (for TGI_LF_SELF)
   uint32_t self_len;
 };
@@ -81,6 +82,7 @@ __device__ __noinline__ void warp_add_link(LinkSink& ls, const uint8_t* p, uint3
   }
   __syncwarp();
   ls.count++;
+  ls.name_bytes += len;
 }
 
 // greedy [a-zA-Z0-9_]{0,32} run length starting at p (bounded by end)

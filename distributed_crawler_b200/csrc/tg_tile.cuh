@@ -26,11 +26,13 @@
 namespace tgi {
 
 constexpr int TILE_WARPS = 8;
-constexpr uint32_t TILE_BUF = 6144;                       // bytes of line buffer per warp
+constexpr uint32_t TILE_BUF = 5888;                       // bytes of line buffer per warp (3 CTAs per SM by shared memory)
 constexpr uint32_t TILE_SCRATCH = (sizeof(MapScratch) + 31u) & ~15u;  // map / comment scratch, placed behind the line
-constexpr uint32_t TILE_LINE_MAX = TILE_BUF - 32;         // longer lines take the slow path (XLF_SLOW)
 constexpr int TILE_GROUP = 16;                            // records prepared at once
 constexpr int TILE_ROW_BYTES = 116;                       // 29 words: the lanes' rows start on distinct banks
+constexpr uint32_t TILE_CHAN_CACHE = 1024;                // the warp's current channel blob (shared by ~100 consecutive records)
+constexpr uint32_t TILE_CFG_CACHE = 256;                  // the context strings (label, created_at, capture_time)
+constexpr int TILE_EARLY = 8;                             // 128-byte string chunks loaded before the shared-memory phases
 // row layout: msgno @0 (16) | chat id @16 (24) | views @40 (12) | shares @52 (12) | comments @64 (12) | time @76 (28) | lengths @104 (8)
 __device__ __constant__ uint8_t kTileFieldOff[8] = {0, 16, 40, 52, 64, 76, 0, 0};
 
@@ -40,6 +42,8 @@ struct TileShared {
   uint32_t pieces[kTgNEnt];
   uint32_t ptype[TGI_CT__COUNT * 8];  // MessageContentType() strings, 32 bytes each, zero padded
   uint32_t vshift[TILE_WARPS][kTgNEnt];  // literal pieces: line offset - template offset (VSHIFT_SKIP: absent); others: line offset
+  __align__(16) uint8_t cfgc[TILE_CFG_CACHE];
+  __align__(16) uint8_t chan[TILE_WARPS][TILE_CHAN_CACHE];
   __align__(4) uint8_t rows[TILE_WARPS][TILE_GROUP][TILE_ROW_BYTES];
   __align__(128) uint8_t buf[TILE_WARPS][TILE_BUF];
 };
@@ -100,8 +104,14 @@ DEVI void ts_flush(TileStream& t, bool end) {
   __syncwarp();
 }
 
-// lane-parallel preparation of one record: the rendered fields of its line
-DEVI void tile_prep(uint8_t* row, const tgi_tg_rec* rec, bool comments_nil, uint32_t ncomments, int32_t tz) {
+// lane-parallel preparation of one record: the rendered fields of its line; its strings are requested from HBM now
+// (L2 prefetch), long before the warp copies them
+DEVI void tile_prep(uint8_t* row, const tgi_tg_rec* rec, const uint8_t* strs, bool comments_nil, uint32_t ncomments, int32_t tz) {
+  {
+    const uint8_t* p = strs + rec->str_off;
+    const uint32_t tot = rec->text_len + rec->alt_len + rec->media_len + rec->handle_len;
+    for (uint32_t o = 0; o < tot + 127u && o < 1024u; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+  }
 #pragma unroll 1
   for (int f = 0; f < 5; f++) {
     const int64_t v = f == 0 ? rec->id / 1048576  // tdutils.go:1008
@@ -121,8 +131,94 @@ struct TileIn {
   int* err;
 };
 
+// n bytes shared -> shared, any alignment (line pieces that come from the warp's caches)
+DEVI void copy_ss(uint32_t dst, uint32_t src, uint32_t n) {
+  for (uint32_t i = lane_id(); i < n; i += 32) sts8(dst + i, lds8(src + i));
+}
+// n bytes global -> shared with eight loads in flight per lane (the plain byte loop pays one memory latency per 32 bytes)
+DEVI void copy_gs_deep(uint32_t dst, const uint8_t* src, uint32_t n) {
+  const uint32_t l = lane_id();
+  for (uint32_t base = 0; base < n; base += 1024) {
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const uint32_t o = base + 128u * k + 4u * l;
+      v[k] = o < n ? ld_u32_unaligned(src + o) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const uint32_t o = base + 128u * k + 4u * l;
+      if (o < n) {
+        sts8(dst + o, v[k]);
+        if (o + 1 < n) sts8(dst + o + 1, v[k] >> 8);
+        if (o + 2 < n) sts8(dst + o + 2, v[k] >> 16);
+        if (o + 3 < n) sts8(dst + o + 3, v[k] >> 24);
+      }
+    }
+  }
+}
+
+// map[string]int that the size pass flagged XLF_SIMPLE_MAP: <= LANE_MAP_MAX entries, distinct keys of 1..8 bytes that
+// need no escaping.  One lane per entry: two loads (entry, key), rank and offset by shuffles, direct byte stores.
+DEVI void tile_emit_simple_map(uint32_t dst, const tgi_reaction* reacts, uint32_t r0, uint32_t nr, const uint8_t* aux) {
+  const uint32_t l = lane_id();
+  uint32_t k0 = 0, k1 = 0, kl = 0, len = 0;
+  int32_t cnt = 0;
+  if (l < nr) {
+    const tgi_reaction rc = reacts[r0 + l];
+    const uint8_t* kp = aux + rc.emoji_off;
+    kl = rc.emoji_len;
+    cnt = rc.count;
+    k0 = ld_u32_unaligned(kp);
+    k1 = kl > 4 ? ld_u32_unaligned(kp + 4) : 0u;
+    if (kl < 4) k0 &= (1u << (8u * kl)) - 1u;
+    if (kl > 4 && kl < 8) k1 &= (1u << (8u * (kl - 4u))) - 1u;
+    len = 4u + kl + ndigits_i64(cnt);  // "key":n and a comma or the closing brace
+  }
+  const uint64_t ck = ((uint64_t)__byte_perm(k0, 0, 0x0123) << 32) | __byte_perm(k1, 0, 0x0123);  // bytewise order
+  uint32_t off = 1, rank = 0;
+  for (uint32_t j = 0; j < nr; j++) {
+    const uint64_t cj = __shfl_sync(FULL, ck, (int)j);
+    const uint32_t lj = __shfl_sync(FULL, len, (int)j);
+    if (cj < ck) {
+      off += lj;
+      rank++;
+    }
+  }
+  if (l == 0) sts8(dst, '{');
+  if (l < nr) {
+    uint32_t d = dst + off;
+    sts8(d, '"');
+    for (uint32_t i = 0; i < kl; i++) sts8(d + 1 + i, (i < 4 ? k0 >> (8u * i) : k1 >> (8u * (i - 4u))));
+    d += 1 + kl;
+    sts8(d, '"');
+    sts8(d + 1, ':');
+    d += 2;
+    uint32_t nd = len - 4u - kl;
+    uint32_t v = cnt < 0 ? (uint32_t)0 - (uint32_t)cnt : (uint32_t)cnt;
+    if (cnt < 0) {
+      sts8(d, '-');
+      d++;
+      nd--;
+    }
+    for (uint32_t i = nd; i-- > 0;) {
+      const uint32_t q = v / 10u;
+      sts8(d + i, '0' + (v - q * 10u));
+      v = q;
+    }
+    sts8(d + nd, rank + 1 == nr ? '}' : ',');
+  }
+}
+
+// per-warp state that survives from record to record
+struct TileWarp {
+  uint32_t chan_idx;   // channel whose blob sits in the warp's cache (0xffffffff: none)
+  bool chan_cached;    // ... and it fitted
+  bool cfg_cached;     // the context strings fitted the CTA's cache
+};
+
 // One record, the whole warp.  The line [t.pos, t.pos + total) is assembled in the buffer; t.pos advances.
-DEVI void tile_emit_record(TileShared& sh, int wid, TileStream& t, const TgBatchDev& b, const CfgDev& cfg, uint64_t r,
+DEVI void tile_emit_record(TileShared& sh, int wid, TileStream& t, TileWarp& tw, const TgBatchDev& b, const CfgDev& cfg, uint64_t r,
                            uint32_t row_s, uint32_t total, const TileIn& in, uint64_t& bytes_in) {
   const int l = lane_id();
   const tgi_tg_rec* rec = &b.recs[r];
@@ -142,13 +238,30 @@ DEVI void tile_emit_record(TileShared& sh, int wid, TileStream& t, const TgBatch
   a.v.ct = rec->content_type;
   a.v.flags = rec->flags;
   a.v.e0 = a.v.e1 = 0;
-  const ChanDerived cd = b.chan_derived[rec->chan_idx];
+  const uint32_t chan_idx = rec->chan_idx;
+  const ChanDerived cd = b.chan_derived[chan_idx];
   const TgDerived d = tg_derive(a, cd);
   const uint32_t condmask = tg_condmask(a, d);
   const uint32_t ct = a.v.ct;
   const uint4 xa = *(const uint4*)(in.xlen + r * 8), xb = *(const uint4*)(in.xlen + r * 8 + 4);
   const uint32_t r0 = b.react_off[r], nr = b.react_off[r + 1] - r0;
   const bool scratch = tg_needs_scratch(nr, d.comments_nil, d.c0, d.c1);
+
+  // ---- 0. the record's clean strings: up to TILE_EARLY 128-byte chunks are requested NOW and stored after the
+  //         shared-memory phases (one memory latency per record instead of one per 32 bytes) ----
+  const bool desc_clean = xa.x != 0 && xa.x == d.desc_len, media_clean = xa.y != 0 && xa.y == a.v.media_len,
+             handle_clean = xa.z != 0 && xa.z == a.v.handle_len;
+  const uint32_t desc_early = desc_clean ? min(d.desc_len, 128u * (TILE_EARLY - 2)) : 0u;
+  const uint32_t media_early = media_clean ? min((uint32_t)a.v.media_len, 128u) : 0u;
+  const uint32_t handle_early = handle_clean ? min((uint32_t)a.v.handle_len, 128u) : 0u;
+  uint32_t ev[TILE_EARLY];
+#pragma unroll
+  for (int k = 0; k < TILE_EARLY - 2; k++) {
+    const uint32_t o = 128u * k + 4u * (uint32_t)l;
+    ev[k] = o < desc_early ? ld_u32_unaligned(d.desc + o) : 0u;
+  }
+  ev[TILE_EARLY - 2] = 4u * (uint32_t)l < media_early ? ld_u32_unaligned(a.v.media + 4 * l) : 0u;
+  ev[TILE_EARLY - 1] = 4u * (uint32_t)l < handle_early ? ld_u32_unaligned(a.v.handle + 4 * l) : 0u;
 
   uint32_t used = (uint32_t)(t.pos - t.gs);
   if (used + total + (scratch ? TILE_SCRATCH : 0u) > TILE_BUF) {
@@ -157,6 +270,23 @@ DEVI void tile_emit_record(TileShared& sh, int wid, TileStream& t, const TgBatch
   }
   const uint32_t line_s = t.buf_s + used;
   MapScratch* ms = (MapScratch*)(sh.buf[wid] + ((used + total + 15u) & ~15u));
+
+  // the channel's pre-rendered strings: kept in shared memory while consecutive records share the channel
+  const uint32_t chan_bytes = pad16(cd.user_len) + pad16(cd.name_len) + pad16(cd.title_len) + pad16(cd.cdata_len);
+  const uint32_t chan_s = smem_addr(sh.chan[wid]);
+  if (tw.chan_idx != chan_idx) {
+    tw.chan_idx = chan_idx;
+    tw.chan_cached = chan_bytes <= TILE_CHAN_CACHE;
+    if (tw.chan_cached) {
+      const uint4* src = (const uint4*)(b.chan_blob + cd.off);  // segments are 16-byte aligned and zero padded
+      __syncwarp();
+      for (uint32_t i = l; i < chan_bytes / 16u; i += 32) {
+        const uint4 v = __ldg(src + i);
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(chan_s + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+      }
+      __syncwarp();
+    }
+  }
 
   // ---- 1. piece table ----
   const uint32_t vs_s = smem_addr(sh.vshift[wid]);
@@ -245,16 +375,19 @@ DEVI void tile_emit_record(TileShared& sh, int wid, TileStream& t, const TgBatch
     const uint32_t e = sh.pieces[idx];
     const uint32_t kind = e & 15u, arg = (e >> 4) & 15u;
     if (!((condmask >> ((e >> 8) & 15u)) & 1u)) continue;
-    const DstS dst{line_s + lds32(vs_s + 4u * idx)};
+    const uint32_t dst_s = line_s + lds32(vs_s + 4u * idx);
+    const DstS dst{dst_s};
     if (kind == K_CHAN) {
       const uint32_t o = arg == 0 ? 0u : arg == 1 ? pad16(cd.user_len) : arg == 2 ? pad16(cd.user_len) + pad16(cd.name_len)
                                                              : pad16(cd.user_len) + pad16(cd.name_len) + pad16(cd.title_len);
       const uint32_t n = arg == 0 ? cd.user_len : arg == 1 ? cd.name_len : arg == 2 ? cd.title_len : cd.cdata_len;
-      copy_g(dst, b.chan_blob + cd.off + o, n);
+      if (tw.chan_cached) copy_ss(dst_s, chan_s + o, n);
+      else copy_gs_deep(dst_s, b.chan_blob + cd.off + o, n);
       copied += n;
     } else if (kind == K_CFG) {
       const uint32_t n = arg == 0 ? cfg.label_len : arg == 1 ? cfg.created_tg_len : arg == 2 ? cfg.created_yt_len : cfg.capture_len;
-      copy_g(dst, cfg.blob + cfg.off[arg], n);
+      if (tw.cfg_cached) copy_ss(dst_s, smem_addr(sh.cfgc) + cfg.off[arg], n);
+      else copy_gs_deep(dst_s, cfg.blob + cfg.off[arg], n);
       copied += n;
     } else if (kind == K_ESC) {
       const uint8_t* sp = arg == XL_DESC ? d.desc : arg == XL_MEDIA ? a.v.media : arg == XL_HANDLE ? a.v.handle : a.v.alt;
@@ -262,15 +395,47 @@ DEVI void tile_emit_record(TileShared& sh, int wid, TileStream& t, const TgBatch
       const uint32_t xl = arg == 0 ? xa.x : arg == 1 ? xa.y : arg == 2 ? xa.z : xa.w;
       if (xl == 0) continue;
       copied += sn;
-      if (xl == sn) copy_g(dst, sp, sn);
-      else if (arg == XL_DESC && !(xb.w & XLF_DESC_EXACT)) esc_ascii_to(dst, sp, sn);
-      else esc_to(dst, sp, sn);
+      if (xl == sn) {  // clean: the chunks requested at the top, then whatever is left
+        const uint32_t early = arg == XL_DESC ? desc_early : arg == XL_MEDIA ? media_early : arg == XL_HANDLE ? handle_early : 0u;
+        if (arg == XL_DESC) {
+#pragma unroll
+          for (int k = 0; k < TILE_EARLY - 2; k++) {
+            const uint32_t o = 128u * k + 4u * (uint32_t)l;
+            if (o < early) {
+              sts8(dst_s + o, ev[k]);
+              if (o + 1 < early) sts8(dst_s + o + 1, ev[k] >> 8);
+              if (o + 2 < early) sts8(dst_s + o + 2, ev[k] >> 16);
+              if (o + 3 < early) sts8(dst_s + o + 3, ev[k] >> 24);
+            }
+          }
+        } else if (arg == XL_MEDIA || arg == XL_HANDLE) {
+          const uint32_t v = arg == XL_MEDIA ? ev[TILE_EARLY - 2] : ev[TILE_EARLY - 1];
+          const uint32_t o = 4u * (uint32_t)l;
+          if (o < early) {
+            sts8(dst_s + o, v);
+            if (o + 1 < early) sts8(dst_s + o + 1, v >> 8);
+            if (o + 2 < early) sts8(dst_s + o + 2, v >> 16);
+            if (o + 3 < early) sts8(dst_s + o + 3, v >> 24);
+          }
+        }
+        if (sn > early) copy_gs_deep(dst_s + early, sp + early, sn - early);
+      } else if (arg == XL_DESC && !(xb.w & XLF_DESC_EXACT)) {
+        esc_ascii_to(dst, sp, sn);
+      } else {
+        esc_to(dst, sp, sn);
+      }
     } else if (kind == K_COMMENTS) {
-      if (d.comments_nil) copy_g(dst, (const uint8_t*)kNullLit, 4);
-      else if (d.c1 == d.c0) put2(dst, '[', ']');
-      else emit_tg_comments_to(dst, ms, b, d.c0, d.c1);
+      if (d.comments_nil) {
+        if (l < 4) sts8(dst_s + l, (0x6c6c756eu >> (8u * l)) & 0xFFu);  // null
+      } else if (d.c1 == d.c0) {
+        put2(dst, '[', ']');
+      } else {
+        emit_tg_comments_to(dst, ms, b, d.c0, d.c1);
+      }
     } else if (kind == K_REACTIONS) {
-      emit_reaction_map_to(dst, ms, b.reacts, r0, r0 + nr, b.aux);
+      if (nr == 0) put2(dst, '{', '}');
+      else if (xb.w & XLF_SIMPLE_MAP) tile_emit_simple_map(dst_s, b.reacts, r0, nr, b.aux);
+      else emit_reaction_map_to(dst, ms, b.reacts, r0, r0 + nr, b.aux);
     } else {  // K_OUTLINKS
       const uint32_t nl = in.link_count[r];
       if (nl) emit_tg_outlinks_to(dst, in.arena + in.link_start[r], nl);

@@ -567,20 +567,17 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       uint64_t want = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
       unsigned g = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms * 8);
       CK(cudaEventRecord(s.ev_p0, st));
-      tg_parse_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
-      {
-        const uint64_t groups = (n + 31) / 32;
-        unsigned ge = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
+      const uint64_t groups = (n + 31) / 32;
+      unsigned ge = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
+      if (s.n_ents) {  // records with entities first: status + links (two kernels by instruction footprint)
         tg_ent_map_kernel<<<ge, CTA_THREADS, 0, st>>>(b, po);
         tg_parse_ent_kernel<<<ge, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
+        launches += 2;
       }
-      launches += 3;
-      if (want_json) {
-        const uint64_t groups = (n + 31) / 32;
-        unsigned gs = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
-        tg_size_lane_kernel<<<gs, CTA_THREADS, 0, st>>>(b, cfg, po);
-        launches++;
-      }
+      // then ONE pass over every record: status, plaintext links, line length
+      if (want_json) tg_scan_kernel<true><<<ge, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
+      else tg_scan_kernel<false><<<ge, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
+      launches++;
       CK(cudaEventRecord(s.ev_p1, st));
     }
     if (want_json) {
@@ -630,8 +627,10 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       ei.out = s.d_jsonl.as<uint8_t>();
       ei.err = (int*)(dsc + SC_CURSOR) + 1;
       ei.counters = (unsigned long long*)(dsc + SC_LANE_OUT);
+      static const int tile_ctas = getenv("TGI_TILE_CTAS") ? atoi(getenv("TGI_TILE_CTAS")) : 3;  // A/B: register budget of the tile kernel
       static const bool attr_set = [] {
-        return cudaFuncSetAttribute(tg_emit_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess &&
+        return cudaFuncSetAttribute(tg_emit_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess &&
+               cudaFuncSetAttribute(tg_emit_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess &&
                cudaFuncSetAttribute(tg_emit_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SlowShared)) == cudaSuccess;
       }();
       if (!attr_set) { set_err(c, "cannot reserve %zu bytes of shared memory for the tile emitter", sizeof(TileShared)); return TGI_E_CUDA; }
@@ -639,8 +638,9 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       const uint64_t ctas = (groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
       CK(cudaEventRecord(s.ev_e0, st));
       // one CTA per SM slot (3 resident CTAs per SM by shared memory), persistent over the record groups
-      unsigned gt = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * 3);
-      tg_emit_tile_kernel<<<gt, CTA_THREADS, sizeof(TileShared), st>>>(b, cfg, ei);
+      unsigned gt = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * (tile_ctas == 2 ? 2 : 3));
+      if (tile_ctas == 2) tg_emit_tile_kernel<2><<<gt, CTA_THREADS, sizeof(TileShared), st>>>(b, cfg, ei);
+      else tg_emit_tile_kernel<3><<<gt, CTA_THREADS, sizeof(TileShared), st>>>(b, cfg, ei);
       CK(cudaEventRecord(s.ev_f1, st));
       launches++;
       if (hsc[SC_SLOW]) {  // lines longer than a tile buffer (counted by the size pass)
@@ -1009,6 +1009,7 @@ int tgi_create(const tgi_config* cfg, tgi_ctx** out) {
 void tgi_destroy(tgi_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  tgi_comm_destroy(c);  // while the stream its collectives ran on still exists
   for (int i = 0; i < TGI_SLOTS; i++) {
     Slot& s = c->slots[i];
     if (s.worker.joinable()) {
@@ -1036,7 +1037,6 @@ void tgi_destroy(tgi_ctx* c) {
     for (cudaEvent_t e : {s.ev_p0, s.ev_p1, s.ev_e0, s.ev_e1, s.ev_f1, s.ev_fr0, s.ev_fr1}) if (e) cudaEventDestroy(e);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
-  tgi_comm_destroy(c);
   for (auto& f : c->stg_free) cudaFreeHost(f.second);
   for (auto& f : c->stg_live) cudaFreeHost(f.first);
   c->stg_free.clear();

@@ -102,8 +102,9 @@ def test_utf8_escape_fuzz_around_strip_boundaries():
             b"\xff", b"\xc0\x80", b"\xc1", b"\xed\xa0\x80", b"\xed\x9f\xbf", b"\xf0\x9f", b"\xf0\x9f\x98", b"\xf4\x90\x80\x80",
             b"\xf4\x8f\xbf\xbf", b"\xe0\x9f\x80", b"\xe0\xa0\x80", b"\xf0\x8f\x80\x80", b"\xf0\x90\x80\x80", b"\xf5\x80\x80\x80"]
     ms = []
-    for t in range(1500):
-        n = rng.choice([120, 124, 126, 127, 128, 129, 130, 132, 250, 256, 260, 384, 5, 0, 1, 3])
+    for t in range(3000):
+        n = rng.choice([120, 124, 126, 127, 128, 129, 130, 132, 250, 256, 260, 384, 5, 0, 1, 3,
+                        496, 507, 508, 509, 510, 511, 512, 513, 514, 516, 1020, 1023, 1024, 1025, 1536])
         body = bytearray()
         while len(body) < n:
             body += rng.choice(frag) if rng.random() < 0.5 else b"xyz "[: rng.randrange(1, 5)]
@@ -204,38 +205,38 @@ def test_full_size_config2_properties():
 
 
 def test_warp_per_record_reference_kernels_still_agree():
-    """The A/B switches (TGI_EMIT_FIXED_WARP, TGI_SIZE_WARP, TGI_YT_WARP) select the warp-per-record kernels the
-    lane kernels replaced; they are read once per process, so this runs in a child process."""
+    """The A/B switch TGI_YT_WARP selects the warp-per-record YouTube kernels the lane kernels replaced; it is read once
+    per process, so this runs in a child process."""
     import os
     import subprocess
     import sys
     code = (
         "import sys; sys.path.insert(0, 'tests')\n"
         "from distributed_crawler_b200 import abi\n"
-        "from distributed_crawler_b200.corpus import Corpus\n"
         "from distributed_crawler_b200.engine import Engine\n"
         "from oracle.pyoracle import Oracle\n"
         "from helpers import assert_results_equal\n"
         "from yt_corpus import make_youtube\n"
         "f = abi.RUN_JSONL | abi.RUN_LINKS\n"
-        "c = Corpus(5000, profile=2)\n"
-        "assert_results_equal(Oracle().telegram(c.batch, f), Engine().telegram(c.batch, f), f)\n"
         "b, _, _ = make_youtube(800, seed=5)\n"
         "assert_results_equal(Oracle().youtube(b, f), Engine().youtube(b, f), f)\n"
         "print('ok')\n")
-    env = dict(os.environ, TGI_EMIT_FIXED_WARP="1", TGI_SIZE_WARP="1", TGI_YT_WARP="1")
+    env = dict(os.environ, TGI_YT_WARP="1")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     p = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]
 
 
-def test_lane_emitter_hand_over_boundaries():
-    """The lane emitter writes the simple cases itself and leaves the rest to the esc / maps kernels: the rules sit at
-    LANE_TEXT_MAX (512 bytes), LANE_LINKS_MAX (4 outlinks), LANE_MAP_MAX (6 entries), 8-byte keys, repeated keys,
-    strings that need escaping.  Messages on both sides of every boundary, in one warp and spread over several."""
+def test_tile_emitter_boundaries():
+    """The tile emitter assembles lines in a 6144-byte shared-memory buffer per warp and leaves lines that do not fit
+    (with 2096 bytes of map scratch behind them when they carry reactions / comments) to the slow-path kernel; the text
+    scanner works on 512-byte strips.  Messages on both sides of every boundary — buffer size with and without scratch,
+    strip ends, map sizes, repeated / long / dirty keys — in one warp and spread over several, in shuffled orders (so
+    that lines start at every alignment and the buffer is flushed at different fill levels)."""
     from distributed_crawler_b200.pack import Comment
     msgs = []
-    for k, n in enumerate([0, 1, 15, 16, 17, 127, 128, 129, 511, 512, 513, 1024, 3000]):
+    for k, n in enumerate([0, 1, 15, 16, 17, 127, 128, 129, 511, 512, 513, 1024, 3000, 1900, 2000, 2100, 3900, 4000, 4100, 4150, 4200,
+                           4250, 4300, 4400, 4700, 6000, 6200, 9000, 20000]):
         body = ("x" * n)
         msgs.append(Message(id=(k + 1) << 20, text=FormattedText(body)))                       # clean, around the text limit
         msgs.append(Message(id=(k + 100) << 20, text=FormattedText(body[: max(n - 1, 0)] + "\n")))   # needs escaping
@@ -253,6 +254,13 @@ def test_lane_emitter_hand_over_boundaries():
     msgs.append(Message(id=504 << 20, comments=None))
     msgs.append(Message(id=505 << 20, comments=[Comment("c1", [("👍", 1)], 3, 4, "h"), Comment("c\n2", None, 0, 0, "unknown")]))
     msgs.append(Message(id=506 << 20, handle='ha"ndle', media="m<edia", content_type="messageVideo", text=FormattedText("cap")))
+    for k, n in enumerate(range(1950, 2250, 12)):  # lines with reactions on both sides of the buffer-minus-scratch limit
+        msgs.append(Message(id=(600 + k) << 20, text=FormattedText("y" * n), reactions=[("👍", 2), ("zz", 1)]))
+    for k, n in enumerate(range(4050, 4330, 8)):   # lines without scratch on both sides of the buffer limit
+        msgs.append(Message(id=(700 + k) << 20, text=FormattedText("w" * (n - 1) + "\t")))
+    big = [Comment("comment %d " % j + "z" * 300, [("🔥", j)], j, 0, "h%d" % j) for j in range(12)]
+    msgs.append(Message(id=800 << 20, comments=big))                                               # comment list longer than the buffer
+    msgs.append(Message(id=801 << 20, comments=big[:3], reactions=[("👍", 1)], text=FormattedText("t.me/with_comments " * 20)))
     rnd = random.Random(5)
     for order in range(3):
         rnd.shuffle(msgs)
