@@ -70,6 +70,13 @@ YT_CHAN = np.dtype([
     ("reserved", "u1", (11,))])
 LINK = np.dtype([("name", "u1", (32,)), ("len", "u1"), ("src", "u1"), ("flags", "u1"),
                  ("filter_reason", "u1")])
+EDGE = np.dtype([("destination", "u1", (32,)), ("record", "<u8"), ("chan_idx", "<u4"), ("dest_len", "u1"), ("source_type", "u1"),
+                 ("status", "u1"), ("reserved", "u1")])  # tgi_edge
+assert EDGE.itemsize == 48
+SET_INVALID, SET_DISCOVERED = 1, 2
+EDGE_PENDING, EDGE_DUPLICATE, EDGE_INVALID_CACHED = 0, 1, 2
+RUN_SKIP_INVALID = 0x40
+LF_INVALID = 0x08
 
 assert TG_REC.itemsize == 64 and ENTITY.itemsize == 16 and REACTION.itemsize == 12
 assert COMMENT.itemsize == 32 and TG_CHAN.itemsize == 40 and YT_REC.itemsize == 80

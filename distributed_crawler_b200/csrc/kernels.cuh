@@ -28,6 +28,45 @@ constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 #define ERR_FRONTIER_FULL 4
 #define ERR_TOO_MANY_LINKS 8
 
+// ---- batch validation: every offset the kernels will follow stays inside its array ------------------------------
+// A malformed batch that crossed the C ABI must come back as TGI_E_ARG, not as an illegal address (or as foreign
+// bytes in the JSONL).  One thread per index of the longest array; big batches only (small ones are checked by the host).
+struct TgBounds {
+  uint64_t strs_len, n_ents, n_reacts, n_comments, aux_len, chan_strs_len;
+};
+__global__ void tg_validate_kernel(TgBatchDev b, TgBounds lim, uint64_t count, int* bad) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  int e = 0;
+  if (i < b.n) {
+    const tgi_tg_rec rc = b.recs[i];
+    const uint64_t end = rc.str_off + (uint64_t)rc.text_len + rc.alt_len + rc.media_len + rc.handle_len;
+    if (end > lim.strs_len || end < rc.str_off) e |= 1;
+    if (rc.chan_idx >= b.n_chans || rc.content_type >= TGI_CT__COUNT) e |= 2;
+    if (b.ent_off[i] > b.ent_off[i + 1] || b.ent_off[i + 1] > lim.n_ents) e |= 4;
+    if (b.react_off[i] > b.react_off[i + 1] || b.react_off[i + 1] > lim.n_reacts) e |= 8;
+    if (b.comment_off[i] > b.comment_off[i + 1] || b.comment_off[i + 1] > lim.n_comments) e |= 16;
+  }
+  if (i < lim.n_ents) {
+    const tgi_entity en = b.ents[i];
+    if (en.type == TGI_ENT_TEXT_URL && (uint64_t)en.url_off + en.url_len > lim.aux_len) e |= 32;
+  }
+  if (i < lim.n_reacts) {
+    const tgi_reaction rc = b.reacts[i];
+    if ((uint64_t)rc.emoji_off + rc.emoji_len > lim.aux_len) e |= 64;
+  }
+  if (i < lim.n_comments) {
+    const tgi_comment cm = b.comments[i];
+    if ((uint64_t)cm.text_off + cm.text_len > lim.aux_len || (uint64_t)cm.handle_off + cm.handle_len > lim.aux_len) e |= 128;
+    if ((cm.flags & 1) && (uint64_t)cm.react_start + cm.react_count > lim.n_reacts) e |= 256;
+  }
+  if (i < b.n_chans) {
+    const tgi_tg_chan ch = b.chans[i];
+    if ((uint64_t)ch.str_off + ch.title_len + ch.name_len + ch.user_len > lim.chan_strs_len) e |= 512;
+  }
+  if (e) atomicOr(bad, e);
+}
+
 // ---- channel job -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CTA_THREADS) tg_chan_size_kernel(TgBatchDev b, ChanDerived* cd, uint32_t* len) {
   int wid = threadIdx.x >> 5;
@@ -95,9 +134,6 @@ DEVI void parse_one_record(const TgBatchDev& b, const CfgDev& cfg, const ParseOu
   } else if (v.flags & TGI_RF_PANIC) {
     status = TGI_ST_FAILED;
   } else {
-    if (b.react_off[r + 1] - b.react_off[r] > 32) {
-      if (l == 0) atomicOr(o.err, ERR_TOO_MANY_REACTIONS);
-    }
     if (!ENTITIES) v.e1 = v.e0;
     uint32_t ub = warp_link_upper_bound(v, b.ents);
     if (ub >= (1u << 20)) {  // seq packing of the frontier needs ordinal < 2^20 (SEQ_ORD_BITS)
@@ -201,7 +237,6 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_scan_kernel(TgBatchDev b, C
     }
     const bool live = inb && status == TGI_ST_EMITTED;
     const uint32_t r0 = b.react_off[r], nr = b.react_off[r + 1] - r0;
-    if (live && nr > 32) atomicOr(o.err, ERR_TOO_MANY_REACTIONS);
     // ---- the lane's own part of the line length ----
     ChanDerived cd{};
     TgDerived d{};
@@ -944,6 +979,32 @@ DEVI uint64_t key_hash(const Key32& k) {
   return h ^ (h >> 29);
 }
 
+// pool index of `key` in set f, or -1
+DEVI int64_t set_lookup(const FrontierDev& f, const Key32& key, uint64_t h) {
+  if (!f.table) return -1;
+  const uint64_t fp = (h >> 40) | 1ull;
+  for (uint64_t s = h & f.tmask;; s = (s + 1) & f.tmask) {
+    const uint64_t e = f.table[s];
+    if (e == 0) return -1;
+    if ((e >> 40) == fp) {
+      const uint64_t pi = (e & 0xFFFFFFFFFFull) - 1;
+      if (key_eq(key, load_key(f.pool + 32 * pi))) return (int64_t)pi;
+    }
+  }
+}
+// the resident exclusion sets of the frontier -> validator hand-off (tgi_set_add): invalid channels expire after
+// TGI_INVALID_TTL_SEC (state/daprstate.go:3556-3564: time.Since(t) < invalidChannelTTL), stamp 0 = never
+struct ExclusionDev {
+  FrontierDev invalid, discovered;
+  long long now_sec;
+};
+DEVI bool set_invalid_hit(const ExclusionDev& x, const Key32& key, uint64_t h, long long now_sec) {
+  const int64_t pi = set_lookup(x.invalid, key, h);
+  if (pi < 0) return false;
+  const long long t = (long long)x.invalid.payload[pi];
+  return t == 0 || now_sec - t < (long long)TGI_INVALID_TTL_SEC;
+}
+
 DEVI bool link_eligible(const tgi_link& lk, uint32_t run_flags) {
   if ((run_flags & TGI_RUN_SKIP_SELF) && (lk.flags & TGI_LF_SELF)) return false;    // runner.go:1231
   if ((run_flags & TGI_RUN_FILTER) && !(lk.flags & TGI_LF_FILTER_OK)) return false; // runner.go:1261
@@ -952,7 +1013,7 @@ DEVI bool link_eligible(const tgi_link& lk, uint32_t run_flags) {
 
 // phase 1: probe the persistent set; unseen keys race into the batch table, min sequence wins
 __global__ void frontier_probe_kernel(uint64_t n, const uint32_t* link_start, const uint32_t* link_count,
-                                      const tgi_link* arena, uint32_t run_flags, FrontierDev f, FrontierBatch fb) {
+                                      tgi_link* arena, uint32_t run_flags, FrontierDev f, FrontierBatch fb, ExclusionDev x) {
   uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   uint32_t cnt = link_count[r];
@@ -960,13 +1021,18 @@ __global__ void frontier_probe_kernel(uint64_t n, const uint32_t* link_start, co
   uint32_t ls = link_start ? link_start[r] : (uint32_t)r;
   for (uint32_t k = 0; k < cnt; k++) {
     uint32_t idx = ls + k;
-    const tgi_link& lk = arena[idx];
+    tgi_link& lk = arena[idx];
     if (!link_eligible(lk, run_flags)) {
       fb.lstate[idx] = LS_INELIGIBLE;
       continue;
     }
     Key32 key = load_key(lk.name);
     uint64_t h = key_hash(key);
+    if ((run_flags & TGI_RUN_SKIP_INVALID) && set_invalid_hit(x, key, h, x.now_sec)) {  // runner.go:1247
+      lk.flags |= TGI_LF_INVALID;
+      fb.lstate[idx] = LS_INELIGIBLE;
+      continue;
+    }
     uint64_t fp = (h >> 40) | 1ull;  // 24-bit fingerprint, never 0
     bool known = false;
     for (uint64_t s = h & f.tmask;; s = (s + 1) & f.tmask) {
@@ -1089,6 +1155,40 @@ __global__ void merge_scatter_kernel(const uint8_t* pool, uint64_t first, uint64
 #pragma unroll
   for (int j = 0; j < 8; j++) dst[j] = k.w[j];
   send_pay[pos] = pay_base | (first + i);
+}
+
+// ---- frontier -> validator hand-off: the new edges of a batch as packed pending_edges rows --------
+// rec_new / new_off are what the frontier phase of the batch left behind: row index = new_off[r] + ordinal among the
+// record's NEW links, i.e. (record, first-insertion) order — the order of the reference's INSERTs.
+__global__ void edges_emit_kernel(uint64_t n, const uint32_t* link_start, const uint32_t* link_count, const tgi_link* arena,
+                                  const uint32_t* chan_idx_of, uint32_t chan_stride, const uint64_t* new_off, ExclusionDev x,
+                                  tgi_edge* rows, uint64_t cap) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const uint32_t cnt = link_count[r];
+  if (!cnt) return;
+  uint64_t row = new_off[r];
+  const tgi_link* lk = arena + link_start[r];
+  for (uint32_t k = 0; k < cnt; k++) {
+    if (!(lk[k].flags & TGI_LF_NEW)) continue;
+    if (row < cap) {
+      const Key32 key = load_key(lk[k].name);
+      const uint64_t h = key_hash(key);
+      tgi_edge e;
+      uint32_t* d = (uint32_t*)e.destination;
+#pragma unroll
+      for (int i = 0; i < 8; i++) d[i] = key.w[i];
+      e.record = r;
+      e.chan_idx = chan_idx_of ? *(const uint32_t*)((const uint8_t*)chan_idx_of + (size_t)r * chan_stride) : 0u;
+      e.dest_len = lk[k].len;
+      e.source_type = lk[k].src;
+      e.status = set_invalid_hit(x, key, h, x.now_sec) ? TGI_EDGE_INVALID_CACHED           // validator.go:205-212
+                 : set_lookup(x.discovered, key, h) >= 0 ? TGI_EDGE_DUPLICATE : TGI_EDGE_PENDING;  // :214-226
+      e.reserved = 0;
+      rows[row] = e;
+    }
+    row++;
+  }
 }
 
 // keys32 -> pseudo arena (one link per "record") for tgi_frontier_insert

@@ -150,6 +150,110 @@ DEVI MapLane warp_map_prepare(const tgi_reaction* reacts, uint32_t r0, uint32_t 
   return m;
 }
 
+// ---- maps with more than 32 entries (no format limit: the reference builds map[string]int from however many
+// reactions TDLib delivers) ----------------------------------------------------------------------------------------
+// Entries are visited 32 at a time; every entry looks at all the others (quadratic, warp-parallel, keys read through
+// L1): live = no later entry has the same key; rank = live entries with a smaller key.  Rare by construction.
+struct BigMapEntry {
+  bool live;
+  uint32_t rank, before;  // before = bytes of the live entries that sort in front of this one (with their commas)
+  uint32_t len;           // "key":count
+};
+DEVI BigMapEntry big_map_entry(const tgi_reaction* reacts, uint32_t r0, uint32_t r1, const uint8_t* aux, uint32_t i, bool want_order) {
+  BigMapEntry m;
+  const tgi_reaction me = reacts[i];
+  const uint8_t* kp = aux + me.emoji_off;
+  m.live = true;
+  for (uint32_t j = i + 1; j < r1 && m.live; j++) {
+    const tgi_reaction o = reacts[j];
+    if (o.emoji_len == me.emoji_len && key_cmp(aux + o.emoji_off, o.emoji_len, kp, me.emoji_len) == 0) m.live = false;
+  }
+  m.len = m.live ? 3u + thread_esc_len(kp, me.emoji_len) + ndigits_i64(me.count) : 0u;
+  m.rank = 0;
+  m.before = 0;
+  if (want_order && m.live) {
+    for (uint32_t j = r0; j < r1; j++) {
+      if (j == i) continue;
+      const tgi_reaction o = reacts[j];
+      const uint8_t* op = aux + o.emoji_off;
+      if (key_cmp(op, o.emoji_len, kp, me.emoji_len) >= 0) continue;
+      bool olive = true;  // only the last occurrence of a smaller key counts
+      for (uint32_t q = j + 1; q < r1 && olive; q++) {
+        const tgi_reaction o2 = reacts[q];
+        if (o2.emoji_len == o.emoji_len && key_cmp(aux + o2.emoji_off, o2.emoji_len, op, o.emoji_len) == 0) olive = false;
+      }
+      if (olive) {
+        m.rank++;
+        m.before += 4u + thread_esc_len(op, o.emoji_len) + ndigits_i64(o.count);
+      }
+    }
+  }
+  return m;
+}
+__device__ __noinline__ uint32_t size_reaction_map_big(const tgi_reaction* reacts, uint32_t r0, uint32_t r1, const uint8_t* aux) {
+  uint32_t bytes = 0, nlive = 0;
+  for (uint32_t i = r0 + lane_id(); i < r1; i += 32) {
+    const BigMapEntry m = big_map_entry(reacts, r0, r1, aux, i, false);
+    bytes += m.len;
+    nlive += m.live ? 1u : 0u;
+  }
+  bytes = warp_sum(bytes);
+  nlive = warp_sum(nlive);
+  return 2u + bytes + (nlive - 1u);
+}
+template <class D>
+__device__ __noinline__ uint32_t emit_reaction_map_big_to(D dst, const tgi_reaction* reacts, uint32_t r0, uint32_t r1, const uint8_t* aux) {
+  uint32_t bytes = 0, nlive = 0;
+  if (lane_id() == 0) dst.st(0, '{');
+  for (uint32_t i = r0 + lane_id(); i < r1; i += 32) {
+    const BigMapEntry m = big_map_entry(reacts, r0, r1, aux, i, true);
+    if (!m.live) continue;
+    bytes += m.len;
+    nlive++;
+    const tgi_reaction me = reacts[i];
+    const uint8_t* kp = aux + me.emoji_off;
+    uint32_t o = 1u + m.before;  // behind the brace and the smaller entries (each followed by a comma)
+    dst.st(o++, '"');
+    for (uint32_t q = 0; q < me.emoji_len;) {  // thread_esc without a staging buffer: one rune at a time
+      const uint32_t bq = ldb(kp + q);
+      if (bq < 0x80) {
+        const uint32_t el = ascii_esc_len(bq);
+        put_escaped(dst, o, bq, el);
+        o += el;
+        q++;
+        continue;
+      }
+      const int need = utf8_valid_lead(kp, q, me.emoji_len);
+      if (need == 0) {
+        put_u(dst, o, 'f', 'f', 'f', 'd');
+        o += 6;
+        q++;
+      } else if (need == 3 && bq == 0xE2 && ldb(kp + q + 1) == 0x80 && (ldb(kp + q + 2) | 1u) == 0xA9) {
+        put_u(dst, o, '2', '0', '2', ldb(kp + q + 2) == 0xA8 ? '8' : '9');
+        o += 6;
+        q += 3;
+      } else {
+        for (int k = 0; k < need; k++) dst.st(o + k, ldb(kp + q + k));
+        o += (uint32_t)need;
+        q += (uint32_t)need;
+      }
+    }
+    dst.st(o++, '"');
+    dst.st(o++, ':');
+    uint8_t num[12];
+    const int nd = render_i64(num, me.count);
+    for (int k = 0; k < nd; k++) dst.st(o + k, num[k]);
+    o += (uint32_t)nd;
+    dst.st(o, ',');  // the last entry's comma is overwritten by the closing brace below
+  }
+  bytes = warp_sum(bytes);
+  nlive = warp_sum(nlive);
+  const uint32_t total = 2u + bytes + (nlive - 1u);
+  __syncwarp();
+  if (lane_id() == 0) dst.st(total - 1u, '}');
+  return total;
+}
+
 // *simple (optional): the map can be rendered by one lane (tg_lane.cuh): at most LANE_MAP_MAX entries,
 // keys of 1..8 bytes that need no escaping, no duplicate keys
 constexpr uint32_t LANE_MAP_MAX = 6;
@@ -158,6 +262,10 @@ __device__ __noinline__ uint32_t size_reaction_map(const tgi_reaction* reacts, u
   if (r1 == r0) {
     if (simple) *simple = 1;
     return 2;
+  }
+  if (r1 - r0 > 32) {
+    if (simple) *simple = 0;
+    return size_reaction_map_big(reacts, r0, r1, aux);
   }
   MapLane m = warp_map_prepare(reacts, r0, r1, aux, false);
   const uint32_t el = m.live ? thread_esc_len(m.kp, m.kl) : 0u;
@@ -179,6 +287,7 @@ __device__ __noinline__ uint32_t emit_reaction_map_to(D dst, MapScratch* ms, con
     put2(dst, '{', '}');
     return 2;
   }
+  if (r1 - r0 > 32) return emit_reaction_map_big_to(dst, reacts, r0, r1, aux);
   int l = lane_id();
   MapLane m = warp_map_prepare(reacts, r0, r1, aux, true);
   uint32_t slot = smem_addr(ms->rslot[l]);

@@ -115,6 +115,9 @@ struct Slot {
   uint64_t n_ents = 0, n_reacts = 0, n_comments = 0, in_bytes = 0;
   bool resident = false;
   uint64_t dev_jsonl_len = 0;
+  // what tgi_pending_edges needs from the slot's last batch
+  uint64_t last_n = 0, last_new = 0;
+  bool last_frontier = false, last_yt = false;
   // job hand-off
   std::mutex mu;
   std::condition_variable cv;
@@ -150,6 +153,9 @@ struct tgi_ctx {
   cudaEvent_t fr_event = nullptr;
   bool fr_event_valid = false;
   InsertScratch ins;  // scratch of tgi_frontier_insert* / the merge (under fr_mu)
+  // frontier -> validator hand-off: resident exclusion sets (tgi_set_add)
+  DevBuf x_pool[2], x_table[2], x_count[2], x_payload;
+  ExclusionDev excl{};
   // multi-GPU merge: communicator + this rank's partition of the global set
   NcclApi* nccl = nullptr;
   ncclComm_t comm = nullptr;
@@ -320,6 +326,39 @@ int h2d(tgi_ctx* c, Slot& s, DevBuf& d, const T* src, size_t count) {
   return TGI_OK;
 }
 
+enum { SC_CHAN_TOTAL = 0, SC_LINE_TOTAL = 1, SC_CURSOR = 2, SC_NEW = 3, SC_FSIZE = 4, SC_LINK_TOTAL = 5, SC_LONG = 6, SC_URL_CURSOR = 7, SC_LANE_OUT = 8, SC_LANE_IN = 9, SC_SLOW = 10, SC_COUNT = 12 };
+constexpr uint64_t HOST_VALIDATE_MAX = 1u << 16;  // batches up to this many elements are range-checked on the host
+
+// the checks of tg_validate_kernel, on the host (small batches: no extra launch / sync in a page-sized call)
+int host_validate_tg(const tgi_tg_batch* in) {
+  const uint64_t n = in->n, n_ents = n ? in->ent_off[n] : 0;
+  int e = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    const tgi_tg_rec& rc = in->recs[i];
+    const uint64_t end = rc.str_off + (uint64_t)rc.text_len + rc.alt_len + rc.media_len + rc.handle_len;
+    if (end > in->strs_len || end < rc.str_off) e |= 1;
+    if (rc.chan_idx >= in->n_chans || rc.content_type >= TGI_CT__COUNT) e |= 2;
+    if (in->ent_off[i] > in->ent_off[i + 1]) e |= 4;
+    if (in->react_off[i] > in->react_off[i + 1] || in->react_off[i + 1] > in->n_reacts) e |= 8;
+    if (in->comment_off[i] > in->comment_off[i + 1] || in->comment_off[i + 1] > in->n_comments) e |= 16;
+  }
+  if (e) return e;  // the entity count itself comes from ent_off: do not follow it if the offsets are broken
+  for (uint64_t i = 0; i < n_ents; i++)
+    if (in->ents[i].type == TGI_ENT_TEXT_URL && (uint64_t)in->ents[i].url_off + in->ents[i].url_len > in->aux_len) e |= 32;
+  for (uint64_t i = 0; i < in->n_reacts; i++)
+    if ((uint64_t)in->reacts[i].emoji_off + in->reacts[i].emoji_len > in->aux_len) e |= 64;
+  for (uint64_t i = 0; i < in->n_comments; i++) {
+    const tgi_comment& cm = in->comments[i];
+    if ((uint64_t)cm.text_off + cm.text_len > in->aux_len || (uint64_t)cm.handle_off + cm.handle_len > in->aux_len) e |= 128;
+    if ((cm.flags & 1) && (uint64_t)cm.react_start + cm.react_count > in->n_reacts) e |= 256;
+  }
+  for (uint32_t i = 0; i < in->n_chans; i++) {
+    const tgi_tg_chan& ch = in->chans[i];
+    if ((uint64_t)ch.str_off + ch.title_len + ch.name_len + ch.user_len > in->chan_strs_len) e |= 512;
+  }
+  return e;
+}
+
 int validate_tg(tgi_ctx* c, const tgi_tg_batch* in) {
   if (!in) { set_err(c, "null batch"); return TGI_E_ARG; }
   if (in->n && (!in->recs || !in->ent_off || !in->react_off || !in->comment_off || !in->chans)) {
@@ -330,6 +369,16 @@ int validate_tg(tgi_ctx* c, const tgi_tg_batch* in) {
   if (!(c->cfg.flags & TGI_CFG_SKIP_MEDIA)) {
     set_err(c, "TGI_CFG_SKIP_MEDIA is required: media download is an RPC outside this path");
     return TGI_E_ARG;
+  }
+  const uint64_t n_ents = in->n ? in->ent_off[in->n] : 0;
+  if ((n_ents && !in->ents) || (in->n_reacts && !in->reacts) || (in->n_comments && !in->comments) ||
+      (in->strs_len && !in->strs) || (in->aux_len && !in->aux) || (in->chan_strs_len && !in->chan_strs)) {
+    set_err(c, "telegram batch: a non-empty array has a null pointer");
+    return TGI_E_ARG;
+  }
+  if (in->n + n_ents + in->n_reacts + in->n_comments + in->n_chans <= HOST_VALIDATE_MAX) {
+    const int e = host_validate_tg(in);
+    if (e) { set_err(c, "telegram batch: offsets outside their arrays (mask 0x%x)", e); return TGI_E_ARG; }
   }
   return TGI_OK;
 }
@@ -372,13 +421,28 @@ int upload_tg(tgi_ctx* c, Slot& s, const tgi_tg_batch* in) {
   s.n_ents = n_ents;
   s.n_reacts = in->n_reacts;
   s.n_comments = in->n_comments;
+  if (n + n_ents + in->n_reacts + in->n_comments + in->n_chans > HOST_VALIDATE_MAX) {  // big batch: range-check on the device
+    CK(s.d_scalars.ensure(SC_COUNT * 8));
+    int* bad = (int*)s.d_scalars.p;
+    CK(cudaMemsetAsync(bad, 0, 4, s.stream));
+    TgBounds lim{in->strs_len, n_ents, in->n_reacts, in->n_comments, in->aux_len, in->chan_strs_len};
+    const uint64_t count = std::max<uint64_t>({n, n_ents, in->n_reacts, in->n_comments, (uint64_t)in->n_chans});
+    tg_validate_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s.stream>>>(b, lim, count, bad);
+    int hbad = 0;
+    CK(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    if (hbad) {
+      s.resident = false;
+      set_err(c, "telegram batch: offsets outside their arrays (mask 0x%x)", hbad);
+      return TGI_E_ARG;
+    }
+  }
   s.resident = true;
   return TGI_OK;
 }
 
 // scalars block (device + pinned mirror): [0] chan total, [1] line total, [2] cursor(u32)+err(int),
 // [3] n_new, [4] frontier size, [5] link total
-enum { SC_CHAN_TOTAL = 0, SC_LINE_TOTAL = 1, SC_CURSOR = 2, SC_NEW = 3, SC_FSIZE = 4, SC_LINK_TOTAL = 5, SC_LONG = 6, SC_URL_CURSOR = 7, SC_LANE_OUT = 8, SC_LANE_IN = 9, SC_SLOW = 10, SC_COUNT = 12 };
 
 // shared tail of the Telegram and YouTube pipelines: frontier phases, link compaction, D2H, result
 int finish_batch(tgi_ctx* c, Slot& s, uint64_t n, uint32_t flags, uint64_t line_total, uint32_t arena_used,
@@ -408,7 +472,7 @@ int finish_batch(tgi_ctx* c, Slot& s, uint64_t n, uint32_t flags, uint64_t line_
     fb.rec_new = s.d_rec_new.as<uint32_t>();
     unsigned g = (unsigned)((n + 255) / 256);
     frontier_probe_kernel<<<g, 256, 0, st>>>(n, s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(),
-                                             s.d_arena.as<tgi_link>(), flags, c->fr, fb);
+                                             s.d_arena.as<tgi_link>(), flags, c->fr, fb, c->excl);
     frontier_count_kernel<<<g, 256, 0, st>>>(n, s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(), fb);
     launches += 2;
     int rc = launch_scan(c, s, fb.rec_new, n, s.d_new_off.as<uint64_t>(), dsc + SC_NEW, launches);
@@ -482,6 +546,10 @@ int finish_batch(tgi_ctx* c, Slot& s, uint64_t n, uint32_t flags, uint64_t line_
   out->jsonl_len = want_json ? line_total : 0;
   out->n_links = n_links_total;
   out->n_new = want_fr ? hsc[SC_NEW] : 0;
+  s.last_n = n;
+  s.last_new = out->n_new;
+  s.last_frontier = want_fr && n;
+  s.last_yt = s.tg.n == 0 && s.yt.n == n && n != 0;
   out->frontier_size = want_fr ? hsc[SC_FSIZE] : 0;
   if (d2h) {
     out->status = s.h_status.as<uint8_t>();
@@ -596,7 +664,6 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     break;
   }
   if (dev_err & ERR_ARENA_OVERFLOW) { set_err(c, "link arena overflow persisted"); return TGI_E_CAPACITY; }
-  if (dev_err & ERR_TOO_MANY_REACTIONS) { set_err(c, "a reactions map has more than 32 entries (format limit)"); return TGI_E_ARG; }
   if (dev_err & ERR_TOO_MANY_LINKS) { set_err(c, "a record has 2^20 or more link candidates"); return TGI_E_ARG; }
   uint64_t chan_total = hsc[SC_CHAN_TOTAL], line_total = hsc[SC_LINE_TOTAL];
   uint32_t arena_used = ((uint32_t*)(hsc + SC_CURSOR))[0];
@@ -659,6 +726,21 @@ int upload_yt(tgi_ctx* c, Slot& s, const tgi_yt_batch* in) {
   if (!in) { set_err(c, "null batch"); return TGI_E_ARG; }
   if (in->n && (!in->recs || !in->chans)) { set_err(c, "youtube batch: recs/chans must be non-null"); return TGI_E_ARG; }
   if (in->n >= (1ull << 40)) { set_err(c, "youtube batch: too many records"); return TGI_E_ARG; }
+  {  // every offset the kernels will follow stays inside its array (O(n) on the host: 80-byte records, no side arrays)
+    int e = 0;
+    for (uint64_t i = 0; i < in->n; i++) {
+      const tgi_yt_rec& r = in->recs[i];
+      uint64_t end = r.str_off + (uint64_t)r.id_len + r.title_len + r.desc_len + r.duration_len + r.lang_len;
+      for (int k = 0; k < 5; k++) end += r.thumb_len[k] == TGI_YT_THUMB_ABSENT ? 0u : r.thumb_len[k];
+      if (end > in->strs_len || end < r.str_off) e |= 1;
+      if (r.chan_idx >= in->n_chans) e |= 2;
+    }
+    for (uint32_t i = 0; i < in->n_chans; i++) {
+      const tgi_yt_chan& ch = in->chans[i];
+      if ((uint64_t)ch.str_off + ch.id_len + ch.title_len + ch.desc_len + ch.thumb_len + ch.country_len > in->chan_strs_len) e |= 512;
+    }
+    if (e) { set_err(c, "youtube batch: offsets outside their arrays (mask 0x%x)", e); return TGI_E_ARG; }
+  }
   s.in_bytes = 0;
   int rc;
 #define UP(buf, ptr, cnt)                      \
@@ -786,6 +868,18 @@ int run_gm(tgi_ctx* c, Slot& s, const tgi_gm_batch* in, uint32_t flags, tgi_resu
   if (!in) { set_err(c, "null batch"); return TGI_E_ARG; }
   if (in->n && !in->recs) { set_err(c, "generic batch: recs must be non-null"); return TGI_E_ARG; }
   if (in->n >= (1ull << 40)) { set_err(c, "generic batch: too many records"); return TGI_E_ARG; }
+  {
+    int e = 0;
+    for (uint64_t i = 0; i < in->n; i++) {
+      const tgi_gm_rec& r = in->recs[i];
+      const uint64_t end = r.str_off + (uint64_t)r.id_len + r.channel_len + r.text_len + r.sender_len;
+      if (end > in->strs_len || end < r.str_off) e |= 1;
+      if (in->react_off && (in->react_off[i] > in->react_off[i + 1] || in->react_off[i + 1] > in->n_reacts)) e |= 8;
+    }
+    for (uint64_t i = 0; i < in->n_reacts; i++)
+      if ((uint64_t)in->reacts[i].key_off + in->reacts[i].key_len > in->aux_len) e |= 64;
+    if (e) { set_err(c, "generic batch: offsets outside their arrays (mask 0x%x)", e); return TGI_E_ARG; }
+  }
   const uint64_t n = in->n;
   cudaStream_t st = s.stream;
   s.in_bytes = 0;
@@ -1042,6 +1136,8 @@ void tgi_destroy(tgi_ctx* c) {
   c->stg_free.clear();
   c->stg_live.clear();
   c->m_host.release();
+  for (int k = 0; k < 2; k++) { c->x_pool[k].release(); c->x_table[k].release(); c->x_count[k].release(); }
+  c->x_payload.release();
   c->d_cfg.release();
   c->d_pool.release();
   c->d_table.release();
@@ -1257,7 +1353,7 @@ static int frontier_insert_locked(tgi_ctx* c, FrontierDev& f, const void* d_keys
   fb.bmask = bslots - 1;
   fb.lstate = z.lstate.as<uint32_t>();
   fb.rec_new = z.recnew.as<uint32_t>();
-  frontier_probe_kernel<<<g, 256, 0, st>>>(n, nullptr, z.cnt.as<uint32_t>(), z.arena.as<tgi_link>(), 0, f, fb);
+  frontier_probe_kernel<<<g, 256, 0, st>>>(n, nullptr, z.cnt.as<uint32_t>(), z.arena.as<tgi_link>(), 0, f, fb, ExclusionDev{});
   frontier_count_kernel<<<g, 256, 0, st>>>(n, nullptr, z.cnt.as<uint32_t>(), fb);
   {
     uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
@@ -1384,6 +1480,105 @@ int tgi_frontier_clear(tgi_ctx* c) {
   c->merged_upto = 0;
   CK(cudaEventRecord(c->fr_event, st));
   c->fr_event_valid = true;
+  CK(cudaStreamSynchronize(st));
+  return TGI_OK;
+}
+
+// ---- frontier -> validator hand-off ------------------------------------------------------------
+static FrontierDev* excl_set(tgi_ctx* c, int which) {
+  return which == TGI_SET_INVALID ? &c->excl.invalid : which == TGI_SET_DISCOVERED ? &c->excl.discovered : nullptr;
+}
+int tgi_set_add(tgi_ctx* c, int which, const uint8_t* keys32, const int64_t* stamp_sec, uint64_t n) {
+  if (!c || (n && !keys32)) return TGI_E_ARG;
+  FrontierDev* f = excl_set(c, which);
+  if (!f) { set_err(c, "tgi_set_add: unknown set %d", which); return TGI_E_ARG; }
+  if (n >= (1ull << 32)) { set_err(c, "too many keys in one call"); return TGI_E_ARG; }
+  cudaSetDevice(c->device);
+  std::lock_guard<std::mutex> g(c->fr_mu);
+  cudaStream_t st = c->slots[0].stream;
+  const int k = which == TGI_SET_INVALID ? 0 : 1;
+  if (!f->table) {  // first use: same capacity as the dedup set
+    const uint64_t fcap = c->fr.cap, tslots = c->fr.tmask + 1;
+    CK(c->x_pool[k].ensure(fcap * 32));
+    CK(c->x_table[k].ensure(tslots * 8));
+    CK(c->x_count[k].ensure(16));
+    if (k == 0) CK(c->x_payload.ensure(fcap * 8));
+    CK(cudaMemsetAsync(c->x_table[k].p, 0, tslots * 8, st));
+    CK(cudaMemsetAsync(c->x_count[k].p, 0, 16, st));
+    f->pool = c->x_pool[k].as<uint8_t>();
+    f->cap = fcap;
+    f->table = c->x_table[k].as<uint64_t>();
+    f->tmask = tslots - 1;
+    f->count = c->x_count[k].as<uint64_t>();
+    f->payload = k == 0 ? c->x_payload.as<uint64_t>() : nullptr;
+  }
+  if (!n) return TGI_OK;
+  DevBuf dk, dp;
+  CK(dk.ensure(n * 32));
+  CK(cudaMemcpyAsync(dk.p, keys32, n * 32, cudaMemcpyHostToDevice, st));
+  const uint64_t* pay = nullptr;
+  if (k == 0 && stamp_sec) {
+    CK(dp.ensure(n * 8));
+    CK(cudaMemcpyAsync(dp.p, stamp_sec, n * 8, cudaMemcpyHostToDevice, st));
+    pay = dp.as<uint64_t>();
+  }
+  int rc = frontier_insert_locked(c, *f, dk.p, pay, n, nullptr);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(st));
+  return frontier_insert_check(c, *f);
+}
+int tgi_set_clear(tgi_ctx* c, int which) {
+  if (!c) return TGI_E_ARG;
+  FrontierDev* f = excl_set(c, which);
+  if (!f) return TGI_E_ARG;
+  cudaSetDevice(c->device);
+  std::lock_guard<std::mutex> g(c->fr_mu);
+  if (!f->table) return TGI_OK;
+  cudaStream_t st = c->slots[0].stream;
+  if (c->fr_event_valid) CK(cudaStreamWaitEvent(st, c->fr_event, 0));
+  int rc = frontier_clear_set(c, *f);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(st));
+  return TGI_OK;
+}
+int tgi_set_size(tgi_ctx* c, int which, uint64_t* n) {
+  if (!c || !n) return TGI_E_ARG;
+  FrontierDev* f = excl_set(c, which);
+  if (!f) return TGI_E_ARG;
+  cudaSetDevice(c->device);
+  std::lock_guard<std::mutex> g(c->fr_mu);
+  *n = 0;
+  if (!f->table) return TGI_OK;
+  return frontier_read_count(c, *f, n);
+}
+int tgi_set_now(tgi_ctx* c, int64_t now_sec) {
+  if (!c) return TGI_E_ARG;
+  std::lock_guard<std::mutex> g(c->fr_mu);
+  c->excl.now_sec = now_sec;
+  return TGI_OK;
+}
+int tgi_pending_edges(tgi_ctx* c, int slot, int64_t now_sec, tgi_edge* rows, uint64_t cap, uint64_t* n) {
+  if (!c || !n || slot < 0 || slot >= TGI_SLOTS || (cap && !rows)) return TGI_E_ARG;
+  cudaSetDevice(c->device);
+  Slot& s = c->slots[slot];
+  if (!s.last_frontier) { *n = 0; if (s.last_n == 0) return TGI_OK; set_err(c, "tgi_pending_edges: the slot's last batch ran without TGI_RUN_FRONTIER"); return TGI_E_STATE; }
+  *n = s.last_new;
+  const uint64_t m = s.last_new < cap ? s.last_new : cap;
+  if (!m) return TGI_OK;
+  std::lock_guard<std::mutex> g(c->fr_mu);
+  cudaStream_t st = s.stream;
+  if (c->fr_event_valid) CK(cudaStreamWaitEvent(st, c->fr_event, 0));
+  DevBuf drows;
+  CK(drows.ensure(m * sizeof(tgi_edge)));
+  ExclusionDev x = c->excl;
+  x.now_sec = now_sec;
+  const uint32_t* chan = s.last_yt ? &s.d_recs.as<tgi_yt_rec>()->chan_idx : &s.d_recs.as<tgi_tg_rec>()->chan_idx;
+  const uint32_t stride = s.last_yt ? (uint32_t)sizeof(tgi_yt_rec) : (uint32_t)sizeof(tgi_tg_rec);
+  edges_emit_kernel<<<(unsigned)((s.last_n + 255) / 256), 256, 0, st>>>(s.last_n, s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(),
+                                                                    s.d_arena.as<tgi_link>(), chan, stride, s.d_new_off.as<uint64_t>(), x,
+                                                                    drows.as<tgi_edge>(), m);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(rows, drows.p, m * sizeof(tgi_edge), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return TGI_OK;
 }

@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = [
     "tgi_frontier_clear", "tgi_frontier_export_dev", "tgi_frontier_insert_dev", "tgi_frontier_sync",
     "tgi_filter_usernames", "tgi_acquire_staging", "tgi_release_staging", "tgi_comm_unique_id", "tgi_comm_init",
     "tgi_comm_destroy", "tgi_frontier_merge", "tgi_frontier_global_export", "tgi_merge_get_stats",
+    "tgi_set_add", "tgi_set_clear", "tgi_set_size", "tgi_set_now", "tgi_pending_edges",
 ]
 
 
@@ -85,6 +86,11 @@ def lib() -> C.CDLL:
         L.tgi_frontier_merge.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
         L.tgi_frontier_global_export.argtypes = [vp, vp, u64, C.POINTER(u64)]
         L.tgi_merge_get_stats.argtypes = [vp, C.POINTER(abi.MergeStatsC)]
+        L.tgi_set_add.argtypes = [vp, i32, vp, vp, u64]
+        L.tgi_set_clear.argtypes = [vp, i32]
+        L.tgi_set_size.argtypes = [vp, i32, C.POINTER(u64)]
+        L.tgi_set_now.argtypes = [vp, C.c_int64]
+        L.tgi_pending_edges.argtypes = [vp, i32, C.c_int64, vp, u64, C.POINTER(u64)]
         _LIB = L
     return _LIB
 
@@ -297,6 +303,32 @@ class Engine:
         s = abi.MergeStatsC()
         self._check(lib().tgi_merge_get_stats(self.h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in s._fields_}
+
+    # --- frontier -> validator hand-off -------------------------------------
+    def set_add(self, which: int, keys32: np.ndarray, stamps: np.ndarray | None = None):
+        keys32 = np.ascontiguousarray(keys32, np.uint8).reshape(-1, 32)
+        st = None if stamps is None else np.ascontiguousarray(stamps, np.int64)
+        self._check(lib().tgi_set_add(self.h, which, keys32.ctypes.data, None if st is None else st.ctypes.data, len(keys32)))
+
+    def set_clear(self, which: int):
+        self._check(lib().tgi_set_clear(self.h, which))
+
+    def set_size(self, which: int) -> int:
+        n = C.c_uint64()
+        self._check(lib().tgi_set_size(self.h, which, C.byref(n)))
+        return n.value
+
+    def set_now(self, now_sec: int):
+        self._check(lib().tgi_set_now(self.h, now_sec))
+
+    def pending_edges(self, slot: int, now_sec: int = 0) -> np.ndarray:
+        """the new edges of the slot's last batch as packed pending_edges rows (call before release)"""
+        n = C.c_uint64()
+        self._check(lib().tgi_pending_edges(self.h, slot, now_sec, None, 0, C.byref(n)))
+        rows = np.zeros(n.value, abi.EDGE)
+        if n.value:
+            self._check(lib().tgi_pending_edges(self.h, slot, now_sec, rows.ctypes.data, n.value, C.byref(n)))
+        return rows
 
     # --- generic client.Message -> sparse Post (SURVEY a12) -------------------------------------
     def generic(self, batch, run_flags=abi.RUN_JSONL, copy=True) -> Result:

@@ -303,10 +303,13 @@ typedef struct tgi_config {
 #define TGI_RUN_FILTER 0x08     /* tandem mode: FilterUsername gate before the set (runner.go:1261) */
 #define TGI_RUN_SKIP_SELF 0x10  /* drop o == owner.URL (runner.go:1231)                           */
 #define TGI_RUN_NO_D2H 0x20     /* bench only: leave results on the device (kernel-only timing)   */
+#define TGI_RUN_SKIP_INVALID 0x40 /* tandem mode: drop outlinks found in the resident invalid-channel set before they
+                                   reach the dedup set (crawl/runner.go:1247 sm.IsInvalidChannel); link.flags INVALID */
 
 #define TGI_LF_FILTER_OK 0x01 /* FilterUsername(name).Valid                                       */
 #define TGI_LF_NEW 0x02       /* first occurrence in the global frontier set                      */
 #define TGI_LF_SELF 0x04      /* equals the record's channel name                                 */
+#define TGI_LF_INVALID 0x08   /* found in the resident invalid-channel set (TGI_RUN_SKIP_INVALID)  */
 
 typedef struct tgi_link { /* 36 bytes */
   uint8_t name[32]; /* lower-cased, zero padded                                                   */
@@ -464,6 +467,44 @@ typedef struct tgi_merge_stats {
   double bucket_ms, exchange_ms, insert_ms; /* device time, summed over the merges */
 } tgi_merge_stats;
 int tgi_merge_get_stats(tgi_ctx* ctx, tgi_merge_stats* out);
+
+/* SURVEY 8f rank 3 — frontier -> validator hand-off.  The reference walks the outlinks of every message, asks
+ * sm.IsInvalidChannel (state/daprstate.go:3556-3564: an in-memory cache with a 30-day TTL), FilterUsername, seenInBatch,
+ * and writes ONE pending_edges row per surviving edge with its own INSERT (crawl/runner.go:1247-1306,
+ * state/daprstate.go:3914-3931, sql/validator-schema.sql:54-76); the validator then asks IsInvalidChannel and
+ * IsChannelDiscovered per edge before any HTTP request (crawl/validator.go:205-226).  Here the two exclusion sets are
+ * resident on the GPU next to the dedup set, the batch call drops invalid channels on the way into the dedup set
+ * (TGI_RUN_SKIP_INVALID), and tgi_pending_edges returns every new edge of the slot's last batch as ONE packed row buffer,
+ * already classified the way the validator's two look-ups would classify it.
+ *   tgi_set_add       add keys (32-byte zero-padded names) to a resident set; stamp_sec[i] = when the channel was marked
+ *                     invalid (unix seconds; NULL = now is irrelevant: never expires); re-adding a key keeps the first stamp
+ *   tgi_pending_edges rows in (record, first-insertion) order = the order the reference inserts them; status:
+ *                     TGI_EDGE_PENDING (needs the HTTP check), TGI_EDGE_DUPLICATE (already discovered: validator.go:214-226),
+ *                     TGI_EDGE_INVALID_CACHED (validator.go:205-212; only if the batch ran without TGI_RUN_SKIP_INVALID or
+ *                     the channel was marked invalid in between).  Call between tgi_*_wait / tgi_*_batch and
+ *                     tgi_result_release.  The per-batch constants of a row (batch_id, crawl_id, sequence_id, discovery_time)
+ *                     stay with the caller; source_channel = the name of channel row `chan_idx`.                          */
+#define TGI_SET_INVALID 1     /* invalid_channels (state/daprstate.go:3489-3564)                  */
+#define TGI_SET_DISCOVERED 2  /* discovered_channels (state/base.go:522-528)                      */
+#define TGI_INVALID_TTL_SEC (30 * 24 * 3600)
+#define TGI_EDGE_PENDING 0
+#define TGI_EDGE_DUPLICATE 1
+#define TGI_EDGE_INVALID_CACHED 2
+typedef struct tgi_edge { /* 48 bytes */
+  uint8_t destination[32]; /* destination_channel, lower-cased, zero padded                       */
+  uint64_t record;         /* source record of the batch                                          */
+  uint32_t chan_idx;       /* its channel row: source_channel                                     */
+  uint8_t dest_len;
+  uint8_t source_type;     /* TGI_SRC_*: 'mention' | 'text_url' | 'url' | 'plaintext'             */
+  uint8_t status;          /* TGI_EDGE_*                                                          */
+  uint8_t reserved;
+} tgi_edge;
+int tgi_set_add(tgi_ctx* ctx, int which, const uint8_t* keys32, const int64_t* stamp_sec, uint64_t n);
+int tgi_set_clear(tgi_ctx* ctx, int which);
+int tgi_set_size(tgi_ctx* ctx, int which, uint64_t* n);
+/* the clock tgi_*_batch uses for the invalid-channel TTL (TGI_RUN_SKIP_INVALID); default: never expire */
+int tgi_set_now(tgi_ctx* ctx, int64_t now_sec);
+int tgi_pending_edges(tgi_ctx* ctx, int slot, int64_t now_sec, tgi_edge* rows, uint64_t cap, uint64_t* n);
 
 /* pure helpers exposed for host code and tests (each runs the device code path on tiny inputs) */
 int tgi_filter_usernames(tgi_ctx* ctx, const uint8_t* names, const uint32_t* off, uint64_t n,

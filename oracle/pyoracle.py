@@ -58,6 +58,13 @@ def lib() -> C.CDLL:
         L.orc_frontier_export.restype = C.c_uint64
         L.orc_frontier_export.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_frontier_clear.argtypes = [C.c_void_p]
+        L.orc_set_add.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.orc_set_clear.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_clear.restype = None
+        L.orc_set_now.argtypes = [C.c_void_p, C.c_int64]
+        L.orc_set_now.restype = None
+        L.orc_pending_edges.restype = C.c_uint64
+        L.orc_pending_edges.argtypes = [C.c_void_p, C.POINTER(OrcResultC), C.c_void_p, C.c_uint32, C.c_int64, C.c_void_p, C.c_uint64]
         L.orc_utf16_offset_to_bytes.argtypes = [C.c_char_p, C.c_int64, C.c_int32, C.c_int32,
                                                 C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.orc_filter_username.argtypes = [C.c_char_p, C.c_int64]
@@ -119,8 +126,25 @@ class Oracle:
         rc = lib().orc_telegram_batch(self.h, C.byref(d), run_flags, nthreads, C.byref(r))
         assert rc == 0
         out = result_from_c(r) if copy else (int(r.n), int(r.jsonl_len), int(r.n_links))
-        lib().orc_result_free(C.byref(r))
+        self._last = (r, batch)  # the arrays stay valid until the next batch call (pending_edges reads them)
         return out
+
+    # frontier -> validator hand-off
+    def set_add(self, which, keys32, stamps=None):
+        keys32 = np.ascontiguousarray(keys32, np.uint8).reshape(-1, 32)
+        st = None if stamps is None else np.ascontiguousarray(stamps, np.int64)
+        assert lib().orc_set_add(self.h, which, keys32.ctypes.data, None if st is None else st.ctypes.data, len(keys32)) == 0
+
+    def set_now(self, now_sec):
+        lib().orc_set_now(self.h, now_sec)
+
+    def pending_edges(self, now_sec=0):
+        r, batch = self._last
+        cap = int(r.n_links)
+        rows = np.zeros(cap, abi.EDGE)
+        base = batch.recs.ctypes.data + batch.recs.dtype.fields["chan_idx"][1]
+        m = lib().orc_pending_edges(self.h, C.byref(r), base, batch.recs.dtype.itemsize, now_sec, rows.ctypes.data, cap)
+        return rows[: int(m)]
 
     def youtube(self, batch, run_flags=abi.RUN_JSONL | abi.RUN_LINKS, nthreads=1, copy=True):
         d = batch.descriptor()

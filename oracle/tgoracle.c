@@ -486,6 +486,22 @@ static int fset_insert_h(fset_t* f, const uint8_t* k, uint64_t hash, uint64_t se
   return 1;
 }
 static inline unsigned key_shard(uint64_t hash) { return (unsigned)(hash >> (64 - ORC_SHARD_BITS)); }
+static int64_t fset_find(const fset_t* f, const uint8_t* k) { /* index of k, or -1 */
+  if (!f->nslots) return -1;
+  uint64_t h = key_hash(k) & (f->nslots - 1);
+  while (f->slots[h]) {
+    if (memcmp(f->keys[f->slots[h] - 1], k, 32) == 0) return (int64_t)f->slots[h] - 1;
+    h = (h + 1) & (f->nslots - 1);
+  }
+  return -1;
+}
+/* sm.IsInvalidChannel (state/daprstate.go:3556-3564): in the cache and time.Since(t) < invalidChannelTTL (30 days, :3489) */
+static int is_invalid_channel(const fset_t* inv, const uint8_t* k, int64_t now_sec) {
+  int64_t i = fset_find(inv, k);
+  if (i < 0) return 0;
+  int64_t t = (int64_t)inv->seq[i];
+  return t == 0 || now_sec - t < (int64_t)TGI_INVALID_TTL_SEC;
+}
 
 /* per-thread scratch + result arrays are owned by the context and only grow: after one warm-up call
  * a batch of the same size touches no fresh pages (first-touch page faults would otherwise dominate
@@ -516,6 +532,8 @@ struct orc_ctx {
   char* label;
   fset_t fs[ORC_SHARDS];
   uint64_t seq; /* next global sequence number */
+  fset_t xset[2]; /* frontier -> validator hand-off: invalid channels (seq[] = time marked), discovered channels */
+  int64_t now_sec; /* clock of the invalid-channel TTL in the batch path; 0 = never expire */
   work_t* w;
   int nw;
   buf_t r_status, r_jsonl, r_line_off, r_link_off, r_links;
@@ -541,6 +559,7 @@ void orc_destroy(orc_ctx* c) {
   free(c->r_status.p); free(c->r_jsonl.p); free(c->r_line_off.p); free(c->r_link_off.p); free(c->r_links.p);
   free(c->label);
   for (int i = 0; i < ORC_SHARDS; i++) { free(c->fs[i].keys); free(c->fs[i].seq); free(c->fs[i].slots); }
+  for (int i = 0; i < 2; i++) { free(c->xset[i].keys); free(c->xset[i].seq); free(c->xset[i].slots); }
   free(c);
 }
 void orc_set_clock(orc_ctx* c, int64_t cs, int32_t cn, int64_t ps, int32_t pn) {
@@ -1216,6 +1235,10 @@ static void produce(work_t* w) {
         if (cname && l->len == cname_n && memcmp(l->name, cname, cname_n) == 0) l->flags |= TGI_LF_SELF;
         if (rf & TGI_RUN_FRONTIER) {
           if ((rf & TGI_RUN_SKIP_SELF) && (l->flags & TGI_LF_SELF)) continue;   /* runner.go:1231 */
+          if ((rf & TGI_RUN_SKIP_INVALID) && is_invalid_channel(&w->c->xset[0], l->name, w->c->now_sec)) { /* runner.go:1247 */
+            l->flags |= TGI_LF_INVALID;
+            continue;
+          }
           if ((rf & TGI_RUN_FILTER) && !(l->flags & TGI_LF_FILTER_OK)) continue; /* runner.go:1261 */
           const uint32_t idx = (uint32_t)(w->links.len / sizeof(tgi_link)) + (uint32_t)k;
           buf_put(&w->bucket[key_shard(key_hash(l->name))], &idx, 4);
@@ -1384,4 +1407,45 @@ int orc_generic_batch(orc_ctx* c, const tgi_gm_batch* in, uint32_t run_flags, in
 }
 void orc_result_free(orc_result* r) { /* arrays are context-owned; valid until the next batch call */
   memset(r, 0, sizeof *r);
+}
+
+/* ---- frontier -> validator hand-off ------------------------------------------------------------- */
+int orc_set_add(orc_ctx* c, int which, const uint8_t* keys32, const int64_t* stamp_sec, uint64_t n) {
+  if (which != TGI_SET_INVALID && which != TGI_SET_DISCOVERED) return -1;
+  fset_t* f = &c->xset[which == TGI_SET_INVALID ? 0 : 1];
+  for (uint64_t i = 0; i < n; i++)
+    fset_insert_h(f, keys32 + 32 * i, key_hash(keys32 + 32 * i), (which == TGI_SET_INVALID && stamp_sec) ? (uint64_t)stamp_sec[i] : 0);
+  return 0;
+}
+void orc_set_clear(orc_ctx* c, int which) {
+  fset_t* f = &c->xset[which == TGI_SET_INVALID ? 0 : 1];
+  f->n = 0;
+  if (f->slots) memset(f->slots, 0, f->nslots * sizeof(uint64_t));
+}
+void orc_set_now(orc_ctx* c, int64_t now_sec) { c->now_sec = now_sec; }
+/* The rows the reference would INSERT for the last batch (crawl/runner.go:1264-1306: one edge per outlink that survived
+ * self / invalid / FilterUsername / seenInBatch, in message order), each with the verdict of the validator's two cache
+ * look-ups (crawl/validator.go:205-226).  `r` = the result of that batch, `chan_idx_of` / stride as in the engine. */
+uint64_t orc_pending_edges(orc_ctx* c, const orc_result* r, const void* chan_idx_of, uint32_t stride, int64_t now_sec,
+                           tgi_edge* rows, uint64_t cap) {
+  uint64_t m = 0;
+  for (uint64_t rec = 0; rec < r->n; rec++) {
+    for (uint32_t k = r->link_off[rec]; k < r->link_off[rec + 1]; k++) {
+      const tgi_link* l = &r->links[k];
+      if (!(l->flags & TGI_LF_NEW)) continue;
+      if (m < cap) {
+        tgi_edge* e = &rows[m];
+        memset(e, 0, sizeof *e);
+        memcpy(e->destination, l->name, 32);
+        e->record = rec;
+        e->chan_idx = chan_idx_of ? *(const uint32_t*)((const uint8_t*)chan_idx_of + (size_t)rec * stride) : 0;
+        e->dest_len = l->len;
+        e->source_type = l->src;
+        e->status = is_invalid_channel(&c->xset[0], l->name, now_sec) ? TGI_EDGE_INVALID_CACHED
+                    : fset_find(&c->xset[1], l->name) >= 0 ? TGI_EDGE_DUPLICATE : TGI_EDGE_PENDING;
+      }
+      m++;
+    }
+  }
+  return m;
 }

@@ -67,6 +67,13 @@ uint64_t orc_frontier_size(orc_ctx* c);
 uint64_t orc_frontier_export(orc_ctx* c, uint8_t* keys32, uint64_t cap);
 void orc_frontier_clear(orc_ctx* c);
 
+/* resident exclusion sets + the pending_edges rows of the last batch (see tgi_pending_edges) */
+int orc_set_add(orc_ctx* c, int which, const uint8_t* keys32, const int64_t* stamp_sec, uint64_t n);
+void orc_set_clear(orc_ctx* c, int which);
+void orc_set_now(orc_ctx* c, int64_t now_sec);
+uint64_t orc_pending_edges(orc_ctx* c, const orc_result* r, const void* chan_idx_of, uint32_t stride, int64_t now_sec,
+                           tgi_edge* rows, uint64_t cap);
+
 /* unit-level entry points (each cites the reference function it restates in tgoracle.c) */
 void orc_utf16_offset_to_bytes(const uint8_t* s, int64_t n, int32_t off16, int32_t len16,
                                int64_t* start, int64_t* end);

@@ -123,12 +123,16 @@ def test_reactions_and_comments():
     both(pack_telegram(ms))
 
 
-def test_too_many_reactions_is_a_batch_error(engine):
-    ms = [msg("messageText", "z", reactions=[(f"k{i:02d}", i) for i in range(33)])]
-    from distributed_crawler_b200.engine import EngineError
-    with pytest.raises(EngineError) as ei:
-        engine.telegram(pack_telegram(ms))
-    assert ei.value.code == abi.E_ARG
+def test_big_maps_and_many_links_are_per_record_slow_paths():
+    """No format limits: a reactions map with more than 32 entries (also inside a comment, also with repeated and dirty
+    keys) and a text with thousands of link candidates are processed like any other record."""
+    rs = [(f"k{i % 47:02d}", i) for i in range(100)] + [('q"%d' % i, -i) for i in range(40)] + [("👍", 1), ("", 2), ("👍", 3)]
+    cm = [Comment("big map inside", [(f"c{i:03d}", i) for i in range(70, -1, -1)], 1, 2, "h")]
+    many = " ".join(f"t.me/chan_{i:05d}" for i in range(6000))
+    ms = [msg("messageText", "a", reactions=rs), msg("messageText", "b", reactions=rs[:33], comments=cm),
+          msg("messageText", many), msg("messageText", "t.me/after_many x" * 3, reactions=[("z", 1)] * 40)]
+    ro, rg = both(pack_telegram(ms))
+    assert len(rg.links) >= 6001
 
 
 def test_frontier_across_batches_and_slots():
@@ -266,3 +270,31 @@ def test_tile_emitter_boundaries():
         rnd.shuffle(msgs)
         both(pack_telegram(msgs), ALL)
         both(pack_telegram(msgs[:31]), ALL)
+
+
+def test_malformed_batches_are_rejected(engine):
+    """A batch whose offsets point outside its arrays comes back as TGI_E_ARG (host check for small batches, device
+    check for big ones) instead of an illegal address; the context stays usable."""
+    from distributed_crawler_b200.engine import EngineError
+
+    def broken(n, field, value, idx):
+        c = Corpus(n, profile=2)
+        recs = c.batch.recs.copy()
+        recs[field][idx] = value
+        b = c.batch
+        return type(b)(**{k: (recs if k == "recs" else getattr(b, k)) for k in b.FIELDS}), c
+
+    for n in (500, 200_000):  # host-side and device-side validation
+        for field, value in (("str_off", 1 << 40), ("chan_idx", 1 << 30), ("text_len", 0xFFFFFFF0), ("content_type", 200)):
+            b, keep = broken(n, field, value, n // 2)
+            with pytest.raises(EngineError) as ei:
+                engine.telegram(b, ALL)
+            assert ei.value.code == abi.E_ARG, (n, field)
+        c = Corpus(n, profile=2)
+        eo = c.batch.ent_off.copy()
+        eo[n // 3] = eo[-1] + 5  # not monotonic / past the entity array
+        b = type(c.batch)(**{k: (eo if k == "ent_off" else getattr(c.batch, k)) for k in c.batch.FIELDS})
+        with pytest.raises(EngineError):
+            engine.telegram(b, ALL)
+    ok = Corpus(1000, profile=2)
+    assert engine.telegram(ok.batch, ALL).n == 1000  # still alive
