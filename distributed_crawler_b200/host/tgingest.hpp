@@ -54,6 +54,10 @@ struct Message {  // client.Message + the RPC results the reference resolves per
   std::string Handle = "unknown";       // GetPoster
   uint32_t Channel = 0;                 // row of the channel table
   bool Panics = false;                  // the reference's per-message recover() fired upstream
+  // messageVideo only, the shape processMessageSafely (tdutils.go:188-199) looks at: Ok = everything there (media_url =
+  // the video's remote id); None = no Video / Thumbnail: its error comes before any read, media_url stays ""; Broken = a
+  // thumbnail with a nil file / remote / caption: nil dereference, recovered (:395-405), the message is "failed"
+  enum class VideoShape { Ok, None, Broken } Video = VideoShape::Ok;
 };
 struct ChannelInfo {
   std::string Title, Name, Username;    // chat.Title, channelName argument, ActiveUsernames[0] ("" = private)
@@ -78,6 +82,9 @@ class Batch {
   void Add(const Message& m) {
     tgi_tg_rec r{};
     std::string alt = m.Alt;
+    const bool video = m.ContentType == TGI_CT_VIDEO;
+    const std::string media = video && m.Video != Message::VideoShape::Ok ? std::string() : m.Media;
+    const bool panics = m.Panics || (video && m.Video == Message::VideoShape::Broken);
     r.id = m.Id;
     r.chat_id = m.ChatId;
     r.media_album_id = m.MediaAlbumId;
@@ -88,12 +95,12 @@ class Batch {
     r.chan_idx = m.Channel;
     r.text_len = m.Text ? (uint32_t)m.Text->Text.size() : 0u;
     r.alt_len = (uint32_t)alt.size();
-    r.media_len = (uint16_t)m.Media.size();
+    r.media_len = (uint16_t)media.size();
     r.handle_len = (uint16_t)m.Handle.size();
     r.content_type = m.ContentType;
-    r.flags = (uint8_t)((m.Text ? TGI_RF_HAS_TEXT : 0) | (m.Comments ? 0 : TGI_RF_COMMENTS_NIL) | (m.Panics ? TGI_RF_PANIC : 0));
+    r.flags = (uint8_t)((m.Text ? TGI_RF_HAS_TEXT : 0) | (m.Comments ? 0 : TGI_RF_COMMENTS_NIL) | (panics ? TGI_RF_PANIC : 0));
     if (m.Text) strs_ += m.Text->Text;
-    strs_ += alt + m.Media + m.Handle;
+    strs_ += alt + media + m.Handle;
     if (m.Text)
       for (const TextEntity& e : m.Text->Entities) {
         tgi_entity en{};

@@ -61,6 +61,12 @@ class Message:  # client.Message + pre-resolved RPC results
     handle: str | bytes = "unknown"
     channel: int = 0
     panics: bool = False
+    # messageVideo only — the shape processMessageSafely (tdutils.go:188-199) looks at.  "ok": Video, Thumbnail, the
+    # two files and the caption are all there (media_url = the video's remote id); "none": no Video / no Thumbnail —
+    # the function returns its error before reading anything, media_url stays ""; "broken": a thumbnail is present
+    # but Thumbnail.File / File.Remote / Video.Video / Video.Video.Remote / Caption is nil — nil dereference, recovered
+    # (:395-405), the message is marked "failed"
+    video_shape: str = "ok"
 
 
 @dataclass
@@ -199,12 +205,14 @@ def pack_telegram(messages: list[Message], channels: list[Channel] | None = None
             alt = _b(m.content_type)
         text = _b(m.text.text) if m.text is not None else b""
         media, handle = _b(m.media), _b(m.handle)
+        if m.content_type == "messageVideo" and m.video_shape != "ok":
+            media = b""
         flags = 0
         if m.text is not None:
             flags |= abi.RF_HAS_TEXT
         if m.comments is None:
             flags |= abi.RF_COMMENTS_NIL
-        if m.panics:
+        if m.panics or (m.content_type == "messageVideo" and m.video_shape == "broken"):
             flags |= abi.RF_PANIC
         r["id"], r["chat_id"], r["media_album_id"] = m.id, m.chat_id, m.media_album_id
         r["str_off"] = len(strs)

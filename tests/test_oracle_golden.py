@@ -248,3 +248,18 @@ def test_oracle_generic_message_sparse_post():
         assert doc["platform_name"] == "telegram" and doc["channel_name"] == doc["channel_id"] and doc["views_count"] == m.views
         assert doc["channel_data"]["published_at"] == "0001-01-01T00:00:00Z" and doc["inner_link"] == {}
         assert doc["performance_scores"] == {"likes": None, "shares": None, "comments": None, "views": 0}
+
+
+def test_message_video_shapes(oracle):
+    """processMessageSafely (tdutils.go:188-199): no thumbnail -> its error comes before any read, media_url stays "" and
+    the description is still the caption; a thumbnail with a nil file / caption -> nil dereference, recovered, "failed"."""
+    import json
+    from distributed_crawler_b200.pack import FormattedText, Message, pack_telegram
+    ms = [Message(content_type="messageVideo", text=FormattedText("cap t.me/fromcaption"), media="VIDEOID", video_shape="ok"),
+          Message(content_type="messageVideo", text=FormattedText("cap t.me/fromcaption"), media="VIDEOID", video_shape="none"),
+          Message(content_type="messageVideo", text=None, media="VIDEOID", video_shape="broken")]
+    r = oracle.telegram(pack_telegram(ms), abi.RUN_JSONL | abi.RUN_LINKS)
+    assert list(r.status) == [abi.ST_EMITTED, abi.ST_EMITTED, abi.ST_FAILED]
+    a, b = json.loads(r.line(0)), json.loads(r.line(1))
+    assert a["media_url"] == "VIDEOID" and b["media_url"] == "" and a["description"] == b["description"] == "cap t.me/fromcaption"
+    assert r.line(2) == b"" and [n for n, _ in r.record_links(1)] == [b"fromcaption"]
