@@ -14,6 +14,7 @@
 #include "tg_walk.cuh"
 #include "tg_scan.cuh"
 #include "tg_tile.cuh"
+#include "tg_lane.cuh"
 #include "yt_walk.cuh"
 #include "gm_walk.cuh"
 #include "yt_lane.cuh"
@@ -97,6 +98,7 @@ struct ParseOut {
   uint32_t* xlen;        // [n][8] emitted lengths of the variable pieces (XL_*)
   unsigned long long* var_total;  // sum of the variable pieces' lengths (statistics)
   unsigned long long* slow_total; // records flagged XLF_SLOW
+  int fast_text;                  // split pipeline: measure descriptions with the 512-byte strip scanner (A/B: TGI_FAST_TEXT=0)
   tgi_link* arena;
   uint32_t arena_cap;
   uint32_t* cursor;      // arena allocation cursor (keeps counting past arena_cap)
@@ -175,6 +177,30 @@ DEVI void parse_one_record(const TgBatchDev& b, const CfgDev& cfg, const ParseOu
 //   tg_ent_map_kernel   = UTF-16 entity offsets -> byte ranges            } records WITH entities (a quarter of the
 //   tg_parse_ent_kernel = status + links of those records                  } corpus; lanes pick them out of groups of 32)
 //   tg_scan_kernel      = everything else in ONE pass over the text (below)
+// Split pipeline (TGI_PIPE=split): status + links of the records WITHOUT entities, one warp per record; the size kernel
+// below then walks the text again.
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) {
+  int wid = threadIdx.x >> 5;
+  uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
+    // The chain header -> string offset -> text is two DRAM round trips per record and this kernel has little else to
+    // do (long_scoreboard 9 cycles per issue): read the NEXT record's header now, touch its text at the bottom of
+    // the loop, when that load has long completed.
+    const uint64_t rn = r + nwarps;
+    unsigned long long nx_off = 0;
+    uint32_t nx_len = 0;
+    if (rn < b.n) {
+      asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(nx_off) : "l"(&b.recs[rn].str_off));
+      asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(nx_len) : "l"(&b.recs[rn].text_len));
+    }
+    if (b.ent_off[r + 1] == b.ent_off[r])  // the others: tg_parse_ent_kernel
+      parse_one_record<false>(b, cfg, o, r, load_rec_view(b, r));
+    if (rn < b.n) {
+      const uint32_t off = (uint32_t)lane_id() * 128u;
+      if (off < nx_len + 127u && off < 2048u) asm volatile("prefetch.global.L1 [%0];" ::"l"(b.strs + nx_off + off));
+    }
+  }
+}
 __global__ void __launch_bounds__(CTA_THREADS, 4) tg_ent_map_kernel(TgBatchDev b, ParseOut o) {
   const int wid = threadIdx.x >> 5, l = lane_id();
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
@@ -416,6 +442,147 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_scan_kernel(TgBatchDev b, C
   if (l == 0 && nslow) atomicAdd(o.slow_total, (unsigned long long)nslow);
 }
 
+// Split pipeline (TGI_PIPE=split): the line length only; links come from the parse kernels.
+// The same sizes, 32 records per warp: every lane sizes the small pieces of its own record (numbers,
+// handle / media strings, comments, reactions, outlinks); only the message text, the one long string,
+// is measured by the whole warp, record after record; the rare complicated pieces (a comment list, a
+// reactions map that is not "simple") go through the warp-wide routines as well.
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_lane_kernel(TgBatchDev b, CfgDev cfg, ParseOut o) {
+  const int wid = threadIdx.x >> 5, l = lane_id();
+  const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  uint64_t var_sum = 0;
+  uint32_t nslow = 0;
+  for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
+    uint64_t r = g * 32 + l;
+    bool active = r < b.n;
+    if (!active) r = b.n - 1;
+    active = active && o.status[r] == TGI_ST_EMITTED;
+    if (!__any_sync(FULL, active)) continue;
+    TgWalkArgs a;
+    a.b = &b;
+    a.cfg = &cfg;
+    a.r = r;
+    a.v = load_rec_view(b, r);
+    a.links = o.arena + o.link_start[r];
+    a.n_links = active ? o.link_count[r] : 0u;
+    const tgi_tg_rec* rec = a.v.rec;
+    const ChanDerived cd = b.chan_derived[rec->chan_idx];
+    const TgDerived d = tg_derive(a, cd);
+    uint32_t xl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t tot = 0;
+    bool warp_comments = false, warp_map = false;
+    const uint32_t r0 = b.react_off[r], nr = b.react_off[r + 1] - r0;
+    if (active && !(cfg.flags & CFGDEV_CLOCK_INVALID)) {
+      uint32_t L[8] = {ndigits_i64(rec->id / 1048576), ndigits_i64(rec->chat_id), ndigits_i64(rec->view_count),
+                       ndigits_i64(rec->share_count), ndigits_i64(d.ncomments), cfg.tz == 0 ? 22u : 27u, 0, 0};
+      uint32_t chan[4] = {cd.user_len, cd.name_len, cd.title_len, cd.cdata_len};
+      uint32_t cf[4] = {cfg.label_len, cfg.created_tg_len, cfg.created_yt_len, cfg.capture_len};
+      tot = tg_size_fixed(L, chan, cf, d.has_user, d.album);
+      tot += a.v.ct == TGI_CT_OTHER ? 0u : (uint32_t)kPostTypeLen[a.v.ct];
+      if (a.v.ct == TGI_CT_OTHER) xl[XL_ALT] = thread_esc_len(a.v.alt, a.v.alt_len);
+      if (d.has_media) xl[XL_MEDIA] = thread_esc_len(a.v.media, a.v.media_len);
+      xl[XL_HANDLE] = thread_esc_len(a.v.handle, a.v.handle_len);
+      if (d.comments_nil) xl[XL_COMMENTS] = 4;
+      else if (d.c1 == d.c0) xl[XL_COMMENTS] = 2;
+      else warp_comments = true;
+      if (nr == 0) {
+        xl[XL_REACTIONS] = 2;
+        xl[XL_FLAGS] = XLF_SIMPLE_MAP;
+      } else if (nr <= LANE_MAP_MAX) {  // size_reaction_map, one lane: "key":n , ... ; simple = short clean keys
+        uint32_t sz = 2u, live = 0;
+        bool simple = true;
+        for (uint32_t j = 0; j < nr; j++) {
+          const tgi_reaction rc = b.reacts[r0 + j];
+          const uint8_t* kp = b.aux + rc.emoji_off;
+          const uint32_t el = thread_esc_len(kp, rc.emoji_len);
+          simple = simple && el == rc.emoji_len && rc.emoji_len >= 1 && rc.emoji_len <= 8;
+          bool last = true;  // a later entry with the same key overwrites this one (Go map assignment)
+          for (uint32_t i = j + 1; i < nr; i++) {
+            const tgi_reaction ri = b.reacts[r0 + i];
+            if (key_cmp(b.aux + ri.emoji_off, ri.emoji_len, kp, rc.emoji_len) == 0) last = false;
+          }
+          if (last) {
+            sz += 3u + el + ndigits_i64(rc.count);
+            live++;
+          }
+        }
+        if (simple) {
+          xl[XL_REACTIONS] = sz + (live - 1u);
+          xl[XL_FLAGS] = XLF_SIMPLE_MAP;
+        } else {
+          warp_map = true;
+        }
+      } else {
+        warp_map = true;
+      }
+      if (a.n_links) {
+        uint32_t s = a.n_links - 1u;
+        for (uint32_t k = 0; k < a.n_links; k++) s += a.links[k].len + 2u;
+        xl[XL_OUTLINKS] = s;
+      }
+    }
+    // the message text (or the other description sources), one record at a time, all lanes
+    const bool sized = active && !(cfg.flags & CFGDEV_CLOCK_INVALID);
+    uint32_t todo = __ballot_sync(FULL, sized && d.desc_len != 0);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint8_t* p = (const uint8_t*)__shfl_sync(FULL, (unsigned long long)(uintptr_t)d.desc, src);
+      const uint32_t n = __shfl_sync(FULL, d.desc_len, src);
+      bool ex = false;
+      uint32_t e;
+      if (o.fast_text) {  // 512-byte strips, SWAR only; anything it cannot vouch for goes to the exact path (tg_scan.cuh)
+        const TextScan ts = warp_text_scan<true, false>(p, n);
+        e = ts.exact ? warp_esc_len(p, n, &ex) : ts.esc;
+      } else {
+        e = warp_esc_len(p, n, &ex);
+      }
+      if (l == src) {
+        xl[XL_DESC] = e;
+        if (ex) xl[XL_FLAGS] |= XLF_DESC_EXACT;
+      }
+    }
+    todo = __ballot_sync(FULL, warp_comments);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t e = size_tg_comments(b, __shfl_sync(FULL, d.c0, src), __shfl_sync(FULL, d.c1, src));
+      if (l == src) xl[XL_COMMENTS] = e;
+    }
+    todo = __ballot_sync(FULL, warp_map);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t q0 = __shfl_sync(FULL, r0, src), qn = __shfl_sync(FULL, nr, src);
+      uint32_t simple = 0;
+      const uint32_t e = size_reaction_map(b.reacts, q0, q0 + qn, b.aux, &simple);
+      if (l == src) {
+        xl[XL_REACTIONS] = e;
+        xl[XL_FLAGS] = (xl[XL_FLAGS] & ~XLF_SIMPLE_MAP) | (simple ? XLF_SIMPLE_MAP : 0u);
+      }
+    }
+    if (active) {
+      uint32_t var = 0;
+#pragma unroll
+      for (int j = 0; j < XL_COUNT; j++) var += xl[j];
+      const uint32_t llen = sized ? tot + var : 0u;
+      if (llen + (tg_needs_scratch(nr, d.comments_nil, d.c0, d.c1) ? TILE_SCRATCH : 0u) > TILE_BUF - 16u) {  // tile emitter only
+        xl[XL_FLAGS] |= XLF_SLOW;
+        nslow++;
+      }
+      *(uint4*)(o.xlen + r * 8) = make_uint4(xl[0], xl[1], xl[2], xl[3]);
+      *(uint4*)(o.xlen + r * 8 + 4) = make_uint4(xl[4], xl[5], xl[6], xl[7]);
+      if (llen == 0) o.status[r] = TGI_ST_NOLINE;
+      o.linelen[r] = llen;
+      if (llen) var_sum += var;
+    }
+  }
+  for (int dd = 16; dd; dd >>= 1) var_sum += __shfl_down_sync(FULL, var_sum, dd);
+  if (l == 0 && var_sum) atomicAdd(o.var_total, (unsigned long long)var_sum);
+  nslow = warp_sum(nslow);
+  if (l == 0 && nslow) atomicAdd(o.slow_total, (unsigned long long)nslow);
+}
+
 // ---- emit --------------------------------------------------------------------------------------------------------
 struct EmitIn {
   const uint8_t* status;
@@ -423,10 +590,13 @@ struct EmitIn {
   const uint32_t* link_start;
   const uint32_t* link_count;
   const uint32_t* xlen;  // [n][8] lengths of the variable pieces + flags
+  uint32_t* xpos;        // [n][8] offsets of the variable pieces inside the line (lane pipeline: written by the lane emitter)
   const tgi_link* arena;
   uint8_t* out;
   int* err;
-  unsigned long long* counters;  // [0] JSONL bytes written by the tile kernel, [1] source bytes it read from HBM
+  uint32_t lane_text_max;        // lane pipeline: see emit_tg_escapes
+  int esc_staged;                // lane pipeline: escaped strings go through shared memory + a bulk store (A/B: TGI_ESC_STAGED=0)
+  unsigned long long* counters;  // [0] JSONL bytes written by the main emit kernel, [1] source bytes it read from HBM
 };
 
 // Tile emitter (tg_tile.cuh): one warp per 32 consecutive records, 16 prepared at a time.  MINB = resident CTAs per SM
@@ -552,6 +722,118 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tg_emit_slow_kernel(TgBatchDev
       emit_reaction_map(line + xp[XL_REACTIONS], &sh.ms[wid], b.reacts, b.react_off[r], b.react_off[r + 1], b.aux);
       const uint32_t nl = in.link_count[r];
       if (nl) emit_tg_outlinks(line + xp[XL_OUTLINKS], in.arena + in.link_start[r], nl);
+      __syncwarp();
+    }
+  }
+}
+
+// ---- lane pipeline (TGI_EMIT=lane): one LANE per record + the two clean-up kernels ---------------------------------
+// the same job, one LANE per record (tg_lane.cuh): 32 records per warp task
+__global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_lane_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
+  extern __shared__ __align__(128) uint8_t lane_smem[];
+  LaneShared& sh = *(LaneShared*)lane_smem;
+  static_assert(LANE_WARPS == WARPS_PER_CTA, "one field row block per warp");
+  lane_shared_fill(sh);
+  __syncthreads();
+  const int wid = threadIdx.x >> 5, l = lane_id();
+  const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  LaneStream s;
+  ls_init(s, smem_addr(sh.stage[wid][l]));
+  uint64_t bytes_out = 0, bytes_in = 0;
+  for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
+    uint64_t r = g * 32 + l;
+    bool active = r < b.n;
+    if (!active) r = b.n - 1;
+    active = active && in.status[r] == TGI_ST_EMITTED;
+    if (!__any_sync(FULL, active)) continue;
+    emit_tg_lane(sh, sh.rows[wid][l], s, b, cfg, r, active, in.out, in.line_off, in.xlen + r * 8, in.xpos + r * 8,
+                 in.arena + in.link_start[r], active ? in.link_count[r] : 0u, in.err, bytes_out, bytes_in);
+  }
+  for (int dd = 16; dd; dd >>= 1) {
+    bytes_out += __shfl_down_sync(FULL, bytes_out, dd);
+    bytes_in += __shfl_down_sync(FULL, bytes_in, dd);
+  }
+  if (l == 0) {
+    atomicAdd(in.counters, (unsigned long long)bytes_out);
+    atomicAdd(in.counters + 1, (unsigned long long)bytes_in);
+  }
+}
+
+// The esc and maps kernels take what the lane emitter left: each lane first checks one record of a
+// group of 32, then the warp walks the records that need it (most do not).
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_esc_kernel(TgBatchDev b, EmitIn in) {
+  __shared__ __align__(128) uint8_t stage[WARPS_PER_CTA][ESC_STAGE + 32];  // escaped strings are assembled here (emit_tg_escapes)
+  const int wid = threadIdx.x >> 5, l = lane_id();
+  const uint32_t stage_s = in.esc_staged ? smem_addr(stage[wid]) : 0u;
+  const bool lane_mode = in.lane_text_max != 0xffffffffu;
+  const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
+    const uint64_t r = g * 32 + l;
+    bool need = false;
+    if (r < b.n && in.status[r] == TGI_ST_EMITTED) {
+      need = true;
+      if (lane_mode) {  // same rule as emit_tg_lane: clean and short strings are already in place
+        const tgi_tg_rec* rec = &b.recs[r];
+        const uint4 xl = *(const uint4*)(in.xlen + r * 8);
+        const uint32_t ct = rec->content_type;
+        const bool text_desc = ct == TGI_CT_TEXT || ct == TGI_CT_VIDEO || ct == TGI_CT_PHOTO || ct == TGI_CT_ANIMATION;
+        const uint32_t dlen = text_desc ? ((rec->flags & TGI_RF_HAS_TEXT) ? rec->text_len : 0u)
+                                        : (ct == TGI_CT_ANIMATED_EMOJI || ct == TGI_CT_POLL || ct == TGI_CT_GIVEAWAY ||
+                                           ct == TGI_CT_PAID_MEDIA || ct == TGI_CT_DOCUMENT) ? rec->alt_len : 0u;
+        auto left = [&](uint32_t x, uint32_t n) { return x != 0 && !(x == n && n <= in.lane_text_max); };
+        need = left(xl.x, dlen) || left(xl.y, rec->media_len) || left(xl.z, rec->handle_len) || left(xl.w, rec->alt_len);
+      }
+    }
+    uint32_t todo = __ballot_sync(FULL, need);
+    while (todo) {
+      const uint64_t rr = g * 32 + (uint32_t)(__ffs(todo) - 1);
+      todo &= todo - 1;
+      TgWalkArgs a;
+      a.b = &b;
+      a.cfg = nullptr;
+      a.r = rr;
+      a.v = load_rec_view(b, rr);
+      emit_tg_escapes(in.out + in.line_off[rr], a, in.xlen + rr * 8, in.xpos + rr * 8, in.lane_text_max, stage_s);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_maps_kernel(TgBatchDev b, EmitIn in) {
+  __shared__ MapScratch mss[WARPS_PER_CTA];
+  const int wid = threadIdx.x >> 5, l = lane_id();
+  const bool lane = in.lane_text_max != 0xffffffffu;  // the lane emitter ran: it wrote the simple cases (tg_lane.cuh)
+  const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
+    const uint64_t rl = g * 32 + l;
+    bool need = false;
+    if (rl < b.n && in.status[rl] == TGI_ST_EMITTED) {
+      need = true;
+      if (lane) {
+        const bool list = !(b.recs[rl].flags & TGI_RF_COMMENTS_NIL) && b.comment_off[rl + 1] != b.comment_off[rl];
+        const bool map = b.react_off[rl + 1] != b.react_off[rl] && !(in.xlen[rl * 8 + XL_FLAGS] & XLF_SIMPLE_MAP);
+        need = list || map || in.link_count[rl] > LANE_LINKS_MAX;
+      }
+    }
+    uint32_t todo = __ballot_sync(FULL, need);
+    while (todo) {
+      const uint64_t r = g * 32 + (uint32_t)(__ffs(todo) - 1);
+      todo &= todo - 1;
+      uint8_t* line = in.out + in.line_off[r];
+      const uint32_t* xp = in.xpos + r * 8;
+      const bool comments_nil = (b.recs[r].flags & TGI_RF_COMMENTS_NIL) != 0;
+      const uint32_t c0 = b.comment_off[r], c1 = b.comment_off[r + 1];
+      if (comments_nil) {
+        if (!lane) gcopy_g(line + xp[XL_COMMENTS], (const uint8_t*)kNullLit, 4);
+      } else if (c1 == c0) {
+        if (!lane) gput2(line + xp[XL_COMMENTS], '[', ']');
+      } else {
+        emit_tg_comments(line + xp[XL_COMMENTS], &mss[wid], b, c0, c1);
+      }
+      const uint32_t r0 = b.react_off[r], r1 = b.react_off[r + 1];
+      if (!(lane && (r1 == r0 || (in.xlen[r * 8 + XL_FLAGS] & XLF_SIMPLE_MAP))))
+        emit_reaction_map(line + xp[XL_REACTIONS], &mss[wid], b.reacts, r0, r1, b.aux);
+      const uint32_t nl = in.link_count[r];
+      if (nl && !(lane && nl <= LANE_LINKS_MAX)) emit_tg_outlinks(line + xp[XL_OUTLINKS], in.arena + in.link_start[r], nl);
       __syncwarp();
     }
   }

@@ -158,8 +158,8 @@ DEVI void copy_gs_deep(uint32_t dst, const uint8_t* src, uint32_t n) {
   }
 }
 
-// map[string]int that the size pass flagged XLF_SIMPLE_MAP: <= LANE_MAP_MAX entries, distinct keys of 1..8 bytes that
-// need no escaping.  One lane per entry: two loads (entry, key), rank and offset by shuffles, direct byte stores.
+// map[string]int that the size pass flagged XLF_SIMPLE_MAP: <= LANE_MAP_MAX entries, keys of 1..8 bytes that need no
+// escaping (repeated keys allowed: the last one wins).  One lane per entry: two loads (entry, key), rank and offset by shuffles, direct byte stores.
 DEVI void tile_emit_simple_map(uint32_t dst, const tgi_reaction* reacts, uint32_t r0, uint32_t nr, const uint8_t* aux) {
   const uint32_t l = lane_id();
   uint32_t k0 = 0, k1 = 0, kl = 0, len = 0;
@@ -176,17 +176,26 @@ DEVI void tile_emit_simple_map(uint32_t dst, const tgi_reaction* reacts, uint32_
     len = 4u + kl + ndigits_i64(cnt);  // "key":n and a comma or the closing brace
   }
   const uint64_t ck = ((uint64_t)__byte_perm(k0, 0, 0x0123) << 32) | __byte_perm(k1, 0, 0x0123);  // bytewise order
+  // a later entry with the same key overwrites this one (Go map assignment, tdutils.go:598); keys hold no NUL byte,
+  // so equal compare keys are equal keys
+  bool live = l < nr;
+  for (uint32_t j = 1; j < nr; j++) {
+    const uint64_t cj = __shfl_sync(FULL, ck, (int)j);
+    if (l < j && cj == ck) live = false;
+  }
+  if (!live) len = 0;
+  const uint32_t nlive = __popc(__ballot_sync(FULL, live));
   uint32_t off = 1, rank = 0;
   for (uint32_t j = 0; j < nr; j++) {
     const uint64_t cj = __shfl_sync(FULL, ck, (int)j);
     const uint32_t lj = __shfl_sync(FULL, len, (int)j);
-    if (cj < ck) {
+    if (lj && cj < ck) {
       off += lj;
       rank++;
     }
   }
   if (l == 0) sts8(dst, '{');
-  if (l < nr) {
+  if (live) {
     uint32_t d = dst + off;
     sts8(d, '"');
     for (uint32_t i = 0; i < kl; i++) sts8(d + 1 + i, (i < 4 ? k0 >> (8u * i) : k1 >> (8u * (i - 4u))));
@@ -206,7 +215,7 @@ DEVI void tile_emit_simple_map(uint32_t dst, const tgi_reaction* reacts, uint32_
       sts8(d + i, '0' + (v - q * 10u));
       v = q;
     }
-    sts8(d + nd, rank + 1 == nr ? '}' : ',');
+    sts8(d + nd, rank + 1 == nlive ? '}' : ',');
   }
 }
 

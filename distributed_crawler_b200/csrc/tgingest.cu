@@ -103,7 +103,7 @@ struct Slot {
       d_chans, d_chan_strs;
   // device intermediates / outputs
   DevBuf d_chan_derived, d_chan_len, d_chan_off, d_chan_blob, d_status, d_linelen, d_line_off,
-      d_link_start, d_link_count, d_xlen, d_arena, d_lstate, d_rec_new, d_new_off, d_link_off, d_links_out,
+      d_link_start, d_link_count, d_xlen, d_xpos, d_arena, d_lstate, d_rec_new, d_new_off, d_link_off, d_links_out,
       d_link_off32, d_btable, d_tiles, d_scalars, d_jsonl, d_url_start, d_url_count, d_urls, d_ent_range;
   // pinned host outputs
   HostBuf h_status, h_line_off, h_jsonl, h_link_off, h_links, h_scalars;
@@ -625,6 +625,10 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     po.xlen = s.d_xlen.as<uint32_t>();
     po.var_total = (unsigned long long*)(dsc + SC_LONG);
     po.slow_total = (unsigned long long*)(dsc + SC_SLOW);
+    {
+      static const bool fast_text = !(getenv("TGI_FAST_TEXT") && !strcmp(getenv("TGI_FAST_TEXT"), "0"));
+      po.fast_text = fast_text ? 1 : 0;
+    }
     po.arena = s.d_arena.as<tgi_link>();
     po.arena_cap = (uint32_t)arena_cap;
     po.cursor = (uint32_t*)(dsc + SC_CURSOR);
@@ -642,10 +646,20 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
         tg_parse_ent_kernel<<<ge, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
         launches += 2;
       }
-      // then ONE pass over every record: status, plaintext links, line length
-      if (want_json) tg_scan_kernel<true><<<ge, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
-      else tg_scan_kernel<false><<<ge, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
-      launches++;
+      static const bool split = [] { const char* e = getenv("TGI_SCAN"); return !(e && !strcmp(e, "fused")); }();  // default: split
+      if (!split) {
+        // then ONE pass over every record: status, plaintext links, line length
+        if (want_json) tg_scan_kernel<true><<<ge, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
+        else tg_scan_kernel<false><<<ge, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
+        launches++;
+      } else {  // A/B: the round-1 split (links of the records without entities, then the sizes: the text is read twice)
+        tg_parse_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
+        launches++;
+        if (want_json) {
+          tg_size_lane_kernel<<<ge, CTA_THREADS, 0, st>>>(b, cfg, po);
+          launches++;
+        }
+      }
       CK(cudaEventRecord(s.ev_p1, st));
     }
     if (want_json) {
@@ -694,26 +708,48 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       ei.out = s.d_jsonl.as<uint8_t>();
       ei.err = (int*)(dsc + SC_CURSOR) + 1;
       ei.counters = (unsigned long long*)(dsc + SC_LANE_OUT);
+      ei.xpos = nullptr;
+      ei.lane_text_max = 0;
+      ei.esc_staged = 0;
+      static const bool lane_pipe = [] { const char* e = getenv("TGI_EMIT"); return !(e && !strcmp(e, "tile")); }();  // default: lane
       static const int tile_ctas = getenv("TGI_TILE_CTAS") ? atoi(getenv("TGI_TILE_CTAS")) : 3;  // A/B: register budget of the tile kernel
       static const bool attr_set = [] {
         return cudaFuncSetAttribute(tg_emit_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess &&
                cudaFuncSetAttribute(tg_emit_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess &&
-               cudaFuncSetAttribute(tg_emit_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SlowShared)) == cudaSuccess;
+               cudaFuncSetAttribute(tg_emit_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SlowShared)) == cudaSuccess &&
+               cudaFuncSetAttribute(tg_emit_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LaneShared)) == cudaSuccess;
       }();
-      if (!attr_set) { set_err(c, "cannot reserve %zu bytes of shared memory for the tile emitter", sizeof(TileShared)); return TGI_E_CUDA; }
+      if (!attr_set) { set_err(c, "cannot reserve %zu bytes of shared memory for the emitter", sizeof(TileShared)); return TGI_E_CUDA; }
       const uint64_t groups = (n + 31) / 32;
       const uint64_t ctas = (groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
       CK(cudaEventRecord(s.ev_e0, st));
-      // one CTA per SM slot (3 resident CTAs per SM by shared memory), persistent over the record groups
-      unsigned gt = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * (tile_ctas == 2 ? 2 : 3));
-      if (tile_ctas == 2) tg_emit_tile_kernel<2><<<gt, CTA_THREADS, sizeof(TileShared), st>>>(b, cfg, ei);
-      else tg_emit_tile_kernel<3><<<gt, CTA_THREADS, sizeof(TileShared), st>>>(b, cfg, ei);
-      CK(cudaEventRecord(s.ev_f1, st));
-      launches++;
-      if (hsc[SC_SLOW]) {  // lines longer than a tile buffer (counted by the size pass)
-        unsigned gsl = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * 2);
-        tg_emit_slow_kernel<<<gsl, CTA_THREADS, sizeof(SlowShared), st>>>(b, cfg, ei);
+      if (lane_pipe) {  // one LANE per record (tg_lane.cuh) + the two clean-up kernels
+        CK(s.d_xpos.ensure(n * 32));
+        ei.xpos = s.d_xpos.as<uint32_t>();
+        ei.lane_text_max = LANE_TEXT_MAX;
+        {
+          static const bool staged = !(getenv("TGI_ESC_STAGED") && !strcmp(getenv("TGI_ESC_STAGED"), "0"));
+          ei.esc_staged = staged ? 1 : 0;
+        }
+        unsigned gl = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * 3);
+        tg_emit_lane_kernel<<<gl, CTA_THREADS, sizeof(LaneShared), st>>>(b, cfg, ei);
+        CK(cudaEventRecord(s.ev_f1, st));
+        unsigned gg = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * 8);
+        tg_emit_esc_kernel<<<gg, CTA_THREADS, 0, st>>>(b, ei);
+        tg_emit_maps_kernel<<<gg, CTA_THREADS, 0, st>>>(b, ei);
+        launches += 3;
+      } else {
+        // one CTA per SM slot (3 resident CTAs per SM by shared memory), persistent over the record groups
+        unsigned gt = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * (tile_ctas == 2 ? 2 : 3));
+        if (tile_ctas == 2) tg_emit_tile_kernel<2><<<gt, CTA_THREADS, sizeof(TileShared), st>>>(b, cfg, ei);
+        else tg_emit_tile_kernel<3><<<gt, CTA_THREADS, sizeof(TileShared), st>>>(b, cfg, ei);
+        CK(cudaEventRecord(s.ev_f1, st));
         launches++;
+        if (hsc[SC_SLOW]) {  // lines longer than a tile buffer (counted by the size pass)
+          unsigned gsl = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * 2);
+          tg_emit_slow_kernel<<<gsl, CTA_THREADS, sizeof(SlowShared), st>>>(b, cfg, ei);
+          launches++;
+        }
       }
       CK(cudaEventRecord(s.ev_e1, st));
     }
@@ -1119,7 +1155,7 @@ void tgi_destroy(tgi_ctx* c) {
     DevBuf* db[] = {&s.d_recs, &s.d_strs, &s.d_ent_off, &s.d_ents, &s.d_react_off, &s.d_reacts, &s.d_comment_off,
                     &s.d_comments, &s.d_aux, &s.d_chans, &s.d_chan_strs, &s.d_chan_derived, &s.d_chan_len,
                     &s.d_chan_off, &s.d_chan_blob, &s.d_status, &s.d_linelen, &s.d_line_off, &s.d_link_start,
-                    &s.d_link_count, &s.d_xlen, &s.d_arena, &s.d_lstate, &s.d_rec_new, &s.d_new_off, &s.d_link_off,
+                    &s.d_link_count, &s.d_xlen, &s.d_xpos, &s.d_arena, &s.d_lstate, &s.d_rec_new, &s.d_new_off, &s.d_link_off,
                     &s.d_links_out, &s.d_link_off32, &s.d_btable, &s.d_tiles, &s.d_scalars, &s.d_jsonl,
                     &s.d_url_start, &s.d_url_count, &s.d_urls, &s.d_ent_range};
     for (DevBuf* d : db) d->release();
