@@ -289,7 +289,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
-    numa = bind_numa(local) if world > 1 else None
+    numa = bind_numa(local)  # pinned result / staging pages on the GPU's own NUMA node, also at N = 1
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -473,17 +473,18 @@ def main():
         if want_json:
             # whole step: every input byte read once, every output byte written once, 8 B line offset
             alg_bytes = in_bytes + jsonl_len + 8 * (n + 1)
-            kname = "yt_emit_tile_kernel" if is_yt else "tg_emit_tile_kernel"
-            # the emit kernel: per record it reads the header (64 B), the line offset (8 B) and the piece lengths of the
-            # size pass (32 B), reads every source byte it copies and writes every JSONL byte; both sums are counted by
-            # the kernel itself (tgi_result.main_bytes_in / main_bytes_out)
-            k_alg = (acc.lane_out + acc.lane_in) // args.steps
+            kname = "yt_emit_lane_kernel" if is_yt else "tg_emit_lane_kernel"
+            # the main emit kernel (one lane per record): per record it reads the header (64 B), the line offset (8 B) and
+            # the piece lengths of the size pass (32 B), writes the piece offsets (32 B), reads every source byte it copies
+            # and writes the JSONL bytes it is responsible for; both sums are counted by the kernel itself
+            # (tgi_result.main_bytes_in / main_bytes_out).  YouTube: the lane writer does not count: line bytes + inputs.
+            k_alg = (acc.lane_out + acc.lane_in) // args.steps + n * (64 + 8 + 32 + 32) if not is_yt else in_bytes + jsonl_len
             k_ms = per("main")
         else:
             # link-extract + dedup: mini header 24 B + text + entities + entity URLs read once,
             # 32 B key write + 64 B hash-slot read-modify-write per link reaching the set
             alg_bytes = sum(24 * c.batch.n + c.batch.strs.nbytes + c.batch.ents.nbytes + c.batch.aux.nbytes for c in corpora) + 96 * n_links
-            kname = "tg_scan_kernel"
+            kname = "tg_parse_kernel (+ tg_ent_map_kernel, tg_parse_ent_kernel)"
             k_alg = alg_bytes - 96 * n_links + 36 * n_links
             k_ms = per("parse")
         achieved = k_alg / (k_ms * 1e-3) / 1e9 if k_ms else 0.0

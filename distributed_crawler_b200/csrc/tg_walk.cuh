@@ -84,7 +84,6 @@ enum { F_MSGNO, F_CHAT, F_VIEW, F_SHARE, F_NCOMM, F_TIME, F_POSTTYPE };
 enum { XL_DESC, XL_MEDIA, XL_HANDLE, XL_ALT, XL_COMMENTS, XL_REACTIONS, XL_OUTLINKS, XL_COUNT, XL_FLAGS = 7 };
 #define XLF_SIMPLE_MAP 1u  // xlen[XL_FLAGS]: the reactions map is lane-renderable (size_reaction_map)
 #define XLF_DESC_EXACT 2u  // the description holds invalid UTF-8 or U+2028/9: only the exact escaper may write it
-#define XLF_SLOW 4u        // the line does not fit a tile buffer: tg_emit_slow_kernel writes it (tg_tile.cuh)
 constexpr uint32_t K_NOP = 15;
 #include "tg_pieces.inc"
 
@@ -663,37 +662,9 @@ DEVI void emit_tg_fixed(uint8_t* line, WarpScratch* ws, const CtaShared* cs, con
 }
 
 // ---- emit, kernel 2 of 3: the escaped strings --------------------------------------------------------
-constexpr uint32_t ESC_STAGE = 4096;  // escaped strings up to this long are assembled in shared memory first
-// One escaped string [gdst, gdst + xl).  The escapers place every lane's few output bytes separately: straight to HBM
-// that is one store instruction per BYTE POSITION with 32 lanes 16-20 bytes apart (32 sectors each).  Staged: the same
-// byte stores go to the warp's shared-memory buffer (at the string's own 16-byte phase), and the buffer leaves with
-// ONE bulk store (cp.async.bulk.global.shared::cta) plus the <= 15 edge bytes on either side.
-template <bool EXACT>
-DEVI void esc_via_smem(uint8_t* gdst, const uint8_t* src, uint32_t n, uint32_t xl, uint32_t buf_s) {
-  const uint32_t l = lane_id();
-  const uint32_t mis = (uint32_t)(uintptr_t)gdst & 15u;
-  const DstS d{buf_s + mis};
-  if (EXACT) esc_to(d, src, n);
-  else esc_ascii_to(d, src, n);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncwarp();
-  const uint32_t head = min((16u - mis) & 15u, xl);
-  if (l < head) gdst[l] = (uint8_t)lds8(buf_s + mis + l);
-  const uint32_t body = (xl - head) & ~15u, tail = xl - head - body;
-  if (body && l == 0) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst + head), "r"(buf_s + mis + head), "r"(body) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  }
-  if (l < tail) gdst[head + body + l] = (uint8_t)lds8(buf_s + mis + head + body + l);
-  if (body && l == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the buffer is reused by the next string
-  __syncwarp();
-}
-
 // lane_text_max: strings that need no escaping and are at most this long were already copied by the
-// lane emitter (tg_lane.cuh, same rule); 0xffffffff = none were.  buf_s: the warp's ESC_STAGE + 32 byte staging buffer
-// (shared-space address), 0 = write straight to the blob.
-DEVI void emit_tg_escapes(uint8_t* line, const TgWalkArgs& a, const uint32_t* xlen_g, const uint32_t* xpos_g, uint32_t lane_text_max,
-                          uint32_t buf_s = 0) {
+// lane emitter (tg_lane.cuh, same rule); 0xffffffff = none were.
+DEVI void emit_tg_escapes(uint8_t* line, const TgWalkArgs& a, const uint32_t* xlen_g, const uint32_t* xpos_g, uint32_t lane_text_max) {
   // description / media by content type (tdutils.go:443-587), as in tg_derive
   const uint32_t ct = a.v.ct;
   const uint8_t* desc = nullptr;
@@ -709,7 +680,7 @@ DEVI void emit_tg_escapes(uint8_t* line, const TgWalkArgs& a, const uint32_t* xl
     myl = xlen_g[lane_id()];
     myp = xpos_g[lane_id()];
   }
-#pragma unroll 1
+#pragma unroll
   for (int j = 0; j < 4; j++) {  // XL_DESC, XL_MEDIA, XL_HANDLE, XL_ALT
     uint32_t ln = __shfl_sync(FULL, myl, j);
     if (ln == 0) continue;
@@ -723,15 +694,8 @@ DEVI void emit_tg_escapes(uint8_t* line, const TgWalkArgs& a, const uint32_t* xl
         continue;
       }
     }
-    const bool ascii = j == 0 && !(xlen_g[XL_FLAGS] & XLF_DESC_EXACT);
-    if (buf_s && ln <= ESC_STAGE) {
-      if (ascii) esc_via_smem<false>(line + o, p, n, ln, buf_s);
-      else esc_via_smem<true>(line + o, p, n, ln, buf_s);
-    } else if (ascii) {
-      esc_ascii_to_global(line + o, p, n);
-    } else {
-      esc_to_global(line + o, p, n);
-    }
+    if (j == 0 && !(xlen_g[XL_FLAGS] & XLF_DESC_EXACT)) esc_ascii_to_global(line + o, p, n);
+    else esc_to_global(line + o, p, n);
   }
 }
 

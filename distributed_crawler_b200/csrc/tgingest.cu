@@ -305,6 +305,12 @@ uint64_t next_pow2(uint64_t v) {
 
 // exclusive scan u32[n] -> u64[n+1]; total also lands in *d_total
 int launch_scan(tgi_ctx* c, Slot& s, const uint32_t* in, uint64_t n, uint64_t* out, uint64_t* d_total, uint32_t& launches) {
+  if (n <= (uint64_t)SCAN_SMALL_MAX) {  // page-sized batch: one launch instead of three
+    scan_small_kernel<<<1, SCAN_SMALL_THREADS, 0, s.stream>>>(in, n, out, d_total);
+    launches += 1;
+    CK(cudaGetLastError());
+    return TGI_OK;
+  }
   uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   if (ntiles == 0) ntiles = 1;
   CK(s.d_tiles.ensure(ntiles * 8));
@@ -326,7 +332,7 @@ int h2d(tgi_ctx* c, Slot& s, DevBuf& d, const T* src, size_t count) {
   return TGI_OK;
 }
 
-enum { SC_CHAN_TOTAL = 0, SC_LINE_TOTAL = 1, SC_CURSOR = 2, SC_NEW = 3, SC_FSIZE = 4, SC_LINK_TOTAL = 5, SC_LONG = 6, SC_URL_CURSOR = 7, SC_LANE_OUT = 8, SC_LANE_IN = 9, SC_SLOW = 10, SC_COUNT = 12 };
+enum { SC_CHAN_TOTAL = 0, SC_LINE_TOTAL = 1, SC_CURSOR = 2, SC_NEW = 3, SC_FSIZE = 4, SC_LINK_TOTAL = 5, SC_LONG = 6, SC_URL_CURSOR = 7, SC_LANE_OUT = 8, SC_LANE_IN = 9, SC_COUNT = 10 };
 constexpr uint64_t HOST_VALIDATE_MAX = 1u << 16;  // batches up to this many elements are range-checked on the host
 
 // the checks of tg_validate_kernel, on the host (small batches: no extra launch / sync in a page-sized call)
@@ -624,11 +630,6 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     po.link_count = s.d_link_count.as<uint32_t>();
     po.xlen = s.d_xlen.as<uint32_t>();
     po.var_total = (unsigned long long*)(dsc + SC_LONG);
-    po.slow_total = (unsigned long long*)(dsc + SC_SLOW);
-    {
-      static const bool fast_text = !(getenv("TGI_FAST_TEXT") && !strcmp(getenv("TGI_FAST_TEXT"), "0"));
-      po.fast_text = fast_text ? 1 : 0;
-    }
     po.arena = s.d_arena.as<tgi_link>();
     po.arena_cap = (uint32_t)arena_cap;
     po.cursor = (uint32_t*)(dsc + SC_CURSOR);
@@ -646,19 +647,11 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
         tg_parse_ent_kernel<<<ge, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
         launches += 2;
       }
-      static const bool split = [] { const char* e = getenv("TGI_SCAN"); return !(e && !strcmp(e, "fused")); }();  // default: split
-      if (!split) {
-        // then ONE pass over every record: status, plaintext links, line length
-        if (want_json) tg_scan_kernel<true><<<ge, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
-        else tg_scan_kernel<false><<<ge, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
+      tg_parse_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, flags, po);  // records without entities
+      launches++;
+      if (want_json) {
+        tg_size_lane_kernel<<<ge, CTA_THREADS, 0, st>>>(b, cfg, po);
         launches++;
-      } else {  // A/B: the round-1 split (links of the records without entities, then the sizes: the text is read twice)
-        tg_parse_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
-        launches++;
-        if (want_json) {
-          tg_size_lane_kernel<<<ge, CTA_THREADS, 0, st>>>(b, cfg, po);
-          launches++;
-        }
       }
       CK(cudaEventRecord(s.ev_p1, st));
     }
@@ -708,49 +701,24 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       ei.out = s.d_jsonl.as<uint8_t>();
       ei.err = (int*)(dsc + SC_CURSOR) + 1;
       ei.counters = (unsigned long long*)(dsc + SC_LANE_OUT);
-      ei.xpos = nullptr;
-      ei.lane_text_max = 0;
-      ei.esc_staged = 0;
-      static const bool lane_pipe = [] { const char* e = getenv("TGI_EMIT"); return !(e && !strcmp(e, "tile")); }();  // default: lane
-      static const int tile_ctas = getenv("TGI_TILE_CTAS") ? atoi(getenv("TGI_TILE_CTAS")) : 3;  // A/B: register budget of the tile kernel
       static const bool attr_set = [] {
-        return cudaFuncSetAttribute(tg_emit_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess &&
-               cudaFuncSetAttribute(tg_emit_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess &&
-               cudaFuncSetAttribute(tg_emit_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SlowShared)) == cudaSuccess &&
-               cudaFuncSetAttribute(tg_emit_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LaneShared)) == cudaSuccess;
+        return cudaFuncSetAttribute(tg_emit_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LaneShared)) == cudaSuccess;
       }();
-      if (!attr_set) { set_err(c, "cannot reserve %zu bytes of shared memory for the emitter", sizeof(TileShared)); return TGI_E_CUDA; }
+      if (!attr_set) { set_err(c, "cannot reserve %zu bytes of shared memory for the lane emitter", sizeof(LaneShared)); return TGI_E_CUDA; }
       const uint64_t groups = (n + 31) / 32;
       const uint64_t ctas = (groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
       CK(cudaEventRecord(s.ev_e0, st));
-      if (lane_pipe) {  // one LANE per record (tg_lane.cuh) + the two clean-up kernels
-        CK(s.d_xpos.ensure(n * 32));
-        ei.xpos = s.d_xpos.as<uint32_t>();
-        ei.lane_text_max = LANE_TEXT_MAX;
-        {
-          static const bool staged = !(getenv("TGI_ESC_STAGED") && !strcmp(getenv("TGI_ESC_STAGED"), "0"));
-          ei.esc_staged = staged ? 1 : 0;
-        }
-        unsigned gl = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * 3);
-        tg_emit_lane_kernel<<<gl, CTA_THREADS, sizeof(LaneShared), st>>>(b, cfg, ei);
-        CK(cudaEventRecord(s.ev_f1, st));
-        unsigned gg = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * 8);
-        tg_emit_esc_kernel<<<gg, CTA_THREADS, 0, st>>>(b, ei);
-        tg_emit_maps_kernel<<<gg, CTA_THREADS, 0, st>>>(b, ei);
-        launches += 3;
-      } else {
-        // one CTA per SM slot (3 resident CTAs per SM by shared memory), persistent over the record groups
-        unsigned gt = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * (tile_ctas == 2 ? 2 : 3));
-        if (tile_ctas == 2) tg_emit_tile_kernel<2><<<gt, CTA_THREADS, sizeof(TileShared), st>>>(b, cfg, ei);
-        else tg_emit_tile_kernel<3><<<gt, CTA_THREADS, sizeof(TileShared), st>>>(b, cfg, ei);
-        CK(cudaEventRecord(s.ev_f1, st));
-        launches++;
-        if (hsc[SC_SLOW]) {  // lines longer than a tile buffer (counted by the size pass)
-          unsigned gsl = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * 2);
-          tg_emit_slow_kernel<<<gsl, CTA_THREADS, sizeof(SlowShared), st>>>(b, cfg, ei);
-          launches++;
-        }
-      }
+      CK(s.d_xpos.ensure(n * 32));
+      ei.xpos = s.d_xpos.as<uint32_t>();
+      ei.lane_text_max = LANE_TEXT_MAX;
+      // one LANE per record (tg_lane.cuh): 3 resident CTAs per SM by shared memory, persistent over the record groups
+      unsigned gl = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * 3);
+      tg_emit_lane_kernel<<<gl, CTA_THREADS, sizeof(LaneShared), st>>>(b, cfg, ei);
+      CK(cudaEventRecord(s.ev_f1, st));
+      unsigned gg = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * 8);
+      tg_emit_esc_kernel<<<gg, CTA_THREADS, 0, st>>>(b, ei);   // strings that need escaping or are long
+      tg_emit_maps_kernel<<<gg, CTA_THREADS, 0, st>>>(b, ei);  // comment lists, non-trivial maps, long outlink lists
+      launches += 3;
       CK(cudaEventRecord(s.ev_e1, st));
     }
     CK(cudaGetLastError());
@@ -1058,6 +1026,38 @@ int wait_job(tgi_ctx* c, int slot, tgi_result* out) {
   return rc;
 }
 
+// Blocking entry points run the job on the CALLER's thread (the slot is claimed exclusively): two condition-variable
+// hand-offs per call are most of what a page-sized batch costs besides the launches themselves.
+int run_inline(tgi_ctx* c, int slot, JobKind kind, const tgi_tg_batch* in_tg, const tgi_yt_batch* in_yt, const tgi_gm_batch* in_gm,
+               uint32_t flags, tgi_result* out) {
+  Slot& s = c->slots[slot];
+  {
+    std::lock_guard<std::mutex> lk(s.mu);
+    if (s.busy) { set_err(c, "slot %d is busy", slot); return TGI_E_STATE; }
+    s.busy = true;
+    s.done = false;
+  }
+  cudaSetDevice(c->device);
+  int rc = TGI_OK;
+  if (kind == JOB_TG) {
+    rc = upload_tg(c, s, in_tg);
+    if (rc == TGI_OK) rc = run_tg(c, s, flags, &s.res);
+  } else if (kind == JOB_YT) {
+    rc = upload_yt(c, s, in_yt);
+    if (rc == TGI_OK) rc = run_yt(c, s, flags, &s.res);
+  } else {
+    rc = run_gm(c, s, in_gm, flags, &s.res);
+  }
+  {
+    std::lock_guard<std::mutex> lk(s.mu);
+    s.rc = rc;
+    s.done = true;
+    if (rc != TGI_OK) s.busy = false;
+  }
+  if (rc == TGI_OK && out) *out = s.res;
+  return rc;
+}
+
 int claim_slot(tgi_ctx* c) {
   std::unique_lock<std::mutex> lk(c->alloc_mu);
   for (;;) {
@@ -1232,8 +1232,7 @@ void tgi_result_release(tgi_ctx* c, int slot) {
 int tgi_telegram_batch(tgi_ctx* c, const tgi_tg_batch* in, uint32_t run_flags, tgi_result* out) {
   if (!c) return TGI_E_ARG;
   int slot = claim_slot(c);
-  int rc = post_job(c, slot, JOB_TG, in, run_flags);
-  if (rc == TGI_OK) rc = wait_job(c, slot, out);
+  int rc = run_inline(c, slot, JOB_TG, in, nullptr, nullptr, run_flags, out);
   if (rc != TGI_OK) {
     tgi_result_release(c, slot);
     return rc;
@@ -1272,8 +1271,7 @@ int tgi_youtube_wait(tgi_ctx* c, int slot, tgi_result* out) { return wait_job(c,
 int tgi_youtube_batch(tgi_ctx* c, const tgi_yt_batch* in, uint32_t run_flags, tgi_result* out) {
   if (!c) return TGI_E_ARG;
   int slot = claim_slot(c);
-  int rc = post_job(c, slot, JOB_YT, nullptr, run_flags, in);
-  if (rc == TGI_OK) rc = wait_job(c, slot, out);
+  int rc = run_inline(c, slot, JOB_YT, nullptr, in, nullptr, run_flags, out);
   if (rc != TGI_OK) tgi_result_release(c, slot);
   return rc;
 }
@@ -1343,8 +1341,7 @@ int tgi_plan_chunks(const uint64_t* line_off, uint64_t n, uint64_t trigger, uint
 int tgi_generic_batch(tgi_ctx* c, const tgi_gm_batch* in, uint32_t run_flags, tgi_result* out) {
   if (!c) return TGI_E_ARG;
   int slot = claim_slot(c);
-  int rc = post_job(c, slot, JOB_GM, nullptr, run_flags, nullptr, in);
-  if (rc == TGI_OK) rc = wait_job(c, slot, out);
+  int rc = run_inline(c, slot, JOB_GM, nullptr, nullptr, in, run_flags, out);
   if (rc != TGI_OK) tgi_result_release(c, slot);
   return rc;
 }

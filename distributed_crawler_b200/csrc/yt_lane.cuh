@@ -62,6 +62,34 @@ __device__ __noinline__ void ld_copy(LaneDirect* sp, const uint8_t* src, uint32_
   *sp = s;
 }
 
+// append the JSON-escaped form of src[0, n): the string is valid UTF-8 without U+2028 / U+2029 (the size pass checked), so
+// only ASCII bytes expand.  16 source bytes at a time: blocks without a special byte (almost all) are appended as they
+// are, the others byte by byte.
+__device__ __noinline__ void ld_copy_esc(LaneDirect* sp, const uint8_t* src, uint32_t n) {
+  __align__(16) uint8_t tmp[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // ld_copy reads whole 16-byte blocks
+  for (uint32_t i = 0; i < n; i += 16) {
+    const uint32_t k = min(16u, n - i);
+    bool special = false;
+    for (uint32_t j = 0; j < k; j += 4) {
+      uint32_t x = ld_u32_unaligned(src + i + j);
+      if (k - j < 4) x = (x & ((1u << (8u * (k - j))) - 1u)) | (0x20202020u << (8u * (k - j)));
+      const uint32_t ctl = ~(((x & 0x7F7F7F7Fu) + 0x60606060u) | x) & 0x80808080u;
+      special = special || (ctl | swar_has_byte(x & 0xFBFBFBFBu, 0x22) | swar_has_byte(x & 0xFDFDFDFDu, 0x3C) | swar_has_byte(x, 0x5C)) != 0;
+    }
+    if (!special) {
+      ld_copy(sp, src + i, k);
+      continue;
+    }
+    for (uint32_t j = 0; j < k; j++) {
+      const uint32_t bt = ldb(src + i + j);
+      const uint32_t el = bt < 0x80u ? ascii_esc_len(bt) : 1u;
+      struct { uint8_t* p; DEVI void st(uint32_t o, uint32_t v) const { p[o] = (uint8_t)v; } } sink{tmp};
+      put_escaped(sink, 0, bt, el);
+      ld_copy(sp, tmp, el);
+    }
+  }
+}
+
 // leave n bytes to another writer: what the current block holds goes out byte-exact, the stream resumes behind the gap
 DEVI void ld_skip(LaneDirect& s, uint32_t n) {
   const uint32_t ph = (uint32_t)s.pos & 15u;
@@ -83,8 +111,9 @@ struct YtLaneWriter {
   uint64_t pend_dst[YT_LANE_PENDING];
   const uint8_t* pend_src[YT_LANE_PENDING];
   uint32_t pend_n[YT_LANE_PENDING];
+  uint32_t pend_el[YT_LANE_PENDING];  // escaped length (== pend_n: plain copy)
   int npend = 0;
-  uint32_t el[2];               // unused (clean records only)
+  uint32_t el[2];               // escaped lengths of the description / the title (size pass)
   __align__(16) uint8_t num[64];  // number / time / file-name rendering
   DEVI void begin(uint64_t addr) {
     s.pos = addr;
@@ -97,15 +126,19 @@ struct YtLaneWriter {
   }
   DEVI void raw(const uint8_t* p, uint32_t n) { ld_copy(&s, p, n); }
   DEVI void esc(const uint8_t* p, uint32_t n) { ld_copy(&s, p, n); }  // nothing to escape on this path
-  DEVI void esc_slot(int, const uint8_t* p, uint32_t n) {
+  DEVI void esc_slot(int k, const uint8_t* p, uint32_t n) {  // description / title: may need (ASCII-only) escaping
+    const uint32_t e = el[k];
     if (n > YT_LANE_LONG && npend < YT_LANE_PENDING) {
       pend_dst[npend] = s.pos;
       pend_src[npend] = p;
       pend_n[npend] = n;
+      pend_el[npend] = e;
       npend++;
-      ld_skip(s, n);
-    } else {
+      ld_skip(s, e);
+    } else if (e == n) {
       ld_copy(&s, p, n);
+    } else {
+      ld_copy_esc(&s, p, n);
     }
   }
   // warp-collective, after the (possibly divergent) walk: every lane's pending long copies, 512 bytes per step
@@ -119,7 +152,9 @@ struct YtLaneWriter {
         const uint64_t d = __shfl_sync(FULL, pend_dst[k < npend ? k : 0], src_lane);
         const uint8_t* p = (const uint8_t*)__shfl_sync(FULL, (unsigned long long)(uintptr_t)pend_src[k < npend ? k : 0], src_lane);
         const uint32_t n = __shfl_sync(FULL, pend_n[k < npend ? k : 0], src_lane);
-        warp_copy_vec((uint8_t*)(uintptr_t)d, p, n);
+        const uint32_t e = __shfl_sync(FULL, pend_el[k < npend ? k : 0], src_lane);
+        if (e == n) warp_copy_vec((uint8_t*)(uintptr_t)d, p, n);
+        else esc_ascii_to_global((uint8_t*)(uintptr_t)d, p, n);
       }
     }
   }
@@ -142,12 +177,14 @@ struct YtLaneSizer {
   static constexpr bool kLane = true;
   uint64_t total = 0;
   uint32_t el[2];
-  bool dirty = false;
+  bool dirty = false;        // some string needs escaping
+  bool small_dirty = false;  // ... and it is not the description / the title: only the warp writer escapes those
   __align__(16) uint8_t num[64];
   DEVI void raw(const uint8_t*, uint32_t n) { total += n; }
   DEVI void esc(const uint8_t* p, uint32_t n) {
     const uint32_t e = thread_esc_len(p, n);
     dirty = dirty || e != n;
+    small_dirty = small_dirty || e != n;
     total += e;
   }
   DEVI void esc_slot(int k, const uint8_t*, uint32_t n) {

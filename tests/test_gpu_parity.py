@@ -231,12 +231,12 @@ def test_warp_per_record_reference_kernels_still_agree():
     assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]
 
 
-def test_tile_emitter_boundaries():
-    """The tile emitter assembles lines in a 6144-byte shared-memory buffer per warp and leaves lines that do not fit
-    (with 2096 bytes of map scratch behind them when they carry reactions / comments) to the slow-path kernel; the text
-    scanner works on 512-byte strips.  Messages on both sides of every boundary — buffer size with and without scratch,
-    strip ends, map sizes, repeated / long / dirty keys — in one warp and spread over several, in shuffled orders (so
-    that lines start at every alignment and the buffer is flushed at different fill levels)."""
+def test_emitter_hand_over_boundaries():
+    """The lane emitter writes the simple cases itself and leaves the rest to the esc / maps kernels: the rules sit at
+    LANE_TEXT_MAX (512 bytes), LANE_LINKS_MAX (4 outlinks), LANE_MAP_MAX (6 entries), 8-byte keys, repeated keys,
+    strings that need escaping.  Messages on both sides of every boundary (and, since the round-2 tile experiments, lines
+    between 2 and 20 KB, with and without maps, comment lists longer than 4 KB) in one warp and spread over several, in
+    shuffled orders so that lines start at every alignment."""
     from distributed_crawler_b200.pack import Comment
     msgs = []
     for k, n in enumerate([0, 1, 15, 16, 17, 127, 128, 129, 511, 512, 513, 1024, 3000, 1900, 2000, 2100, 3900, 4000, 4100, 4150, 4200,
