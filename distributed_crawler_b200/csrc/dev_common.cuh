@@ -670,6 +670,56 @@ __device__ __noinline__ void warp_copy_vec(uint8_t* dst, const uint8_t* src, uin
   const uint32_t t0 = nb << 4;
   if (t0 + l < n) dst[t0 + l] = (uint8_t)ldb(src + t0 + l);
 }
+// JSON-escape s[0..n) to dst when only a FEW bytes need escaping (a message whose only specials are its line breaks):
+// the text between two special bytes is a plain copy at a shifted position, so the string goes out segment by segment
+// with the vector memcpy and the escapes themselves are written by lane 0.  The per-byte placement of esc_ascii_to
+// (one store instruction per byte position, every lane on its own bytes) is only worth it for dense specials.
+// Requires valid UTF-8 without U+2028 / U+2029 (non-ASCII bytes pass through).  Returns the bytes written.
+__device__ __noinline__ uint32_t esc_sparse_to_global(uint8_t* dst, const uint8_t* s, uint32_t n) {
+  const uint32_t l = lane_id();
+  uint32_t cur = 0, out = 0;  // warp-uniform: next source byte to copy, next output byte
+  for (uint32_t base = 0; base < n; base += 512) {
+    const uint32_t p0 = base + 16u * l;
+    const uint32_t nv = p0 >= n ? 0u : min(16u, n - p0);
+    uint32_t m = 0;  // bit k: byte p0 + k needs escaping
+#pragma unroll 1
+    for (uint32_t j = 0; j < nv; j += 4) {
+      const uint32_t nj = min(4u, nv - j);
+      uint32_t x = ld_u32_unaligned(s + p0 + j);
+      if (nj < 4) x = (x & ((1u << (8u * nj)) - 1u)) | (0x20202020u << (8u * nj));
+      const uint32_t ctl = ~(((x & 0x7F7F7F7Fu) + 0x60606060u) | x) & 0x80808080u;  // < 0x20
+      if (ctl | swar_has_byte(x & 0xFBFBFBFBu, 0x22) | swar_has_byte(x & 0xFDFDFDFDu, 0x3C) | swar_has_byte(x, 0x5C)) {
+        for (uint32_t k = 0; k < nj; k++) {
+          const uint32_t bt = (x >> (8u * k)) & 0xFFu;
+          if (bt < 0x80u && ascii_esc_len(bt) != 1u) m |= 1u << (j + k);
+        }
+      }
+    }
+    uint32_t lanes = __ballot_sync(FULL, m != 0);
+    while (lanes) {
+      const int sl = __ffs(lanes) - 1;
+      lanes &= lanes - 1;
+      uint32_t mm = __shfl_sync(FULL, m, sl);
+      while (mm) {
+        const uint32_t p = base + 16u * (uint32_t)sl + (uint32_t)(__ffs(mm) - 1);
+        mm &= mm - 1;
+        const uint32_t seg = p - cur;
+        if (seg >= 48) warp_copy_vec(dst + out, s + cur, seg);
+        else if (seg) gcopy_g(dst + out, s + cur, seg);
+        out += seg;
+        const uint32_t bt = ldb(s + p), el = ascii_esc_len(bt);
+        if (l == 0) put_escaped(DstG{dst}, out, bt, el);
+        out += el;
+        cur = p + 1;
+      }
+    }
+  }
+  const uint32_t seg = n - cur;
+  if (seg >= 48) warp_copy_vec(dst + out, s + cur, seg);
+  else if (seg) gcopy_g(dst + out, s + cur, seg);
+  return out + seg;
+}
+
 // the same three through a byte sink (DstG: the output blob, DstS: a line being assembled in shared memory)
 template <class D>
 DEVI void copy_g(const D& d, const uint8_t* src, uint32_t n) {

@@ -399,7 +399,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_lane_kernel(TgBatchDev
 }
 
 // The esc and maps kernels take what the lane emitter left: each lane first checks one record of a
-// group of 32, then the warp walks the records that need it (most do not).
+// group of 32, then the warp walks the records that need it (most do not).  Two instantiations, launched one after the
+// other: ESC_SPARSE writes the descriptions whose only specials are a few line breaks (segment copies), ESC_DENSE the
+// rest (per-byte placement, exact UTF-8 path, long clean strings, the other three strings).
+template <int MODE>
 __global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_esc_kernel(TgBatchDev b, EmitIn in) {
   const int wid = threadIdx.x >> 5, l = lane_id();
   const bool lane_mode = in.lane_text_max != 0xffffffffu;
@@ -418,7 +421,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_esc_kernel(TgBatchDev 
                                         : (ct == TGI_CT_ANIMATED_EMOJI || ct == TGI_CT_POLL || ct == TGI_CT_GIVEAWAY ||
                                            ct == TGI_CT_PAID_MEDIA || ct == TGI_CT_DOCUMENT) ? rec->alt_len : 0u;
         auto left = [&](uint32_t x, uint32_t n) { return x != 0 && !(x == n && n <= in.lane_text_max); };
-        need = left(xl.x, dlen) || left(xl.y, rec->media_len) || left(xl.z, rec->handle_len) || left(xl.w, rec->alt_len);
+        const bool sparse = esc_desc_is_sparse(xl.x, dlen, in.xlen[r * 8 + XL_FLAGS]);
+        if (MODE == ESC_SPARSE) need = sparse;
+        else need = (left(xl.x, dlen) && !(MODE == ESC_DENSE && sparse)) || left(xl.y, rec->media_len) || left(xl.z, rec->handle_len) || left(xl.w, rec->alt_len);
+      } else if (MODE == ESC_SPARSE) {
+        need = false;
       }
     }
     uint32_t todo = __ballot_sync(FULL, need);
@@ -430,7 +437,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_esc_kernel(TgBatchDev 
       a.cfg = nullptr;
       a.r = rr;
       a.v = load_rec_view(b, rr);
-      emit_tg_escapes(in.out + in.line_off[rr], a, in.xlen + rr * 8, in.xpos + rr * 8, in.lane_text_max);
+      if (lane_mode) emit_tg_escapes<MODE>(in.out + in.line_off[rr], a, in.xlen + rr * 8, in.xpos + rr * 8, in.lane_text_max);
+      else emit_tg_escapes<ESC_ALL>(in.out + in.line_off[rr], a, in.xlen + rr * 8, in.xpos + rr * 8, in.lane_text_max);
     }
   }
 }

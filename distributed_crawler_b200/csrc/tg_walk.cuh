@@ -664,6 +664,12 @@ DEVI void emit_tg_fixed(uint8_t* line, WarpScratch* ws, const CtaShared* cs, con
 // ---- emit, kernel 2 of 3: the escaped strings --------------------------------------------------------
 // lane_text_max: strings that need no escaping and are at most this long were already copied by the
 // lane emitter (tg_lane.cuh, same rule); 0xffffffff = none were.
+// MODE splits the work between two kernels by instruction footprint: ESC_ALL = every string; ESC_SPARSE = only a
+// description with few special bytes (esc_sparse_to_global); ESC_DENSE = everything else.
+enum { ESC_ALL = 0, ESC_DENSE = 1, ESC_SPARSE = 2 };
+constexpr uint32_t ESC_SPARSE_EXTRA = 24;  // at most this many added bytes (a line break adds 1, a control character 5)
+DEVI bool esc_desc_is_sparse(uint32_t xl, uint32_t n, uint32_t flags) { return xl > n && xl - n <= ESC_SPARSE_EXTRA && !(flags & XLF_DESC_EXACT); }
+template <int MODE>
 DEVI void emit_tg_escapes(uint8_t* line, const TgWalkArgs& a, const uint32_t* xlen_g, const uint32_t* xpos_g, uint32_t lane_text_max) {
   // description / media by content type (tdutils.go:443-587), as in tg_derive
   const uint32_t ct = a.v.ct;
@@ -681,12 +687,20 @@ DEVI void emit_tg_escapes(uint8_t* line, const TgWalkArgs& a, const uint32_t* xl
     myp = xpos_g[lane_id()];
   }
 #pragma unroll
-  for (int j = 0; j < 4; j++) {  // XL_DESC, XL_MEDIA, XL_HANDLE, XL_ALT
+  for (int j = 0; j < (MODE == ESC_SPARSE ? 1 : 4); j++) {  // XL_DESC, XL_MEDIA, XL_HANDLE, XL_ALT
     uint32_t ln = __shfl_sync(FULL, myl, j);
     if (ln == 0) continue;
     uint32_t o = __shfl_sync(FULL, myp, j);
     const uint8_t* p = j == 0 ? desc : j == 1 ? a.v.media : j == 2 ? a.v.handle : a.v.alt;
     uint32_t n = j == 0 ? desc_len : j == 1 ? a.v.media_len : j == 2 ? a.v.handle_len : a.v.alt_len;
+    if (MODE != ESC_ALL && j == 0) {
+      const bool sparse = esc_desc_is_sparse(ln, n, xlen_g[XL_FLAGS]);
+      if (MODE == ESC_SPARSE) {
+        if (sparse) esc_sparse_to_global(line + o, p, n);
+        continue;
+      }
+      if (sparse) continue;  // ESC_DENSE: the other kernel writes it
+    }
     if (ln == n) {  // nothing to escape
       if (n <= lane_text_max && lane_text_max != 0xffffffffu) continue;
       if (n >= 64) {

@@ -716,9 +716,17 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       tg_emit_lane_kernel<<<gl, CTA_THREADS, sizeof(LaneShared), st>>>(b, cfg, ei);
       CK(cudaEventRecord(s.ev_f1, st));
       unsigned gg = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * 8);
-      tg_emit_esc_kernel<<<gg, CTA_THREADS, 0, st>>>(b, ei);   // strings that need escaping or are long
+      static const bool one_esc = getenv("TGI_ESC_ONE") != nullptr;  // A/B: the round-1 single escape kernel
+      if (one_esc) {
+        tg_emit_esc_kernel<ESC_ALL><<<gg, CTA_THREADS, 0, st>>>(b, ei);
+        launches += 1;
+      } else {
+        tg_emit_esc_kernel<ESC_SPARSE><<<gg, CTA_THREADS, 0, st>>>(b, ei);  // descriptions with a few line breaks
+        tg_emit_esc_kernel<ESC_DENSE><<<gg, CTA_THREADS, 0, st>>>(b, ei);   // the other strings that need escaping or are long
+        launches += 2;
+      }
       tg_emit_maps_kernel<<<gg, CTA_THREADS, 0, st>>>(b, ei);  // comment lists, non-trivial maps, long outlink lists
-      launches += 3;
+      launches += 2;
       CK(cudaEventRecord(s.ev_e1, st));
     }
     CK(cudaGetLastError());

@@ -656,7 +656,7 @@ static void put_reaction_map(buf_t* o, const tgi_tg_batch* b, uint32_t r0, uint3
 }
 
 /* returns status; on TGI_ST_EMITTED appends one line to o and the links to ls */
-static int tg_record(const orc_ctx* c, const tgi_tg_batch* b, uint64_t r, buf_t* o, linkset_t* ls) {
+static int tg_record(const orc_ctx* c, const tgi_tg_batch* b, uint64_t r, buf_t* o, linkset_t* ls, int want_json) {
   const tgi_config* cfg = &c->cfg;
   const tgi_tg_rec* rec = &b->recs[r];
   const tgi_tg_chan* ch = &b->chans[rec->chan_idx];
@@ -692,6 +692,7 @@ static int tg_record(const orc_ctx* c, const tgi_tg_batch* b, uint64_t r, buf_t*
 
   /* :590 outlinks */
   if (extract_links(b, r, ls) < 0) return TGI_ST_FAILED;
+  if (!want_json) return TGI_ST_EMITTED; /* link extraction + dedup only (BASELINE configs 3 / 5): no Post is built */
 
   size_t line_start = o->len;
   /* link, tdutils.go:1005-1031 */
@@ -1217,7 +1218,7 @@ static void produce(work_t* w) {
     w->scratch.len = 0;
     w->nlinks[r - w->r0] = 0;
     size_t before = o->len;
-    int st = w->tg ? tg_record(w->c, w->tg, r, o, &ls) : w->yt ? yt_record(w->c, w->yt, r, o, &ls) : gm_record(w->c, w->gm, r, o);
+    int st = w->tg ? tg_record(w->c, w->tg, r, o, &ls, (rf & TGI_RUN_JSONL) != 0) : w->yt ? yt_record(w->c, w->yt, r, o, &ls) : gm_record(w->c, w->gm, r, o);
     w->status[r - w->r0] = (uint8_t)st;
     w->linelen[r - w->r0] = (rf & TGI_RUN_JSONL) ? o->len - before : 0;
     if (st == TGI_ST_EMITTED || st == TGI_ST_NOLINE) {
