@@ -38,7 +38,8 @@ sys.path.insert(0, ROOT)
 METRIC = "messages/sec parsed+link-extracted+JSONL"
 UNIT = "messages/s"
 E2E_CHUNK = int(os.environ.get("TGI_BENCH_CHUNK", 500_000))   # records per C-ABI call in the e2e leg
-SLOT_MAX = int(os.environ.get("TGI_BENCH_SLOT_MAX", 34_000_000))  # records per resident slot (links-only configs)
+SLOT_MAX = int(os.environ.get("TGI_BENCH_SLOT_MAX", 42_000_000))  # records per resident slot (links-only configs)
+GEN_BUDGET_S = float(os.environ.get("TGI_BENCH_GEN_BUDGET_S", 300))  # host time the synthetic-corpus generator may take per rank
 ORC_RUN_SLICES, ORC_RUN_PIN = 0x10000, 0x20000
 
 J, L, F, S = 0x01, 0x02, 0x04, 0x10  # TGI_RUN_JSONL / LINKS / FRONTIER / SKIP_SELF
@@ -315,6 +316,18 @@ def main():
     RUN = cfg["flags"]
     want_json = bool(RUN & J)
     n = cfg["n"] // world if cfg["scaling"] == "strong" else cfg["n"]   # records per GPU
+    n_asked = n
+    if n > 4_000_000:  # the corpus is generated on the host: keep that inside a time budget, whatever CPUs this box grants
+        t_probe = time.perf_counter()
+        make_corpus(cfg, 1_000_000, rank * n, gen_threads).close()
+        rate = 1_000_000 / (time.perf_counter() - t_probe)
+        fit = int(rate * GEN_BUDGET_S)
+        if world > 1:
+            fit_t = torch.tensor([fit], dtype=torch.int64, device=dev)
+            dist.all_reduce(fit_t, op=dist.ReduceOp.MIN)
+            fit = int(fit_t.item())
+        if fit < n:
+            n = max(1_000_000, fit // 1_000_000 * 1_000_000)
     first = rank * n
     eng = Engine(device=local, frontier_capacity=cfg["fcap"])
     merger = None
@@ -508,7 +521,10 @@ def main():
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
             "config": {"workload": cfg["workload"], "bench_config": args.config, "run_flags": RUN,
-                       "records_per_gpu": n, "resident_batches": len(corpora), "seed": hex(cfg["seed"]), "input_bytes_per_gpu": in_bytes,
+                       "records_per_gpu": n, "records_per_gpu_of_the_configuration": n_asked,
+                       "reduced": (None if n == n_asked else f"the host generator (~{int(rate)} records/s on this rank's CPUs) would need more than "
+                                                             f"{int(GEN_BUDGET_S)} s for {n_asked} records: TGI_BENCH_GEN_BUDGET_S"),
+                       "resident_batches": len(corpora), "seed": hex(cfg["seed"]), "input_bytes_per_gpu": in_bytes,
                        "jsonl_bytes_per_gpu": jsonl_len, "links_per_gpu": n_links,
                        "l2": "inputs (%.1f GB) and outputs (%.1f GB) per step are far larger than the 126 MB L2" % (in_bytes / 1e9, jsonl_len / 1e9),
                        "timing": "wall clock around the K steps between barriers + synchronize, max over ranks"

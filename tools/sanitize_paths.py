@@ -20,4 +20,24 @@ for mk in (make_youtube, make_youtube_config4):
 g, _ = make_generic(500, seed=4)
 print("gm", e.generic(g).jsonl_len)
 print("join", e.key_join(np.arange(2000).reshape(-1, 2), np.arange(1000).reshape(-1, 2))[:4])
+# round-2 paths: library-owned staging, exclusion sets + pending_edges rows, big maps / many links, single-rank merge
+from distributed_crawler_b200.engine import names_to_keys32
+from distributed_crawler_b200.pack import pack_telegram
+from helpers import msg
+c = Corpus(4000, profile=3, nthreads=4)
+st = e.stage(c.batch)
+print("staged", e.telegram(st, f).n_links)
+e.unstage(st)
+e.set_add(abi.SET_INVALID, names_to_keys32([b"name%05d" % i for i in range(500)]), np.full(500, 1_700_000_000, np.int64))
+e.set_add(abi.SET_DISCOVERED, names_to_keys32([b"chan%05d" % i for i in range(500)]))
+e.set_now(1_700_000_100)
+T = abi.RUN_LINKS | abi.RUN_FRONTIER | abi.RUN_FILTER | abi.RUN_SKIP_SELF | abi.RUN_SKIP_INVALID
+e.telegram_submit(1, c.batch, T)
+r = e.telegram_wait(1)
+print("edges", len(e.pending_edges(1, 1_700_000_100)), r.n_new)
+e.release(1)
+big = [msg("messageText", " ".join("t.me/chan_%05d" % i for i in range(3000)), reactions=[("k%02d" % (i % 47), i) for i in range(90)])]
+print("big", e.telegram(pack_telegram(big), f).n_links)
+e.comm_init(Engine.comm_unique_id(), 0, 1)
+print("merge", e.frontier_merge(), len(e.frontier_global_export()))
 print("done")
