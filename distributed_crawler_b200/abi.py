@@ -73,6 +73,9 @@ LINK = np.dtype([("name", "u1", (32,)), ("len", "u1"), ("src", "u1"), ("flags", 
 EDGE = np.dtype([("destination", "u1", (32,)), ("record", "<u8"), ("chan_idx", "<u4"), ("dest_len", "u1"), ("source_type", "u1"),
                  ("status", "u1"), ("reserved", "u1")])  # tgi_edge
 assert EDGE.itemsize == 48
+APPEND_RUN = np.dtype([("chan_idx", "<u4"), ("n_lines", "<u4"), ("first", "<u8"), ("end", "<u8"), ("byte_begin", "<u8"),
+                       ("byte_end", "<u8")])  # tgi_append_run
+assert APPEND_RUN.itemsize == 40
 SET_INVALID, SET_DISCOVERED = 1, 2
 EDGE_PENDING, EDGE_DUPLICATE, EDGE_INVALID_CACHED = 0, 1, 2
 RUN_SKIP_INVALID = 0x40
@@ -134,7 +137,8 @@ class ResultC(C.Structure):
 
 class MergeStatsC(C.Structure):
     _fields_ = [("merges", C.c_uint64), ("keys_sent", C.c_uint64), ("keys_received", C.c_uint64), ("keys_owned", C.c_uint64),
-                ("bytes_sent", C.c_uint64), ("bucket_ms", C.c_double), ("exchange_ms", C.c_double), ("insert_ms", C.c_double)]
+                ("bytes_sent", C.c_uint64), ("bucket_ms", C.c_double), ("exchange_ms", C.c_double), ("insert_ms", C.c_double),
+                ("last_bucket_ms", C.c_double), ("last_exchange_ms", C.c_double), ("last_insert_ms", C.c_double)]
 
 
 class StatsC(C.Structure):

@@ -365,7 +365,20 @@ struct EmitIn {
   int* err;
   uint32_t lane_text_max;        // see emit_tg_escapes
   unsigned long long* counters;  // [0] JSONL bytes written by the main emit kernel, [1] source bytes it read from HBM
+  // work lists written by the lane emitter: the records whose line it did not finish, by what is left
+  uint32_t* list[3];             // WL_SPARSE, WL_DENSE, WL_MAPS: record indices
+  uint32_t* list_count;          // [3]
 };
+enum { WL_SPARSE = 0, WL_DENSE = 1, WL_MAPS = 2 };
+// warp-aggregated append of the lanes with `need` to a work list
+DEVI void wl_append(uint32_t* list, uint32_t* count, bool need, uint32_t value) {
+  const uint32_t m = __ballot_sync(FULL, need);
+  if (!m) return;
+  uint32_t base = 0;
+  if (lane_id() == 0) base = atomicAdd(count, (uint32_t)__popc(m));
+  base = __shfl_sync(FULL, base, 0);
+  if (need) list[base + __popc(m & ((1u << lane_id()) - 1u))] = value;
+}
 
 // the same job, one LANE per record (tg_lane.cuh): 32 records per warp task
 __global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_lane_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
@@ -385,8 +398,21 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_lane_kernel(TgBatchDev
     if (!active) r = b.n - 1;
     active = active && in.status[r] == TGI_ST_EMITTED;
     if (!__any_sync(FULL, active)) continue;
+    uint32_t left = 0;
     emit_tg_lane(sh, sh.rows[wid][l], s, b, cfg, r, active, in.out, in.line_off, in.xlen + r * 8, in.xpos + r * 8,
-                 in.arena + in.link_start[r], active ? in.link_count[r] : 0u, in.err, bytes_out, bytes_in);
+                 in.arena + in.link_start[r], active ? in.link_count[r] : 0u, in.err, bytes_out, bytes_in, left);
+    // hand the unfinished lines to the clean-up kernels as lists (they used to re-derive this from every record)
+    bool sparse = false;
+    if (active && (left & 1u)) {
+      const tgi_tg_rec* rec = &b.recs[r];
+      const uint32_t ct = rec->content_type;
+      const bool text_desc = ct == TGI_CT_TEXT || ct == TGI_CT_VIDEO || ct == TGI_CT_PHOTO || ct == TGI_CT_ANIMATION;
+      const uint32_t dlen = text_desc ? ((rec->flags & TGI_RF_HAS_TEXT) ? rec->text_len : 0u) : rec->alt_len;
+      sparse = esc_desc_is_sparse(in.xlen[r * 8 + XL_DESC], dlen, in.xlen[r * 8 + XL_FLAGS]);
+    }
+    wl_append(in.list[WL_SPARSE], in.list_count + WL_SPARSE, active && sparse, (uint32_t)r);
+    wl_append(in.list[WL_DENSE], in.list_count + WL_DENSE, active && (((left & 1u) && !sparse) || (left & 0xEu)), (uint32_t)r);
+    wl_append(in.list[WL_MAPS], in.list_count + WL_MAPS, active && (left & 16u), (uint32_t)r);
   }
   for (int dd = 16; dd; dd >>= 1) {
     bytes_out += __shfl_down_sync(FULL, bytes_out, dd);
@@ -398,89 +424,44 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_lane_kernel(TgBatchDev
   }
 }
 
-// The esc and maps kernels take what the lane emitter left: each lane first checks one record of a
-// group of 32, then the warp walks the records that need it (most do not).  Two instantiations, launched one after the
-// other: ESC_SPARSE writes the descriptions whose only specials are a few line breaks (segment copies), ESC_DENSE the
-// rest (per-byte placement, exact UTF-8 path, long clean strings, the other three strings).
+// The esc and maps kernels take what the lane emitter left, from its work lists: one warp per listed record.
+// Two instantiations of the escape kernel by instruction footprint: ESC_SPARSE writes the descriptions whose only specials
+// are a few line breaks (segment copies), ESC_DENSE the rest (per-byte placement, exact UTF-8 path, long clean strings,
+// the other three strings).
 template <int MODE>
 __global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_esc_kernel(TgBatchDev b, EmitIn in) {
-  const int wid = threadIdx.x >> 5, l = lane_id();
-  const bool lane_mode = in.lane_text_max != 0xffffffffu;
-  const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
-  for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
-    const uint64_t r = g * 32 + l;
-    bool need = false;
-    if (r < b.n && in.status[r] == TGI_ST_EMITTED) {
-      need = true;
-      if (lane_mode) {  // same rule as emit_tg_lane: clean and short strings are already in place
-        const tgi_tg_rec* rec = &b.recs[r];
-        const uint4 xl = *(const uint4*)(in.xlen + r * 8);
-        const uint32_t ct = rec->content_type;
-        const bool text_desc = ct == TGI_CT_TEXT || ct == TGI_CT_VIDEO || ct == TGI_CT_PHOTO || ct == TGI_CT_ANIMATION;
-        const uint32_t dlen = text_desc ? ((rec->flags & TGI_RF_HAS_TEXT) ? rec->text_len : 0u)
-                                        : (ct == TGI_CT_ANIMATED_EMOJI || ct == TGI_CT_POLL || ct == TGI_CT_GIVEAWAY ||
-                                           ct == TGI_CT_PAID_MEDIA || ct == TGI_CT_DOCUMENT) ? rec->alt_len : 0u;
-        auto left = [&](uint32_t x, uint32_t n) { return x != 0 && !(x == n && n <= in.lane_text_max); };
-        const bool sparse = esc_desc_is_sparse(xl.x, dlen, in.xlen[r * 8 + XL_FLAGS]);
-        if (MODE == ESC_SPARSE) need = sparse;
-        else need = (left(xl.x, dlen) && !(MODE == ESC_DENSE && sparse)) || left(xl.y, rec->media_len) || left(xl.z, rec->handle_len) || left(xl.w, rec->alt_len);
-      } else if (MODE == ESC_SPARSE) {
-        need = false;
-      }
-    }
-    uint32_t todo = __ballot_sync(FULL, need);
-    while (todo) {
-      const uint64_t rr = g * 32 + (uint32_t)(__ffs(todo) - 1);
-      todo &= todo - 1;
-      TgWalkArgs a;
-      a.b = &b;
-      a.cfg = nullptr;
-      a.r = rr;
-      a.v = load_rec_view(b, rr);
-      if (lane_mode) emit_tg_escapes<MODE>(in.out + in.line_off[rr], a, in.xlen + rr * 8, in.xpos + rr * 8, in.lane_text_max);
-      else emit_tg_escapes<ESC_ALL>(in.out + in.line_off[rr], a, in.xlen + rr * 8, in.xpos + rr * 8, in.lane_text_max);
-    }
+  const int wid = threadIdx.x >> 5;
+  const uint32_t* list = in.list[MODE == ESC_SPARSE ? WL_SPARSE : WL_DENSE];
+  const uint32_t cnt = in.list_count[MODE == ESC_SPARSE ? WL_SPARSE : WL_DENSE];
+  const uint32_t nwarps = gridDim.x * WARPS_PER_CTA;
+  for (uint32_t i = blockIdx.x * WARPS_PER_CTA + wid; i < cnt; i += nwarps) {
+    const uint64_t rr = list[i];
+    TgWalkArgs a;
+    a.b = &b;
+    a.cfg = nullptr;
+    a.r = rr;
+    a.v = load_rec_view(b, rr);
+    emit_tg_escapes<MODE>(in.out + in.line_off[rr], a, in.xlen + rr * 8, in.xpos + rr * 8, in.lane_text_max);
   }
 }
 
 __global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_maps_kernel(TgBatchDev b, EmitIn in) {
   __shared__ MapScratch mss[WARPS_PER_CTA];
-  const int wid = threadIdx.x >> 5, l = lane_id();
-  const bool lane = in.lane_text_max != 0xffffffffu;  // the lane emitter ran: it wrote the simple cases (tg_lane.cuh)
-  const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
-  for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
-    const uint64_t rl = g * 32 + l;
-    bool need = false;
-    if (rl < b.n && in.status[rl] == TGI_ST_EMITTED) {
-      need = true;
-      if (lane) {
-        const bool list = !(b.recs[rl].flags & TGI_RF_COMMENTS_NIL) && b.comment_off[rl + 1] != b.comment_off[rl];
-        const bool map = b.react_off[rl + 1] != b.react_off[rl] && !(in.xlen[rl * 8 + XL_FLAGS] & XLF_SIMPLE_MAP);
-        need = list || map || in.link_count[rl] > LANE_LINKS_MAX;
-      }
-    }
-    uint32_t todo = __ballot_sync(FULL, need);
-    while (todo) {
-      const uint64_t r = g * 32 + (uint32_t)(__ffs(todo) - 1);
-      todo &= todo - 1;
-      uint8_t* line = in.out + in.line_off[r];
-      const uint32_t* xp = in.xpos + r * 8;
-      const bool comments_nil = (b.recs[r].flags & TGI_RF_COMMENTS_NIL) != 0;
-      const uint32_t c0 = b.comment_off[r], c1 = b.comment_off[r + 1];
-      if (comments_nil) {
-        if (!lane) gcopy_g(line + xp[XL_COMMENTS], (const uint8_t*)kNullLit, 4);
-      } else if (c1 == c0) {
-        if (!lane) gput2(line + xp[XL_COMMENTS], '[', ']');
-      } else {
-        emit_tg_comments(line + xp[XL_COMMENTS], &mss[wid], b, c0, c1);
-      }
-      const uint32_t r0 = b.react_off[r], r1 = b.react_off[r + 1];
-      if (!(lane && (r1 == r0 || (in.xlen[r * 8 + XL_FLAGS] & XLF_SIMPLE_MAP))))
-        emit_reaction_map(line + xp[XL_REACTIONS], &mss[wid], b.reacts, r0, r1, b.aux);
-      const uint32_t nl = in.link_count[r];
-      if (nl && !(lane && nl <= LANE_LINKS_MAX)) emit_tg_outlinks(line + xp[XL_OUTLINKS], in.arena + in.link_start[r], nl);
-      __syncwarp();
-    }
+  const int wid = threadIdx.x >> 5;
+  const uint32_t cnt = in.list_count[WL_MAPS], nwarps = gridDim.x * WARPS_PER_CTA;
+  for (uint32_t i = blockIdx.x * WARPS_PER_CTA + wid; i < cnt; i += nwarps) {
+    const uint64_t r = in.list[WL_MAPS][i];
+    uint8_t* line = in.out + in.line_off[r];
+    const uint32_t* xp = in.xpos + r * 8;
+    // the lane emitter wrote the simple cases itself (tg_lane.cuh): nil / empty comment lists, simple maps, short outlink lists
+    const bool comments_nil = (b.recs[r].flags & TGI_RF_COMMENTS_NIL) != 0;
+    const uint32_t c0 = b.comment_off[r], c1 = b.comment_off[r + 1];
+    if (!comments_nil && c1 != c0) emit_tg_comments(line + xp[XL_COMMENTS], &mss[wid], b, c0, c1);
+    const uint32_t r0 = b.react_off[r], r1 = b.react_off[r + 1];
+    if (r1 != r0 && !(in.xlen[r * 8 + XL_FLAGS] & XLF_SIMPLE_MAP)) emit_reaction_map(line + xp[XL_REACTIONS], &mss[wid], b.reacts, r0, r1, b.aux);
+    const uint32_t nl = in.link_count[r];
+    if (nl > LANE_LINKS_MAX) emit_tg_outlinks(line + xp[XL_OUTLINKS], in.arena + in.link_start[r], nl);
+    __syncwarp();
   }
 }
 

@@ -189,8 +189,9 @@ DEVI void lane_shared_fill(LaneShared& sh) {
 // One lane, one record.  `active` lanes emit; the others only keep the warp's control flow company.
 DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBatchDev& b, const CfgDev& cfg, uint64_t r, bool active,
                        uint8_t* out, const uint64_t* line_off, const uint32_t* xlen_g, uint32_t* xpos_g, const tgi_link* links,
-                       uint32_t nl, int* err, uint64_t& bytes_out, uint64_t& bytes_in) {
+                       uint32_t nl, int* err, uint64_t& bytes_out, uint64_t& bytes_in, uint32_t& left) {
   uint32_t gaps = 0, copied = 0;  // statistics: bytes left to the other emit kernels / bytes copied from HBM sources
+  left = 0;  // what this lane leaves to the other emit kernels: bit arg (XL_DESC..XL_ALT) = that string, bit 4 = a map / list
   TgWalkArgs a;
   a.b = &b;
   a.cfg = &cfg;
@@ -282,6 +283,7 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
       }
       const bool mine = on && xl == sn && sn <= LANE_TEXT_MAX;  // same rule in emit_tg_escapes
       g = mine ? 0u : xl;                                       // else the esc kernel writes it
+      if (g) left |= 1u << arg;
       if (mine) {
         src = sp;
         n = sn;
@@ -402,6 +404,7 @@ DEVI void emit_tg_lane(LaneShared& sh, uint32_t* row, LaneStream& s, const TgBat
       more = t + 1 < multi_max;
       padded = false;
     }
+    if (g && kind != K_ESC) left |= 16u;  // a comment list, a map or an outlink list for the maps kernel
     ls_skip(s, g);
     gaps += g;
     {  // the copy loop: one aligned 16-byte block of the source per step, bytes [0, n) of src

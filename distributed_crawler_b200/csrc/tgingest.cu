@@ -103,7 +103,7 @@ struct Slot {
       d_chans, d_chan_strs;
   // device intermediates / outputs
   DevBuf d_chan_derived, d_chan_len, d_chan_off, d_chan_blob, d_status, d_linelen, d_line_off,
-      d_link_start, d_link_count, d_xlen, d_xpos, d_arena, d_lstate, d_rec_new, d_new_off, d_link_off, d_links_out,
+      d_link_start, d_link_count, d_xlen, d_xpos, d_lists, d_arena, d_lstate, d_rec_new, d_new_off, d_link_off, d_links_out,
       d_link_off32, d_btable, d_tiles, d_scalars, d_jsonl, d_url_start, d_url_count, d_urls, d_ent_range;
   // pinned host outputs
   HostBuf h_status, h_line_off, h_jsonl, h_link_off, h_links, h_scalars;
@@ -332,7 +332,7 @@ int h2d(tgi_ctx* c, Slot& s, DevBuf& d, const T* src, size_t count) {
   return TGI_OK;
 }
 
-enum { SC_CHAN_TOTAL = 0, SC_LINE_TOTAL = 1, SC_CURSOR = 2, SC_NEW = 3, SC_FSIZE = 4, SC_LINK_TOTAL = 5, SC_LONG = 6, SC_URL_CURSOR = 7, SC_LANE_OUT = 8, SC_LANE_IN = 9, SC_COUNT = 10 };
+enum { SC_CHAN_TOTAL = 0, SC_LINE_TOTAL = 1, SC_CURSOR = 2, SC_NEW = 3, SC_FSIZE = 4, SC_LINK_TOTAL = 5, SC_LONG = 6, SC_URL_CURSOR = 7, SC_LANE_OUT = 8, SC_LANE_IN = 9, SC_LISTS = 10 /* 3 x u32 */, SC_COUNT = 12 };
 constexpr uint64_t HOST_VALIDATE_MAX = 1u << 16;  // batches up to this many elements are range-checked on the host
 
 // the checks of tg_validate_kernel, on the host (small batches: no extra launch / sync in a page-sized call)
@@ -371,7 +371,7 @@ int validate_tg(tgi_ctx* c, const tgi_tg_batch* in) {
     set_err(c, "telegram batch: recs/ent_off/react_off/comment_off/chans must be non-null");
     return TGI_E_ARG;
   }
-  if (in->n >= (1ull << 40)) { set_err(c, "telegram batch: too many records"); return TGI_E_ARG; }
+  if (in->n >= (1ull << 32)) { set_err(c, "telegram batch: too many records (the work lists hold 32-bit record indices)"); return TGI_E_ARG; }
   if (!(c->cfg.flags & TGI_CFG_SKIP_MEDIA)) {
     set_err(c, "TGI_CFG_SKIP_MEDIA is required: media download is an RPC outside this path");
     return TGI_E_ARG;
@@ -710,6 +710,9 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       CK(cudaEventRecord(s.ev_e0, st));
       CK(s.d_xpos.ensure(n * 32));
       ei.xpos = s.d_xpos.as<uint32_t>();
+      CK(s.d_lists.ensure(3 * n * 4));  // work lists of the clean-up kernels (record indices; n < 2^32 checked at upload)
+      for (int k = 0; k < 3; k++) ei.list[k] = s.d_lists.as<uint32_t>() + (size_t)k * n;
+      ei.list_count = (uint32_t*)(dsc + SC_LISTS);
       ei.lane_text_max = LANE_TEXT_MAX;
       // one LANE per record (tg_lane.cuh): 3 resident CTAs per SM by shared memory, persistent over the record groups
       unsigned gl = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * 3);
@@ -1163,7 +1166,7 @@ void tgi_destroy(tgi_ctx* c) {
     DevBuf* db[] = {&s.d_recs, &s.d_strs, &s.d_ent_off, &s.d_ents, &s.d_react_off, &s.d_reacts, &s.d_comment_off,
                     &s.d_comments, &s.d_aux, &s.d_chans, &s.d_chan_strs, &s.d_chan_derived, &s.d_chan_len,
                     &s.d_chan_off, &s.d_chan_blob, &s.d_status, &s.d_linelen, &s.d_line_off, &s.d_link_start,
-                    &s.d_link_count, &s.d_xlen, &s.d_xpos, &s.d_arena, &s.d_lstate, &s.d_rec_new, &s.d_new_off, &s.d_link_off,
+                    &s.d_link_count, &s.d_xlen, &s.d_xpos, &s.d_lists, &s.d_arena, &s.d_lstate, &s.d_rec_new, &s.d_new_off, &s.d_link_off,
                     &s.d_links_out, &s.d_link_off32, &s.d_btable, &s.d_tiles, &s.d_scalars, &s.d_jsonl,
                     &s.d_url_start, &s.d_url_count, &s.d_urls, &s.d_ent_range};
     for (DevBuf* d : db) d->release();
@@ -1343,6 +1346,41 @@ int tgi_plan_chunks(const uint64_t* line_off, uint64_t n, uint64_t trigger, uint
   }
   if (!flush(n)) return TGI_E_CAPACITY;  // :339-343
   *n_groups = g;
+  return TGI_OK;
+}
+
+int tgi_plan_channel_appends(const uint64_t* line_off, const void* chan_idx, uint32_t chan_stride, uint64_t n, tgi_append_run* runs,
+                             uint64_t max_runs, uint64_t* n_runs) {
+  if (!line_off || !n_runs || (n && !chan_idx) || (max_runs && !runs)) return TGI_E_ARG;
+  uint64_t g = 0;
+  bool open = false;
+  tgi_append_run cur{};
+  for (uint64_t i = 0; i < n; i++) {
+    if (line_off[i + 1] == line_off[i]) continue;  // no post was stored for this record
+    const uint32_t ch = *(const uint32_t*)((const uint8_t*)chan_idx + (size_t)i * chan_stride);
+    if (open && ch == cur.chan_idx) {  // lines without a post in between are empty ranges: the bytes stay contiguous
+      cur.end = i + 1;
+      cur.byte_end = line_off[i + 1];
+      cur.n_lines++;
+      continue;
+    }
+    if (open) {
+      if (g >= max_runs) return TGI_E_CAPACITY;
+      runs[g++] = cur;
+    }
+    cur.chan_idx = ch;
+    cur.n_lines = 1;
+    cur.first = i;
+    cur.end = i + 1;
+    cur.byte_begin = line_off[i];
+    cur.byte_end = line_off[i + 1];
+    open = true;
+  }
+  if (open) {
+    if (g >= max_runs) return TGI_E_CAPACITY;
+    runs[g++] = cur;
+  }
+  *n_runs = g;
   return TGI_OK;
 }
 
@@ -1853,6 +1891,9 @@ int tgi_frontier_merge(tgi_ctx* c, uint64_t* global_size, uint64_t* owned) {
   c->mstats.bucket_ms += t0;
   c->mstats.exchange_ms += t1;
   c->mstats.insert_ms += t2;
+  c->mstats.last_bucket_ms = t0;
+  c->mstats.last_exchange_ms = t1;
+  c->mstats.last_insert_ms = t2;
   c->merged_upto = sz;
   c->merge_round++;
   return TGI_OK;

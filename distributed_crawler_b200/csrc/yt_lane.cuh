@@ -171,6 +171,9 @@ struct YtLaneWriter {
   DEVI bool duration(const uint8_t* d, uint32_t dn, int64_t& vlen) { return yt_parse_duration(d, dn, vlen); }
 };
 
+// thread_esc_len is force-inlined; the sizer's walk has ~15 call sites of it: one shared copy keeps the kernel small
+__device__ __noinline__ uint32_t yt_thread_esc_len(const uint8_t* p, uint32_t n) { return thread_esc_len(p, n); }
+
 // length pass of the same walk, one lane per record.  The escaped lengths of the two long strings
 // (description, title) come from the warp (el[]); every other string is short and measured by the lane.
 struct YtLaneSizer {
@@ -182,7 +185,7 @@ struct YtLaneSizer {
   __align__(16) uint8_t num[64];
   DEVI void raw(const uint8_t*, uint32_t n) { total += n; }
   DEVI void esc(const uint8_t* p, uint32_t n) {
-    const uint32_t e = thread_esc_len(p, n);
+    const uint32_t e = yt_thread_esc_len(p, n);
     dirty = dirty || e != n;
     small_dirty = small_dirty || e != n;
     total += e;

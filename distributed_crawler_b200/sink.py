@@ -49,3 +49,31 @@ def write_combined(jsonl: bytes | np.ndarray, line_off: np.ndarray, combine_dir:
                         f.write(buf[int(line_off[i]): int(line_off[i + 1])])
         paths.append(path)
     return paths
+
+
+def plan_channel_appends(line_off: np.ndarray, recs: np.ndarray) -> np.ndarray:
+    """runs of consecutive lines of one channel (tgi_plan_channel_appends) -> abi.APPEND_RUN[]"""
+    from . import abi
+    line_off = np.ascontiguousarray(line_off, dtype=np.uint64)
+    n = len(line_off) - 1
+    runs = np.zeros(max(n, 1), abi.APPEND_RUN)
+    ng = C.c_uint64()
+    base = recs.ctypes.data + recs.dtype.fields["chan_idx"][1] if n else None
+    rc = engine.lib().tgi_plan_channel_appends(line_off.ctypes.data, base, recs.dtype.itemsize, n, runs.ctypes.data, len(runs), C.byref(ng))
+    if rc:
+        raise RuntimeError(f"tgi_plan_channel_appends: {rc}")
+    return runs[: ng.value]
+
+
+def append_posts(jsonl: bytes | np.ndarray, line_off: np.ndarray, recs: np.ndarray, channel_ids: list[str], base_path: str, crawl_id: str) -> int:
+    """LocalStateManager.StorePost for a whole result (state/storageproviders.go:275-298): <base>/<crawl>/<channel>/posts/
+    posts.jsonl gets the channel's lines, one append per run instead of one open / append / close per post.  Returns the
+    number of appends."""
+    buf = memoryview(jsonl)
+    runs = plan_channel_appends(line_off, recs)
+    for r in runs:
+        d = os.path.join(base_path, crawl_id, channel_ids[int(r["chan_idx"])], "posts")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "posts.jsonl"), "ab") as f:
+            f.write(buf[int(r["byte_begin"]): int(r["byte_end"])])
+    return len(runs)

@@ -393,6 +393,20 @@ int tgi_youtube_batch(tgi_ctx* ctx, const tgi_yt_batch* in, uint32_t run_flags, 
 int tgi_plan_chunks(const uint64_t* line_off, uint64_t n, uint64_t trigger, uint64_t hard_cap, uint64_t* groups,
                     uint64_t max_groups, uint64_t* n_groups, uint8_t* dropped);
 
+/* SURVEY 8f rank 1, local sink — LocalStateManager.StorePost opens, appends to and closes <crawl>/<channel>/posts/posts.jsonl
+ * once per POST (state/storageproviders.go:39-53,275-298).  The lines of consecutive records of one channel are contiguous
+ * in the result blob, so a run of them is ONE append of jsonl[byte_begin, byte_end): same file contents, one open / write
+ * / close per run instead of per post.  chan_idx / chan_stride: the channel row of every record (e.g. &recs[0].chan_idx,
+ * sizeof(tgi_tg_rec)); records without a line neither start nor break a run.  Pure host arithmetic.                   */
+typedef struct tgi_append_run {
+  uint32_t chan_idx;   /* channel row: the caller maps it to the channelID argument of StorePost                         */
+  uint32_t n_lines;    /* posts in this run                                                                             */
+  uint64_t first, end; /* records [first, end)                                                                          */
+  uint64_t byte_begin, byte_end; /* their lines in tgi_result.jsonl                                                     */
+} tgi_append_run;
+int tgi_plan_channel_appends(const uint64_t* line_off, const void* chan_idx, uint32_t chan_stride, uint64_t n,
+                             tgi_append_run* runs, uint64_t max_runs, uint64_t* n_runs);
+
 /* SURVEY §8f rank 2 — the message-status join.  The reference looks messages up by (ChatID, MessageID) with
  * string-keyed maps or linear scans: resampleMarker (crawl/runner.go:1572-1635), addNewMessages (:1650-1697), the
  * per-message search for the fetched *client.Message (:1171-1176), BaseStateManager.UpdateMessage's scan
@@ -464,7 +478,9 @@ int tgi_frontier_merge(tgi_ctx* ctx, uint64_t* global_size, uint64_t* owned);
 int tgi_frontier_global_export(tgi_ctx* ctx, uint8_t* keys32, uint64_t cap, uint64_t* n);
 typedef struct tgi_merge_stats {
   uint64_t merges, keys_sent, keys_received, keys_owned, bytes_sent;
-  double bucket_ms, exchange_ms, insert_ms; /* device time, summed over the merges */
+  double bucket_ms, exchange_ms, insert_ms; /* device time between the phases' events, summed over the merges: includes
+                                               waiting for the slowest rank and, in the first merge, NCCL's connection set-up */
+  double last_bucket_ms, last_exchange_ms, last_insert_ms; /* the same for the most recent merge only */
 } tgi_merge_stats;
 int tgi_merge_get_stats(tgi_ctx* ctx, tgi_merge_stats* out);
 

@@ -60,3 +60,33 @@ def test_write_combined_concatenates_lines(engine_lib, tmp_path):
     got = b"".join(open(p, "rb").read() for p in paths)
     assert got == b"".join(l for i, l in enumerate(lines) if i != 20)
     assert all(len(open(p, "rb").read()) <= 130 for p in paths)
+
+
+def test_channel_appends_equal_per_post_appends(engine_lib, tmp_path):
+    """tgi_plan_channel_appends / sink.append_posts against LocalStateManager.StorePost called once per post
+    (state/storageproviders.go:39-53,275-298): identical posts.jsonl per channel, far fewer open/append/close cycles."""
+    import os
+    from distributed_crawler_b200 import abi
+    rnd = random.Random(9)
+    n, n_chans = 400, 7
+    recs = np.zeros(n, abi.TG_REC)
+    chan, lines = 0, []
+    for i in range(n):
+        if rnd.random() < 0.1:
+            chan = rnd.randrange(n_chans)  # pages of several channels in one batch; channels come back later
+        recs["chan_idx"][i] = chan
+        lines.append(b"" if rnd.random() < 0.15 else b'{"i":%d,"c":%d}\n' % (i, chan))
+    blob = b"".join(lines)
+    line_off = np.concatenate([[0], np.cumsum([len(l) for l in lines])]).astype(np.uint64)
+    names = ["chan%d" % c for c in range(n_chans)]
+    ref = {}
+    for i, l in enumerate(lines):  # StorePost per post: append to the channel's file
+        if l:
+            ref.setdefault(names[int(recs["chan_idx"][i])], []).append(l)
+    appends = sink.append_posts(blob, line_off, recs, names, str(tmp_path), "crawl1")
+    for name, ls in ref.items():
+        assert open(os.path.join(tmp_path, "crawl1", name, "posts", "posts.jsonl"), "rb").read() == b"".join(ls)
+    runs = sink.plan_channel_appends(line_off, recs)
+    assert appends == len(runs) < sum(1 for l in lines if l) / 3
+    assert int(runs["n_lines"].sum()) == sum(1 for l in lines if l)
+    assert sink.plan_channel_appends(np.zeros(1, np.uint64), recs[:0]).size == 0

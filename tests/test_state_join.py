@@ -61,3 +61,27 @@ def test_gpu_join_matches_oracle():
     b = rnd.integers(-50000, 50000, size=(200000, 2))
     assert np.array_equal(e.key_join(a, b), Oracle.key_join(a, b))
     e.close()
+
+
+def test_update_messages_batch_equals_sequential_update_message():
+    """state_join.update_messages_batch against BaseStateManager.UpdateMessage (state/base.go:182-215) called once per
+    update: first match wins, unknown keys append, later updates hit what was appended."""
+    import random
+    from distributed_crawler_b200.state_join import update_messages_batch
+    rnd = random.Random(3)
+    for trial in range(50):
+        page = [(rnd.randrange(3), rnd.randrange(12)) for _ in range(rnd.randrange(0, 25))]  # duplicates on purpose
+        status = [rnd.choice(["unfetched", "fetched"]) for _ in page]
+        ups = [((rnd.randrange(3), rnd.randrange(16)), rnd.choice(["fetched", "failed", "deleted"])) for _ in range(rnd.randrange(0, 40))]
+        want_keys, want_status = list(page), list(status)
+        for k, st in ups:  # the reference, one call per update
+            for i, pk in enumerate(want_keys):
+                if pk == k:
+                    want_status[i] = st
+                    break
+            else:
+                want_keys.append(k)
+                want_status.append(st)
+        keys, got = update_messages_batch(Oracle.key_join, np.array(page, np.int64).reshape(-1, 2), status,
+                                          np.array([k for k, _ in ups], np.int64).reshape(-1, 2), [s for _, s in ups])
+        assert [tuple(map(int, k)) for k in keys] == want_keys and got == want_status, trial
