@@ -196,10 +196,13 @@ def cpu_baseline(cfg, batch, cores):
     flags = cfg["flags"] | ORC_RUN_SLICES | ORC_RUN_PIN
     o = Oracle()
     orc_run(o, cfg, batch, flags, cores)  # warm-up: grow the context-owned buffers
-    pyoracle.lib().orc_frontier_clear(o.h)
-    t0 = time.perf_counter()
-    orc_run(o, cfg, batch, flags, cores)
-    dt = time.perf_counter() - t0
+    dt = None
+    for _ in range(3):  # best of three: the sample is short and the box's other tenants show up in a single run
+        pyoracle.lib().orc_frontier_clear(o.h)
+        t0 = time.perf_counter()
+        orc_run(o, cfg, batch, flags, cores)
+        d = time.perf_counter() - t0
+        dt = d if dt is None else min(dt, d)
     o.close()
     o1 = Oracle()
     n1 = max(1, batch.n // 20)
@@ -515,7 +518,7 @@ def main():
             cpu = {"value": cpu_v, "unit": UNIT, "cores": cores, "cores_basis": cores_why, "kind": "port", "one_thread": cpu_v1,
                    "per_thread_efficiency": (cpu_v / cores / cpu_v1) if cpu_v1 else None,
                    "sample": f"first {sample_n} records of the same corpus, {cpu_dt:.1f} s, C restatement of the Go path (oracle), same run flags, "
-                             f"{cores} threads pinned one per core, warm"}
+                             f"{cores} threads pinned one per core, warm, best of 3"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "u8",
