@@ -67,24 +67,31 @@ __global__ void tg_validate_kernel(TgBatchDev b, TgBounds lim, uint64_t count, i
 }
 
 // ---- channel job -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CTA_THREADS) tg_chan_size_kernel(TgBatchDev b, ChanDerived* cd, uint32_t* len) {
-  int wid = threadIdx.x >> 5;
-  uint32_t c = blockIdx.x * WARPS_PER_CTA + wid;
-  if (c >= b.n_chans) return;
-  ChanDerived d = size_tg_chan(b, c);
-  if (lane_id() == 0) {
-    cd[c] = d;
-    len[c] = pad16(d.user_len) + pad16(d.name_len) + pad16(d.title_len) + pad16(d.cdata_len);
+// Every kernel of the Telegram pipeline is a *_body (grid-stride over blockIdx / gridDim) plus a one-line __global__
+// wrapper: the page kernel (tg_page.cuh) runs the same bodies as phases of ONE cooperative launch.
+DEVI void tg_chan_size_body(const TgBatchDev& b, ChanDerived* cd, uint32_t* len) {
+  const int wid = threadIdx.x >> 5;
+  for (uint32_t c = blockIdx.x * WARPS_PER_CTA + wid; c < b.n_chans; c += gridDim.x * WARPS_PER_CTA) {
+    ChanDerived d = size_tg_chan(b, c);
+    if (lane_id() == 0) {
+      cd[c] = d;
+      len[c] = pad16(d.user_len) + pad16(d.name_len) + pad16(d.title_len) + pad16(d.cdata_len);
+    }
   }
 }
+__global__ void __launch_bounds__(CTA_THREADS) tg_chan_size_kernel(TgBatchDev b, ChanDerived* cd, uint32_t* len) { tg_chan_size_body(b, cd, len); }
 
-__global__ void __launch_bounds__(CTA_THREADS) tg_chan_emit_kernel(TgBatchDev b, ChanDerived* cd, const uint64_t* off, uint8_t* blob) {
+DEVI void tg_chan_emit_body(const TgBatchDev& b, ChanDerived* cd, const uint64_t* off, uint8_t* blob, bool write_off = true) {
   __shared__ WarpScratch wss[WARPS_PER_CTA];
-  int wid = threadIdx.x >> 5;
-  uint32_t c = blockIdx.x * WARPS_PER_CTA + wid;
-  if (c >= b.n_chans) return;
-  if (lane_id() == 0) cd[c].off = off[c];
-  emit_tg_chan(blob + off[c], &wss[wid], b, c);
+  const int wid = threadIdx.x >> 5;
+  for (uint32_t c = blockIdx.x * WARPS_PER_CTA + wid; c < b.n_chans; c += gridDim.x * WARPS_PER_CTA) {
+    if (write_off && lane_id() == 0) cd[c].off = off[c];
+    emit_tg_chan(blob + off[c], &wss[wid], b, c);
+    __syncwarp();
+  }
+}
+__global__ void __launch_bounds__(CTA_THREADS) tg_chan_emit_kernel(TgBatchDev b, ChanDerived* cd, const uint64_t* off, uint8_t* blob) {
+  tg_chan_emit_body(b, cd, off, blob);
 }
 
 // ---- parse: status + links + line length ---------------------------------------------------------
@@ -176,7 +183,7 @@ DEVI void parse_one_record(const TgBatchDev& b, const CfgDev& cfg, const ParseOu
 // one parse kernel (2 560 SASS instructions) showed 3.5 stall_no_instruction cycles per issue in round 1; the round-2
 // attempt to fold parse + size into ONE pass over the text (8.7 G instead of 9.2 G warp instructions per 10 M
 // messages) ran at 18.6 no_instruction stall cycles per issue and took 27.2 ms instead of 14.3 (profiles/README.md).
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) {
+DEVI void tg_parse_body(const TgBatchDev& b, const CfgDev& cfg, uint32_t run_flags, const ParseOut& o) {
   int wid = threadIdx.x >> 5;
   uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
@@ -198,7 +205,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_kernel(TgBatchDev b, 
     }
   }
 }
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_ent_map_kernel(TgBatchDev b, ParseOut o) {
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) { tg_parse_body(b, cfg, run_flags, o); }
+DEVI void tg_ent_map_body(const TgBatchDev& b, const ParseOut& o) {
   const int wid = threadIdx.x >> 5, l = lane_id();
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
@@ -211,7 +219,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_ent_map_kernel(TgBatchDev b
     }
   }
 }
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_ent_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) {
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_ent_map_kernel(TgBatchDev b, ParseOut o) { tg_ent_map_body(b, o); }
+DEVI void tg_parse_ent_body(const TgBatchDev& b, const CfgDev& cfg, uint32_t run_flags, const ParseOut& o) {
   const int wid = threadIdx.x >> 5, l = lane_id();
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
@@ -224,12 +233,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_ent_kernel(TgBatchDev
     }
   }
 }
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_ent_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) {
+  tg_parse_ent_body(b, cfg, run_flags, o);
+}
 
 // The same sizes, 32 records per warp: every lane sizes the small pieces of its own record (numbers,
 // handle / media strings, comments, reactions, outlinks); only the message text, the one long string,
 // is measured by the whole warp, record after record; the rare complicated pieces (a comment list, a
 // reactions map that is not "simple") go through the warp-wide routines as well.
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_lane_kernel(TgBatchDev b, CfgDev cfg, ParseOut o) {
+DEVI void tg_size_lane_body(const TgBatchDev& b, const CfgDev& cfg, const ParseOut& o) {
   const int wid = threadIdx.x >> 5, l = lane_id();
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   uint64_t var_sum = 0;
@@ -351,6 +363,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_lane_kernel(TgBatchDev
   for (int dd = 16; dd; dd >>= 1) var_sum += __shfl_down_sync(FULL, var_sum, dd);
   if (l == 0 && var_sum) atomicAdd(o.var_total, (unsigned long long)var_sum);
 }
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_lane_kernel(TgBatchDev b, CfgDev cfg, ParseOut o) { tg_size_lane_body(b, cfg, o); }
 
 // ---- emit --------------------------------------------------------------------------------------------------------
 struct EmitIn {
@@ -381,9 +394,7 @@ DEVI void wl_append(uint32_t* list, uint32_t* count, bool need, uint32_t value) 
 }
 
 // the same job, one LANE per record (tg_lane.cuh): 32 records per warp task
-__global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_lane_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
-  extern __shared__ __align__(128) uint8_t lane_smem[];
-  LaneShared& sh = *(LaneShared*)lane_smem;
+DEVI void tg_emit_lane_body(const TgBatchDev& b, const CfgDev& cfg, const EmitIn& in, LaneShared& sh) {
   static_assert(LANE_WARPS == WARPS_PER_CTA, "one field row block per warp");
   lane_shared_fill(sh);
   __syncthreads();
@@ -423,13 +434,17 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_lane_kernel(TgBatchDev
     atomicAdd(in.counters + 1, (unsigned long long)bytes_in);
   }
 }
+__global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_lane_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
+  extern __shared__ __align__(128) uint8_t lane_smem[];
+  tg_emit_lane_body(b, cfg, in, *(LaneShared*)lane_smem);
+}
 
 // The esc and maps kernels take what the lane emitter left, from its work lists: one warp per listed record.
 // Two instantiations of the escape kernel by instruction footprint: ESC_SPARSE writes the descriptions whose only specials
 // are a few line breaks (segment copies), ESC_DENSE the rest (per-byte placement, exact UTF-8 path, long clean strings,
 // the other three strings).
 template <int MODE>
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_esc_kernel(TgBatchDev b, EmitIn in) {
+DEVI void tg_emit_esc_body(const TgBatchDev& b, const EmitIn& in) {
   const int wid = threadIdx.x >> 5;
   const uint32_t* list = in.list[MODE == ESC_SPARSE ? WL_SPARSE : WL_DENSE];
   const uint32_t cnt = in.list_count[MODE == ESC_SPARSE ? WL_SPARSE : WL_DENSE];
@@ -444,8 +459,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_esc_kernel(TgBatchDev 
     emit_tg_escapes<MODE>(in.out + in.line_off[rr], a, in.xlen + rr * 8, in.xpos + rr * 8, in.lane_text_max);
   }
 }
+template <int MODE>
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_esc_kernel(TgBatchDev b, EmitIn in) { tg_emit_esc_body<MODE>(b, in); }
 
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_maps_kernel(TgBatchDev b, EmitIn in) {
+DEVI void tg_emit_maps_body(const TgBatchDev& b, const EmitIn& in) {
   __shared__ MapScratch mss[WARPS_PER_CTA];
   const int wid = threadIdx.x >> 5;
   const uint32_t cnt = in.list_count[WL_MAPS], nwarps = gridDim.x * WARPS_PER_CTA;
@@ -464,6 +481,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_maps_kernel(TgBatchDev
     __syncwarp();
   }
 }
+__global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_maps_kernel(TgBatchDev b, EmitIn in) { tg_emit_maps_body(b, in); }
 
 // ---- YouTube (config 4) ------------------------------------------------------------------------------
 struct YtOut {
@@ -967,12 +985,12 @@ DEVI bool link_eligible(const tgi_link& lk, uint32_t run_flags) {
 }
 
 // phase 1: probe the persistent set; unseen keys race into the batch table, min sequence wins
-__global__ void frontier_probe_kernel(uint64_t n, const uint32_t* link_start, const uint32_t* link_count,
-                                      tgi_link* arena, uint32_t run_flags, FrontierDev f, FrontierBatch fb, ExclusionDev x) {
-  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
+DEVI void frontier_probe_body(uint64_t n, const uint32_t* link_start, const uint32_t* link_count, tgi_link* arena,
+                              uint32_t run_flags, const FrontierDev& f, const FrontierBatch& fb, const ExclusionDev& x,
+                              uint64_t t0, uint64_t nt) {  // thread t0 of nt: the whole grid, or one CTA (page kernel)
+ for (uint64_t r = t0; r < n; r += nt) {
   uint32_t cnt = link_count[r];
-  if (!cnt) return;
+  if (!cnt) continue;
   uint32_t ls = link_start ? link_start[r] : (uint32_t)r;
   for (uint32_t k = 0; k < cnt; k++) {
     uint32_t idx = ls + k;
@@ -1028,33 +1046,41 @@ __global__ void frontier_probe_kernel(uint64_t n, const uint32_t* link_start, co
       }
     }
   }
+ }
+}
+__global__ void frontier_probe_kernel(uint64_t n, const uint32_t* link_start, const uint32_t* link_count,
+                                      tgi_link* arena, uint32_t run_flags, FrontierDev f, FrontierBatch fb, ExclusionDev x) {
+  frontier_probe_body(n, link_start, link_count, arena, run_flags, f, fb, x, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, (uint64_t)gridDim.x * blockDim.x);
 }
 
 // phase 2: per record, how many of its links are the global first occurrence of a new key
+DEVI void frontier_count_body(uint64_t n, const uint32_t* link_start, const uint32_t* link_count, const FrontierBatch& fb,
+                              uint64_t t0, uint64_t nt) {
+  for (uint64_t r = t0; r < n; r += nt) {
+    uint32_t cnt = link_count[r], c = 0;
+    uint32_t ls = link_start ? link_start[r] : (uint32_t)r;
+    for (uint32_t k = 0; k < cnt; k++) {
+      uint32_t st = fb.lstate[ls + k];
+      if (st >= LS_KNOWN) continue;
+      if (fb.btable[st] == (((uint64_t)r << SEQ_ORD_BITS) | k) + 1) c++;
+    }
+    fb.rec_new[r] = c;
+  }
+}
 __global__ void frontier_count_kernel(uint64_t n, const uint32_t* link_start, const uint32_t* link_count,
                                       FrontierBatch fb) {
-  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  uint32_t cnt = link_count[r], c = 0;
-  uint32_t ls = link_start ? link_start[r] : (uint32_t)r;
-  for (uint32_t k = 0; k < cnt; k++) {
-    uint32_t st = fb.lstate[ls + k];
-    if (st >= LS_KNOWN) continue;
-    if (fb.btable[st] == (((uint64_t)r << SEQ_ORD_BITS) | k) + 1) c++;
-  }
-  fb.rec_new[r] = c;
+  frontier_count_body(n, link_start, link_count, fb, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, (uint64_t)gridDim.x * blockDim.x);
 }
 
 // phase 3: append the new keys to the pool in (record, ordinal) order and publish them
-__global__ void frontier_append_kernel(uint64_t n, const uint32_t* link_start, const uint32_t* link_count,
-                                       tgi_link* arena, FrontierDev f, FrontierBatch fb,
-                                       const uint64_t* new_off, int* err, const uint64_t* payload_in = nullptr) {
-  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  if (!fb.rec_new[r]) return;
+DEVI void frontier_append_body(uint64_t n, const uint32_t* link_start, const uint32_t* link_count, tgi_link* arena,
+                               const FrontierDev& f, const FrontierBatch& fb, const uint64_t* new_off, int* err,
+                               const uint64_t* payload_in, uint64_t t0, uint64_t nt) {
+ for (uint64_t r = t0; r < n; r += nt) {
+  if (!fb.rec_new[r]) continue;
   uint64_t base = *f.count, total = new_off[n];
   if (base + total > f.cap) {
-    if (r == 0 || true) atomicOr(err, ERR_FRONTIER_FULL);
+    atomicOr(err, ERR_FRONTIER_FULL);
     return;
   }
   uint32_t cnt = link_count[r];
@@ -1078,8 +1104,14 @@ __global__ void frontier_append_kernel(uint64_t n, const uint32_t* link_start, c
     lk.flags |= TGI_LF_NEW;
     pi++;
   }
+ }
 }
-__global__ void frontier_commit_kernel(FrontierDev f, const uint64_t* new_off, uint64_t n, uint64_t* out_new, int* err) {
+__global__ void frontier_append_kernel(uint64_t n, const uint32_t* link_start, const uint32_t* link_count,
+                                       tgi_link* arena, FrontierDev f, FrontierBatch fb,
+                                       const uint64_t* new_off, int* err, const uint64_t* payload_in = nullptr) {
+  frontier_append_body(n, link_start, link_count, arena, f, fb, new_off, err, payload_in, (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, (uint64_t)gridDim.x * blockDim.x);
+}
+DEVI void frontier_commit_body(const FrontierDev& f, const uint64_t* new_off, uint64_t n, uint64_t* out_new, int* err) {
   uint64_t total = new_off[n];
   if (*f.count + total <= f.cap) {
     *f.count += total;
@@ -1089,6 +1121,9 @@ __global__ void frontier_commit_kernel(FrontierDev f, const uint64_t* new_off, u
     atomicOr(err, ERR_FRONTIER_FULL);
   }
   out_new[1] = *f.count;
+}
+__global__ void frontier_commit_kernel(FrontierDev f, const uint64_t* new_off, uint64_t n, uint64_t* out_new, int* err) {
+  frontier_commit_body(f, new_off, n, out_new, err);
 }
 
 // ---- multi-GPU merge (SURVEY 8e option A): bucket the new local keys by owner rank ----------------------------------
@@ -1173,17 +1208,21 @@ __global__ void links_new_flags_kernel(const tgi_link* arena, uint64_t n, uint8_
 }
 
 // ---- compaction of the per-record links for the host result -----------------------------------------
+DEVI void links_compact_body(uint64_t n, const uint32_t* link_start, const uint32_t* link_count, const uint64_t* link_off,
+                             const tgi_link* arena, tgi_link* out, uint32_t* link_off32) {
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= n; r += (uint64_t)gridDim.x * blockDim.x) {
+    link_off32[r] = (uint32_t)link_off[r];
+    if (r == n) break;
+    uint32_t cnt = link_count[r];
+    const uint32_t* src = (const uint32_t*)(arena + link_start[r]);
+    uint32_t* dst = (uint32_t*)(out + link_off[r]);
+    for (uint32_t k = 0; k < cnt * 9; k++) dst[k] = src[k];
+  }
+}
 __global__ void links_compact_kernel(uint64_t n, const uint32_t* link_start, const uint32_t* link_count,
                                      const uint64_t* link_off, const tgi_link* arena, tgi_link* out,
                                      uint32_t* link_off32) {
-  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r > n) return;
-  link_off32[r] = (uint32_t)link_off[r];
-  if (r == n) return;
-  uint32_t cnt = link_count[r];
-  const uint32_t* src = (const uint32_t*)(arena + link_start[r]);
-  uint32_t* dst = (uint32_t*)(out + link_off[r]);
-  for (uint32_t k = 0; k < cnt * 9; k++) dst[k] = src[k];
+  links_compact_body(n, link_start, link_count, link_off, arena, out, link_off32);
 }
 
 // FilterUsername over a list of names (tgi_filter_usernames): one warp per name

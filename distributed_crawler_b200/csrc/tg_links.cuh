@@ -217,6 +217,13 @@ __device__ __noinline__ void warp_utf16_to_bytes(const uint8_t* s, int64_t n, in
     uint32_t e, u;
     strip_lane_totals(st, s, base, n, e, u);
     uint32_t incl = warp_incl_scan(u);
+    {  // neither offset falls into this strip's units [run, run + total): nothing to look for (most strips of a long text)
+      const uint32_t total = __shfl_sync(FULL, incl, 31);
+      if ((uint32_t)off16 - run >= total && (uint32_t)stop - run >= total) {
+        run += total;
+        continue;
+      }
+    }
     uint32_t pos = run + incl - u;  // u16pos before this lane's first byte
     // visit the lane's rune starts in order
     int64_t hit_start = -1, hit_end = -1;

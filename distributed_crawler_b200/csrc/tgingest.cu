@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -19,6 +20,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "tg_page.cuh"
 
 using namespace tgi;
 
@@ -54,12 +56,13 @@ struct DevBuf {
 struct HostBuf {  // pinned
   void* p = nullptr;
   size_t cap = 0;
+  unsigned flags = cudaHostAllocDefault;
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap && p) return cudaSuccess;
     if (p) cudaFreeHost(p);
     p = nullptr;
     size_t want = bytes + bytes / 8 + 64;
-    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(&p, want, flags);
     cap = e == cudaSuccess ? want : 0;
     return e;
   }
@@ -97,6 +100,7 @@ struct NcclApi {
 struct Slot {
   int idx = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_in = nullptr, stream_out = nullptr;  // bulk batches: uploads / result copies off the kernels' stream (copy_streams())
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_mid = nullptr, ev_p0 = nullptr, ev_p1 = nullptr, ev_e0 = nullptr, ev_e1 = nullptr, ev_f1 = nullptr, ev_fr0 = nullptr, ev_fr1 = nullptr;
   // device inputs
   DevBuf d_recs, d_strs, d_ent_off, d_ents, d_react_off, d_reacts, d_comment_off, d_comments, d_aux,
@@ -107,12 +111,17 @@ struct Slot {
       d_link_off32, d_btable, d_tiles, d_scalars, d_jsonl, d_url_start, d_url_count, d_urls, d_ent_range;
   // pinned host outputs
   HostBuf h_status, h_line_off, h_jsonl, h_link_off, h_links, h_scalars;
+  // page-sized Telegram batches (tg_page.cuh): the input arrays in ONE block / copy, the result arrays in one block / copy
+  DevBuf d_page_in, d_page_out;
+  HostBuf h_page_in, h_page_out;
+  uint32_t page_bpr = 3072;              // running estimate of result bytes per record (sizes the speculative read)
+  const uint8_t* dev_jsonl = nullptr;    // where the last batch's JSONL lives on the device (tgi_result_read_jsonl)
   // resident batch descriptor
   TgBatchDev tg{};
   YtBatchDev yt{};
   GmBatchDev gm{};
   uint64_t yt_desc_bytes = 0;
-  uint64_t n_ents = 0, n_reacts = 0, n_comments = 0, in_bytes = 0;
+  uint64_t n_ents = 0, n_reacts = 0, n_comments = 0, in_bytes = 0, chan_strs_len = 0;
   bool resident = false;
   uint64_t dev_jsonl_len = 0;
   // what tgi_pending_edges needs from the slot's last batch
@@ -127,6 +136,8 @@ struct Slot {
   const tgi_yt_batch* in_yt = nullptr;
   const tgi_gm_batch* in_gm = nullptr;
   uint32_t run_flags = 0;
+  uint64_t ticket = 0;
+  bool has_ticket = false;
   int rc = 0;
   tgi_result res{};
   std::thread worker;
@@ -142,6 +153,7 @@ struct tgi_ctx {
   std::string err;
   std::mutex err_mu;
   Slot slots[TGI_SLOTS];
+  HostBuf h_zero;  // PAD pinned zero bytes (h2d)
   // config blob on device
   DevBuf d_cfg;
   CfgDev cfgdev{};
@@ -152,6 +164,11 @@ struct tgi_ctx {
   std::mutex fr_mu;
   cudaEvent_t fr_event = nullptr;
   bool fr_event_valid = false;
+  // frontier turns: batches with TGI_RUN_FRONTIER take a ticket when they are submitted and enter their frontier phase in
+  // ticket order, so NEW flags / n_new / the export order are those of one thread processing the batches in submission order
+  std::mutex tk_mu;
+  std::condition_variable tk_cv;
+  uint64_t tk_next = 0, tk_serving = 0;
   InsertScratch ins;  // scratch of tgi_frontier_insert* / the merge (under fr_mu)
   // frontier -> validator hand-off: resident exclusion sets (tgi_set_add)
   DevBuf x_pool[2], x_table[2], x_count[2], x_payload;
@@ -195,6 +212,16 @@ void set_err(tgi_ctx* c, const char* fmt, ...) {
   } else {
     g_create_err = buf;
   }
+}
+
+// TGI_TRACE_SLOTS=1: host time (ms since the first stamp) at the synchronisation points of a bulk batch, one line each,
+// to stderr — the only timeline tool this image has (no nsys): which slot's copies / kernels overlap with which
+void trace_slot(const Slot& s, const char* what) {
+  static const bool on = getenv("TGI_TRACE_SLOTS") != nullptr;
+  if (!on) return;
+  static const auto t0 = std::chrono::steady_clock::now();
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  fprintf(stderr, "slot %d %9.3f ms  %s\n", s.idx, ms, what);
 }
 
 #define CK(call)                                                                        \
@@ -322,13 +349,47 @@ int launch_scan(tgi_ctx* c, Slot& s, const uint32_t* in, uint64_t n, uint64_t* o
   return TGI_OK;
 }
 
+// bit 0: result copies on the slot's stream_out, bit 1: uploads on its stream_in (A/B switch, TGI_COPY_STREAMS)
+int copy_streams() {
+  static const int v = [] {
+    const char* e = getenv("TGI_COPY_STREAMS");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
 template <class T>
 int h2d(tgi_ctx* c, Slot& s, DevBuf& d, const T* src, size_t count) {
   size_t bytes = count * sizeof(T);
+  cudaStream_t st = (copy_streams() & 2) ? s.stream_in : s.stream;
   CK(d.ensure(bytes));
-  if (bytes) CK(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, s.stream));
-  CK(cudaMemsetAsync((uint8_t*)d.p + bytes, 0, PAD, s.stream));
+  if (bytes) CK(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, st));
+  // the pad behind the array: a COPY of zeros, not a memset — a memset is a kernel and would queue behind whatever the
+  // other slots' (persistent, SM-filling) kernels are doing, which chains every one of the eleven uploads to them
+  CK(cudaMemcpyAsync((uint8_t*)d.p + bytes, c->h_zero.p, PAD, cudaMemcpyHostToDevice, st));
   s.in_bytes += bytes;
+  return TGI_OK;
+}
+// the kernels' stream continues behind the uploads
+int join_uploads(tgi_ctx* c, Slot& s) {
+  if (!(copy_streams() & 2)) return TGI_OK;
+  CK(cudaEventRecord(s.ev_mid, s.stream_in));
+  CK(cudaStreamWaitEvent(s.stream, s.ev_mid, 0));
+  return TGI_OK;
+}
+
+// Small read-backs (the scalars block between the size and the emit pass, the validation flag) do NOT go through the copy
+// engine: a device->host cudaMemcpyAsync queues behind the other slots' bulk result copies (1.1 GB each at 500 K messages)
+// and the slot's host thread then waits ~45 ms for 96 bytes — measured with TGI_TRACE_SLOTS, profiles/README.md.  A
+// one-warp kernel stores them into mapped pinned memory instead; the host sees them after the stream synchronises.
+__global__ void publish_kernel(const uint64_t* src, uint64_t* dst_mapped, int n) {
+  if ((int)threadIdx.x < n) dst_mapped[threadIdx.x] = src[threadIdx.x];
+  __threadfence_system();
+}
+int publish(tgi_ctx* c, const void* d_src, HostBuf& h, int n_words, cudaStream_t st) {
+  void* dp = nullptr;
+  CK(cudaHostGetDevicePointer(&dp, h.p, 0));
+  publish_kernel<<<1, 32, 0, st>>>((const uint64_t*)d_src, (uint64_t*)dp, n_words);
+  CK(cudaGetLastError());
   return TGI_OK;
 }
 
@@ -389,12 +450,84 @@ int validate_tg(tgi_ctx* c, const tgi_tg_batch* in) {
   return TGI_OK;
 }
 
+// ---- page-sized batches: one block in, one launch, one block out (tg_page.cuh) ---------------------------------------
+constexpr uint64_t PAGE_MAX_RECS = 8192;          // the in-kernel scans are single-CTA
+constexpr uint64_t PAGE_MAX_IN_BYTES = 4u << 20;
+bool page_enabled() {
+  return getenv("TGI_NO_PAGE") == nullptr;  // A/B switch (read per call): the ordinary pipeline for every size
+}
+struct PageInLayout {
+  size_t off[11], bytes[11], total;
+};
+PageInLayout page_in_layout(const tgi_tg_batch* in, uint64_t n_ents) {
+  const uint64_t n = in->n;
+  const size_t b[11] = {n * sizeof(tgi_tg_rec), in->strs_len, (n + 1) * 4, n_ents * sizeof(tgi_entity), (n + 1) * 4,
+                        in->n_reacts * sizeof(tgi_reaction), (n + 1) * 4, in->n_comments * sizeof(tgi_comment), in->aux_len,
+                        in->n_chans * sizeof(tgi_tg_chan), in->chan_strs_len};
+  PageInLayout L;
+  size_t o = 0;
+  for (int i = 0; i < 11; i++) {
+    L.off[i] = o;
+    L.bytes[i] = b[i];
+    o += (b[i] + PAD + 15) & ~(size_t)15;  // PAD readable zero bytes behind every array, as h2d() leaves them
+  }
+  L.total = o;
+  return L;
+}
+bool page_sized(const tgi_tg_batch* in, uint64_t n_ents) {
+  if (!page_enabled() || in->n == 0 || in->n > PAGE_MAX_RECS || in->n_chans > PAGE_MAX_RECS) return false;
+  if (in->n + n_ents + in->n_reacts + in->n_comments + in->n_chans > HOST_VALIDATE_MAX) return false;  // validate_tg checked every offset
+  return page_in_layout(in, n_ents).total <= PAGE_MAX_IN_BYTES;
+}
+
+// The eleven input arrays packed into one pinned block and sent with ONE copy (eleven copies + eleven pad memsets are a
+// third of what a 100-message call costs otherwise).  The pack is a host memcpy of the page (tens of KB).
+int upload_tg_page(tgi_ctx* c, Slot& s, const tgi_tg_batch* in, uint64_t n_ents) {
+  const uint64_t n = in->n;
+  const PageInLayout L = page_in_layout(in, n_ents);
+  CK(s.h_page_in.ensure(L.total));
+  CK(s.d_page_in.ensure(L.total));
+  uint8_t* h = s.h_page_in.as<uint8_t>();
+  const void* src[11] = {in->recs, in->strs, in->ent_off, in->ents, in->react_off, in->reacts, in->comment_off, in->comments,
+                         in->aux, in->chans, in->chan_strs};
+  for (int i = 0; i < 11; i++) {
+    if (L.bytes[i]) memcpy(h + L.off[i], src[i], L.bytes[i]);
+    const size_t end = i + 1 < 11 ? L.off[i + 1] : L.total;
+    memset(h + L.off[i] + L.bytes[i], 0, end - L.off[i] - L.bytes[i]);
+  }
+  CK(cudaMemcpyAsync(s.d_page_in.p, h, L.total, cudaMemcpyHostToDevice, s.stream));
+  uint8_t* d = s.d_page_in.as<uint8_t>();
+  TgBatchDev& b = s.tg;
+  b.n = n;
+  b.recs = (const tgi_tg_rec*)(d + L.off[0]);
+  b.strs = d + L.off[1];
+  b.ent_off = (const uint32_t*)(d + L.off[2]);
+  b.ents = (const tgi_entity*)(d + L.off[3]);
+  b.react_off = (const uint32_t*)(d + L.off[4]);
+  b.reacts = (const tgi_reaction*)(d + L.off[5]);
+  b.comment_off = (const uint32_t*)(d + L.off[6]);
+  b.comments = (const tgi_comment*)(d + L.off[7]);
+  b.aux = d + L.off[8];
+  b.n_chans = in->n_chans;
+  b.chans = (const tgi_tg_chan*)(d + L.off[9]);
+  b.chan_strs = d + L.off[10];
+  s.n_ents = n_ents;
+  s.n_reacts = in->n_reacts;
+  s.n_comments = in->n_comments;
+  s.chan_strs_len = in->chan_strs_len;
+  for (int i = 0; i < 11; i++) s.in_bytes += L.bytes[i];
+  s.resident = true;  // the element count is below HOST_VALIDATE_MAX: validate_tg has range-checked every offset
+  return TGI_OK;
+}
+
 int upload_tg(tgi_ctx* c, Slot& s, const tgi_tg_batch* in) {
   int rc = validate_tg(c, in);
   if (rc) return rc;
+  trace_slot(s, "upload: enqueue");
   uint64_t n = in->n;
   s.in_bytes = 0;
   uint64_t n_ents = n ? in->ent_off[n] : 0;
+  if (page_sized(in, n_ents)) return upload_tg_page(c, s, in, n_ents);
 #define UP(buf, ptr, cnt)                      \
   rc = h2d(c, s, s.buf, ptr, (size_t)(cnt));   \
   if (rc) return rc;
@@ -410,6 +543,8 @@ int upload_tg(tgi_ctx* c, Slot& s, const tgi_tg_batch* in) {
   UP(d_chans, in->chans, in->n_chans);
   UP(d_chan_strs, in->chan_strs, in->chan_strs_len);
 #undef UP
+  rc = join_uploads(c, s);
+  if (rc) return rc;
   TgBatchDev& b = s.tg;
   b.n = n;
   b.recs = s.d_recs.as<tgi_tg_rec>();
@@ -427,6 +562,7 @@ int upload_tg(tgi_ctx* c, Slot& s, const tgi_tg_batch* in) {
   s.n_ents = n_ents;
   s.n_reacts = in->n_reacts;
   s.n_comments = in->n_comments;
+  s.chan_strs_len = in->chan_strs_len;
   if (n + n_ents + in->n_reacts + in->n_comments + in->n_chans > HOST_VALIDATE_MAX) {  // big batch: range-check on the device
     CK(s.d_scalars.ensure(SC_COUNT * 8));
     int* bad = (int*)s.d_scalars.p;
@@ -434,9 +570,14 @@ int upload_tg(tgi_ctx* c, Slot& s, const tgi_tg_batch* in) {
     TgBounds lim{in->strs_len, n_ents, in->n_reacts, in->n_comments, in->aux_len, in->chan_strs_len};
     const uint64_t count = std::max<uint64_t>({n, n_ents, in->n_reacts, in->n_comments, (uint64_t)in->n_chans});
     tg_validate_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s.stream>>>(b, lim, count, bad);
-    int hbad = 0;
-    CK(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, s.stream));
+    CK(s.h_scalars.ensure(SC_COUNT * 8));
+    {
+      const int prc = publish(c, bad, s.h_scalars, 1, s.stream);
+      if (prc) return prc;
+    }
     CK(cudaStreamSynchronize(s.stream));
+    const int hbad = *s.h_scalars.as<int>();
+    trace_slot(s, "upload: landed + validated");
     if (hbad) {
       s.resident = false;
       set_err(c, "telegram batch: offsets outside their arrays (mask 0x%x)", hbad);
@@ -445,6 +586,35 @@ int upload_tg(tgi_ctx* c, Slot& s, const tgi_tg_batch* in) {
   }
   s.resident = true;
   return TGI_OK;
+}
+
+// ---- frontier turns ---------------------------------------------------------------------------------------------------
+void take_ticket(tgi_ctx* c, Slot& s, JobKind kind, uint32_t flags) {
+  const bool runs = kind == JOB_TG || kind == JOB_TG_RESIDENT || kind == JOB_YT || kind == JOB_YT_RESIDENT;
+  if (!runs || !(flags & TGI_RUN_FRONTIER)) return;
+  std::lock_guard<std::mutex> g(c->tk_mu);
+  s.ticket = c->tk_next++;
+  s.has_ticket = true;
+}
+void turn_begin(tgi_ctx* c, Slot& s) {
+  if (!s.has_ticket) return;
+  std::unique_lock<std::mutex> lk(c->tk_mu);
+  c->tk_cv.wait(lk, [&] { return c->tk_serving == s.ticket; });
+}
+void turn_end(tgi_ctx* c, Slot& s) {
+  if (!s.has_ticket) return;
+  {
+    std::lock_guard<std::mutex> g(c->tk_mu);
+    c->tk_serving++;
+    s.has_ticket = false;
+  }
+  c->tk_cv.notify_all();
+}
+// a job that ended without a frontier phase (error, empty batch) still has to let the next ticket through
+void turn_pass(tgi_ctx* c, Slot& s) {
+  if (!s.has_ticket) return;
+  turn_begin(c, s);
+  turn_end(c, s);
 }
 
 // scalars block (device + pinned mirror): [0] chan total, [1] line total, [2] cursor(u32)+err(int),
@@ -459,9 +629,11 @@ int finish_batch(tgi_ctx* c, Slot& s, uint64_t n, uint32_t flags, uint64_t line_
   uint64_t* hsc = s.h_scalars.as<uint64_t>();
   int dev_err = 0;
   s.dev_jsonl_len = want_json ? line_total : 0;
+  s.dev_jsonl = s.d_jsonl.as<uint8_t>();
 
   if (want_fr && n) {
-    // frontier phases of different slots are serialised in submission order
+    // frontier phases of different slots are serialised in submission order (tickets)
+    turn_begin(c, s);
     std::unique_lock<std::mutex> fg(c->fr_mu);
     if (c->fr_event_valid) CK(cudaStreamWaitEvent(st, c->fr_event, 0));
     uint64_t bslots = next_pow2(std::max<uint64_t>(2ull * arena_used, 1024));
@@ -492,6 +664,8 @@ int finish_batch(tgi_ctx* c, Slot& s, uint64_t n, uint32_t flags, uint64_t line_
     CK(cudaEventRecord(s.ev_fr1, st));
     CK(cudaEventRecord(c->fr_event, st));
     c->fr_event_valid = true;
+    fg.unlock();
+    turn_end(c, s);
   }
   if (want_links) {
     CK(s.d_link_off.ensure((n + 1) * 8));
@@ -507,6 +681,10 @@ int finish_batch(tgi_ctx* c, Slot& s, uint64_t n, uint32_t flags, uint64_t line_
     CK(cudaGetLastError());
   }
   CK(cudaEventRecord(s.ev_k1, st));
+  if (copy_streams() & 1) {  // the result copies leave the kernels' stream (the slot's next job starts behind the host sync below)
+    CK(cudaStreamWaitEvent(s.stream_out, s.ev_k1, 0));
+    st = s.stream_out;
+  }
   CK(cudaMemcpyAsync(hsc, dsc, SC_COUNT * 8, cudaMemcpyDeviceToHost, st));
 
   memset(out, 0, sizeof *out);
@@ -522,19 +700,23 @@ int finish_batch(tgi_ctx* c, Slot& s, uint64_t n, uint32_t flags, uint64_t line_
       CK(cudaMemcpyAsync(s.h_line_off.p, s.d_line_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
       if (line_total) CK(cudaMemcpyAsync(s.h_jsonl.p, s.d_jsonl.p, line_total, cudaMemcpyDeviceToHost, st));
     }
+    if (want_links) {
+      // the exact link count is one more host round trip away (behind the other slots' bulk copies on the copy engine);
+      // the arena's fill is an upper bound the host already has: copy that many rows, the tail past n_links is unused
+      CK(s.h_link_off.ensure((n + 1) * 4));
+      CK(s.h_links.ensure((size_t)arena_used * sizeof(tgi_link) + 64));
+      CK(cudaMemcpyAsync(s.h_link_off.p, s.d_link_off32.p, (n + 1) * 4, cudaMemcpyDeviceToHost, st));
+      if (arena_used) CK(cudaMemcpyAsync(s.h_links.p, s.d_links_out.p, (size_t)arena_used * sizeof(tgi_link), cudaMemcpyDeviceToHost, st));
+    }
   }
+  trace_slot(s, "emit + frontier + result copy: enqueued");
   CK(cudaStreamSynchronize(st));
+  trace_slot(s, "result landed");
   dev_err = ((int*)(hsc + SC_CURSOR))[1];
   if (dev_err & ERR_FRONTIER_FULL) { set_err(c, "frontier capacity %llu exceeded", (unsigned long long)c->fr.cap); return TGI_E_CAPACITY; }
   if (dev_err & 16) { set_err(c, "internal: sized and emitted line lengths disagree"); return TGI_E_STATE; }
   n_links_total = want_links ? hsc[SC_LINK_TOTAL] : 0;
-  if (d2h && want_links) {
-    CK(s.h_link_off.ensure((n + 1) * 4));
-    CK(s.h_links.ensure(n_links_total * sizeof(tgi_link) + 64));
-    CK(cudaMemcpyAsync(s.h_link_off.p, s.d_link_off32.p, (n + 1) * 4, cudaMemcpyDeviceToHost, st));
-    if (n_links_total) CK(cudaMemcpyAsync(s.h_links.p, s.d_links_out.p, n_links_total * sizeof(tgi_link), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-  }
+  if (n_links_total > arena_used) { set_err(c, "internal: more links than arena rows"); return TGI_E_STATE; }
   float ms = 0;
   cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1);
   out->kernel_ms = ms;
@@ -581,6 +763,217 @@ int finish_batch(tgi_ctx* c, Slot& s, uint64_t n, uint32_t flags, uint64_t line_
   return TGI_OK;
 }
 
+// One cooperative launch and one result copy for a page-sized batch.  PAGE_FALLBACK: the batch did not fit the
+// estimate-sized result block or the link arena (nothing was committed): run_tg goes on with the ordinary pipeline.
+constexpr int PAGE_FALLBACK = -1000;
+bool page_run_ok(const Slot& s, uint32_t flags) {
+  if (!page_enabled() || s.tg.n == 0 || s.tg.n > PAGE_MAX_RECS || s.tg.n_chans > PAGE_MAX_RECS || s.in_bytes > PAGE_MAX_IN_BYTES) return false;
+  if (flags & TGI_RUN_NO_D2H) return false;  // a device-resident result keeps the ordinary buffers
+  return (flags & (TGI_RUN_JSONL | TGI_RUN_LINKS | TGI_RUN_FRONTIER)) != 0;
+}
+int run_tg_page(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
+  TgBatchDev& b = s.tg;
+  const uint64_t n = b.n;
+  cudaStream_t st = s.stream;
+  const bool want_json = flags & TGI_RUN_JSONL, want_links = flags & TGI_RUN_LINKS, want_fr = flags & TGI_RUN_FRONTIER;
+  static const int occ = [] {
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, tg_page_kernel, CTA_THREADS, 0) != cudaSuccess) return 0;
+    return o;
+  }();
+  if (occ <= 0) { cudaGetLastError(); return PAGE_FALLBACK; }
+  PageArgs pa{};
+  {
+    std::lock_guard<std::mutex> g(c->cfg_mu);
+    pa.cfg = c->cfgdev;
+  }
+  pa.run_flags = flags;
+  const uint64_t arena_cap = s.n_ents + 2 * n + 1024;
+  const uint64_t blob_cap = 8 * s.chan_strs_len + 1024ull * b.n_chans + 1024;
+  const uint64_t bslots = next_pow2(std::max<uint64_t>(2 * arena_cap, 1024));
+  // scratch (the buffers of the ordinary pipeline, so that tgi_pending_edges finds the same arrays afterwards)
+  CK(s.d_linelen.ensure(n * 4));
+  CK(s.d_link_start.ensure(n * 4));
+  CK(s.d_link_count.ensure(n * 4));
+  CK(s.d_xlen.ensure(n * 32));
+  CK(s.d_xpos.ensure(n * 32));
+  CK(s.d_lists.ensure(3 * n * 4));
+  CK(s.d_arena.ensure(arena_cap * sizeof(tgi_link)));
+  CK(s.d_ent_range.ensure((size_t)s.n_ents * sizeof(int2)));
+  CK(s.d_link_off.ensure((n + 1) * 8));
+  CK(s.d_chan_derived.ensure((size_t)b.n_chans * sizeof(ChanDerived)));
+  CK(s.d_chan_len.ensure((size_t)b.n_chans * 4));
+  CK(s.d_chan_off.ensure(((size_t)b.n_chans + 1) * 8));
+  CK(s.d_chan_blob.ensure(blob_cap));
+  if (want_fr) {
+    CK(s.d_btable.ensure(bslots * 8));
+    CK(s.d_lstate.ensure((size_t)arena_cap * 4));
+    CK(s.d_rec_new.ensure(n * 4));
+    CK(s.d_new_off.ensure((n + 1) * 8));
+  }
+  // the result block: scalars | status | line_off | link_off | links, JSONL
+  auto up = [](uint64_t v, uint64_t a) { return (v + a - 1) / a * a; };
+  const uint64_t o_status = 256, o_line_off = o_status + up(n + 1, 16), o_link_off = o_line_off + (n + 1) * 8,
+                 o_var = up(o_link_off + (n + 1) * 4, 256);
+  uint64_t var_cap = up(6 * s.in_bytes + 3072 * n + 65536, 256);
+  if (const char* v = getenv("TGI_PAGE_VAR_CAP")) var_cap = up(strtoull(v, nullptr, 10), 256);  // tests: force the fallback
+  CK(s.d_page_out.ensure(o_var + var_cap));
+  CK(s.h_page_out.ensure(o_var + var_cap));
+  uint8_t* d = s.d_page_out.as<uint8_t>();
+  uint8_t* h = s.h_page_out.as<uint8_t>();
+  uint64_t* dsc = (uint64_t*)d;
+
+  b.chan_derived = s.d_chan_derived.as<ChanDerived>();
+  b.chan_blob = s.d_chan_blob.as<uint8_t>();
+  pa.b = b;
+  ParseOut& po = pa.po;
+  po.status = d + o_status;
+  po.linelen = s.d_linelen.as<uint32_t>();
+  po.link_start = s.d_link_start.as<uint32_t>();
+  po.link_count = s.d_link_count.as<uint32_t>();
+  po.xlen = s.d_xlen.as<uint32_t>();
+  po.var_total = (unsigned long long*)(dsc + SC_LONG);
+  po.arena = s.d_arena.as<tgi_link>();
+  po.arena_cap = (uint32_t)arena_cap;
+  po.cursor = (uint32_t*)(dsc + SC_CURSOR);
+  po.err = (int*)(dsc + SC_CURSOR) + 1;
+  po.ent_range = s.d_ent_range.as<int2>();
+  EmitIn& ei = pa.ei;
+  ei.status = po.status;
+  ei.line_off = (const uint64_t*)(d + o_line_off);
+  ei.link_start = po.link_start;
+  ei.link_count = po.link_count;
+  ei.xlen = po.xlen;
+  ei.xpos = s.d_xpos.as<uint32_t>();
+  ei.arena = po.arena;
+  ei.out = nullptr;
+  ei.err = po.err;
+  ei.lane_text_max = LANE_TEXT_MAX;
+  ei.counters = (unsigned long long*)(dsc + SC_LANE_OUT);
+  for (int k = 0; k < 3; k++) ei.list[k] = s.d_lists.as<uint32_t>() + (size_t)k * n;
+  ei.list_count = (uint32_t*)(dsc + SC_LISTS);
+  pa.chan_derived = s.d_chan_derived.as<ChanDerived>();
+  pa.chan_len = s.d_chan_len.as<uint32_t>();
+  pa.chan_off = s.d_chan_off.as<uint64_t>();
+  pa.chan_blob = s.d_chan_blob.as<uint8_t>();
+  pa.chan_blob_cap = blob_cap;
+  pa.scalars = dsc;
+  pa.line_off = (uint64_t*)(d + o_line_off);
+  pa.link_off = s.d_link_off.as<uint64_t>();
+  pa.link_off32 = (uint32_t*)(d + o_link_off);
+  pa.var = d + o_var;
+  pa.var_cap = var_cap;
+  pa.fr = c->fr;
+  pa.fb.btable = s.d_btable.as<uint64_t>();
+  pa.fb.bmask = bslots - 1;
+  pa.fb.lstate = s.d_lstate.as<uint32_t>();
+  pa.fb.rec_new = s.d_rec_new.as<uint32_t>();
+  pa.excl = c->excl;
+  pa.bslots = bslots;
+  pa.new_off = s.d_new_off.as<uint64_t>();
+  pa.sc_chan_total = SC_CHAN_TOTAL;
+  pa.sc_line_total = SC_LINE_TOTAL;
+  pa.sc_link_total = SC_LINK_TOTAL;
+  pa.sc_new = SC_NEW;
+  pa.sc_count = SC_COUNT;
+
+  const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c->sms * occ, std::max<uint64_t>(1, (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA));
+  void* kargs[] = {&pa};
+  {
+    // the launch holds frontier phases: serialised with the other slots' in submission order, like finish_batch
+    std::unique_lock<std::mutex> fg(c->fr_mu, std::defer_lock);
+    if (want_fr) {
+      turn_begin(c, s);
+      fg.lock();
+      if (c->fr_event_valid) CK(cudaStreamWaitEvent(st, c->fr_event, 0));
+      pa.fr = c->fr;
+      pa.excl = c->excl;
+    }
+    CK(cudaEventRecord(s.ev_k0, st));
+    CK(cudaLaunchCooperativeKernel((void*)tg_page_kernel, dim3(grid), dim3(CTA_THREADS), kargs, 0, st));
+    CK(cudaEventRecord(s.ev_k1, st));
+    if (want_fr) {
+      CK(cudaEventRecord(c->fr_event, st));
+      c->fr_event_valid = true;
+    }
+  }
+  // ONE read of the result block, sized by what the previous pages needed; a second one only for the rest of a bigger page
+  const uint64_t spec = std::min<uint64_t>(var_cap, up((uint64_t)s.page_bpr * n * 5 / 4 + 4096, 256));
+  CK(cudaMemcpyAsync(h, d, o_var + spec, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const uint64_t* hsc = (const uint64_t*)h;
+  const int dev_err = ((const int*)(hsc + SC_CURSOR))[1];
+  if (dev_err & (ERR_ARENA_OVERFLOW | ERR_TOO_MANY_LINKS | ERR_PAGE_OVERFLOW)) return PAGE_FALLBACK;  // keeps its turn
+  turn_end(c, s);
+  if (dev_err & ERR_FRONTIER_FULL) { set_err(c, "frontier capacity %llu exceeded", (unsigned long long)c->fr.cap); return TGI_E_CAPACITY; }
+  if (dev_err & 16) { set_err(c, "internal: sized and emitted line lengths disagree"); return TGI_E_STATE; }
+  const uint64_t line_total = want_json ? hsc[SC_LINE_TOTAL] : 0, n_links_total = want_links ? hsc[SC_LINK_TOTAL] : 0;
+  const uint64_t links_bytes = want_links ? up(n_links_total * sizeof(tgi_link), 256) : 0;
+  if (want_json && c->cfg.max_out_bytes && line_total > c->cfg.max_out_bytes) {
+    set_err(c, "JSONL output %llu bytes exceeds max_out_bytes", (unsigned long long)line_total);
+    return TGI_E_CAPACITY;
+  }
+  const uint64_t need = links_bytes + line_total;
+  if (need > spec) {
+    CK(cudaMemcpyAsync(h + o_var + spec, d + o_var + spec, need - spec, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  if (getenv("TGI_PAGE_TRACE")) {
+    const uint64_t* t = hsc + PAGE_TRACE_AT;
+    fprintf(stderr, "tg_page n=%llu grid=%u phases us:", (unsigned long long)n, grid);
+    for (int k = 0; k < PAGE_PHASES; k++) fprintf(stderr, " P%d %.1f", k, (double)(t[k + 1] - t[k]) * 1e-3);
+    fprintf(stderr, "  total %.1f |", (double)(t[PAGE_PHASES] - t[0]) * 1e-3);
+    static const char* const what[3] = {"parse", "size", "emit"};
+    for (int k = 0; k < 3; k++)  // SM cycles (1.965 GHz)
+      fprintf(stderr, " slowest %s: rec %u %.1f us", what[k], (unsigned)t[PAGE_PHASES + 1 + k], (double)(t[PAGE_PHASES + 1 + k] >> 32) / 1965.0);
+    fprintf(stderr, "\n");
+  }
+  s.page_bpr = (uint32_t)std::min<uint64_t>(1u << 20, (3ull * s.page_bpr + need / n + 1) / 4 + (need > spec ? need / n / 4 : 0));
+
+  memset(out, 0, sizeof *out);
+  out->n = n;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1);
+  out->kernel_ms = ms;
+  out->gpu_launches = 1;
+  out->slot = s.idx;
+  if (want_json) {
+    out->var_bytes = hsc[SC_LONG];
+    out->main_bytes_out = hsc[SC_LANE_OUT];
+    out->main_bytes_in = hsc[SC_LANE_IN];
+  }
+  out->jsonl_len = line_total;
+  out->n_links = n_links_total;
+  out->n_new = want_fr ? hsc[SC_NEW] : 0;
+  out->frontier_size = want_fr ? hsc[SC_FSIZE] : 0;
+  out->status = h + o_status;
+  if (want_json) {
+    out->jsonl = h + o_var + links_bytes;
+    out->line_off = (const uint64_t*)(h + o_line_off);
+  }
+  if (want_links) {
+    out->link_off = (const uint32_t*)(h + o_link_off);
+    out->links = (const tgi_link*)(h + o_var);
+  }
+  s.dev_jsonl_len = line_total;
+  s.dev_jsonl = d + o_var + links_bytes;
+  s.last_n = n;
+  s.last_new = out->n_new;
+  s.last_frontier = want_fr;
+  s.last_yt = false;
+  {
+    std::lock_guard<std::mutex> g(c->st_mu);
+    c->stats.records += n;
+    c->stats.bytes_in += s.in_bytes;
+    c->stats.bytes_out += out->jsonl_len;
+    c->stats.links += n_links_total;
+    c->stats.launches += 1;
+    c->stats.kernel_ms_total += ms;
+    if (want_fr) c->stats.frontier_size = out->frontier_size;
+  }
+  return TGI_OK;
+}
+
 int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   TgBatchDev& b = s.tg;
   uint64_t n = b.n;
@@ -591,6 +984,10 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   {
     std::lock_guard<std::mutex> g(c->cfg_mu);
     cfg = c->cfgdev;
+  }
+  if (page_run_ok(s, flags)) {
+    const int rc = run_tg_page(c, s, flags, out);
+    if (rc != PAGE_FALLBACK) return rc;
   }
   CK(s.d_scalars.ensure(SC_COUNT * 8));
   CK(s.h_scalars.ensure(SC_COUNT * 8));
@@ -660,8 +1057,14 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       if (rc) return rc;
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(hsc, dsc, SC_COUNT * 8, cudaMemcpyDeviceToHost, st));
+    {
+      const int rc = publish(c, dsc, s.h_scalars, SC_COUNT, st);
+      if (rc) return rc;
+      launches++;
+    }
+    trace_slot(s, "parse + size: enqueued");
     CK(cudaStreamSynchronize(st));
+    trace_slot(s, "parse + size: done");
     dev_err = ((int*)(hsc + SC_CURSOR))[1];
     uint32_t cursor = ((uint32_t*)(hsc + SC_CURSOR))[0];
     if (dev_err & ERR_ARENA_OVERFLOW) {
@@ -766,6 +1169,8 @@ int upload_yt(tgi_ctx* c, Slot& s, const tgi_yt_batch* in) {
   UP(d_chans, in->chans, in->n_chans);
   UP(d_chan_strs, in->chan_strs, in->chan_strs_len);
 #undef UP
+  rc = join_uploads(c, s);
+  if (rc) return rc;
   YtBatchDev& b = s.yt;
   b.n = in->n;
   b.recs = s.d_recs.as<tgi_yt_rec>();
@@ -846,7 +1251,11 @@ int run_yt(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     if (rc) return rc;
   }
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(hsc, dsc, SC_COUNT * 8, cudaMemcpyDeviceToHost, st));
+  {
+    const int rc = publish(c, dsc, s.h_scalars, SC_COUNT, st);
+    if (rc) return rc;
+    launches++;
+  }
   CK(cudaStreamSynchronize(st));
   int dev_err = ((int*)(hsc + SC_CURSOR))[1];
   if (dev_err & ERR_ARENA_OVERFLOW) { set_err(c, "youtube url/link arena overflow (cannot happen: capacities are upper bounds)"); return TGI_E_CAPACITY; }
@@ -951,7 +1360,9 @@ int run_gm(tgi_ctx* c, Slot& s, const tgi_gm_batch* in, uint32_t flags, tgi_resu
   if (want_json) {
     rc = launch_scan(c, s, s.d_linelen.as<uint32_t>(), n, s.d_line_off.as<uint64_t>(), dsc + SC_LINE_TOTAL, launches);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(hsc, dsc, SC_COUNT * 8, cudaMemcpyDeviceToHost, st));
+    rc = publish(c, dsc, s.h_scalars, SC_COUNT, st);
+    if (rc) return rc;
+    launches++;
     CK(cudaStreamSynchronize(st));
     line_total = hsc[SC_LINE_TOTAL];
     if (c->cfg.max_out_bytes && line_total > c->cfg.max_out_bytes) {
@@ -995,6 +1406,7 @@ void worker_main(tgi_ctx* c, Slot* s) {
     }
     if (rc == TGI_OK && (job == JOB_YT || job == JOB_YT_RESIDENT)) rc = run_yt(c, *s, s->run_flags, &s->res);
     if (job == JOB_GM) rc = run_gm(c, *s, s->in_gm, s->run_flags, &s->res);
+    turn_pass(c, *s);
     {
       std::lock_guard<std::mutex> lk(s->mu);
       s->rc = rc;
@@ -1019,6 +1431,7 @@ int post_job(tgi_ctx* c, int slot, JobKind kind, const tgi_tg_batch* in, uint32_
   s.in_yt = in_yt;
   s.in_gm = in_gm;
   s.run_flags = flags;
+  take_ticket(c, s, kind, flags);
   s.job = kind;
   s.cv.notify_all();
   return TGI_OK;
@@ -1048,6 +1461,7 @@ int run_inline(tgi_ctx* c, int slot, JobKind kind, const tgi_tg_batch* in_tg, co
     s.busy = true;
     s.done = false;
   }
+  take_ticket(c, s, kind, flags);
   cudaSetDevice(c->device);
   int rc = TGI_OK;
   if (kind == JOB_TG) {
@@ -1059,6 +1473,7 @@ int run_inline(tgi_ctx* c, int slot, JobKind kind, const tgi_tg_batch* in_tg, co
   } else {
     rc = run_gm(c, s, in_gm, flags, &s.res);
   }
+  turn_pass(c, s);
   {
     std::lock_guard<std::mutex> lk(s.mu);
     s.rc = rc;
@@ -1109,10 +1524,15 @@ int tgi_create(const tgi_config* cfg, tgi_ctx** out) {
   if (cudaSetDevice(ctx->device) != cudaSuccess) { set_err(c, "cudaSetDevice failed"); return fail(TGI_E_CUDA); }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) ctx->sms = prop.multiProcessorCount;
+  if (ctx->h_zero.ensure(PAD) != cudaSuccess) { set_err(c, "pinned allocation failed"); return fail(TGI_E_CUDA); }
+  memset(ctx->h_zero.p, 0, PAD);
   for (int i = 0; i < TGI_SLOTS; i++) {
     Slot& s = ctx->slots[i];
     s.idx = i;
+    s.h_scalars.flags = cudaHostAllocMapped;  // publish() stores into it from the device
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s.stream_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s.stream_out, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&s.ev_k0) != cudaSuccess || cudaEventCreate(&s.ev_k1) != cudaSuccess ||
         cudaEventCreate(&s.ev_p0) != cudaSuccess || cudaEventCreate(&s.ev_p1) != cudaSuccess ||
         cudaEventCreate(&s.ev_e0) != cudaSuccess || cudaEventCreate(&s.ev_e1) != cudaSuccess || cudaEventCreate(&s.ev_f1) != cudaSuccess ||
@@ -1168,20 +1588,23 @@ void tgi_destroy(tgi_ctx* c) {
                     &s.d_chan_off, &s.d_chan_blob, &s.d_status, &s.d_linelen, &s.d_line_off, &s.d_link_start,
                     &s.d_link_count, &s.d_xlen, &s.d_xpos, &s.d_lists, &s.d_arena, &s.d_lstate, &s.d_rec_new, &s.d_new_off, &s.d_link_off,
                     &s.d_links_out, &s.d_link_off32, &s.d_btable, &s.d_tiles, &s.d_scalars, &s.d_jsonl,
-                    &s.d_url_start, &s.d_url_count, &s.d_urls, &s.d_ent_range};
+                    &s.d_url_start, &s.d_url_count, &s.d_urls, &s.d_ent_range, &s.d_page_in, &s.d_page_out};
     for (DevBuf* d : db) d->release();
-    HostBuf* hb[] = {&s.h_status, &s.h_line_off, &s.h_jsonl, &s.h_link_off, &s.h_links, &s.h_scalars};
+    HostBuf* hb[] = {&s.h_status, &s.h_line_off, &s.h_jsonl, &s.h_link_off, &s.h_links, &s.h_scalars, &s.h_page_in, &s.h_page_out};
     for (HostBuf* h : hb) h->release();
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_mid) cudaEventDestroy(s.ev_mid);
     for (cudaEvent_t e : {s.ev_p0, s.ev_p1, s.ev_e0, s.ev_e1, s.ev_f1, s.ev_fr0, s.ev_fr1}) if (e) cudaEventDestroy(e);
     if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.stream_in) cudaStreamDestroy(s.stream_in);
+    if (s.stream_out) cudaStreamDestroy(s.stream_out);
   }
   for (auto& f : c->stg_free) cudaFreeHost(f.second);
   for (auto& f : c->stg_live) cudaFreeHost(f.first);
   c->stg_free.clear();
   c->stg_live.clear();
+  c->h_zero.release();
   c->m_host.release();
   for (int k = 0; k < 2; k++) { c->x_pool[k].release(); c->x_table[k].release(); c->x_count[k].release(); }
   c->x_payload.release();
@@ -1271,7 +1694,7 @@ int tgi_result_read_jsonl(tgi_ctx* c, int slot, uint64_t off, uint64_t len, uint
   cudaSetDevice(c->device);
   Slot& s = c->slots[slot];
   if (off + len > s.dev_jsonl_len) { set_err(c, "read_jsonl out of range"); return TGI_E_ARG; }
-  CK(cudaMemcpy(dst, s.d_jsonl.as<uint8_t>() + off, len, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(dst, s.dev_jsonl + off, len, cudaMemcpyDeviceToHost));
   return TGI_OK;
 }
 

@@ -2,6 +2,9 @@
 (telegramhelper/channel_links_test.go:34-60: msgText, msgPhoto, ...)."""
 from __future__ import annotations
 
+import contextlib
+import os
+
 import numpy as np
 
 from distributed_crawler_b200 import abi
@@ -47,3 +50,13 @@ def assert_results_equal(ro, rg, flags, label=""):
 
 ALL = abi.RUN_JSONL | abi.RUN_LINKS | abi.RUN_FRONTIER | abi.RUN_SKIP_SELF
 TANDEM = abi.RUN_LINKS | abi.RUN_FRONTIER | abi.RUN_FILTER | abi.RUN_SKIP_SELF
+
+
+@contextlib.contextmanager
+def no_page():
+    """The ordinary multi-launch pipeline also for page-sized batches (the library reads TGI_NO_PAGE per call)."""
+    os.environ["TGI_NO_PAGE"] = "1"
+    try:
+        yield
+    finally:
+        del os.environ["TGI_NO_PAGE"]

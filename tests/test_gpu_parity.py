@@ -9,7 +9,7 @@ from distributed_crawler_b200 import abi
 from distributed_crawler_b200.corpus import Corpus
 from distributed_crawler_b200.engine import Engine, names_to_keys32
 from distributed_crawler_b200.pack import Channel, Comment, FormattedText, Message, pack_telegram
-from helpers import ALL, TANDEM, assert_results_equal, msg, names, vector_message
+from helpers import ALL, TANDEM, assert_results_equal, msg, names, no_page, vector_message
 from oracle.pyoracle import Oracle
 
 pytestmark = pytest.mark.gpu
@@ -22,6 +22,15 @@ def both(batch, flags=ALL, **cfg):
     if flags & abi.RUN_FRONTIER:
         assert np.array_equal(o.frontier_export(), e.frontier_export())
     assert rg.gpu_launches > 0
+    if rg.gpu_launches == 1 and batch.n:  # a page-sized batch took the one-launch path: the ordinary pipeline as well
+        with no_page():
+            e2 = Engine(**cfg)
+            r2 = e2.telegram(batch, flags)
+            assert r2.gpu_launches > 1
+            assert_results_equal(ro, r2, flags, "ordinary pipeline")
+            if flags & abi.RUN_FRONTIER:
+                assert np.array_equal(o.frontier_export(), e2.frontier_export())
+            e2.close()
     e.close()
     return ro, rg
 
