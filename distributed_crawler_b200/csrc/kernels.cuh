@@ -502,7 +502,7 @@ struct YtOut {
 };
 
 // unique outlink URLs (extractURLs) and snowball channel ids (extractChannelIDsFromText)
-__global__ void __launch_bounds__(CTA_THREADS, 4) yt_parse_kernel(YtBatchDev b, CfgDev cfg, uint32_t run_flags, YtOut o) {
+DEVI void yt_parse_body(const YtBatchDev& b, const CfgDev& cfg, uint32_t run_flags, const YtOut& o) {
   int wid = threadIdx.x >> 5, l = lane_id();
   uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
@@ -554,13 +554,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) yt_parse_kernel(YtBatchDev b, 
     }
   }
 }
+__global__ void __launch_bounds__(CTA_THREADS, 4) yt_parse_kernel(YtBatchDev b, CfgDev cfg, uint32_t run_flags, YtOut o) { yt_parse_body(b, cfg, run_flags, o); }
 
-__global__ void __launch_bounds__(CTA_THREADS, 4) yt_size_kernel(YtBatchDev b, CfgDev cfg, YtOut o) {
-  __shared__ YtScratch scs[WARPS_PER_CTA];
-  int wid = threadIdx.x >> 5, l = lane_id();
-  uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
-  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
-    if (o.status[r] != TGI_ST_EMITTED) continue;  // linelen stays 0
+// one record by one warp (yt_size_kernel, yt_page_kernel)
+DEVI void yt_size_record(const YtBatchDev& b, const CfgDev& cfg, const YtOut& o, uint64_t r, YtScratch* sc) {
+  const int l = lane_id();
+  {
     YtArgs a;
     a.b = &b;
     a.cfg = &cfg;
@@ -568,7 +567,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) yt_size_kernel(YtBatchDev b, C
     a.urls = o.urls + o.url_start[r];
     a.n_urls = o.url_count[r];
     YtSizer z;
-    z.sc = &scs[wid];
+    z.sc = sc;
     {
       const tgi_yt_rec* rec = &b.recs[r];
       const uint8_t* title = b.strs + rec->str_off + rec->id_len;
@@ -583,6 +582,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) yt_size_kernel(YtBatchDev b, C
       o.linelen[r] = ok ? (uint32_t)z.total : 0u;
       if (!ok) o.status[r] = TGI_ST_NOLINE;
     }
+  }
+}
+__global__ void __launch_bounds__(CTA_THREADS, 4) yt_size_kernel(YtBatchDev b, CfgDev cfg, YtOut o) {
+  __shared__ YtScratch scs[WARPS_PER_CTA];
+  int wid = threadIdx.x >> 5;
+  uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
+  for (uint64_t r = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; r < b.n; r += nwarps) {
+    if (o.status[r] != TGI_ST_EMITTED) continue;  // linelen stays 0
+    yt_size_record(b, cfg, o, r, &scs[wid]);
   }
 }
 
@@ -636,6 +644,23 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) yt_size_lane_kernel(YtBatchDev
 
 // warp writer: the records the lane writer does not take (a string needs escaping); lanes pick them out of
 // groups of 32.  lane_mode == 0: every record (A/B reference, TGI_YT_WARP=1).
+DEVI void yt_emit_record(const YtBatchDev& b, const CfgDev& cfg, const YtOut& o, const uint64_t* line_off, uint8_t* out, int* err,
+                         uint64_t r, YtScratch* sc) {
+  YtArgs a;
+  a.b = &b;
+  a.cfg = &cfg;
+  a.r = r;
+  a.urls = o.urls + o.url_start[r];
+  a.n_urls = o.url_count[r];
+  YtWriter w;
+  w.sc = sc;
+  w.el[0] = o.esc_len[3 * r];
+  w.el[1] = o.esc_len[3 * r + 1];
+  w.p = out + line_off[r];
+  walk_yt_record(w, a);
+  if (lane_id() == 0 && (uint64_t)(w.p - out) != line_off[r + 1]) atomicOr(err, 16);
+  __syncwarp();
+}
 __global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_kernel(YtBatchDev b, CfgDev cfg, YtOut o, const uint64_t* line_off, uint8_t* out, int* err,
                                                                  int lane_mode) {
   __shared__ YtScratch scs[WARPS_PER_CTA];
@@ -647,20 +672,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_kernel(YtBatchDev b, C
     while (todo) {
       const uint64_t r = g * 32 + (uint32_t)(__ffs(todo) - 1);
       todo &= todo - 1;
-      YtArgs a;
-      a.b = &b;
-      a.cfg = &cfg;
-      a.r = r;
-      a.urls = o.urls + o.url_start[r];
-      a.n_urls = o.url_count[r];
-      YtWriter w;
-      w.sc = &scs[wid];
-      w.el[0] = o.esc_len[3 * r];
-      w.el[1] = o.esc_len[3 * r + 1];
-      w.p = out + line_off[r];
-      walk_yt_record(w, a);
-      if (l == 0 && (uint64_t)(w.p - out) != line_off[r + 1]) atomicOr(err, 16);
-      __syncwarp();
+      yt_emit_record(b, cfg, o, line_off, out, err, r, &scs[wid]);
     }
   }
 }

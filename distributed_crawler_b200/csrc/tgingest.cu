@@ -21,6 +21,7 @@
 
 #include "kernels.cuh"
 #include "tg_page.cuh"
+#include "yt_page.cuh"
 
 using namespace tgi;
 
@@ -771,11 +772,135 @@ bool page_run_ok(const Slot& s, uint32_t flags) {
   if (flags & TGI_RUN_NO_D2H) return false;  // a device-resident result keeps the ordinary buffers
   return (flags & (TGI_RUN_JSONL | TGI_RUN_LINKS | TGI_RUN_FRONTIER)) != 0;
 }
+// ---- shared by the Telegram and the YouTube page paths ------------------------------------------------------------------
+struct PageOut {  // the result block: scalars | status | line_off | link_off | links, JSONL
+  uint64_t o_status, o_line_off, o_link_off, o_var, var_cap;
+};
+int page_out_prepare(tgi_ctx* c, Slot& s, uint64_t n, PageOut& L) {
+  auto up = [](uint64_t v, uint64_t a) { return (v + a - 1) / a * a; };
+  L.o_status = 256;
+  L.o_line_off = L.o_status + up(n + 1, 16);
+  L.o_link_off = L.o_line_off + (n + 1) * 8;
+  L.o_var = up(L.o_link_off + (n + 1) * 4, 256);
+  L.var_cap = up(6 * s.in_bytes + 3072 * n + 65536, 256);
+  if (const char* v = getenv("TGI_PAGE_VAR_CAP")) L.var_cap = up(strtoull(v, nullptr, 10), 256);  // tests: force the fallback
+  CK(s.d_page_out.ensure(L.o_var + L.var_cap));
+  CK(s.h_page_out.ensure(L.o_var + L.var_cap));
+  return TGI_OK;
+}
+// launch (in the batch's frontier turn), ONE read of the result block, the result.  PAGE_FALLBACK: nothing was committed.
+int page_launch_and_read(tgi_ctx* c, Slot& s, uint32_t flags, uint64_t n, const void* kernel, void** kargs, int occ, const PageOut& L,
+                         FrontierDev* fr_arg, ExclusionDev* excl_arg, const char* name, bool is_yt, tgi_result* out) {
+  cudaStream_t st = s.stream;
+  const bool want_json = flags & TGI_RUN_JSONL, want_links = flags & TGI_RUN_LINKS, want_fr = flags & TGI_RUN_FRONTIER;
+  auto up = [](uint64_t v, uint64_t a) { return (v + a - 1) / a * a; };
+  const uint64_t o_status = L.o_status, o_line_off = L.o_line_off, o_link_off = L.o_link_off, o_var = L.o_var, var_cap = L.var_cap;
+  uint8_t* d = s.d_page_out.as<uint8_t>();
+  uint8_t* h = s.h_page_out.as<uint8_t>();
+  const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c->sms * occ, std::max<uint64_t>(1, (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA));
+  {
+    // the launch holds frontier phases: serialised with the other slots' in submission order, like finish_batch
+    std::unique_lock<std::mutex> fg(c->fr_mu, std::defer_lock);
+    if (want_fr) {
+      turn_begin(c, s);
+      fg.lock();
+      if (c->fr_event_valid) CK(cudaStreamWaitEvent(st, c->fr_event, 0));
+      *fr_arg = c->fr;
+      *excl_arg = c->excl;
+    }
+    CK(cudaEventRecord(s.ev_k0, st));
+    if (cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(CTA_THREADS), kargs, 0, st) != cudaSuccess) {
+      cudaGetLastError();  // e.g. the device is shared and cannot hold the grid: the bulk pipeline needs no co-residency
+      return PAGE_FALLBACK;
+    }
+    CK(cudaEventRecord(s.ev_k1, st));
+    if (want_fr) {
+      CK(cudaEventRecord(c->fr_event, st));
+      c->fr_event_valid = true;
+    }
+  }
+  // ONE read of the result block, sized by what the previous pages needed; a second one only for the rest of a bigger page
+  const uint64_t spec = std::min<uint64_t>(var_cap, up((uint64_t)s.page_bpr * n * 5 / 4 + 4096, 256));
+  CK(cudaMemcpyAsync(h, d, o_var + spec, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const uint64_t* hsc = (const uint64_t*)h;
+  const int dev_err = ((const int*)(hsc + SC_CURSOR))[1];
+  if (dev_err & (ERR_ARENA_OVERFLOW | ERR_TOO_MANY_LINKS | ERR_PAGE_OVERFLOW)) return PAGE_FALLBACK;  // keeps its turn
+  turn_end(c, s);
+  if (dev_err & ERR_FRONTIER_FULL) { set_err(c, "frontier capacity %llu exceeded", (unsigned long long)c->fr.cap); return TGI_E_CAPACITY; }
+  if (dev_err & 16) { set_err(c, "internal: sized and emitted line lengths disagree"); return TGI_E_STATE; }
+  const uint64_t line_total = want_json ? hsc[SC_LINE_TOTAL] : 0, n_links_total = want_links ? hsc[SC_LINK_TOTAL] : 0;
+  const uint64_t links_bytes = want_links ? up(n_links_total * sizeof(tgi_link), 256) : 0;
+  if (want_json && c->cfg.max_out_bytes && line_total > c->cfg.max_out_bytes) {
+    set_err(c, "JSONL output %llu bytes exceeds max_out_bytes", (unsigned long long)line_total);
+    return TGI_E_CAPACITY;
+  }
+  const uint64_t need = links_bytes + line_total;
+  if (need > spec) {
+    CK(cudaMemcpyAsync(h + o_var + spec, d + o_var + spec, need - spec, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  if (getenv("TGI_PAGE_TRACE")) {
+    const uint64_t* t = hsc + PAGE_TRACE_AT;
+    fprintf(stderr, "%s n=%llu grid=%u phases us:", name, (unsigned long long)n, grid);
+    for (int k = 0; k < PAGE_PHASES; k++) fprintf(stderr, " P%d %.1f", k, (double)(t[k + 1] - t[k]) * 1e-3);
+    fprintf(stderr, "  total %.1f |", (double)(t[PAGE_PHASES] - t[0]) * 1e-3);
+    static const char* const what[3] = {"parse", "size", "emit"};
+    for (int k = 0; k < 3; k++)  // SM cycles (1.965 GHz)
+      fprintf(stderr, " slowest %s: rec %u %.1f us", what[k], (unsigned)t[PAGE_PHASES + 1 + k], (double)(t[PAGE_PHASES + 1 + k] >> 32) / 1965.0);
+    fprintf(stderr, "\n");
+  }
+  s.page_bpr = (uint32_t)std::min<uint64_t>(1u << 20, (3ull * s.page_bpr + need / n + 1) / 4 + (need > spec ? need / n / 4 : 0));
+
+  memset(out, 0, sizeof *out);
+  out->n = n;
+  float ms = 0;
+  cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1);
+  out->kernel_ms = ms;
+  out->gpu_launches = 1;
+  out->slot = s.idx;
+  if (want_json) {
+    out->var_bytes = hsc[SC_LONG];
+    out->main_bytes_out = hsc[SC_LANE_OUT];
+    out->main_bytes_in = hsc[SC_LANE_IN];
+  }
+  out->jsonl_len = line_total;
+  out->n_links = n_links_total;
+  out->n_new = want_fr ? hsc[SC_NEW] : 0;
+  out->frontier_size = want_fr ? hsc[SC_FSIZE] : 0;
+  out->status = h + o_status;
+  if (want_json) {
+    out->jsonl = h + o_var + links_bytes;
+    out->line_off = (const uint64_t*)(h + o_line_off);
+  }
+  if (want_links) {
+    out->link_off = (const uint32_t*)(h + o_link_off);
+    out->links = (const tgi_link*)(h + o_var);
+  }
+  s.dev_jsonl_len = line_total;
+  s.dev_jsonl = d + o_var + links_bytes;
+  s.last_n = n;
+  s.last_new = out->n_new;
+  s.last_frontier = want_fr;
+  s.last_yt = is_yt;
+  {
+    std::lock_guard<std::mutex> g(c->st_mu);
+    c->stats.records += n;
+    c->stats.bytes_in += s.in_bytes;
+    c->stats.bytes_out += out->jsonl_len;
+    c->stats.links += n_links_total;
+    c->stats.launches += 1;
+    c->stats.kernel_ms_total += ms;
+    if (want_fr) c->stats.frontier_size = out->frontier_size;
+  }
+  return TGI_OK;
+}
+
+
 int run_tg_page(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   TgBatchDev& b = s.tg;
   const uint64_t n = b.n;
-  cudaStream_t st = s.stream;
-  const bool want_json = flags & TGI_RUN_JSONL, want_links = flags & TGI_RUN_LINKS, want_fr = flags & TGI_RUN_FRONTIER;
+  const bool want_fr = flags & TGI_RUN_FRONTIER;
   static const int occ = [] {
     int o = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, tg_page_kernel, CTA_THREADS, 0) != cudaSuccess) return 0;
@@ -811,16 +936,13 @@ int run_tg_page(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     CK(s.d_rec_new.ensure(n * 4));
     CK(s.d_new_off.ensure((n + 1) * 8));
   }
-  // the result block: scalars | status | line_off | link_off | links, JSONL
-  auto up = [](uint64_t v, uint64_t a) { return (v + a - 1) / a * a; };
-  const uint64_t o_status = 256, o_line_off = o_status + up(n + 1, 16), o_link_off = o_line_off + (n + 1) * 8,
-                 o_var = up(o_link_off + (n + 1) * 4, 256);
-  uint64_t var_cap = up(6 * s.in_bytes + 3072 * n + 65536, 256);
-  if (const char* v = getenv("TGI_PAGE_VAR_CAP")) var_cap = up(strtoull(v, nullptr, 10), 256);  // tests: force the fallback
-  CK(s.d_page_out.ensure(o_var + var_cap));
-  CK(s.h_page_out.ensure(o_var + var_cap));
+  PageOut L;
+  {
+    const int rc = page_out_prepare(c, s, n, L);
+    if (rc) return rc;
+  }
+  const uint64_t o_status = L.o_status, o_line_off = L.o_line_off, o_link_off = L.o_link_off, o_var = L.o_var, var_cap = L.var_cap;
   uint8_t* d = s.d_page_out.as<uint8_t>();
-  uint8_t* h = s.h_page_out.as<uint8_t>();
   uint64_t* dsc = (uint64_t*)d;
 
   b.chan_derived = s.d_chan_derived.as<ChanDerived>();
@@ -877,101 +999,8 @@ int run_tg_page(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   pa.sc_new = SC_NEW;
   pa.sc_count = SC_COUNT;
 
-  const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c->sms * occ, std::max<uint64_t>(1, (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA));
   void* kargs[] = {&pa};
-  {
-    // the launch holds frontier phases: serialised with the other slots' in submission order, like finish_batch
-    std::unique_lock<std::mutex> fg(c->fr_mu, std::defer_lock);
-    if (want_fr) {
-      turn_begin(c, s);
-      fg.lock();
-      if (c->fr_event_valid) CK(cudaStreamWaitEvent(st, c->fr_event, 0));
-      pa.fr = c->fr;
-      pa.excl = c->excl;
-    }
-    CK(cudaEventRecord(s.ev_k0, st));
-    CK(cudaLaunchCooperativeKernel((void*)tg_page_kernel, dim3(grid), dim3(CTA_THREADS), kargs, 0, st));
-    CK(cudaEventRecord(s.ev_k1, st));
-    if (want_fr) {
-      CK(cudaEventRecord(c->fr_event, st));
-      c->fr_event_valid = true;
-    }
-  }
-  // ONE read of the result block, sized by what the previous pages needed; a second one only for the rest of a bigger page
-  const uint64_t spec = std::min<uint64_t>(var_cap, up((uint64_t)s.page_bpr * n * 5 / 4 + 4096, 256));
-  CK(cudaMemcpyAsync(h, d, o_var + spec, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  const uint64_t* hsc = (const uint64_t*)h;
-  const int dev_err = ((const int*)(hsc + SC_CURSOR))[1];
-  if (dev_err & (ERR_ARENA_OVERFLOW | ERR_TOO_MANY_LINKS | ERR_PAGE_OVERFLOW)) return PAGE_FALLBACK;  // keeps its turn
-  turn_end(c, s);
-  if (dev_err & ERR_FRONTIER_FULL) { set_err(c, "frontier capacity %llu exceeded", (unsigned long long)c->fr.cap); return TGI_E_CAPACITY; }
-  if (dev_err & 16) { set_err(c, "internal: sized and emitted line lengths disagree"); return TGI_E_STATE; }
-  const uint64_t line_total = want_json ? hsc[SC_LINE_TOTAL] : 0, n_links_total = want_links ? hsc[SC_LINK_TOTAL] : 0;
-  const uint64_t links_bytes = want_links ? up(n_links_total * sizeof(tgi_link), 256) : 0;
-  if (want_json && c->cfg.max_out_bytes && line_total > c->cfg.max_out_bytes) {
-    set_err(c, "JSONL output %llu bytes exceeds max_out_bytes", (unsigned long long)line_total);
-    return TGI_E_CAPACITY;
-  }
-  const uint64_t need = links_bytes + line_total;
-  if (need > spec) {
-    CK(cudaMemcpyAsync(h + o_var + spec, d + o_var + spec, need - spec, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-  }
-  if (getenv("TGI_PAGE_TRACE")) {
-    const uint64_t* t = hsc + PAGE_TRACE_AT;
-    fprintf(stderr, "tg_page n=%llu grid=%u phases us:", (unsigned long long)n, grid);
-    for (int k = 0; k < PAGE_PHASES; k++) fprintf(stderr, " P%d %.1f", k, (double)(t[k + 1] - t[k]) * 1e-3);
-    fprintf(stderr, "  total %.1f |", (double)(t[PAGE_PHASES] - t[0]) * 1e-3);
-    static const char* const what[3] = {"parse", "size", "emit"};
-    for (int k = 0; k < 3; k++)  // SM cycles (1.965 GHz)
-      fprintf(stderr, " slowest %s: rec %u %.1f us", what[k], (unsigned)t[PAGE_PHASES + 1 + k], (double)(t[PAGE_PHASES + 1 + k] >> 32) / 1965.0);
-    fprintf(stderr, "\n");
-  }
-  s.page_bpr = (uint32_t)std::min<uint64_t>(1u << 20, (3ull * s.page_bpr + need / n + 1) / 4 + (need > spec ? need / n / 4 : 0));
-
-  memset(out, 0, sizeof *out);
-  out->n = n;
-  float ms = 0;
-  cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1);
-  out->kernel_ms = ms;
-  out->gpu_launches = 1;
-  out->slot = s.idx;
-  if (want_json) {
-    out->var_bytes = hsc[SC_LONG];
-    out->main_bytes_out = hsc[SC_LANE_OUT];
-    out->main_bytes_in = hsc[SC_LANE_IN];
-  }
-  out->jsonl_len = line_total;
-  out->n_links = n_links_total;
-  out->n_new = want_fr ? hsc[SC_NEW] : 0;
-  out->frontier_size = want_fr ? hsc[SC_FSIZE] : 0;
-  out->status = h + o_status;
-  if (want_json) {
-    out->jsonl = h + o_var + links_bytes;
-    out->line_off = (const uint64_t*)(h + o_line_off);
-  }
-  if (want_links) {
-    out->link_off = (const uint32_t*)(h + o_link_off);
-    out->links = (const tgi_link*)(h + o_var);
-  }
-  s.dev_jsonl_len = line_total;
-  s.dev_jsonl = d + o_var + links_bytes;
-  s.last_n = n;
-  s.last_new = out->n_new;
-  s.last_frontier = want_fr;
-  s.last_yt = false;
-  {
-    std::lock_guard<std::mutex> g(c->st_mu);
-    c->stats.records += n;
-    c->stats.bytes_in += s.in_bytes;
-    c->stats.bytes_out += out->jsonl_len;
-    c->stats.links += n_links_total;
-    c->stats.launches += 1;
-    c->stats.kernel_ms_total += ms;
-    if (want_fr) c->stats.frontier_size = out->frontier_size;
-  }
-  return TGI_OK;
+  return page_launch_and_read(c, s, flags, n, (const void*)tg_page_kernel, kargs, occ, L, &pa.fr, &pa.excl, "tg_page", false, out);
 }
 
 int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
@@ -1161,27 +1190,129 @@ int upload_yt(tgi_ctx* c, Slot& s, const tgi_yt_batch* in) {
   }
   s.in_bytes = 0;
   int rc;
+  YtBatchDev& b = s.yt;
+  const size_t yb[4] = {in->n * sizeof(tgi_yt_rec), in->strs_len, in->n_chans * sizeof(tgi_yt_chan), in->chan_strs_len};
+  size_t yo[5] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) yo[i + 1] = yo[i] + ((yb[i] + PAD + 15) & ~(size_t)15);
+  if (page_enabled() && in->n && in->n <= PAGE_MAX_RECS && in->n_chans <= PAGE_MAX_RECS && yo[4] <= PAGE_MAX_IN_BYTES) {
+    // page-sized: the four arrays in one pinned block, ONE copy (upload_tg_page)
+    CK(s.h_page_in.ensure(yo[4]));
+    CK(s.d_page_in.ensure(yo[4]));
+    uint8_t* h = s.h_page_in.as<uint8_t>();
+    const void* src[4] = {in->recs, in->strs, in->chans, in->chan_strs};
+    for (int i = 0; i < 4; i++) {
+      if (yb[i]) memcpy(h + yo[i], src[i], yb[i]);
+      memset(h + yo[i] + yb[i], 0, yo[i + 1] - yo[i] - yb[i]);
+      s.in_bytes += yb[i];
+    }
+    CK(cudaMemcpyAsync(s.d_page_in.p, h, yo[4], cudaMemcpyHostToDevice, s.stream));
+    uint8_t* d = s.d_page_in.as<uint8_t>();
+    b.recs = (const tgi_yt_rec*)(d + yo[0]);
+    b.strs = d + yo[1];
+    b.chans = (const tgi_yt_chan*)(d + yo[2]);
+    b.chan_strs = d + yo[3];
+  } else {
 #define UP(buf, ptr, cnt)                      \
   rc = h2d(c, s, s.buf, ptr, (size_t)(cnt));   \
   if (rc) return rc;
-  UP(d_recs, in->recs, in->n);
-  UP(d_strs, in->strs, in->strs_len);
-  UP(d_chans, in->chans, in->n_chans);
-  UP(d_chan_strs, in->chan_strs, in->chan_strs_len);
+    UP(d_recs, in->recs, in->n);
+    UP(d_strs, in->strs, in->strs_len);
+    UP(d_chans, in->chans, in->n_chans);
+    UP(d_chan_strs, in->chan_strs, in->chan_strs_len);
 #undef UP
-  rc = join_uploads(c, s);
-  if (rc) return rc;
-  YtBatchDev& b = s.yt;
+    rc = join_uploads(c, s);
+    if (rc) return rc;
+    b.recs = s.d_recs.as<tgi_yt_rec>();
+    b.strs = s.d_strs.as<uint8_t>();
+    b.chans = s.d_chans.as<tgi_yt_chan>();
+    b.chan_strs = s.d_chan_strs.as<uint8_t>();
+  }
   b.n = in->n;
-  b.recs = s.d_recs.as<tgi_yt_rec>();
-  b.strs = s.d_strs.as<uint8_t>();
   b.n_chans = in->n_chans;
-  b.chans = s.d_chans.as<tgi_yt_chan>();
-  b.chan_strs = s.d_chan_strs.as<uint8_t>();
   s.yt_desc_bytes = in->strs_len;
   s.resident = true;
   s.tg.n = 0;
   return TGI_OK;
+}
+
+// a page of the Data API (50 videos) in one cooperative launch (yt_page.cuh); PAGE_FALLBACK as in run_tg_page
+int run_yt_page(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
+  YtBatchDev& b = s.yt;
+  const uint64_t n = b.n;
+  const bool want_fr = flags & TGI_RUN_FRONTIER;
+  static const int occ = [] {
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, yt_page_kernel, CTA_THREADS, 0) != cudaSuccess) return 0;
+    return o;
+  }();
+  if (occ <= 0) { cudaGetLastError(); return PAGE_FALLBACK; }
+  YtPageArgs pa{};
+  {
+    std::lock_guard<std::mutex> g(c->cfg_mu);
+    pa.cfg = c->cfgdev;
+  }
+  pa.run_flags = flags;
+  pa.b = b;
+  // every URL needs "http://x" (8 bytes), every channel link "youtube.com/" (12 bytes): upper bounds, as in run_yt
+  const uint64_t urls_cap = s.yt_desc_bytes / 4 + 1024, arena_cap = s.yt_desc_bytes / 12 + 1024;
+  const uint64_t bslots = next_pow2(std::max<uint64_t>(2 * arena_cap, 1024));
+  CK(s.d_linelen.ensure(n * 4));
+  CK(s.d_link_start.ensure(n * 4));
+  CK(s.d_link_count.ensure(n * 4));
+  CK(s.d_url_start.ensure(n * 4));
+  CK(s.d_url_count.ensure(n * 4));
+  CK(s.d_urls.ensure(urls_cap * sizeof(YtUrl)));
+  CK(s.d_arena.ensure(arena_cap * sizeof(tgi_link)));
+  CK(s.d_xlen.ensure(n * 12));
+  CK(s.d_link_off.ensure((n + 1) * 8));
+  if (want_fr) {
+    CK(s.d_btable.ensure(bslots * 8));
+    CK(s.d_lstate.ensure((size_t)arena_cap * 4));
+    CK(s.d_rec_new.ensure(n * 4));
+    CK(s.d_new_off.ensure((n + 1) * 8));
+  }
+  PageOut L;
+  {
+    const int rc = page_out_prepare(c, s, n, L);
+    if (rc) return rc;
+  }
+  uint8_t* d = s.d_page_out.as<uint8_t>();
+  uint64_t* dsc = (uint64_t*)d;
+  YtOut& yo = pa.yo;
+  yo.status = d + L.o_status;
+  yo.linelen = s.d_linelen.as<uint32_t>();
+  yo.esc_len = s.d_xlen.as<uint32_t>();
+  yo.url_start = s.d_url_start.as<uint32_t>();
+  yo.url_count = s.d_url_count.as<uint32_t>();
+  yo.urls = s.d_urls.as<YtUrl>();
+  yo.urls_cap = (uint32_t)urls_cap;
+  yo.url_cursor = (uint32_t*)(dsc + SC_URL_CURSOR);
+  yo.link_start = s.d_link_start.as<uint32_t>();
+  yo.link_count = s.d_link_count.as<uint32_t>();
+  yo.arena = s.d_arena.as<tgi_link>();
+  yo.arena_cap = (uint32_t)arena_cap;
+  yo.cursor = (uint32_t*)(dsc + SC_CURSOR);
+  yo.err = (int*)(dsc + SC_CURSOR) + 1;
+  pa.scalars = dsc;
+  pa.line_off = (uint64_t*)(d + L.o_line_off);
+  pa.link_off = s.d_link_off.as<uint64_t>();
+  pa.link_off32 = (uint32_t*)(d + L.o_link_off);
+  pa.var = d + L.o_var;
+  pa.var_cap = L.var_cap;
+  pa.fr = c->fr;
+  pa.fb.btable = s.d_btable.as<uint64_t>();
+  pa.fb.bmask = bslots - 1;
+  pa.fb.lstate = s.d_lstate.as<uint32_t>();
+  pa.fb.rec_new = s.d_rec_new.as<uint32_t>();
+  pa.excl = c->excl;
+  pa.bslots = bslots;
+  pa.new_off = s.d_new_off.as<uint64_t>();
+  pa.sc_line_total = SC_LINE_TOTAL;
+  pa.sc_link_total = SC_LINK_TOTAL;
+  pa.sc_new = SC_NEW;
+  pa.sc_count = SC_COUNT;
+  void* kargs[] = {&pa};
+  return page_launch_and_read(c, s, flags, n, (const void*)yt_page_kernel, kargs, occ, L, &pa.fr, &pa.excl, "yt_page", true, out);
 }
 
 int run_yt(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
@@ -1190,6 +1321,11 @@ int run_yt(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   cudaStream_t st = s.stream;
   uint32_t launches = 0;
   const bool want_json = flags & TGI_RUN_JSONL;
+  if (page_enabled() && n && n <= PAGE_MAX_RECS && b.n_chans <= PAGE_MAX_RECS && s.in_bytes <= PAGE_MAX_IN_BYTES && !(flags & TGI_RUN_NO_D2H) &&
+      (flags & (TGI_RUN_JSONL | TGI_RUN_LINKS | TGI_RUN_FRONTIER))) {
+    const int rc = run_yt_page(c, s, flags, out);
+    if (rc != PAGE_FALLBACK) return rc;
+  }
   CfgDev cfg;
   {
     std::lock_guard<std::mutex> g(c->cfg_mu);

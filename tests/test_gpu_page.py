@@ -133,3 +133,45 @@ def test_page_path_is_cheaper_than_the_pipeline():
         pipe = best()
     e.close()
     assert page < pipe, (page, pipe)
+
+
+# ---- YouTube pages (the Data API returns 50 videos per page: crawler/youtube/youtube_crawler.go:353-427) -------------------
+import test_gpu_youtube as ytt
+from yt_corpus import make_youtube, make_youtube_config4
+
+
+@pytest.mark.parametrize("n", [1, 7, 50, 333, 2000])
+@pytest.mark.parametrize("make", [make_youtube, make_youtube_config4])
+def test_youtube_page_parity(n, make):
+    batch, _, _ = make(n, seed=100 + n)
+    _, rg = ytt.both(batch)  # oracle == page path == bulk pipeline
+    assert rg.gpu_launches == 1
+
+
+def test_youtube_page_flags_and_sequence():
+    batch, _, _ = make_youtube(600, seed=5)
+    for flags in (abi.RUN_JSONL, abi.RUN_LINKS, abi.RUN_LINKS | abi.RUN_FRONTIER):
+        _, rg = ytt.both(batch, flags, tz_offset_sec=-18000, crawl_label=b"yt<page>")
+        assert rg.gpu_launches == 1
+    o, e = Oracle(), Engine()
+    for k in range(8):  # pages of 50 sharing the snowball frontier
+        page, _, _ = make_youtube(50, seed=900 + k % 3)  # every third page repeats: nothing new the second time
+        ro, rg = o.youtube(page, ytt.ALL), e.youtube(page, ytt.ALL)
+        assert rg.gpu_launches == 1
+        assert_results_equal(ro, rg, ytt.ALL, f"page {k}")
+    assert np.array_equal(o.frontier_export(), e.frontier_export())
+    e.close()
+
+
+def test_youtube_page_falls_back_when_the_block_is_too_small():
+    batch, _, _ = make_youtube(400, seed=8)
+    os.environ["TGI_PAGE_VAR_CAP"] = "65536"
+    try:
+        o, e = Oracle(), Engine()
+        ro, rg = o.youtube(batch, ytt.ALL), e.youtube(batch, ytt.ALL)
+        assert rg.gpu_launches > 1
+        assert_results_equal(ro, rg, ytt.ALL)
+        assert np.array_equal(o.frontier_export(), e.frontier_export())
+        e.close()
+    finally:
+        del os.environ["TGI_PAGE_VAR_CAP"]

@@ -6,7 +6,7 @@ import pytest
 from distributed_crawler_b200 import abi
 from distributed_crawler_b200.engine import Engine
 from distributed_crawler_b200.pack import YouTubeChannel, YouTubeVideo, pack_youtube
-from helpers import assert_results_equal
+from helpers import assert_results_equal, no_page
 from oracle.pyoracle import Oracle
 from yt_corpus import make_youtube
 
@@ -21,6 +21,15 @@ def both(batch, flags=ALL, **cfg):
     if flags & abi.RUN_FRONTIER:
         assert np.array_equal(o.frontier_export(), e.frontier_export())
     assert rg.gpu_launches > 0
+    if rg.gpu_launches == 1 and batch.n:  # a page-sized batch took the one-launch path: the bulk pipeline as well
+        with no_page():
+            e2 = Engine(**cfg)
+            r2 = e2.youtube(batch, flags)
+            assert r2.gpu_launches > 1
+            assert_results_equal(ro, r2, flags, "bulk pipeline")
+            if flags & abi.RUN_FRONTIER:
+                assert np.array_equal(o.frontier_export(), e2.frontier_export())
+            e2.close()
     e.close()
     return ro, rg
 
