@@ -101,7 +101,6 @@ struct NcclApi {
 struct Slot {
   int idx = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t stream_in = nullptr, stream_out = nullptr;  // bulk batches: uploads / result copies off the kernels' stream (copy_streams())
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_mid = nullptr, ev_p0 = nullptr, ev_p1 = nullptr, ev_e0 = nullptr, ev_e1 = nullptr, ev_f1 = nullptr, ev_fr0 = nullptr, ev_fr1 = nullptr;
   // device inputs
   DevBuf d_recs, d_strs, d_ent_off, d_ents, d_react_off, d_reacts, d_comment_off, d_comments, d_aux,
@@ -350,31 +349,16 @@ int launch_scan(tgi_ctx* c, Slot& s, const uint32_t* in, uint64_t n, uint64_t* o
   return TGI_OK;
 }
 
-// bit 0: result copies on the slot's stream_out, bit 1: uploads on its stream_in (A/B switch, TGI_COPY_STREAMS)
-int copy_streams() {
-  static const int v = [] {
-    const char* e = getenv("TGI_COPY_STREAMS");
-    return e ? atoi(e) : 0;
-  }();
-  return v;
-}
 template <class T>
 int h2d(tgi_ctx* c, Slot& s, DevBuf& d, const T* src, size_t count) {
   size_t bytes = count * sizeof(T);
-  cudaStream_t st = (copy_streams() & 2) ? s.stream_in : s.stream;
+  cudaStream_t st = s.stream;
   CK(d.ensure(bytes));
   if (bytes) CK(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, st));
   // the pad behind the array: a COPY of zeros, not a memset — a memset is a kernel and would queue behind whatever the
   // other slots' (persistent, SM-filling) kernels are doing, which chains every one of the eleven uploads to them
   CK(cudaMemcpyAsync((uint8_t*)d.p + bytes, c->h_zero.p, PAD, cudaMemcpyHostToDevice, st));
   s.in_bytes += bytes;
-  return TGI_OK;
-}
-// the kernels' stream continues behind the uploads
-int join_uploads(tgi_ctx* c, Slot& s) {
-  if (!(copy_streams() & 2)) return TGI_OK;
-  CK(cudaEventRecord(s.ev_mid, s.stream_in));
-  CK(cudaStreamWaitEvent(s.stream, s.ev_mid, 0));
   return TGI_OK;
 }
 
@@ -544,8 +528,6 @@ int upload_tg(tgi_ctx* c, Slot& s, const tgi_tg_batch* in) {
   UP(d_chans, in->chans, in->n_chans);
   UP(d_chan_strs, in->chan_strs, in->chan_strs_len);
 #undef UP
-  rc = join_uploads(c, s);
-  if (rc) return rc;
   TgBatchDev& b = s.tg;
   b.n = n;
   b.recs = s.d_recs.as<tgi_tg_rec>();
@@ -682,10 +664,6 @@ int finish_batch(tgi_ctx* c, Slot& s, uint64_t n, uint32_t flags, uint64_t line_
     CK(cudaGetLastError());
   }
   CK(cudaEventRecord(s.ev_k1, st));
-  if (copy_streams() & 1) {  // the result copies leave the kernels' stream (the slot's next job starts behind the host sync below)
-    CK(cudaStreamWaitEvent(s.stream_out, s.ev_k1, 0));
-    st = s.stream_out;
-  }
   CK(cudaMemcpyAsync(hsc, dsc, SC_COUNT * 8, cudaMemcpyDeviceToHost, st));
 
   memset(out, 0, sizeof *out);
@@ -1220,8 +1198,6 @@ int upload_yt(tgi_ctx* c, Slot& s, const tgi_yt_batch* in) {
     UP(d_chans, in->chans, in->n_chans);
     UP(d_chan_strs, in->chan_strs, in->chan_strs_len);
 #undef UP
-    rc = join_uploads(c, s);
-    if (rc) return rc;
     b.recs = s.d_recs.as<tgi_yt_rec>();
     b.strs = s.d_strs.as<uint8_t>();
     b.chans = s.d_chans.as<tgi_yt_chan>();
@@ -1667,8 +1643,6 @@ int tgi_create(const tgi_config* cfg, tgi_ctx** out) {
     s.idx = i;
     s.h_scalars.flags = cudaHostAllocMapped;  // publish() stores into it from the device
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&s.stream_in, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&s.stream_out, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&s.ev_k0) != cudaSuccess || cudaEventCreate(&s.ev_k1) != cudaSuccess ||
         cudaEventCreate(&s.ev_p0) != cudaSuccess || cudaEventCreate(&s.ev_p1) != cudaSuccess ||
         cudaEventCreate(&s.ev_e0) != cudaSuccess || cudaEventCreate(&s.ev_e1) != cudaSuccess || cudaEventCreate(&s.ev_f1) != cudaSuccess ||
@@ -1733,8 +1707,6 @@ void tgi_destroy(tgi_ctx* c) {
     if (s.ev_mid) cudaEventDestroy(s.ev_mid);
     for (cudaEvent_t e : {s.ev_p0, s.ev_p1, s.ev_e0, s.ev_e1, s.ev_f1, s.ev_fr0, s.ev_fr1}) if (e) cudaEventDestroy(e);
     if (s.stream) cudaStreamDestroy(s.stream);
-    if (s.stream_in) cudaStreamDestroy(s.stream_in);
-    if (s.stream_out) cudaStreamDestroy(s.stream_out);
   }
   for (auto& f : c->stg_free) cudaFreeHost(f.second);
   for (auto& f : c->stg_live) cudaFreeHost(f.first);
@@ -2210,7 +2182,8 @@ int tgi_pending_edges(tgi_ctx* c, int slot, int64_t now_sec, tgi_edge* rows, uin
   CK(drows.ensure(m * sizeof(tgi_edge)));
   ExclusionDev x = c->excl;
   x.now_sec = now_sec;
-  const uint32_t* chan = s.last_yt ? &s.d_recs.as<tgi_yt_rec>()->chan_idx : &s.d_recs.as<tgi_tg_rec>()->chan_idx;
+  // the resident batch descriptor, not the upload buffers: a page-sized batch lives in the slot's one-block upload
+  const uint32_t* chan = s.last_yt ? &s.yt.recs->chan_idx : &s.tg.recs->chan_idx;
   const uint32_t stride = s.last_yt ? (uint32_t)sizeof(tgi_yt_rec) : (uint32_t)sizeof(tgi_tg_rec);
   edges_emit_kernel<<<(unsigned)((s.last_n + 255) / 256), 256, 0, st>>>(s.last_n, s.d_link_start.as<uint32_t>(), s.d_link_count.as<uint32_t>(),
                                                                     s.d_arena.as<tgi_link>(), chan, stride, s.d_new_off.as<uint64_t>(), x,

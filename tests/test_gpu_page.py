@@ -175,3 +175,32 @@ def test_youtube_page_falls_back_when_the_block_is_too_small():
         e.close()
     finally:
         del os.environ["TGI_PAGE_VAR_CAP"]
+
+
+def test_page_hand_off_rows():
+    """f3 on the page path: exclusion sets, TGI_RUN_SKIP_INVALID and the pending_edges rows of a page equal the oracle's."""
+    from distributed_crawler_b200.engine import names_to_keys32
+    from test_handoff import NOW, _sets
+    c = Corpus(3000, profile=3, nthreads=2)
+    plain = Oracle().telegram(c.batch, abi.RUN_LINKS)
+    inv, stamps, disc = _sets(plain.links)
+    o, e = Oracle(), Engine()
+    for x in (o, e):
+        x.set_add(abi.SET_INVALID, names_to_keys32(inv), np.array(stamps, np.int64))
+        x.set_add(abi.SET_DISCOVERED, names_to_keys32(disc))
+        x.set_now(NOW)
+    T = TANDEM | abi.RUN_SKIP_INVALID
+    total = 0
+    for k in range(6):
+        page = c.batch.slice(k * 500, (k + 1) * 500)
+        ro = o.telegram(page, T)
+        e.telegram_submit(2, page, T)
+        rg = e.telegram_wait(2, copy=True)
+        assert rg.gpu_launches == 1
+        assert np.array_equal(ro.links, rg.links) and ro.n_new == rg.n_new
+        rows_o, rows_g = o.pending_edges(NOW), e.pending_edges(2, NOW)
+        assert np.array_equal(rows_o, rows_g) and len(rows_g) == rg.n_new
+        total += len(rows_g)
+        e.release(2)
+    assert total > 0
+    e.close()

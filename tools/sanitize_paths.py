@@ -9,14 +9,21 @@ from yt_corpus import make_youtube, make_youtube_config4
 from gm_corpus import make_generic
 e = Engine()
 f = abi.RUN_JSONL | abi.RUN_LINKS | abi.RUN_FRONTIER | abi.RUN_SKIP_SELF
-for p in (1, 2, 3):
-    c = Corpus(3000, profile=p, nthreads=4)
-    r = e.telegram(c.batch, f)
-    print("tg", p, r.jsonl_len, r.n_links)
-for mk in (make_youtube, make_youtube_config4):
-    b, _, _ = mk(600, seed=3)
-    r = e.youtube(b, abi.RUN_JSONL | abi.RUN_LINKS | abi.RUN_FRONTIER)
-    print("yt", r.jsonl_len, r.n_links)
+# page-sized batches take the one-launch page kernels; TGI_NO_PAGE=1 sends the same batches through the bulk pipeline
+for no_page in (False, True):
+    if no_page:
+        os.environ["TGI_NO_PAGE"] = "1"
+    for p in (1, 2, 3):
+        c = Corpus(3000, profile=p, nthreads=4)
+        r = e.telegram(c.batch, f)
+        print("tg", p, r.jsonl_len, r.n_links, "launches", r.gpu_launches)
+    for mk in (make_youtube, make_youtube_config4):
+        b, _, _ = mk(600, seed=3)
+        r = e.youtube(b, abi.RUN_JSONL | abi.RUN_LINKS | abi.RUN_FRONTIER)
+        print("yt", r.jsonl_len, r.n_links, "launches", r.gpu_launches)
+    os.environ.pop("TGI_NO_PAGE", None)
+c = Corpus(20000, profile=2, nthreads=4)  # above the page limit: the bulk pipeline with its multi-launch scans
+print("tg bulk", e.telegram(c.batch, f).gpu_launches)
 g, _ = make_generic(500, seed=4)
 print("gm", e.generic(g).jsonl_len)
 print("join", e.key_join(np.arange(2000).reshape(-1, 2), np.arange(1000).reshape(-1, 2))[:4])
