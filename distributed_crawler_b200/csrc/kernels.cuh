@@ -21,6 +21,24 @@ namespace tgi {
 
 constexpr int WARPS_PER_CTA = 8;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+// Resident CTAs per SM the compiler budgets registers for.  Swept on the config-2 step (tools/variants.sh, profiles/README.md):
+// 4 (64 registers) 41.2 ms, 5: 38.6, 6: 38.0, 7 (32 registers): 37.7, 8: 38.2 — the spills barely grow (most of the "spill"
+// is local arrays), the extra warps per scheduler are worth more.
+#ifndef LB_PARSE
+#define LB_PARSE 7
+#endif
+#ifndef LB_SIZE
+#define LB_SIZE 7
+#endif
+#ifndef LB_ESC
+#define LB_ESC 7
+#endif
+#ifndef LB_MAPS
+#define LB_MAPS 7
+#endif
+#ifndef LB_YT
+#define LB_YT 6  // 3: 22.8 ms per 2 M config-4 records, 4: 20.4, 5: 19.2, 6: 18.7, 8: 18.6 (tools/variants_yt.sh)
+#endif
 
 #define ERR_ARENA_OVERFLOW 1
 #define ERR_TOO_MANY_REACTIONS 2
@@ -205,7 +223,7 @@ DEVI void tg_parse_body(const TgBatchDev& b, const CfgDev& cfg, uint32_t run_fla
     }
   }
 }
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) { tg_parse_body(b, cfg, run_flags, o); }
+__global__ void __launch_bounds__(CTA_THREADS, LB_PARSE) tg_parse_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) { tg_parse_body(b, cfg, run_flags, o); }
 DEVI void tg_ent_map_body(const TgBatchDev& b, const ParseOut& o) {
   const int wid = threadIdx.x >> 5, l = lane_id();
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
@@ -219,7 +237,7 @@ DEVI void tg_ent_map_body(const TgBatchDev& b, const ParseOut& o) {
     }
   }
 }
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_ent_map_kernel(TgBatchDev b, ParseOut o) { tg_ent_map_body(b, o); }
+__global__ void __launch_bounds__(CTA_THREADS, LB_PARSE) tg_ent_map_kernel(TgBatchDev b, ParseOut o) { tg_ent_map_body(b, o); }
 DEVI void tg_parse_ent_body(const TgBatchDev& b, const CfgDev& cfg, uint32_t run_flags, const ParseOut& o) {
   const int wid = threadIdx.x >> 5, l = lane_id();
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
@@ -233,7 +251,7 @@ DEVI void tg_parse_ent_body(const TgBatchDev& b, const CfgDev& cfg, uint32_t run
     }
   }
 }
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_parse_ent_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) {
+__global__ void __launch_bounds__(CTA_THREADS, LB_PARSE) tg_parse_ent_kernel(TgBatchDev b, CfgDev cfg, uint32_t run_flags, ParseOut o) {
   tg_parse_ent_body(b, cfg, run_flags, o);
 }
 
@@ -363,7 +381,7 @@ DEVI void tg_size_lane_body(const TgBatchDev& b, const CfgDev& cfg, const ParseO
   for (int dd = 16; dd; dd >>= 1) var_sum += __shfl_down_sync(FULL, var_sum, dd);
   if (l == 0 && var_sum) atomicAdd(o.var_total, (unsigned long long)var_sum);
 }
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_size_lane_kernel(TgBatchDev b, CfgDev cfg, ParseOut o) { tg_size_lane_body(b, cfg, o); }
+__global__ void __launch_bounds__(CTA_THREADS, LB_SIZE) tg_size_lane_kernel(TgBatchDev b, CfgDev cfg, ParseOut o) { tg_size_lane_body(b, cfg, o); }
 
 // ---- emit --------------------------------------------------------------------------------------------------------
 struct EmitIn {
@@ -460,7 +478,7 @@ DEVI void tg_emit_esc_body(const TgBatchDev& b, const EmitIn& in) {
   }
 }
 template <int MODE>
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_esc_kernel(TgBatchDev b, EmitIn in) { tg_emit_esc_body<MODE>(b, in); }
+__global__ void __launch_bounds__(CTA_THREADS, LB_ESC) tg_emit_esc_kernel(TgBatchDev b, EmitIn in) { tg_emit_esc_body<MODE>(b, in); }
 
 DEVI void tg_emit_maps_body(const TgBatchDev& b, const EmitIn& in) {
   __shared__ MapScratch mss[WARPS_PER_CTA];
@@ -481,7 +499,7 @@ DEVI void tg_emit_maps_body(const TgBatchDev& b, const EmitIn& in) {
     __syncwarp();
   }
 }
-__global__ void __launch_bounds__(CTA_THREADS, 4) tg_emit_maps_kernel(TgBatchDev b, EmitIn in) { tg_emit_maps_body(b, in); }
+__global__ void __launch_bounds__(CTA_THREADS, LB_MAPS) tg_emit_maps_kernel(TgBatchDev b, EmitIn in) { tg_emit_maps_body(b, in); }
 
 // ---- YouTube (config 4) ------------------------------------------------------------------------------
 struct YtOut {
@@ -554,7 +572,7 @@ DEVI void yt_parse_body(const YtBatchDev& b, const CfgDev& cfg, uint32_t run_fla
     }
   }
 }
-__global__ void __launch_bounds__(CTA_THREADS, 4) yt_parse_kernel(YtBatchDev b, CfgDev cfg, uint32_t run_flags, YtOut o) { yt_parse_body(b, cfg, run_flags, o); }
+__global__ void __launch_bounds__(CTA_THREADS, LB_YT) yt_parse_kernel(YtBatchDev b, CfgDev cfg, uint32_t run_flags, YtOut o) { yt_parse_body(b, cfg, run_flags, o); }
 
 // one record by one warp (yt_size_kernel, yt_page_kernel)
 DEVI void yt_size_record(const YtBatchDev& b, const CfgDev& cfg, const YtOut& o, uint64_t r, YtScratch* sc) {
@@ -584,7 +602,7 @@ DEVI void yt_size_record(const YtBatchDev& b, const CfgDev& cfg, const YtOut& o,
     }
   }
 }
-__global__ void __launch_bounds__(CTA_THREADS, 4) yt_size_kernel(YtBatchDev b, CfgDev cfg, YtOut o) {
+__global__ void __launch_bounds__(CTA_THREADS, LB_YT) yt_size_kernel(YtBatchDev b, CfgDev cfg, YtOut o) {
   __shared__ YtScratch scs[WARPS_PER_CTA];
   int wid = threadIdx.x >> 5;
   uint64_t nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
@@ -595,7 +613,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) yt_size_kernel(YtBatchDev b, C
 }
 
 // length pass, one lane per record (yt_lane.cuh); the description and the title are measured by the warp
-__global__ void __launch_bounds__(CTA_THREADS, 4) yt_size_lane_kernel(YtBatchDev b, CfgDev cfg, YtOut o) {
+__global__ void __launch_bounds__(CTA_THREADS, LB_YT) yt_size_lane_kernel(YtBatchDev b, CfgDev cfg, YtOut o) {
   const int wid = threadIdx.x >> 5, l = lane_id();
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {
@@ -661,7 +679,7 @@ DEVI void yt_emit_record(const YtBatchDev& b, const CfgDev& cfg, const YtOut& o,
   if (lane_id() == 0 && (uint64_t)(w.p - out) != line_off[r + 1]) atomicOr(err, 16);
   __syncwarp();
 }
-__global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_kernel(YtBatchDev b, CfgDev cfg, YtOut o, const uint64_t* line_off, uint8_t* out, int* err,
+__global__ void __launch_bounds__(CTA_THREADS, LB_YT) yt_emit_kernel(YtBatchDev b, CfgDev cfg, YtOut o, const uint64_t* line_off, uint8_t* out, int* err,
                                                                  int lane_mode) {
   __shared__ YtScratch scs[WARPS_PER_CTA];
   int wid = threadIdx.x >> 5, l = lane_id();
@@ -678,7 +696,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_kernel(YtBatchDev b, C
 }
 
 // lane writer (yt_lane.cuh): one lane per clean record
-__global__ void __launch_bounds__(CTA_THREADS, 4) yt_emit_lane_kernel(YtBatchDev b, CfgDev cfg, YtOut o, const uint64_t* line_off, uint8_t* out, int* err) {
+__global__ void __launch_bounds__(CTA_THREADS, LB_YT) yt_emit_lane_kernel(YtBatchDev b, CfgDev cfg, YtOut o, const uint64_t* line_off, uint8_t* out, int* err) {
   const int wid = threadIdx.x >> 5, l = lane_id();
   const uint64_t ngroups = (b.n + 31) / 32, nwarps = (uint64_t)gridDim.x * WARPS_PER_CTA;
   for (uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_CTA + wid; g < ngroups; g += nwarps) {

@@ -435,6 +435,17 @@ int validate_tg(tgi_ctx* c, const tgi_tg_batch* in) {
   return TGI_OK;
 }
 
+// CTAs per SM in the grids of the grid-stride kernels.  Records differ in cost (text length, entities, comments), so a
+// grid of exactly the resident CTAs leaves SMs idle behind the slowest stride; many more CTAs than fit let the hardware
+// scheduler balance: 8 per SM 41.2 ms per config-2 step, 24: 38.9, 48: 37.7, 96-192: 37.1 (TGI_GRID_MULT, tools/variants_bench.sh)
+unsigned grid_mult() {
+  static const unsigned v = [] {
+    const char* e = getenv("TGI_GRID_MULT");
+    return e && atoi(e) > 0 ? (unsigned)atoi(e) : 128u;
+  }();
+  return v;
+}
+
 // ---- page-sized batches: one block in, one launch, one block out (tg_page.cuh) ---------------------------------------
 constexpr uint64_t PAGE_MAX_RECS = 8192;          // the in-kernel scans are single-CTA
 constexpr uint64_t PAGE_MAX_IN_BYTES = 4u << 20;
@@ -1042,10 +1053,10 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
     po.ent_range = s.d_ent_range.as<int2>();
     if (n) {
       uint64_t want = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-      unsigned g = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms * 8);
+      unsigned g = (unsigned)std::min<uint64_t>(want, (uint64_t)c->sms * grid_mult());
       CK(cudaEventRecord(s.ev_p0, st));
       const uint64_t groups = (n + 31) / 32;
-      unsigned ge = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
+      unsigned ge = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * grid_mult());
       if (s.n_ents) {  // records with entities first: status + links (two kernels by instruction footprint)
         tg_ent_map_kernel<<<ge, CTA_THREADS, 0, st>>>(b, po);
         tg_parse_ent_kernel<<<ge, CTA_THREADS, 0, st>>>(b, cfg, flags, po);
@@ -1125,10 +1136,11 @@ int run_tg(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       ei.list_count = (uint32_t*)(dsc + SC_LISTS);
       ei.lane_text_max = LANE_TEXT_MAX;
       // one LANE per record (tg_lane.cuh): 3 resident CTAs per SM by shared memory, persistent over the record groups
-      unsigned gl = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * 3);
+      static const unsigned lane_mult = [] { const char* e = getenv("TGI_LANE_MULT"); return e && atoi(e) > 0 ? (unsigned)atoi(e) : 24u; }();  // 3 resident: 13.06 ms, 24: 12.58
+      unsigned gl = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * lane_mult);
       tg_emit_lane_kernel<<<gl, CTA_THREADS, sizeof(LaneShared), st>>>(b, cfg, ei);
       CK(cudaEventRecord(s.ev_f1, st));
-      unsigned gg = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * 8);
+      unsigned gg = (unsigned)std::min<uint64_t>(ctas, (uint64_t)c->sms * grid_mult());
       static const bool one_esc = getenv("TGI_ESC_ONE") != nullptr;  // A/B: the round-1 single escape kernel
       if (one_esc) {
         tg_emit_esc_kernel<ESC_ALL><<<gg, CTA_THREADS, 0, st>>>(b, ei);
@@ -1340,7 +1352,7 @@ int run_yt(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   yo.arena_cap = (uint32_t)std::min<uint64_t>(arena_cap, 0xFFFFFFFFu);
   yo.cursor = (uint32_t*)(dsc + SC_CURSOR);
   yo.err = (int*)(dsc + SC_CURSOR) + 1;
-  unsigned g = (unsigned)std::min<uint64_t>((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
+  unsigned g = (unsigned)std::min<uint64_t>((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * grid_mult());
   if (n) {
     CK(cudaEventRecord(s.ev_p0, st));
     yt_parse_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, flags, yo);
@@ -1351,7 +1363,7 @@ int run_yt(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
         yt_size_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, yo);
       } else {
         const uint64_t groups = (n + 31) / 32;
-        unsigned gs = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
+        unsigned gs = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * grid_mult());
         yt_size_lane_kernel<<<gs, CTA_THREADS, 0, st>>>(b, cfg, yo);
       }
       launches++;
@@ -1384,7 +1396,7 @@ int run_yt(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
       CK(cudaEventRecord(s.ev_e0, st));
       static const bool yt_warp = getenv("TGI_YT_WARP") != nullptr;  // A/B switch: the warp writer for every record
       const uint64_t groups = (n + 31) / 32;
-      unsigned gg = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
+      unsigned gg = (unsigned)std::min<uint64_t>((groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * grid_mult());
       if (!yt_warp) {
         yt_emit_lane_kernel<<<gg, CTA_THREADS, 0, st>>>(b, cfg, yo, s.d_line_off.as<uint64_t>(), s.d_jsonl.as<uint8_t>(), yo.err);
         launches++;
@@ -1461,7 +1473,7 @@ int run_gm(tgi_ctx* c, Slot& s, const tgi_gm_batch* in, uint32_t flags, tgi_resu
     CK(cudaMemsetAsync(s.d_link_count.p, 0, n * 4, st));
   }
   int* derr = (int*)(dsc + SC_CURSOR) + 1;
-  unsigned g = (unsigned)std::min<uint64_t>((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * 8);
+  unsigned g = (unsigned)std::min<uint64_t>((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (uint64_t)c->sms * grid_mult());
   CK(cudaEventRecord(s.ev_p0, st));
   if (n) {  // the status does not depend on TGI_RUN_JSONL: the size pass always runs
     gm_size_kernel<<<g, CTA_THREADS, 0, st>>>(b, cfg, s.d_status.as<uint8_t>(), s.d_linelen.as<uint32_t>());
