@@ -452,7 +452,10 @@ DEVI void tg_emit_lane_body(const TgBatchDev& b, const CfgDev& cfg, const EmitIn
     atomicAdd(in.counters + 1, (unsigned long long)bytes_in);
   }
 }
-__global__ void __launch_bounds__(CTA_THREADS, 3) tg_emit_lane_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
+#ifndef LB_LANE
+#define LB_LANE 3
+#endif
+__global__ void __launch_bounds__(CTA_THREADS, LB_LANE) tg_emit_lane_kernel(TgBatchDev b, CfgDev cfg, EmitIn in) {
   extern __shared__ __align__(128) uint8_t lane_smem[];
   tg_emit_lane_body(b, cfg, in, *(LaneShared*)lane_smem);
 }

@@ -21,7 +21,10 @@
 
 namespace tgi {
 
-constexpr uint32_t LANE_STAGE_BYTES = 128;                    // staged per lane between two drains
+#ifndef LANE_STAGE
+#define LANE_STAGE 128
+#endif
+constexpr uint32_t LANE_STAGE_BYTES = LANE_STAGE;             // staged per lane between two drains (128 or 64)
 constexpr uint32_t LANE_STAGE_ROW = LANE_STAGE_BYTES + 16;    // +16 spreads the lanes' rows over the banks
 
 struct LaneStream {
@@ -47,10 +50,11 @@ DEVI void ls_stage(LaneStream& s, uint64_t blk) {
 DEVI void ls_drain_warp(LaneStream& s) {
   if (!__any_sync(FULL, s.fill != 0)) return;
   __syncwarp();
-  const int l = lane_id(), sub = l >> 3, t16 = (l & 7) * 16;
+  constexpr int LPR = LANE_STAGE_BYTES / 16, RPP = 32 / LPR;  // lanes per row, rows per pass
+  const int l = lane_id(), sub = l / LPR, t16 = (l % LPR) * 16;
   const uint32_t warp_rows = s.row_s - (uint32_t)l * LANE_STAGE_ROW;
 #pragma unroll 2
-  for (int j = 0; j < 32; j += 4) {
+  for (int j = 0; j < 32; j += RPP) {
     const int rj = j + sub;
     const uint32_t f = __shfl_sync(FULL, s.fill, rj);
     const uint64_t sg = __shfl_sync(FULL, s.seg, rj);
