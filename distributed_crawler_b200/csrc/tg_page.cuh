@@ -50,6 +50,7 @@ struct PageArgs {
   uint32_t* link_off32;    // [n+1] result block
   uint8_t* var;            // result block: links (36 bytes each), then the JSONL at the next 256-byte boundary
   uint64_t var_cap;
+  uint64_t max_out;        // tgi_config.max_out_bytes (0 = no limit): a page over it falls back BEFORE the frontier is touched
   // frontier
   FrontierDev fr;
   FrontierBatch fb;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tg_page_kernel(const __grid_co
   stamp();
   const uint64_t links_bytes = want_links ? (a.scalars[a.sc_link_total] * sizeof(tgi_link) + 255) & ~255ull : 0;
   const uint64_t line_total = want_json ? a.scalars[a.sc_line_total] : 0;
-  if (links_bytes + line_total > a.var_cap) {
+  if (links_bytes + line_total > a.var_cap || (a.max_out && line_total > a.max_out)) {
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.po.err, ERR_PAGE_OVERFLOW);
     return;
   }

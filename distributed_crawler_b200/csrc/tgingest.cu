@@ -974,6 +974,7 @@ int run_tg_page(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   pa.link_off32 = (uint32_t*)(d + o_link_off);
   pa.var = d + o_var;
   pa.var_cap = var_cap;
+  pa.max_out = c->cfg.max_out_bytes;
   pa.fr = c->fr;
   pa.fb.btable = s.d_btable.as<uint64_t>();
   pa.fb.bmask = bslots - 1;
@@ -1287,6 +1288,7 @@ int run_yt_page(tgi_ctx* c, Slot& s, uint32_t flags, tgi_result* out) {
   pa.link_off32 = (uint32_t*)(d + L.o_link_off);
   pa.var = d + L.o_var;
   pa.var_cap = L.var_cap;
+  pa.max_out = c->cfg.max_out_bytes;
   pa.fr = c->fr;
   pa.fb.btable = s.d_btable.as<uint64_t>();
   pa.fb.bmask = bslots - 1;

@@ -26,6 +26,7 @@ struct YtPageArgs {
   uint32_t* link_off32;  // [n+1] result block
   uint8_t* var;          // result block: links, then the JSONL at the next 256-byte boundary
   uint64_t var_cap;
+  uint64_t max_out;      // as PageArgs.max_out
   FrontierDev fr;
   FrontierBatch fb;
   ExclusionDev excl;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) yt_page_kernel(const __grid_co
   stamp();
   const uint64_t links_bytes = want_links ? (a.scalars[a.sc_link_total] * sizeof(tgi_link) + 255) & ~255ull : 0;
   const uint64_t line_total = want_json ? a.scalars[a.sc_line_total] : 0;
-  if (links_bytes + line_total > a.var_cap) {
+  if (links_bytes + line_total > a.var_cap || (a.max_out && line_total > a.max_out)) {
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.yo.err, ERR_PAGE_OVERFLOW);
     return;
   }

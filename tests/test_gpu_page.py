@@ -204,3 +204,45 @@ def test_page_hand_off_rows():
         e.release(2)
     assert total > 0
     e.close()
+
+
+def test_youtube_page_pending_edges_equal_the_bulk_pipelines():
+    """tgi_pending_edges after a YouTube batch reads the resident descriptor: same rows from the page path and the bulk path."""
+    batch, _, _ = make_youtube(500, seed=12)
+    rows = []
+    for bulk in (False, True):
+        e = Engine()
+        if bulk:
+            os.environ["TGI_NO_PAGE"] = "1"
+        try:
+            e.youtube_submit(1, batch, ytt.ALL)
+            r = e.youtube_wait(1, copy=True)
+        finally:
+            os.environ.pop("TGI_NO_PAGE", None)
+        assert (r.gpu_launches == 1) == (not bulk)
+        got = e.pending_edges(1, 1_760_000_000)
+        assert len(got) == r.n_new and r.n_new > 0
+        rows.append(got.copy())
+        e.release(1)
+        e.close()
+    assert np.array_equal(rows[0], rows[1])
+
+
+@pytest.mark.parametrize("bulk", [False, True])
+def test_max_out_bytes_rejects_the_batch_without_touching_the_frontier(bulk):
+    """tgi_config.max_out_bytes: a batch whose JSONL is over the limit is TGI_E_CAPACITY and leaves the dedup set alone."""
+    from distributed_crawler_b200.engine import EngineError
+    c = Corpus(300, profile=2, first=4)
+    e = Engine(max_out_bytes=10_000)
+    if bulk:
+        os.environ["TGI_NO_PAGE"] = "1"
+    try:
+        with pytest.raises(EngineError) as ei:
+            e.telegram(c.batch, ALL)
+        assert ei.value.code == abi.E_CAPACITY
+    finally:
+        os.environ.pop("TGI_NO_PAGE", None)
+    assert e.frontier_size() == 0
+    ro, rg = Oracle().telegram(c.batch, abi.RUN_LINKS | abi.RUN_FRONTIER), e.telegram(c.batch, abi.RUN_LINKS | abi.RUN_FRONTIER)
+    assert ro.n_new == rg.n_new > 0  # links-only batches carry no JSONL: not limited
+    e.close()
