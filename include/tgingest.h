@@ -366,7 +366,22 @@ int tgi_set_clock(tgi_ctx* ctx, int64_t created_at_sec, int32_t created_at_nsec,
  * slice of messages in one call.  `slot` selects one of TGI_SLOTS independent staging slots so
  * calls from different goroutines / pipelined calls overlap (H2D, kernels and D2H on the slot's
  * stream).  Inputs must stay valid until the matching wait returns.  tgi_telegram_batch = claim a
- * free slot + submit + wait; its result is released with tgi_result_release(ctx, out->slot).     */
+ * free slot + submit + wait; its result is released with tgi_result_release(ctx, out->slot).
+ *
+ * Batch size.  A batch of at most 8192 records and 4 MB — the reference calls ParseMessage with one
+ * page of 100 messages (crawl/runner.go:1110) — runs as ONE cooperative kernel launch with one copy
+ * in and one copy out (tgi_result.gpu_launches == 1; ~0.15 ms per 100 messages); bigger batches
+ * take the multi-kernel pipeline (~27 launches, PCIe-bound at ~22 M messages/s per GPU).  The bytes
+ * are the same either way.  tgi_youtube_batch: the same split (a Data-API page is 50 videos).
+ *
+ * Order.  Batches with TGI_RUN_FRONTIER enter the dedup set in the order in which they were
+ * SUBMITTED (tgi_*_submit / the blocking calls), whichever slot or thread carries them: TGI_LF_NEW,
+ * n_new and the export order are those of one thread processing the batches one after the other.
+ *
+ * Diagnostics (environment, read per call or at first use; none changes results): TGI_NO_PAGE=1 the
+ * multi-kernel pipeline for every size; TGI_PAGE_TRACE=1 phase clock of the page kernels on
+ * stderr; TGI_TRACE_SLOTS=1 host-side timeline of the slots' synchronisation points;
+ * TGI_GRID_MULT / TGI_LANE_MULT grid sizes in CTAs per SM (defaults 128 / 24).                    */
 #define TGI_SLOTS 3
 int tgi_telegram_submit(tgi_ctx* ctx, int slot, const tgi_tg_batch* in, uint32_t run_flags);
 int tgi_telegram_wait(tgi_ctx* ctx, int slot, tgi_result* out);
