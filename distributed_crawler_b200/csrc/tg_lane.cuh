@@ -171,7 +171,10 @@ constexpr int LANE_ROW_WORDS = 36;  // per lane: 8 blocks of rendered fields + 8
                                     // keeps the lanes' LDS.128 on distinct banks
 constexpr int LANE_WARPS = 8;
 constexpr uint32_t LANE_LINKS_MAX = 4;   // more outlinks than this are left to the maps kernel
-constexpr uint32_t LANE_TEXT_MAX = 512;  // longer (or escaped) strings are left to the warp-per-record esc kernel
+#ifndef LANE_TEXT
+#define LANE_TEXT 512
+#endif
+constexpr uint32_t LANE_TEXT_MAX = LANE_TEXT;  // longer (or escaped) strings are left to the warp-per-record esc kernel
 struct LaneShared {
   uint4 tmpl[kTgLaneTemplateLen / 16];
   uint4 ptype[TGI_CT__COUNT * 2];  // MessageContentType() strings, 32 bytes each, zero padded
