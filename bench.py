@@ -481,6 +481,27 @@ def main():
             eng.unstage(s)
         del staged, subs
 
+    # ---- page-sized calls: the granularity the reference calls ParseMessage / convertVideoToPost with ------------------
+    page_calls = None
+    if rank == 0 and not args.no_e2e and hasattr(corpora[0].batch, "slice"):
+        import ctypes as C
+        from distributed_crawler_b200.engine import lib
+        call = lib().tgi_youtube_batch if is_yt else lib().tgi_telegram_batch
+        page_calls = {"what": "blocking C-ABI call, host buffers in, host result out, mean of 100 calls after 5 warm-up calls; "
+                              "same run flags as the step; one cooperative launch per call (csrc/tg_page.cuh, yt_page.cuh)"}
+        for pn in ((50, 500) if is_yt else (100, 1000)):
+            pb = corpora[0].batch.slice(0, pn)
+            d = pb.descriptor()
+            r = abi.ResultC()
+            for i in range(105):
+                if i == 5:
+                    t0 = time.perf_counter()
+                if call(eng.h, C.byref(d), RUN, C.byref(r)) != 0:
+                    raise SystemExit("page call failed: " + lib().tgi_last_error(eng.h).decode())
+                lib().tgi_result_release(eng.h, r.slot)
+            page_calls[str(pn)] = {"ms_per_call": (time.perf_counter() - t0) / 100 * 1e3, "gpu_launches_per_call": int(r.gpu_launches),
+                                   "result_bytes": int(r.jsonl_len)}
+
     if rank == 0:
         peak, peak_src = load_peaks()
         step_ms = dt_max / args.steps * 1e3
@@ -537,6 +558,7 @@ def main():
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": acc.launches,
+            "page_calls": page_calls,
             "roofline": roofline,
             "cpu_baseline": cpu,
         }

@@ -329,6 +329,28 @@ class YtBatch:
     def input_bytes(self) -> int:
         return sum(getattr(self, k).nbytes for k in self.FIELDS)
 
+    def slice(self, a: int, b: int) -> "YtBatch":
+        """records [a,b) as a self-contained batch (string offsets rebased, only the referenced channel rows kept): what a
+        caller packing one page of the Data API on its own would have produced."""
+        recs = self.recs[a:b].copy()
+        s0 = int(self.recs["str_off"][a]) if a < self.n else self.strs.size
+        s1 = int(self.recs["str_off"][b]) if b < self.n else self.strs.size
+        recs["str_off"] -= s0
+        if len(recs):
+            cmin, cmax = int(recs["chan_idx"].min()), int(recs["chan_idx"].max())
+        else:
+            cmin, cmax = 0, -1
+        chans = self.chans[cmin:cmax + 1].copy()
+        recs["chan_idx"] -= cmin
+        if len(chans):
+            clo = int(chans["str_off"].min())
+            ln = sum(chans[k].astype(np.int64) for k in ("id_len", "title_len", "desc_len", "thumb_len", "country_len"))
+            chi = int((chans["str_off"] + ln).max())
+            chans["str_off"] -= clo
+        else:
+            clo = chi = 0
+        return YtBatch(recs=recs, strs=_pad(self.strs[s0:s1]), chans=chans, chan_strs=_pad(self.chan_strs[clo:chi]))
+
 
 def pack_youtube(videos: list[YouTubeVideo], channels: list[YouTubeChannel] | None = None) -> YtBatch:
     channels = channels or [YouTubeChannel()]

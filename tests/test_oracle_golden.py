@@ -187,6 +187,20 @@ def test_corpus_deterministic_and_shardable():
     assert np.array_equal(r1.jsonl, r2.jsonl) and np.array_equal(r1.links, r2.links)
 
 
+def test_youtube_slice_is_a_self_contained_page():
+    """YtBatch.slice (bench.py's page-sized calls, tests/test_gpu_page.py): the lines / links of records [a,b) of the whole."""
+    from distributed_crawler_b200.corpus import YtCorpus
+    from yt_corpus import make_youtube
+    F = abi.RUN_JSONL | abi.RUN_LINKS
+    for b in (YtCorpus(3000, seed=7, nthreads=2).batch, make_youtube(1500, seed=5)[0]):
+        full = pyoracle.Oracle().youtube(b, F)
+        for a, e in ((0, 50), (1000, 1050), (b.n - 50, b.n), (17, 18)):
+            part = pyoracle.Oracle().youtube(b.slice(a, e), F)
+            assert np.array_equal(part.jsonl, full.jsonl[int(full.line_off[a]):int(full.line_off[e])])
+            assert np.array_equal(part.status, full.status[a:e])
+            assert np.array_equal(part.links, full.links[int(full.link_off[a]):int(full.link_off[e])])
+
+
 def test_oracle_threads_agree():
     c = Corpus(20000, nthreads=2)
     r1 = pyoracle.Oracle().telegram(c.batch, ALL, nthreads=1)
