@@ -7,6 +7,8 @@ the test sources, not outputs of a run:
   /root/reference/telegramhelper/channel_links_test.go      (extractChannelLinksFromMessage)
   /root/reference/telegramhelper/username_filter_test.go    (FilterUsername)
   /root/reference/crawl/runner_tandem_test.go               (tandem frontier fan-out)
+  /root/reference/crawl/validator_test.go                   (validateSingleEdge: the two cache look-ups)
+  /root/reference/chunk/main_test.go                        (processBatches: the combiner's batching rule)
 Nothing under /root/reference is read at test time.
 """
 import json
@@ -65,7 +67,33 @@ TANDEM = {  # crawl/runner_tandem_test.go:15-93 (WithEdges) and :161-214 (invali
         "entities": [(10, 14, "mention", ""), (29, 13, "mention", "")],
         "expected_edges": ["valid_channel", "another_chan"],  # 2 InsertPendingEdge, 1 batch
     },
+    "no_edges": {  # TestTandemMode_NoEdges: nothing to insert, no batch created
+        "go_line": 97, "owner_url": "source_channel",
+        "text": "Just a regular message with no channels", "entities": [], "expected_edges": [],
+    },
+    "invalid_channel_skipped": {  # TestTandemMode_InvalidChannelSkipped: IsInvalidChannel("invalid_chan") == true
+        "go_line": 161, "owner_url": "source_channel",
+        "text": "Check @invalid_chan", "entities": [(6, 13, "mention", "")],
+        "invalid": ["invalid_chan"], "expected_edges": [],  # InsertPendingEdge / CreatePendingBatch never called
+    },
 }
+
+VALIDATOR = [  # crawl/validator_test.go: what validateSingleEdge answers from the two caches, before any request
+    # (test name, go line, destination_channel, in invalid cache, in discovered cache, status, reason)
+    ("Valid", 28, "testchan", False, False, "pending", ""),              # goes on to the HTTP validation
+    ("AlreadyInvalid", 145, "badchan", True, False, "invalid", "cached_invalid"),  # IsChannelDiscovered is not consulted
+    ("AlreadyDiscovered", 167, "known_chan", False, True, "duplicate", ""),
+]
+
+CHUNK = [  # chunk/main_test.go TestProcessBatches_*: (test name, go line, trigger, hard cap, file sizes, expectation)
+    ("FlushOnTrigger", 313, 100, 1000, [40, 40, 40], {"batches": [[0, 1, 2]]}),
+    ("FlushOnTrigger_ExactSplit", 335, 60, 1000, [50, 50, 50], {"min_batches": 2}),
+    ("HardCapDropsOversizedFile", 356, 1000, 100, [200, 50], {"files_in_batches": 1, "dropped": [0]}),
+    ("HardCapForceFlush", 392, 10000, 100, [60, 60], {"min_batches": 2, "first_batches": [[0], [1]]}),
+    ("FinalPartialBatchFlushed", 415, 10000, 100000, [10, 10], {"batches": [[0, 1]]}),
+    ("EmptyChannelProducesNoBatches", 434, 100, 1000, [], {"batches": []}),
+    ("TotalUploadSizeTracked", 448, 1, 1000000, [50, 75], {"total_size": 125, "files_in_batches": 2}),
+]
 
 
 def main():
@@ -77,11 +105,16 @@ def main():
         "filter_username": [dict(name=n, go_file="telegramhelper/username_filter_test.go", username=u, valid=v, reason=r)
                             for n, u, v, r in FILTER],
         "tandem": TANDEM,
+        "validator_cache": [dict(name=n, go_file="crawl/validator_test.go", go_line=ln, destination=d, invalid=i, discovered=k,
+                                 status=st, reason=r) for n, ln, d, i, k, st, r in VALIDATOR],
+        "chunk_batches": [dict(name=n, go_file="chunk/main_test.go", go_line=ln, trigger=t, hard_cap=h, sizes=sz, expect=ex)
+                          for n, ln, t, h, sz, ex in CHUNK],
     }
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors.json")
     with open(path, "w", encoding="utf-8") as f:
         json.dump(out, f, ensure_ascii=False, indent=1)
-    print("wrote", path, len(LINKS), "link vectors,", len(FILTER), "filter vectors")
+    print("wrote", path, len(LINKS), "link vectors,", len(FILTER), "filter vectors,", len(TANDEM), "tandem,", len(VALIDATOR),
+          "validator-cache,", len(CHUNK), "chunk-batching vectors")
 
 
 if __name__ == "__main__":

@@ -105,3 +105,87 @@ def test_gpu_pending_edges_match_oracle():
         assert np.array_equal(rows_o, rows_g) and len(rows_g) == rg.n_new
         e.release(1)
     e.close()
+
+
+STATUS = {"pending": abi.EDGE_PENDING, "duplicate": abi.EDGE_DUPLICATE, "invalid": abi.EDGE_INVALID_CACHED}
+
+
+def _tandem_case(x, t):
+    """one reference tandem vector through x (Oracle or Engine): names of the edges that would be inserted"""
+    from distributed_crawler_b200.pack import Channel, pack_telegram
+    from helpers import msg
+    if t.get("invalid"):
+        x.set_add(abi.SET_INVALID, names_to_keys32([n.encode() for n in t["invalid"]]), np.zeros(len(t["invalid"]), np.int64))
+    x.set_now(NOW)
+    b = pack_telegram([msg("messageText", t["text"], [tuple(e) for e in t["entities"]])],
+                      [Channel(name=t["owner_url"], username=t["owner_url"])])
+    return b
+
+
+def test_reference_tandem_vectors_oracle(vectors):
+    """crawl/runner_tandem_test.go: WithEdges (two rows), NoEdges (none), InvalidChannelSkipped (IsInvalidChannel -> no
+    InsertPendingEdge) — the rows tgi_pending_edges would hand to the one INSERT."""
+    for name, t in vectors["tandem"].items():
+        o = Oracle()
+        b = _tandem_case(o, t)
+        r = o.telegram(b, TANDEM)
+        rows = o.pending_edges(NOW)
+        got = [bytes(e["destination"][: e["dest_len"]]).decode() for e in rows]
+        assert got == t["expected_edges"], f'{name} (crawl/runner_tandem_test.go:{t["go_line"]})'
+        assert r.n_new == len(t["expected_edges"])
+        for inv in t.get("invalid", []):
+            hit = [l for l in r.links if bytes(l["name"][: l["len"]]).decode() == inv]
+            assert hit and all(l["flags"] & abi.LF_INVALID for l in hit)
+
+
+def _validator_case(x, v):
+    from distributed_crawler_b200.pack import Channel, pack_telegram
+    from helpers import msg
+    d = v["destination"]
+    b = pack_telegram([msg("messageText", "see t.me/" + d)], [Channel(name="source_channel", username="source_channel")])
+    plain = abi.RUN_LINKS | abi.RUN_FRONTIER | abi.RUN_FILTER | abi.RUN_SKIP_SELF  # the edge was inserted BEFORE the caches knew
+    return b, plain, d
+
+
+def test_reference_validator_cache_vectors_oracle(vectors):
+    """crawl/validator_test.go TestValidateSingleEdge_{Valid,AlreadyInvalid,AlreadyDiscovered}: what the two cache
+    look-ups of validateSingleEdge (validator.go:205-226) answer, as the status column of the packed rows."""
+    for v in vectors["validator_cache"]:
+        o = Oracle()
+        b, flags, d = _validator_case(o, v)
+        o.telegram(b, flags)
+        if v["invalid"]:
+            o.set_add(abi.SET_INVALID, names_to_keys32([d.encode()]), np.zeros(1, np.int64))
+        if v["discovered"]:
+            o.set_add(abi.SET_DISCOVERED, names_to_keys32([d.encode()]))
+        rows = o.pending_edges(NOW)
+        assert len(rows) == 1 and bytes(rows[0]["destination"][: rows[0]["dest_len"]]).decode() == d
+        assert rows[0]["status"] == STATUS[v["status"]], f'{v["name"]} ({v["go_file"]}:{v["go_line"]})'
+
+
+@pytest.mark.gpu
+def test_reference_tandem_and_validator_vectors_gpu(vectors):
+    from distributed_crawler_b200.engine import Engine
+    for name, t in vectors["tandem"].items():
+        e = Engine()
+        b = _tandem_case(e, t)
+        e.telegram_submit(0, b, TANDEM)
+        r = e.telegram_wait(0, copy=True)
+        rows = e.pending_edges(0, NOW)
+        assert [bytes(x["destination"][: x["dest_len"]]).decode() for x in rows] == t["expected_edges"], name
+        assert r.n_new == len(t["expected_edges"])
+        e.release(0)
+        e.close()
+    for v in vectors["validator_cache"]:
+        e = Engine()
+        b, flags, d = _validator_case(e, v)
+        e.telegram_submit(0, b, flags)
+        e.telegram_wait(0)
+        if v["invalid"]:
+            e.set_add(abi.SET_INVALID, names_to_keys32([d.encode()]), np.zeros(1, np.int64))
+        if v["discovered"]:
+            e.set_add(abi.SET_DISCOVERED, names_to_keys32([d.encode()]))
+        rows = e.pending_edges(0, NOW)
+        assert len(rows) == 1 and rows[0]["status"] == STATUS[v["status"]], v["name"]
+        e.release(0)
+        e.close()

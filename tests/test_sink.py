@@ -90,3 +90,27 @@ def test_channel_appends_equal_per_post_appends(engine_lib, tmp_path):
     assert appends == len(runs) < sum(1 for l in lines if l) / 3
     assert int(runs["n_lines"].sum()) == sum(1 for l in lines if l)
     assert sink.plan_channel_appends(np.zeros(1, np.uint64), recs[:0]).size == 0
+
+
+def test_reference_process_batches_vectors(engine_lib, vectors):
+    """The reference's own known-answer tests of the batching rule (chunk/main_test.go TestProcessBatches_*), through
+    tgi_plan_chunks and through the restatement above."""
+    for v in vectors["chunk_batches"]:
+        sizes, where = v["sizes"], f'{v["name"]} ({v["go_file"]}:{v["go_line"]})'
+        line_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+        groups, dropped = sink.plan_chunks(line_off, v["trigger"], v["hard_cap"])
+        got = [[i for i in range(a, b) if not dropped[i]] for a, b in groups]
+        assert got == process_batches(sizes, v["trigger"], v["hard_cap"]), where
+        ex = v["expect"]
+        if "batches" in ex:
+            assert got == ex["batches"], where
+        if "min_batches" in ex:
+            assert len(got) >= ex["min_batches"], where
+        if "first_batches" in ex:
+            assert got[: len(ex["first_batches"])] == ex["first_batches"], where
+        if "files_in_batches" in ex:
+            assert sum(len(b) for b in got) == ex["files_in_batches"], where
+        if "dropped" in ex:
+            assert [i for i in range(len(sizes)) if dropped[i]] == ex["dropped"], where
+        if "total_size" in ex:  # Chunker.totalUploadSize after the run
+            assert sum(sizes[i] for b in got for i in b) == ex["total_size"], where
