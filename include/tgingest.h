@@ -389,7 +389,9 @@ int tgi_telegram_batch(tgi_ctx* ctx, const tgi_tg_batch* in, uint32_t run_flags,
 
 /* YouTube: replaces the worker body crawler/youtube/youtube_crawler.go:380-418 ->
  * convertVideoToPost (:530-836) + json.Marshal+'\n'; links = extractChannelIDsFromText
- * (client/youtube_client.go:1856-1878) for the snowball frontier (:1706-1721).                   */
+ * (client/youtube_client.go:1856-1878) for the snowball frontier (:1706-1721).  A link row holds the
+ * first 32 bytes of an id (tgi_link.name): real channel ids are 24 characters and handles at most 30,
+ * so only malformed ids are cut; the JSONL line itself is never shortened.                       */
 int tgi_youtube_submit(tgi_ctx* ctx, int slot, const tgi_yt_batch* in, uint32_t run_flags);
 int tgi_youtube_wait(tgi_ctx* ctx, int slot, tgi_result* out);
 int tgi_youtube_batch(tgi_ctx* ctx, const tgi_yt_batch* in, uint32_t run_flags, tgi_result* out);

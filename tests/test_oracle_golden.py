@@ -201,6 +201,82 @@ def test_youtube_slice_is_a_self_contained_page():
             assert np.array_equal(part.links, full.links[int(full.link_off[a]):int(full.link_off[e])])
 
 
+def _random_messages(rnd, n):
+    """messages over every content type and every awkward shape the Go code distinguishes"""
+    from distributed_crawler_b200.pack import TextEntity, FormattedText, Message
+    pieces = [b"hello ", b"t.me/", b"https://t.me/", b"@", b"chan_name1 ", b"SomeChannel ", b"joinchat/x ", b"abcd ", b"\n", b"\t",
+              b'"q"', b"\\", b"<b>&", "привет ".encode(), "😀".encode(), "مرحبا ".encode(), b"\xe2\x80\xa8", b"\xe2\x80\xa9",
+              b"\xff", b"\xc0\xaf", b"\xed\xa0\x80", b"\xf0\x9f", b"\x01", b"\x7f", b"x" * 40, b"some_bot ", b"a_b_c_d_e "]
+    emojis = ["👍", "❤", "🔥", "a", "zz", b"\xff", '"', "k<"]
+
+    def text(maxp):
+        return b"".join(rnd.choice(pieces) for _ in range(rnd.randrange(0, maxp)))
+
+    def reacts():
+        return [(rnd.choice(emojis), rnd.randrange(-3, 10 ** rnd.randrange(1, 10))) for _ in range(rnd.randrange(0, 6))]
+
+    types = abi.CT_NAMES[:-1] + ["messageLocation", "messageContact"]
+    out = []
+    for _ in range(n):
+        ct = rnd.choice(types)
+        t = None if rnd.random() < 0.15 else text(12)
+        ents = []
+        if t is not None:
+            for _ in range(rnd.randrange(0, 4)):
+                ents.append(TextEntity(rnd.randrange(-2, 40), rnd.randrange(-2, 30), rnd.choice(["mention", "url", "text_url", "bold"]),
+                                       rnd.choice([b"https://t.me/linked_chan", b"http://example.com", b"t.me/x", b""])))
+        comments = rnd.choice([None, [], [Comment(text(4), rnd.choice([None, [], reacts()]), rnd.randrange(0, 99), rnd.randrange(0, 9),
+                                                  rnd.choice(["bob", b"\xfe", "unknown", ""])) for _ in range(rnd.randrange(1, 4))]])
+        out.append(Message(content_type=ct, text=None if t is None else FormattedText(t, ents), alt=text(3), media=rnd.choice([b"", b"REMOTE-id_1", text(2)]),
+                           id=rnd.choice([1 << 20, 77 << 20, (5 << 20) + 123, -(3 << 20) - 7, rnd.randrange(0, 1 << 50)]),
+                           chat_id=rnd.choice([-1001234567890, 5, -7]), date=rnd.choice([0, 1_600_000_000, 1_700_000_000, 1_800_000_000, 2 ** 31 - 1]),
+                           media_album_id=rnd.choice([0, 0, 9]), view_count=rnd.randrange(0, 10 ** rnd.randrange(1, 10)),
+                           share_count=rnd.randrange(0, 1000), reactions=reacts(), comments=comments, handle=rnd.choice(["Chan", "", b"\xe9", 'h"x']),
+                           channel=rnd.randrange(0, 3), panics=rnd.random() < 0.03, video_shape=rnd.choice(["ok", "ok", "none", "broken"])))
+    return out
+
+
+def test_whole_post_line_vs_independent_restatement():
+    """Every byte of the Telegram Post line against tests/go_rules.py:telegram_post_line — a second restatement of
+    ParseMessage + json.Marshal written from the Go sources over the host-side message model, not from the oracle."""
+    import random
+    chans = [Channel("T<itle> \u2028", "nm", "usr", 10, 20, 30), Channel(b"\xff\"t", "name_2", "", 0, 0, 0), Channel("", "", "u3", 2 ** 31 - 1, 7, 2 ** 40)]
+    for trial, cfg in enumerate([dict(), dict(tz_offset_sec=19800, crawl_label=b'lab"<el>\xff', capture_nsec=0, created_at_sec=1_760_000_000),
+                                 dict(tz_offset_sec=-12600, min_post_date=1_650_000_000, created_at_nsec=999, capture_nsec=120_000_000)]):
+        rnd = random.Random(100 + trial)
+        ms = _random_messages(rnd, 800)
+        r = pyoracle.Oracle(**cfg).telegram(pack_telegram(ms, chans), abi.RUN_JSONL | abi.RUN_LINKS)
+        kw = dict(crawl_label=cfg.get("crawl_label", b""), created=(cfg.get("created_at_sec", 1_750_000_000), cfg.get("created_at_nsec", 0)),
+                  capture=(1_750_000_000, cfg.get("capture_nsec", 123_456_789)), tz=cfg.get("tz_offset_sec", 0),
+                  min_post_date=cfg.get("min_post_date"))
+        want_status = {"emitted": abi.ST_EMITTED, "skipped": abi.ST_SKIPPED, "failed": abi.ST_FAILED}
+        for i, m in enumerate(ms):
+            st, line, links = go_rules.telegram_post_line(m, chans[m.channel], **kw)
+            assert r.status[i] == want_status[st], (trial, i, st, m)
+            assert r.line(i) == (line or b""), (trial, i, m)
+            assert [n for n, _ in r.record_links(i)] == [go_rules._bs(x) for x in links], (trial, i)
+
+
+def test_whole_youtube_line_vs_independent_restatement():
+    """Every byte of the YouTube Post line (and the snowball ids) against tests/go_rules.py:youtube_post_line — a second
+    restatement of convertVideoToPost + json.Marshal written from the Go sources, not from the oracle."""
+    from yt_corpus import make_youtube, make_youtube_config4
+    for mk, n, seed, cfg in ((make_youtube, 1200, 3, dict()), (make_youtube_config4, 500, 5, dict()),
+                             (make_youtube, 600, 9, dict(tz_offset_sec=19800, crawl_label=b'yt"<lbl>', created_at_nsec=987_000_000, capture_nsec=0))):
+        b, vids, chans = mk(n, seed=seed)
+        r = pyoracle.Oracle(**cfg).youtube(b, abi.RUN_JSONL | abi.RUN_LINKS)
+        kw = dict(crawl_label=cfg.get("crawl_label", b""), created=(1_750_000_000, cfg.get("created_at_nsec", 0)),
+                  capture=(1_750_000_000, cfg.get("capture_nsec", 123_456_789)), tz=cfg.get("tz_offset_sec", 0))
+        nolines = 0
+        for i, v in enumerate(vids):
+            line, _, ids = go_rules.youtube_post_line(v, chans[v.channel], **kw)
+            assert r.line(i) == (line or b""), (mk.__name__, i)
+            assert r.status[i] == (abi.ST_EMITTED if line else abi.ST_NOLINE)
+            assert [x for x, _ in r.record_links(i)] == [x[:32] for x in ids], (mk.__name__, i)  # link rows keep 32 bytes of an id
+            nolines += line is None
+        assert nolines > 0 or mk is make_youtube_config4  # the adversarial corpus holds unrepresentable dates
+
+
 def test_oracle_threads_agree():
     c = Corpus(20000, nthreads=2)
     r1 = pyoracle.Oracle().telegram(c.batch, ALL, nthreads=1)
