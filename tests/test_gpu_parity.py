@@ -307,3 +307,16 @@ def test_malformed_batches_are_rejected(engine):
             engine.telegram(b, ALL)
     ok = Corpus(1000, profile=2)
     assert engine.telegram(ok.batch, ALL).n == 1000  # still alive
+
+
+def test_random_messages_of_every_shape():
+    """The random messages of tests/test_oracle_golden.py (every content type, nil / empty / filled lists and maps, invalid
+    UTF-8, negative ids ...; there the oracle is compared with the independent restatement of tests/go_rules.py) through
+    the CUDA path: page kernel and bulk pipeline."""
+    from test_oracle_golden import _random_messages
+    chans = [Channel("T<itle>  ", "nm", "usr", 10, 20, 30), Channel(b"\xff\"t", "name_2", "", 0, 0, 0), Channel("", "", "u3", 2 ** 31 - 1, 7, 2 ** 40)]
+    for trial, cfg in enumerate([dict(), dict(tz_offset_sec=19800, crawl_label=b'lab"<el>\xff', capture_nsec=0, created_at_sec=1_760_000_000),
+                                 dict(tz_offset_sec=-12600, min_post_date=1_650_000_000, created_at_nsec=999, capture_nsec=120_000_000)]):
+        ms = _random_messages(random.Random(100 + trial), 800)
+        both(pack_telegram(ms, chans), ALL, **cfg)
+        both(pack_telegram(ms, chans), TANDEM, **cfg)
